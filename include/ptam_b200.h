@@ -1,0 +1,252 @@
+/*
+ * ptam_b200.h — C-ABI of the B200-native PTAM hot paths (libptam_b200.so).
+ *
+ * The reference (cggos/ptam_cg) has no FFI/plugin layer: its boundary is ordinary C++ class methods
+ * on TooN/CVD value types.  This header is the thin C-ABI those classes are re-hosted on
+ * (the headers in ptam_cg_b200/host/ mirror Tracker / KeyFrame / PatchFinder / Bundle on top of it).
+ * Plain pointers and sizes only; all host pointers are caller-owned and only touched during the
+ * call; all device memory is owned by the handle.  Every function returns 0 (PTAM_OK) or a
+ * negative error code unless stated; ptam_*_last_error() gives the text.  Algorithmic outcomes
+ * (patch not found, bad template, BA not converged) are data, not errors.  A handle may be used by
+ * one thread at a time; tracker and bundle handles own separate CUDA streams and may run
+ * concurrently (the reference runs Tracker and MapMaker on two threads, MapMaker.h:37-38).
+ *
+ * There is NO CPU fallback: creating a handle without a usable sm_100 device fails.
+ *
+ * SE3 layout everywhere: 12 doubles = rotation matrix row-major (9) then translation (3),
+ * "camera from world" as in KeyFrame::se3CfromW (KeyFrame.h:136).
+ */
+#ifndef PTAM_B200_H
+#define PTAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTAM_LEVELS 4 /* KeyFrame.h:34 */
+
+enum {
+  PTAM_OK = 0,
+  PTAM_ERR_INVALID = -1,  /* bad argument */
+  PTAM_ERR_CUDA = -2,     /* CUDA runtime error (sticky per handle) */
+  PTAM_ERR_NO_DEVICE = -3,
+  PTAM_ERR_CAPACITY = -4,
+  PTAM_ERR_NCCL = -5
+};
+
+/* per-point result flags (TrackerData booleans, Tracker.h:54-61) */
+enum {
+  PTAM_PT_IN_IMAGE = 1,   /* bInImage after the last Project */
+  PTAM_PT_IN_PVS = 2,     /* entered the potentially-visible set this frame */
+  PTAM_PT_SEARCHED = 4,   /* bSearched */
+  PTAM_PT_FOUND = 8,      /* bFound */
+  PTAM_PT_SUBPIX = 16,    /* bDidSubPix */
+  PTAM_PT_TEMPLATE_BAD = 32
+};
+
+/* ------------------------------------------------------------------------------------------
+ * Path T — per-frame tracker.
+ * Replaces: Tracker::TrackFrame (Tracker.cc:86-188, the MakeKeyFrame_Lite / PredictPose /
+ * TrackMap / UpdateMotionModel / AssessTrackingQuality part), KeyFrame::MakeKeyFrame_Lite
+ * (KeyFrame.cc:18-54), PatchFinder steps 1-5 as driven by Tracker::SearchForPoints
+ * (Tracker.cc:867-912, PatchFinder.cc:52-318), Tracker::CalcPoseUpdate (Tracker.cc:928-1005).
+ * ------------------------------------------------------------------------------------------ */
+
+/* GVars3 keys the tracker reads, with the reference defaults (Tracker.cc:491-496,596,931,1088-1089;
+ * Tracker.cc:95-96). */
+typedef struct ptam_tracker_params {
+  int32_t coarse_min;            /* Tracker.CoarseMin            = 20  */
+  int32_t coarse_max;            /* Tracker.CoarseMax            = 60  */
+  int32_t coarse_range;          /* Tracker.CoarseRange          = 30  */
+  int32_t coarse_subpix_its;     /* Tracker.CoarseSubPixIts      = 8   */
+  int32_t disable_coarse;        /* Tracker.DisableCoarse        = 0   */
+  int32_t max_patches_per_frame; /* Tracker.MaxPatchesPerFrame   = 1000 */
+  int32_t mestimator;            /* Tracker.MEstimator: 0 Tukey (default), 1 Cauchy, 2 Huber */
+  int32_t use_constant_velocity; /* Tracker.UseConstantVelocity  = 1   */
+  double coarse_min_velocity;    /* Tracker.CoarseMinVelocity    = 0.006 */
+  double quality_good;           /* Tracker.TrackingQualityGood  = 0.3  */
+  double quality_lost;           /* Tracker.TrackingQualityLost  = 0.13 */
+} ptam_tracker_params;
+
+/* Tracker member state carried from frame to frame (Tracker.h:176-215). */
+typedef struct ptam_tracker_state {
+  double se3_cam_from_world[12];        /* mse3CamFromWorld */
+  double velocity[6];                   /* mv6CameraVelocity */
+  double msd_scaled_velocity_magnitude; /* mdMSDScaledVelocityMagnitude */
+  double scene_depth_mean;              /* mCurrentKF.dSceneDepthMean */
+  double scene_depth_sigma;             /* mCurrentKF.dSceneDepthSigma */
+  int32_t just_recovered_so_use_coarse; /* mbJustRecoveredSoUseCoarse */
+  int32_t tracking_quality;             /* 0 BAD, 1 DODGY, 2 GOOD (Tracker.h:203) */
+  int32_t lost_frames;                  /* mnLostFrames */
+  int32_t frame;                        /* mnFrame */
+} ptam_tracker_state;
+
+/* What one TrackFrame leaves behind, per stream. */
+typedef struct ptam_track_result {
+  double se3_cam_from_world[12]; /* pose after TrackMap (mCurrentKF.se3CfromW, Tracker.cc:662) */
+  double scene_depth_mean;       /* Tracker.cc:680-697 (unchanged when <= 20 points found) */
+  double scene_depth_sigma;
+  int32_t meas_attempted[PTAM_LEVELS]; /* manMeasAttempted */
+  int32_t meas_found[PTAM_LEVELS];     /* manMeasFound */
+  int32_t n_corners[PTAM_LEVELS];      /* FAST corners per pyramid level of the current frame */
+  int32_t did_coarse;                  /* mbDidCoarse */
+  int32_t n_coarse;                    /* size of the coarse-stage search set */
+  int32_t n_level3;                    /* level-3 points searched in the fine stage */
+  int32_t n_fine;                      /* level 2..0 points searched in the fine stage */
+  int32_t tracking_quality;            /* after AssessTrackingQuality */
+  int32_t quality_needs_kf_distance;   /* 1: reference would consult MapMaker::ClosestKeyFrame
+                                          (Tracker.cc:1095-1099); left to the caller */
+  int32_t n_pvs[PTAM_LEVELS];          /* PVS size per level before selection */
+  int32_t reserved;
+} ptam_track_result;
+
+typedef struct ptam_tracker ptam_tracker;
+
+void ptam_tracker_default_params(ptam_tracker_params* p);
+
+/* n_streams independent trackers (own pose, map, per-point template cache) that share one camera
+ * model, image size and keyframe store and are processed as one batch per call.  n_streams = 1 is
+ * the reference's single Tracker.  Returns NULL on failure (see ptam_global_last_error). */
+ptam_tracker* ptam_tracker_create(int device, const double cam_params[5], int width, int height,
+                                  int n_streams, const ptam_tracker_params* params);
+void ptam_tracker_destroy(ptam_tracker* t);
+const char* ptam_tracker_last_error(const ptam_tracker* t);
+const char* ptam_global_last_error(void);
+
+/* Store a source keyframe (pyramid only) so map points can take their templates from it
+ * (MapPoint::pPatchSourceKF, Map.h:67).  Returns the keyframe id (>= 0) or an error. */
+int ptam_tracker_add_keyframe(ptam_tracker* t, const uint8_t* image, int stride);
+
+/* Replace stream `stream`'s map.  SoA of MapPoint fields the tracker reads (Map.h:64-84):
+ * world_pos / pixel_right_w / pixel_down_w: n*3 doubles; src_kf: id from add_keyframe;
+ * src_level: nSourceLevel; ir_center: n*2 ints (x,y) in source-level pixels.  Clears the per-point
+ * template cache and the M-estimator inlier/outlier counters. */
+int ptam_tracker_set_map(ptam_tracker* t, int stream, int n_points, const double* world_pos,
+                         const double* pixel_right_w, const double* pixel_down_w,
+                         const int32_t* src_kf, const int32_t* src_level, const int32_t* ir_center);
+
+int ptam_tracker_set_state(ptam_tracker* t, int stream, const ptam_tracker_state* s);
+int ptam_tracker_get_state(ptam_tracker* t, int stream, ptam_tracker_state* s);
+
+/* KeyFrame::MakeKeyFrame_Lite only, for every stream: images[s] is stream s's W x H u8 frame. */
+int ptam_tracker_make_keyframes(ptam_tracker* t, const uint8_t* const* images, int stride);
+
+/* One TrackFrame per stream: MakeKeyFrame_Lite + PredictPoseWithMotionModel (velocity only; the
+ * SmallBlurryImage rotation estimator is a "next" row) + TrackMap + UpdateMotionModel +
+ * AssessTrackingQuality.  std::random_shuffle (Tracker.cc:483,601) is the identity permutation.
+ * images: n_streams host pointers; results: n_streams structs (may be NULL). */
+int ptam_tracker_track_frames(ptam_tracker* t, const uint8_t* const* images, int stride,
+                              ptam_track_result* results);
+
+/* Same, with the frames already resident in device memory: frame s starts at
+ * d_images + s * frame_pitch_bytes, rows `stride` bytes apart.  results may be NULL (no D2H, no
+ * host synchronisation: the call only enqueues work on the handle's stream). */
+int ptam_tracker_track_frames_device(ptam_tracker* t, const uint8_t* d_images,
+                                     size_t frame_pitch_bytes, int stride,
+                                     ptam_track_result* results);
+int ptam_tracker_synchronize(ptam_tracker* t);
+/* cudaStream_t of the handle, as an opaque pointer (for CUDA-event timing by the caller). */
+void* ptam_tracker_cuda_stream(ptam_tracker* t);
+/* Number of kernel launches issued by the handle so far. */
+int64_t ptam_tracker_launch_count(const ptam_tracker* t);
+
+/* Read back the current frame's keyframe level of one stream (Level, KeyFrame.h:55-125):
+ * pixels (w*h, may be NULL), corners as interleaved (x,y) int32 in raster order (cap pairs, may be
+ * NULL), row_lut (h ints, may be NULL).  Returns the number of corners on that level. */
+int ptam_tracker_get_level(ptam_tracker* t, int stream, int level, uint8_t* pixels,
+                           int32_t* corners_xy, int corners_cap, int32_t* row_lut);
+int ptam_tracker_level_size(const ptam_tracker* t, int level, int* w, int* h);
+
+/* Per-point results of the last frame of one stream (any pointer may be NULL):
+ * flags: PTAM_PT_* bits; level: nSearchLevel (-1 if not in the PVS); v2_found / v2_image: n*2. */
+int ptam_tracker_get_points(ptam_tracker* t, int stream, int32_t* flags, int32_t* level,
+                            double* v2_found, double* v2_image, int32_t* outlier_count,
+                            int32_t* inlier_count);
+/* Cached coarse templates of one stream: tmpl n*64 bytes, sums n*2 ints (sum, sum of squares). */
+int ptam_tracker_get_templates(ptam_tracker* t, int stream, uint8_t* tmpl, int32_t* sums);
+/* vIterationSet of the last frame in order (coarse set, level-3 set, fine set); returns its size. */
+int ptam_tracker_get_iteration_set(ptam_tracker* t, int stream, int32_t* idx, int cap);
+
+/* ------------------------------------------------------------------------------------------
+ * Path B — bundle adjuster.  Replaces class Bundle (Bundle.h:105-156), whose only caller is
+ * MapMaker::BundleAdjust (MapMaker.cc:838-933).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ptam_bundle_params {
+  int32_t max_iterations;              /* Bundle.MaxIterations = 20 (Bundle.cc:40) */
+  int32_t mestimator;                  /* Bundle.MEstimator: 0 Tukey (default), 1 Cauchy, 2 Huber */
+  double update_squared_convergence;   /* Bundle.UpdateSquaredConvergenceLimit = 1e-6 (Bundle.cc:41) */
+  double min_tukey_sigma;              /* Bundle.MinTukeySigma = 0.4 (Bundle.cc:234) */
+} ptam_bundle_params;
+
+typedef struct ptam_bundle_stats {
+  int32_t accepted;        /* mnAccepted */
+  int32_t lambda_trials;   /* mnCounter */
+  int32_t lm_steps;        /* calls of Do_LM_Step */
+  int32_t converged;       /* mbConverged */
+  int32_t hit_max_iterations;
+  int32_t n_outliers;      /* measurements erased so far */
+  double sigma_squared;    /* mdSigmaSquared of the last step */
+  double lambda;           /* mdLambda */
+  double last_error;       /* dCurrentError of the last step */
+  double last_new_error;   /* dNewError of the last lambda trial */
+} ptam_bundle_stats;
+
+typedef struct ptam_bundle ptam_bundle;
+
+void ptam_bundle_default_params(ptam_bundle_params* p);
+/* Bundle::Bundle(const ATANCamera&) — Bundle.cc:35-43.  width/height = ATANCamera image size. */
+ptam_bundle* ptam_bundle_create(int device, const double cam_params[5], int width, int height,
+                                const ptam_bundle_params* params);
+void ptam_bundle_destroy(ptam_bundle* b);
+const char* ptam_bundle_last_error(const ptam_bundle* b);
+
+/* Bundle::AddCamera (Bundle.cc:46-63) → camera id. */
+int ptam_bundle_add_camera(ptam_bundle* b, const double se3_cam_from_world[12], int fixed);
+/* Bundle::AddPoint (Bundle.cc:66-78) → point id; NaN positions are zeroed as in the reference. */
+int ptam_bundle_add_point(ptam_bundle* b, const double xyz[3]);
+/* Bundle::AddMeas (Bundle.cc:81-93). */
+int ptam_bundle_add_meas(ptam_bundle* b, int cam, int point, const double uv[2], double sigma_squared);
+/* Bulk ingest in the same insertion order as repeated Add* calls. */
+int ptam_bundle_add_cameras(ptam_bundle* b, int n, const double* se3, const int32_t* fixed);
+int ptam_bundle_add_points(ptam_bundle* b, int n, const double* xyz);
+int ptam_bundle_add_measurements(ptam_bundle* b, int n, const int32_t* cam, const int32_t* point,
+                                 const double* uv, const double* sigma_squared);
+
+/* Multi-GPU: this handle holds shard `rank` of `world` (points partitioned by the caller; cameras
+ * replicated).  nccl_comm is an ncclComm_t created by the caller (e.g. torch.distributed's) or NULL
+ * for world == 1.  The reduced camera system, the error sums and the sigma-squared order statistic
+ * are reduced across ranks inside ptam_bundle_compute. */
+int ptam_bundle_set_shard(ptam_bundle* b, int rank, int world, void* nccl_comm);
+
+/* Bundle::Compute (Bundle.cc:116-158): returns the number of accepted LM steps (>= 0) or a negative
+ * error.  abort_flag is polled between device phases like *pbAbortSignal (Bundle.cc:134,338);
+ * may be NULL. */
+int ptam_bundle_compute(ptam_bundle* b, const volatile unsigned char* abort_flag);
+/* One Do_LM_Step only (Bundle.cc:209-551), for step-wise parity tests.  Call
+ * ptam_bundle_begin() once before the first step (does what Compute does before its loop). */
+int ptam_bundle_begin(ptam_bundle* b);
+int ptam_bundle_lm_step(ptam_bundle* b, const volatile unsigned char* abort_flag);
+
+int ptam_bundle_converged(const ptam_bundle* b);
+int ptam_bundle_get_point(ptam_bundle* b, int n, double xyz[3]);
+int ptam_bundle_get_camera(ptam_bundle* b, int n, double se3[12]);
+int ptam_bundle_get_points(ptam_bundle* b, double* xyz /* n_points*3 */);
+int ptam_bundle_get_cameras(ptam_bundle* b, double* se3 /* n_cameras*12 */);
+/* Bundle::GetOutlierMeasurements: (point, camera) pairs in erase order; returns the total count
+ * (may exceed cap; only cap pairs are written). */
+int ptam_bundle_get_outliers(ptam_bundle* b, int32_t* point_cam_pairs, int cap);
+int ptam_bundle_get_stats(ptam_bundle* b, ptam_bundle_stats* s);
+/* Reduced camera system of the last lambda trial, for parity tests: S n*n row-major (both
+ * triangles), vE n; returns n = 6 * non-fixed cameras. */
+int ptam_bundle_get_reduced_system(ptam_bundle* b, double* S, double* vE, int cap_n);
+int ptam_bundle_synchronize(ptam_bundle* b);
+void* ptam_bundle_cuda_stream(ptam_bundle* b);
+int64_t ptam_bundle_launch_count(const ptam_bundle* b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTAM_B200_H */

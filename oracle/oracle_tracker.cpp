@@ -1,0 +1,761 @@
+// TEST INFRASTRUCTURE — CPU oracle for PTAM path T (per-frame tracker).  NOT part of the product.
+// PARITY UNPINNED (no upstream tests/golden vectors; libCVD/TooN semantics restated from their
+// published behaviour — see oracle_math.h and DESIGN.md).  Single-threaded, faithful loop order.
+//
+// Restates:  KeyFrame::MakeKeyFrame_Lite        src/KeyFrame.cc:18-54
+//            CVD::halfSample / fast_corner_detect_10 / transform / sample   (libCVD 20150407)
+//            PatchFinder (all five steps)        src/PatchFinder.cc:52-318
+//            ImageProcess::ZMSSDAtPoint          src/ImageProcess.cc:130-163
+//            TrackerData                         include/Tracker.h:41-146
+//            Tracker::TrackMap / SearchForPoints / CalcPoseUpdate / motion model / quality
+//                                                src/Tracker.cc:442-698,867-1107
+// The exported orc_tracker_* functions have the signatures of ptam_tracker_* in
+// include/ptam_b200.h so that tests drive oracle and product with the same code.
+#include "oracle_math.h"
+#include "../include/ptam_b200.h"
+#include <cstdio>
+#include <string>
+
+namespace orc {
+
+struct IRef { int x, y; };
+
+struct Level {
+  int w = 0, h = 0;
+  std::vector<uint8_t> im;
+  std::vector<IRef> corners;
+  std::vector<int> lut;
+  const uint8_t* row(int y) const { return im.data() + (size_t)y * w; }
+  bool in_image_with_border(int x, int y, int b) const { return x >= b && y >= b && x < w - b && y < h - b; }
+};
+
+struct KeyFrame { Level lev[PTAM_LEVELS]; };
+
+// CVD::halfSample (called KeyFrame.cc:27): truncating mean of each 2x2 block; out = in/2.
+static void half_sample(const Level& in, Level& out) {
+  out.w = in.w / 2; out.h = in.h / 2;
+  out.im.assign((size_t)out.w * out.h, 0);
+  for (int y = 0; y < out.h; y++) {
+    const uint8_t* t = in.row(2 * y);
+    const uint8_t* b = in.row(2 * y + 1);
+    uint8_t* o = out.im.data() + (size_t)y * out.w;
+    for (int x = 0; x < out.w; x++) o[x] = (uint8_t)((t[2 * x] + t[2 * x + 1] + b[2 * x] + b[2 * x + 1]) / 4);
+  }
+}
+
+// CVD::fast_corner_detect_10 by definition (called KeyFrame.cc:35-42): corner iff >= 10 contiguous
+// ring pixels are all > p+t or all < p-t; 3-pixel border; raster order.
+static inline bool has_run10(unsigned m) {
+  m |= m << 16;  // circular
+  unsigned a = m & (m >> 1);
+  a &= a >> 2;          // runs >= 4
+  a &= a >> 4;          // runs >= 8
+  a &= m >> 8;          // runs >= 9
+  a &= m >> 9;          // runs >= 10
+  return (a & 0xFFFFu) != 0;
+}
+static void fast10(const Level& L, std::vector<IRef>& corners, int t) {
+  static const int dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+  static const int dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+  corners.clear();
+  int off[16];
+  for (int k = 0; k < 16; k++) off[k] = dy[k] * L.w + dx[k];
+  for (int y = 3; y < L.h - 3; y++) {
+    const uint8_t* r = L.row(y);
+    for (int x = 3; x < L.w - 3; x++) {
+      const uint8_t* c = r + x;
+      const int cb = *c + t, c_b = *c - t;
+      // any 10-arc contains at least one of ring[0], ring[8]
+      const int p0 = c[off[0]], p8 = c[off[8]];
+      if (!(p0 > cb || p8 > cb || p0 < c_b || p8 < c_b)) continue;
+      unsigned mb = 0, md = 0;
+      for (int k = 0; k < 16; k++) {
+        const int v = c[off[k]];
+        mb |= (unsigned)(v > cb) << k;
+        md |= (unsigned)(v < c_b) << k;
+      }
+      if (has_run10(mb) || has_run10(md)) corners.push_back({x, y});
+    }
+  }
+}
+
+static void make_keyframe_lite(KeyFrame& kf, const uint8_t* im, int w, int h, int stride, bool detect = true) {
+  static const int thr[4] = {10, 15, 15, 10};
+  kf.lev[0].w = w; kf.lev[0].h = h;
+  kf.lev[0].im.resize((size_t)w * h);
+  for (int y = 0; y < h; y++) std::memcpy(kf.lev[0].im.data() + (size_t)y * w, im + (size_t)y * stride, w);
+  for (int i = 0; i < PTAM_LEVELS; i++) {
+    Level& lev = kf.lev[i];
+    if (i != 0) half_sample(kf.lev[i - 1], lev);
+    lev.corners.clear();
+    lev.lut.clear();
+    if (!detect) continue;
+    fast10(lev, lev.corners, thr[i]);
+    unsigned v = 0;
+    for (int y = 0; y < lev.h; y++) {
+      while (v < lev.corners.size() && y > lev.corners[v].y) v++;
+      lev.lut.push_back((int)v);
+    }
+  }
+}
+
+// ImageProcess::ZMSSDAtPoint, 8x8 (ImageProcess.cc:130-163).
+static int zmssd_at_point(const Level& L, IRef ir, const uint8_t* tmpl, int tsum, int tsumsq, int max_ssd) {
+  if (!L.in_image_with_border(ir.x, ir.y, 4)) return max_ssd + 1;
+  int isq = 0, isum = 0, cross = 0;
+  for (int r = 0; r < 8; r++) {
+    const uint8_t* ip = L.row(ir.y - 4 + r) + (ir.x - 4);
+    const uint8_t* tp = tmpl + 8 * r;
+    for (int c = 0; c < 8; c++) {
+      int n = ip[c];
+      isum += n; isq += n * n; cross += n * tp[c];
+    }
+  }
+  int SA = tsum, SB = isum;
+  return ((2 * SA * SB - SA * SA - SB * SB) / 64 + isq + tsumsq - 2 * cross);
+}
+
+struct MapPoint {
+  double world[3], right[3], down[3];
+  int src_kf, src_level;
+  IRef center;
+  int outliers = 0, inliers = 0;
+};
+
+// PatchFinder + TrackerData merged (one Finder per map point, Tracker.h:46-47).
+struct TData {
+  // PatchFinder state
+  uint8_t tmpl[64];
+  int tsum = 0, tsumsq = 0;
+  bool has_template = false;      // mpLastTemplateMapPoint == &p
+  double last_warp[4] = {9999.9, 0, 0, 9999.9};
+  bool template_bad = false;
+  double warp_inv[4];
+  int search_level = 0;
+  float jac[36][2];
+  double hinv[9];
+  double subpix[2], coarse[2], mean_diff;
+  // TrackerData
+  double v3cam[3], implane[2], v2image[2], derivs[4];
+  bool in_image = false, in_pvs = false, searched = false, found = false, did_subpix = false;
+  int n_search_level = -1;
+  double v2found[2] = {0, 0};
+  double sqrt_inv_noise = 1;
+  double err[2];
+  double J[12];  // 2x6 row-major
+};
+
+static inline double level_zero_pos(double p, int l) { return (p + 0.5) * (1 << l) - 0.5; }
+static inline double level_n_pos(double p, int l) { return (p + 0.5) / (1 << l) - 0.5; }
+
+struct Tracker {
+  Camera cam;
+  int W, H, S;
+  ptam_tracker_params prm;
+  std::vector<KeyFrame> store;
+  struct Stream {
+    std::vector<MapPoint> pts;
+    std::vector<TData> td;
+    KeyFrame cur;
+    ptam_tracker_state st;
+    SE3 pose, start;
+    int attempted[4], found[4];
+    bool did_coarse = false;
+    std::vector<int> iter_set;
+    ptam_track_result res;
+  };
+  std::vector<Stream> streams;
+  std::string err;
+
+  // TrackerData::Project (Tracker.h:70-86)
+  void project(TData& d, const MapPoint& p, const SE3& pose, Camera::Proj& q) {
+    d.in_image = false;
+    pose.apply(p.world, d.v3cam);
+    if (d.v3cam[2] < 0.001) return;
+    d.implane[0] = d.v3cam[0] / d.v3cam[2];
+    d.implane[1] = d.v3cam[1] / d.v3cam[2];
+    if (d.implane[0] * d.implane[0] + d.implane[1] * d.implane[1] > cam.largest_radius * cam.largest_radius) return;
+    q = cam.project(d.implane);
+    d.v2image[0] = q.im[0]; d.v2image[1] = q.im[1];
+    if (q.invalid) return;
+    if (d.v2image[0] < 0 || d.v2image[1] < 0 || d.v2image[0] > W || d.v2image[1] > H) return;
+    d.in_image = true;
+  }
+  // TrackerData::ProjectAndDerivs (Tracker.h:89-94).  NB: the reference calls
+  // Cam.GetProjectionDerivs() whenever bFound, even if Project bailed out early; the camera then
+  // still holds the state of its most recent Project() call.  `last` carries that state.
+  void project_and_derivs(TData& d, const MapPoint& p, const SE3& pose, Camera::Proj& last) {
+    project(d, p, pose, last);
+    if (d.found) cam.derivs(last, d.derivs);
+  }
+  // PatchFinder::CalcSearchLevelAndWarpMatrix (PatchFinder.cc:52-84)
+  int calc_search_level(TData& d, const MapPoint& p, const SE3& pose) {
+    double v3cam[3], mr[3], md[3];
+    pose.apply(p.world, v3cam);
+    const double ooz = 1.0 / v3cam[2];
+    pose.rotate(p.right, mr);
+    pose.rotate(p.down, md);
+    double a0 = (mr[0] - v3cam[0] * mr[2] * ooz), a1 = (mr[1] - v3cam[1] * mr[2] * ooz);
+    double c0 = (d.derivs[0] * a0 + d.derivs[1] * a1) * ooz, c1 = (d.derivs[2] * a0 + d.derivs[3] * a1) * ooz;
+    d.warp_inv[0] = c0; d.warp_inv[2] = c1;  // column 0
+    a0 = (md[0] - v3cam[0] * md[2] * ooz); a1 = (md[1] - v3cam[1] * md[2] * ooz);
+    c0 = (d.derivs[0] * a0 + d.derivs[1] * a1) * ooz; c1 = (d.derivs[2] * a0 + d.derivs[3] * a1) * ooz;
+    d.warp_inv[1] = c0; d.warp_inv[3] = c1;  // column 1
+    double det = d.warp_inv[0] * d.warp_inv[3] - d.warp_inv[1] * d.warp_inv[2];
+    d.search_level = 0;
+    while (det > 3 && d.search_level < PTAM_LEVELS - 1) { d.search_level++; det *= 0.25; }
+    if (det > 3 || det < 0.25) { d.template_bad = true; return -1; }
+    return d.search_level;
+  }
+  // PatchFinder::MakeTemplateCoarseCont (PatchFinder.cc:98-127) + CVD::transform/sample.
+  void make_template(TData& d, const MapPoint& p) {
+    const double* m = d.warp_inv;
+    const double det = m[0] * m[3] - m[2] * m[1];
+    const double idet = 1.0 / det;
+    const int sc = 1 << d.search_level;
+    double m2[4];  // M2Inverse (Tools.h:54-65) * LevelScale
+    m2[0] = (m[3] * idet) * sc; m2[3] = (m[0] * idet) * sc;
+    m2[2] = (-m[2] * idet) * sc; m2[1] = (-m[1] * idet) * sc;
+    bool refresh = !d.has_template;
+    for (int i = 0; !refresh && i < 2; i++) {
+      double d0 = m2[i] - d.last_warp[i], d1 = m2[2 + i] - d.last_warp[2 + i];
+      if (d0 * d0 + d1 * d1 > 0.07 * 0.07) refresh = true;
+    }
+    if (!refresh) return;
+    const Level& src = store[p.src_kf].lev[p.src_level];
+    // CVD::transform(in, out, M, inOrig, outOrig): p = inOrig + M (out - outOrig), accumulated
+    // incrementally across/down exactly like libCVD (vision.h).
+    const double across[2] = {m2[0], m2[2]}, downv[2] = {m2[1], m2[3]};
+    double pp[2] = {p.center.x - (m2[0] * 4.0 + m2[1] * 4.0), p.center.y - (m2[2] * 4.0 + m2[3] * 4.0)};
+    const double cr[2] = {downv[0] - 8 * across[0], downv[1] - 8 * across[1]};
+    const double xb = src.w - 1, yb = src.h - 1;
+    int outside = 0;
+    for (int i = 0; i < 8; i++, pp[0] += cr[0], pp[1] += cr[1])
+      for (int j = 0; j < 8; j++, pp[0] += across[0], pp[1] += across[1]) {
+        if (0 <= pp[0] && 0 <= pp[1] && pp[0] < xb && pp[1] < yb) {
+          double x = pp[0], y = pp[1];
+          const int lx = (int)x, ly = (int)y;
+          x -= lx; y -= ly;
+          const uint8_t* r0 = src.row(ly) + lx;
+          const uint8_t* r1 = src.row(ly + 1) + lx;
+          double v = (1 - y) * ((1 - x) * r0[0] + x * r0[1]) + y * ((1 - x) * r1[0] + x * r1[1]);
+          d.tmpl[8 * i + j] = (uint8_t)v;
+        } else {
+          d.tmpl[8 * i + j] = 0;
+          ++outside;
+        }
+      }
+    d.template_bad = outside != 0;
+    int s = 0, ss = 0;
+    for (int k = 0; k < 64; k++) { int b = d.tmpl[k]; s += b; ss += b * b; }
+    d.tsum = s; d.tsumsq = ss;
+    d.has_template = true;
+    for (int k = 0; k < 4; k++) d.last_warp[k] = m2[k];
+  }
+  // PatchFinder::FindPatchCoarse (PatchFinder.cc:160-211)
+  bool find_patch_coarse(TData& d, IRef pos, const KeyFrame& kf, unsigned range) {
+    const int max_ssd = 8 * 8 * 500;
+    const int sc = 1 << d.search_level;
+    pos.x /= sc; pos.y /= sc;
+    range = (range + sc - 1) / sc;
+    int top = pos.y - (int)range, bot1 = pos.y + (int)range + 1;
+    const int left = pos.x - (int)range, right = pos.x + (int)range;
+    const Level& L = kf.lev[d.search_level];
+    if (top < 0) top = 0;
+    if (top >= L.h) return false;
+    if (bot1 <= 0) return false;
+    IRef best{0, 0};
+    int best_ssd = max_ssd + 1;
+    size_t i = L.lut[top];
+    size_t i_end = bot1 >= L.h ? L.corners.size() : (size_t)L.lut[bot1];
+    for (; i < i_end; i++) {
+      const IRef c = L.corners[i];
+      if (c.x < left || c.x > right) continue;
+      const int ddx = pos.x - c.x, ddy = pos.y - c.y;
+      if ((unsigned)(ddx * ddx + ddy * ddy) > range * range) continue;
+      int ssd = zmssd_at_point(L, c, d.tmpl, d.tsum, d.tsumsq, max_ssd);
+      if (ssd < best_ssd) { best = c; best_ssd = ssd; }
+    }
+    if (best_ssd < max_ssd) {
+      d.coarse[0] = level_zero_pos((double)best.x, d.search_level);
+      d.coarse[1] = level_zero_pos((double)best.y, d.search_level);
+      return true;
+    }
+    return false;
+  }
+  // PatchFinder::MakeSubPixTemplate (PatchFinder.cc:219-240)
+  void make_subpix_template(TData& d) {
+    double H[9] = {0};
+    for (int x = 1; x < 7; x++)
+      for (int y = 1; y < 7; y++) {
+        double g[3];
+        g[0] = 0.5 * (d.tmpl[8 * y + x + 1] - d.tmpl[8 * y + x - 1]);
+        g[1] = 0.5 * (d.tmpl[8 * (y + 1) + x] - d.tmpl[8 * (y - 1) + x]);
+        g[2] = 1.0;
+        d.jac[(y - 1) * 6 + (x - 1)][0] = (float)g[0];
+        d.jac[(y - 1) * 6 + (x - 1)][1] = (float)g[1];
+        for (int r = 0; r < 3; r++)
+          for (int c = 0; c < 3; c++) H[3 * r + c] += g[r] * g[c];
+      }
+    ldlt_inverse(H, 3, d.hinv);
+    d.subpix[0] = d.coarse[0]; d.subpix[1] = d.coarse[1];
+    d.mean_diff = 0.0;
+  }
+  // PatchFinder::IterateSubPix (PatchFinder.cc:275-318)
+  double iterate_subpix(TData& d, const KeyFrame& kf) {
+    const int l = d.search_level;
+    const double cx = level_n_pos(d.subpix[0], l), cy = level_n_pos(d.subpix[1], l);
+    const Level& L = kf.lev[l];
+    const int rx = (int)(cx > 0.0 ? cx + 0.5 : cx - 0.5), ry = (int)(cy > 0.0 ? cy + 0.5 : cy - 0.5);
+    if (!L.in_image_with_border(rx, ry, 5)) return -1.0;
+    const double bx = cx - 4, by = cy - 4;
+    const double dX = bx - std::floor(bx), dY = by - std::floor(by);
+    const float fTL = (float)((1.0 - dX) * (1.0 - dY));
+    const float fTR = (float)((dX) * (1.0 - dY));
+    const float fBL = (float)((1.0 - dX) * (dY));
+    const float fBR = (float)((dX) * (dY));
+    double acc[3] = {0, 0, 0};
+    const int ibx = (int)bx, iby = (int)by;
+    for (int y = 1; y < 7; y++) {
+      const uint8_t* tl = L.row(iby + y) + ibx + 1;
+      for (int x = 1; x < 7; x++) {
+        float fp = fTL * tl[0] + fTR * tl[1] + fBL * tl[L.w] + fBR * tl[L.w + 1];
+        tl++;
+        double diff = fp - d.tmpl[8 * y + x] + d.mean_diff;
+        acc[0] += diff * d.jac[(y - 1) * 6 + (x - 1)][0];
+        acc[1] += diff * d.jac[(y - 1) * 6 + (x - 1)][1];
+        acc[2] += diff;
+      }
+    }
+    double u[3];
+    for (int r = 0; r < 3; r++) u[r] = d.hinv[3 * r] * acc[0] + d.hinv[3 * r + 1] * acc[1] + d.hinv[3 * r + 2] * acc[2];
+    d.subpix[0] -= u[0] * (1 << l);
+    d.subpix[1] -= u[1] * (1 << l);
+    d.mean_diff -= u[2];
+    return u[0] * u[0] + u[1] * u[1];
+  }
+  bool iterate_subpix_to_convergence(TData& d, const KeyFrame& kf, int max_its) {
+    for (int it = 0; it < max_its; it++) {
+      double u2 = iterate_subpix(d, kf);
+      if (u2 < 0) return false;
+      if (u2 < 0.03 * 0.03) return true;
+    }
+    return false;
+  }
+  // Tracker::SearchForPoints (Tracker.cc:867-912)
+  unsigned search_for_points(Stream& s, const std::vector<int>& v, unsigned range, int subpix_its) {
+    unsigned nfound = 0;
+    for (int idx : v) {
+      TData& d = s.td[idx];
+      make_template(d, s.pts[idx]);
+      if (d.template_bad) { d.in_image = d.found = false; continue; }
+      s.attempted[d.search_level]++;
+      bool f = find_patch_coarse(d, IRef{(int)d.v2image[0], (int)d.v2image[1]}, s.cur, range);
+      d.searched = true;
+      if (!f) { d.found = false; continue; }
+      d.found = true;
+      d.sqrt_inv_noise = 1.0 / (1 << d.search_level);
+      nfound++;
+      s.found[d.search_level]++;
+      if (subpix_its > 0) {
+        d.did_subpix = true;
+        make_subpix_template(d);
+        if (!iterate_subpix_to_convergence(d, s.cur, subpix_its)) {
+          d.found = false; nfound--; s.found[d.search_level]--;
+          continue;
+        }
+        d.v2found[0] = d.subpix[0]; d.v2found[1] = d.subpix[1];
+      } else {
+        d.v2found[0] = d.coarse[0]; d.v2found[1] = d.coarse[1];
+        d.did_subpix = false;
+      }
+    }
+    return nfound;
+  }
+  // TrackerData::CalcJacobian (Tracker.h:125-136)
+  void calc_jacobian(TData& d) {
+    const double ooz = 1.0 / d.v3cam[2];
+    const double X = d.v3cam[0], Y = d.v3cam[1], Z = d.v3cam[2];
+    // SE3<>::generator_field(m, (X,Y,Z,1)): translations e_m; rotations (0,-Z,Y),(Z,0,-X),(-Y,X,0)
+    const double g[6][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, -Z, Y}, {Z, 0, -X}, {-Y, X, 0}};
+    for (int m = 0; m < 6; m++) {
+      double a0 = (g[m][0] - X * g[m][2] * ooz) * ooz;
+      double a1 = (g[m][1] - Y * g[m][2] * ooz) * ooz;
+      d.J[m] = d.derivs[0] * a0 + d.derivs[1] * a1;
+      d.J[6 + m] = d.derivs[2] * a0 + d.derivs[3] * a1;
+    }
+  }
+  // Tracker::CalcPoseUpdate (Tracker.cc:928-1005) with TooN WLS<6>.
+  void calc_pose_update(Stream& s, const std::vector<int>& v, double override_sigma, bool mark, double* mu) {
+    const int est = prm.mestimator;
+    std::vector<double> e2;
+    for (int idx : v) {
+      TData& d = s.td[idx];
+      if (!d.found) continue;
+      d.err[0] = d.sqrt_inv_noise * (d.v2found[0] - d.v2image[0]);
+      d.err[1] = d.sqrt_inv_noise * (d.v2found[1] - d.v2image[1]);
+      e2.push_back(d.err[0] * d.err[0] + d.err[1] * d.err[1]);
+    }
+    for (int i = 0; i < 6; i++) mu[i] = 0;
+    if (e2.empty()) return;
+    double sigma2 = override_sigma > 0 ? override_sigma : mest_find_sigma_squared(e2, est);
+    double C[36] = {0}, b[6] = {0};
+    for (int i = 0; i < 6; i++) C[7 * i] += 100.0;  // add_prior
+    for (int idx : v) {
+      TData& d = s.td[idx];
+      if (!d.found) continue;
+      const double es = d.err[0] * d.err[0] + d.err[1] * d.err[1];
+      const double wgt = mest_weight(es, sigma2, est);
+      if (wgt == 0.0) { if (mark) s.pts[idx].outliers++; continue; }
+      else if (mark) s.pts[idx].inliers++;
+      for (int r = 0; r < 2; r++) {  // add_mJ(m, J, w): C += (J w) J^T ; b += m (J w)
+        double Jr[6], Jw[6];
+        for (int k = 0; k < 6; k++) { Jr[k] = d.sqrt_inv_noise * d.J[6 * r + k]; Jw[k] = Jr[k] * wgt; }
+        for (int i = 0; i < 6; i++)
+          for (int j = 0; j < 6; j++) C[6 * i + j] += Jw[i] * Jr[j];
+        for (int i = 0; i < 6; i++) b[i] += d.err[r] * Jw[i];
+      }
+    }
+    ldlt_factor(C, 6, 6);
+    ldlt_backsub(C, 6, 6, b, mu);
+  }
+
+  // Tracker::TrackMap (Tracker.cc:442-698); std::random_shuffle == identity permutation.
+  void track_map(Stream& s) {
+    for (int i = 0; i < 4; i++) s.attempted[i] = s.found[i] = 0;
+    std::vector<int> pvs[4];
+    Camera::Proj last{};
+    for (size_t i = 0; i < s.pts.size(); i++) {
+      TData& d = s.td[i];
+      d.in_pvs = false;
+      d.n_search_level = -1;
+      project(d, s.pts[i], s.pose, last);
+      if (!d.in_image) continue;
+      cam.derivs(last, d.derivs);
+      d.n_search_level = calc_search_level(d, s.pts[i], s.pose);
+      if (d.n_search_level == -1) continue;
+      d.searched = false; d.found = false;
+      d.in_pvs = true;
+      pvs[d.n_search_level].push_back((int)i);
+    }
+    for (int l = 0; l < 4; l++) s.res.n_pvs[l] = (int)pvs[l].size();
+    std::vector<int> next, iter;
+    unsigned coarse_max = prm.coarse_max, coarse_range = prm.coarse_range;
+    s.did_coarse = false;
+    bool try_coarse = true;
+    if (prm.disable_coarse || s.st.msd_scaled_velocity_magnitude < prm.coarse_min_velocity || coarse_max == 0) try_coarse = false;
+    if (s.st.just_recovered_so_use_coarse) {
+      try_coarse = true; coarse_max *= 2; coarse_range *= 2; s.st.just_recovered_so_use_coarse = 0;
+    }
+    s.res.n_coarse = 0;
+    if (try_coarse && pvs[3].size() + pvs[2].size() > (unsigned)prm.coarse_min) {
+      if (pvs[3].size() <= coarse_max) { next = pvs[3]; pvs[3].clear(); }
+      else {
+        for (unsigned i = 0; i < coarse_max; i++) next.push_back(pvs[3][i]);
+        pvs[3].erase(pvs[3].begin(), pvs[3].begin() + coarse_max);
+      }
+      if (next.size() < coarse_max) {
+        unsigned more = coarse_max - (unsigned)next.size();
+        if (pvs[2].size() <= more) { next = pvs[2]; pvs[2].clear(); }  // sic: assignment, as in Tracker.cc:533
+        else {
+          for (unsigned i = 0; i < more; i++) next.push_back(pvs[2][i]);
+          pvs[2].erase(pvs[2].begin(), pvs[2].begin() + more);
+        }
+      }
+      s.res.n_coarse = (int)next.size();
+      unsigned nf = search_for_points(s, next, coarse_range, prm.coarse_subpix_its);
+      iter = next;
+      if (nf >= (unsigned)prm.coarse_min) {
+        s.did_coarse = true;
+        for (int it = 0; it < 10; it++) {
+          if (it != 0)
+            for (int idx : iter) if (s.td[idx].found) project_and_derivs(s.td[idx], s.pts[idx], s.pose, last);
+          for (int idx : iter) if (s.td[idx].found) calc_jacobian(s.td[idx]);
+          double mu[6];
+          calc_pose_update(s, iter, it > 5 ? 1.0 : 0.0, false, mu);
+          s.pose = se3_mul(se3_exp(mu), s.pose);
+        }
+      }
+    }
+    const unsigned fine_range = s.did_coarse ? 5 : 10;
+    {
+      for (int idx : pvs[3]) project_and_derivs(s.td[idx], s.pts[idx], s.pose, last);
+      search_for_points(s, pvs[3], fine_range, 8);
+      for (int idx : pvs[3]) iter.push_back(idx);
+      s.res.n_level3 = (int)pvs[3].size();
+    }
+    {
+      next.clear();
+      for (int l = 2; l >= 0; l--) for (int idx : pvs[l]) next.push_back(idx);
+      int use = prm.max_patches_per_frame - (int)iter.size();
+      if (use < 0) use = 0;
+      if ((int)next.size() > use) next.resize(use);  // random_shuffle == identity, then chop
+      if (s.did_coarse)
+        for (int idx : next) project_and_derivs(s.td[idx], s.pts[idx], s.pose, last);
+      search_for_points(s, next, fine_range, 0);
+      for (int idx : next) iter.push_back(idx);
+      s.res.n_fine = (int)next.size();
+    }
+    double last_update[6] = {0, 0, 0, 0, 0, 0};
+    for (int it = 0; it < 10; it++) {
+      const bool nonlin = it == 0 || it == 4 || it == 9;
+      if (it != 0) {
+        if (nonlin) {
+          for (int idx : iter) if (s.td[idx].found) project_and_derivs(s.td[idx], s.pts[idx], s.pose, last);
+        } else {
+          for (int idx : iter) {
+            TData& d = s.td[idx];
+            if (!d.found) continue;
+            for (int r = 0; r < 2; r++) {  // LinearUpdate (Tracker.h:139-142)
+              double a = 0;
+              for (int k = 0; k < 6; k++) a += d.J[6 * r + k] * last_update[k];
+              d.v2image[r] += a;
+            }
+          }
+        }
+      }
+      if (nonlin) for (int idx : iter) if (s.td[idx].found) calc_jacobian(s.td[idx]);
+      double mu[6];
+      calc_pose_update(s, iter, it > 5 ? 16.0 : 0.0, it == 9, mu);
+      s.pose = se3_mul(se3_exp(mu), s.pose);
+      for (int k = 0; k < 6; k++) last_update[k] = mu[k];
+    }
+    s.iter_set = iter;
+    // scene depth (Tracker.cc:680-697)
+    double sum = 0, sumsq = 0; int n = 0;
+    for (int idx : iter) if (s.td[idx].found) { double z = s.td[idx].v3cam[2]; sum += z; sumsq += z * z; n++; }
+    if (n > 20) {
+      s.st.scene_depth_mean = sum / n;
+      s.st.scene_depth_sigma = std::sqrt((sumsq / n) - s.st.scene_depth_mean * s.st.scene_depth_mean);
+    }
+  }
+
+  void track_frame(Stream& s, const uint8_t* im, int stride) {
+    make_keyframe_lite(s.cur, im, W, H, stride);
+    s.st.frame++;
+    s.pose = SE3::from12(s.st.se3_cam_from_world);
+    // PredictPoseWithMotionModel (Tracker.cc:1012-1029), mbUseSBIInit = false
+    s.start = s.pose;
+    s.pose = se3_mul(se3_exp(s.st.velocity), s.start);
+    track_map(s);
+    // UpdateMotionModel (Tracker.cc:1035-1056)
+    double motion[6];
+    se3_ln(se3_mul(s.pose, se3_inverse(s.start)), motion);
+    if (prm.use_constant_velocity) for (int k = 0; k < 6; k++) s.st.velocity[k] = motion[k];
+    else for (int k = 0; k < 6; k++) s.st.velocity[k] = 0.9 * (0.5 * motion[k] + 0.5 * s.st.velocity[k]);
+    double v6[6];
+    for (int k = 0; k < 6; k++) v6[k] = s.st.velocity[k];
+    for (int k = 0; k < 3; k++) v6[k] *= 1.0 / s.st.scene_depth_mean;
+    double m = 0;
+    for (int k = 0; k < 6; k++) m += v6[k] * v6[k];
+    s.st.msd_scaled_velocity_magnitude = std::sqrt(m);
+    // AssessTrackingQuality (Tracker.cc:1062-1107)
+    int ta = 0, tf = 0, la = 0, lf = 0;
+    for (int i = 0; i < 4; i++) {
+      ta += s.attempted[i]; tf += s.found[i];
+      if (i >= 2) { la += s.attempted[i]; lf += s.found[i]; }
+    }
+    s.res.quality_needs_kf_distance = 0;
+    if (tf == 0 || ta == 0) s.st.tracking_quality = 0;
+    else {
+      double tfrac = (double)tf / ta;
+      double lfrac = la > 10 ? (double)lf / la : tfrac;
+      if (tfrac > prm.quality_good) s.st.tracking_quality = 2;
+      else if (lfrac < prm.quality_lost) s.st.tracking_quality = 0;
+      else s.res.quality_needs_kf_distance = 1;
+    }
+    if (s.st.tracking_quality == 0) s.st.lost_frames++; else s.st.lost_frames = 0;
+    s.pose.to12(s.st.se3_cam_from_world);
+    // result
+    ptam_track_result& r = s.res;
+    s.pose.to12(r.se3_cam_from_world);
+    r.scene_depth_mean = s.st.scene_depth_mean; r.scene_depth_sigma = s.st.scene_depth_sigma;
+    for (int i = 0; i < 4; i++) {
+      r.meas_attempted[i] = s.attempted[i]; r.meas_found[i] = s.found[i];
+      r.n_corners[i] = (int)s.cur.lev[i].corners.size();
+    }
+    r.did_coarse = s.did_coarse;
+    r.tracking_quality = s.st.tracking_quality;
+    r.reserved = 0;
+  }
+};
+
+}  // namespace orc
+
+using orc::Tracker;
+
+extern "C" {
+
+void orc_tracker_default_params(ptam_tracker_params* p) {
+  p->coarse_min = 20; p->coarse_max = 60; p->coarse_range = 30; p->coarse_subpix_its = 8;
+  p->disable_coarse = 0; p->max_patches_per_frame = 1000; p->mestimator = 0; p->use_constant_velocity = 1;
+  p->coarse_min_velocity = 0.006; p->quality_good = 0.3; p->quality_lost = 0.13;
+}
+
+void* orc_tracker_create(int, const double* cam_params, int width, int height, int n_streams, const ptam_tracker_params* params) {
+  Tracker* t = new Tracker;
+  t->cam.init(cam_params, width, height);
+  t->W = width; t->H = height; t->S = n_streams;
+  if (params) t->prm = *params; else orc_tracker_default_params(&t->prm);
+  t->streams.resize(n_streams);
+  for (auto& s : t->streams) {
+    std::memset(&s.st, 0, sizeof(s.st));
+    std::memset(&s.res, 0, sizeof(s.res));
+    orc::SE3().to12(s.st.se3_cam_from_world);
+    s.st.tracking_quality = 2;
+    s.st.scene_depth_mean = 1.0; s.st.scene_depth_sigma = 1.0;
+  }
+  return t;
+}
+void orc_tracker_destroy(void* t) { delete (Tracker*)t; }
+const char* orc_tracker_last_error(const void* t) { return ((const Tracker*)t)->err.c_str(); }
+
+int orc_tracker_add_keyframe(void* tp, const uint8_t* image, int stride) {
+  Tracker* t = (Tracker*)tp;
+  t->store.emplace_back();
+  orc::make_keyframe_lite(t->store.back(), image, t->W, t->H, stride, false);
+  return (int)t->store.size() - 1;
+}
+
+int orc_tracker_set_map(void* tp, int stream, int n, const double* world, const double* right, const double* down,
+                        const int32_t* src_kf, const int32_t* src_level, const int32_t* center) {
+  Tracker* t = (Tracker*)tp;
+  if (stream < 0 || stream >= t->S) return PTAM_ERR_INVALID;
+  auto& s = t->streams[stream];
+  s.pts.assign(n, orc::MapPoint());
+  s.td.assign(n, orc::TData());
+  for (int i = 0; i < n; i++) {
+    if (src_kf[i] < 0 || src_kf[i] >= (int)t->store.size() || src_level[i] < 0 || src_level[i] >= PTAM_LEVELS) return PTAM_ERR_INVALID;
+    for (int k = 0; k < 3; k++) { s.pts[i].world[k] = world[3 * i + k]; s.pts[i].right[k] = right[3 * i + k]; s.pts[i].down[k] = down[3 * i + k]; }
+    s.pts[i].src_kf = src_kf[i]; s.pts[i].src_level = src_level[i];
+    s.pts[i].center = {center[2 * i], center[2 * i + 1]};
+  }
+  return 0;
+}
+int orc_tracker_set_state(void* tp, int stream, const ptam_tracker_state* st) {
+  Tracker* t = (Tracker*)tp;
+  if (stream < 0 || stream >= t->S) return PTAM_ERR_INVALID;
+  t->streams[stream].st = *st; return 0;
+}
+int orc_tracker_get_state(void* tp, int stream, ptam_tracker_state* st) {
+  Tracker* t = (Tracker*)tp;
+  if (stream < 0 || stream >= t->S) return PTAM_ERR_INVALID;
+  *st = t->streams[stream].st; return 0;
+}
+int orc_tracker_make_keyframes(void* tp, const uint8_t* const* images, int stride) {
+  Tracker* t = (Tracker*)tp;
+  for (int s = 0; s < t->S; s++) orc::make_keyframe_lite(t->streams[s].cur, images[s], t->W, t->H, stride);
+  return 0;
+}
+int orc_tracker_track_frames(void* tp, const uint8_t* const* images, int stride, ptam_track_result* results) {
+  Tracker* t = (Tracker*)tp;
+  for (int s = 0; s < t->S; s++) {
+    t->track_frame(t->streams[s], images[s], stride);
+    if (results) results[s] = t->streams[s].res;
+  }
+  return 0;
+}
+int orc_tracker_synchronize(void*) { return 0; }
+int orc_tracker_level_size(const void* tp, int level, int* w, int* h) {
+  const Tracker* t = (const Tracker*)tp;
+  int ww = t->W, hh = t->H;
+  for (int l = 0; l < level; l++) { ww /= 2; hh /= 2; }
+  *w = ww; *h = hh; return 0;
+}
+int orc_tracker_get_level(void* tp, int stream, int level, uint8_t* pixels, int32_t* corners_xy, int cap, int32_t* row_lut) {
+  Tracker* t = (Tracker*)tp;
+  const orc::Level& L = t->streams[stream].cur.lev[level];
+  if (pixels) std::memcpy(pixels, L.im.data(), L.im.size());
+  if (corners_xy)
+    for (size_t i = 0; i < L.corners.size() && (int)i < cap; i++) { corners_xy[2 * i] = L.corners[i].x; corners_xy[2 * i + 1] = L.corners[i].y; }
+  if (row_lut) for (size_t i = 0; i < L.lut.size(); i++) row_lut[i] = L.lut[i];
+  return (int)L.corners.size();
+}
+int orc_tracker_get_points(void* tp, int stream, int32_t* flags, int32_t* level, double* v2_found, double* v2_image,
+                           int32_t* outl, int32_t* inl) {
+  Tracker* t = (Tracker*)tp;
+  auto& s = t->streams[stream];
+  for (size_t i = 0; i < s.pts.size(); i++) {
+    const orc::TData& d = s.td[i];
+    if (flags) {
+      int f = 0;
+      if (d.in_pvs) {
+        f |= PTAM_PT_IN_PVS;
+        if (d.in_image) f |= PTAM_PT_IN_IMAGE;
+        if (d.searched) f |= PTAM_PT_SEARCHED;
+        if (d.found) f |= PTAM_PT_FOUND;
+        if (d.found && d.did_subpix) f |= PTAM_PT_SUBPIX;
+      }
+      if (d.template_bad) f |= PTAM_PT_TEMPLATE_BAD;
+      flags[i] = f;
+    }
+    if (level) level[i] = d.n_search_level;
+    if (v2_found) { v2_found[2 * i] = d.found && d.in_pvs ? d.v2found[0] : 0; v2_found[2 * i + 1] = d.found && d.in_pvs ? d.v2found[1] : 0; }
+    if (v2_image) { v2_image[2 * i] = d.in_pvs ? d.v2image[0] : 0; v2_image[2 * i + 1] = d.in_pvs ? d.v2image[1] : 0; }
+    if (outl) outl[i] = s.pts[i].outliers;
+    if (inl) inl[i] = s.pts[i].inliers;
+  }
+  return (int)s.pts.size();
+}
+int orc_tracker_get_templates(void* tp, int stream, uint8_t* tmpl, int32_t* sums) {
+  Tracker* t = (Tracker*)tp;
+  auto& s = t->streams[stream];
+  for (size_t i = 0; i < s.pts.size(); i++) {
+    const orc::TData& d = s.td[i];
+    if (tmpl) { if (d.has_template) std::memcpy(tmpl + 64 * i, d.tmpl, 64); else std::memset(tmpl + 64 * i, 0, 64); }
+    if (sums) { sums[2 * i] = d.has_template ? d.tsum : 0; sums[2 * i + 1] = d.has_template ? d.tsumsq : 0; }
+  }
+  return (int)s.pts.size();
+}
+int orc_tracker_get_iteration_set(void* tp, int stream, int32_t* idx, int cap) {
+  Tracker* t = (Tracker*)tp;
+  auto& s = t->streams[stream];
+  for (size_t i = 0; i < s.iter_set.size() && (int)i < cap; i++) idx[i] = s.iter_set[i];
+  return (int)s.iter_set.size();
+}
+
+// ---- unit-level helpers used only by tests -------------------------------------------------
+double orc_atan(double x) { return orc::spec_atan(x); }
+void orc_se3_exp(const double* mu, double* out12) { orc::se3_exp(mu).to12(out12); }
+void orc_se3_ln(const double* in12, double* out6) { orc::se3_ln(orc::SE3::from12(in12), out6); }
+void orc_cam_project(const double* params, int w, int h, const double* cam_xy, double* im_xy, double* derivs4, int* invalid) {
+  orc::Camera c; c.init(params, w, h);
+  auto q = c.project(cam_xy);
+  im_xy[0] = q.im[0]; im_xy[1] = q.im[1];
+  if (derivs4) c.derivs(q, derivs4);
+  if (invalid) *invalid = q.invalid;
+}
+void orc_cam_unproject(const double* params, int w, int h, const double* im_xy, double* cam_xy) {
+  orc::Camera c; c.init(params, w, h);
+  c.unproject(im_xy, cam_xy);
+}
+double orc_cam_largest_radius(const double* params, int w, int h) { orc::Camera c; c.init(params, w, h); return c.largest_radius; }
+int orc_zmssd(const uint8_t* im, int w, int h, int x, int y, const uint8_t* tmpl) {
+  orc::Level L; L.w = w; L.h = h; L.im.assign(im, im + (size_t)w * h);
+  int s = 0, ss = 0;
+  for (int k = 0; k < 64; k++) { s += tmpl[k]; ss += tmpl[k] * tmpl[k]; }
+  return orc::zmssd_at_point(L, orc::IRef{x, y}, tmpl, s, ss, 32000);
+}
+// brute-force FAST-10 straight from the definition (independent of fast10's shortcut): for tests
+int orc_fast10_bruteforce(const uint8_t* im, int w, int h, int t, int32_t* xy, int cap) {
+  static const int dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+  static const int dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+  int n = 0;
+  for (int y = 3; y < h - 3; y++)
+    for (int x = 3; x < w - 3; x++) {
+      int p = im[y * w + x];
+      bool corner = false;
+      for (int start = 0; start < 16 && !corner; start++) {
+        bool allb = true, alld = true;
+        for (int k = 0; k < 10; k++) {
+          int v = im[(y + dy[(start + k) & 15]) * w + x + dx[(start + k) & 15]];
+          if (!(v > p + t)) allb = false;
+          if (!(v < p - t)) alld = false;
+        }
+        corner = allb || alld;
+      }
+      if (corner) { if (n < cap) { xy[2 * n] = x; xy[2 * n + 1] = y; } n++; }
+    }
+  return n;
+}
+}  // extern "C"

@@ -1,0 +1,500 @@
+// Host side of path T behind the C-ABI (include/ptam_b200.h): owns the device buffers, builds the
+// level geometry, enqueues the kernels of tracker_kernels.cuh on the handle's stream.
+// One TrackFrame for a whole batch of streams = 8 kernel launches, no host round trip in between;
+// the only D2H is the per-stream result block at the end (skipped when results == NULL).
+#include "tracker_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+using namespace ptam;
+
+static thread_local std::string g_last_error;
+
+namespace {
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    free();
+    n = count;
+    if (!count) return cudaSuccess;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+    if (e == cudaSuccess) e = cudaMemset(p, 0, count * sizeof(T));
+    return e;
+  }
+  void free() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+CamModel make_cam(const double* p, double W, double H) {  // ATANCamera::RefreshParams
+  CamModel c;
+  c.img_w = W; c.img_h = H;
+  c.focal[0] = W * p[0]; c.focal[1] = H * p[1];
+  c.center[0] = W * p[2] - 0.5; c.center[1] = H * p[3] - 0.5;
+  c.inv_focal[0] = 1.0 / c.focal[0]; c.inv_focal[1] = 1.0 / c.focal[1];
+  c.w = p[4];
+  if (c.w != 0.0) {
+    c.tan2 = 2.0 * std::tan(c.w / 2.0);
+    c.one_over_tan2 = 1.0 / c.tan2;
+    c.winv = 1.0 / c.w;
+    c.dist_enabled = 1.0;
+  } else {
+    c.winv = 0.0; c.tan2 = 0.0; c.one_over_tan2 = 0.0; c.dist_enabled = 0.0;
+  }
+  const double v0 = std::max(p[2], 1.0 - p[2]) / p[0];
+  const double v1 = std::max(p[3], 1.0 - p[3]) / p[1];
+  const double r = std::sqrt(v0 * v0 + v1 * v1);
+  c.largest_radius = c.w == 0.0 ? r : std::tan(r * c.w) * c.one_over_tan2;
+  c.max_r = 1.5 * c.largest_radius;
+  return c;
+}
+}  // namespace
+
+ptam::CamModel ptam_make_cam_model(const double* p, double W, double H) { return make_cam(p, W, H); }
+
+struct ptam_tracker {
+  int device = 0, W = 0, H = 0, S = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  TrackerDev dev{};
+  // per-stream frame buffers
+  DevBuf<uint8_t> pyr;
+  DevBuf<int2> corners;
+  DevBuf<int> lut;
+  DevBuf<uint32_t> mask;
+  DevBuf<StreamCtl> ctl;
+  DevBuf<int> pt_count;
+  std::vector<int> h_pt_count;
+  // keyframe store
+  std::vector<uint8_t*> kf_bufs;
+  DevBuf<const uint8_t*> kf_ptrs;
+  size_t kf_ptr_cap = 0;
+  // per-point arrays
+  int cap = 0;
+  DevBuf<double> world, right, down, last_warp, v3cam, v2image, derivs, warp_inv, v2found, sin_, J, e2;
+  DevBuf<int> src_kf, src_level, tsum, tsumsq, flags, level, search_level, outliers, inliers, pvs, iter_idx;
+  DevBuf<int2> center;
+  DevBuf<uint8_t> tmpl;
+  // pinned staging
+  uint8_t* h_stage = nullptr;
+  StreamCtl* h_ctl = nullptr;
+  cudaEvent_t stage_ev = nullptr;  // staging buffer is free again once this has fired
+  int max_h = 0;
+
+  void set_error(const std::string& e) { err = e; g_last_error = e; }
+
+  ~ptam_tracker() {
+    cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);
+    for (auto p : kf_bufs) cudaFree(p);
+    pyr.free(); corners.free(); lut.free(); mask.free(); ctl.free(); pt_count.free(); kf_ptrs.free();
+    world.free(); right.free(); down.free(); last_warp.free(); v3cam.free(); v2image.free(); derivs.free();
+    warp_inv.free(); v2found.free(); sin_.free(); J.free(); e2.free(); src_kf.free(); src_level.free();
+    tsum.free(); tsumsq.free(); flags.free(); level.free(); search_level.free(); outliers.free(); inliers.free();
+    pvs.free(); iter_idx.free(); center.free(); tmpl.free();
+    if (stage_ev) cudaEventDestroy(stage_ev);
+    if (h_stage) cudaFreeHost(h_stage);
+    if (h_ctl) cudaFreeHost(h_ctl);
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  int init(int dev_id, const double* cam_params, int w, int h, int n_streams, const ptam_tracker_params* prm) {
+    device = dev_id; W = w; H = h; S = n_streams;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device: the B200 path has no CPU fallback"); return PTAM_ERR_NO_DEVICE; }
+    if (dev_id < 0 || dev_id >= ndev) { set_error("bad device index"); return PTAM_ERR_INVALID; }
+    if (w < 64 || h < 64 || n_streams < 1) { set_error("image must be at least 64x64 and n_streams >= 1"); return PTAM_ERR_INVALID; }
+    PTAM_CUDA_TRY(this, cudaSetDevice(dev_id));
+    PTAM_CUDA_TRY(this, cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    PTAM_CUDA_TRY(this, cudaEventCreateWithFlags(&stage_ev, cudaEventDisableTiming));
+    Geom& g = dev.g;
+    const int thr[4] = {10, 15, 15, 10};  // KeyFrame.cc:35-42
+    size_t img = 0, cor = 0, msk = 0;
+    int lut_o = 0, tiles = 0, lw = w, lh = h;
+    for (int l = 0; l < kLevels; l++) {
+      LevelDesc& L = g.lev[l];
+      L.w = lw; L.h = lh; L.pitch = (lw + 15) & ~15;
+      L.nwords = (lw + 31) / 32;
+      L.corner_cap = std::max(0, lw - 6) * std::max(0, lh - 6);
+      L.img_off = img; img += (size_t)L.pitch * lh; img = (img + 255) & ~(size_t)255;
+      L.corner_off = cor; cor += L.corner_cap;
+      L.lut_off = lut_o; lut_o += lh;
+      L.mask_off = msk; msk += (size_t)L.nwords * lh;
+      L.tiles_x = (lw + kFastTW - 1) / kFastTW; L.tiles_y = (lh + kFastTH - 1) / kFastTH;
+      L.tile_base = tiles; tiles += L.tiles_x * L.tiles_y;
+      g.thresholds[l] = thr[l];
+      lw /= 2; lh /= 2;
+    }
+    g.pyr_bytes = img; g.corner_stride = cor; g.lut_stride = lut_o; g.mask_stride = msk; g.fast_tiles = tiles;
+    max_h = h;
+    dev.cam = make_cam(cam_params, w, h);
+    if (prm) dev.prm = *prm; else ptam_tracker_default_params(&dev.prm);
+    dev.S = S;
+    PTAM_CUDA_TRY(this, pyr.alloc(g.pyr_bytes * S));
+    PTAM_CUDA_TRY(this, corners.alloc(g.corner_stride * S));
+    PTAM_CUDA_TRY(this, lut.alloc((size_t)g.lut_stride * S));
+    PTAM_CUDA_TRY(this, mask.alloc(g.mask_stride * S));
+    PTAM_CUDA_TRY(this, ctl.alloc(S));
+    PTAM_CUDA_TRY(this, pt_count.alloc(S));
+    h_pt_count.assign(S, 0);
+    PTAM_CUDA_TRY(this, cudaMallocHost(&h_stage, g.pyr_bytes * S));
+    PTAM_CUDA_TRY(this, cudaMallocHost(&h_ctl, sizeof(StreamCtl) * S));
+    std::memset(h_ctl, 0, sizeof(StreamCtl) * S);
+    for (int s = 0; s < S; s++) {
+      ptam_tracker_state& st = h_ctl[s].st;
+      st.se3_cam_from_world[0] = st.se3_cam_from_world[4] = st.se3_cam_from_world[8] = 1.0;
+      st.tracking_quality = 2;
+      st.scene_depth_mean = 1.0; st.scene_depth_sigma = 1.0;
+    }
+    PTAM_CUDA_TRY(this, cudaMemcpy(ctl.p, h_ctl, sizeof(StreamCtl) * S, cudaMemcpyHostToDevice));
+    dev.pyr = pyr.p; dev.corners = corners.p; dev.lut = lut.p; dev.mask = mask.p; dev.ctl = ctl.p;
+    dev.pt_count = pt_count.p;
+    dev.kf_ptrs = nullptr; dev.n_kf = 0;
+    PTAM_CUDA_TRY(this, ensure_points(1024));
+    if ((size_t)(max_h + 1) * sizeof(int) > 48 * 1024)
+      PTAM_CUDA_TRY(this, cudaFuncSetAttribute(k_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (max_h + 1) * (int)sizeof(int)));
+    return PTAM_OK;
+  }
+
+  template <class T>
+  cudaError_t regrow(DevBuf<T>& b, int per_point, int old_cap, int new_cap) {
+    DevBuf<T> nb;
+    cudaError_t e = nb.alloc((size_t)new_cap * per_point * S);
+    if (e != cudaSuccess) return e;
+    if (b.p && old_cap)
+      e = cudaMemcpy2D(nb.p, (size_t)new_cap * per_point * sizeof(T), b.p, (size_t)old_cap * per_point * sizeof(T),
+                       (size_t)old_cap * per_point * sizeof(T), S, cudaMemcpyDeviceToDevice);
+    b.free();
+    b = nb;
+    return e;
+  }
+
+  cudaError_t ensure_points(int n) {
+    if (n <= cap) return cudaSuccess;
+    cudaStreamSynchronize(stream);
+    const int nc = std::max(n, cap * 2);
+    cudaError_t e = cudaSuccess;
+#define RG(buf, k) if (e == cudaSuccess) e = regrow(buf, k, cap, nc)
+    RG(world, 3); RG(right, 3); RG(down, 3); RG(last_warp, 4); RG(v3cam, 3); RG(v2image, 2); RG(derivs, 4);
+    RG(warp_inv, 4); RG(v2found, 2); RG(sin_, 1); RG(J, 12); RG(e2, 1); RG(src_kf, 1); RG(src_level, 1);
+    RG(tsum, 1); RG(tsumsq, 1); RG(flags, 1); RG(level, 1); RG(search_level, 1); RG(outliers, 1); RG(inliers, 1);
+    RG(pvs, 4); RG(iter_idx, 1); RG(center, 1); RG(tmpl, 64);
+#undef RG
+    if (e != cudaSuccess) return e;
+    cap = nc;
+    PointArrays& p = dev.p;
+    p.world = world.p; p.right = right.p; p.down = down.p; p.src_kf = src_kf.p; p.src_level = src_level.p; p.center = center.p;
+    p.tmpl = tmpl.p; p.tsum = tsum.p; p.tsumsq = tsumsq.p; p.last_warp = last_warp.p;
+    p.flags = flags.p; p.level = level.p; p.search_level = search_level.p;
+    p.v3cam = v3cam.p; p.v2image = v2image.p; p.derivs = derivs.p; p.warp_inv = warp_inv.p;
+    p.v2found = v2found.p; p.sqrt_inv_noise = sin_.p; p.J = J.p; p.outliers = outliers.p; p.inliers = inliers.p;
+    p.pvs = pvs.p; p.iter_idx = iter_idx.p; p.e2 = e2.p; p.cap = cap;
+    return cudaSuccess;
+  }
+
+  int upload_images(const uint8_t* const* images, int stride, uint8_t* dst, size_t dst_stream_pitch, int n) {
+    // pack into pinned staging with the library pitch, then one async H2D
+    const LevelDesc& L0 = dev.g.lev[0];
+    PTAM_CUDA_TRY(this, cudaEventSynchronize(stage_ev));
+    for (int s = 0; s < n; s++) {
+      uint8_t* o = h_stage + (size_t)s * dst_stream_pitch;
+      for (int y = 0; y < H; y++) std::memcpy(o + (size_t)y * L0.pitch, images[s] + (size_t)y * stride, W);
+    }
+    for (int s = 0; s < n; s++)
+      PTAM_CUDA_TRY(this, cudaMemcpyAsync(dst + (size_t)s * dst_stream_pitch, h_stage + (size_t)s * dst_stream_pitch,
+                                          (size_t)L0.pitch * H, cudaMemcpyHostToDevice, stream));
+    PTAM_CUDA_TRY(this, cudaEventRecord(stage_ev, stream));
+    return PTAM_OK;
+  }
+
+  int launch_keyframe(const TrackerDev& d) {
+    const LevelDesc& L0 = d.g.lev[0];
+    dim3 gp((L0.w + 63) / 64, (L0.h + 63) / 64, S);
+    k_pyramid<<<gp, 256, 0, stream>>>(d);
+    k_fast<<<dim3(d.g.fast_tiles, S), 256, 0, stream>>>(d);
+    k_compact<<<dim3(kLevels, S), 1024, (max_h + 1) * sizeof(int), stream>>>(d);
+    launches += 3;
+    PTAM_CUDA_TRY(this, cudaGetLastError());
+    return PTAM_OK;
+  }
+
+  int launch_track(const TrackerDev& d) {
+    int rc = launch_keyframe(d);
+    if (rc) return rc;
+    int maxn = 0;
+    for (int s = 0; s < S; s++) maxn = std::max(maxn, h_pt_count[s]);
+    k_pvs_select<<<S, 1024, 0, stream>>>(d);
+    const int coarse_items = std::min(maxn, 2 * std::max(0, d.prm.coarse_max));
+    if (coarse_items > 0) k_search<<<dim3((coarse_items + 3) / 4, S), 128, 0, stream>>>(d, 0);
+    k_pose<<<S, kPoseThreads, 0, stream>>>(d, 0);
+    if (maxn > 0) k_search<<<dim3((maxn + 3) / 4, S), 128, 0, stream>>>(d, 1);
+    k_pose<<<S, kPoseThreads, 0, stream>>>(d, 1);
+    launches += 3 + (coarse_items > 0) + (maxn > 0);
+    PTAM_CUDA_TRY(this, cudaGetLastError());
+    return PTAM_OK;
+  }
+
+  int fetch_results(ptam_track_result* results) {
+    PTAM_CUDA_TRY(this, cudaMemcpyAsync(h_ctl, ctl.p, sizeof(StreamCtl) * S, cudaMemcpyDeviceToHost, stream));
+    PTAM_CUDA_TRY(this, cudaStreamSynchronize(stream));
+    for (int s = 0; s < S; s++) {
+      const StreamCtl& c = h_ctl[s];
+      ptam_track_result& r = results[s];
+      std::memcpy(r.se3_cam_from_world, c.st.se3_cam_from_world, sizeof(double) * 12);
+      r.scene_depth_mean = c.st.scene_depth_mean; r.scene_depth_sigma = c.st.scene_depth_sigma;
+      for (int l = 0; l < kLevels; l++) {
+        r.meas_attempted[l] = c.attempted[l]; r.meas_found[l] = c.found[l];
+        r.n_corners[l] = c.n_corners[l]; r.n_pvs[l] = c.n_pvs[l];
+      }
+      r.did_coarse = c.did_coarse; r.n_coarse = c.n_coarse; r.n_level3 = c.n_l3; r.n_fine = c.n_fine;
+      r.tracking_quality = c.st.tracking_quality; r.quality_needs_kf_distance = c.needs_kf_distance;
+      r.reserved = 0;
+    }
+    return PTAM_OK;
+  }
+};
+
+extern "C" {
+
+void ptam_tracker_default_params(ptam_tracker_params* p) {
+  p->coarse_min = 20; p->coarse_max = 60; p->coarse_range = 30; p->coarse_subpix_its = 8;
+  p->disable_coarse = 0; p->max_patches_per_frame = 1000; p->mestimator = 0; p->use_constant_velocity = 1;
+  p->coarse_min_velocity = 0.006; p->quality_good = 0.3; p->quality_lost = 0.13;
+}
+
+const char* ptam_global_last_error(void) { return g_last_error.c_str(); }
+
+ptam_tracker* ptam_tracker_create(int device, const double* cam_params, int width, int height, int n_streams,
+                                  const ptam_tracker_params* params) {
+  ptam_tracker* t = new ptam_tracker;
+  if (t->init(device, cam_params, width, height, n_streams, params) != PTAM_OK) {
+    g_last_error = t->err;
+    delete t;
+    return nullptr;
+  }
+  return t;
+}
+void ptam_tracker_destroy(ptam_tracker* t) { delete t; }
+const char* ptam_tracker_last_error(const ptam_tracker* t) { return t->err.c_str(); }
+
+int ptam_tracker_add_keyframe(ptam_tracker* t, const uint8_t* image, int stride) {
+  cudaSetDevice(t->device);
+  uint8_t* buf = nullptr;
+  PTAM_CUDA_TRY(t, cudaMalloc(&buf, t->dev.g.pyr_bytes));
+  t->kf_bufs.push_back(buf);
+  const uint8_t* imgs[1] = {image};
+  int rc = t->upload_images(imgs, stride, buf, t->dev.g.pyr_bytes, 1);
+  if (rc) return rc;
+  TrackerDev d = t->dev;
+  d.pyr = buf; d.src.l0 = buf; d.src.stream_pitch = 0; d.src.pitch = d.g.lev[0].pitch;
+  const LevelDesc& L0 = d.g.lev[0];
+  k_pyramid<<<dim3((L0.w + 63) / 64, (L0.h + 63) / 64, 1), 256, 0, t->stream>>>(d);
+  t->launches++;
+  PTAM_CUDA_TRY(t, cudaGetLastError());
+  if (t->kf_bufs.size() > t->kf_ptr_cap) {
+    PTAM_CUDA_TRY(t, cudaStreamSynchronize(t->stream));
+    t->kf_ptr_cap = std::max<size_t>(256, t->kf_ptr_cap * 2);
+    PTAM_CUDA_TRY(t, t->kf_ptrs.alloc(t->kf_ptr_cap));
+  }
+  PTAM_CUDA_TRY(t, cudaStreamSynchronize(t->stream));
+  PTAM_CUDA_TRY(t, cudaMemcpy(t->kf_ptrs.p, t->kf_bufs.data(), sizeof(uint8_t*) * t->kf_bufs.size(), cudaMemcpyHostToDevice));
+  t->dev.kf_ptrs = t->kf_ptrs.p;
+  t->dev.n_kf = (int)t->kf_bufs.size();
+  return t->dev.n_kf - 1;
+}
+
+int ptam_tracker_set_map(ptam_tracker* t, int stream, int n, const double* world, const double* right, const double* down,
+                         const int32_t* src_kf, const int32_t* src_level, const int32_t* center) {
+  cudaSetDevice(t->device);
+  if (stream < 0 || stream >= t->S || n < 0) { t->set_error("bad stream / point count"); return PTAM_ERR_INVALID; }
+  for (int i = 0; i < n; i++)
+    if (src_kf[i] < 0 || src_kf[i] >= t->dev.n_kf || src_level[i] < 0 || src_level[i] >= kLevels) {
+      t->set_error("map point references an unknown keyframe or level");
+      return PTAM_ERR_INVALID;
+    }
+  PTAM_CUDA_TRY(t, t->ensure_points(n));
+  PTAM_CUDA_TRY(t, cudaStreamSynchronize(t->stream));
+  const size_t o = (size_t)stream * t->cap;
+#define UP(buf, src, k, T) PTAM_CUDA_TRY(t, cudaMemcpy(buf.p + o * k, src, sizeof(T) * k * n, cudaMemcpyHostToDevice))
+  if (n) {
+    UP(t->world, world, 3, double); UP(t->right, right, 3, double); UP(t->down, down, 3, double);
+    UP(t->src_kf, src_kf, 1, int); UP(t->src_level, src_level, 1, int);
+    PTAM_CUDA_TRY(t, cudaMemcpy(t->center.p + o, center, sizeof(int2) * n, cudaMemcpyHostToDevice));
+  }
+#undef UP
+  PTAM_CUDA_TRY(t, cudaMemset(t->flags.p + o, 0, sizeof(int) * t->cap));
+  PTAM_CUDA_TRY(t, cudaMemset(t->outliers.p + o, 0, sizeof(int) * t->cap));
+  PTAM_CUDA_TRY(t, cudaMemset(t->inliers.p + o, 0, sizeof(int) * t->cap));
+  PTAM_CUDA_TRY(t, cudaMemset(t->level.p + o, 0xff, sizeof(int) * t->cap));
+  t->h_pt_count[stream] = n;
+  PTAM_CUDA_TRY(t, cudaMemcpy(t->pt_count.p, t->h_pt_count.data(), sizeof(int) * t->S, cudaMemcpyHostToDevice));
+  return PTAM_OK;
+}
+
+int ptam_tracker_set_state(ptam_tracker* t, int stream, const ptam_tracker_state* s) {
+  cudaSetDevice(t->device);
+  if (stream < 0 || stream >= t->S) { t->set_error("bad stream"); return PTAM_ERR_INVALID; }
+  PTAM_CUDA_TRY(t, cudaStreamSynchronize(t->stream));
+  PTAM_CUDA_TRY(t, cudaMemcpy(&t->ctl.p[stream].st, s, sizeof(*s), cudaMemcpyHostToDevice));
+  return PTAM_OK;
+}
+int ptam_tracker_get_state(ptam_tracker* t, int stream, ptam_tracker_state* s) {
+  cudaSetDevice(t->device);
+  if (stream < 0 || stream >= t->S) { t->set_error("bad stream"); return PTAM_ERR_INVALID; }
+  PTAM_CUDA_TRY(t, cudaStreamSynchronize(t->stream));
+  PTAM_CUDA_TRY(t, cudaMemcpy(s, &t->ctl.p[stream].st, sizeof(*s), cudaMemcpyDeviceToHost));
+  return PTAM_OK;
+}
+
+static int use_host_frames(ptam_tracker* t, const uint8_t* const* images, int stride, TrackerDev& d) {
+  int rc = t->upload_images(images, stride, t->pyr.p, t->dev.g.pyr_bytes, t->S);
+  if (rc) return rc;
+  d = t->dev;
+  d.src.l0 = t->pyr.p; d.src.stream_pitch = d.g.pyr_bytes; d.src.pitch = d.g.lev[0].pitch;
+  t->dev.src = d.src;
+  return PTAM_OK;
+}
+
+int ptam_tracker_make_keyframes(ptam_tracker* t, const uint8_t* const* images, int stride) {
+  cudaSetDevice(t->device);
+  TrackerDev d;
+  int rc = use_host_frames(t, images, stride, d);
+  if (rc) return rc;
+  rc = t->launch_keyframe(d);
+  if (rc) return rc;
+  PTAM_CUDA_TRY(t, cudaStreamSynchronize(t->stream));
+  return PTAM_OK;
+}
+
+int ptam_tracker_track_frames(ptam_tracker* t, const uint8_t* const* images, int stride, ptam_track_result* results) {
+  cudaSetDevice(t->device);
+  TrackerDev d;
+  int rc = use_host_frames(t, images, stride, d);
+  if (rc) return rc;
+  rc = t->launch_track(d);
+  if (rc) return rc;
+  if (results) return t->fetch_results(results);
+  return PTAM_OK;
+}
+
+int ptam_tracker_track_frames_device(ptam_tracker* t, const uint8_t* d_images, size_t frame_pitch_bytes, int stride,
+                                     ptam_track_result* results) {
+  cudaSetDevice(t->device);
+  if (!d_images || stride < t->W) { t->set_error("bad device frame description"); return PTAM_ERR_INVALID; }
+  TrackerDev d = t->dev;
+  d.src.l0 = d_images; d.src.stream_pitch = frame_pitch_bytes; d.src.pitch = stride;
+  t->dev.src = d.src;
+  int rc = t->launch_track(d);
+  if (rc) return rc;
+  if (results) return t->fetch_results(results);
+  return PTAM_OK;
+}
+
+int ptam_tracker_synchronize(ptam_tracker* t) {
+  cudaSetDevice(t->device);
+  PTAM_CUDA_TRY(t, cudaStreamSynchronize(t->stream));
+  return PTAM_OK;
+}
+void* ptam_tracker_cuda_stream(ptam_tracker* t) { return (void*)t->stream; }
+int64_t ptam_tracker_launch_count(const ptam_tracker* t) { return t->launches; }
+
+int ptam_tracker_level_size(const ptam_tracker* t, int level, int* w, int* h) {
+  if (level < 0 || level >= kLevels) return PTAM_ERR_INVALID;
+  *w = t->dev.g.lev[level].w; *h = t->dev.g.lev[level].h;
+  return PTAM_OK;
+}
+
+int ptam_tracker_get_level(ptam_tracker* t, int stream, int level, uint8_t* pixels, int32_t* corners_xy, int cap, int32_t* row_lut) {
+  cudaSetDevice(t->device);
+  if (stream < 0 || stream >= t->S || level < 0 || level >= kLevels) { t->set_error("bad stream / level"); return PTAM_ERR_INVALID; }
+  PTAM_CUDA_TRY(t, cudaStreamSynchronize(t->stream));
+  const LevelDesc& L = t->dev.g.lev[level];
+  if (pixels) {
+    const uint8_t* src; size_t pitch;
+    if (level == 0) { src = t->dev.src.l0 + (size_t)stream * t->dev.src.stream_pitch; pitch = t->dev.src.pitch; }
+    else { src = t->pyr.p + (size_t)stream * t->dev.g.pyr_bytes + L.img_off; pitch = L.pitch; }
+    if (!src) { t->set_error("no frame processed yet"); return PTAM_ERR_INVALID; }
+    PTAM_CUDA_TRY(t, cudaMemcpy2D(pixels, L.w, src, pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+  }
+  int n = 0;
+  PTAM_CUDA_TRY(t, cudaMemcpy(&n, &t->ctl.p[stream].n_corners[level], sizeof(int), cudaMemcpyDeviceToHost));
+  if (corners_xy && cap > 0 && n > 0)
+    PTAM_CUDA_TRY(t, cudaMemcpy(corners_xy, t->corners.p + (size_t)stream * t->dev.g.corner_stride + L.corner_off,
+                                sizeof(int2) * std::min(n, cap), cudaMemcpyDeviceToHost));
+  if (row_lut)
+    PTAM_CUDA_TRY(t, cudaMemcpy(row_lut, t->lut.p + (size_t)stream * t->dev.g.lut_stride + L.lut_off, sizeof(int) * L.h, cudaMemcpyDeviceToHost));
+  return n;
+}
+
+int ptam_tracker_get_points(ptam_tracker* t, int stream, int32_t* flags, int32_t* level, double* v2_found, double* v2_image,
+                            int32_t* outl, int32_t* inl) {
+  cudaSetDevice(t->device);
+  if (stream < 0 || stream >= t->S) { t->set_error("bad stream"); return PTAM_ERR_INVALID; }
+  PTAM_CUDA_TRY(t, cudaStreamSynchronize(t->stream));
+  const int n = t->h_pt_count[stream];
+  const size_t o = (size_t)stream * t->cap;
+  if (!n) return 0;
+  std::vector<int> fl(n);
+  PTAM_CUDA_TRY(t, cudaMemcpy(fl.data(), t->flags.p + o, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  if (level) PTAM_CUDA_TRY(t, cudaMemcpy(level, t->level.p + o, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  if (v2_found) PTAM_CUDA_TRY(t, cudaMemcpy(v2_found, t->v2found.p + 2 * o, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost));
+  if (v2_image) PTAM_CUDA_TRY(t, cudaMemcpy(v2_image, t->v2image.p + 2 * o, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost));
+  if (outl) PTAM_CUDA_TRY(t, cudaMemcpy(outl, t->outliers.p + o, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  if (inl) PTAM_CUDA_TRY(t, cudaMemcpy(inl, t->inliers.p + o, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; i++) {
+    const int f = fl[i];
+    int out = 0;
+    if (f & F_IN_PVS) {
+      out |= PTAM_PT_IN_PVS;
+      if (f & F_IN_IMAGE) out |= PTAM_PT_IN_IMAGE;
+      if (f & F_SEARCHED) out |= PTAM_PT_SEARCHED;
+      if (f & F_FOUND) out |= PTAM_PT_FOUND;
+      if ((f & F_FOUND) && (f & F_SUBPIX)) out |= PTAM_PT_SUBPIX;
+    }
+    if (f & F_TEMPLATE_BAD) out |= PTAM_PT_TEMPLATE_BAD;
+    if (flags) flags[i] = out;
+    const bool fnd = (f & F_IN_PVS) && (f & F_FOUND);
+    if (v2_found && !fnd) v2_found[2 * i] = v2_found[2 * i + 1] = 0;
+    if (v2_image && !(f & F_IN_PVS)) v2_image[2 * i] = v2_image[2 * i + 1] = 0;
+  }
+  return n;
+}
+
+int ptam_tracker_get_templates(ptam_tracker* t, int stream, uint8_t* tmpl, int32_t* sums) {
+  cudaSetDevice(t->device);
+  if (stream < 0 || stream >= t->S) { t->set_error("bad stream"); return PTAM_ERR_INVALID; }
+  PTAM_CUDA_TRY(t, cudaStreamSynchronize(t->stream));
+  const int n = t->h_pt_count[stream];
+  const size_t o = (size_t)stream * t->cap;
+  if (!n) return 0;
+  std::vector<int> fl(n), a(n), b(n);
+  PTAM_CUDA_TRY(t, cudaMemcpy(fl.data(), t->flags.p + o, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  PTAM_CUDA_TRY(t, cudaMemcpy(a.data(), t->tsum.p + o, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  PTAM_CUDA_TRY(t, cudaMemcpy(b.data(), t->tsumsq.p + o, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  if (tmpl) PTAM_CUDA_TRY(t, cudaMemcpy(tmpl, t->tmpl.p + 64 * o, (size_t)64 * n, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; i++) {
+    const bool has = fl[i] & F_HAS_TEMPLATE;
+    if (tmpl && !has) std::memset(tmpl + 64 * i, 0, 64);
+    if (sums) { sums[2 * i] = has ? a[i] : 0; sums[2 * i + 1] = has ? b[i] : 0; }
+  }
+  return n;
+}
+
+int ptam_tracker_get_iteration_set(ptam_tracker* t, int stream, int32_t* idx, int cap) {
+  cudaSetDevice(t->device);
+  if (stream < 0 || stream >= t->S) { t->set_error("bad stream"); return PTAM_ERR_INVALID; }
+  PTAM_CUDA_TRY(t, cudaStreamSynchronize(t->stream));
+  StreamCtl c;
+  PTAM_CUDA_TRY(t, cudaMemcpy(&c, &t->ctl.p[stream], sizeof(c), cudaMemcpyDeviceToHost));
+  const int n = c.n_coarse + c.n_l3 + c.n_fine;
+  if (idx && n && cap)
+    PTAM_CUDA_TRY(t, cudaMemcpy(idx, t->iter_idx.p + (size_t)stream * t->cap, sizeof(int) * std::min(n, cap), cudaMemcpyDeviceToHost));
+  return n;
+}
+
+}  // extern "C"

@@ -1,0 +1,1029 @@
+// sm_100a kernels of path T (per-frame tracker).  Compiled with -fmad=false: the integer outputs
+// (template bytes, search levels, patch offsets) depend on IEEE-exact f64 intermediates.
+//
+//   k_pyramid      CVD::halfSample x3 (KeyFrame.cc:25-28), one 64x64 L0 tile per CTA
+//   k_fast         fast_corner_detect_10 on all four levels (KeyFrame.cc:35-42): smem-staged tiles,
+//                  4 pixels per thread from 32-bit words, corner bitmask per row
+//   k_compact      raster-ordered corner lists + row LUT from the bitmasks (KeyFrame.cc:46-52)
+//   k_pvs_select   motion-model prediction, TrackerData::Project + GetProjectionDerivs +
+//                  CalcSearchLevelAndWarpMatrix per map point, PVS lists, coarse/fine selection
+//                  (Tracker.cc:454-611, PatchFinder.cc:52-84)
+//   k_search       warp per point: MakeTemplateCoarseCont + FindPatchCoarse/ZMSSD + sub-pixel
+//                  (Tracker.cc:867-912, PatchFinder.cc:98-318, ImageProcess.cc:130-163)
+//   k_pose         one CTA per stream: the ten Gauss-Newton iterations of CalcPoseUpdate with the
+//                  Tukey sigma by radix select, then motion model + quality (Tracker.cc:552-568,
+//                  614-643,928-1107)
+#pragma once
+#include "common.cuh"
+#include "../../include/ptam_b200.h"
+
+namespace ptam {
+
+struct LevelDesc {
+  int w, h, pitch;      // pitch of the library-owned image buffer for this level
+  int nwords;           // 32-pixel mask words per row
+  int corner_cap;       // capacity of the corner list
+  int lut_off;          // offset (ints) into the per-stream LUT buffer
+  size_t img_off;       // byte offset inside a pyramid buffer
+  size_t corner_off;    // offset (int2) inside the per-stream corner buffer
+  size_t mask_off;      // offset (words) inside the per-stream mask buffer
+  int tiles_x, tiles_y, tile_base;  // k_fast tiling
+};
+
+struct Geom {
+  LevelDesc lev[kLevels];
+  size_t pyr_bytes;      // one pyramid (L0..L3)
+  size_t corner_stride;  // int2 per stream
+  int lut_stride;        // ints per stream
+  size_t mask_stride;    // words per stream
+  int fast_tiles;        // tiles per frame over all levels
+  int thresholds[kLevels];
+};
+
+// per-stream persistent tracker state (ptam_tracker_state) + per-frame control block
+struct StreamCtl {
+  ptam_tracker_state st;
+  double start_pose[12];  // mse3StartPos
+  double pose[12];        // working pose (mse3CamFromWorld)
+  int n_pvs[kLevels];
+  int attempted[kLevels], found[kLevels];
+  int n_coarse, n_l3, n_fine;
+  int try_coarse, coarse_range, did_coarse;
+  int n_corners[kLevels];
+  int needs_kf_distance;
+  int pad;
+};
+
+// frame-scoped point flags (low byte) and persistent flags (high bits)
+enum : int {
+  F_IN_IMAGE = 1, F_IN_PVS = 2, F_SEARCHED = 4, F_FOUND = 8, F_SUBPIX = 16,
+  F_TEMPLATE_BAD = 32,   // persistent: PatchFinder::mbTemplateBad
+  F_HAS_TEMPLATE = 64    // persistent: mpLastTemplateMapPoint == &p
+};
+
+struct PointArrays {
+  // map (inputs)
+  const double* world; const double* right; const double* down;
+  const int* src_kf; const int* src_level; const int2* center;
+  // template cache
+  uint8_t* tmpl; int* tsum; int* tsumsq; double* last_warp;
+  // frame state
+  int* flags; int* level; int* search_level;
+  double* v3cam; double* v2image; double* derivs; double* warp_inv;
+  double* v2found; double* sqrt_inv_noise; double* J;
+  int* outliers; int* inliers;
+  int* pvs;       // [S][4][cap]
+  int* iter_idx;  // [S][cap]
+  double* e2;     // [S][cap] scratch
+  int cap;        // points per stream (stride)
+};
+
+struct FrameSrc {
+  const uint8_t* l0;     // level-0 pixels of stream 0
+  size_t stream_pitch;   // bytes between streams
+  int pitch;             // bytes between rows
+};
+
+struct TrackerDev {
+  Geom g;
+  CamModel cam;
+  ptam_tracker_params prm;
+  FrameSrc src;
+  uint8_t* pyr;          // [S] pyramids (levels 1..3 used; level 0 when frames come from the host)
+  int2* corners;         // [S] corner lists
+  int* lut;              // [S] row LUTs
+  uint32_t* mask;        // [S] corner bitmasks
+  const uint8_t* const* kf_ptrs;  // stored keyframe pyramids
+  int n_kf;
+  StreamCtl* ctl;        // [S]
+  const int* pt_count;   // [S]
+  PointArrays p;
+  int S;
+};
+
+PTAM_DEV const uint8_t* level_image(const TrackerDev& d, int s, int l, int& pitch) {
+  if (l == 0) { pitch = d.src.pitch; return d.src.l0 + (size_t)s * d.src.stream_pitch; }
+  pitch = d.g.lev[l].pitch;
+  return d.pyr + (size_t)s * d.g.pyr_bytes + d.g.lev[l].img_off;
+}
+
+// =============================================================================================
+// k_pyramid — one CTA = 64x64 level-0 tile -> 32x32 L1, 16x16 L2, 8x8 L3.  256 threads, each
+// reads a 4x4 block of L0 (four 32-bit loads when rows are 4-byte aligned).
+// Truncating mean at every level, exactly CVD::halfSample.
+// =============================================================================================
+__global__ void __launch_bounds__(256) k_pyramid(TrackerDev d) {
+  __shared__ uint8_t s2[16][16];
+  const int s = blockIdx.z;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int x0 = blockIdx.x * 64 + tx * 4, y0 = blockIdx.y * 64 + ty * 4;
+  const LevelDesc &L0 = d.g.lev[0], &L1 = d.g.lev[1], &L2 = d.g.lev[2], &L3 = d.g.lev[3];
+  int p0;
+  const uint8_t* im0 = level_image(d, s, 0, p0);
+  uint8_t* base = d.pyr + (size_t)s * d.g.pyr_bytes;
+  uint8_t* im1 = base + L1.img_off;
+  uint8_t* im2 = base + L2.img_off;
+  uint8_t* im3 = base + L3.img_off;
+  const bool aligned = ((p0 & 3) == 0) && ((reinterpret_cast<uintptr_t>(im0) & 3) == 0);
+  unsigned rows[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const int y = y0 + r;
+    if (y < L0.h && x0 < L0.w) {
+      const uint8_t* p = im0 + (size_t)y * p0 + x0;
+      if (aligned && x0 + 3 < L0.w) rows[r] = __ldg(reinterpret_cast<const unsigned*>(p));
+      else {
+        unsigned v = 0;
+        for (int k = 0; k < 4; k++) if (x0 + k < L0.w) v |= (unsigned)__ldg(p + k) << (8 * k);
+        rows[r] = v;
+      }
+    }
+  }
+  // 2x2 L1 pixels
+  int l1[2][2];
+#pragma unroll
+  for (int j = 0; j < 2; j++)
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      const unsigned a = rows[2 * j] >> (16 * i), b = rows[2 * j + 1] >> (16 * i);
+      l1[j][i] = (int)((a & 255) + ((a >> 8) & 255) + (b & 255) + ((b >> 8) & 255)) / 4;
+    }
+  const int x1 = x0 >> 1, y1 = y0 >> 1;
+#pragma unroll
+  for (int j = 0; j < 2; j++)
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+      if (x1 + i < L1.w && y1 + j < L1.h) im1[(size_t)(y1 + j) * L1.pitch + x1 + i] = (uint8_t)l1[j][i];
+  const int v2 = (l1[0][0] + l1[0][1] + l1[1][0] + l1[1][1]) / 4;
+  const int x2 = x0 >> 2, y2 = y0 >> 2;
+  if (x2 < L2.w && y2 < L2.h) im2[(size_t)y2 * L2.pitch + x2] = (uint8_t)v2;
+  s2[ty][tx] = (uint8_t)v2;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int ax = threadIdx.x & 7, ay = threadIdx.x >> 3;
+    const int x3 = blockIdx.x * 8 + ax, y3 = blockIdx.y * 8 + ay;
+    if (x3 < L3.w && y3 < L3.h) {
+      const int v3 = (s2[2 * ay][2 * ax] + s2[2 * ay][2 * ax + 1] + s2[2 * ay + 1][2 * ax] + s2[2 * ay + 1][2 * ax + 1]) / 4;
+      im3[(size_t)y3 * L3.pitch + x3] = (uint8_t)v3;
+    }
+  }
+}
+
+// =============================================================================================
+// k_fast — FAST-10.  Tile = 128 px x 16 rows, 256 threads (8 warps x 2 rows), each thread tests 4
+// consecutive pixels.  The tile plus a 3-row / 4-byte-aligned halo is staged in shared memory with
+// 32-bit loads; ring pixels are extracted from three words per ring row.  Output: one bit per pixel.
+// A pixel is a corner iff >= 10 contiguous ring pixels are all > p+t or all < p-t (strict).
+// =============================================================================================
+constexpr int kFastTW = 128, kFastTH = 16;
+constexpr int kFastSW = kFastTW + 8;  // staged bytes per row: x0-4 .. x0+131
+
+PTAM_DEV bool run10(unsigned m) {
+  m |= m << 16;
+  unsigned a = m & (m >> 1);
+  a &= a >> 2;
+  a &= a >> 4;
+  a &= m >> 8;
+  a &= m >> 9;
+  return (a & 0xFFFFu) != 0;
+}
+
+__global__ void __launch_bounds__(256) k_fast(TrackerDev d) {
+  __shared__ __align__(16) uint8_t tile[kFastTH + 6][kFastSW];
+  const int s = blockIdx.y;
+  int l = 0;
+#pragma unroll
+  for (int k = 1; k < kLevels; k++) if ((int)blockIdx.x >= d.g.lev[k].tile_base) l = k;
+  const LevelDesc& L = d.g.lev[l];
+  const int t = blockIdx.x - L.tile_base;
+  const int tx = t % L.tiles_x, ty = t / L.tiles_x;
+  const int x0 = tx * kFastTW, y0 = ty * kFastTH;
+  int pitch;
+  const uint8_t* im = level_image(d, s, l, pitch);
+  const bool aligned = ((pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(im) & 3) == 0);
+  // stage rows y0-3 .. y0+18, bytes x0-4 .. x0+131 (zero outside the image)
+  for (int i = threadIdx.x; i < (kFastTH + 6) * (kFastSW / 4); i += 256) {
+    const int r = i / (kFastSW / 4), c = i % (kFastSW / 4);
+    const int y = y0 - 3 + r, x = x0 - 4 + 4 * c;
+    unsigned v = 0;
+    if (y >= 0 && y < L.h) {
+      const uint8_t* p = im + (size_t)y * pitch + x;
+      if (aligned && x >= 0 && x + 3 < L.w) v = __ldg(reinterpret_cast<const unsigned*>(p));
+      else
+        for (int k = 0; k < 4; k++) if (x + k >= 0 && x + k < L.w) v |= (unsigned)__ldg(p + k) << (8 * k);
+    }
+    *reinterpret_cast<unsigned*>(&tile[r][4 * c]) = v;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int thr = d.g.thresholds[l];
+#pragma unroll
+  for (int rr = 0; rr < 2; rr++) {
+    const int ry = warp * 2 + rr;  // row inside tile
+    const int y = y0 + ry;
+    const int x = x0 + 4 * lane;   // first of this thread's 4 pixels
+    unsigned nib = 0;
+    if (y >= 3 && y < L.h - 3) {
+      // words covering bytes [x-4, x+8) of rows ry .. ry+6 (tile row ry+3 is the centre row)
+      // centre pixels: bytes 4..7 of the centre row triple
+      const unsigned* crow = reinterpret_cast<const unsigned*>(&tile[ry + 3][4 * lane]);
+      const unsigned cw = crow[1];
+      // Quick reject (any 10-arc contains ring[0] or ring[8], i.e. (0,+3) or (0,-3)):
+      const unsigned up = reinterpret_cast<const unsigned*>(&tile[ry][4 * lane])[1];
+      const unsigned dn = reinterpret_cast<const unsigned*>(&tile[ry + 6][4 * lane])[1];
+      unsigned cand = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int p = (cw >> (8 * k)) & 255, a = (dn >> (8 * k)) & 255, b = (up >> (8 * k)) & 255;
+        const int cb = p + thr, c_b = p - thr;
+        if (a > cb || b > cb || a < c_b || b < c_b) cand |= 1u << k;
+      }
+      if (cand) {
+        // gather the 7 ring rows as 12-byte windows
+        unsigned w[7][3];
+#pragma unroll
+        for (int r = 0; r < 7; r++) {
+          const unsigned* q = reinterpret_cast<const unsigned*>(&tile[ry + r][4 * lane]);
+          w[r][0] = q[0]; w[r][1] = q[1]; w[r][2] = q[2];
+        }
+        // ring offsets (dx,dy), dy measured downwards; window byte index = 4 + k + dx, row = 3 + dy
+        const int dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+        const int dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          if (!((cand >> k) & 1)) continue;
+          const int xx = x + k;
+          if (xx < 3 || xx >= L.w - 3) continue;
+          const int p = (cw >> (8 * k)) & 255;
+          const int cb = p + thr, c_b = p - thr;
+          unsigned mb = 0, md = 0;
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            const int bi = 4 + k + dx[j];
+            const int v = (w[3 + dy[j]][bi >> 2] >> (8 * (bi & 3))) & 255;
+            mb |= (unsigned)(v > cb) << j;
+            md |= (unsigned)(v < c_b) << j;
+          }
+          if (run10(mb) || run10(md)) nib |= 1u << k;
+        }
+      }
+    }
+    // pack 8 lanes x 4 bits into one 32-pixel word
+    unsigned v = nib << (4 * (lane & 7));
+    v |= __shfl_xor_sync(kFull, v, 1);
+    v |= __shfl_xor_sync(kFull, v, 2);
+    v |= __shfl_xor_sync(kFull, v, 4);
+    if ((lane & 7) == 0 && y < L.h) {
+      const int word = (x0 >> 5) + (lane >> 3);
+      if (word < L.nwords) d.mask[(size_t)s * d.g.mask_stride + L.mask_off + (size_t)y * L.nwords + word] = v;
+    }
+  }
+}
+
+// =============================================================================================
+// k_compact — one CTA per (level, stream): row counts by popc, exclusive scan = the row LUT
+// (LUT[y] = number of corners in rows < y, KeyFrame.cc:46-52), then corners written in raster order.
+// =============================================================================================
+__global__ void __launch_bounds__(1024) k_compact(TrackerDev d) {
+  extern __shared__ int rowbase[];  // h + 1 ints
+  __shared__ int wsum[32];
+  __shared__ int carry;
+  const int l = blockIdx.x, s = blockIdx.y;
+  const LevelDesc& L = d.g.lev[l];
+  const uint32_t* mask = d.mask + (size_t)s * d.g.mask_stride + L.mask_off;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int y = warp; y < L.h; y += nwarps) {
+    int c = 0;
+    for (int wi = lane; wi < L.nwords; wi += 32) c += __popc(mask[(size_t)y * L.nwords + wi]);
+    c = warp_sum_int(c);
+    if (lane == 0) rowbase[y] = c;
+  }
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  // block-wide exclusive scan over rows, 1024 rows per round
+  for (int base = 0; base < L.h; base += blockDim.x) {
+    const int y = base + threadIdx.x;
+    const int v = y < L.h ? rowbase[y] : 0;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(kFull, inc, o);
+      if (lane >= o) inc += n;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      int ws = lane < nwarps ? wsum[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(kFull, ws, o);
+        if (lane >= o) ws += n;
+      }
+      wsum[lane] = ws;
+    }
+    __syncthreads();
+    const int excl = carry + (warp ? wsum[warp - 1] : 0) + inc - v;
+    if (y < L.h) rowbase[y] = excl;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += wsum[nwarps - 1];
+    __syncthreads();
+  }
+  int* lut = d.lut + (size_t)s * d.g.lut_stride + L.lut_off;
+  for (int y = threadIdx.x; y < L.h; y += blockDim.x) lut[y] = rowbase[y];
+  if (threadIdx.x == 0) d.ctl[s].n_corners[l] = carry;
+  int2* out = d.corners + (size_t)s * d.g.corner_stride + L.corner_off;
+  for (int y = warp; y < L.h; y += nwarps) {
+    int pos = rowbase[y];
+    for (int w0 = 0; w0 < L.nwords; w0 += 32) {
+      const int wi = w0 + lane;
+      unsigned m = wi < L.nwords ? mask[(size_t)y * L.nwords + wi] : 0u;
+      const int c = __popc(m);
+      int inc = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += n;
+      }
+      int o = pos + inc - c;
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        out[o++] = make_int2(wi * 32 + b, y);
+      }
+      pos += __shfl_sync(kFull, inc, 31);
+    }
+  }
+}
+
+// =============================================================================================
+// Projection helpers (TrackerData::Project, Tracker.h:70-86)
+// =============================================================================================
+struct ProjOut { double v3cam[3]; double v2image[2]; bool in_image; bool reached_cam; CamProj q; };
+
+PTAM_DEV void project_point(const TrackerDev& d, const double* pose, const double* world, ProjOut& o) {
+  o.in_image = false; o.reached_cam = false;
+  se3_apply(pose, world, o.v3cam);
+  if (o.v3cam[2] < 0.001) return;
+  const double ix = o.v3cam[0] / o.v3cam[2], iy = o.v3cam[1] / o.v3cam[2];
+  if (ix * ix + iy * iy > d.cam.largest_radius * d.cam.largest_radius) return;
+  o.q = cam_project(d.cam, ix, iy);
+  o.reached_cam = true;
+  o.v2image[0] = o.q.im[0]; o.v2image[1] = o.q.im[1];
+  if (o.q.invalid) return;
+  if (o.v2image[0] < 0 || o.v2image[1] < 0 || o.v2image[0] > d.cam.img_w || o.v2image[1] > d.cam.img_h) return;
+  o.in_image = true;
+}
+
+// =============================================================================================
+// k_pvs_select — one CTA (1024 threads) per stream.
+// =============================================================================================
+__global__ void __launch_bounds__(1024) k_pvs_select(TrackerDev d) {
+  __shared__ double pose[12];
+  __shared__ int wcnt[kLevels][32];
+  __shared__ int running[kLevels];
+  __shared__ int seg_src[6], seg_off[6], seg_n[6], seg_dst[6];
+  __shared__ int nseg;
+  const int s = blockIdx.x;
+  StreamCtl& ctl = d.ctl[s];
+  const int n = d.pt_count[s];
+  const int cap = d.p.cap;
+  const size_t gb = (size_t)s * cap;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    // mnFrame++, PredictPoseWithMotionModel (Tracker.cc:1012-1029, velocity only)
+    ctl.st.frame++;
+    double ex[12], np[12];
+    for (int i = 0; i < 12; i++) ctl.start_pose[i] = ctl.st.se3_cam_from_world[i];
+    se3_exp(ctl.st.velocity, ex);
+    se3_mul(ex, ctl.start_pose, np);
+    for (int i = 0; i < 12; i++) { pose[i] = np[i]; ctl.pose[i] = np[i]; }
+    for (int l = 0; l < kLevels; l++) { running[l] = 0; ctl.attempted[l] = 0; ctl.found[l] = 0; }
+  }
+  __syncthreads();
+  int* pvs = d.p.pvs + (size_t)s * kLevels * cap;
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    int lvl = -1;
+    if (i < n) {
+      const size_t g = gb + i;
+      int fl = d.p.flags[g] & (F_TEMPLATE_BAD | F_HAS_TEMPLATE);
+      ProjOut o;
+      project_point(d, pose, d.p.world + 3 * g, o);
+      d.p.v3cam[3 * g] = o.v3cam[0]; d.p.v3cam[3 * g + 1] = o.v3cam[1]; d.p.v3cam[3 * g + 2] = o.v3cam[2];
+      if (o.reached_cam) { d.p.v2image[2 * g] = o.v2image[0]; d.p.v2image[2 * g + 1] = o.v2image[1]; }
+      if (o.in_image) {
+        fl |= F_IN_IMAGE;
+        double dv[4];
+        cam_derivs(d.cam, o.q, dv);
+        for (int k = 0; k < 4; k++) d.p.derivs[4 * g + k] = dv[k];
+        // PatchFinder::CalcSearchLevelAndWarpMatrix (PatchFinder.cc:52-84)
+        const double ooz = 1.0 / o.v3cam[2];
+        double mr[3], md[3], wi[4];
+        so3_rotate(pose, d.p.right + 3 * g, mr);
+        so3_rotate(pose, d.p.down + 3 * g, md);
+        double a0 = (mr[0] - o.v3cam[0] * mr[2] * ooz), a1 = (mr[1] - o.v3cam[1] * mr[2] * ooz);
+        wi[0] = (dv[0] * a0 + dv[1] * a1) * ooz; wi[2] = (dv[2] * a0 + dv[3] * a1) * ooz;
+        a0 = (md[0] - o.v3cam[0] * md[2] * ooz); a1 = (md[1] - o.v3cam[1] * md[2] * ooz);
+        wi[1] = (dv[0] * a0 + dv[1] * a1) * ooz; wi[3] = (dv[2] * a0 + dv[3] * a1) * ooz;
+        for (int k = 0; k < 4; k++) d.p.warp_inv[4 * g + k] = wi[k];
+        double det = wi[0] * wi[3] - wi[1] * wi[2];
+        int sl = 0;
+        while (det > 3 && sl < kLevels - 1) { sl++; det *= 0.25; }
+        d.p.search_level[g] = sl;
+        if (det > 3 || det < 0.25) fl |= F_TEMPLATE_BAD;
+        else { lvl = sl; fl |= F_IN_PVS; }
+      }
+      d.p.flags[g] = fl;
+      d.p.level[g] = lvl;
+    }
+    // ordered compaction into the four per-level PVS lists (map order == identity shuffle)
+    unsigned same = 0;
+#pragma unroll
+    for (int l = 0; l < kLevels; l++) {
+      const unsigned b = __ballot_sync(kFull, lvl == l);
+      if (lane == 0) wcnt[l][warp] = __popc(b);
+      if (lvl == l) same = b;
+    }
+    __syncthreads();
+    if (lvl >= 0) {
+      int before = 0;
+      for (int wq = 0; wq < warp; wq++) before += wcnt[lvl][wq];
+      const int pos = running[lvl] + before + __popc(same & ((1u << lane) - 1));
+      pvs[(size_t)lvl * cap + pos] = i;
+    }
+    __syncthreads();
+    if (threadIdx.x < kLevels) {
+      int tot = 0;
+      for (int wq = 0; wq < (int)(blockDim.x >> 5); wq++) tot += wcnt[threadIdx.x][wq];
+      running[threadIdx.x] += tot;
+    }
+    __syncthreads();
+  }
+  // ---- selection (Tracker.cc:485-611), identity shuffle --------------------------------------
+  if (threadIdx.x == 0) {
+    int n3 = running[3], n2 = running[2], n1 = running[1], n0 = running[0];
+    for (int l = 0; l < kLevels; l++) ctl.n_pvs[l] = running[l];
+    unsigned coarse_max = d.prm.coarse_max, coarse_range = d.prm.coarse_range;
+    bool try_coarse = true;
+    if (d.prm.disable_coarse || ctl.st.msd_scaled_velocity_magnitude < d.prm.coarse_min_velocity || coarse_max == 0) try_coarse = false;
+    if (ctl.st.just_recovered_so_use_coarse) {
+      try_coarse = true; coarse_max *= 2; coarse_range *= 2; ctl.st.just_recovered_so_use_coarse = 0;
+    }
+    int ns = 0, dst = 0;
+    int o3 = 0, o2 = 0;  // consumed from the front of the level-3 / level-2 lists
+    int ncoarse = 0;
+    if (try_coarse && (unsigned)(n3 + n2) > (unsigned)d.prm.coarse_min) {
+      unsigned c3 = (unsigned)n3 <= coarse_max ? n3 : coarse_max;
+      o3 = c3;
+      unsigned have = c3;
+      bool keep3 = true;
+      unsigned c2 = 0;
+      if (have < coarse_max) {
+        const unsigned more = coarse_max - have;
+        if ((unsigned)n2 <= more) { c2 = n2; keep3 = false; }  // sic: vNextToSearch = avPVS[2] (Tracker.cc:533)
+        else c2 = more;
+        o2 = c2;
+      }
+      if (keep3 && c3) { seg_src[ns] = 3; seg_off[ns] = 0; seg_n[ns] = c3; seg_dst[ns] = dst; dst += c3; ns++; }
+      if (c2) { seg_src[ns] = 2; seg_off[ns] = 0; seg_n[ns] = c2; seg_dst[ns] = dst; dst += c2; ns++; }
+      ncoarse = dst;
+      ctl.try_coarse = 1;
+    } else ctl.try_coarse = 0;
+    ctl.n_coarse = ncoarse;
+    ctl.coarse_range = coarse_range;
+    ctl.did_coarse = 0;
+    // remaining level-3 points
+    const int nl3 = n3 - o3;
+    if (nl3) { seg_src[ns] = 3; seg_off[ns] = o3; seg_n[ns] = nl3; seg_dst[ns] = dst; dst += nl3; ns++; }
+    ctl.n_l3 = nl3;
+    int use = d.prm.max_patches_per_frame - dst;
+    if (use < 0) use = 0;
+    int nfine = 0;
+    const int cnt[3] = {n2 - o2, n1, n0};
+    const int off[3] = {o2, 0, 0};
+    for (int k = 0; k < 3; k++) {
+      int take = cnt[k];
+      if (take > use - nfine) take = use - nfine;
+      if (take > 0) { seg_src[ns] = 2 - k; seg_off[ns] = off[k]; seg_n[ns] = take; seg_dst[ns] = dst; dst += take; ns++; nfine += take; }
+    }
+    ctl.n_fine = nfine;
+    nseg = ns;
+  }
+  __syncthreads();
+  int* iter = d.p.iter_idx + (size_t)s * cap;
+  for (int k = 0; k < nseg; k++)
+    for (int j = threadIdx.x; j < seg_n[k]; j += blockDim.x)
+      iter[seg_dst[k] + j] = pvs[(size_t)seg_src[k] * cap + seg_off[k] + j];
+}
+
+// =============================================================================================
+// k_search — one warp per iteration-set entry.  stage 0: coarse set; stage 1: level-3 + fine sets.
+// =============================================================================================
+constexpr int kMaxSSD = 8 * 8 * 500;  // PatchFinder.cc:18-19
+
+PTAM_DEV double level_zero_pos(double p, int l) { return (p + 0.5) * (double)(1 << l) - 0.5; }
+PTAM_DEV double level_n_pos(double p, int l) { return (p + 0.5) / (double)(1 << l) - 0.5; }
+
+__global__ void __launch_bounds__(128) k_search(TrackerDev d, int stage) {
+  __shared__ uint8_t stmpl[4][64];
+  const int s = blockIdx.y;
+  StreamCtl& ctl = d.ctl[s];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int item = blockIdx.x * 4 + warp;
+  int begin, end;
+  if (stage == 0) { begin = 0; end = ctl.n_coarse; }
+  else { begin = ctl.n_coarse; end = ctl.n_coarse + ctl.n_l3 + ctl.n_fine; }
+  const int k = begin + item;
+  if (k >= end) return;
+  const int cap = d.p.cap;
+  const int idx = d.p.iter_idx[(size_t)s * cap + k];
+  const size_t g = (size_t)s * cap + idx;
+  int fl = d.p.flags[g];
+  unsigned range;
+  int subpix_its;
+  bool reproject;
+  if (stage == 0) { range = ctl.coarse_range; subpix_its = d.prm.coarse_subpix_its; reproject = false; }
+  else {
+    range = ctl.did_coarse ? 5 : 10;
+    const bool is_l3 = k < ctl.n_coarse + ctl.n_l3;
+    subpix_its = is_l3 ? 8 : 0;
+    reproject = is_l3 || ctl.did_coarse;
+  }
+  double v2image[2] = {d.p.v2image[2 * g], d.p.v2image[2 * g + 1]};
+  if (reproject) {
+    // ProjectAndDerivs with bFound == false: Project only (Tracker.h:89-94)
+    ProjOut o;
+    project_point(d, ctl.pose, d.p.world + 3 * g, o);
+    if (lane == 0) { d.p.v3cam[3 * g] = o.v3cam[0]; d.p.v3cam[3 * g + 1] = o.v3cam[1]; d.p.v3cam[3 * g + 2] = o.v3cam[2]; }
+    if (o.reached_cam) { v2image[0] = o.v2image[0]; v2image[1] = o.v2image[1]; }
+    fl = o.in_image ? (fl | F_IN_IMAGE) : (fl & ~F_IN_IMAGE);
+  }
+  const int sl = d.p.search_level[g];
+  // ---- MakeTemplateCoarseCont (PatchFinder.cc:98-127) ----------------------------------------
+  const double wi0 = d.p.warp_inv[4 * g], wi1 = d.p.warp_inv[4 * g + 1], wi2 = d.p.warp_inv[4 * g + 2], wi3 = d.p.warp_inv[4 * g + 3];
+  const double det = wi0 * wi3 - wi2 * wi1;
+  const double idet = 1.0 / det;
+  const double sc = (double)(1 << sl);
+  double m2[4];
+  m2[0] = (wi3 * idet) * sc; m2[3] = (wi0 * idet) * sc;
+  m2[2] = (-wi2 * idet) * sc; m2[1] = (-wi1 * idet) * sc;
+  bool refresh = !(fl & F_HAS_TEMPLATE);
+  if (!refresh) {
+    for (int i = 0; !refresh && i < 2; i++) {
+      const double d0 = m2[i] - d.p.last_warp[4 * g + i], d1 = m2[2 + i] - d.p.last_warp[4 * g + 2 + i];
+      if (d0 * d0 + d1 * d1 > 0.07 * 0.07) refresh = true;
+    }
+  }
+  // lane owns template pixels (row = lane/4, cols 2*(lane%4), +1)
+  const int trow = lane >> 2, tcol = (lane & 3) * 2;
+  int t0, t1, tsum, tsumsq;
+  if (refresh) {
+    const int kf = d.p.src_kf[g], slv = d.p.src_level[g];
+    const LevelDesc& SL = d.g.lev[slv];
+    const uint8_t* src = d.kf_ptrs[kf] + SL.img_off;
+    const int2 c = d.p.center[g];
+    // CVD::transform: p = inOrig + M (out - outOrig), accumulated across/down like libCVD
+    const double ax = m2[0], ay = m2[2];
+    const double crx = m2[1] - 8 * ax, cry = m2[3] - 8 * ay;
+    double px = (double)c.x - (m2[0] * 4.0 + m2[1] * 4.0), py = (double)c.y - (m2[2] * 4.0 + m2[3] * 4.0);
+    for (int i = 0; i < trow; i++) {
+      for (int j = 0; j < 8; j++) { px += ax; py += ay; }
+      px += crx; py += cry;
+    }
+    for (int j = 0; j < tcol; j++) { px += ax; py += ay; }
+    const double xb = (double)(SL.w - 1), yb = (double)(SL.h - 1);
+    int outside = 0;
+    int tv[2];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      if (0 <= px && 0 <= py && px < xb && py < yb) {
+        double x = px, y = py;
+        const int lx = (int)x, ly = (int)y;
+        x -= lx; y -= ly;
+        const uint8_t* r0 = src + (size_t)ly * SL.pitch + lx;
+        const uint8_t* r1 = r0 + SL.pitch;
+        const double v = (1 - y) * ((1 - x) * (double)r0[0] + x * (double)r0[1]) + y * ((1 - x) * (double)r1[0] + x * (double)r1[1]);
+        tv[q] = (int)(uint8_t)(int)v;
+      } else { tv[q] = 0; outside++; }
+      px += ax; py += ay;
+    }
+    t0 = tv[0]; t1 = tv[1];
+    outside = warp_sum_int(outside);
+    tsum = warp_sum_int(t0 + t1);
+    tsumsq = warp_sum_int(t0 * t0 + t1 * t1);
+    fl = outside ? (fl | F_TEMPLATE_BAD) : (fl & ~F_TEMPLATE_BAD);
+    fl |= F_HAS_TEMPLATE;
+    *reinterpret_cast<uchar2*>(d.p.tmpl + 64 * g + 2 * lane) = make_uchar2((uint8_t)t0, (uint8_t)t1);
+    if (lane == 0) {
+      d.p.tsum[g] = tsum; d.p.tsumsq[g] = tsumsq;
+      for (int q = 0; q < 4; q++) d.p.last_warp[4 * g + q] = m2[q];
+    }
+  } else {
+    const uchar2 t = *reinterpret_cast<const uchar2*>(d.p.tmpl + 64 * g + 2 * lane);
+    t0 = t.x; t1 = t.y;
+    tsum = d.p.tsum[g]; tsumsq = d.p.tsumsq[g];
+  }
+  if (fl & F_TEMPLATE_BAD) {  // Tracker.cc:873-876
+    fl &= ~(F_IN_IMAGE | F_FOUND);
+    if (lane == 0) { d.p.flags[g] = fl; d.p.v2image[2 * g] = v2image[0]; d.p.v2image[2 * g + 1] = v2image[1]; }
+    return;
+  }
+  if (lane == 0) atomicAdd(&ctl.attempted[sl], 1);
+  // ---- FindPatchCoarse (PatchFinder.cc:160-211) ------------------------------------------------
+  bool found = false;
+  double coarse[2] = {0, 0};
+  {
+    const int scale = 1 << sl;
+    const int posx = (int)v2image[0] / scale, posy = (int)v2image[1] / scale;
+    const unsigned r = (range + scale - 1) / scale;
+    int top = posy - (int)r;
+    const int bot1 = posy + (int)r + 1;
+    const int left = posx - (int)r, right = posx + (int)r;
+    const LevelDesc& L = d.g.lev[sl];
+    int pitch;
+    const uint8_t* im = level_image(d, s, sl, pitch);
+    if (top < 0) top = 0;
+    if (!(top >= L.h) && !(bot1 <= 0)) {
+      const int* lut = d.lut + (size_t)s * d.g.lut_stride + L.lut_off;
+      const int2* corners = d.corners + (size_t)s * d.g.corner_stride + L.corner_off;
+      const int i0 = lut[top];
+      const int i1 = bot1 >= L.h ? ctl.n_corners[sl] : lut[bot1];
+      int best_ssd = kMaxSSD + 1, bx = 0, by = 0;
+      for (int b0 = i0; b0 < i1; b0 += 32) {
+        const int i = b0 + lane;
+        int2 c = make_int2(0, 0);
+        bool pass = false;
+        if (i < i1) {
+          c = corners[i];
+          if (!(c.x < left || c.x > right)) {
+            const int ddx = posx - c.x, ddy = posy - c.y;
+            pass = !((unsigned)(ddx * ddx + ddy * ddy) > r * r);
+          }
+        }
+        unsigned m = __ballot_sync(kFull, pass);
+        while (m) {
+          const int src_lane = __ffs(m) - 1;
+          m &= m - 1;
+          const int cx = __shfl_sync(kFull, c.x, src_lane), cy = __shfl_sync(kFull, c.y, src_lane);
+          int ssd = kMaxSSD + 1;
+          if (cx >= 4 && cy >= 4 && cx < L.w - 4 && cy < L.h - 4) {  // in_image_with_border(ir, 4)
+            const uint8_t* ip = im + (size_t)(cy - 4 + trow) * pitch + (cx - 4 + tcol);
+            const int a = ip[0], b = ip[1];
+            const int isum = warp_sum_int(a + b);
+            const int isq = warp_sum_int(a * a + b * b);
+            const int cross = warp_sum_int(a * t0 + b * t1);
+            const int SA = tsum, SB = isum;
+            ssd = ((2 * SA * SB - SA * SA - SB * SB) / 64 + isq + tsumsq - 2 * cross);  // C++ truncating division
+          }
+          if (ssd < best_ssd) { best_ssd = ssd; bx = cx; by = cy; }
+        }
+      }
+      if (best_ssd < kMaxSSD) {
+        coarse[0] = level_zero_pos((double)bx, sl);
+        coarse[1] = level_zero_pos((double)by, sl);
+        found = true;
+      }
+    }
+  }
+  fl |= F_SEARCHED;
+  if (!found) {
+    fl &= ~F_FOUND;
+    if (lane == 0) { d.p.flags[g] = fl; d.p.v2image[2 * g] = v2image[0]; d.p.v2image[2 * g + 1] = v2image[1]; }
+    return;
+  }
+  fl |= F_FOUND;
+  double v2found[2] = {coarse[0], coarse[1]};
+  if (subpix_its > 0) {
+    fl |= F_SUBPIX;
+    // ---- MakeSubPixTemplate (PatchFinder.cc:219-240) -------------------------------------------
+    stmpl[warp][2 * lane] = (uint8_t)t0; stmpl[warp][2 * lane + 1] = (uint8_t)t1;
+    __syncwarp();
+    float jx[2] = {0.f, 0.f}, jy[2] = {0.f, 0.f};
+    int tq[2] = {0, 0};
+    double h00 = 0, h01 = 0, h02 = 0, h11 = 0, h12 = 0, h22 = 0;
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      const int pi = lane + 32 * q;
+      if (pi < 36) {
+        const int y = pi / 6 + 1, x = pi % 6 + 1;
+        const uint8_t* T = stmpl[warp];
+        const double gx = 0.5 * (double)((int)T[8 * y + x + 1] - (int)T[8 * y + x - 1]);
+        const double gy = 0.5 * (double)((int)T[8 * (y + 1) + x] - (int)T[8 * (y - 1) + x]);
+        jx[q] = (float)gx; jy[q] = (float)gy; tq[q] = T[8 * y + x];
+        h00 += gx * gx; h01 += gx * gy; h02 += gx; h11 += gy * gy; h12 += gy; h22 += 1.0;
+      }
+    }
+    double H[9], Hi[9];
+    H[0] = warp_sum(h00); H[1] = H[3] = warp_sum(h01); H[2] = H[6] = warp_sum(h02);
+    H[4] = warp_sum(h11); H[5] = H[7] = warp_sum(h12); H[8] = warp_sum(h22);
+    ldlt_inverse<3>(H, Hi);
+    double sp[2] = {coarse[0], coarse[1]};
+    double mean_diff = 0.0;
+    // ---- IterateSubPixToConvergence (PatchFinder.cc:250-318) -----------------------------------
+    const LevelDesc& L = d.g.lev[sl];
+    int pitch;
+    const uint8_t* im = level_image(d, s, sl, pitch);
+    bool converged = false;
+    for (int it = 0; it < subpix_its; it++) {
+      const double cx = level_n_pos(sp[0], sl), cy = level_n_pos(sp[1], sl);
+      const int rx = (int)(cx > 0.0 ? cx + 0.5 : cx - 0.5), ry = (int)(cy > 0.0 ? cy + 0.5 : cy - 0.5);
+      if (!(rx >= 5 && ry >= 5 && rx < L.w - 5 && ry < L.h - 5)) break;  // went off the image
+      const double bx = cx - 4, by = cy - 4;
+      const double dX = bx - floor(bx), dY = by - floor(by);
+      const float fTL = (float)((1.0 - dX) * (1.0 - dY));
+      const float fTR = (float)((dX) * (1.0 - dY));
+      const float fBL = (float)((1.0 - dX) * (dY));
+      const float fBR = (float)((dX) * (dY));
+      const int ibx = (int)bx, iby = (int)by;
+      double a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const int pi = lane + 32 * q;
+        if (pi < 36) {
+          const int y = pi / 6 + 1, x = pi % 6 + 1;
+          const uint8_t* tl = im + (size_t)(iby + y) * pitch + ibx + x;
+          const float fp = fTL * (float)tl[0] + fTR * (float)tl[1] + fBL * (float)tl[pitch] + fBR * (float)tl[pitch + 1];
+          const double diff = (double)(fp - (float)tq[q]) + mean_diff;
+          a0 += diff * (double)jx[q]; a1 += diff * (double)jy[q]; a2 += diff;
+        }
+      }
+      a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+      const double u0 = Hi[0] * a0 + Hi[1] * a1 + Hi[2] * a2;
+      const double u1 = Hi[3] * a0 + Hi[4] * a1 + Hi[5] * a2;
+      const double u2 = Hi[6] * a0 + Hi[7] * a1 + Hi[8] * a2;
+      sp[0] -= u0 * (double)(1 << sl);
+      sp[1] -= u1 * (double)(1 << sl);
+      mean_diff -= u2;
+      const double uu = u0 * u0 + u1 * u1;
+      if (uu < 0.03 * 0.03) { converged = true; break; }
+    }
+    if (!converged) {  // Tracker.cc:898-903
+      fl &= ~F_FOUND;
+      if (lane == 0) { d.p.flags[g] = fl; d.p.v2image[2 * g] = v2image[0]; d.p.v2image[2 * g + 1] = v2image[1]; }
+      return;
+    }
+    v2found[0] = sp[0]; v2found[1] = sp[1];
+  } else {
+    fl &= ~F_SUBPIX;
+  }
+  if (lane == 0) {
+    atomicAdd(&ctl.found[sl], 1);
+    d.p.flags[g] = fl;
+    d.p.v2image[2 * g] = v2image[0]; d.p.v2image[2 * g + 1] = v2image[1];
+    d.p.v2found[2 * g] = v2found[0]; d.p.v2found[2 * g + 1] = v2found[1];
+    d.p.sqrt_inv_noise[g] = 1.0 / (double)(1 << sl);
+  }
+}
+
+// =============================================================================================
+// k_pose — one CTA per stream.  stage 0: coarse-stage Gauss-Newton (Tracker.cc:552-568) when enough
+// coarse points were found; stage 1: the ten fine iterations (Tracker.cc:614-643), measurement
+// export statistics, UpdateMotionModel, AssessTrackingQuality.
+// =============================================================================================
+constexpr int kPoseThreads = 512;
+
+// exact k-th smallest (0-based) of the non-negative doubles keys[0..n) flagged valid: MSB-first
+// radix select on the IEEE bit patterns, 8 bits per pass.
+PTAM_DEV double block_select_kth(const double* keys, const int* valid_idx, int n, int kth, int* hist /*256*/, unsigned long long* sh_prefix, int* sh_k) {
+  if (threadIdx.x == 0) { *sh_prefix = 0ull; *sh_k = kth; }
+  __syncthreads();
+  for (int pass = 0; pass < 8; pass++) {
+    const int shift = 56 - 8 * pass;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const unsigned long long prefix = *sh_prefix;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned long long key = (unsigned long long)__double_as_longlong(keys[valid_idx[i]]);
+      if (pass == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&hist[(key >> shift) & 255], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int kk = *sh_k, b = 0;
+      while (b < 255 && kk >= hist[b]) { kk -= hist[b]; b++; }
+      *sh_k = kk;
+      *sh_prefix = prefix | ((unsigned long long)b << shift);
+    }
+    __syncthreads();
+  }
+  return __longlong_as_double((long long)*sh_prefix);
+}
+
+__global__ void __launch_bounds__(kPoseThreads) k_pose(TrackerDev d, int stage) {
+  __shared__ double pose[12];
+  __shared__ double red[16][27];
+  __shared__ double mu_s[6];
+  __shared__ int hist[256];
+  __shared__ unsigned long long sh_prefix;
+  __shared__ int sh_k;
+  __shared__ int sh_cnt[16];
+  __shared__ int nfound_s;
+  __shared__ double sigma_s;
+  const int s = blockIdx.x;
+  StreamCtl& ctl = d.ctl[s];
+  const int cap = d.p.cap;
+  const size_t gb = (size_t)s * cap;
+  const int* iter = d.p.iter_idx + gb;
+  double* e2 = d.p.e2 + gb;
+  int* fidx = d.p.pvs + (size_t)s * kLevels * cap;  // PVS lists are dead after selection: reuse as found-index scratch
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_set = stage == 0 ? ctl.n_coarse : ctl.n_coarse + ctl.n_l3 + ctl.n_fine;
+  const int est = d.prm.mestimator;
+
+  // compact the found entries (order preserved) once: the found set does not change during GN
+  if (threadIdx.x == 0) nfound_s = 0;
+  for (int i = threadIdx.x; i < 12; i += blockDim.x) pose[i] = ctl.pose[i];
+  __syncthreads();
+  for (int base = 0; base < n_set; base += blockDim.x) {
+    const int k = base + threadIdx.x;
+    bool f = false;
+    if (k < n_set) f = (d.p.flags[gb + iter[k]] & F_FOUND) != 0;
+    const unsigned b = __ballot_sync(kFull, f);
+    if (lane == 0) sh_cnt[warp] = __popc(b);
+    __syncthreads();
+    int before = nfound_s;
+    for (int wq = 0; wq < warp; wq++) before += sh_cnt[wq];
+    if (f) fidx[before + __popc(b & ((1u << lane) - 1))] = iter[k];
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int wq = 0; wq < (int)(blockDim.x >> 5); wq++) t += sh_cnt[wq]; nfound_s += t; }
+    __syncthreads();
+  }
+  const int nf = nfound_s;
+  bool run = true;
+  if (stage == 0) {
+    run = ctl.try_coarse && nf >= d.prm.coarse_min;
+    if (threadIdx.x == 0) ctl.did_coarse = run ? 1 : 0;
+  }
+  if (run) {
+    double last_mu[6] = {0, 0, 0, 0, 0, 0};
+    for (int it = 0; it < 10; it++) {
+      const bool nonlin = stage == 0 || it == 0 || it == 4 || it == 9;
+      const double override_sigma = it > 5 ? (stage == 0 ? 1.0 : 16.0) : 0.0;
+      const bool mark = stage == 1 && it == 9;
+      // per-point update: reprojection / linear update, Jacobian, scaled error
+      for (int i = threadIdx.x; i < nf; i += blockDim.x) {
+        const size_t g = gb + fidx[i];
+        double v2i[2] = {d.p.v2image[2 * g], d.p.v2image[2 * g + 1]};
+        if (it != 0) {
+          if (nonlin) {  // ProjectAndDerivs (Tracker.h:89-94)
+            ProjOut o;
+            project_point(d, pose, d.p.world + 3 * g, o);
+            d.p.v3cam[3 * g] = o.v3cam[0]; d.p.v3cam[3 * g + 1] = o.v3cam[1]; d.p.v3cam[3 * g + 2] = o.v3cam[2];
+            if (o.reached_cam) {
+              v2i[0] = o.v2image[0]; v2i[1] = o.v2image[1];
+              double dv[4];
+              cam_derivs(d.cam, o.q, dv);
+              for (int q = 0; q < 4; q++) d.p.derivs[4 * g + q] = dv[q];
+            }
+          } else {  // LinearUpdate (Tracker.h:139-142)
+            for (int r = 0; r < 2; r++) {
+              double a = 0;
+              for (int q = 0; q < 6; q++) a += d.p.J[12 * g + 6 * r + q] * last_mu[q];
+              v2i[r] += a;
+            }
+          }
+          d.p.v2image[2 * g] = v2i[0]; d.p.v2image[2 * g + 1] = v2i[1];
+        }
+        if (nonlin) {  // CalcJacobian (Tracker.h:125-136)
+          const double X = d.p.v3cam[3 * g], Y = d.p.v3cam[3 * g + 1], Z = d.p.v3cam[3 * g + 2];
+          const double ooz = 1.0 / Z;
+          const double dv0 = d.p.derivs[4 * g], dv1 = d.p.derivs[4 * g + 1], dv2 = d.p.derivs[4 * g + 2], dv3 = d.p.derivs[4 * g + 3];
+          const double gx[6] = {1, 0, 0, 0, Z, -Y}, gy[6] = {0, 1, 0, -Z, 0, X}, gz[6] = {0, 0, 1, Y, -X, 0};
+#pragma unroll
+          for (int m = 0; m < 6; m++) {
+            const double a0 = (gx[m] - X * gz[m] * ooz) * ooz;
+            const double a1 = (gy[m] - Y * gz[m] * ooz) * ooz;
+            d.p.J[12 * g + m] = dv0 * a0 + dv1 * a1;
+            d.p.J[12 * g + 6 + m] = dv2 * a0 + dv3 * a1;
+          }
+        }
+        const double sn = d.p.sqrt_inv_noise[g];
+        const double e0 = sn * (d.p.v2found[2 * g] - v2i[0]), e1 = sn * (d.p.v2found[2 * g + 1] - v2i[1]);
+        e2[fidx[i]] = e0 * e0 + e1 * e1;
+      }
+      __syncthreads();
+      double mu[6] = {0, 0, 0, 0, 0, 0};
+      if (nf > 0) {
+        double sigma2;
+        if (override_sigma > 0) sigma2 = override_sigma;
+        else {
+          const double med = block_select_kth(e2, fidx, nf, nf / 2, hist, &sh_prefix, &sh_k);
+          sigma2 = mest_sigma_from_median(med, nf, est);
+        }
+        // weighted normal equations (TooN WLS<6>::add_mJ twice per point)
+        double acc[27];
+#pragma unroll
+        for (int q = 0; q < 27; q++) acc[q] = 0;
+        for (int i = threadIdx.x; i < nf; i += blockDim.x) {
+          const size_t g = gb + fidx[i];
+          const double sn = d.p.sqrt_inv_noise[g];
+          const double e0 = sn * (d.p.v2found[2 * g] - d.p.v2image[2 * g]), e1 = sn * (d.p.v2found[2 * g + 1] - d.p.v2image[2 * g + 1]);
+          const double es = e0 * e0 + e1 * e1;
+          const double wgt = mest_weight(es, sigma2, est);
+          if (wgt == 0.0) { if (mark) d.p.outliers[g]++; continue; }
+          if (mark) d.p.inliers[g]++;
+#pragma unroll
+          for (int r = 0; r < 2; r++) {
+            double Jr[6], Jw[6];
+#pragma unroll
+            for (int q = 0; q < 6; q++) { Jr[q] = sn * d.p.J[12 * g + 6 * r + q]; Jw[q] = Jr[q] * wgt; }
+            const double er = r ? e1 : e0;
+            int c = 0;
+#pragma unroll
+            for (int a = 0; a < 6; a++) {
+#pragma unroll
+              for (int b = 0; b <= a; b++) acc[c++] += Jw[a] * Jr[b];
+            }
+#pragma unroll
+            for (int a = 0; a < 6; a++) acc[21 + a] += er * Jw[a];
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 27; q++) acc[q] = warp_sum(acc[q]);
+        if (lane == 0)
+#pragma unroll
+          for (int q = 0; q < 27; q++) red[warp][q] = acc[q];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          double tot[27];
+          for (int q = 0; q < 27; q++) { double t = 0; for (int wq = 0; wq < kPoseThreads / 32; wq++) t += red[wq][q]; tot[q] = t; }
+          double C[36], b[6], x[6];
+          int c = 0;
+          for (int a = 0; a < 6; a++)
+            for (int bb = 0; bb <= a; bb++) { C[6 * a + bb] = tot[c]; C[6 * bb + a] = tot[c]; c++; }
+          for (int a = 0; a < 6; a++) { C[7 * a] += 100.0; b[a] = tot[21 + a]; }  // add_prior(100)
+          ldlt_factor<6>(C);
+          ldlt_backsub<6>(C, b, x);
+          for (int a = 0; a < 6; a++) mu_s[a] = x[a];
+          (void)sigma_s;
+        }
+        __syncthreads();
+        for (int a = 0; a < 6; a++) mu[a] = mu_s[a];
+      }
+      // mse3CamFromWorld = SE3<>::exp(v6Update) * mse3CamFromWorld
+      if (threadIdx.x == 0) {
+        double ex[12], np[12];
+        se3_exp(mu, ex);
+        se3_mul(ex, pose, np);
+        for (int i = 0; i < 12; i++) pose[i] = np[i];
+      }
+      for (int a = 0; a < 6; a++) last_mu[a] = mu[a];
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x < 12) ctl.pose[threadIdx.x] = pose[threadIdx.x];
+  if (stage == 0) return;
+  // ---- scene depth (Tracker.cc:680-697) ---------------------------------------------------------
+  {
+    double sum = 0, sumsq = 0;
+    for (int i = threadIdx.x; i < nf; i += blockDim.x) {
+      const double z = d.p.v3cam[3 * (gb + fidx[i]) + 2];
+      sum += z; sumsq += z * z;
+    }
+    sum = warp_sum(sum); sumsq = warp_sum(sumsq);
+    __syncthreads();
+    if (lane == 0) { red[warp][0] = sum; red[warp][1] = sumsq; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double sum = 0, sumsq = 0;
+    for (int wq = 0; wq < kPoseThreads / 32; wq++) { sum += red[wq][0]; sumsq += red[wq][1]; }
+    ptam_tracker_state& st = ctl.st;
+    if (nf > 20) {
+      st.scene_depth_mean = sum / nf;
+      st.scene_depth_sigma = sqrt((sumsq / nf) - st.scene_depth_mean * st.scene_depth_mean);
+    }
+    // UpdateMotionModel (Tracker.cc:1035-1056)
+    double inv[12], rel[12], motion[6];
+    se3_inverse(ctl.start_pose, inv);
+    se3_mul(pose, inv, rel);
+    se3_ln(rel, motion);
+    if (d.prm.use_constant_velocity) for (int q = 0; q < 6; q++) st.velocity[q] = motion[q];
+    else for (int q = 0; q < 6; q++) st.velocity[q] = 0.9 * (0.5 * motion[q] + 0.5 * st.velocity[q]);
+    double m = 0;
+    for (int q = 0; q < 6; q++) {
+      double v = st.velocity[q];
+      if (q < 3) v *= 1.0 / st.scene_depth_mean;
+      m += v * v;
+    }
+    st.msd_scaled_velocity_magnitude = sqrt(m);
+    // AssessTrackingQuality (Tracker.cc:1062-1107)
+    int ta = 0, tf = 0, la = 0, lf = 0;
+    for (int l = 0; l < kLevels; l++) {
+      ta += ctl.attempted[l]; tf += ctl.found[l];
+      if (l >= 2) { la += ctl.attempted[l]; lf += ctl.found[l]; }
+    }
+    ctl.needs_kf_distance = 0;
+    if (tf == 0 || ta == 0) st.tracking_quality = 0;
+    else {
+      const double tfrac = (double)tf / ta;
+      const double lfrac = la > 10 ? (double)lf / la : tfrac;
+      if (tfrac > d.prm.quality_good) st.tracking_quality = 2;
+      else if (lfrac < d.prm.quality_lost) st.tracking_quality = 0;
+      else ctl.needs_kf_distance = 1;
+    }
+    if (st.tracking_quality == 0) st.lost_frames++; else st.lost_frames = 0;
+    for (int i = 0; i < 12; i++) st.se3_cam_from_world[i] = pose[i];
+  }
+}
+
+}  // namespace ptam

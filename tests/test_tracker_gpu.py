@@ -1,0 +1,184 @@
+"""GPU parity: CUDA path T (through the C-ABI) against the CPU oracle on the same inputs.
+Bar: bit-exact pyramid pixels, FAST corner lists (order included), row LUTs, search levels,
+template bytes, found flags and coarse patch positions; poses / sub-pixel positions to 1e-9."""
+import numpy as np
+import pytest
+
+from ptam_cg_b200 import synth
+from ptam_cg_b200.capi import Tracker, PT_FOUND, PT_SUBPIX
+
+pytestmark = pytest.mark.gpu
+
+POSE_TOL = 1e-9      # absolute, SE3 entries (rotation entries ~1, translations ~1)
+SUBPIX_TOL = 1e-6    # pixels (float32 arithmetic inside IterateSubPix, order of summation differs)
+
+
+def _compare_levels(a: Tracker, b: Tracker, stream=0):
+    for l in range(4):
+        pa, ca, la = a.get_level(stream, l)
+        pb, cb, lb = b.get_level(stream, l)
+        assert np.array_equal(pa, pb), f"level {l} pixels differ"
+        assert ca.shape == cb.shape and np.array_equal(ca, cb), f"level {l} corners differ ({len(ca)} vs {len(cb)})"
+        assert np.array_equal(la, lb), f"level {l} LUT differs"
+
+
+@pytest.mark.parametrize("shape", [(640, 480), (1280, 720), (321, 243), (64, 64), (200, 67)])
+def test_keyframe_lite_matches_oracle(oracle, product, shape):
+    w, h = shape
+    rng = np.random.default_rng(5)
+    tex = synth.make_texture(seed=3)
+    imgs = [
+        tex[100:100 + h, 200:200 + w].copy(),
+        rng.integers(0, 256, (h, w), dtype=np.uint8),
+        np.full((h, w), 77, np.uint8),
+        (rng.integers(0, 2, (h, w)) * 255).astype(np.uint8),
+    ]
+    o, p = Tracker(oracle, w, h), Tracker(product, w, h)
+    for im in imgs:
+        o.make_keyframes([im]); p.make_keyframes([im])
+        _compare_levels(o, p)
+
+
+def test_keyframe_batch_streams(oracle, product, seq640):
+    frames, _ = seq640
+    S = 5
+    o, p = Tracker(oracle, 640, 480, S), Tracker(product, 640, 480, S)
+    ims = [frames[3 * i] for i in range(S)]
+    o.make_keyframes(ims); p.make_keyframes(ims)
+    for s in range(S):
+        _compare_levels(o, p, s)
+
+
+def _setup(lib, kfs, m, S=1, **prm):
+    t = Tracker(lib, 640, 480, S, **prm)
+    for k in kfs:
+        t.add_keyframe(k)
+    for s in range(S):
+        t.set_map(s, m)
+    return t
+
+
+def _compare_frame(o, p, ro, rp, stream=0):
+    for f in ("meas_attempted", "meas_found", "n_corners", "n_pvs"):
+        assert list(getattr(ro, f)) == list(getattr(rp, f)), f
+    for f in ("did_coarse", "n_coarse", "n_level3", "n_fine", "tracking_quality", "quality_needs_kf_distance"):
+        assert getattr(ro, f) == getattr(rp, f), f
+    assert np.array_equal(o.get_iteration_set(stream), p.get_iteration_set(stream))
+    po, pp = o.get_points(stream), p.get_points(stream)
+    assert np.array_equal(po["level"], pp["level"])
+    assert np.array_equal(po["flags"], pp["flags"])
+    to, so = o.get_templates(stream)
+    tp, sp = p.get_templates(stream)
+    assert np.array_equal(to, tp), "template bytes differ"
+    assert np.array_equal(so, sp)
+    found = (po["flags"] & PT_FOUND) != 0
+    sub = (po["flags"] & PT_SUBPIX) != 0
+    coarse_only = found & ~sub
+    assert np.array_equal(po["v2_found"][coarse_only], pp["v2_found"][coarse_only]), "coarse patch positions differ"
+    np.testing.assert_allclose(pp["v2_found"][sub], po["v2_found"][sub], atol=SUBPIX_TOL, rtol=0)
+    np.testing.assert_allclose(pp["v2_image"], po["v2_image"], atol=1e-6, rtol=0)
+    np.testing.assert_allclose(np.array(rp.se3_cam_from_world), np.array(ro.se3_cam_from_world), atol=POSE_TOL, rtol=0)
+    np.testing.assert_allclose(rp.scene_depth_mean, ro.scene_depth_mean, atol=1e-9)
+    np.testing.assert_allclose(rp.scene_depth_sigma, ro.scene_depth_sigma, atol=1e-7)
+    assert np.array_equal(po["outliers"], pp["outliers"])
+    assert np.array_equal(po["inliers"], pp["inliers"])
+
+
+def test_track_frame_from_identical_state(oracle, product, seq640, map640):
+    """Every frame: both sides start from the oracle's state (per-step parity from identical state)."""
+    frames, poses = seq640
+    kfs, m = map640
+    o, p = _setup(oracle, kfs, m), _setup(product, kfs, m)
+    rng = np.random.default_rng(7)
+    start = synth.perturb_pose(poses[5], rng)
+    o.set_state(0, pose12=start); p.set_state(0, pose12=start)
+    n_coarse_frames = 0
+    for f in range(5, 30):
+        st = o.get_state(0)
+        p.set_state(0, state=st)
+        ro = o.track_frames([frames[f]])[0]
+        rp = p.track_frames([frames[f]])[0]
+        _compare_frame(o, p, ro, rp)
+        n_coarse_frames += ro.did_coarse
+        so, sp = o.get_state(0), p.get_state(0)
+        np.testing.assert_allclose(np.array(sp.velocity), np.array(so.velocity), atol=1e-9)
+        np.testing.assert_allclose(sp.msd_scaled_velocity_magnitude, so.msd_scaled_velocity_magnitude, atol=1e-9)
+        assert sum(ro.meas_found) > 200
+    assert n_coarse_frames > 5  # the coarse stage was exercised
+
+
+def test_track_sequence_free_running(oracle, product, seq640, map640):
+    """Whole run without re-synchronising.  A 1e-15 pose difference (f64 summation order) can flip
+    a discrete decision (template refresh at 0.07, ir() truncation, sub-pixel convergence) a few
+    frames later, after which the two runs use slightly different measurement sets; both must keep
+    tracking the same trajectory, so the poses are compared loosely (well inside tracker noise,
+    which is ~5e-4 against ground truth on this sequence)."""
+    frames, poses = seq640
+    kfs, m = map640
+    o, p = _setup(oracle, kfs, m), _setup(product, kfs, m)
+    start = synth.perturb_pose(poses[5], np.random.default_rng(7))
+    o.set_state(0, pose12=start); p.set_state(0, pose12=start)
+    worst = 0.0
+    for f in range(5, 40):
+        ro = o.track_frames([frames[f]])[0]
+        rp = p.track_frames([frames[f]])[0]
+        worst = max(worst, np.abs(np.array(rp.se3_cam_from_world) - np.array(ro.se3_cam_from_world)).max())
+        assert abs(sum(rp.meas_found) - sum(ro.meas_found)) <= 10
+    assert worst < 2e-4, worst
+    Rt, tt = synth.se3_from12(poses[39])
+    assert np.abs(np.array(rp.se3_cam_from_world)[9:] - tt).max() < 5e-3
+    assert np.abs(np.array(ro.se3_cam_from_world)[9:] - tt).max() < 5e-3
+
+
+def test_batched_streams_match_single(oracle, product, seq640, map640):
+    frames, poses = seq640
+    kfs, m = map640
+    S = 4
+    o, p = _setup(oracle, kfs, m, S), _setup(product, kfs, m, S)
+    rng = np.random.default_rng(11)
+    for s in range(S):
+        st = synth.perturb_pose(poses[6 + 2 * s], rng)
+        o.set_state(s, pose12=st, msd=0.01 * s); p.set_state(s, pose12=st, msd=0.01 * s)
+    ims = [frames[6 + 2 * s] for s in range(S)]
+    ro, rp = o.track_frames(ims), p.track_frames(ims)
+    for s in range(S):
+        _compare_frame(o, p, ro[s], rp[s], s)
+
+
+def test_settings_variants(oracle, product, seq640, map640):
+    frames, poses = seq640
+    kfs, m = map640
+    for prm in (dict(disable_coarse=1), dict(max_patches_per_frame=150), dict(coarse_max=10, coarse_min=5),
+                dict(mestimator=1), dict(mestimator=2), dict(use_constant_velocity=0)):
+        o, p = _setup(oracle, kfs, m, **prm), _setup(product, kfs, m, **prm)
+        start = synth.perturb_pose(poses[8], np.random.default_rng(3))
+        for t in (o, p):
+            t.set_state(0, pose12=start, msd=0.02, just_recovered=(1 if "coarse_max" in prm else 0))
+        ro, rp = o.track_frames([frames[8]])[0], p.track_frames([frames[8]])[0]
+        _compare_frame(o, p, ro, rp)
+
+
+def test_device_resident_frames(product, oracle, seq640, map640):
+    import torch
+    frames, poses = seq640
+    kfs, m = map640
+    S = 3
+    o, p = _setup(oracle, kfs, m, S), _setup(product, kfs, m, S)
+    start = synth.perturb_pose(poses[10], np.random.default_rng(1))
+    for s in range(S):
+        o.set_state(s, pose12=start); p.set_state(s, pose12=start)
+    ims = [frames[10], frames[10], frames[11]]
+    d = torch.from_numpy(np.stack(ims)).cuda()
+    torch.cuda.synchronize()
+    rp = p.track_frames_device(d.data_ptr(), 640 * 480, 640, want_results=True)
+    ro = o.track_frames(ims)
+    for s in range(S):
+        _compare_frame(o, p, ro[s], rp[s], s)
+
+
+def test_empty_map_and_no_cuda_fallback(product):
+    t = Tracker(product, 640, 480, 2)
+    im = np.zeros((480, 640), np.uint8)
+    r = t.track_frames([im, im])
+    assert sum(r[0].meas_attempted) == 0 and r[0].tracking_quality == 0
+    assert t.launch_count() > 0
