@@ -1,0 +1,418 @@
+#!/usr/bin/env python
+"""bench.py — tracker frames/s (+ BA lambda-trials/s) on B200, with roofline and CPU baseline.
+
+Workload at N=1 (BASELINE.json configs[1]): 640x480, 4-level pyramid, ~1000-point map, full
+TrackFrame (MakeKeyFrame_Lite + motion model + TrackMap + quality) for a batch of S independent
+streams per step.  One "step" = one TrackFrame for every stream of the batch.
+
+  value : whole-job frames/s with the frames already resident in HBM (device-resident batches,
+          CUDA events on the library's stream, max over ranks).
+  e2e   : the same through the C-ABI call a user makes, frames in pinned HOST memory, H2D of the
+          frames and D2H of the per-stream results inside the timed region.
+  roofline / cpu_baseline / clocks / gpu_launches: see DESIGN.md §Measurement.
+
+N>1 (torchrun): every rank runs its own S streams on its own GPU (replicas, no collective on the
+data path — SURVEY.md §8e path T), weak scaling; rank 0 prints the one JSON line.
+`--impl reference` times the CPU oracle port (the reference itself cannot be built here) on all
+host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+W, H = 640, 480
+FRAME_BYTES = W * H
+
+
+def pingpong(i, n):
+    p = i % (2 * n - 2)
+    return p if p < n else 2 * n - 2 - p
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            return float(d.get("hbm_gbs", 6650.0)), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """Polls NVML during the timed region (the region is tens of ms: nvidia-smi -lms is too slow)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def build_workload(detect_factory, n_frames, seed):
+    from ptam_cg_b200 import synth
+    frames, poses = synth.render_sequence(W, H, n_frames, seed=seed)
+    cam = synth.AtanCamera(W, H)
+    q = n_frames // 4
+    kfs, m = synth.build_map(frames, poses, detect_factory(), cam, kf_indices=(0, q, 2 * q, 3 * q))
+    return frames, poses, kfs, m
+
+
+def init_streams(trk, poses, offsets, n_frames, rng_seed=7):
+    from ptam_cg_b200 import synth
+    rng = np.random.default_rng(rng_seed)
+    for s, off in enumerate(offsets):
+        trk.set_state(s, pose12=synth.perturb_pose(poses[pingpong(off, n_frames)], rng),
+                      velocity=np.zeros(6), msd=0.0, depth_mean=1.0)
+
+
+def run_cpu_baseline(orc, kfs, m, frames, poses, budget_s=10.0):
+    """Oracle port, one core (the reference runs the tracker on one thread): single stream,
+    consecutive frames, for ~budget_s seconds."""
+    from ptam_cg_b200.capi import Tracker
+    t = Tracker(orc, W, H, 1)
+    for k in kfs:
+        t.add_keyframe(k)
+    t.set_map(0, m)
+    init_streams(t, poses, [0], len(frames))
+    for i in range(3):
+        t.track_frames([frames[pingpong(i, len(frames))]])
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < budget_s:
+        t.track_frames([frames[pingpong(3 + n, len(frames))]])
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "frames/s", "cores": 1, "kind": "port",
+            "sample": f"{n} consecutive TrackFrame calls, 1 stream, same frames/map as the GPU arm, {dt:.1f}s"}
+
+
+def reference_arm(args, rank, world):
+    """--impl reference: the CPU oracle port on all host threads (rank 0 only)."""
+    if rank != 0:
+        return
+    from oracle.binding import oracle_lib, detect_with
+    from ptam_cg_b200.capi import Tracker
+    orc = oracle_lib()
+    n_frames = args.frames
+    frames, poses, kfs, m = build_workload(lambda: detect_with(Tracker, orc, W, H), n_frames, 20260101)
+    threads = os.cpu_count() or 1
+    per_step = 4  # frames per thread per step (bounded sample of the S-stream batch)
+    trackers = []
+    for th in range(threads):
+        t = Tracker(orc, W, H, 1)
+        for k in kfs:
+            t.add_keyframe(k)
+        t.set_map(0, m)
+        init_streams(t, poses, [(3 * th) % (n_frames - 1)], n_frames, rng_seed=7 + th)
+        trackers.append(t)
+    pos = [0] * threads
+
+    def work(th):
+        t = trackers[th]
+        off = (3 * th) % (n_frames - 1)
+        for _ in range(per_step):
+            t.track_frames([frames[pingpong(off + pos[th], n_frames)]])
+            pos[th] += 1
+
+    def step():
+        ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+        for x in ths:
+            x.start()
+        for x in ths:
+            x.join()
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    n = args.steps * threads * per_step
+    val = n / dt
+    sample = f"{threads} threads x {per_step} TrackFrame per step (independent streams), {n} frames in {dt:.1f}s"
+    print(json.dumps({
+        "impl": "reference", "metric": "tracker frames/sec", "value": val, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32/f64",
+        "data": "synthetic",
+        "config": {"workload": "C2: 640x480 4-level pyramid, ~1000-point map, full TrackFrame", "map_points": int(len(m["src_kf"]))},
+        "cpu_baseline": {"value": val, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--streams", type=int, default=128, help="independent tracker streams per GPU (batch)")
+    ap.add_argument("--frames", type=int, default=64, help="distinct synthetic frames per trajectory")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ba", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from ptam_cg_b200.capi import Tracker, product_lib
+    from ptam_cg_b200 import capi
+    prod = product_lib()
+    S, K, Wm, F = args.streams, args.steps, args.warmup, args.frames
+
+    def detect_factory():
+        det_trk = Tracker(prod, W, H, 1, device=local)
+
+        def detect(image):
+            det_trk.make_keyframes([image])
+            return [det_trk.get_level(0, l)[:2] for l in range(4)]
+        return detect
+
+    frames, poses, kfs, m = build_workload(detect_factory, F, 20260101 + rank)
+    trk = Tracker(prod, W, H, S, device=local)
+    for k in kfs:
+        trk.add_keyframe(k)
+    for s in range(S):
+        trk.set_map(s, m)
+    offsets = [(5 * s) % (2 * F - 2) for s in range(S)]
+    n_steps = Wm + K
+
+    # ---- device-resident batches: step i reads its own S x 307 KB batch (never touched before) ----
+    frames_dev = torch.from_numpy(frames).cuda()
+    need = n_steps * S * FRAME_BYTES
+    if need > 48e9:
+        raise SystemExit("steps*streams too large for the resident frame set")
+    batches = []
+    for i in range(n_steps):
+        idx = torch.tensor([pingpong(o + i, F) for o in offsets], device="cuda")
+        batches.append(frames_dev.index_select(0, idx).contiguous())
+    torch.cuda.synchronize()
+    ext = torch.cuda.ExternalStream(trk.cuda_stream(), device=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ================= value: frames resident in HBM =================
+    init_streams(trk, poses, offsets, F)
+    for i in range(Wm):
+        trk.track_frames_device(batches[i].data_ptr(), FRAME_BYTES, W)
+    trk.synchronize()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = trk.launch_count()
+    with ClockSampler(local) as clk:
+        ev0.record(ext)
+        for i in range(Wm, n_steps):
+            trk.track_frames_device(batches[i].data_ptr(), FRAME_BYTES, W)
+        ev1.record(ext)
+        trk.synchronize()
+        torch.cuda.synchronize()
+    launches = trk.launch_count() - l0
+    ms = ev0.elapsed_time(ev1)
+    barrier()
+    last = trk.track_frames_device(batches[n_steps - 1].data_ptr(), FRAME_BYTES, W, want_results=True)
+    found = float(np.mean([sum(r.meas_found) for r in last]))
+    attempted = float(np.mean([sum(r.meas_attempted) for r in last]))
+    n_corners = float(np.mean([sum(r.n_corners) for r in last]))
+    tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_max = float(tms.item())
+    value = world * S * K / (ms_max * 1e-3)
+
+    # ================= e2e: pinned host frames through the C-ABI, results back every step ==========
+    host_frames = torch.from_numpy(frames).pin_memory()
+    base = host_frames.data_ptr()
+    init_streams(trk, poses, offsets, F)
+
+    def e2e_step(i):
+        ptrs = [base + pingpong(o + i, F) * FRAME_BYTES for o in offsets]
+        return trk.track_frames_ptrs(ptrs, W, want_results=True)
+
+    for i in range(Wm):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(Wm, n_steps):
+        res = e2e_step(i)
+    trk.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * S * K / float(te.item())
+    import ctypes
+    d2h = S * ctypes.sizeof(capi.TrackResult)
+
+    # ================= per-kernel device times (separate pass, events around every launch) =========
+    init_streams(trk, poses, offsets, F)
+    for i in range(Wm):
+        trk.track_frames_device(batches[i].data_ptr(), FRAME_BYTES, W)
+    trk.set_profiling(True)
+    for i in range(Wm, n_steps):
+        trk.track_frames_device(batches[i].data_ptr(), FRAME_BYTES, W)
+    kt = trk.kernel_times()
+    trk.set_profiling(False)
+    peak, peak_src = measured_peaks()
+    pyr_px = sum((W >> l) * (H >> l) for l in range(4))
+    alg = {  # algorithmic bytes per launch
+        "k_pyramid": S * pyr_px,
+        "k_fast": S * (pyr_px + pyr_px // 8),
+        "k_compact": S * (pyr_px // 8 + 8 * n_corners + 4 * sum(H >> l for l in range(4))),
+    }
+    per_kernel = {}
+    for k, (tot, n) in kt.items():
+        if n:
+            avg = tot / n
+            e = {"avg_ms": avg, "launches": int(n)}
+            if k in alg:
+                e["alg_bytes"] = float(alg[k])
+                e["gbs"] = alg[k] / (avg * 1e-3) / 1e9
+                e["frac_hbm"] = e["gbs"] / peak
+            per_kernel[k] = e
+    step_kernel_ms = sum(v["avg_ms"] for v in per_kernel.values())
+    top = max(per_kernel, key=lambda k: per_kernel[k]["avg_ms"])
+    traffic = None
+    tj = ROOT / "profiles" / "traffic.json"
+    if tj.exists():
+        try:
+            traffic = json.loads(tj.read_text()).get(top)
+        except Exception:
+            traffic = None
+    rl = {"kernel": top, "bound": "hbm", "achieved": per_kernel[top].get("gbs"), "peak": peak, "unit": "GB/s",
+          "frac": per_kernel[top].get("frac_hbm"), "traffic": traffic, "peak_source": peak_src,
+          "share_of_step": per_kernel[top]["avg_ms"] / step_kernel_ms}
+    a1_ms = sum(per_kernel[k]["avg_ms"] for k in ("k_pyramid", "k_fast", "k_compact") if k in per_kernel)
+    a1_bytes = S * (411600 + 8 * n_corners)
+    rl_a1 = {"kernels": "k_pyramid+k_fast+k_compact (SURVEY a1: pyramid+FAST+LUT)", "alg_bytes": a1_bytes,
+             "achieved": a1_bytes / (a1_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+             "frac": a1_bytes / (a1_ms * 1e-3) / 1e9 / peak}
+
+    # ================= single-stream latency (S=1, host frames, for the record) ====================
+    t1 = Tracker(prod, W, H, 1, device=local)
+    for k in kfs:
+        t1.add_keyframe(k)
+    t1.set_map(0, m)
+    init_streams(t1, poses, [0], F)
+    for i in range(5):
+        t1.track_frames_ptrs([base + pingpong(i, F) * FRAME_BYTES], W)
+    t0 = time.perf_counter()
+    nlat = 50
+    for i in range(5, 5 + nlat):
+        t1.track_frames_ptrs([base + pingpong(i, F) * FRAME_BYTES], W)
+    lat_ms = (time.perf_counter() - t0) / nlat * 1e3
+
+    out = {
+        "metric": "tracker frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K,
+        "warmup": Wm, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8/int32/f64", "data": "synthetic",
+        "config": {"workload": "C2: 640x480 4-level pyramid, ~1000-point map, full TrackFrame",
+                   "streams_per_gpu": S, "map_points": int(len(m["src_kf"])), "frames_per_step": world * S,
+                   "l2": f"inputs > L2: every step reads a distinct {S}x{FRAME_BYTES} B batch out of a "
+                         f"{n_steps * S * FRAME_BYTES / 1e6:.0f} MB resident set",
+                   "mean_found_per_frame": found, "mean_attempted_per_frame": attempted,
+                   "mean_corners_per_frame": n_corners},
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": S * FRAME_BYTES,
+                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * float(te.item()) / K},
+        "gpu_launches": int(launches),
+        "clocks": clk.summary(),
+        "roofline": rl, "roofline_a1_group": rl_a1, "kernels": per_kernel,
+        "single_stream_latency_ms": lat_ms,
+    }
+
+    # ================= BA (config C3) =================
+    if rank == 0 and not args.no_ba and prod.has("bundle_create"):
+        try:
+            from ptam_cg_b200.bench_ba import bench_ba
+            out["ba"] = bench_ba(prod, local)
+        except Exception as e:  # the tracker line must still be printed
+            out["ba"] = {"error": repr(e)}
+
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle.binding import oracle_lib
+        out["cpu_baseline"] = run_cpu_baseline(oracle_lib(), kfs, m, frames, poses)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -152,6 +152,12 @@ int ptam_tracker_synchronize(ptam_tracker* t);
 void* ptam_tracker_cuda_stream(ptam_tracker* t);
 /* Number of kernel launches issued by the handle so far. */
 int64_t ptam_tracker_launch_count(const ptam_tracker* t);
+/* Per-kernel device timing: when on, every launch is bracketed by CUDA events on the handle's
+ * stream and each call synchronises to accumulate them.  Kernel ids: 0 k_pyramid, 1 k_fast,
+ * 2 k_compact, 3 k_pvs_select, 4 k_search(coarse), 5 k_pose(coarse), 6 k_search(fine), 7 k_pose(fine).
+ * Turning it on or off resets the accumulators. */
+int ptam_tracker_set_profiling(ptam_tracker* t, int on);
+int ptam_tracker_get_kernel_times(ptam_tracker* t, double ms_total[8], int64_t launches[8]);
 
 /* Read back the current frame's keyframe level of one stream (Level, KeyFrame.h:55-125):
  * pixels (w*h, may be NULL), corners as interleaved (x,y) int32 in raster order (cap pairs, may be

@@ -84,8 +84,11 @@ BUNDLE_SYMBOLS = [
 # exported by the product only (CUDA plumbing)
 PRODUCT_ONLY_SYMBOLS = [
     "global_last_error", "tracker_track_frames_device", "tracker_cuda_stream",
-    "tracker_launch_count", "bundle_cuda_stream", "bundle_launch_count",
+    "tracker_launch_count", "tracker_set_profiling", "tracker_get_kernel_times",
+    "bundle_cuda_stream", "bundle_launch_count",
 ]
+TRACKER_KERNELS = ["k_pyramid", "k_fast", "k_compact", "k_pvs_select", "k_search_coarse", "k_pose_coarse",
+                   "k_search_fine", "k_pose_fine"]
 
 
 def _dp(a):
@@ -145,6 +148,8 @@ class Lib:
             "tracker_synchronize": (i, [vp]),
             "tracker_cuda_stream": (vp, [vp]),
             "tracker_launch_count": (C.c_int64, [vp]),
+            "tracker_set_profiling": (i, [vp, i]),
+            "tracker_get_kernel_times": (i, [vp, P(d), P(C.c_int64)]),
             "tracker_get_level": (i, [vp, i, i, P(C.c_uint8), P(C.c_int32), i, P(C.c_int32)]),
             "tracker_level_size": (i, [vp, i, P(i), P(i)]),
             "tracker_get_points": (i, [vp, i, P(C.c_int32), P(C.c_int32), P(d), P(d), P(C.c_int32), P(C.c_int32)]),
@@ -297,6 +302,23 @@ class Tracker:
 
     def launch_count(self):
         return int(self.lib.fn("tracker_launch_count")(self.h))
+
+    def set_profiling(self, on):
+        self._chk(self.lib.fn("tracker_set_profiling")(self.h, int(on)))
+
+    def kernel_times(self):
+        """{kernel name: (total ms, launches)} accumulated since set_profiling(True)."""
+        ms = (C.c_double * 8)()
+        n = (C.c_int64 * 8)()
+        self._chk(self.lib.fn("tracker_get_kernel_times")(self.h, ms, n))
+        return {k: (ms[j], n[j]) for j, k in enumerate(TRACKER_KERNELS)}
+
+    def track_frames_ptrs(self, ptrs, stride, want_results=True):
+        """track_frames on raw host pointers (e.g. pinned torch tensors), one per stream."""
+        arr = (C.c_void_p * self.S)(*ptrs)
+        res = (TrackResult * self.S)() if want_results else None
+        self._chk(self.lib.fn("tracker_track_frames")(self.h, arr, stride, res))
+        return list(res) if want_results else None
 
     def level_size(self, level):
         w, h = C.c_int(), C.c_int()

@@ -84,6 +84,11 @@ struct ptam_tracker {
   uint8_t* h_stage = nullptr;
   StreamCtl* h_ctl = nullptr;
   cudaEvent_t stage_ev = nullptr;  // staging buffer is free again once this has fired
+  // optional per-kernel timing (CUDA events on the handle's stream around every launch)
+  bool profiling = false;
+  cudaEvent_t prof_ev[16] = {};
+  double prof_ms[8] = {};
+  int64_t prof_n[8] = {};
   int max_h = 0;
 
   void set_error(const std::string& e) { err = e; g_last_error = e; }
@@ -98,6 +103,7 @@ struct ptam_tracker {
     tsum.free(); tsumsq.free(); flags.free(); level.free(); search_level.free(); outliers.free(); inliers.free();
     pvs.free(); iter_idx.free(); center.free(); tmpl.free();
     if (stage_ev) cudaEventDestroy(stage_ev);
+    for (auto e : prof_ev) if (e) cudaEventDestroy(e);
     if (h_stage) cudaFreeHost(h_stage);
     if (h_ctl) cudaFreeHost(h_ctl);
     if (stream) cudaStreamDestroy(stream);
@@ -197,9 +203,24 @@ struct ptam_tracker {
     return cudaSuccess;
   }
 
+  static bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+  }
+
   int upload_images(const uint8_t* const* images, int stride, uint8_t* dst, size_t dst_stream_pitch, int n) {
-    // pack into pinned staging with the library pitch, then one async H2D
     const LevelDesc& L0 = dev.g.lev[0];
+    // page-locked caller buffers (cudaHostAlloc / cudaHostRegister): DMA straight from them
+    bool pinned = true;
+    for (int s = 0; s < n && pinned; s++) pinned = is_pinned(images[s]);
+    if (pinned) {
+      for (int s = 0; s < n; s++)
+        PTAM_CUDA_TRY(this, cudaMemcpy2DAsync(dst + (size_t)s * dst_stream_pitch, L0.pitch, images[s], stride, W, H,
+                                              cudaMemcpyHostToDevice, stream));
+      return PTAM_OK;
+    }
+    // pageable memory: pack into the pinned staging buffer with the library pitch, then async H2D
     PTAM_CUDA_TRY(this, cudaEventSynchronize(stage_ev));
     for (int s = 0; s < n; s++) {
       uint8_t* o = h_stage + (size_t)s * dst_stream_pitch;
@@ -212,31 +233,44 @@ struct ptam_tracker {
     return PTAM_OK;
   }
 
-  int launch_keyframe(const TrackerDev& d) {
-    const LevelDesc& L0 = d.g.lev[0];
-    dim3 gp((L0.w + 63) / 64, (L0.h + 63) / 64, S);
-    k_pyramid<<<gp, 256, 0, stream>>>(d);
-    k_fast<<<dim3(d.g.fast_tiles, S), 256, 0, stream>>>(d);
-    k_compact<<<dim3(kLevels, S), 1024, (max_h + 1) * sizeof(int), stream>>>(d);
-    launches += 3;
-    PTAM_CUDA_TRY(this, cudaGetLastError());
+  void pbegin(int k) { if (profiling) cudaEventRecord(prof_ev[2 * k], stream); }
+  void pend(int k) { if (profiling) cudaEventRecord(prof_ev[2 * k + 1], stream); launches++; }
+  int pcollect(unsigned used) {
+    if (!profiling) return PTAM_OK;
+    PTAM_CUDA_TRY(this, cudaStreamSynchronize(stream));
+    for (int k = 0; k < 8; k++)
+      if (used & (1u << k)) {
+        float ms = 0;
+        PTAM_CUDA_TRY(this, cudaEventElapsedTime(&ms, prof_ev[2 * k], prof_ev[2 * k + 1]));
+        prof_ms[k] += ms; prof_n[k]++;
+      }
     return PTAM_OK;
   }
 
+  int launch_keyframe(const TrackerDev& d, bool collect = true) {
+    const LevelDesc& L0 = d.g.lev[0];
+    dim3 gp((L0.w + 63) / 64, (L0.h + 63) / 64, S);
+    pbegin(0); k_pyramid<<<gp, 256, 0, stream>>>(d); pend(0);
+    pbegin(1); k_fast<<<dim3(d.g.fast_tiles, S), 256, 0, stream>>>(d); pend(1);
+    pbegin(2); k_compact<<<dim3(kLevels, S), 1024, (max_h + 1) * sizeof(int), stream>>>(d); pend(2);
+    PTAM_CUDA_TRY(this, cudaGetLastError());
+    return collect ? pcollect(7u) : PTAM_OK;
+  }
+
   int launch_track(const TrackerDev& d) {
-    int rc = launch_keyframe(d);
+    int rc = launch_keyframe(d, false);
     if (rc) return rc;
     int maxn = 0;
     for (int s = 0; s < S; s++) maxn = std::max(maxn, h_pt_count[s]);
-    k_pvs_select<<<S, 1024, 0, stream>>>(d);
+    unsigned used = 7u | 8u | 32u | 128u;
+    pbegin(3); k_pvs_select<<<S, 1024, 0, stream>>>(d); pend(3);
     const int coarse_items = std::min(maxn, 2 * std::max(0, d.prm.coarse_max));
-    if (coarse_items > 0) k_search<<<dim3((coarse_items + 3) / 4, S), 128, 0, stream>>>(d, 0);
-    k_pose<<<S, kPoseThreads, 0, stream>>>(d, 0);
-    if (maxn > 0) k_search<<<dim3((maxn + 3) / 4, S), 128, 0, stream>>>(d, 1);
-    k_pose<<<S, kPoseThreads, 0, stream>>>(d, 1);
-    launches += 3 + (coarse_items > 0) + (maxn > 0);
+    if (coarse_items > 0) { pbegin(4); k_search<<<dim3((coarse_items + 3) / 4, S), 128, 0, stream>>>(d, 0); pend(4); used |= 16u; }
+    pbegin(5); k_pose<<<S, kPoseThreads, 0, stream>>>(d, 0); pend(5);
+    if (maxn > 0) { pbegin(6); k_search<<<dim3((maxn + 3) / 4, S), 128, 0, stream>>>(d, 1); pend(6); used |= 64u; }
+    pbegin(7); k_pose<<<S, kPoseThreads, 0, stream>>>(d, 1); pend(7);
     PTAM_CUDA_TRY(this, cudaGetLastError());
-    return PTAM_OK;
+    return pcollect(used);
   }
 
   int fetch_results(ptam_track_result* results) {
@@ -402,6 +436,19 @@ int ptam_tracker_synchronize(ptam_tracker* t) {
 }
 void* ptam_tracker_cuda_stream(ptam_tracker* t) { return (void*)t->stream; }
 int64_t ptam_tracker_launch_count(const ptam_tracker* t) { return t->launches; }
+
+int ptam_tracker_set_profiling(ptam_tracker* t, int on) {
+  cudaSetDevice(t->device);
+  if (on && !t->prof_ev[0])
+    for (auto& e : t->prof_ev) PTAM_CUDA_TRY(t, cudaEventCreate(&e));
+  t->profiling = on != 0;
+  for (int k = 0; k < 8; k++) { t->prof_ms[k] = 0; t->prof_n[k] = 0; }
+  return PTAM_OK;
+}
+int ptam_tracker_get_kernel_times(ptam_tracker* t, double* ms_total, int64_t* launches) {
+  for (int k = 0; k < 8; k++) { ms_total[k] = t->prof_ms[k]; launches[k] = t->prof_n[k]; }
+  return PTAM_OK;
+}
 
 int ptam_tracker_level_size(const ptam_tracker* t, int level, int* w, int* h) {
   if (level < 0 || level >= kLevels) return PTAM_ERR_INVALID;
