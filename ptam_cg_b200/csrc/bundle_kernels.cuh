@@ -1,2 +1,610 @@
+// sm_100a kernels of path B (Bundle::Compute, reference src/Bundle.cc:209-551).
+//
+// per LM step      k_ba_project      ProjectAndFindSquaredError per measurement (Bundle.cc:219-225)
+//                  k_ba_select       exact order statistic of the squared errors (sigma^2, :230-237)
+//                  k_ba_jacobian     weights, A (2x6), B (2x3), W = A^T B, warp-aggregated f64 atomics
+//                                    into U / epsA (per camera) and V / epsB (per point) (:251-332)
+// per lambda trial k_ba_vinv         V*_i^-1 by 3x3 LDL^T (:341-359)
+//                  k_ba_init_s       S diagonal blocks <- U*, vE <- epsA (:374-392)
+//                  k_ba_schur        warp per point: S_jk -= W_ij V*^-1 W_ik^T, vE_j -= W_ij V*^-1 epsB
+//                                    (:396-446) with atomics into the dense lower triangle
+//                  k_ldlt_*          blocked square-root-free LDL^T of S + k_ldlt_solve (:457-458)
+//                  k_ba_point_update delta_b_i (:461-483), k_ba_cam_update exp(delta_a) (:496-504)
+//                  k_ba_new_error    FindNewError (:188-207)
 #pragma once
 #include "common.cuh"
+#include "../../include/ptam_b200.h"
+
+namespace ptam {
+
+enum : int { M_ALIVE = 0, M_BAD = 1, M_ERASED = 2 };
+
+struct BundleDev {
+  CamModel cam;
+  int n_cams, n_pts, n_meas, n;  // n = 6 * non-fixed cameras
+  int est;
+  // cameras
+  double* cam_se3;      // [C][12]
+  double* cam_se3_new;  // [C][12]
+  const int* cam_fixed; // [C]
+  const int* cam_row;   // [C] start row or -1
+  double* U;            // [C][21] lower triangle, row-major packed
+  double* epsA;         // [C][6]
+  // points
+  double* pt_pos;       // [P][3]
+  double* pt_pos_new;   // [P][3]
+  double* V;            // [P][6] lower triangle packed (00,10,11,20,21,22)
+  double* epsB;         // [P][3]
+  double* Vinv;         // [P][9]
+  double* Ve;           // [P][3]  V*^-1 epsB
+  const int* pt_off;    // [P+1] CSR by point (measurement ids sorted by camera id)
+  const int* pt_meas;   // [M]
+  // measurements (insertion order)
+  const int* m_cam; const int* m_pt;
+  const double* m_found;  // [M][2]
+  const double* m_sin;    // [M] dSqrtInvNoise
+  int* m_state;           // [M]
+  double* m_v3cam;        // [M][3]
+  double* m_derivs;       // [M][4]
+  double* m_eps;          // [M][2]
+  double* m_e2;           // [M]
+  double* m_W;            // [M][18]
+  double* e2_compact;     // [M] squared errors of the non-bad measurements
+  // reduced system
+  double* S;   // [n][n] (lower triangle valid; mirrored on request)
+  double* vE;  // [n]
+  double* upd; // [n] camera update
+  // scalars: 0 n_valid (as double), 1 sigma^2, 2 current error, 3 new error, 4 sum sq update,
+  //          5 lambda, 6 median
+  double* scal;
+  int* counters;  // 0 n_valid, 1 n_outliers_total, 2 n_bad_this_step
+  int* outliers;  // [M][2] (point, camera) in erase order
+};
+
+PTAM_DEV double block_sum(double v, double* sh /*32*/) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  double t = 0;
+  if (warp == 0) {
+    t = lane < (int)(blockDim.x >> 5) ? sh[lane] : 0.0;
+    t = warp_sum(t);
+  }
+  return t;  // valid in warp 0
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ba_project(BundleDev d) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= d.n_meas) return;
+  if (d.m_state[m] == M_ERASED) return;
+  const int c = d.m_cam[m], p = d.m_pt[m];
+  double v3[3];
+  se3_apply(d.cam_se3 + 12 * c, d.pt_pos + 3 * p, v3);
+  d.m_v3cam[3 * m] = v3[0]; d.m_v3cam[3 * m + 1] = v3[1]; d.m_v3cam[3 * m + 2] = v3[2];
+  if (v3[2] <= 0) { d.m_state[m] = M_BAD; return; }
+  d.m_state[m] = M_ALIVE;
+  const CamProj q = cam_project(d.cam, v3[0] / v3[2], v3[1] / v3[2]);
+  double dv[4];
+  cam_derivs(d.cam, q, dv);
+  for (int k = 0; k < 4; k++) d.m_derivs[4 * m + k] = dv[k];
+  const double s = d.m_sin[m];
+  const double e0 = s * (d.m_found[2 * m] - q.im[0]), e1 = s * (d.m_found[2 * m + 1] - q.im[1]);
+  d.m_eps[2 * m] = e0; d.m_eps[2 * m + 1] = e1;
+  d.m_e2[m] = e0 * e0 + e1 * e1;
+}
+
+// compaction of the valid squared errors (order irrelevant for an order statistic)
+__global__ void __launch_bounds__(256) k_ba_gather_e2(BundleDev d) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool ok = m < d.n_meas && d.m_state[m] == M_ALIVE;
+  const unsigned b = __ballot_sync(kFull, ok);
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == 0 && b) base = atomicAdd(&d.counters[0], __popc(b));
+  base = __shfl_sync(kFull, base, 0);
+  if (ok) d.e2_compact[base + __popc(b & ((1u << lane) - 1))] = d.m_e2[m];
+}
+
+// sigma^2 = MEstimator::FindSigmaSquared (Tools.h:152-162), clamped to MinTukeySigma^2 (Bundle.cc:234-237).
+// One CTA: MSB-first radix select (8 bits per pass) of element n/2 on the IEEE bit patterns.
+__global__ void __launch_bounds__(1024) k_ba_select(BundleDev d, double min_sigma_sq) {
+  __shared__ int hist[256];
+  __shared__ unsigned long long prefix;
+  __shared__ int kk;
+  const int n = d.counters[0];
+  if (threadIdx.x == 0) { prefix = 0ull; kk = n / 2; }
+  __syncthreads();
+  for (int pass = 0; pass < 8 && n > 0; pass++) {
+    const int shift = 56 - 8 * pass;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const unsigned long long pf = prefix;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned long long key = (unsigned long long)__double_as_longlong(d.e2_compact[i]);
+      if (pass == 0 || (key >> (shift + 8)) == (pf >> (shift + 8))) atomicAdd(&hist[(key >> shift) & 255], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int k = kk, b = 0;
+      while (b < 255 && k >= hist[b]) { k -= hist[b]; b++; }
+      kk = k;
+      prefix = pf | ((unsigned long long)b << shift);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double med = __longlong_as_double((long long)prefix);
+    double s2 = mest_sigma_from_median(med, n, d.est);
+    if (s2 < min_sigma_sq) s2 = min_sigma_sq;
+    d.scal[6] = med;
+    d.scal[1] = s2;
+    d.scal[0] = (double)n;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_ba_jacobian — one thread per observation.  Camera accumulators: measurements usually arrive
+// camera-major (MapMaker.cc:871-882), so a whole warp mostly shares one camera: warp-reduce the 27
+// values and issue one atomic per value; otherwise per-lane atomics.  Point accumulators: per-lane
+// atomics (a point's few observations are scattered over warps).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_ba_jacobian(BundleDev d) {
+  __shared__ double sh[32];
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const double sigma2 = d.scal[1];
+  double err = 0.0;
+  bool active = false;
+  int c = -1;
+  double A[12], eps[2] = {0, 0};
+#pragma unroll
+  for (int i = 0; i < 12; i++) A[i] = 0;
+  bool cam_free = false;
+  if (m < d.n_meas && d.m_state[m] != M_ERASED) {
+    if (d.m_state[m] == M_BAD) err = 1.0;
+    else {
+      const double e2 = d.m_e2[m];
+      const double w = mest_sqrt_weight(e2, sigma2, d.est);
+      eps[0] = w * d.m_eps[2 * m]; eps[1] = w * d.m_eps[2 * m + 1];
+      d.m_eps[2 * m] = eps[0]; d.m_eps[2 * m + 1] = eps[1];
+      if (w == 0) { d.m_state[m] = M_BAD; err = 1.0; }
+      else {
+        active = true;
+        err = mest_objective(e2, sigma2, d.est);
+        c = d.m_cam[m];
+        const int p = d.m_pt[m];
+        const double s = d.m_sin[m];
+        const double d0 = s * (w * d.m_derivs[4 * m]), d1 = s * (w * d.m_derivs[4 * m + 1]);
+        const double d2 = s * (w * d.m_derivs[4 * m + 2]), d3 = s * (w * d.m_derivs[4 * m + 3]);
+        const double X = d.m_v3cam[3 * m], Y = d.m_v3cam[3 * m + 1], Z = d.m_v3cam[3 * m + 2];
+        const double ooz = 1.0 / Z;
+        cam_free = !d.cam_fixed[c];
+        if (cam_free) {
+          const double gx[6] = {1, 0, 0, 0, Z, -Y}, gy[6] = {0, 1, 0, -Z, 0, X}, gz[6] = {0, 0, 1, Y, -X, 0};
+#pragma unroll
+          for (int q = 0; q < 6; q++) {
+            const double a0 = (gx[q] - X * gz[q] * ooz) * ooz, a1 = (gy[q] - Y * gz[q] * ooz) * ooz;
+            A[q] = d0 * a0 + d1 * a1;
+            A[6 + q] = d2 * a0 + d3 * a1;
+          }
+        }
+        double B[6];
+        const double* R = d.cam_se3 + 12 * c;
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+          const double a0 = (R[q] - X * R[6 + q] * ooz) * ooz, a1 = (R[3 + q] - Y * R[6 + q] * ooz) * ooz;
+          B[q] = d0 * a0 + d1 * a1;
+          B[3 + q] = d2 * a0 + d3 * a1;
+        }
+        // V (lower, packed) and epsB: per-lane atomics
+        double* Vp = d.V + 6 * p;
+        int o = 0;
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+          for (int cc = 0; cc <= r; cc++) atomicAdd(&Vp[o++], B[r] * B[cc] + B[3 + r] * B[3 + cc]);
+#pragma unroll
+        for (int r = 0; r < 3; r++) atomicAdd(&d.epsB[3 * p + r], B[r] * eps[0] + B[3 + r] * eps[1]);
+        // W = A^T B (6x3), zero for a fixed camera
+        double* Wm = d.m_W + 18 * m;
+#pragma unroll
+        for (int r = 0; r < 6; r++)
+#pragma unroll
+          for (int cc = 0; cc < 3; cc++) Wm[3 * r + cc] = A[r] * B[cc] + A[6 + r] * B[3 + cc];
+      }
+    }
+  }
+  // camera accumulators U (lower, packed 21) and epsA (6)
+  const int c_acc = (active && cam_free) ? c : -1;
+  const int c0 = __shfl_sync(kFull, c_acc, 0);
+  const bool uniform = __all_sync(kFull, c_acc == c0);
+  if (uniform) {
+    if (c0 >= 0) {
+      int o = 0;
+#pragma unroll
+      for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int cc = 0; cc <= r; cc++) {
+          const double v = warp_sum(A[r] * A[cc] + A[6 + r] * A[6 + cc]);
+          if (lane == 0) atomicAdd(&d.U[21 * c0 + o], v);
+          o++;
+        }
+#pragma unroll
+      for (int r = 0; r < 6; r++) {
+        const double v = warp_sum(A[r] * eps[0] + A[6 + r] * eps[1]);
+        if (lane == 0) atomicAdd(&d.epsA[6 * c0 + r], v);
+      }
+    }
+  } else if (c_acc >= 0) {
+    int o = 0;
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+      for (int cc = 0; cc <= r; cc++) atomicAdd(&d.U[21 * c_acc + o++], A[r] * A[cc] + A[6 + r] * A[6 + cc]);
+#pragma unroll
+    for (int r = 0; r < 6; r++) atomicAdd(&d.epsA[6 * c_acc + r], A[r] * eps[0] + A[6 + r] * eps[1]);
+  }
+  const double t = block_sum(err, sh);
+  if (threadIdx.x == 0 && t != 0.0) atomicAdd(&d.scal[2], t);
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ba_vinv(BundleDev d) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.n_pts) return;
+  const double lambda = d.scal[5];
+  const double* v = d.V + 6 * i;
+  double Vs[9] = {v[0], v[1], v[3], v[1], v[2], v[4], v[3], v[4], v[5]};
+  double inv[9];
+  if (Vs[0] * Vs[4] * Vs[8] == 0) {
+#pragma unroll
+    for (int k = 0; k < 9; k++) inv[k] = 0;
+  } else {
+    Vs[0] *= (1.0 + lambda); Vs[4] *= (1.0 + lambda); Vs[8] *= (1.0 + lambda);
+    ldlt_inverse<3>(Vs, inv);
+  }
+#pragma unroll
+  for (int k = 0; k < 9; k++) d.Vinv[9 * i + k] = inv[k];
+  const double* e = d.epsB + 3 * i;
+#pragma unroll
+  for (int r = 0; r < 3; r++) d.Ve[3 * i + r] = inv[3 * r] * e[0] + inv[3 * r + 1] * e[1] + inv[3 * r + 2] * e[2];
+}
+
+// S <- 0 except diagonal blocks U*_j (lambda-damped, both triangles); vE <- epsA
+__global__ void __launch_bounds__(256) k_ba_init_s(BundleDev d) {
+  const size_t tot = (size_t)d.n * d.n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x) d.S[i] = 0.0;
+}
+__global__ void __launch_bounds__(64) k_ba_init_diag(BundleDev d) {
+  const int c = blockIdx.x;
+  const int row = d.cam_row[c];
+  if (row < 0) return;
+  const double lambda = d.scal[5];
+  const int t = threadIdx.x;
+  if (t < 36) {
+    const int r = t / 6, cc = t % 6;
+    const int a = r >= cc ? r : cc, b = r >= cc ? cc : r;
+    double v = d.U[21 * c + a * (a + 1) / 2 + b];
+    if (r == cc) v *= (1.0 + lambda);
+    d.S[(size_t)(row + r) * d.n + row + cc] = v;
+  } else if (t < 42) d.vE[row + t - 36] = d.epsA[6 * c + t - 36];
+}
+
+// warp per point: all camera pairs (j >= k) observing it, both cameras free, both measurements good
+__global__ void __launch_bounds__(256) k_ba_schur(BundleDev d) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= d.n_pts) return;
+  const int lane = threadIdx.x & 31;
+  const int o0 = d.pt_off[i], k = d.pt_off[i + 1] - o0;
+  if (k == 0) return;
+  double Vi[9];
+#pragma unroll
+  for (int q = 0; q < 9; q++) Vi[q] = d.Vinv[9 * i + q];
+  const int npairs = k * (k + 1) / 2;
+  for (int pr = lane; pr < npairs; pr += 32) {
+    // pr -> (a, b), b <= a
+    int a = (int)((sqrt(8.0 * pr + 1.0) - 1.0) * 0.5);
+    while (a * (a + 1) / 2 > pr) a--;
+    while ((a + 1) * (a + 2) / 2 <= pr) a++;
+    const int b = pr - a * (a + 1) / 2;
+    const int mj = d.pt_meas[o0 + a], mk = d.pt_meas[o0 + b];
+    if (d.m_state[mj] != M_ALIVE || d.m_state[mk] != M_ALIVE) continue;
+    const int jrow = d.cam_row[d.m_cam[mj]], krow = d.cam_row[d.m_cam[mk]];
+    if (jrow < 0 || krow < 0) continue;
+    const double* Wj = d.m_W + 18 * mj;
+    const double* Wk = d.m_W + 18 * mk;
+    double WV[18];
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+      for (int c = 0; c < 3; c++) WV[3 * r + c] = Wj[3 * r] * Vi[c] + Wj[3 * r + 1] * Vi[3 + c] + Wj[3 * r + 2] * Vi[6 + c];
+    double* Sb = d.S + (size_t)jrow * d.n + krow;
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+      for (int c = 0; c < 6; c++) {
+        const double v = WV[3 * r] * Wk[3 * c] + WV[3 * r + 1] * Wk[3 * c + 1] + WV[3 * r + 2] * Wk[3 * c + 2];
+        atomicAdd(&Sb[(size_t)r * d.n + c], -v);
+      }
+    if (a == b) {
+      const double* ve = d.Ve + 3 * i;
+#pragma unroll
+      for (int r = 0; r < 6; r++) atomicAdd(&d.vE[jrow + r], -(Wj[3 * r] * ve[0] + Wj[3 * r + 1] * ve[1] + Wj[3 * r + 2] * ve[2]));
+    }
+  }
+}
+
+// mirror lower -> upper (Bundle.cc:451-453); only needed when S is exported
+__global__ void __launch_bounds__(256) k_ba_mirror(double* S, int n) {
+  const size_t tot = (size_t)n * n;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t / n), j = (int)(t % n);
+    if (j > i) S[t] = S[(size_t)j * n + i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Blocked LDL^T, panel width 32 (right-looking).  L (unit lower) overwrites the strict lower
+// triangle, D the diagonal; `Wp` [n][32] receives the current panel times D (L21 * D1).
+//   k_ldlt_diag : one CTA factors the 32x32 diagonal block in shared memory
+//   k_ldlt_panel: rows below the block: L21 = A21 L11^-T D1^-1 (one thread per row)
+//   k_ldlt_update: A22 -= (L21 D1) L21^T on the lower triangle, 64x64 tiles, f64 FMA
+// ---------------------------------------------------------------------------------------------
+constexpr int kNB = 32;
+
+__global__ void __launch_bounds__(32) k_ldlt_diag(double* A, int n, int k0) {
+  __shared__ double a[kNB][kNB + 1];
+  const int nb = min(kNB, n - k0);
+  const int t = threadIdx.x;
+  for (int r = 0; r < nb; r++) if (t < nb) a[r][t] = A[(size_t)(k0 + r) * n + k0 + t];
+  __syncwarp();
+  // row t of the block; column-by-column elimination
+  for (int col = 0; col < nb; col++) {
+    // d_col = a[col][col] - sum_{c2<col} (L[col][c2] * D[c2]) * L[col][c2]; stored incrementally:
+    // after processing column c2 we subtract its contribution from all later entries (right-looking)
+    const double dcol = a[col][col];
+    const double inv = 1.0 / dcol;
+    double l = 0.0;
+    if (t > col && t < nb) { l = a[t][col] * inv; }
+    __syncwarp();
+    if (t > col && t < nb) {
+      // update row t, columns col+1..t with l * (a[c][col])   (a[c][col] still holds L*D value)
+      for (int c = col + 1; c <= t; c++) a[t][c] -= l * a[c][col];
+    }
+    __syncwarp();
+    if (t > col && t < nb) a[t][col] = l;
+    __syncwarp();
+  }
+  for (int r = 0; r < nb; r++) if (t < nb && t <= r) A[(size_t)(k0 + r) * n + k0 + t] = a[r][t];
+}
+
+__global__ void __launch_bounds__(128) k_ldlt_panel(double* A, double* Wp, int n, int k0) {
+  __shared__ double L[kNB][kNB + 1];
+  __shared__ double Dg[kNB];
+  const int nb = min(kNB, n - k0);
+  for (int i = threadIdx.x; i < nb * nb; i += blockDim.x) {
+    const int r = i / nb, c = i % nb;
+    L[r][c] = c <= r ? A[(size_t)(k0 + r) * n + k0 + c] : 0.0;
+  }
+  __syncthreads();
+  if (threadIdx.x < nb) Dg[threadIdx.x] = L[threadIdx.x][threadIdx.x];
+  __syncthreads();
+  const int row = k0 + nb + blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  double x[kNB];
+  double* Ar = A + (size_t)row * n + k0;
+#pragma unroll
+  for (int c = 0; c < kNB; c++) x[c] = c < nb ? Ar[c] : 0.0;
+  // solve w L11^T = a  (w = L21 D1), forward over columns
+#pragma unroll
+  for (int c = 0; c < kNB; c++) {
+    if (c < nb) {
+      double v = x[c];
+#pragma unroll
+      for (int q = 0; q < kNB; q++) if (q < c) v -= x[q] * L[c][q];
+      x[c] = v;  // = (L21 D1)[row][c]
+    }
+  }
+  double* Wr = Wp + (size_t)row * kNB;
+#pragma unroll
+  for (int c = 0; c < kNB; c++) {
+    if (c < nb) { Wr[c] = x[c]; Ar[c] = x[c] / Dg[c]; } else Wr[c] = 0.0;
+  }
+}
+
+constexpr int kUT = 64;  // update tile
+__global__ void __launch_bounds__(256) k_ldlt_update(double* A, const double* Wp, int n, int k0) {
+  // tile (bi, bj) with bj <= bi of the trailing matrix starting at r0 = k0 + nb
+  __shared__ double sW[kUT][kNB + 1];  // (L21 D1) rows of the i-tile
+  __shared__ double sL[kUT][kNB + 1];  // L21 rows of the j-tile
+  const int nb = min(kNB, n - k0);
+  const int r0 = k0 + nb;
+  // linear tile index -> (bi, bj)
+  int bi = (int)((sqrt(8.0 * blockIdx.x + 1.0) - 1.0) * 0.5);
+  while (bi * (bi + 1) / 2 > (int)blockIdx.x) bi--;
+  while ((bi + 1) * (bi + 2) / 2 <= (int)blockIdx.x) bi++;
+  const int bj = blockIdx.x - bi * (bi + 1) / 2;
+  const int i0 = r0 + bi * kUT, j0 = r0 + bj * kUT;
+  for (int t = threadIdx.x; t < kUT * kNB; t += blockDim.x) {
+    const int r = t / kNB, c = t % kNB;
+    sW[r][c] = (i0 + r < n) ? Wp[(size_t)(i0 + r) * kNB + c] : 0.0;
+    sL[r][c] = (j0 + r < n && c < nb) ? A[(size_t)(j0 + r) * n + k0 + c] : 0.0;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16x16 threads, 4x4 each
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
+#pragma unroll 8
+  for (int c = 0; c < kNB; c++) {
+    double w[4], l[4];
+#pragma unroll
+    for (int a = 0; a < 4; a++) { w[a] = sW[ty + 16 * a][c]; l[a] = sL[tx + 16 * a][c]; }
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int b = 0; b < 4; b++) acc[a][b] += w[a] * l[b];
+  }
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      const int i = i0 + ty + 16 * a, j = j0 + tx + 16 * b;
+      if (i < n && j <= i) A[(size_t)i * n + j] -= acc[a][b];
+    }
+}
+
+// x = (L D L^T)^-1 b, one CTA; blocked by 32 columns.
+__global__ void __launch_bounds__(1024) k_ldlt_solve(const double* A, const double* b, double* x, int n) {
+  extern __shared__ double y[];  // n
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = blockDim.x >> 5;
+  for (int i = t; i < n; i += blockDim.x) y[i] = b[i];
+  __syncthreads();
+  // forward: L y = b
+  for (int k0 = 0; k0 < n; k0 += 32) {
+    const int nb = min(32, n - k0);
+    if (warp == 0) {
+      for (int c = 0; c < nb; c++) {
+        const double yc = y[k0 + c];
+        if (lane > c && lane < nb) y[k0 + lane] -= A[(size_t)(k0 + lane) * n + k0 + c] * yc;
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    for (int i = k0 + nb + warp; i < n; i += nw) {
+      double v = lane < nb ? A[(size_t)i * n + k0 + lane] * y[k0 + lane] : 0.0;
+      v = warp_sum(v);
+      if (lane == 0) y[i] -= v;
+    }
+    __syncthreads();
+  }
+  for (int i = t; i < n; i += blockDim.x) y[i] /= A[(size_t)i * n + i];
+  __syncthreads();
+  // backward: L^T x = y
+  for (int k1 = n; k1 > 0; k1 -= 32) {
+    const int k0 = max(0, k1 - 32), nb = k1 - k0;
+    if (warp == 0) {
+      for (int c = nb - 1; c >= 0; c--) {
+        const double xc = y[k0 + c];
+        if (lane < c) y[k0 + lane] -= A[(size_t)(k0 + c) * n + k0 + lane] * xc;
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // y[i] -= sum_c L[k0+c][i] * x[k0+c] for i < k0: threads over i (coalesced along i)
+    for (int i = t; i < k0; i += blockDim.x) {
+      double v = 0;
+      for (int c = 0; c < nb; c++) v += A[(size_t)(k0 + c) * n + i] * y[k0 + c];
+      y[i] -= v;
+    }
+    __syncthreads();
+  }
+  for (int i = t; i < n; i += blockDim.x) x[i] = y[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ba_point_update(BundleDev d) {
+  __shared__ double sh[32];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double ss = 0.0;
+  if (i < d.n_pts) {
+    double sum[3] = {0, 0, 0};
+    for (int o = d.pt_off[i]; o < d.pt_off[i + 1]; o++) {
+      const int m = d.pt_meas[o];
+      if (d.m_state[m] != M_ALIVE) continue;
+      const int row = d.cam_row[d.m_cam[m]];
+      if (row < 0) continue;
+      const double* W = d.m_W + 18 * m;
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        double a = 0;
+#pragma unroll
+        for (int q = 0; q < 6; q++) a += W[3 * q + r] * d.upd[row + q];
+        sum[r] += a;
+      }
+    }
+    const double v0 = d.epsB[3 * i] - sum[0], v1 = d.epsB[3 * i + 1] - sum[1], v2 = d.epsB[3 * i + 2] - sum[2];
+    const double* Vi = d.Vinv + 9 * i;
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      const double u = Vi[3 * r] * v0 + Vi[3 * r + 1] * v1 + Vi[3 * r + 2] * v2;
+      d.pt_pos_new[3 * i + r] = d.pt_pos[3 * i + r] + u;
+      ss += u * u;
+    }
+  }
+  const double t = block_sum(ss, sh);
+  if (threadIdx.x == 0) atomicAdd(&d.scal[4], t);
+}
+
+__global__ void __launch_bounds__(128) k_ba_cam_update(BundleDev d) {
+  __shared__ double sh[32];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  double ss = 0.0;
+  if (c < d.n_cams) {
+    const int row = d.cam_row[c];
+    if (row < 0) {
+      for (int k = 0; k < 12; k++) d.cam_se3_new[12 * c + k] = d.cam_se3[12 * c + k];
+    } else {
+      double mu[6], ex[12], np[12];
+      for (int k = 0; k < 6; k++) { mu[k] = d.upd[row + k]; ss += mu[k] * mu[k]; }
+      se3_exp(mu, ex);
+      se3_mul(ex, d.cam_se3 + 12 * c, np);
+      for (int k = 0; k < 12; k++) d.cam_se3_new[12 * c + k] = np[k];
+    }
+  }
+  const double t = block_sum(ss, sh);
+  if (threadIdx.x == 0) atomicAdd(&d.scal[4], t);
+}
+
+__global__ void __launch_bounds__(256) k_ba_new_error(BundleDev d) {
+  __shared__ double sh[32];
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  double e = 0.0;
+  if (m < d.n_meas && d.m_state[m] != M_ERASED) {
+    double v3[3];
+    se3_apply(d.cam_se3_new + 12 * d.m_cam[m], d.pt_pos_new + 3 * d.m_pt[m], v3);
+    if (v3[2] <= 0) e = 1.0;
+    else {
+      const CamProj q = cam_project(d.cam, v3[0] / v3[2], v3[1] / v3[2]);
+      const double s = d.m_sin[m];
+      const double e0 = s * (d.m_found[2 * m] - q.im[0]), e1 = s * (d.m_found[2 * m + 1] - q.im[1]);
+      e = mest_objective(e0 * e0 + e1 * e1, d.scal[1], d.est);
+    }
+  }
+  const double t = block_sum(e, sh);
+  if (threadIdx.x == 0) atomicAdd(&d.scal[3], t);
+}
+
+// end of an LM step: erase the bad measurements, appending (point, camera) in list order
+__global__ void __launch_bounds__(1024) k_ba_erase(BundleDev d) {
+  __shared__ int wcnt[32];
+  __shared__ int base_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) base_s = d.counters[1];
+  __syncthreads();
+  for (int m0 = 0; m0 < d.n_meas; m0 += blockDim.x) {
+    const int m = m0 + threadIdx.x;
+    const bool bad = m < d.n_meas && d.m_state[m] == M_BAD;
+    const unsigned b = __ballot_sync(kFull, bad);
+    if (lane == 0) wcnt[warp] = __popc(b);
+    __syncthreads();
+    int before = base_s;
+    for (int w = 0; w < warp; w++) before += wcnt[w];
+    if (bad) {
+      const int o = before + __popc(b & ((1u << lane) - 1));
+      d.outliers[2 * o] = d.m_pt[m]; d.outliers[2 * o + 1] = d.m_cam[m];
+      d.m_state[m] = M_ERASED;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += wcnt[w]; base_s += t; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) d.counters[1] = base_s;
+}
+
+}  // namespace ptam

@@ -250,54 +250,73 @@ def make_ba_graph(n_cams=50, n_points=5000, n_meas=20000, seed=42, width=640, he
     state, camera 0 fixed.  Measurements are inserted camera-major then by point."""
     rng = np.random.default_rng(seed)
     cam = AtanCamera(width, height, params)
-    pts = np.column_stack([rng.uniform(-2, 2, n_points), rng.uniform(-2, 2, n_points), rng.uniform(-0.25, 0.25, n_points)])
+    # slab side: 4 units (SURVEY.md §8d) unless there are so few cameras that the requested mean
+    # track length cannot be reached with this lens at height 1 (footprint ~0.63 units^2): then the
+    # slab shrinks until every point has >= 2 observers and the totals fit.
+    mean_k = n_meas / n_points
+    side = min(4.0, float(np.sqrt(n_cams * 0.63 / (2.5 * mean_k))))
     g = int(np.ceil(np.sqrt(n_cams)))
-    cam_R, cam_t, cam_c = [], [], []
-    for i in range(n_cams):
-        r, cidx = divmod(i, g)
-        if r % 2:
-            cidx = g - 1 - cidx
-        c = np.array([-1.6 + 3.2 * cidx / max(g - 1, 1), -1.6 + 3.2 * r / max(g - 1, 1), 1.0])
-        ax, ay, az = np.deg2rad(rng.uniform(-20, 20, 2)).tolist() + [rng.uniform(0, 2 * np.pi)]
-        Rx = np.array([[1, 0, 0], [0, np.cos(np.pi + ax), -np.sin(np.pi + ax)], [0, np.sin(np.pi + ax), np.cos(np.pi + ax)]])
-        Ry = np.array([[np.cos(ay), 0, np.sin(ay)], [0, 1, 0], [-np.sin(ay), 0, np.cos(ay)]])
-        Rz = np.array([[np.cos(az), -np.sin(az), 0], [np.sin(az), np.cos(az), 0], [0, 0, 1]])
-        Rwc = Rz @ Ry @ Rx
-        R = Rwc.T
-        cam_R.append(R); cam_t.append(-R @ c); cam_c.append(c)
-    cam_R, cam_t, cam_c = np.array(cam_R), np.array(cam_t), np.array(cam_c)
-    # visibility: project every point into every camera
-    uv = np.zeros((n_cams, n_points, 2))
-    vis = np.zeros((n_cams, n_points), bool)
-    for j in range(n_cams):
-        pc = pts @ cam_R[j].T + cam_t[j]
-        z = pc[:, 2]
-        ok = z > 0.1
-        ip = pc[:, :2] / np.where(ok, z, 1.0)[:, None]
-        p = cam.project(ip)
-        uv[j] = p
-        vis[j] = ok & (p[:, 0] >= 8) & (p[:, 1] >= 8) & (p[:, 0] < width - 8) & (p[:, 1] < height - 8) & ((ip * ip).sum(1) < 1.0)
+    base = int(np.ceil(mean_k))
+    for attempt in range(40):
+        hs = side / 2
+        pts = np.column_stack([rng.uniform(-hs, hs, n_points), rng.uniform(-hs, hs, n_points), rng.uniform(-0.25, 0.25, n_points)])
+        cam_R, cam_t, cam_c = [], [], []
+        for i in range(n_cams):
+            r, cidx = divmod(i, g)
+            if r % 2:
+                cidx = g - 1 - cidx
+            c = np.array([-0.8 * hs + 1.6 * hs * cidx / max(g - 1, 1), -0.8 * hs + 1.6 * hs * r / max(g - 1, 1), 1.0])
+            ax, ay, az = np.deg2rad(rng.uniform(-20, 20, 2)).tolist() + [rng.uniform(0, 2 * np.pi)]
+            Rx = np.array([[1, 0, 0], [0, np.cos(np.pi + ax), -np.sin(np.pi + ax)], [0, np.sin(np.pi + ax), np.cos(np.pi + ax)]])
+            Ry = np.array([[np.cos(ay), 0, np.sin(ay)], [0, 1, 0], [-np.sin(ay), 0, np.cos(ay)]])
+            Rz = np.array([[np.cos(az), -np.sin(az), 0], [np.sin(az), np.cos(az), 0], [0, 0, 1]])
+            R = (Rz @ Ry @ Rx).T
+            cam_R.append(R); cam_t.append(-R @ c); cam_c.append(c)
+        cam_R, cam_t, cam_c = np.array(cam_R), np.array(cam_t), np.array(cam_c)
+
+        def visibility(P):
+            uv_ = np.zeros((n_cams, len(P), 2))
+            vis_ = np.zeros((n_cams, len(P)), bool)
+            for j in range(n_cams):
+                pc = P @ cam_R[j].T + cam_t[j]
+                z = pc[:, 2]
+                ok = z > 0.1
+                ip = pc[:, :2] / np.where(ok, z, 1.0)[:, None]
+                q = cam.project(ip)
+                uv_[j] = q
+                vis_[j] = ok & (q[:, 0] >= 8) & (q[:, 1] >= 8) & (q[:, 0] < width - 8) & (q[:, 1] < height - 8) & ((ip * ip).sum(1) < 1.0)
+            return uv_, vis_
+
+        uv, vis = visibility(pts)
+        for _ in range(20):  # re-draw the points nobody (or only one camera) sees
+            lonely = np.flatnonzero(vis.sum(0) < 2)
+            if len(lonely) == 0:
+                break
+            pts[lonely] = np.column_stack([rng.uniform(-hs, hs, len(lonely)), rng.uniform(-hs, hs, len(lonely)), rng.uniform(-0.25, 0.25, len(lonely))])
+            uv_l, vis_l = visibility(pts[lonely])
+            uv[:, lonely], vis[:, lonely] = uv_l, vis_l
+        nvis = vis.sum(0)
+        level_cap = np.minimum(nvis, 2 * base + 2)
+        if nvis.min() >= 2 and int(level_cap.sum()) >= n_meas:
+            break
+        side *= 0.85
+    else:
+        raise ValueError("could not build a graph with the requested sizes")
     d2 = ((pts[None, :, :2] - cam_c[:, None, :2]) ** 2).sum(-1)
     d2 = np.where(vis, d2, np.inf)
     order = np.argsort(d2, axis=0)  # cameras by distance, per point
-    nvis = vis.sum(0)
-    # choose k per point: start with 2 each, then hand out the remainder round-robin by capacity
-    k = np.minimum(nvis, 2)
+    # k per point: 2 each, then hand out the remainder round-robin up to the cap
+    k = np.full(n_points, 2)
     remaining = n_meas - int(k.sum())
     if remaining < 0:
-        raise ValueError("n_meas too small")
-    base = int(np.ceil(n_meas / n_points))
+        raise ValueError("n_meas must be at least 2 per point")
     prio = rng.permutation(n_points)
-    level_cap = np.minimum(nvis, 2 * base + 2)
     while remaining > 0:
-        progressed = False
         for i in prio:
             if remaining == 0:
                 break
             if k[i] < level_cap[i]:
-                k[i] += 1; remaining -= 1; progressed = True
-        if not progressed:
-            raise ValueError("not enough visibility for requested n_meas")
+                k[i] += 1; remaining -= 1
     mc, mp = [], []
     for i in range(n_points):
         for j in order[:k[i], i]:

@@ -1,0 +1,135 @@
+"""GPU parity for path B: CUDA Bundle (through the C-ABI) against the CPU oracle.
+Integer outcomes (accepted steps, lambda trials, outlier list incl. order) must be equal; f64 states
+to the tolerances below (GPU uses FMA and atomics, so sums are reordered at the 1e-16 level)."""
+import numpy as np
+import pytest
+
+from ptam_cg_b200 import synth
+from ptam_cg_b200.capi import Bundle
+
+pytestmark = pytest.mark.gpu
+
+STATE_TOL = 1e-8   # absolute, points (units ~1) and SE3 entries after a whole Compute()
+STEP_TOL = 1e-10   # after one LM step from the same state
+
+
+def _pair(oracle, product, g, **prm):
+    o, p = Bundle(oracle, g["width"], g["height"], **prm), Bundle(product, g["width"], g["height"], **prm)
+    o.add_graph(g); p.add_graph(g)
+    return o, p
+
+
+def _same_stats(so, sp, rtol=1e-9):
+    for f in ("accepted", "lambda_trials", "lm_steps", "converged", "hit_max_iterations", "n_outliers"):
+        assert getattr(so, f) == getattr(sp, f), (f, getattr(so, f), getattr(sp, f))
+    for f in ("sigma_squared", "lambda_", "last_error", "last_new_error"):
+        np.testing.assert_allclose(getattr(sp, f), getattr(so, f), rtol=rtol, err_msg=f)
+
+
+@pytest.mark.parametrize("shape", [(6, 200, 800, 3), (12, 600, 3000, 4), (50, 5000, 20000, 42)])
+def test_compute_matches_oracle(oracle, product, shape):
+    nc, npts, nm, seed = shape
+    g = synth.make_ba_graph(nc, npts, nm, seed=seed)
+    o, p = _pair(oracle, product, g)
+    ao, ap = o.Compute(), p.Compute()
+    assert ao == ap and ao > 0
+    # whole run: the 1e-16 reordering differences are amplified by the conditioning of S over ~10
+    # solves (states agree to ~1e-8), and sigma^2 / the error sums inherit ~focal x that
+    _same_stats(o.stats(), p.stats(), rtol=1e-5)
+    assert o.Converged() == p.Converged()
+    assert np.array_equal(o.GetOutlierMeasurements(), p.GetOutlierMeasurements())
+    np.testing.assert_allclose(p.get_points(), o.get_points(), atol=STATE_TOL, rtol=0)
+    np.testing.assert_allclose(p.get_cameras(), o.get_cameras(), atol=STATE_TOL, rtol=0)
+    # the fixed camera never moves (gauge)
+    np.testing.assert_array_equal(p.get_cameras()[0], g["cam_se3"][0])
+    # and BA did its job
+    assert np.abs(p.get_points() - g["true_points"]).mean() < 0.6 * np.abs(g["points"] - g["true_points"]).mean()
+
+
+def test_stepwise_and_reduced_system(oracle, product):
+    g = synth.make_ba_graph(10, 500, 2500, seed=9)
+    o, p = _pair(oracle, product, g)
+    o.begin(); p.begin()
+    n = 6 * int((g["cam_fixed"] == 0).sum())
+    for step in range(4):
+        o.lm_step(); p.lm_step()
+        # step 0 starts from bit-identical state: tight; later steps start from states that
+        # already differ by ~1e-10, which S / vE / sigma^2 see multiplied by the focal length
+        tight = step == 0
+        _same_stats(o.stats(), p.stats(), rtol=1e-11 if tight else 1e-6)
+        So, eo = o.reduced_system(n)
+        Sp, ep = p.reduced_system(n)
+        rel = 1e-12 if tight else 1e-6
+        np.testing.assert_allclose(Sp, So, atol=rel * np.abs(So).max(), rtol=0)
+        np.testing.assert_allclose(ep, eo, atol=rel * np.abs(eo).max(), rtol=0)
+        assert np.array_equal(Sp, Sp.T)
+        tol = STEP_TOL if tight else 1e-8
+        np.testing.assert_allclose(p.get_points(), o.get_points(), atol=tol, rtol=0)
+        np.testing.assert_allclose(p.get_cameras(), o.get_cameras(), atol=tol, rtol=0)
+        assert np.array_equal(o.GetOutlierMeasurements(), p.GetOutlierMeasurements())
+
+
+def test_individual_add_calls_and_getters(oracle, product):
+    g = synth.make_ba_graph(5, 60, 200, seed=2)
+    res = []
+    for lib in (oracle, product):
+        b = Bundle(lib, 640, 480)
+        for j in range(5):
+            assert b.AddCamera(g["cam_se3"][j], g["cam_fixed"][j]) == j
+        for i in range(60):
+            assert b.AddPoint(g["points"][i]) == i
+        for c, pt, uv, s2 in zip(g["meas_cam"], g["meas_point"], g["meas_uv"], g["meas_sigma_sq"]):
+            b.AddMeas(c, pt, uv, s2)
+        acc = b.Compute()
+        res.append((acc, np.array([b.GetPoint(i) for i in range(60)]), np.array([b.GetCamera(j) for j in range(5)])))
+    assert res[0][0] == res[1][0]
+    np.testing.assert_allclose(res[1][1], res[0][1], atol=STATE_TOL)
+    np.testing.assert_allclose(res[1][2], res[0][2], atol=STATE_TOL)
+
+
+def test_noise_free_graph_is_fixed_point(product):
+    g = synth.make_ba_graph(6, 150, 600, seed=5, outlier_frac=0.0)
+    cam = synth.AtanCamera(640, 480)
+    g = dict(g)
+    g["points"] = g["true_points"].copy()
+    g["cam_se3"] = g["true_se3"].copy()
+    uv = []
+    for c, p in zip(g["meas_cam"], g["meas_point"]):
+        R, t = synth.se3_from12(g["true_se3"][c])
+        pc = R @ g["true_points"][p] + t
+        uv.append(cam.project(pc[:2] / pc[2]))
+    g["meas_uv"] = np.array(uv)
+    b = Bundle(product, 640, 480)
+    b.add_graph(g)
+    b.Compute()
+    s = b.stats()
+    assert s.converged and s.lambda_trials == 1 and s.n_outliers == 0
+    np.testing.assert_allclose(b.get_points(), g["true_points"], atol=1e-9)
+
+
+def test_mestimators_and_abort(oracle, product):
+    g = synth.make_ba_graph(8, 300, 1200, seed=4)
+    for est in (1, 2):
+        o, p = _pair(oracle, product, g, mestimator=est)
+        assert o.Compute() == p.Compute()
+        _same_stats(o.stats(), p.stats(), rtol=1e-8)
+        np.testing.assert_allclose(p.get_points(), o.get_points(), atol=1e-7)
+    import ctypes
+    flag = (ctypes.c_ubyte * 1)(1)
+    o, p = _pair(oracle, product, g)
+    assert o.Compute(flag) == 0 and p.Compute(flag) == 0
+    assert p.stats().lm_steps == 0
+    np.testing.assert_array_equal(p.get_points(), g["points"])
+
+
+def test_bad_input_is_an_error(product):
+    from ptam_cg_b200.capi import PtamError
+    b = Bundle(product, 640, 480)
+    b.AddCamera(np.r_[np.eye(3).ravel(), 0, 0, 0], True)
+    b.AddPoint([0, 0, 1])
+    with pytest.raises(PtamError):
+        b.AddMeas(3, 0, [1, 1], 1.0)
+    b.AddMeas(0, 0, [1, 1], 1.0)
+    b.AddMeas(0, 0, [2, 2], 1.0)
+    with pytest.raises(PtamError):
+        b.Compute()
