@@ -400,7 +400,11 @@ def main():
     if rank == 0 and not args.no_ba and prod.has("bundle_create"):
         try:
             from ptam_cg_b200.bench_ba import bench_ba
-            out["ba"] = bench_ba(prod, local)
+            cpu_lib = None
+            if not args.no_cpu_baseline:
+                from oracle.binding import oracle_lib
+                cpu_lib = oracle_lib()
+            out["ba"] = bench_ba(prod, local, cpu_lib=cpu_lib)
         except Exception as e:  # the tracker line must still be printed
             out["ba"] = {"error": repr(e)}
 

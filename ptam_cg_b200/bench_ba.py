@@ -6,7 +6,9 @@ from . import synth
 from .capi import Bundle
 
 
-def bench_ba(prod, device=0, n_cams=50, n_points=5000, n_meas=20000, seed=42, reps=5, cpu=True):
+def bench_ba(prod, device=0, n_cams=50, n_points=5000, n_meas=20000, seed=42, reps=5, cpu_lib=None):
+    """cpu_lib: an already-loaded CPU library exporting the same ABI (bench.py passes the oracle for the
+    cpu_baseline leg); this package never loads it itself."""
     g = synth.make_ba_graph(n_cams, n_points, n_meas, seed=seed)
     best = None
     for r in range(reps + 1):  # first repetition is the warm-up
@@ -26,9 +28,8 @@ def bench_ba(prod, device=0, n_cams=50, n_points=5000, n_meas=20000, seed=42, re
            "value": trials / dt, "unit": "lambda-trials/s", "accepted_steps_per_s": acc / dt, "compute_ms": dt * 1e3,
            "lambda_trials": trials, "accepted": acc, "lm_steps": steps, "outliers": outl, "gpu_launches": launches,
            "timing": "wall clock around ptam_bundle_compute (host LM control + device phases), best of %d" % reps}
-    if cpu:
-        from oracle.binding import oracle_lib
-        o = Bundle(oracle_lib(), g["width"], g["height"])
+    if cpu_lib is not None:
+        o = Bundle(cpu_lib, g["width"], g["height"])
         o.add_graph(g)
         t0 = time.perf_counter()
         acc_o = o.Compute()

@@ -13,6 +13,7 @@
 using namespace ptam;
 
 ptam::CamModel ptam_make_cam_model(const double* p, double W, double H);
+void ptam_set_global_error(const std::string& e);
 
 namespace {
 template <class T>
@@ -238,7 +239,7 @@ void ptam_bundle_default_params(ptam_bundle_params* p) {
 
 ptam_bundle* ptam_bundle_create(int device, const double* cam_params, int width, int height, const ptam_bundle_params* params) {
   ptam_bundle* b = new ptam_bundle;
-  if (b->init(device, cam_params, width, height, params) != PTAM_OK) { delete b; return nullptr; }
+  if (b->init(device, cam_params, width, height, params) != PTAM_OK) { ptam_set_global_error(b->err); delete b; return nullptr; }
   return b;
 }
 void ptam_bundle_destroy(ptam_bundle* b) { delete b; }

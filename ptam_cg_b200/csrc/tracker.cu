@@ -55,6 +55,7 @@ CamModel make_cam(const double* p, double W, double H) {  // ATANCamera::Refresh
 }  // namespace
 
 ptam::CamModel ptam_make_cam_model(const double* p, double W, double H) { return make_cam(p, W, H); }
+void ptam_set_global_error(const std::string& e) { g_last_error = e; }
 
 struct ptam_tracker {
   int device = 0, W = 0, H = 0, S = 0;

@@ -1,0 +1,114 @@
+"""CPU-only checks that pin the bundle-adjustment oracle: the reduced camera
+system is re-derived with numpy from numerically differentiated residuals, plus LM invariants."""
+import numpy as np
+
+from ptam_cg_b200 import synth
+from ptam_cg_b200.capi import Bundle
+
+
+def _residual(cam, se3, X, uv, s):
+    R, t = synth.se3_from12(se3)
+    pc = R @ X + t
+    return s * (uv - cam.project(pc[:2] / pc[2]))
+
+
+def _dense_reduced_system(g, sigma2, lam):
+    cam = synth.AtanCamera(g["width"], g["height"])
+    C, P = len(g["cam_fixed"]), len(g["points"])
+    free = np.flatnonzero(g["cam_fixed"] == 0)
+    row = {c: 6 * i for i, c in enumerate(free)}
+    nc, npar = 6 * len(free), 6 * len(free) + 3 * P
+    H = np.zeros((npar, npar)); gvec = np.zeros(npar)
+    h = 1e-6
+    for c, p, uv, s2 in zip(g["meas_cam"], g["meas_point"], g["meas_uv"], g["meas_sigma_sq"]):
+        s = np.sqrt(1.0 / s2)
+        se3, X = g["cam_se3"][c], g["points"][p]
+        e = _residual(cam, se3, X, uv, s)
+        e2 = e @ e
+        if e2 > sigma2:
+            continue
+        w = 1.0 - e2 / sigma2
+        J = np.zeros((2, npar))
+        if c in row:
+            for k in range(6):
+                d = np.zeros(6); d[k] = h
+                ep = _residual(cam, synth.se3_to12(*synth.se3_mul(synth.se3_exp(d), synth.se3_from12(se3))), X, uv, s)
+                em = _residual(cam, synth.se3_to12(*synth.se3_mul(synth.se3_exp(-d), synth.se3_from12(se3))), X, uv, s)
+                J[:, row[c] + k] = -(ep - em) / (2 * h) * w   # A = d proj / d xi, reweighted
+        for k in range(3):
+            d = np.zeros(3); d[k] = h
+            J[:, nc + 3 * p + k] = -(_residual(cam, se3, X + d, uv, s) - _residual(cam, se3, X - d, uv, s)) / (2 * h) * w
+        H += J.T @ J
+        gvec += J.T @ (w * e)
+    Hd = H.copy()
+    Hd[np.diag_indices(npar)] *= (1.0 + lam)
+    Hcc, Hcp, Hpp = Hd[:nc, :nc], Hd[:nc, nc:], Hd[nc:, nc:]
+    Vinv = np.zeros_like(Hpp)
+    for i in range(P):
+        blk = Hpp[3 * i:3 * i + 3, 3 * i:3 * i + 3]
+        if blk[0, 0] * blk[1, 1] * blk[2, 2] != 0:
+            Vinv[3 * i:3 * i + 3, 3 * i:3 * i + 3] = np.linalg.inv(blk)
+    S = Hcc - Hcp @ Vinv @ Hcp.T
+    vE = gvec[:nc] - Hcp @ Vinv @ gvec[nc:]
+    return S, vE
+
+
+def test_reduced_system_matches_dense_numpy_derivation(oracle):
+    g = synth.make_ba_graph(5, 40, 140, seed=3)
+    b = Bundle(oracle, g["width"], g["height"])
+    b.add_graph(g)
+    b.begin()
+    b.lm_step()
+    st = b.stats()
+    assert st.lambda_trials == 1 and st.accepted == 1      # first trial accepted: lambda was 1e-4
+    n = 6 * int((g["cam_fixed"] == 0).sum())
+    S, vE = b.reduced_system(n)
+    Sd, vEd = _dense_reduced_system(g, st.sigma_squared, 1e-4)
+    np.testing.assert_allclose(S, S.T, atol=0)
+    np.testing.assert_allclose(S, Sd, atol=1e-5 * np.abs(Sd).max())
+    np.testing.assert_allclose(vE, vEd, atol=1e-5 * np.abs(vEd).max())
+    # and the update the oracle took solves that system
+    delta = np.linalg.solve(Sd, vEd)
+    cams = b.get_cameras()
+    for i, c in enumerate(np.flatnonzero(g["cam_fixed"] == 0)):
+        expect = synth.se3_to12(*synth.se3_mul(synth.se3_exp(delta[6 * i:6 * i + 6]), synth.se3_from12(g["cam_se3"][c])))
+        np.testing.assert_allclose(cams[c], expect, atol=1e-6)
+
+
+def test_lm_invariants(oracle):
+    g = synth.make_ba_graph(8, 300, 1200, seed=4)
+    b = Bundle(oracle, g["width"], g["height"])
+    b.add_graph(g)
+    b.begin()
+    prev_acc, seen_outliers = 0, 0
+    while True:
+        before = b.get_cameras().copy()
+        b.lm_step()
+        s = b.stats()
+        if s.accepted > prev_acc:
+            assert s.last_new_error < s.last_error       # accepted steps lower the robust error
+        else:
+            np.testing.assert_array_equal(b.get_cameras(), before)
+        prev_acc = s.accepted
+        assert s.n_outliers >= seen_outliers
+        seen_outliers = s.n_outliers
+        np.testing.assert_array_equal(b.get_cameras()[0], g["cam_se3"][0])   # gauge: fixed camera
+        assert s.sigma_squared >= 0.16 - 1e-15                                # MinTukeySigma^2
+        if s.converged or s.hit_max_iterations:
+            break
+    assert s.lambda_trials <= 20
+    out = b.GetOutlierMeasurements()
+    assert len(out) == s.n_outliers and len({tuple(o) for o in out}) == len(out)
+    assert np.abs(b.get_points() - g["true_points"]).mean() < np.abs(g["points"] - g["true_points"]).mean()
+
+
+def test_max_iterations_and_lambda_schedule(oracle):
+    g = synth.make_ba_graph(6, 150, 600, seed=5)
+    b = Bundle(oracle, g["width"], g["height"], max_iterations=3)
+    b.add_graph(g)
+    b.Compute()
+    s = b.stats()
+    assert s.lambda_trials == 3 and s.hit_max_iterations == 1
+    # three good steps from 1e-4: lambda *= 0.3 each
+    if s.accepted == 3:
+        np.testing.assert_allclose(s.lambda_, 1e-4 * 0.3 ** 3)
