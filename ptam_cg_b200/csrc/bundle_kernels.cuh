@@ -115,8 +115,8 @@ __global__ void __launch_bounds__(1024) k_ba_select(BundleDev d, double min_sigm
   __shared__ unsigned long long prefix;
   __shared__ int kk;
   const int n = d.counters[0];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) { prefix = 0ull; kk = n / 2; }
-  __syncthreads();
   for (int pass = 0; pass < 8 && n > 0; pass++) {
     const int shift = 56 - 8 * pass;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
@@ -127,11 +127,24 @@ __global__ void __launch_bounds__(1024) k_ba_select(BundleDev d, double min_sigm
       if (pass == 0 || (key >> (shift + 8)) == (pf >> (shift + 8))) atomicAdd(&hist[(key >> shift) & 255], 1);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      int k = kk, b = 0;
-      while (b < 255 && k >= hist[b]) { k -= hist[b]; b++; }
-      kk = k;
-      prefix = pf | ((unsigned long long)b << shift);
+    if (warp == 0) {
+      int c[8], tot = 0;
+#pragma unroll
+      for (int q = 0; q < 8; q++) { c[q] = hist[8 * lane + q]; tot += c[q]; }
+      int inc = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += v;
+      }
+      const int k0 = kk;
+      const int excl = inc - tot;
+      if (k0 >= excl && k0 < inc) {
+        int r = k0 - excl, q = 0;
+        while (q < 7 && r >= c[q]) { r -= c[q]; q++; }
+        kk = r;
+        prefix = pf | ((unsigned long long)(8 * lane + q) << shift);
+      }
     }
     __syncthreads();
   }

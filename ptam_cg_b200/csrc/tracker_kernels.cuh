@@ -190,6 +190,8 @@ PTAM_DEV bool run10(unsigned m) {
 
 __global__ void __launch_bounds__(256) k_fast(TrackerDev d) {
   __shared__ __align__(16) uint8_t tile[kFastTH + 6][kFastSW];
+  __shared__ uint8_t cand_list[8][kFastTW];
+  __shared__ unsigned row_words[8][4];
   const int s = blockIdx.y;
   int l = 0;
 #pragma unroll
@@ -217,66 +219,71 @@ __global__ void __launch_bounds__(256) k_fast(TrackerDev d) {
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int thr = d.g.thresholds[l];
-#pragma unroll
+#pragma unroll 1
   for (int rr = 0; rr < 2; rr++) {
-    const int ry = warp * 2 + rr;  // row inside tile
+    const int ry = warp * 2 + rr;  // row inside tile (tile row ry+3 is the centre row)
     const int y = y0 + ry;
+    if (y >= L.h) break;           // warp-uniform
     const int x = x0 + 4 * lane;   // first of this thread's 4 pixels
-    unsigned nib = 0;
+    unsigned cand = 0;
     if (y >= 3 && y < L.h - 3) {
-      // words covering bytes [x-4, x+8) of rows ry .. ry+6 (tile row ry+3 is the centre row)
-      // centre pixels: bytes 4..7 of the centre row triple
+      // ---- stage 1: compass test.  Any arc of >= 10 ring pixels contains two ADJACENT compass
+      // points (ring 0/4/8/12 = below/right/above/left), so both must be brighter (or darker).
       const unsigned* crow = reinterpret_cast<const unsigned*>(&tile[ry + 3][4 * lane]);
-      const unsigned cw = crow[1];
-      // Quick reject (any 10-arc contains ring[0] or ring[8], i.e. (0,+3) or (0,-3)):
+      const unsigned w0 = crow[0], cw = crow[1], w2 = crow[2];
       const unsigned up = reinterpret_cast<const unsigned*>(&tile[ry][4 * lane])[1];
       const unsigned dn = reinterpret_cast<const unsigned*>(&tile[ry + 6][4 * lane])[1];
-      unsigned cand = 0;
+      const unsigned lft = __byte_perm(w0, cw, 0x4321);  // bytes x-3 .. x of the centre row
+      const unsigned rgt = __byte_perm(cw, w2, 0x6543);  // bytes x+3 .. x+6
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        const int p = (cw >> (8 * k)) & 255, a = (dn >> (8 * k)) & 255, b = (up >> (8 * k)) & 255;
+        const int p = (cw >> (8 * k)) & 255;
         const int cb = p + thr, c_b = p - thr;
-        if (a > cb || b > cb || a < c_b || b < c_b) cand |= 1u << k;
-      }
-      if (cand) {
-        // gather the 7 ring rows as 12-byte windows
-        unsigned w[7][3];
-#pragma unroll
-        for (int r = 0; r < 7; r++) {
-          const unsigned* q = reinterpret_cast<const unsigned*>(&tile[ry + r][4 * lane]);
-          w[r][0] = q[0]; w[r][1] = q[1]; w[r][2] = q[2];
-        }
-        // ring offsets (dx,dy), dy measured downwards; window byte index = 4 + k + dx, row = 3 + dy
-        const int dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
-        const int dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          if (!((cand >> k) & 1)) continue;
-          const int xx = x + k;
-          if (xx < 3 || xx >= L.w - 3) continue;
-          const int p = (cw >> (8 * k)) & 255;
-          const int cb = p + thr, c_b = p - thr;
-          unsigned mb = 0, md = 0;
-#pragma unroll
-          for (int j = 0; j < 16; j++) {
-            const int bi = 4 + k + dx[j];
-            const int v = (w[3 + dy[j]][bi >> 2] >> (8 * (bi & 3))) & 255;
-            mb |= (unsigned)(v > cb) << j;
-            md |= (unsigned)(v < c_b) << j;
-          }
-          if (run10(mb) || run10(md)) nib |= 1u << k;
-        }
+        const int a = (dn >> (8 * k)) & 255, b = (rgt >> (8 * k)) & 255, c = (up >> (8 * k)) & 255, e = (lft >> (8 * k)) & 255;
+        const bool ba = a > cb, bb = b > cb, bc = c > cb, be = e > cb;
+        const bool da = a < c_b, db = b < c_b, dc = c < c_b, de = e < c_b;
+        const bool q = (ba && bb) || (bb && bc) || (bc && be) || (be && ba) || (da && db) || (db && dc) || (dc && de) || (de && da);
+        const int xx = x + k;
+        if (q && xx >= 3 && xx < L.w - 3) cand |= 1u << k;
       }
     }
-    // pack 8 lanes x 4 bits into one 32-pixel word
-    unsigned v = nib << (4 * (lane & 7));
-    v |= __shfl_xor_sync(kFull, v, 1);
-    v |= __shfl_xor_sync(kFull, v, 2);
-    v |= __shfl_xor_sync(kFull, v, 4);
-    if ((lane & 7) == 0 && y < L.h) {
-      const int word = (x0 >> 5) + (lane >> 3);
-      if (word < L.nwords) d.mask[(size_t)s * d.g.mask_stride + L.mask_off + (size_t)y * L.nwords + word] = v;
+    // ---- stage 2: compact the warp's candidates so that every lane runs a full ring test
+    const int nc = __popc(cand);
+    int inc = nc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(kFull, inc, o);
+      if (lane >= o) inc += n;
     }
+    const int total = __shfl_sync(kFull, inc, 31);
+    if (lane < 4) row_words[warp][lane] = 0u;
+    int o = inc - nc;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if ((cand >> k) & 1) cand_list[warp][o++] = (uint8_t)(4 * lane + k);
+    __syncwarp();
+    for (int ci = lane; ci < total; ci += 32) {
+      const int px = cand_list[warp][ci];
+      const uint8_t* c = &tile[ry + 3][4 + px];
+      const int p = *c;
+      const int cb = p + thr, c_b = p - thr;
+      unsigned mb = 0, md = 0;
+      const int dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+      const int dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        const int v = c[dy[j] * kFastSW + dx[j]];
+        mb |= (unsigned)(v > cb) << j;
+        md |= (unsigned)(v < c_b) << j;
+      }
+      if (run10(mb) || run10(md)) atomicOr(&row_words[warp][px >> 5], 1u << (px & 31));
+    }
+    __syncwarp();
+    if (lane < 4) {
+      const int word = (x0 >> 5) + lane;
+      if (word < L.nwords) d.mask[(size_t)s * d.g.mask_stride + L.mask_off + (size_t)y * L.nwords + word] = row_words[warp][lane];
+    }
+    __syncwarp();
   }
 }
 
@@ -782,33 +789,52 @@ __global__ void __launch_bounds__(128) k_search(TrackerDev d, int stage) {
 // =============================================================================================
 constexpr int kPoseThreads = 512;
 
-// exact k-th smallest (0-based) of the non-negative doubles keys[0..n) flagged valid: MSB-first
-// radix select on the IEEE bit patterns, 8 bits per pass.
-PTAM_DEV double block_select_kth(const double* keys, const int* valid_idx, int n, int kth, int* hist /*256*/, unsigned long long* sh_prefix, int* sh_k) {
+// exact k-th smallest (0-based) of n non-negative doubles: MSB-first radix select on the IEEE bit
+// patterns (order-isomorphic to the values), 8 bits per pass; the 256-bin histogram is scanned by
+// warp 0 (8 bins per lane + shuffle scan), so a pass costs three barriers and no serial loop.
+// keys are read through `at(i)`.  All threads of the block must call it.
+template <class At>
+PTAM_DEV double block_select_kth(At at, int n, int kth, int* hist /*256*/, unsigned long long* sh_prefix, int* sh_k) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) { *sh_prefix = 0ull; *sh_k = kth; }
-  __syncthreads();
   for (int pass = 0; pass < 8; pass++) {
     const int shift = 56 - 8 * pass;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
     __syncthreads();
     const unsigned long long prefix = *sh_prefix;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const unsigned long long key = (unsigned long long)__double_as_longlong(keys[valid_idx[i]]);
+      const unsigned long long key = (unsigned long long)__double_as_longlong(at(i));
       if (pass == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&hist[(key >> shift) & 255], 1);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      int kk = *sh_k, b = 0;
-      while (b < 255 && kk >= hist[b]) { kk -= hist[b]; b++; }
-      *sh_k = kk;
-      *sh_prefix = prefix | ((unsigned long long)b << shift);
+    if (warp == 0) {
+      int c[8], tot = 0;
+#pragma unroll
+      for (int q = 0; q < 8; q++) { c[q] = hist[8 * lane + q]; tot += c[q]; }
+      int inc = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += v;
+      }
+      const int kk = *sh_k;
+      const int excl = inc - tot;
+      if (kk >= excl && kk < inc) {  // exactly one lane
+        int r = kk - excl, q = 0;
+        while (q < 7 && r >= c[q]) { r -= c[q]; q++; }
+        *sh_k = r;
+        *sh_prefix = prefix | ((unsigned long long)(8 * lane + q) << shift);
+      }
     }
     __syncthreads();
   }
   return __longlong_as_double((long long)*sh_prefix);
 }
 
+constexpr int kPoseSmemPts = 2048;  // found sets up to this size take the shared-memory median path
+
 __global__ void __launch_bounds__(kPoseThreads) k_pose(TrackerDev d, int stage) {
+  __shared__ double s_e2[kPoseSmemPts];
   __shared__ double pose[12];
   __shared__ double red[16][27];
   __shared__ double mu_s[6];
@@ -898,7 +924,8 @@ __global__ void __launch_bounds__(kPoseThreads) k_pose(TrackerDev d, int stage) 
         }
         const double sn = d.p.sqrt_inv_noise[g];
         const double e0 = sn * (d.p.v2found[2 * g] - v2i[0]), e1 = sn * (d.p.v2found[2 * g + 1] - v2i[1]);
-        e2[fidx[i]] = e0 * e0 + e1 * e1;
+        const double ee = e0 * e0 + e1 * e1;
+        if (nf <= kPoseSmemPts) s_e2[i] = ee; else e2[fidx[i]] = ee;
       }
       __syncthreads();
       double mu[6] = {0, 0, 0, 0, 0, 0};
@@ -906,7 +933,9 @@ __global__ void __launch_bounds__(kPoseThreads) k_pose(TrackerDev d, int stage) 
         double sigma2;
         if (override_sigma > 0) sigma2 = override_sigma;
         else {
-          const double med = block_select_kth(e2, fidx, nf, nf / 2, hist, &sh_prefix, &sh_k);
+          double med;
+          if (nf <= kPoseSmemPts) med = block_select_kth([&](int i) { return s_e2[i]; }, nf, nf / 2, hist, &sh_prefix, &sh_k);
+          else med = block_select_kth([&](int i) { return e2[fidx[i]]; }, nf, nf / 2, hist, &sh_prefix, &sh_k);
           sigma2 = mest_sigma_from_median(med, nf, est);
         }
         // weighted normal equations (TooN WLS<6>::add_mJ twice per point)
@@ -943,9 +972,15 @@ __global__ void __launch_bounds__(kPoseThreads) k_pose(TrackerDev d, int stage) 
 #pragma unroll
           for (int q = 0; q < 27; q++) red[warp][q] = acc[q];
         __syncthreads();
+        if (threadIdx.x < 27) {
+          double t = 0;
+          for (int wq = 0; wq < kPoseThreads / 32; wq++) t += red[wq][threadIdx.x];
+          red[0][threadIdx.x] = t;
+        }
+        __syncthreads();
         if (threadIdx.x == 0) {
           double tot[27];
-          for (int q = 0; q < 27; q++) { double t = 0; for (int wq = 0; wq < kPoseThreads / 32; wq++) t += red[wq][q]; tot[q] = t; }
+          for (int q = 0; q < 27; q++) tot[q] = red[0][q];
           double C[36], b[6], x[6];
           int c = 0;
           for (int a = 0; a < 6; a++)
