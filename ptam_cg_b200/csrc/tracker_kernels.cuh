@@ -170,13 +170,21 @@ __global__ void __launch_bounds__(256) k_pyramid(TrackerDev d) {
 }
 
 // =============================================================================================
-// k_fast — FAST-10.  Tile = 128 px x 16 rows, 256 threads (8 warps x 2 rows), each thread tests 4
-// consecutive pixels.  The tile plus a 3-row / 4-byte-aligned halo is staged in shared memory with
-// 32-bit loads; ring pixels are extracted from three words per ring row.  Output: one bit per pixel.
-// A pixel is a corner iff >= 10 contiguous ring pixels are all > p+t or all < p-t (strict).
+// k_fast — FAST-10.  Tile = 128 px x 32 rows per CTA (256 threads), staged in shared memory with a
+// 3-row halo by 16-byte loads.  Three phases:
+//   1. compass pre-test on packed data: every thread tests 4 adjacent pixels of 4 rows.  Any arc of
+//      >= 10 ring pixels contains two ADJACENT compass points (ring 0/4/8/12 = below/right/above/
+//      left), so a corner needs (below|above) & (right|left) all brighter than p+t (or all darker
+//      than p-t).  The comparisons run two pixels per 32-bit register in 16-bit lanes:
+//      bit 15 of  x + (0x8000 - p - t - 1)  is set iff x > p + t,  bit 15 of  (0x8000 + p - t - 1) - x
+//      iff x < p - t;  no lane can carry or borrow into its neighbour.
+//   2. the surviving candidates (~9 % of level-0 pixels) are compacted into a CTA-wide list, so that
+//   3. every thread runs the full 16-pixel ring test (>= 10 contiguous, strict) on one candidate.
+// Output: one bit per pixel.  Raster order is restored by k_compact.
 // =============================================================================================
-constexpr int kFastTW = 128, kFastTH = 16;
-constexpr int kFastSW = kFastTW + 8;  // staged bytes per row: x0-4 .. x0+131
+constexpr int kFastTW = 128, kFastTH = 32;
+constexpr int kFastSW = kFastTW + 32;   // staged bytes per row: x0-16 .. x0+143 (ten 16-byte chunks)
+constexpr int kFastSR = kFastTH + 6;    // staged rows: y0-3 .. y0+34
 
 PTAM_DEV bool run10(unsigned m) {
   m |= m << 16;
@@ -189,9 +197,10 @@ PTAM_DEV bool run10(unsigned m) {
 }
 
 __global__ void __launch_bounds__(256) k_fast(TrackerDev d) {
-  __shared__ __align__(16) uint8_t tile[kFastTH + 6][kFastSW];
-  __shared__ uint8_t cand_list[8][kFastTW];
-  __shared__ unsigned row_words[8][4];
+  __shared__ __align__(16) uint8_t tile[kFastSR * kFastSW];
+  __shared__ uint16_t cand_list[kFastTW * kFastTH];
+  __shared__ unsigned out_mask[kFastTH][4];
+  __shared__ int cand_count;
   const int s = blockIdx.y;
   int l = 0;
 #pragma unroll
@@ -202,88 +211,110 @@ __global__ void __launch_bounds__(256) k_fast(TrackerDev d) {
   const int x0 = tx * kFastTW, y0 = ty * kFastTH;
   int pitch;
   const uint8_t* im = level_image(d, s, l, pitch);
-  const bool aligned = ((pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(im) & 3) == 0);
-  // stage rows y0-3 .. y0+18, bytes x0-4 .. x0+131 (zero outside the image)
-  for (int i = threadIdx.x; i < (kFastTH + 6) * (kFastSW / 4); i += 256) {
-    const int r = i / (kFastSW / 4), c = i % (kFastSW / 4);
-    const int y = y0 - 3 + r, x = x0 - 4 + 4 * c;
-    unsigned v = 0;
-    if (y >= 0 && y < L.h) {
+  const bool al16 = ((pitch & 15) == 0) && ((reinterpret_cast<uintptr_t>(im) & 15) == 0);
+  if (threadIdx.x < kFastTH * 4) (&out_mask[0][0])[threadIdx.x] = 0u;
+  if (threadIdx.x == 0) cand_count = 0;
+  // ---- stage rows y0-3 .. y0+34, bytes x0-16 .. x0+143 (zero outside the image)
+  for (int i = threadIdx.x; i < kFastSR * (kFastSW / 16); i += 256) {
+    const int r = i / (kFastSW / 16), c = i - r * (kFastSW / 16);
+    const int y = y0 - 3 + r, x = x0 - 16 + 16 * c;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (y >= 0 && y < L.h && x + 15 >= 0 && x < L.w) {
       const uint8_t* p = im + (size_t)y * pitch + x;
-      if (aligned && x >= 0 && x + 3 < L.w) v = __ldg(reinterpret_cast<const unsigned*>(p));
-      else
-        for (int k = 0; k < 4; k++) if (x + k >= 0 && x + k < L.w) v |= (unsigned)__ldg(p + k) << (8 * k);
+      if (al16 && x >= 0 && x + 15 < L.w) v = __ldg(reinterpret_cast<const uint4*>(p));
+      else {
+        unsigned w4[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+          if (x + k >= 0 && x + k < L.w) w4[k >> 2] |= (unsigned)__ldg(p + k) << (8 * (k & 3));
+        v = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+      }
     }
-    *reinterpret_cast<unsigned*>(&tile[r][4 * c]) = v;
+    *reinterpret_cast<uint4*>(&tile[r * kFastSW + 16 * c]) = v;
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int thr = d.g.thresholds[l];
-#pragma unroll 1
-  for (int rr = 0; rr < 2; rr++) {
-    const int ry = warp * 2 + rr;  // row inside tile (tile row ry+3 is the centre row)
-    const int y = y0 + ry;
-    if (y >= L.h) break;           // warp-uniform
-    const int x = x0 + 4 * lane;   // first of this thread's 4 pixels
-    unsigned cand = 0;
-    if (y >= 3 && y < L.h - 3) {
-      // ---- stage 1: compass test.  Any arc of >= 10 ring pixels contains two ADJACENT compass
-      // points (ring 0/4/8/12 = below/right/above/left), so both must be brighter (or darker).
-      const unsigned* crow = reinterpret_cast<const unsigned*>(&tile[ry + 3][4 * lane]);
-      const unsigned w0 = crow[0], cw = crow[1], w2 = crow[2];
-      const unsigned up = reinterpret_cast<const unsigned*>(&tile[ry][4 * lane])[1];
-      const unsigned dn = reinterpret_cast<const unsigned*>(&tile[ry + 6][4 * lane])[1];
-      const unsigned lft = __byte_perm(w0, cw, 0x4321);  // bytes x-3 .. x of the centre row
-      const unsigned rgt = __byte_perm(cw, w2, 0x6543);  // bytes x+3 .. x+6
+  // ---- phase 1: compass pre-test, 4 pixels x 4 rows per thread
+  const unsigned K = 0x80008000u - (unsigned)(thr + 1) * 0x00010001u;
+  unsigned vmask = 0;
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const int p = (cw >> (8 * k)) & 255;
-        const int cb = p + thr, c_b = p - thr;
-        const int a = (dn >> (8 * k)) & 255, b = (rgt >> (8 * k)) & 255, c = (up >> (8 * k)) & 255, e = (lft >> (8 * k)) & 255;
-        const bool ba = a > cb, bb = b > cb, bc = c > cb, be = e > cb;
-        const bool da = a < c_b, db = b < c_b, dc = c < c_b, de = e < c_b;
-        const bool q = (ba && bb) || (bb && bc) || (bc && be) || (be && ba) || (da && db) || (db && dc) || (dc && de) || (de && da);
-        const int xx = x + k;
-        if (q && xx >= 3 && xx < L.w - 3) cand |= 1u << k;
+  for (int k = 0; k < 4; k++) {
+    const int xx = x0 + 4 * lane + k;
+    if (xx >= 3 && xx < L.w - 3) vmask |= 1u << k;
+  }
+  unsigned cand16 = 0;
+#pragma unroll
+  for (int rr = 0; rr < 4; rr++) {
+    const int ry = 4 * warp + rr;  // row inside the tile; staged row ry+3 is the centre row
+    const int y = y0 + ry;
+    if (y >= 3 && y < L.h - 3) {  // warp-uniform
+      const unsigned* crow = reinterpret_cast<const unsigned*>(&tile[(ry + 3) * kFastSW + 12 + 4 * lane]);
+      const unsigned w0 = crow[0], cw = crow[1], w2 = crow[2];
+      const unsigned up = *reinterpret_cast<const unsigned*>(&tile[ry * kFastSW + 16 + 4 * lane]);
+      const unsigned dn = *reinterpret_cast<const unsigned*>(&tile[(ry + 6) * kFastSW + 16 + 4 * lane]);
+      const unsigned lft = __byte_perm(w0, cw, 0x4321);  // pixels x-3 .. x
+      const unsigned rgt = __byte_perm(cw, w2, 0x6543);  // pixels x+3 .. x+6
+      const unsigned Plo = __byte_perm(cw, 0u, 0x4140), Phi = __byte_perm(cw, 0u, 0x4342);
+      const unsigned Blo = K - Plo, Bhi = K - Phi, Dlo = Plo + K, Dhi = Phi + K;
+      unsigned b_lo[4], b_hi[4], d_lo[4], d_hi[4];
+      const unsigned ring4[4] = {dn, rgt, up, lft};
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const unsigned Xlo = __byte_perm(ring4[q], 0u, 0x4140), Xhi = __byte_perm(ring4[q], 0u, 0x4342);
+        b_lo[q] = Xlo + Blo; b_hi[q] = Xhi + Bhi;
+        d_lo[q] = Dlo - Xlo; d_hi[q] = Dhi - Xhi;
       }
+      const unsigned r_lo = ((b_lo[0] | b_lo[2]) & (b_lo[1] | b_lo[3])) | ((d_lo[0] | d_lo[2]) & (d_lo[1] | d_lo[3]));
+      const unsigned r_hi = ((b_hi[0] | b_hi[2]) & (b_hi[1] | b_hi[3])) | ((d_hi[0] | d_hi[2]) & (d_hi[1] | d_hi[3]));
+      const unsigned r = ((r_lo >> 15) & 1u) | ((r_lo >> 30) & 2u) | ((r_hi >> 13) & 4u) | ((r_hi >> 28) & 8u);
+      cand16 |= (r & vmask) << (4 * rr);
     }
-    // ---- stage 2: compact the warp's candidates so that every lane runs a full ring test
-    const int nc = __popc(cand);
+  }
+  // ---- phase 2: CTA-wide candidate list (order is irrelevant: the output is a bit mask)
+  {
+    const int nc = __popc(cand16);
     int inc = nc;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int n = __shfl_up_sync(kFull, inc, o);
       if (lane >= o) inc += n;
     }
-    const int total = __shfl_sync(kFull, inc, 31);
-    if (lane < 4) row_words[warp][lane] = 0u;
-    int o = inc - nc;
-#pragma unroll
-    for (int k = 0; k < 4; k++)
-      if ((cand >> k) & 1) cand_list[warp][o++] = (uint8_t)(4 * lane + k);
-    __syncwarp();
-    for (int ci = lane; ci < total; ci += 32) {
-      const int px = cand_list[warp][ci];
-      const uint8_t* c = &tile[ry + 3][4 + px];
-      const int p = *c;
-      const int cb = p + thr, c_b = p - thr;
-      unsigned mb = 0, md = 0;
-      const int dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
-      const int dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
-#pragma unroll
-      for (int j = 0; j < 16; j++) {
-        const int v = c[dy[j] * kFastSW + dx[j]];
-        mb |= (unsigned)(v > cb) << j;
-        md |= (unsigned)(v < c_b) << j;
-      }
-      if (run10(mb) || run10(md)) atomicOr(&row_words[warp][px >> 5], 1u << (px & 31));
+    int base = 0;
+    if (lane == 31 && inc > 0) base = atomicAdd(&cand_count, inc);
+    base = __shfl_sync(kFull, base, 31);
+    int o = base + inc - nc;
+    while (cand16) {
+      const int b = __ffs(cand16) - 1;
+      cand16 &= cand16 - 1;
+      cand_list[o++] = (uint16_t)(((4 * warp + (b >> 2)) << 7) | (4 * lane + (b & 3)));
     }
-    __syncwarp();
-    if (lane < 4) {
-      const int word = (x0 >> 5) + lane;
-      if (word < L.nwords) d.mask[(size_t)s * d.g.mask_stride + L.mask_off + (size_t)y * L.nwords + word] = row_words[warp][lane];
+  }
+  __syncthreads();
+  // ---- phase 3: full ring test, one candidate per thread
+  const int n_cand = cand_count;
+  for (int ci = threadIdx.x; ci < n_cand; ci += 256) {
+    const int e = cand_list[ci];
+    const int ry = e >> 7, px = e & 127;
+    const uint8_t* c = &tile[(ry + 3) * kFastSW + 16 + px];
+    const int p = *c;
+    const int hi = p + thr, lo = p - thr;
+    unsigned mb = 0, md = 0;
+    const int dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+    const int dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      const int v = c[dy[j] * kFastSW + dx[j]];
+      mb = __funnelshift_l((unsigned)(hi - v), mb, 1);  // shifts in the sign of (p+t) - v: v > p+t
+      md = __funnelshift_l((unsigned)(v - lo), md, 1);  // sign of v - (p-t): v < p-t
     }
-    __syncwarp();
+    if (run10(mb) || run10(md)) atomicOr(&out_mask[ry][px >> 5], 1u << (px & 31));
+  }
+  __syncthreads();
+  if (threadIdx.x < kFastTH * 4) {
+    const int ry = threadIdx.x >> 2, wq = threadIdx.x & 3;
+    const int y = y0 + ry, word = (x0 >> 5) + wq;
+    if (y < L.h && word < L.nwords) d.mask[(size_t)s * d.g.mask_stride + L.mask_off + (size_t)y * L.nwords + word] = out_mask[ry][wq];
   }
 }
 

@@ -1,0 +1,122 @@
+// Host mirror of class Tracker (reference include/Tracker.h:155-241) for the measured path:
+// TrackFrame(CVD::Image<byte>&, bool) = MakeKeyFrame_Lite + PredictPoseWithMotionModel + TrackMap +
+// UpdateMotionModel + AssessTrackingQuality (src/Tracker.cc:86-188,442-698,1012-1107), all on the
+// device through ptam_tracker_track_frames; GetCurrentPose() as in Tracker.h:163.
+// Not mirrored (out of scope): trail tracking / stereo initialisation, GUI commands, GL
+// drawing, relocalisation, MapMaker::AddKeyFrame hand-off (the caller decides from LastResult()).
+#pragma once
+#include <map>
+#include "KeyFrame.h"
+
+namespace ptam_b200 {
+
+class Tracker {
+ public:
+  // reference: Tracker(ImageRef irVideoSize, const ATANCamera &c, Map &m, MapMaker &mm)
+  Tracker(CVD::ImageRef irVideoSize, const ATANCamera& c, Map& m, int device = 0, const ptam_tracker_params* params = nullptr)
+      : mMap(m), mCamera(c), mirSize(irVideoSize) {
+    double p[5];
+    for (int i = 0; i < 5; i++) p[i] = c.GetParams()[i];
+    h = ptam_tracker_create(device, p, irVideoSize.x, irVideoSize.y, 1, params);
+    if (!h) throw std::runtime_error(std::string("ptam_tracker_create: ") + ptam_global_last_error());
+  }
+  ~Tracker() { if (h) ptam_tracker_destroy(h); }
+  Tracker(const Tracker&) = delete;
+  Tracker& operator=(const Tracker&) = delete;
+
+  // bDraw is accepted for signature compatibility; there is no GL on this path.
+  void TrackFrame(CVD::Image<CVD::byte>& imFrame, bool bDraw) {
+    (void)bDraw;
+    if (imFrame.size() != mirSize) throw std::invalid_argument("frame size differs from irVideoSize");
+    SyncMap();
+    const uint8_t* ptrs[1] = {imFrame.data()};
+    if (ptam_tracker_track_frames(h, ptrs, imFrame.row_stride(), &mLast) != PTAM_OK) throw std::runtime_error(ptam_tracker_last_error(h));
+    mse3CamFromWorld = se3_from_array(mLast.se3_cam_from_world);
+    mCurrentKF.se3CfromW = mse3CamFromWorld;  // Tracker.cc:662
+    mCurrentKF.dSceneDepthMean = mLast.scene_depth_mean;
+    mCurrentKF.dSceneDepthSigma = mLast.scene_depth_sigma;
+    mbKFCurrent = false;
+  }
+  TooN::SE3<> GetCurrentPose() { return mse3CamFromWorld; }
+
+  // Sets mse3CamFromWorld (and zero velocity) — what the reference does after stereo initialisation
+  // (Tracker.cc:332-335) or recovery.
+  void SetCurrentPose(const TooN::SE3<>& se3) {
+    ptam_tracker_state st;
+    ptam_tracker_get_state(h, 0, &st);
+    se3_to_array(se3, st.se3_cam_from_world);
+    for (double& v : st.velocity) v = 0;
+    st.msd_scaled_velocity_magnitude = 0;
+    ptam_tracker_set_state(h, 0, &st);
+    mse3CamFromWorld = se3;
+  }
+
+  // mCurrentKF as the reference leaves it after TrackFrame: levels with corners (MakeKeyFrame_Lite)
+  // and the measurements of the found points (Tracker.cc:665-677) + per-point M-estimator counters
+  // (Tracker.cc:990-997).  Fetched lazily: it is only needed when the frame becomes a keyframe.
+  KeyFrame& CurrentKeyFrame() {
+    if (mbKFCurrent) return mCurrentKF;
+    for (int l = 0; l < LEVELS; l++) mCurrentKF.FetchLevel(h, 0, l);
+    const size_t n = mvUploaded.size();
+    std::vector<int32_t> flags(n), level(n), outl(n), inl(n);
+    std::vector<double> found(2 * n);
+    if (n) ptam_tracker_get_points(h, 0, flags.data(), level.data(), found.data(), nullptr, outl.data(), inl.data());
+    mCurrentKF.mMeasurements.clear();
+    for (size_t i = 0; i < n; i++) {
+      mvUploaded[i]->nMEstimatorOutlierCount = outl[i];
+      mvUploaded[i]->nMEstimatorInlierCount = inl[i];
+      if (!(flags[i] & PTAM_PT_FOUND)) continue;
+      Measurement m;
+      m.nLevel = level[i];
+      m.bSubPix = (flags[i] & PTAM_PT_SUBPIX) != 0;
+      m.v2RootPos = TooN::makeVector(found[2 * i], found[2 * i + 1]);
+      m.Source = Measurement::SRC_TRACKER;
+      mCurrentKF.mMeasurements[mvUploaded[i]] = m;
+    }
+    mbKFCurrent = true;
+    return mCurrentKF;
+  }
+  const ptam_track_result& LastResult() const { return mLast; }
+  ptam_tracker* handle() { return h; }
+
+ private:
+  // Upload the map when its revision changed: new source keyframes go to the device keyframe store
+  // (their level-0 pixels; the library rebuilds the pyramid), points as SoA.
+  void SyncMap() {
+    if (mbMapUploaded && mnRevision == mMap.nRevision && mvUploaded.size() == mMap.vpPoints.size()) return;
+    const size_t n = mMap.vpPoints.size();
+    std::vector<double> world(3 * n), right(3 * n), down(3 * n);
+    std::vector<int32_t> kf(n), lvl(n), ctr(2 * n);
+    for (size_t i = 0; i < n; i++) {
+      MapPoint& p = *mMap.vpPoints[i];
+      auto it = mKFIds.find(p.pPatchSourceKF);
+      if (it == mKFIds.end()) {
+        Level& L0 = p.pPatchSourceKF->aLevels[0];
+        const int id = ptam_tracker_add_keyframe(h, L0.im.data(), L0.im.row_stride());
+        if (id < 0) throw std::runtime_error(ptam_tracker_last_error(h));
+        it = mKFIds.emplace(p.pPatchSourceKF, id).first;
+      }
+      for (int k = 0; k < 3; k++) { world[3 * i + k] = p.v3WorldPos[k]; right[3 * i + k] = p.v3PixelRight_W[k]; down[3 * i + k] = p.v3PixelDown_W[k]; }
+      kf[i] = it->second; lvl[i] = p.nSourceLevel; ctr[2 * i] = p.irCenter.x; ctr[2 * i + 1] = p.irCenter.y;
+    }
+    if (ptam_tracker_set_map(h, 0, (int)n, world.data(), right.data(), down.data(), kf.data(), lvl.data(), ctr.data()) != PTAM_OK)
+      throw std::runtime_error(ptam_tracker_last_error(h));
+    mvUploaded = mMap.vpPoints;
+    mnRevision = mMap.nRevision;
+    mbMapUploaded = true;
+  }
+
+  Map& mMap;
+  ATANCamera mCamera;
+  CVD::ImageRef mirSize;
+  ptam_tracker* h = nullptr;
+  KeyFrame mCurrentKF;
+  TooN::SE3<> mse3CamFromWorld;
+  ptam_track_result mLast{};
+  std::map<KeyFrame*, int> mKFIds;
+  std::vector<MapPoint*> mvUploaded;
+  unsigned mnRevision = 0;
+  bool mbMapUploaded = false, mbKFCurrent = false;
+};
+
+}  // namespace ptam_b200

@@ -1,0 +1,122 @@
+// Exercises the C++ host mirror (Bundle / KeyFrame / Tracker with TooN/CVD-style types) end to end
+// against libptam_b200.so.  Driven by tests/test_host_cpp_gpu.py: reads raw arrays from a directory,
+// runs them through the classes exactly as MapMaker::BundleAdjust (MapMaker.cc:852-904) and
+// System::UpdateFrame (System.cc:94) would, writes the results back as raw arrays.
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include "Bundle.h"
+#include "Tracker.h"
+
+using namespace ptam_b200;
+using namespace TooN;
+
+template <class T>
+static std::vector<T> rd(const std::string& dir, const char* name) {
+  std::ifstream f(dir + "/" + name, std::ios::binary | std::ios::ate);
+  if (!f) { std::cerr << "missing " << name << "\n"; std::exit(2); }
+  const size_t bytes = (size_t)f.tellg();
+  f.seekg(0);
+  std::vector<T> v(bytes / sizeof(T));
+  f.read(reinterpret_cast<char*>(v.data()), bytes);
+  return v;
+}
+template <class T>
+static void wr(const std::string& dir, const char* name, const std::vector<T>& v) {
+  std::ofstream f(dir + "/" + name, std::ios::binary);
+  f.write(reinterpret_cast<const char*>(v.data()), v.size() * sizeof(T));
+}
+
+static void run_bundle(const std::string& dir) {
+  auto cams = rd<double>(dir, "ba_cams.f64");
+  auto fixed = rd<int32_t>(dir, "ba_fixed.i32");
+  auto pts = rd<double>(dir, "ba_pts.f64");
+  auto mcam = rd<int32_t>(dir, "ba_mcam.i32");
+  auto mpt = rd<int32_t>(dir, "ba_mpt.i32");
+  auto uv = rd<double>(dir, "ba_uv.f64");
+  auto s2 = rd<double>(dir, "ba_s2.f64");
+  ATANCamera cam("Camera");
+  Bundle b(cam);
+  for (size_t c = 0; c < fixed.size(); c++) b.AddCamera(se3_from_array(&cams[12 * c]), fixed[c] != 0);
+  for (size_t p = 0; p < pts.size() / 3; p++) b.AddPoint(makeVector(pts[3 * p], pts[3 * p + 1], pts[3 * p + 2]));
+  for (size_t m = 0; m < mcam.size(); m++) b.AddMeas(mcam[m], mpt[m], makeVector(uv[2 * m], uv[2 * m + 1]), s2[m]);
+  bool abort = false;
+  const int accepted = b.Compute(&abort);
+  std::vector<double> opts, ocams(12 * fixed.size());
+  for (size_t p = 0; p < pts.size() / 3; p++) { Vector<3> v = b.GetPoint((int)p); opts.insert(opts.end(), {v[0], v[1], v[2]}); }
+  for (size_t c = 0; c < fixed.size(); c++) se3_to_array(b.GetCamera((int)c), &ocams[12 * c]);
+  auto outl = b.GetOutlierMeasurements();
+  std::vector<int32_t> oo, meta = {accepted, b.Converged() ? 1 : 0, (int32_t)outl.size()};
+  for (auto& pc : outl) { oo.push_back(pc.first); oo.push_back(pc.second); }
+  wr(dir, "ba_out_pts.f64", opts); wr(dir, "ba_out_cams.f64", ocams); wr(dir, "ba_out_meta.i32", meta); wr(dir, "ba_out_outliers.i32", oo);
+  std::printf("bundle: accepted %d converged %d outliers %zu\n", accepted, (int)b.Converged(), outl.size());
+}
+
+static void run_tracker(const std::string& dir) {
+  auto dims = rd<int32_t>(dir, "trk_dims.i32");  // W, H, n_kf, n_pts, n_frames
+  const int W = dims[0], H = dims[1], nkf = dims[2], npts = dims[3], nfr = dims[4];
+  auto kfim = rd<uint8_t>(dir, "trk_kf.u8");
+  auto frames = rd<uint8_t>(dir, "trk_frames.u8");
+  auto world = rd<double>(dir, "trk_world.f64");
+  auto right = rd<double>(dir, "trk_right.f64");
+  auto down = rd<double>(dir, "trk_down.f64");
+  auto skf = rd<int32_t>(dir, "trk_srckf.i32");
+  auto slv = rd<int32_t>(dir, "trk_srclevel.i32");
+  auto ctr = rd<int32_t>(dir, "trk_center.i32");
+  auto pose0 = rd<double>(dir, "trk_pose0.f64");
+  ATANCamera cam("Camera", makeVector(1.0803, 1.43987, 0.519983, 0.548655, 0.244943), CVD::ImageRef(W, H));
+  Map map;
+  std::vector<KeyFrame> kfs(nkf);
+  for (int k = 0; k < nkf; k++) {
+    CVD::BasicImage<CVD::byte> im(kfim.data() + (size_t)k * W * H, CVD::ImageRef(W, H));
+    kfs[k].MakeKeyFrame_Lite(im);  // KeyFrame.cc:18-54 through the device
+    map.vpKeyFrames.push_back(&kfs[k]);
+  }
+  std::vector<MapPoint> points(npts);
+  for (int i = 0; i < npts; i++) {
+    MapPoint& p = points[i];
+    p.v3WorldPos = makeVector(world[3 * i], world[3 * i + 1], world[3 * i + 2]);
+    p.v3PixelRight_W = makeVector(right[3 * i], right[3 * i + 1], right[3 * i + 2]);
+    p.v3PixelDown_W = makeVector(down[3 * i], down[3 * i + 1], down[3 * i + 2]);
+    p.pPatchSourceKF = &kfs[skf[i]];
+    p.nSourceLevel = slv[i];
+    p.irCenter = CVD::ImageRef(ctr[2 * i], ctr[2 * i + 1]);
+    map.vpPoints.push_back(&p);
+  }
+  map.bGood = true; map.nRevision++;
+  Tracker trk(CVD::ImageRef(W, H), cam, map);
+  trk.SetCurrentPose(se3_from_array(pose0.data()));
+  std::vector<double> poses;
+  std::vector<int32_t> counts;
+  CVD::Image<CVD::byte> frame(CVD::ImageRef(W, H));
+  for (int f = 0; f < nfr; f++) {
+    std::memcpy(frame.data(), frames.data() + (size_t)f * W * H, (size_t)W * H);
+    trk.TrackFrame(frame, false);
+    double a[12];
+    se3_to_array(trk.GetCurrentPose(), a);
+    poses.insert(poses.end(), a, a + 12);
+    const ptam_track_result& r = trk.LastResult();
+    for (int l = 0; l < LEVELS; l++) counts.push_back(r.meas_found[l]);
+  }
+  KeyFrame& kf = trk.CurrentKeyFrame();
+  std::vector<int32_t> last = {(int32_t)kf.mMeasurements.size()};
+  for (int l = 0; l < LEVELS; l++) last.push_back((int32_t)kf.aLevels[l].vCorners.size());
+  // corners of source keyframe 0, level 0 (raster order) for a bit-exact check
+  std::vector<int32_t> c0;
+  for (auto& c : kfs[0].aLevels[0].vCorners) { c0.push_back(c.x); c0.push_back(c.y); }
+  wr(dir, "trk_out_poses.f64", poses); wr(dir, "trk_out_found.i32", counts); wr(dir, "trk_out_last.i32", last); wr(dir, "trk_out_kf0_corners.i32", c0);
+  std::printf("tracker: %d frames, last frame %zu measurements\n", nfr, kf.mMeasurements.size());
+}
+
+int main(int argc, char** argv) {
+  if (argc < 2) { std::cerr << "usage: host_check <dir>\n"; return 2; }
+  try {
+    run_bundle(argv[1]);
+    run_tracker(argv[1]);
+  } catch (const std::exception& e) {
+    std::cerr << "host_check failed: " << e.what() << "\n";
+    return 1;
+  }
+  return 0;
+}
