@@ -563,7 +563,8 @@ PTAM_DEV double level_zero_pos(double p, int l) { return (p + 0.5) * (double)(1 
 PTAM_DEV double level_n_pos(double p, int l) { return (p + 0.5) / (double)(1 << l) - 0.5; }
 
 __global__ void __launch_bounds__(128) k_search(TrackerDev d, int stage) {
-  __shared__ uint8_t stmpl[4][64];
+  __shared__ __align__(8) uint8_t stmpl[4][64];
+  __shared__ int2 squeue[4][64];
   const int s = blockIdx.y;
   StreamCtl& ctl = d.ctl[s];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -667,6 +668,8 @@ __global__ void __launch_bounds__(128) k_search(TrackerDev d, int stage) {
     return;
   }
   if (lane == 0) atomicAdd(&ctl.attempted[sl], 1);
+  stmpl[warp][2 * lane] = (uint8_t)t0; stmpl[warp][2 * lane + 1] = (uint8_t)t1;
+  __syncwarp();
   // ---- FindPatchCoarse (PatchFinder.cc:160-211) ------------------------------------------------
   bool found = false;
   double coarse[2] = {0, 0};
@@ -686,7 +689,41 @@ __global__ void __launch_bounds__(128) k_search(TrackerDev d, int stage) {
       const int2* corners = d.corners + (size_t)s * d.g.corner_stride + L.corner_off;
       const int i0 = lut[top];
       const int i1 = bot1 >= L.h ? ctl.n_corners[sl] : lut[bot1];
-      int best_ssd = kMaxSSD + 1, bx = 0, by = 0;
+      // Candidates (disc test + 4-px border, PatchFinder.cc:193-196, ImageProcess.cc:134) are queued per
+      // warp; ZMSSD then runs four candidates at a time, eight lanes per candidate, one 8-pixel window
+      // row per lane: three aligned 32-bit loads + byte_perm, six dp4a, group reduction.  The winner is
+      // the minimum of (ssd, corner index), i.e. the first minimum in raster order (PatchFinder.cc:198).
+      const int sub = lane & 7, grp = lane >> 3;
+      const unsigned gmask = 0xFFu << (8 * grp);
+      const unsigned tw0 = *reinterpret_cast<const unsigned*>(&stmpl[warp][8 * sub]);
+      const unsigned tw1 = *reinterpret_cast<const unsigned*>(&stmpl[warp][8 * sub + 4]);
+      int best_ssd = kMaxSSD + 1, best_idx = 0x7fffffff;
+      auto process = [&](int n) {
+        for (int r0 = 0; r0 < n; r0 += 4) {
+          const int kq = r0 + grp;
+          const bool valid = kq < n;
+          const int2 e = squeue[warp][valid ? kq : 0];
+          const int cx = e.x & 0xffff, cy = e.x >> 16;
+          const uint8_t* ip = im + (size_t)(cy - 4 + sub) * pitch + (cx - 4);
+          const unsigned a = (unsigned)(reinterpret_cast<uintptr_t>(ip) & 3);
+          const unsigned* wp = reinterpret_cast<const unsigned*>(ip - a);
+          const unsigned w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = a ? __ldg(wp + 2) : 0u;
+          const unsigned sel = 0x3210u + 0x1111u * a;
+          const unsigned v0 = __byte_perm(w0, w1, sel), v1 = __byte_perm(w1, w2, sel);
+          int isum = (int)__dp4a(v0, 0x01010101u, __dp4a(v1, 0x01010101u, 0u));
+          int isq = (int)__dp4a(v0, v0, __dp4a(v1, v1, 0u));
+          int cross = (int)__dp4a(v0, tw0, __dp4a(v1, tw1, 0u));
+          isum = __reduce_add_sync(gmask, isum);
+          isq = __reduce_add_sync(gmask, isq);
+          cross = __reduce_add_sync(gmask, cross);
+          const int SA = tsum, SB = isum;
+          const int ssd = ((2 * SA * SB - SA * SA - SB * SB) / 64 + isq + tsumsq - 2 * cross);  // C++ truncating division
+          if (valid && (ssd < best_ssd || (ssd == best_ssd && e.y < best_idx))) { best_ssd = ssd; best_idx = e.y; }
+        }
+        __syncwarp();
+      };
+      int qn = 0;
+      const unsigned lt = (1u << lane) - 1u;
       for (int b0 = i0; b0 < i1; b0 += 32) {
         const int i = b0 + lane;
         int2 c = make_int2(0, 0);
@@ -695,27 +732,23 @@ __global__ void __launch_bounds__(128) k_search(TrackerDev d, int stage) {
           c = corners[i];
           if (!(c.x < left || c.x > right)) {
             const int ddx = posx - c.x, ddy = posy - c.y;
-            pass = !((unsigned)(ddx * ddx + ddy * ddy) > r * r);
+            pass = !((unsigned)(ddx * ddx + ddy * ddy) > r * r) && c.x >= 4 && c.y >= 4 && c.x < L.w - 4 && c.y < L.h - 4;
           }
         }
-        unsigned m = __ballot_sync(kFull, pass);
-        while (m) {
-          const int src_lane = __ffs(m) - 1;
-          m &= m - 1;
-          const int cx = __shfl_sync(kFull, c.x, src_lane), cy = __shfl_sync(kFull, c.y, src_lane);
-          int ssd = kMaxSSD + 1;
-          if (cx >= 4 && cy >= 4 && cx < L.w - 4 && cy < L.h - 4) {  // in_image_with_border(ir, 4)
-            const uint8_t* ip = im + (size_t)(cy - 4 + trow) * pitch + (cx - 4 + tcol);
-            const int a = ip[0], b = ip[1];
-            const int isum = warp_sum_int(a + b);
-            const int isq = warp_sum_int(a * a + b * b);
-            const int cross = warp_sum_int(a * t0 + b * t1);
-            const int SA = tsum, SB = isum;
-            ssd = ((2 * SA * SB - SA * SA - SB * SB) / 64 + isq + tsumsq - 2 * cross);  // C++ truncating division
-          }
-          if (ssd < best_ssd) { best_ssd = ssd; bx = cx; by = cy; }
-        }
+        const unsigned m = __ballot_sync(kFull, pass);
+        if (pass) squeue[warp][qn + __popc(m & lt)] = make_int2(c.x | (c.y << 16), i);
+        qn += __popc(m);
+        if (qn > 32) { __syncwarp(); process(qn); qn = 0; }
       }
+      __syncwarp();
+      process(qn);
+      {
+        const int bs = __reduce_min_sync(kFull, best_ssd);
+        best_idx = __reduce_min_sync(kFull, best_ssd == bs ? best_idx : 0x7fffffff);
+        best_ssd = bs;
+      }
+      int bx = 0, by = 0;
+      if (best_ssd < kMaxSSD) { const int2 bc = corners[best_idx]; bx = bc.x; by = bc.y; }
       if (best_ssd < kMaxSSD) {
         coarse[0] = level_zero_pos((double)bx, sl);
         coarse[1] = level_zero_pos((double)by, sl);
@@ -733,9 +766,7 @@ __global__ void __launch_bounds__(128) k_search(TrackerDev d, int stage) {
   double v2found[2] = {coarse[0], coarse[1]};
   if (subpix_its > 0) {
     fl |= F_SUBPIX;
-    // ---- MakeSubPixTemplate (PatchFinder.cc:219-240) -------------------------------------------
-    stmpl[warp][2 * lane] = (uint8_t)t0; stmpl[warp][2 * lane + 1] = (uint8_t)t1;
-    __syncwarp();
+    // ---- MakeSubPixTemplate (PatchFinder.cc:219-240); the template is already in stmpl[warp] ----
     float jx[2] = {0.f, 0.f}, jy[2] = {0.f, 0.f};
     int tq[2] = {0, 0};
     double h00 = 0, h01 = 0, h02 = 0, h11 = 0, h12 = 0, h22 = 0;
@@ -818,30 +849,32 @@ __global__ void __launch_bounds__(128) k_search(TrackerDev d, int stage) {
 // coarse points were found; stage 1: the ten fine iterations (Tracker.cc:614-643), measurement
 // export statistics, UpdateMotionModel, AssessTrackingQuality.
 // =============================================================================================
-constexpr int kPoseThreads = 512;
+constexpr int kPoseThreads = 256;  // two CTAs (streams) resident per SM
 
 // exact k-th smallest (0-based) of n non-negative doubles: MSB-first radix select on the IEEE bit
 // patterns (order-isomorphic to the values), 8 bits per pass; the 256-bin histogram is scanned by
 // warp 0 (8 bins per lane + shuffle scan), so a pass costs three barriers and no serial loop.
 // keys are read through `at(i)`.  All threads of the block must call it.
 template <class At>
-PTAM_DEV double block_select_kth(At at, int n, int kth, int* hist /*256*/, unsigned long long* sh_prefix, int* sh_k) {
+PTAM_DEV double block_select_kth(At at, int n, int kth, int* hist /*2 x 256*/, unsigned long long* sh_prefix, int* sh_k) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) { *sh_prefix = 0ull; *sh_k = kth; }
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
   for (int pass = 0; pass < 8; pass++) {
     const int shift = 56 - 8 * pass;
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
-    __syncthreads();
+    int* h = hist + 256 * (pass & 1);
+    int* hnext = hist + 256 * ((pass + 1) & 1);
     const unsigned long long prefix = *sh_prefix;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
       const unsigned long long key = (unsigned long long)__double_as_longlong(at(i));
-      if (pass == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&hist[(key >> shift) & 255], 1);
+      if (pass == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&h[(key >> shift) & 255], 1);
     }
     __syncthreads();
     if (warp == 0) {
       int c[8], tot = 0;
 #pragma unroll
-      for (int q = 0; q < 8; q++) { c[q] = hist[8 * lane + q]; tot += c[q]; }
+      for (int q = 0; q < 8; q++) { c[q] = h[8 * lane + q]; tot += c[q]; }
       int inc = tot;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -856,23 +889,41 @@ PTAM_DEV double block_select_kth(At at, int n, int kth, int* hist /*256*/, unsig
         *sh_k = r;
         *sh_prefix = prefix | ((unsigned long long)(8 * lane + q) << shift);
       }
+    } else {
+      for (int i = threadIdx.x - 32; i < 256; i += blockDim.x - 32) hnext[i] = 0;  // for the next pass
     }
     __syncthreads();
   }
   return __longlong_as_double((long long)*sh_prefix);
 }
 
+// Sum v[i] over the 32 lanes for 32 values at once: after the call lane i holds the total of v[i]
+// in v[0].  Halving exchange: 16 + 8 + 4 + 2 + 1 = 31 shuffles instead of 32 x 5.
+PTAM_DEV void warp_transpose_sum32(double (&v)[32]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int k = 0; k < off; k++) {
+      const double send = up ? v[k] : v[k + off];
+      const double keep = up ? v[k + off] : v[k];
+      v[k] = keep + __shfl_xor_sync(kFull, send, off);
+    }
+  }
+}
+
 constexpr int kPoseSmemPts = 2048;  // found sets up to this size take the shared-memory median path
 
-__global__ void __launch_bounds__(kPoseThreads) k_pose(TrackerDev d, int stage) {
+__global__ void __launch_bounds__(kPoseThreads, 2) k_pose(TrackerDev d, int stage) {
   __shared__ double s_e2[kPoseSmemPts];
   __shared__ double pose[12];
-  __shared__ double red[16][27];
+  __shared__ double red[kPoseThreads / 32][27];
   __shared__ double mu_s[6];
-  __shared__ int hist[256];
+  __shared__ int hist[512];
   __shared__ unsigned long long sh_prefix;
   __shared__ int sh_k;
-  __shared__ int sh_cnt[16];
+  __shared__ int sh_cnt[kPoseThreads / 32];
   __shared__ int nfound_s;
   __shared__ double sigma_s;
   const int s = blockIdx.x;
@@ -970,9 +1021,9 @@ __global__ void __launch_bounds__(kPoseThreads) k_pose(TrackerDev d, int stage) 
           sigma2 = mest_sigma_from_median(med, nf, est);
         }
         // weighted normal equations (TooN WLS<6>::add_mJ twice per point)
-        double acc[27];
+        double acc[32];
 #pragma unroll
-        for (int q = 0; q < 27; q++) acc[q] = 0;
+        for (int q = 0; q < 32; q++) acc[q] = 0;
         for (int i = threadIdx.x; i < nf; i += blockDim.x) {
           const size_t g = gb + fidx[i];
           const double sn = d.p.sqrt_inv_noise[g];
@@ -997,11 +1048,8 @@ __global__ void __launch_bounds__(kPoseThreads) k_pose(TrackerDev d, int stage) 
             for (int a = 0; a < 6; a++) acc[21 + a] += er * Jw[a];
           }
         }
-#pragma unroll
-        for (int q = 0; q < 27; q++) acc[q] = warp_sum(acc[q]);
-        if (lane == 0)
-#pragma unroll
-          for (int q = 0; q < 27; q++) red[warp][q] = acc[q];
+        warp_transpose_sum32(acc);
+        if (lane < 27) red[warp][lane] = acc[0];
         __syncthreads();
         if (threadIdx.x < 27) {
           double t = 0;
