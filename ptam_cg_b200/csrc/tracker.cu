@@ -77,7 +77,7 @@ struct ptam_tracker {
   size_t kf_ptr_cap = 0;
   // per-point arrays
   int cap = 0;
-  DevBuf<double> world, right, down, last_warp, v3cam, v2image, derivs, warp_inv, v2found, sin_, J, e2;
+  DevBuf<double> world, right, down, last_warp, m2buf, v3cam, v2image, derivs, warp_inv, v2found, sin_, J, e2;
   DevBuf<int> src_kf, src_level, tsum, tsumsq, flags, level, search_level, outliers, inliers, pvs, iter_idx;
   DevBuf<int2> center;
   DevBuf<uint8_t> tmpl;
@@ -99,7 +99,7 @@ struct ptam_tracker {
     if (stream) cudaStreamSynchronize(stream);
     for (auto p : kf_bufs) cudaFree(p);
     pyr.free(); corners.free(); lut.free(); mask.free(); ctl.free(); pt_count.free(); kf_ptrs.free();
-    world.free(); right.free(); down.free(); last_warp.free(); v3cam.free(); v2image.free(); derivs.free();
+    world.free(); right.free(); down.free(); last_warp.free(); m2buf.free(); v3cam.free(); v2image.free(); derivs.free();
     warp_inv.free(); v2found.free(); sin_.free(); J.free(); e2.free(); src_kf.free(); src_level.free();
     tsum.free(); tsumsq.free(); flags.free(); level.free(); search_level.free(); outliers.free(); inliers.free();
     pvs.free(); iter_idx.free(); center.free(); tmpl.free();
@@ -187,7 +187,7 @@ struct ptam_tracker {
     const int nc = std::max(n, cap * 2);
     cudaError_t e = cudaSuccess;
 #define RG(buf, k) if (e == cudaSuccess) e = regrow(buf, k, cap, nc)
-    RG(world, 3); RG(right, 3); RG(down, 3); RG(last_warp, 4); RG(v3cam, 3); RG(v2image, 2); RG(derivs, 4);
+    RG(world, 3); RG(right, 3); RG(down, 3); RG(last_warp, 4); RG(m2buf, 4); RG(v3cam, 3); RG(v2image, 2); RG(derivs, 4);
     RG(warp_inv, 4); RG(v2found, 2); RG(sin_, 1); RG(J, 12); RG(e2, 1); RG(src_kf, 1); RG(src_level, 1);
     RG(tsum, 1); RG(tsumsq, 1); RG(flags, 1); RG(level, 1); RG(search_level, 1); RG(outliers, 1); RG(inliers, 1);
     RG(pvs, 4); RG(iter_idx, 1); RG(center, 1); RG(tmpl, 64);
@@ -196,7 +196,7 @@ struct ptam_tracker {
     cap = nc;
     PointArrays& p = dev.p;
     p.world = world.p; p.right = right.p; p.down = down.p; p.src_kf = src_kf.p; p.src_level = src_level.p; p.center = center.p;
-    p.tmpl = tmpl.p; p.tsum = tsum.p; p.tsumsq = tsumsq.p; p.last_warp = last_warp.p;
+    p.tmpl = tmpl.p; p.tsum = tsum.p; p.tsumsq = tsumsq.p; p.last_warp = last_warp.p; p.m2 = m2buf.p;
     p.flags = flags.p; p.level = level.p; p.search_level = search_level.p;
     p.v3cam = v3cam.p; p.v2image = v2image.p; p.derivs = derivs.p; p.warp_inv = warp_inv.p;
     p.v2found = v2found.p; p.sqrt_inv_noise = sin_.p; p.J = J.p; p.outliers = outliers.p; p.inliers = inliers.p;
@@ -266,9 +266,19 @@ struct ptam_tracker {
     unsigned used = 7u | 8u | 32u | 128u;
     pbegin(3); k_pvs_select<<<S, 1024, 0, stream>>>(d); pend(3);
     const int coarse_items = std::min(maxn, 2 * std::max(0, d.prm.coarse_max));
-    if (coarse_items > 0) { pbegin(4); k_search<<<dim3((coarse_items + 3) / 4, S), 128, 0, stream>>>(d, 0); pend(4); used |= 16u; }
+    if (coarse_items > 0) {
+      pbegin(4);
+      k_search_prep<<<dim3((coarse_items + 127) / 128, S), 128, 0, stream>>>(d, 0);
+      k_search<<<dim3((coarse_items + 3) / 4, S), 128, 0, stream>>>(d, 0);
+      pend(4); launches++; used |= 16u;
+    }
     pbegin(5); k_pose<<<S, kPoseThreads, 0, stream>>>(d, 0); pend(5);
-    if (maxn > 0) { pbegin(6); k_search<<<dim3((maxn + 3) / 4, S), 128, 0, stream>>>(d, 1); pend(6); used |= 64u; }
+    if (maxn > 0) {
+      pbegin(6);
+      k_search_prep<<<dim3((maxn + 127) / 128, S), 128, 0, stream>>>(d, 1);
+      k_search<<<dim3((maxn + 3) / 4, S), 128, 0, stream>>>(d, 1);
+      pend(6); launches++; used |= 64u;
+    }
     pbegin(7); k_pose<<<S, kPoseThreads, 0, stream>>>(d, 1); pend(7);
     PTAM_CUDA_TRY(this, cudaGetLastError());
     return pcollect(used);

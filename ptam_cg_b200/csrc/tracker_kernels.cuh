@@ -58,7 +58,8 @@ struct StreamCtl {
 enum : int {
   F_IN_IMAGE = 1, F_IN_PVS = 2, F_SEARCHED = 4, F_FOUND = 8, F_SUBPIX = 16,
   F_TEMPLATE_BAD = 32,   // persistent: PatchFinder::mbTemplateBad
-  F_HAS_TEMPLATE = 64    // persistent: mpLastTemplateMapPoint == &p
+  F_HAS_TEMPLATE = 64,   // persistent: mpLastTemplateMapPoint == &p
+  F_REFRESH = 128        // frame-scoped: k_search_prep decided that the coarse template must be re-warped
 };
 
 struct PointArrays {
@@ -66,7 +67,7 @@ struct PointArrays {
   const double* world; const double* right; const double* down;
   const int* src_kf; const int* src_level; const int2* center;
   // template cache
-  uint8_t* tmpl; int* tsum; int* tsumsq; double* last_warp;
+  uint8_t* tmpl; int* tsum; int* tsumsq; double* last_warp; double* m2;
   // frame state
   int* flags; int* level; int* search_level;
   double* v3cam; double* v2image; double* derivs; double* warp_inv;
@@ -562,6 +563,52 @@ constexpr int kMaxSSD = 8 * 8 * 500;  // PatchFinder.cc:18-19
 PTAM_DEV double level_zero_pos(double p, int l) { return (p + 0.5) * (double)(1 << l) - 0.5; }
 PTAM_DEV double level_n_pos(double p, int l) { return (p + 0.5) / (double)(1 << l) - 0.5; }
 
+// k_search_prep — one THREAD per iteration-set entry: everything of SearchForPoints that is scalar per
+// point (re-projection with the current pose, Tracker.h:89-94; inverse warp matrix and the template
+// cache test, PatchFinder.cc:100-110), so that the warp-per-point k_search does not repeat it 32 times.
+__global__ void __launch_bounds__(128) k_search_prep(TrackerDev d, int stage) {
+  const int s = blockIdx.y;
+  StreamCtl& ctl = d.ctl[s];
+  int begin, end;
+  if (stage == 0) { begin = 0; end = ctl.n_coarse; }
+  else { begin = ctl.n_coarse; end = ctl.n_coarse + ctl.n_l3 + ctl.n_fine; }
+  const int k = begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= end) return;
+  const int cap = d.p.cap;
+  const size_t g = (size_t)s * cap + d.p.iter_idx[(size_t)s * cap + k];
+  int fl = d.p.flags[g] & ~F_REFRESH;
+  const bool reproject = stage == 1 && (k < ctl.n_coarse + ctl.n_l3 || ctl.did_coarse);
+  if (reproject) {
+    // ProjectAndDerivs with bFound == false: Project only (Tracker.h:89-94)
+    ProjOut o;
+    project_point(d, ctl.pose, d.p.world + 3 * g, o);
+    d.p.v3cam[3 * g] = o.v3cam[0]; d.p.v3cam[3 * g + 1] = o.v3cam[1]; d.p.v3cam[3 * g + 2] = o.v3cam[2];
+    if (o.reached_cam) { d.p.v2image[2 * g] = o.v2image[0]; d.p.v2image[2 * g + 1] = o.v2image[1]; }
+    fl = o.in_image ? (fl | F_IN_IMAGE) : (fl & ~F_IN_IMAGE);
+  }
+  const int sl = d.p.search_level[g];
+  // ---- MakeTemplateCoarseCont, the decision part (PatchFinder.cc:98-110)
+  const double wi0 = d.p.warp_inv[4 * g], wi1 = d.p.warp_inv[4 * g + 1], wi2 = d.p.warp_inv[4 * g + 2], wi3 = d.p.warp_inv[4 * g + 3];
+  const double det = wi0 * wi3 - wi2 * wi1;
+  const double idet = 1.0 / det;
+  const double sc = (double)(1 << sl);
+  double m2[4];
+  m2[0] = (wi3 * idet) * sc; m2[3] = (wi0 * idet) * sc;
+  m2[2] = (-wi2 * idet) * sc; m2[1] = (-wi1 * idet) * sc;
+  bool refresh = !(fl & F_HAS_TEMPLATE);
+  if (!refresh) {
+    for (int i = 0; !refresh && i < 2; i++) {
+      const double d0 = m2[i] - d.p.last_warp[4 * g + i], d1 = m2[2 + i] - d.p.last_warp[4 * g + 2 + i];
+      if (d0 * d0 + d1 * d1 > 0.07 * 0.07) refresh = true;
+    }
+  }
+  if (refresh) {
+    fl |= F_REFRESH;
+    for (int q = 0; q < 4; q++) d.p.m2[4 * g + q] = m2[q];
+  }
+  d.p.flags[g] = fl;
+}
+
 __global__ void __launch_bounds__(128) k_search(TrackerDev d, int stage) {
   __shared__ __align__(8) uint8_t stmpl[4][64];
   __shared__ int2 squeue[4][64];
@@ -580,39 +627,15 @@ __global__ void __launch_bounds__(128) k_search(TrackerDev d, int stage) {
   int fl = d.p.flags[g];
   unsigned range;
   int subpix_its;
-  bool reproject;
-  if (stage == 0) { range = ctl.coarse_range; subpix_its = d.prm.coarse_subpix_its; reproject = false; }
+  if (stage == 0) { range = ctl.coarse_range; subpix_its = d.prm.coarse_subpix_its; }
   else {
     range = ctl.did_coarse ? 5 : 10;
-    const bool is_l3 = k < ctl.n_coarse + ctl.n_l3;
-    subpix_its = is_l3 ? 8 : 0;
-    reproject = is_l3 || ctl.did_coarse;
+    subpix_its = k < ctl.n_coarse + ctl.n_l3 ? 8 : 0;
   }
-  double v2image[2] = {d.p.v2image[2 * g], d.p.v2image[2 * g + 1]};
-  if (reproject) {
-    // ProjectAndDerivs with bFound == false: Project only (Tracker.h:89-94)
-    ProjOut o;
-    project_point(d, ctl.pose, d.p.world + 3 * g, o);
-    if (lane == 0) { d.p.v3cam[3 * g] = o.v3cam[0]; d.p.v3cam[3 * g + 1] = o.v3cam[1]; d.p.v3cam[3 * g + 2] = o.v3cam[2]; }
-    if (o.reached_cam) { v2image[0] = o.v2image[0]; v2image[1] = o.v2image[1]; }
-    fl = o.in_image ? (fl | F_IN_IMAGE) : (fl & ~F_IN_IMAGE);
-  }
+  const double v2image[2] = {d.p.v2image[2 * g], d.p.v2image[2 * g + 1]};  // re-projected by k_search_prep
   const int sl = d.p.search_level[g];
-  // ---- MakeTemplateCoarseCont (PatchFinder.cc:98-127) ----------------------------------------
-  const double wi0 = d.p.warp_inv[4 * g], wi1 = d.p.warp_inv[4 * g + 1], wi2 = d.p.warp_inv[4 * g + 2], wi3 = d.p.warp_inv[4 * g + 3];
-  const double det = wi0 * wi3 - wi2 * wi1;
-  const double idet = 1.0 / det;
-  const double sc = (double)(1 << sl);
-  double m2[4];
-  m2[0] = (wi3 * idet) * sc; m2[3] = (wi0 * idet) * sc;
-  m2[2] = (-wi2 * idet) * sc; m2[1] = (-wi1 * idet) * sc;
-  bool refresh = !(fl & F_HAS_TEMPLATE);
-  if (!refresh) {
-    for (int i = 0; !refresh && i < 2; i++) {
-      const double d0 = m2[i] - d.p.last_warp[4 * g + i], d1 = m2[2 + i] - d.p.last_warp[4 * g + 2 + i];
-      if (d0 * d0 + d1 * d1 > 0.07 * 0.07) refresh = true;
-    }
-  }
+  const bool refresh = (fl & F_REFRESH) != 0;
+  fl &= ~F_REFRESH;
   // lane owns template pixels (row = lane/4, cols 2*(lane%4), +1)
   const int trow = lane >> 2, tcol = (lane & 3) * 2;
   int t0, t1, tsum, tsumsq;
@@ -621,6 +644,7 @@ __global__ void __launch_bounds__(128) k_search(TrackerDev d, int stage) {
     const LevelDesc& SL = d.g.lev[slv];
     const uint8_t* src = d.kf_ptrs[kf] + SL.img_off;
     const int2 c = d.p.center[g];
+    const double m2[4] = {d.p.m2[4 * g], d.p.m2[4 * g + 1], d.p.m2[4 * g + 2], d.p.m2[4 * g + 3]};
     // CVD::transform: p = inOrig + M (out - outOrig), accumulated across/down like libCVD
     const double ax = m2[0], ay = m2[2];
     const double crx = m2[1] - 8 * ax, cry = m2[3] - 8 * ay;
@@ -664,7 +688,7 @@ __global__ void __launch_bounds__(128) k_search(TrackerDev d, int stage) {
   }
   if (fl & F_TEMPLATE_BAD) {  // Tracker.cc:873-876
     fl &= ~(F_IN_IMAGE | F_FOUND);
-    if (lane == 0) { d.p.flags[g] = fl; d.p.v2image[2 * g] = v2image[0]; d.p.v2image[2 * g + 1] = v2image[1]; }
+    if (lane == 0) d.p.flags[g] = fl;
     return;
   }
   if (lane == 0) atomicAdd(&ctl.attempted[sl], 1);
@@ -759,7 +783,7 @@ __global__ void __launch_bounds__(128) k_search(TrackerDev d, int stage) {
   fl |= F_SEARCHED;
   if (!found) {
     fl &= ~F_FOUND;
-    if (lane == 0) { d.p.flags[g] = fl; d.p.v2image[2 * g] = v2image[0]; d.p.v2image[2 * g + 1] = v2image[1]; }
+    if (lane == 0) d.p.flags[g] = fl;
     return;
   }
   fl |= F_FOUND;
@@ -828,7 +852,7 @@ __global__ void __launch_bounds__(128) k_search(TrackerDev d, int stage) {
     }
     if (!converged) {  // Tracker.cc:898-903
       fl &= ~F_FOUND;
-      if (lane == 0) { d.p.flags[g] = fl; d.p.v2image[2 * g] = v2image[0]; d.p.v2image[2 * g + 1] = v2image[1]; }
+      if (lane == 0) d.p.flags[g] = fl;
       return;
     }
     v2found[0] = sp[0]; v2found[1] = sp[1];
@@ -838,7 +862,6 @@ __global__ void __launch_bounds__(128) k_search(TrackerDev d, int stage) {
   if (lane == 0) {
     atomicAdd(&ctl.found[sl], 1);
     d.p.flags[g] = fl;
-    d.p.v2image[2 * g] = v2image[0]; d.p.v2image[2 * g + 1] = v2image[1];
     d.p.v2found[2 * g] = v2found[0]; d.p.v2found[2 * g + 1] = v2found[1];
     d.p.sqrt_inv_noise[g] = 1.0 / (double)(1 << sl);
   }
