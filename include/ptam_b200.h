@@ -221,11 +221,24 @@ int ptam_bundle_add_points(ptam_bundle* b, int n, const double* xyz);
 int ptam_bundle_add_measurements(ptam_bundle* b, int n, const int32_t* cam, const int32_t* point,
                                  const double* uv, const double* sigma_squared);
 
-/* Multi-GPU: this handle holds shard `rank` of `world` (points partitioned by the caller; cameras
- * replicated).  nccl_comm is an ncclComm_t created by the caller (e.g. torch.distributed's) or NULL
- * for world == 1.  The reduced camera system, the error sums and the sigma-squared order statistic
- * are reduced across ranks inside ptam_bundle_compute. */
+/* Multi-GPU (no reference counterpart): one process per GPU, every rank feeds the SAME
+ * graph through the Add* calls, and the handle of rank r keeps the points of its contiguous range
+ * (ptam_bundle_shard_plan, balanced by measurement count) with all their measurements; cameras are
+ * replicated.  Inside ptam_bundle_compute / _lm_step the partial reduced camera system (S, vE) of
+ * every rank is summed with ncclAllReduce (the cross-camera J^T J reduction) and solved identically
+ * everywhere; the sigma-squared order statistic is found exactly by a radix select whose digit
+ * histograms are all-reduced; error sums and abort votes ride in one small all-reduce per lambda
+ * trial.  After compute every rank holds all points, cameras and the merged outlier list.
+ * In a sharded run compute / lm_step / get_point(s) / get_outliers / get_stats are COLLECTIVE.
+ *   ptam_nccl_unique_id   rank 0 creates the id and ships it to the other ranks by any host channel;
+ *   ptam_bundle_init_shard  creates the handle's own communicator from it (ncclCommInitRank);
+ *   ptam_bundle_set_shard   alternatively adopts an ncclComm_t the caller already owns. */
+#define PTAM_NCCL_UNIQUE_ID_BYTES 128
+int ptam_nccl_unique_id(unsigned char id[PTAM_NCCL_UNIQUE_ID_BYTES]);
+int ptam_bundle_init_shard(ptam_bundle* b, int rank, int world, const unsigned char id[PTAM_NCCL_UNIQUE_ID_BYTES]);
 int ptam_bundle_set_shard(ptam_bundle* b, int rank, int world, void* nccl_comm);
+/* Host-only: point_begin[world + 1], shard r owns points [point_begin[r], point_begin[r + 1]). */
+int ptam_bundle_shard_plan(int n_points, int n_meas, const int32_t* meas_point, int world, int32_t* point_begin);
 
 /* Bundle::Compute (Bundle.cc:116-158): returns the number of accepted LM steps (>= 0) or a negative
  * error.  abort_flag is polled between device phases like *pbAbortSignal (Bundle.cc:134,338);

@@ -86,6 +86,7 @@ PRODUCT_ONLY_SYMBOLS = [
     "global_last_error", "tracker_track_frames_device", "tracker_cuda_stream",
     "tracker_launch_count", "tracker_set_profiling", "tracker_get_kernel_times",
     "bundle_cuda_stream", "bundle_launch_count",
+    "nccl_unique_id", "bundle_init_shard", "bundle_shard_plan",
 ]
 TRACKER_KERNELS = ["k_pyramid", "k_fast", "k_compact", "k_pvs_select", "k_search_coarse", "k_pose_coarse",
                    "k_search_fine", "k_pose_fine"]
@@ -167,6 +168,9 @@ class Lib:
             "bundle_add_points": (i, [vp, i, P(d)]),
             "bundle_add_measurements": (i, [vp, i, P(C.c_int32), P(C.c_int32), P(d), P(d)]),
             "bundle_set_shard": (i, [vp, i, i, vp]),
+            "nccl_unique_id": (i, [P(C.c_ubyte)]),
+            "bundle_init_shard": (i, [vp, i, i, P(C.c_ubyte)]),
+            "bundle_shard_plan": (i, [i, i, P(C.c_int32), i, P(C.c_int32)]),
             "bundle_compute": (i, [vp, P(C.c_ubyte)]),
             "bundle_begin": (i, [vp]),
             "bundle_lm_step": (i, [vp, P(C.c_ubyte)]),
@@ -197,6 +201,25 @@ def product_lib() -> Lib:
     if _product is None:
         _product = Lib(LIB_PATH, "ptam_")
     return _product
+
+
+NCCL_UNIQUE_ID_BYTES = 128
+
+
+def nccl_unique_id(lib: Lib) -> bytes:
+    buf = (C.c_ubyte * NCCL_UNIQUE_ID_BYTES)()
+    if lib.fn("nccl_unique_id")(buf) != 0:
+        raise PtamError(lib.fn("global_last_error")().decode())
+    return bytes(buf)
+
+
+def shard_plan(lib: Lib, n_points, meas_point, world):
+    """point_begin[world + 1]: shard r owns points [point_begin[r], point_begin[r + 1])."""
+    mp = _i32(meas_point)
+    out = np.zeros(world + 1, np.int32)
+    if lib.fn("bundle_shard_plan")(int(n_points), len(mp), _ip(mp), int(world), _ip(out)) != 0:
+        raise PtamError("bad shard plan arguments")
+    return out
 
 
 CAMERA_PARAMS = np.array([1.0803, 1.43987, 0.519983, 0.548655, 0.244943])  # config/camera.cfg:7
@@ -416,6 +439,11 @@ class Bundle:
 
     def set_shard(self, rank, world, comm):
         self._chk(self.lib.fn("bundle_set_shard")(self.h, rank, world, C.c_void_p(comm)))
+
+    def init_shard(self, rank, world, unique_id: bytes):
+        """Join the NCCL communicator described by `unique_id` (from nccl_unique_id() on rank 0)."""
+        buf = (C.c_ubyte * NCCL_UNIQUE_ID_BYTES).from_buffer_copy(unique_id)
+        self._chk(self.lib.fn("bundle_init_shard")(self.h, rank, world, buf))
 
     def Compute(self, abort=None):
         return self._chk(self.lib.fn("bundle_compute")(self.h, abort))

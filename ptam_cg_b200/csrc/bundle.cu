@@ -5,12 +5,62 @@
 // where the reference takes them; everything else stays on the device.
 #include "bundle_kernels.cuh"
 
+#include <dlfcn.h>
+#include <nccl.h>  // types and enums only: the symbols are resolved with dlopen (torch's bundled
+                   // libnccl.so.2 when the process already loaded it, else the system library)
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <numeric>
 #include <vector>
 
 using namespace ptam;
+
+namespace {
+struct NcclApi {
+  void* lib = nullptr;
+  bool tried = false;
+  std::string err;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool load() {
+    if (tried) return lib != nullptr;
+    tried = true;
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+      lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) { err = std::string("cannot load NCCL: ") + dlerror(); return false; }
+    GetUniqueId = reinterpret_cast<decltype(GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+    CommInitRank = reinterpret_cast<decltype(CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
+    CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+    AllReduce = reinterpret_cast<decltype(AllReduce)>(dlsym(lib, "ncclAllReduce"));
+    GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+    if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce || !GetErrorString) { err = "NCCL library lacks required symbols"; lib = nullptr; return false; }
+    return true;
+  }
+};
+NcclApi& nccl_api() { static NcclApi a; return a; }
+
+// Contiguous point ranges balanced by measurement count: shard r owns points [begin[r], begin[r+1]).
+void shard_plan(int n_points, int n_meas, const int32_t* meas_point, int world, int32_t* begin) {
+  std::vector<long long> cnt(n_points + 1, 0);
+  for (int m = 0; m < n_meas; m++) cnt[meas_point[m] + 1]++;
+  for (int i = 0; i < n_points; i++) cnt[i + 1] += cnt[i];
+  begin[0] = 0;
+  for (int r = 1; r < world; r++) {
+    const long long target = (long long)n_meas * r / world;
+    int b = (int)(std::lower_bound(cnt.begin(), cnt.end(), target) - cnt.begin());
+    b = std::min(std::max(b, (int)begin[r - 1]), n_points);
+    begin[r] = b;
+  }
+  begin[world] = n_points;
+}
+}  // namespace
 
 ptam::CamModel ptam_make_cam_model(const double* p, double W, double H);
 void ptam_set_global_error(const std::string& e);
@@ -54,9 +104,17 @@ struct ptam_bundle {
   Buf<int> cam_fixed, cam_row, pt_off, pt_meas, m_cam, m_pt, m_state, counters, outliers;
   double* h_scal = nullptr;  // pinned
   int* h_cnt = nullptr;      // pinned
-  // multi-GPU shard
+  // multi-GPU shard: points [p_lo, p_hi) and their measurements live here; cameras are replicated
   int rank = 0, world = 1;
-  void* nccl_comm = nullptr;
+  ncclComm_t comm = nullptr;
+  bool own_comm = false;
+  int p_lo = 0, p_hi = 0;
+  std::vector<int> l_gid;            // local measurement -> insertion index
+  Buf<int> m_gid, m_erase_step, g_steps, hist16;
+  Buf<unsigned long long> sel_state;
+  bool shards_dirty = false, abort_seen = false;
+  std::vector<int> h_outliers;       // merged (point, camera) pairs in the reference's erase order
+  int n_meas_local = 0;
 
   void set_error(const std::string& e) { err = e; }
 
@@ -67,9 +125,22 @@ struct ptam_bundle {
                     &m_v3cam, &m_derivs, &m_eps, &m_e2, &m_W, &e2c, &S, &vE, &upd, &scal, &Wp})
       b->release();
     for (auto* b : {&cam_fixed, &cam_row, &pt_off, &pt_meas, &m_cam, &m_pt, &m_state, &counters, &outliers}) b->release();
+    for (auto* b : {&m_gid, &m_erase_step, &g_steps, &hist16}) b->release();
+    sel_state.release();
+    if (comm && own_comm) nccl_api().CommDestroy(comm);
     if (h_scal) cudaFreeHost(h_scal);
     if (h_cnt) cudaFreeHost(h_cnt);
     if (stream) cudaStreamDestroy(stream);
+  }
+
+  int nccl_try(ncclResult_t r, const char* what) {
+    if (r == ncclSuccess) return PTAM_OK;
+    set_error(std::string(what) + ": " + nccl_api().GetErrorString(r));
+    return PTAM_ERR_NCCL;
+  }
+  int all_reduce(void* buf, size_t count, ncclDataType_t type, ncclRedOp_t op, const char* what) {
+    if (world == 1) return PTAM_OK;
+    return nccl_try(nccl_api().AllReduce(buf, buf, count, type, op, comm, stream), what);
   }
 
   int init(int dev, const double* cam_params, int w, int h, const ptam_bundle_params* p) {
@@ -91,21 +162,39 @@ struct ptam_bundle {
   int n_meas() const { return (int)h_mcam.size(); }
 
   // Compute() before its loop: GenerateMeasLUTs / GenerateOffDiagScripts become a CSR by point with
-  // each point's measurements sorted by camera id (std::set<int> order, Bundle.h:69).
+  // each point's measurements sorted by camera id (std::set<int> order, Bundle.h:69).  A sharded
+  // handle keeps only the measurements of the points it owns.
   int begin() {
     cudaSetDevice(device);
-    const int C = n_cams(), P = n_pts(), M = n_meas();
+    if (world > 1 && !comm) { set_error("sharded handle without a communicator: call ptam_bundle_init_shard first"); return PTAM_ERR_NCCL; }
+    const int C = n_cams(), P = n_pts(), MG = n_meas();
     const int n = 6 * n_free;
+    p_lo = 0; p_hi = P;
+    if (world > 1) {
+      std::vector<int32_t> plan(world + 1);
+      shard_plan(P, MG, h_mpt.data(), world, plan.data());
+      p_lo = plan[rank]; p_hi = plan[rank + 1];
+    }
+    l_gid.clear();
+    std::vector<int> l_mcam, l_mpt;
+    std::vector<double> l_found, l_sin;
+    for (int m = 0; m < MG; m++) {
+      if (h_mpt[m] < p_lo || h_mpt[m] >= p_hi) continue;
+      l_gid.push_back(m); l_mcam.push_back(h_mcam[m]); l_mpt.push_back(h_mpt[m]);
+      l_found.push_back(h_found[2 * m]); l_found.push_back(h_found[2 * m + 1]); l_sin.push_back(h_sin[m]);
+    }
+    const int M = (int)l_gid.size();
+    n_meas_local = M;
     std::vector<int> off(P + 1, 0), idx(M);
-    for (int m = 0; m < M; m++) off[h_mpt[m] + 1]++;
+    for (int m = 0; m < M; m++) off[l_mpt[m] + 1]++;
     for (int i = 0; i < P; i++) off[i + 1] += off[i];
     {
       std::vector<int> cur(off.begin(), off.end() - 1);
-      for (int m = 0; m < M; m++) idx[cur[h_mpt[m]]++] = m;
+      for (int m = 0; m < M; m++) idx[cur[l_mpt[m]]++] = m;
       for (int i = 0; i < P; i++) {
-        std::sort(idx.begin() + off[i], idx.begin() + off[i + 1], [&](int a, int b) { return h_mcam[a] < h_mcam[b]; });
+        std::sort(idx.begin() + off[i], idx.begin() + off[i + 1], [&](int a, int b) { return l_mcam[a] < l_mcam[b]; });
         for (int o = off[i] + 1; o < off[i + 1]; o++)
-          if (h_mcam[idx[o]] == h_mcam[idx[o - 1]]) { set_error("duplicate (camera, point) measurement"); return PTAM_ERR_INVALID; }
+          if (l_mcam[idx[o]] == l_mcam[idx[o - 1]]) { set_error("duplicate (camera, point) measurement"); return PTAM_ERR_INVALID; }
       }
     }
 #define AL(buf, cnt) PTAM_CUDA_TRY(this, buf.alloc(cnt))
@@ -117,21 +206,28 @@ struct ptam_bundle {
     AL(m_derivs, 4 * (size_t)M); AL(m_eps, 2 * (size_t)M); AL(m_e2, M); AL(m_W, 18 * (size_t)M); AL(e2c, M);
     AL(S, (size_t)n * n); AL(vE, n); AL(upd, n); AL(scal, 8); AL(counters, 4); AL(outliers, 2 * (size_t)M);
     AL(Wp, (size_t)n * kNB);
+    AL(m_gid, M); AL(m_erase_step, M); AL(hist16, 65536); AL(sel_state, 2);
+    if (world > 1) AL(g_steps, MG);
 #undef AL
 #define UP(buf, vec) if (!vec.empty()) PTAM_CUDA_TRY(this, cudaMemcpy(buf.p, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice))
     UP(cam_se3, h_cam_se3); UP(cam_fixed, h_cam_fixed); UP(cam_row, h_cam_row); UP(pt_pos, h_pts);
-    UP(pt_off, off); UP(pt_meas, idx); UP(m_cam, h_mcam); UP(m_pt, h_mpt); UP(m_found, h_found); UP(m_sin, h_sin);
+    UP(pt_off, off); UP(pt_meas, idx); UP(m_cam, l_mcam); UP(m_pt, l_mpt); UP(m_found, l_found); UP(m_sin, l_sin);
+    UP(m_gid, l_gid);
 #undef UP
     d.cam = cam; d.n_cams = C; d.n_pts = P; d.n_meas = M; d.n = n; d.est = prm.mestimator;
+    d.p_lo = p_lo; d.p_hi = p_hi; d.add_cam_update = rank == 0 ? 1 : 0;
     d.cam_se3 = cam_se3.p; d.cam_se3_new = cam_se3_new.p; d.cam_fixed = cam_fixed.p; d.cam_row = cam_row.p;
     d.U = U.p; d.epsA = epsA.p; d.pt_pos = pt_pos.p; d.pt_pos_new = pt_pos_new.p; d.V = V.p; d.epsB = epsB.p;
     d.Vinv = Vinv.p; d.Ve = Ve.p; d.pt_off = pt_off.p; d.pt_meas = pt_meas.p; d.m_cam = m_cam.p; d.m_pt = m_pt.p;
     d.m_found = m_found.p; d.m_sin = m_sin.p; d.m_state = m_state.p; d.m_v3cam = m_v3cam.p; d.m_derivs = m_derivs.p;
     d.m_eps = m_eps.p; d.m_e2 = m_e2.p; d.m_W = m_W.p; d.e2_compact = e2c.p; d.S = S.p; d.vE = vE.p; d.upd = upd.p;
     d.scal = scal.p; d.counters = counters.p; d.outliers = outliers.p;
+    d.hist16 = hist16.p; d.sel_state = sel_state.p; d.m_erase_step = m_erase_step.p;
     lambda = 0.0001; lambda_factor = 2.0;
-    converged = false; hit_max = false;
+    converged = false; hit_max = false; abort_seen = false;
     counter = 0; accepted = 0; lm_steps = 0; n_outliers = 0;
+    h_outliers.clear();
+    shards_dirty = false;
     begun = true;
     return PTAM_OK;
   }
@@ -157,13 +253,44 @@ struct ptam_bundle {
     return PTAM_OK;
   }
 
+  // sigma^2 (Bundle.cc:230-237).  Small single-GPU problems: one-CTA select on the compacted errors;
+  // large or sharded ones: 4-pass 16-bit radix select whose histograms are summed across shards.
+  int find_sigma_squared() {
+    const int M = d.n_meas;
+    const double min_s2 = prm.min_tukey_sigma * prm.min_tukey_sigma;
+    if (world == 1 && M < 65536) {
+      if (M > 0) {
+        const int gm = (M + 255) / 256;
+        k_ba_gather_e2<<<gm, 256, 0, stream>>>(d);
+        k_ba_select<<<1, 1024, 0, stream>>>(d, min_s2);
+        launches += 2;
+      }
+      return PTAM_OK;
+    }
+    for (int pass = 0; pass < 4; pass++) {
+      PTAM_CUDA_TRY(this, cudaMemsetAsync(hist16.p, 0, sizeof(int) * 65536, stream));
+      if (M > 0) { k_ba_hist16<<<std::min((M + 255) / 256, 148 * 8), 256, 0, stream>>>(d, pass); launches++; }
+      int rc = all_reduce(hist16.p, 65536, ncclInt32, ncclSum, "all-reduce of the select histogram");
+      if (rc) return rc;
+      k_ba_pick16<<<1, 1024, 0, stream>>>(d, pass, min_s2);
+      launches++;
+    }
+    return PTAM_OK;
+  }
+
   // Do_LM_Step (Bundle.cc:209-551)
   int lm_step(const volatile unsigned char* abort_flag) {
     cudaSetDevice(device);
     if (!begun) { set_error("ptam_bundle_begin() has not been called"); return PTAM_ERR_INVALID; }
-    auto aborted = [&]() { return abort_flag && *abort_flag; };
+    // a sharded run must take the same branch on every rank: the local flags are summed with the
+    // error scalars and only the reduced value is acted on
+    auto local_abort = [&]() { return abort_flag && *abort_flag; };
+    auto aborted = [&]() { return world > 1 ? abort_seen : local_abort(); };
     const int C = d.n_cams, P = d.n_pts, M = d.n_meas, n = d.n;
+    const int PO = d.p_hi - d.p_lo;  // points owned by this shard
+    int rc;
     lm_steps++;
+    shards_dirty = true;
     // ClearAccumulators + error / counter scalars
     PTAM_CUDA_TRY(this, cudaMemsetAsync(U.p, 0, sizeof(double) * 21 * C, stream));
     PTAM_CUDA_TRY(this, cudaMemsetAsync(epsA.p, 0, sizeof(double) * 6 * C, stream));
@@ -171,47 +298,50 @@ struct ptam_bundle {
     PTAM_CUDA_TRY(this, cudaMemsetAsync(epsB.p, 0, sizeof(double) * 3 * P, stream));
     PTAM_CUDA_TRY(this, cudaMemsetAsync(scal.p, 0, sizeof(double) * 8, stream));
     PTAM_CUDA_TRY(this, cudaMemsetAsync(counters.p, 0, sizeof(int), stream));
-    if (M > 0) {
-      const int gm = (M + 255) / 256;
-      k_ba_project<<<gm, 256, 0, stream>>>(d);
-      k_ba_gather_e2<<<gm, 256, 0, stream>>>(d);
-      k_ba_select<<<1, 1024, 0, stream>>>(d, prm.min_tukey_sigma * prm.min_tukey_sigma);
-      k_ba_jacobian<<<(M + 127) / 128, 128, 0, stream>>>(d);
-      launches += 4;
-    }
+    if (M > 0) { k_ba_project<<<(M + 255) / 256, 256, 0, stream>>>(d); launches++; }
+    if ((rc = find_sigma_squared())) return rc;
+    if (M > 0) { k_ba_jacobian<<<(M + 127) / 128, 128, 0, stream>>>(d); launches++; }
     PTAM_CUDA_TRY(this, cudaGetLastError());
+    if (world > 1) {
+      h_scal[5] = local_abort() ? 1.0 : 0.0;
+      PTAM_CUDA_TRY(this, cudaMemcpyAsync(scal.p + 5, h_scal + 5, sizeof(double), cudaMemcpyHostToDevice, stream));
+      if ((rc = all_reduce(scal.p + 2, 4, ncclDouble, ncclSum, "all-reduce of the error sums"))) return rc;
+    }
     PTAM_CUDA_TRY(this, cudaMemcpyAsync(h_scal, scal.p, sizeof(double) * 8, cudaMemcpyDeviceToHost, stream));
     PTAM_CUDA_TRY(this, cudaStreamSynchronize(stream));
     sigma_sq = h_scal[1];
     const double cur_err = h_scal[2];
+    if (world > 1) abort_seen = h_scal[5] > 0.0;
     last_error = cur_err;
     double new_err = cur_err + 9999;
     while (new_err > cur_err && !converged && !hit_max && !aborted()) {
-      // scal[3] new error, scal[4] squared update, scal[5] lambda
+      // scal[3] new error, scal[4] squared update, scal[5] abort votes, scal[6] lambda
       trial_lambda = lambda;
-      double init[3] = {0.0, 0.0, lambda};
-      h_scal[3] = init[0]; h_scal[4] = init[1]; h_scal[5] = init[2];
-      PTAM_CUDA_TRY(this, cudaMemcpyAsync(scal.p + 3, h_scal + 3, sizeof(double) * 3, cudaMemcpyHostToDevice, stream));
-      if (P > 0) k_ba_vinv<<<(P + 255) / 256, 256, 0, stream>>>(d);
+      h_scal[3] = 0.0; h_scal[4] = 0.0; h_scal[5] = (world > 1 && local_abort()) ? 1.0 : 0.0; h_scal[6] = lambda;
+      PTAM_CUDA_TRY(this, cudaMemcpyAsync(scal.p + 3, h_scal + 3, sizeof(double) * 4, cudaMemcpyHostToDevice, stream));
+      if (PO > 0) { k_ba_vinv<<<(PO + 255) / 256, 256, 0, stream>>>(d); launches++; }
       if (n > 0) {
         k_ba_init_s<<<std::min<size_t>(((size_t)n * n + 255) / 256, 148 * 8), 256, 0, stream>>>(d);
         k_ba_init_diag<<<C, 64, 0, stream>>>(d);
         launches += 2;
       }
-      if (P > 0) k_ba_schur<<<(P + 7) / 8, 256, 0, stream>>>(d);
-      launches += 2;
+      if (PO > 0) { k_ba_schur<<<(PO + 7) / 8, 256, 0, stream>>>(d); launches++; }
       s_mirrored = false;
-      int rc = solve_reduced();
-      if (rc) return rc;
-      if (P > 0) k_ba_point_update<<<(P + 255) / 256, 256, 0, stream>>>(d);
-      if (C > 0) k_ba_cam_update<<<(C + 127) / 128, 128, 0, stream>>>(d);
-      if (M > 0) k_ba_new_error<<<(M + 255) / 256, 256, 0, stream>>>(d);
-      launches += 3;
+      if (n > 0) {  // the cross-camera J^T J reduction: partial S, vE of every shard -> total on every shard
+        if ((rc = all_reduce(d.S, (size_t)n * n, ncclDouble, ncclSum, "all-reduce of S"))) return rc;
+        if ((rc = all_reduce(d.vE, n, ncclDouble, ncclSum, "all-reduce of vE"))) return rc;
+      }
+      if ((rc = solve_reduced())) return rc;
+      if (PO > 0) { k_ba_point_update<<<(PO + 255) / 256, 256, 0, stream>>>(d); launches++; }
+      if (C > 0) { k_ba_cam_update<<<(C + 127) / 128, 128, 0, stream>>>(d); launches++; }
+      if (M > 0) { k_ba_new_error<<<(M + 255) / 256, 256, 0, stream>>>(d); launches++; }
       PTAM_CUDA_TRY(this, cudaGetLastError());
-      PTAM_CUDA_TRY(this, cudaMemcpyAsync(h_scal + 3, scal.p + 3, sizeof(double) * 2, cudaMemcpyDeviceToHost, stream));
+      if ((rc = all_reduce(scal.p + 3, 3, ncclDouble, ncclSum, "all-reduce of the trial scalars"))) return rc;
+      PTAM_CUDA_TRY(this, cudaMemcpyAsync(h_scal + 3, scal.p + 3, sizeof(double) * 3, cudaMemcpyDeviceToHost, stream));
       PTAM_CUDA_TRY(this, cudaStreamSynchronize(stream));
       new_err = h_scal[3];
       last_new_error = new_err;
+      if (world > 1) abort_seen = h_scal[5] > 0.0;
       if (h_scal[4] < prm.update_squared_convergence) converged = true;
       if (new_err > cur_err) { lambda = lambda * lambda_factor; lambda_factor = lambda_factor * 2; }  // ModifyLambda_BadStep
       counter++;
@@ -220,13 +350,45 @@ struct ptam_bundle {
     if (new_err < cur_err) {  // ModifyLambda_GoodStep + commit
       lambda_factor = 2.0; lambda *= 0.3;
       PTAM_CUDA_TRY(this, cudaMemcpyAsync(cam_se3.p, cam_se3_new.p, sizeof(double) * 12 * C, cudaMemcpyDeviceToDevice, stream));
-      PTAM_CUDA_TRY(this, cudaMemcpyAsync(pt_pos.p, pt_pos_new.p, sizeof(double) * 3 * P, cudaMemcpyDeviceToDevice, stream));
+      if (PO > 0)
+        PTAM_CUDA_TRY(this, cudaMemcpyAsync(pt_pos.p + 3 * (size_t)d.p_lo, pt_pos_new.p + 3 * (size_t)d.p_lo, sizeof(double) * 3 * PO,
+                                            cudaMemcpyDeviceToDevice, stream));
       accepted++;
     }
-    if (M > 0) { k_ba_erase<<<1, 1024, 0, stream>>>(d); launches++; }
+    if (M > 0) { k_ba_erase<<<1, 1024, 0, stream>>>(d, lm_steps); launches++; }
     PTAM_CUDA_TRY(this, cudaMemcpyAsync(h_cnt, counters.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, stream));
     PTAM_CUDA_TRY(this, cudaStreamSynchronize(stream));
     n_outliers = h_cnt[1];
+    return PTAM_OK;
+  }
+
+  // Sharded handles: make every rank hold all adjusted points and the merged outlier list (in the
+  // reference's erase order: LM step by LM step, measurement list order inside a step).  Collective.
+  int sync_shards() {
+    if (world == 1 || !begun || !shards_dirty) return PTAM_OK;
+    cudaSetDevice(device);
+    const int P = d.n_pts, MG = n_meas(), M = d.n_meas;
+    int rc;
+    if (d.p_lo > 0) PTAM_CUDA_TRY(this, cudaMemsetAsync(pt_pos.p, 0, sizeof(double) * 3 * (size_t)d.p_lo, stream));
+    if (d.p_hi < P) PTAM_CUDA_TRY(this, cudaMemsetAsync(pt_pos.p + 3 * (size_t)d.p_hi, 0, sizeof(double) * 3 * (size_t)(P - d.p_hi), stream));
+    if (P > 0 && (rc = all_reduce(pt_pos.p, 3 * (size_t)P, ncclDouble, ncclSum, "all-gather of the points"))) return rc;
+    h_outliers.clear();
+    if (MG > 0) {
+      PTAM_CUDA_TRY(this, cudaMemsetAsync(g_steps.p, 0, sizeof(int) * (size_t)MG, stream));
+      if (M > 0) { k_ba_scatter_steps<<<(M + 255) / 256, 256, 0, stream>>>(m_erase_step.p, m_gid.p, g_steps.p, M); launches++; }
+      if ((rc = all_reduce(g_steps.p, MG, ncclInt32, ncclMax, "all-reduce of the outlier marks"))) return rc;
+      std::vector<int> steps(MG);
+      PTAM_CUDA_TRY(this, cudaMemcpyAsync(steps.data(), g_steps.p, sizeof(int) * (size_t)MG, cudaMemcpyDeviceToHost, stream));
+      PTAM_CUDA_TRY(this, cudaStreamSynchronize(stream));
+      std::vector<int> ids;
+      for (int m = 0; m < MG; m++) if (steps[m] > 0) ids.push_back(m);
+      std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) { return steps[a] < steps[b]; });
+      for (int m : ids) { h_outliers.push_back(h_mpt[m]); h_outliers.push_back(h_mcam[m]); }
+    } else {
+      PTAM_CUDA_TRY(this, cudaStreamSynchronize(stream));
+    }
+    n_outliers = (int)h_outliers.size() / 2;
+    shards_dirty = false;
     return PTAM_OK;
   }
 };
@@ -286,8 +448,43 @@ int ptam_bundle_add_measurements(ptam_bundle* b, int n, const int32_t* cam, cons
 
 int ptam_bundle_set_shard(ptam_bundle* b, int rank, int world, void* comm) {
   if (world < 1 || rank < 0 || rank >= world) { b->set_error("bad shard description"); return PTAM_ERR_INVALID; }
-  if (world > 1) { b->set_error("sharded bundle adjustment is not available in this build"); return PTAM_ERR_NCCL; }
-  b->rank = rank; b->world = world; b->nccl_comm = comm;
+  if (world > 1 && !comm) { b->set_error("world > 1 needs an ncclComm_t (or use ptam_bundle_init_shard)"); return PTAM_ERR_NCCL; }
+  if (world > 1 && !nccl_api().load()) { b->set_error(nccl_api().err); return PTAM_ERR_NCCL; }
+  if (b->comm && b->own_comm) nccl_api().CommDestroy(b->comm);
+  b->rank = rank; b->world = world; b->comm = world > 1 ? (ncclComm_t)comm : nullptr; b->own_comm = false;
+  b->begun = false;
+  return PTAM_OK;
+}
+
+int ptam_nccl_unique_id(unsigned char id[PTAM_NCCL_UNIQUE_ID_BYTES]) {
+  static_assert(sizeof(ncclUniqueId) == PTAM_NCCL_UNIQUE_ID_BYTES, "ncclUniqueId size");
+  if (!nccl_api().load()) { ptam_set_global_error(nccl_api().err); return PTAM_ERR_NCCL; }
+  ncclUniqueId u;
+  const ncclResult_t r = nccl_api().GetUniqueId(&u);
+  if (r != ncclSuccess) { ptam_set_global_error(std::string("ncclGetUniqueId: ") + nccl_api().GetErrorString(r)); return PTAM_ERR_NCCL; }
+  std::memcpy(id, &u, sizeof(u));
+  return PTAM_OK;
+}
+
+int ptam_bundle_init_shard(ptam_bundle* b, int rank, int world, const unsigned char id[PTAM_NCCL_UNIQUE_ID_BYTES]) {
+  if (world < 1 || rank < 0 || rank >= world) { b->set_error("bad shard description"); return PTAM_ERR_INVALID; }
+  if (b->comm && b->own_comm) { nccl_api().CommDestroy(b->comm); b->comm = nullptr; }
+  b->rank = rank; b->world = world; b->own_comm = false; b->begun = false;
+  if (world == 1) return PTAM_OK;
+  if (!nccl_api().load()) { b->set_error(nccl_api().err); return PTAM_ERR_NCCL; }
+  cudaSetDevice(b->device);
+  ncclUniqueId u;
+  std::memcpy(&u, id, sizeof(u));
+  int rc = b->nccl_try(nccl_api().CommInitRank(&b->comm, world, u, rank), "ncclCommInitRank");
+  if (rc) { b->comm = nullptr; return rc; }
+  b->own_comm = true;
+  return PTAM_OK;
+}
+
+int ptam_bundle_shard_plan(int n_points, int n_meas, const int32_t* meas_point, int world, int32_t* point_begin) {
+  if (n_points < 0 || n_meas < 0 || world < 1 || !point_begin) return PTAM_ERR_INVALID;
+  for (int m = 0; m < n_meas; m++) if (meas_point[m] < 0 || meas_point[m] >= n_points) return PTAM_ERR_INVALID;
+  shard_plan(n_points, n_meas, meas_point, world, point_begin);
   return PTAM_OK;
 }
 
@@ -297,10 +494,13 @@ int ptam_bundle_lm_step(ptam_bundle* b, const volatile unsigned char* abort_flag
 int ptam_bundle_compute(ptam_bundle* b, const volatile unsigned char* abort_flag) {  // Bundle.cc:116-158
   int rc = b->begin();
   if (rc) return rc;
-  while (!b->converged && !b->hit_max && !(abort_flag && *abort_flag)) {
+  // a sharded run acts on the reduced abort votes only, so that all ranks leave the loop together
+  while (!b->converged && !b->hit_max && !(b->world > 1 ? b->abort_seen : (abort_flag && *abort_flag))) {
     rc = b->lm_step(abort_flag);
     if (rc) return rc;
   }
+  rc = b->sync_shards();
+  if (rc) return rc;
   return b->accepted;
 }
 
@@ -308,6 +508,7 @@ int ptam_bundle_converged(const ptam_bundle* b) { return b->converged ? 1 : 0; }
 
 int ptam_bundle_get_points(ptam_bundle* b, double* xyz) {
   cudaSetDevice(b->device);
+  { const int rc = b->sync_shards(); if (rc) return rc; }
   if (!b->begun) { std::memcpy(xyz, b->h_pts.data(), b->h_pts.size() * sizeof(double)); return PTAM_OK; }
   PTAM_CUDA_TRY(b, cudaStreamSynchronize(b->stream));
   PTAM_CUDA_TRY(b, cudaMemcpy(xyz, b->pt_pos.p, sizeof(double) * 3 * b->d.n_pts, cudaMemcpyDeviceToHost));
@@ -322,6 +523,7 @@ int ptam_bundle_get_cameras(ptam_bundle* b, double* se3) {
 }
 int ptam_bundle_get_point(ptam_bundle* b, int n, double* xyz) {
   cudaSetDevice(b->device);
+  { const int rc = b->sync_shards(); if (rc) return rc; }
   if (n < 0 || n >= b->n_pts()) { b->set_error("bad point id"); return PTAM_ERR_INVALID; }
   if (!b->begun) { std::memcpy(xyz, b->h_pts.data() + 3 * n, 24); return PTAM_OK; }
   PTAM_CUDA_TRY(b, cudaStreamSynchronize(b->stream));
@@ -339,6 +541,13 @@ int ptam_bundle_get_camera(ptam_bundle* b, int n, double* se3) {
 int ptam_bundle_get_outliers(ptam_bundle* b, int32_t* pairs, int cap) {
   cudaSetDevice(b->device);
   if (!b->begun) return 0;
+  if (b->world > 1) {
+    const int rc = b->sync_shards();
+    if (rc) return rc;
+    const int n = b->n_outliers;
+    if (pairs && cap > 0 && n > 0) std::memcpy(pairs, b->h_outliers.data(), sizeof(int) * 2 * std::min(n, cap));
+    return n;
+  }
   PTAM_CUDA_TRY(b, cudaStreamSynchronize(b->stream));
   const int n = b->n_outliers;
   if (pairs && cap > 0 && n > 0)
@@ -346,6 +555,7 @@ int ptam_bundle_get_outliers(ptam_bundle* b, int32_t* pairs, int cap) {
   return n;
 }
 int ptam_bundle_get_stats(ptam_bundle* b, ptam_bundle_stats* s) {
+  { const int rc = b->sync_shards(); if (rc) return rc; }
   s->accepted = b->accepted; s->lambda_trials = b->counter; s->lm_steps = b->lm_steps;
   s->converged = b->converged; s->hit_max_iterations = b->hit_max; s->n_outliers = b->n_outliers;
   s->sigma_squared = b->sigma_sq; s->lambda = b->lambda; s->last_error = b->last_error; s->last_new_error = b->last_new_error;
@@ -360,12 +570,15 @@ int ptam_bundle_get_reduced_system(ptam_bundle* b, double* S, double* vE, int ca
   if (cap_n < n || n == 0) return n;
   // re-assemble S, vE for the current lambda / accumulators (same kernels as the LM loop)
   double l = b->trial_lambda;
-  PTAM_CUDA_TRY(b, cudaMemcpyAsync(b->scal.p + 5, &l, sizeof(double), cudaMemcpyHostToDevice, b->stream));
+  PTAM_CUDA_TRY(b, cudaMemcpyAsync(b->scal.p + 6, &l, sizeof(double), cudaMemcpyHostToDevice, b->stream));
   PTAM_CUDA_TRY(b, cudaStreamSynchronize(b->stream));
-  if (b->d.n_pts > 0) k_ba_vinv<<<(b->d.n_pts + 255) / 256, 256, 0, b->stream>>>(b->d);
+  const int PO = b->d.p_hi - b->d.p_lo;
+  if (PO > 0) k_ba_vinv<<<(PO + 255) / 256, 256, 0, b->stream>>>(b->d);
   k_ba_init_s<<<std::min<size_t>(((size_t)n * n + 255) / 256, 148 * 8), 256, 0, b->stream>>>(b->d);
   k_ba_init_diag<<<b->d.n_cams, 64, 0, b->stream>>>(b->d);
-  if (b->d.n_pts > 0) k_ba_schur<<<(b->d.n_pts + 7) / 8, 256, 0, b->stream>>>(b->d);
+  if (PO > 0) k_ba_schur<<<(PO + 7) / 8, 256, 0, b->stream>>>(b->d);
+  { int rc = b->all_reduce(b->d.S, (size_t)n * n, ncclDouble, ncclSum, "all-reduce of S"); if (rc) return rc;
+    rc = b->all_reduce(b->d.vE, n, ncclDouble, ncclSum, "all-reduce of vE"); if (rc) return rc; }
   k_ba_mirror<<<std::min<size_t>(((size_t)n * n + 255) / 256, 148 * 8), 256, 0, b->stream>>>(b->d.S, n);
   b->launches += 5;
   PTAM_CUDA_TRY(b, cudaGetLastError());

@@ -21,8 +21,10 @@ enum : int { M_ALIVE = 0, M_BAD = 1, M_ERASED = 2 };
 
 struct BundleDev {
   CamModel cam;
-  int n_cams, n_pts, n_meas, n;  // n = 6 * non-fixed cameras
+  int n_cams, n_pts, n_meas, n;  // n = 6 * non-fixed cameras; n_meas = measurements held by THIS shard
   int est;
+  int p_lo, p_hi;        // points owned by this shard [p_lo, p_hi); everything for world == 1
+  int add_cam_update;    // 1 on the rank that contributes the (replicated) camera part of |delta|^2
   // cameras
   double* cam_se3;      // [C][12]
   double* cam_se3_new;  // [C][12]
@@ -55,10 +57,13 @@ struct BundleDev {
   double* vE;  // [n]
   double* upd; // [n] camera update
   // scalars: 0 n_valid (as double), 1 sigma^2, 2 current error, 3 new error, 4 sum sq update,
-  //          5 lambda, 6 median
+  //          5 abort votes, 6 lambda, 7 median   (2..5 are the slots summed across shards)
   double* scal;
+  int* hist16;                   // [65536] digit histogram of the distributed radix select
+  unsigned long long* sel_state; // [0] key prefix found so far, [1] rank still to find inside it
   int* counters;  // 0 n_valid, 1 n_outliers_total, 2 n_bad_this_step
   int* outliers;  // [M][2] (point, camera) in erase order
+  int* m_erase_step;  // [M] LM step (1-based) at which the measurement was erased, 0 = still in the graph
 };
 
 PTAM_DEV double block_sum(double v, double* sh /*32*/) {
@@ -152,9 +157,86 @@ __global__ void __launch_bounds__(1024) k_ba_select(BundleDev d, double min_sigm
     const double med = __longlong_as_double((long long)prefix);
     double s2 = mest_sigma_from_median(med, n, d.est);
     if (s2 < min_sigma_sq) s2 = min_sigma_sq;
-    d.scal[6] = med;
+    d.scal[7] = med;
     d.scal[1] = s2;
     d.scal[0] = (double)n;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Exact order statistic for large or sharded problems: MSB-first radix select with 16-bit digits
+// (4 passes).  Every pass: k_ba_hist16 (all CTAs, global atomics into 65536 bins) -> [all-reduce of
+// the bins across shards] -> k_ba_pick16 (one CTA finds the bin holding the wanted rank).  After
+// the last pass the prefix IS the bit pattern of the floor(n/2)-th smallest squared error
+// (Tools.h:152-162 sorts and takes element n/2), identical on every shard.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ba_hist16(BundleDev d, int pass) {
+  const int shift = 48 - 16 * pass;
+  const unsigned long long prefix = d.sel_state[0];
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < d.n_meas; m += gridDim.x * blockDim.x) {
+    if (d.m_state[m] != M_ALIVE) continue;
+    const unsigned long long key = (unsigned long long)__double_as_longlong(d.m_e2[m]);
+    if (pass == 0 || (key >> (shift + 16)) == (prefix >> (shift + 16))) atomicAdd(&d.hist16[(key >> shift) & 0xffff], 1);
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_ba_pick16(BundleDev d, int pass, double min_sigma_sq) {
+  __shared__ int wsum[32];
+  __shared__ int total_s;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int shift = 48 - 16 * pass;
+  int tot = 0;
+  {
+    const int4* h4 = reinterpret_cast<const int4*>(d.hist16 + 64 * t);
+#pragma unroll 4
+    for (int q = 0; q < 16; q++) { const int4 v = h4[q]; tot += v.x + v.y + v.z + v.w; }
+  }
+  int inc = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(kFull, inc, o);
+    if (lane >= o) inc += v;
+  }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int ws = wsum[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(kFull, ws, o);
+      if (lane >= o) ws += v;
+    }
+    wsum[lane] = ws;
+    if (lane == 31) total_s = ws;
+  }
+  __syncthreads();
+  const int n_all = total_s;  // pass 0: number of valid measurements over all shards
+  long long kk = pass == 0 ? (long long)(n_all / 2) : (long long)d.sel_state[1];
+  const int excl = (warp ? wsum[warp - 1] : 0) + inc - tot;
+  if (n_all > 0 && kk >= excl && kk < excl + tot) {  // exactly one thread
+    int r = (int)(kk - excl), q = 0;
+    while (q < 63 && r >= d.hist16[64 * t + q]) { r -= d.hist16[64 * t + q]; q++; }
+    const unsigned long long prefix = (pass == 0 ? 0ull : d.sel_state[0]) | ((unsigned long long)(64 * t + q) << shift);
+    d.sel_state[0] = prefix;
+    d.sel_state[1] = (unsigned long long)r;
+    if (pass == 3) {
+      const double med = __longlong_as_double((long long)prefix);
+      const long long n = (long long)d.scal[0];
+      double s2 = mest_sigma_from_median(med, n, d.est);
+      if (s2 < min_sigma_sq) s2 = min_sigma_sq;
+      d.scal[7] = med;
+      d.scal[1] = s2;
+    }
+  }
+  if (pass == 0 && t == 0) {
+    d.scal[0] = (double)n_all;
+    d.counters[0] = n_all;
+    if (n_all == 0) {  // no valid measurement anywhere: same result as the single-CTA select on n = 0
+      double s2 = mest_sigma_from_median(0.0, 0, d.est);
+      if (s2 < min_sigma_sq) s2 = min_sigma_sq;
+      d.scal[7] = 0.0; d.scal[1] = s2;
+      d.sel_state[0] = 0ull; d.sel_state[1] = 0ull;
+    }
   }
 }
 
@@ -266,9 +348,9 @@ __global__ void __launch_bounds__(128) k_ba_jacobian(BundleDev d) {
 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_ba_vinv(BundleDev d) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= d.n_pts) return;
-  const double lambda = d.scal[5];
+  const int i = d.p_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.p_hi) return;
+  const double lambda = d.scal[6];
   const double* v = d.V + 6 * i;
   double Vs[9] = {v[0], v[1], v[3], v[1], v[2], v[4], v[3], v[4], v[5]};
   double inv[9];
@@ -295,7 +377,7 @@ __global__ void __launch_bounds__(64) k_ba_init_diag(BundleDev d) {
   const int c = blockIdx.x;
   const int row = d.cam_row[c];
   if (row < 0) return;
-  const double lambda = d.scal[5];
+  const double lambda = d.scal[6];
   const int t = threadIdx.x;
   if (t < 36) {
     const int r = t / 6, cc = t % 6;
@@ -308,8 +390,8 @@ __global__ void __launch_bounds__(64) k_ba_init_diag(BundleDev d) {
 
 // warp per point: all camera pairs (j >= k) observing it, both cameras free, both measurements good
 __global__ void __launch_bounds__(256) k_ba_schur(BundleDev d) {
-  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (i >= d.n_pts) return;
+  const int i = d.p_lo + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= d.p_hi) return;
   const int lane = threadIdx.x & 31;
   const int o0 = d.pt_off[i], k = d.pt_off[i + 1] - o0;
   if (k == 0) return;
@@ -523,9 +605,9 @@ __global__ void __launch_bounds__(1024) k_ldlt_solve(const double* A, const doub
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_ba_point_update(BundleDev d) {
   __shared__ double sh[32];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = d.p_lo + blockIdx.x * blockDim.x + threadIdx.x;
   double ss = 0.0;
-  if (i < d.n_pts) {
+  if (i < d.p_hi) {
     double sum[3] = {0, 0, 0};
     for (int o = d.pt_off[i]; o < d.pt_off[i + 1]; o++) {
       const int m = d.pt_meas[o];
@@ -564,7 +646,7 @@ __global__ void __launch_bounds__(128) k_ba_cam_update(BundleDev d) {
       for (int k = 0; k < 12; k++) d.cam_se3_new[12 * c + k] = d.cam_se3[12 * c + k];
     } else {
       double mu[6], ex[12], np[12];
-      for (int k = 0; k < 6; k++) { mu[k] = d.upd[row + k]; ss += mu[k] * mu[k]; }
+      for (int k = 0; k < 6; k++) { mu[k] = d.upd[row + k]; if (d.add_cam_update) ss += mu[k] * mu[k]; }
       se3_exp(mu, ex);
       se3_mul(ex, d.cam_se3 + 12 * c, np);
       for (int k = 0; k < 12; k++) d.cam_se3_new[12 * c + k] = np[k];
@@ -594,7 +676,7 @@ __global__ void __launch_bounds__(256) k_ba_new_error(BundleDev d) {
 }
 
 // end of an LM step: erase the bad measurements, appending (point, camera) in list order
-__global__ void __launch_bounds__(1024) k_ba_erase(BundleDev d) {
+__global__ void __launch_bounds__(1024) k_ba_erase(BundleDev d, int step) {
   __shared__ int wcnt[32];
   __shared__ int base_s;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -612,12 +694,19 @@ __global__ void __launch_bounds__(1024) k_ba_erase(BundleDev d) {
       const int o = before + __popc(b & ((1u << lane) - 1));
       d.outliers[2 * o] = d.m_pt[m]; d.outliers[2 * o + 1] = d.m_cam[m];
       d.m_state[m] = M_ERASED;
+      d.m_erase_step[m] = step;
     }
     __syncthreads();
     if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += wcnt[w]; base_s += t; }
     __syncthreads();
   }
   if (threadIdx.x == 0) d.counters[1] = base_s;
+}
+
+// sharded handles: local erase marks -> global measurement order (merged with an all-reduce max)
+__global__ void __launch_bounds__(256) k_ba_scatter_steps(const int* step, const int* gid, int* out, int n) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < n && step[m] > 0) out[gid[m]] = step[m];
 }
 
 }  // namespace ptam
