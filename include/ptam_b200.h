@@ -264,6 +264,13 @@ int ptam_bundle_get_reduced_system(ptam_bundle* b, double* S, double* vE, int ca
 int ptam_bundle_synchronize(ptam_bundle* b);
 void* ptam_bundle_cuda_stream(ptam_bundle* b);
 int64_t ptam_bundle_launch_count(const ptam_bundle* b);
+/* Per-phase device timing (CUDA events on the handle's stream).  Phase ids: 0 project (Bundle.cc:219-225),
+ * 1 sigma-squared select (:230-237), 2 Jacobian/accumulate (:251-332), 3 V*^-1 + S/vE init (:341-392),
+ * 4 Schur build (:396-446), 5 cross-shard all-reduce of S/vE, 6 dense LDL^T solve (:457-458),
+ * 7 updates + FindNewError (:461-506).  Turning it on or off resets the accumulators. */
+#define PTAM_BA_PHASES 8
+int ptam_bundle_set_profiling(ptam_bundle* b, int on);
+int ptam_bundle_get_phase_times(ptam_bundle* b, double ms_total[PTAM_BA_PHASES], int64_t count[PTAM_BA_PHASES]);
 
 #ifdef __cplusplus
 }

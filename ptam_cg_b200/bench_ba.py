@@ -1,40 +1,82 @@
-"""BA leg of bench.py: Bundle::Compute on the synthetic C3 graph (50 keyframes x 5000 points x
-20000 measurements), lambda-trials/s on one B200 next to the CPU oracle port on one core."""
+"""BA legs of bench.py: Bundle::Compute on the synthetic graphs of SURVEY.md §8d.
+
+C3: 50 keyframes x 5 000 points x 20 000 measurements on one B200.
+C4: 500 keyframes x 100 000 points x 600 000 measurements, one B200 or sharded over the ranks of a
+    torchrun job (points partitioned, NCCL all-reduce of the reduced camera system per lambda trial).
+Unit: lambda trials / s (one trial = V*^-1, Schur build, dense solve, updates, FindNewError plus the
+amortised projection / Jacobian pass of its LM step).  Timing: device time between CUDA events on
+the handle's stream around the whole ptam_bundle_compute call (host LM control included).
+"""
 import time
+
+import numpy as np
 
 from . import synth
 from .capi import Bundle
 
+CONFIGS = {
+    "C3": dict(n_cams=50, n_points=5000, n_meas=20000, seed=42),
+    "C4": dict(n_cams=500, n_points=100000, n_meas=600000, seed=43),
+}
 
-def bench_ba(prod, device=0, n_cams=50, n_points=5000, n_meas=20000, seed=42, reps=5, cpu_lib=None):
-    """cpu_lib: an already-loaded CPU library exporting the same ABI (bench.py passes the oracle for the
-    cpu_baseline leg); this package never loads it itself."""
-    g = synth.make_ba_graph(n_cams, n_points, n_meas, seed=seed)
+
+def flops_per_trial(n):
+    """dense LDL^T + two triangular solves."""
+    return n ** 3 / 3.0 + 2.0 * n ** 2
+
+
+def bench_ba(prod, device=0, config="C3", reps=3, cpu_lib=None, shard=None, graph=None, cpu_trials=None):
+    """shard: None or (rank, world, nccl_unique_id_bytes).  cpu_lib: an already-loaded CPU library
+    exporting the same ABI (bench.py passes the oracle for the cpu_baseline leg; this package never
+    loads it itself).  cpu_trials: cap on the CPU leg's lambda trials (bounded sample)."""
+    import torch
+    cfg = CONFIGS[config]
+    g = graph if graph is not None else synth.make_ba_graph(**cfg)
+    n = 6 * int((np.asarray(g["cam_fixed"]) == 0).sum())
     best = None
     for r in range(reps + 1):  # first repetition is the warm-up
         b = Bundle(prod, g["width"], g["height"], device=device)
         b.add_graph(g)
+        if shard is not None:
+            b.init_shard(*shard)
+        if r == reps:
+            b.set_profiling(True)  # last repetition: per-phase events (adds synchronisation, not the timed one)
         b.synchronize()
+        ext = torch.cuda.ExternalStream(b.cuda_stream(), device=torch.device("cuda", device))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = b.launch_count()
         t0 = time.perf_counter()
+        e0.record(ext)
         acc = b.Compute()
-        dt = time.perf_counter() - t0
+        e1.record(ext)
+        b.synchronize()
+        wall = time.perf_counter() - t0
+        dt = e0.elapsed_time(e1) * 1e-3
         s = b.stats()
-        if r and (best is None or dt < best[0]):
-            best = (dt, acc, s.lambda_trials, s.lm_steps, s.n_outliers, b.launch_count() - l0)
+        if 0 < r < reps and (best is None or dt < best[0]):
+            best = (dt, acc, s.lambda_trials, s.lm_steps, s.n_outliers, b.launch_count() - l0, wall)
+        phases = b.phase_times() if r == reps else None
         b.close()
-    dt, acc, trials, steps, outl, launches = best
-    out = {"workload": f"C3: Bundle::Compute LM, {n_cams} keyframes x {n_points} points x {n_meas} measurements",
+    dt, acc, trials, steps, outl, launches, wall = best
+    out = {"workload": f"{config}: Bundle::Compute LM, {cfg['n_cams']} keyframes x {cfg['n_points']} points x {cfg['n_meas']} measurements",
            "value": trials / dt, "unit": "lambda-trials/s", "accepted_steps_per_s": acc / dt, "compute_ms": dt * 1e3,
-           "lambda_trials": trials, "accepted": acc, "lm_steps": steps, "outliers": outl, "gpu_launches": launches,
-           "timing": "wall clock around ptam_bundle_compute (host LM control + device phases), best of %d" % reps}
+           "wall_ms": wall * 1e3, "lambda_trials": trials, "accepted": acc, "lm_steps": steps, "outliers": outl,
+           "gpu_launches": launches, "reduced_system_n": n,
+           "timing": "CUDA events on the handle's stream around ptam_bundle_compute (host LM control + device phases), best of %d" % (reps - 1),
+           "phases_ms_per_call": {k: (v[0] / v[1] if v[1] else None) for k, v in phases.items()},
+           "phases_calls": {k: int(v[1]) for k, v in phases.items()}}
+    sol = phases["solve"]
+    if sol[1]:
+        out["solve_gflops"] = flops_per_trial(n) / (sol[0] / sol[1] * 1e-3) / 1e9
     if cpu_lib is not None:
-        o = Bundle(cpu_lib, g["width"], g["height"])
+        kw = dict(max_iterations=cpu_trials) if cpu_trials else {}
+        o = Bundle(cpu_lib, g["width"], g["height"], **kw)
         o.add_graph(g)
         t0 = time.perf_counter()
         acc_o = o.Compute()
         dto = time.perf_counter() - t0
         so = o.stats()
         out["cpu_baseline"] = {"value": so.lambda_trials / dto, "unit": "lambda-trials/s", "cores": 1, "kind": "port",
-                               "sample": f"one full Compute() on the same graph: {so.lambda_trials} trials, {acc_o} accepted, {dto * 1e3:.0f} ms"}
+                               "sample": f"Compute() on the same graph capped at {so.lambda_trials} lambda trials "
+                                         f"({acc_o} accepted), {dto * 1e3:.0f} ms"}
     return out

@@ -87,7 +87,9 @@ PRODUCT_ONLY_SYMBOLS = [
     "tracker_launch_count", "tracker_set_profiling", "tracker_get_kernel_times",
     "bundle_cuda_stream", "bundle_launch_count",
     "nccl_unique_id", "bundle_init_shard", "bundle_shard_plan",
+    "bundle_set_profiling", "bundle_get_phase_times",
 ]
+BUNDLE_PHASES = ["project", "select", "jacobian", "vinv_init", "schur", "allreduce", "solve", "update_newerror"]
 TRACKER_KERNELS = ["k_pyramid", "k_fast", "k_compact", "k_pvs_select", "k_search_coarse", "k_pose_coarse",
                    "k_search_fine", "k_pose_fine"]
 
@@ -185,6 +187,8 @@ class Lib:
             "bundle_synchronize": (i, [vp]),
             "bundle_cuda_stream": (vp, [vp]),
             "bundle_launch_count": (C.c_int64, [vp]),
+            "bundle_set_profiling": (i, [vp, i]),
+            "bundle_get_phase_times": (i, [vp, P(d), P(C.c_int64)]),
         }
         for name, (res, args) in sig.items():
             if self.has(name):
@@ -498,3 +502,12 @@ class Bundle:
 
     def launch_count(self):
         return int(self.lib.fn("bundle_launch_count")(self.h))
+
+    def set_profiling(self, on):
+        self._chk(self.lib.fn("bundle_set_profiling")(self.h, int(on)))
+
+    def phase_times(self):
+        """{phase: (total ms, count)} accumulated since set_profiling(True)."""
+        ms, n = (C.c_double * 8)(), (C.c_int64 * 8)()
+        self._chk(self.lib.fn("bundle_get_phase_times")(self.h, ms, n))
+        return {k: (ms[j], n[j]) for j, k in enumerate(BUNDLE_PHASES)}

@@ -115,6 +115,20 @@ struct ptam_bundle {
   bool shards_dirty = false, abort_seen = false;
   std::vector<int> h_outliers;       // merged (point, camera) pairs in the reference's erase order
   int n_meas_local = 0;
+  // optional per-phase device timing (CUDA events on the handle's stream around each phase)
+  bool profiling = false;
+  cudaEvent_t prof_ev[2 * PTAM_BA_PHASES] = {};
+  double prof_ms[PTAM_BA_PHASES] = {};
+  int64_t prof_n[PTAM_BA_PHASES] = {};
+  unsigned prof_pending = 0;
+  void pbegin(int k) { if (profiling) cudaEventRecord(prof_ev[2 * k], stream); }
+  void pend(int k) { if (profiling) { cudaEventRecord(prof_ev[2 * k + 1], stream); prof_pending |= 1u << k; } }
+  void pcollect() {  // call after a stream synchronisation
+    if (!profiling) return;
+    for (int k = 0; k < PTAM_BA_PHASES; k++)
+      if (prof_pending & (1u << k)) { float ms = 0; if (cudaEventElapsedTime(&ms, prof_ev[2 * k], prof_ev[2 * k + 1]) == cudaSuccess) { prof_ms[k] += ms; prof_n[k]++; } }
+    prof_pending = 0;
+  }
 
   void set_error(const std::string& e) { err = e; }
 
@@ -126,6 +140,7 @@ struct ptam_bundle {
       b->release();
     for (auto* b : {&cam_fixed, &cam_row, &pt_off, &pt_meas, &m_cam, &m_pt, &m_state, &counters, &outliers}) b->release();
     for (auto* b : {&m_gid, &m_erase_step, &g_steps, &hist16}) b->release();
+    for (auto e : prof_ev) if (e) cudaEventDestroy(e);
     sel_state.release();
     if (comm && own_comm) nccl_api().CommDestroy(comm);
     if (h_scal) cudaFreeHost(h_scal);
@@ -298,9 +313,9 @@ struct ptam_bundle {
     PTAM_CUDA_TRY(this, cudaMemsetAsync(epsB.p, 0, sizeof(double) * 3 * P, stream));
     PTAM_CUDA_TRY(this, cudaMemsetAsync(scal.p, 0, sizeof(double) * 8, stream));
     PTAM_CUDA_TRY(this, cudaMemsetAsync(counters.p, 0, sizeof(int), stream));
-    if (M > 0) { k_ba_project<<<(M + 255) / 256, 256, 0, stream>>>(d); launches++; }
-    if ((rc = find_sigma_squared())) return rc;
-    if (M > 0) { k_ba_jacobian<<<(M + 127) / 128, 128, 0, stream>>>(d); launches++; }
+    pbegin(0); if (M > 0) { k_ba_project<<<(M + 255) / 256, 256, 0, stream>>>(d); launches++; } pend(0);
+    pbegin(1); if ((rc = find_sigma_squared())) return rc; pend(1);
+    pbegin(2); if (M > 0) { k_ba_jacobian<<<(M + 127) / 128, 128, 0, stream>>>(d); launches++; } pend(2);
     PTAM_CUDA_TRY(this, cudaGetLastError());
     if (world > 1) {
       h_scal[5] = local_abort() ? 1.0 : 0.0;
@@ -309,6 +324,7 @@ struct ptam_bundle {
     }
     PTAM_CUDA_TRY(this, cudaMemcpyAsync(h_scal, scal.p, sizeof(double) * 8, cudaMemcpyDeviceToHost, stream));
     PTAM_CUDA_TRY(this, cudaStreamSynchronize(stream));
+    pcollect();
     sigma_sq = h_scal[1];
     const double cur_err = h_scal[2];
     if (world > 1) abort_seen = h_scal[5] > 0.0;
@@ -319,26 +335,33 @@ struct ptam_bundle {
       trial_lambda = lambda;
       h_scal[3] = 0.0; h_scal[4] = 0.0; h_scal[5] = (world > 1 && local_abort()) ? 1.0 : 0.0; h_scal[6] = lambda;
       PTAM_CUDA_TRY(this, cudaMemcpyAsync(scal.p + 3, h_scal + 3, sizeof(double) * 4, cudaMemcpyHostToDevice, stream));
+      pbegin(3);
       if (PO > 0) { k_ba_vinv<<<(PO + 255) / 256, 256, 0, stream>>>(d); launches++; }
       if (n > 0) {
         k_ba_init_s<<<std::min<size_t>(((size_t)n * n + 255) / 256, 148 * 8), 256, 0, stream>>>(d);
         k_ba_init_diag<<<C, 64, 0, stream>>>(d);
         launches += 2;
       }
-      if (PO > 0) { k_ba_schur<<<(PO + 7) / 8, 256, 0, stream>>>(d); launches++; }
+      pend(3);
+      pbegin(4); if (PO > 0) { k_ba_schur<<<(PO + 7) / 8, 256, 0, stream>>>(d); launches++; } pend(4);
       s_mirrored = false;
+      pbegin(5);
       if (n > 0) {  // the cross-camera J^T J reduction: partial S, vE of every shard -> total on every shard
         if ((rc = all_reduce(d.S, (size_t)n * n, ncclDouble, ncclSum, "all-reduce of S"))) return rc;
         if ((rc = all_reduce(d.vE, n, ncclDouble, ncclSum, "all-reduce of vE"))) return rc;
       }
-      if ((rc = solve_reduced())) return rc;
+      pend(5);
+      pbegin(6); if ((rc = solve_reduced())) return rc; pend(6);
+      pbegin(7);
       if (PO > 0) { k_ba_point_update<<<(PO + 255) / 256, 256, 0, stream>>>(d); launches++; }
       if (C > 0) { k_ba_cam_update<<<(C + 127) / 128, 128, 0, stream>>>(d); launches++; }
       if (M > 0) { k_ba_new_error<<<(M + 255) / 256, 256, 0, stream>>>(d); launches++; }
+      pend(7);
       PTAM_CUDA_TRY(this, cudaGetLastError());
       if ((rc = all_reduce(scal.p + 3, 3, ncclDouble, ncclSum, "all-reduce of the trial scalars"))) return rc;
       PTAM_CUDA_TRY(this, cudaMemcpyAsync(h_scal + 3, scal.p + 3, sizeof(double) * 3, cudaMemcpyDeviceToHost, stream));
       PTAM_CUDA_TRY(this, cudaStreamSynchronize(stream));
+      pcollect();
       new_err = h_scal[3];
       last_new_error = new_err;
       if (world > 1) abort_seen = h_scal[5] > 0.0;
@@ -590,6 +613,19 @@ int ptam_bundle_get_reduced_system(ptam_bundle* b, double* S, double* vE, int ca
 int ptam_bundle_synchronize(ptam_bundle* b) {
   cudaSetDevice(b->device);
   PTAM_CUDA_TRY(b, cudaStreamSynchronize(b->stream));
+  return PTAM_OK;
+}
+int ptam_bundle_set_profiling(ptam_bundle* b, int on) {
+  cudaSetDevice(b->device);
+  if (on && !b->prof_ev[0])
+    for (auto& e : b->prof_ev) PTAM_CUDA_TRY(b, cudaEventCreate(&e));
+  b->profiling = on != 0;
+  b->prof_pending = 0;
+  for (int k = 0; k < PTAM_BA_PHASES; k++) { b->prof_ms[k] = 0; b->prof_n[k] = 0; }
+  return PTAM_OK;
+}
+int ptam_bundle_get_phase_times(ptam_bundle* b, double* ms_total, int64_t* count) {
+  for (int k = 0; k < PTAM_BA_PHASES; k++) { ms_total[k] = b->prof_ms[k]; count[k] = b->prof_n[k]; }
   return PTAM_OK;
 }
 void* ptam_bundle_cuda_stream(ptam_bundle* b) { return (void*)b->stream; }

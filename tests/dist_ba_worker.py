@@ -56,7 +56,7 @@ def main():
     dist.barrier()
     dist.destroy_process_group()
     ok = (acc == acc1 and st.lambda_trials == st1.lambda_trials and res["outliers_equal"]
-          and res["max_pt"] < 1e-6 and res["max_cam"] < 1e-6 and st.sigma_squared == st1.sigma_squared)
+          and res["max_pt"] < 1e-6 and res["max_cam"] < 1e-6 and abs(st.sigma_squared - st1.sigma_squared) <= 1e-9 * st1.sigma_squared)
     sys.exit(0 if ok else 1)
 
 
