@@ -503,6 +503,9 @@ class Bundle:
     def launch_count(self):
         return int(self.lib.fn("bundle_launch_count")(self.h))
 
+    def cuda_stream(self):
+        return self.lib.fn("bundle_cuda_stream")(self.h)
+
     def set_profiling(self, on):
         self._chk(self.lib.fn("bundle_set_profiling")(self.h, int(on)))
 

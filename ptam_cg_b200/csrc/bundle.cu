@@ -169,6 +169,7 @@ struct ptam_bundle {
     PTAM_CUDA_TRY(this, cudaMallocHost(&h_cnt, 4 * sizeof(int)));
     if (p) prm = *p; else ptam_bundle_default_params(&prm);
     cam = ptam_make_cam_model(cam_params, w, h);
+    PTAM_CUDA_TRY(this, cudaFuncSetAttribute(k_ldlt_update, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpdateSmem));
     return PTAM_OK;
   }
 
@@ -250,20 +251,24 @@ struct ptam_bundle {
   int solve_reduced() {
     const int n = d.n;
     if (n == 0) return PTAM_OK;
+    // vE is consumed in place as the right-hand side (forward substitution rides with the panels)
     for (int k0 = 0; k0 < n; k0 += kNB) {
       const int nb = std::min(kNB, n - k0);
-      k_ldlt_diag<<<1, 32, 0, stream>>>(d.S, n, k0);
-      launches++;
       const int rem = n - k0 - nb;
+      k_ldlt_panel<<<std::max(1, (rem + kPanelRows - 1) / kPanelRows), kPanelThreads, 0, stream>>>(d.S, Wp.p, d.vE, n, k0);
+      launches++;
       if (rem > 0) {
-        k_ldlt_panel<<<(rem + 127) / 128, 128, 0, stream>>>(d.S, Wp.p, n, k0);
-        const int nt = (rem + kUT - 1) / kUT;
-        k_ldlt_update<<<nt * (nt + 1) / 2, 256, 0, stream>>>(d.S, Wp.p, n, k0);
-        launches += 2;
+        const int nt = (rem + kUTM - 1) / kUTM;
+        k_ldlt_update<<<nt * (nt + 1), 256, kUpdateSmem, stream>>>(d.S, Wp.p, n, k0);
+        launches++;
       }
     }
-    k_ldlt_solve<<<1, 1024, n * sizeof(double), stream>>>(d.S, d.vE, d.upd, n);
+    k_ldlt_scale<<<(n + 255) / 256, 256, 0, stream>>>(d.S, d.vE, d.vE, n);
     launches++;
+    for (int k0 = ((n - 1) / kNB) * kNB; k0 >= 0; k0 -= kNB) {
+      k_ldlt_back<<<std::max(1, (k0 + 255) / 256), 256, 0, stream>>>(d.S, d.vE, d.upd, n, k0);
+      launches++;
+    }
     PTAM_CUDA_TRY(this, cudaGetLastError());
     return PTAM_OK;
   }
@@ -628,6 +633,9 @@ int ptam_bundle_get_phase_times(ptam_bundle* b, double* ms_total, int64_t* count
   for (int k = 0; k < PTAM_BA_PHASES; k++) { ms_total[k] = b->prof_ms[k]; count[k] = b->prof_n[k]; }
   return PTAM_OK;
 }
+#ifdef PTAM_PANEL_DEBUG
+int ptam_debug_read(long long* out) { cudaDeviceSynchronize(); return (int)cudaMemcpyFromSymbol(out, g_dbg, sizeof(long long) * 8); }
+#endif
 void* ptam_bundle_cuda_stream(ptam_bundle* b) { return (void*)b->stream; }
 int64_t ptam_bundle_launch_count(const ptam_bundle* b) { return b->launches; }
 

@@ -8,7 +8,7 @@
 //                  k_ba_init_s       S diagonal blocks <- U*, vE <- epsA (:374-392)
 //                  k_ba_schur        warp per point: S_jk -= W_ij V*^-1 W_ik^T, vE_j -= W_ij V*^-1 epsB
 //                                    (:396-446) with atomics into the dense lower triangle
-//                  k_ldlt_*          blocked square-root-free LDL^T of S + k_ldlt_solve (:457-458)
+//                  k_ldlt_*          blocked square-root-free LDL^T of S (DMMA trailing update) + solve (:457-458)
 //                  k_ba_point_update delta_b_i (:461-483), k_ba_cam_update exp(delta_a) (:496-504)
 //                  k_ba_new_error    FindNewError (:188-207)
 #pragma once
@@ -442,164 +442,327 @@ __global__ void __launch_bounds__(256) k_ba_mirror(double* S, int n) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Blocked LDL^T, panel width 32 (right-looking).  L (unit lower) overwrites the strict lower
-// triangle, D the diagonal; `Wp` [n][32] receives the current panel times D (L21 * D1).
-//   k_ldlt_diag : one CTA factors the 32x32 diagonal block in shared memory
-//   k_ldlt_panel: rows below the block: L21 = A21 L11^-T D1^-1 (one thread per row)
-//   k_ldlt_update: A22 -= (L21 D1) L21^T on the lower triangle, 64x64 tiles, f64 FMA
+// Dense solve  delta_a = S^-1 vE  (Bundle.cc:457-458, TooN Cholesky<>: square-root-free LDL^T, no
+// pivoting, no failure path — a non-positive-definite S yields inf/NaN exactly as in the reference).
+// Right-looking blocked factorisation, panel width 64, with the forward substitution folded in:
+//   k_ldlt_panel   every CTA factors the 64x64 diagonal block in shared memory (redundantly: it is
+//                  8 us of work and saves a launch and a dependency), then solves 128 rows of the
+//                  panel below it, one thread per row:  w = a L11^-T  (= L21 D1),  L21 = w D1^-1,
+//                  and applies the panel to the right-hand side:  y2 -= L21 y1.
+//   k_ldlt_update  trailing update  A22 -= (L21 D1) L21^T  on the lower triangle, 128x128 tiles,
+//                  K = 64: the one genuine dense contraction of either hot path.  FP64 has no
+//                  tcgen05 form, so it runs on the f64 tensor pipe (DMMA, mma.sync m8n8k4);
+//                  operand tiles are staged in shared memory by the TMA engine (one 512-byte
+//                  cp.async.bulk per row, completion on an mbarrier), rows padded to 68 doubles so
+//                  that fragment loads are bank-conflict free.
+//   k_ldlt_back    z = D^-1 y,  L^T x = z  (one CTA, 32-column blocks).
 // ---------------------------------------------------------------------------------------------
-constexpr int kNB = 32;
+constexpr int kNB = 64;     // panel width
+constexpr int kUTM = 128;   // trailing-update tile rows
+constexpr int kUTN = 64;    // trailing-update tile columns
+constexpr int kLds = kNB + 4;  // padded shared-memory row, doubles
+constexpr int kUpdateSmem = (kUTM + kUTN) * kLds * (int)sizeof(double) + 16;
 
-__global__ void __launch_bounds__(32) k_ldlt_diag(double* A, int n, int k0) {
-  __shared__ double a[kNB][kNB + 1];
-  const int nb = min(kNB, n - k0);
-  const int t = threadIdx.x;
-  for (int r = 0; r < nb; r++) if (t < nb) a[r][t] = A[(size_t)(k0 + r) * n + k0 + t];
-  __syncwarp();
-  // row t of the block; column-by-column elimination
-  for (int col = 0; col < nb; col++) {
-    // d_col = a[col][col] - sum_{c2<col} (L[col][c2] * D[c2]) * L[col][c2]; stored incrementally:
-    // after processing column c2 we subtract its contribution from all later entries (right-looking)
-    const double dcol = a[col][col];
-    const double inv = 1.0 / dcol;
-    double l = 0.0;
-    if (t > col && t < nb) { l = a[t][col] * inv; }
-    __syncwarp();
-    if (t > col && t < nb) {
-      // update row t, columns col+1..t with l * (a[c][col])   (a[c][col] still holds L*D value)
-      for (int c = col + 1; c <= t; c++) a[t][c] -= l * a[c][col];
+// LDL^T of a 64x64 block held in registers by 256 threads: thread (ty = tid / 16, tx = tid % 16) owns
+// rows ty + 16 i x columns tx + 16 j (i, j < 4).  One barrier per column: the owners of column `col`
+// publish it (double-buffered) and the owner of the pivot publishes its reciprocal, so the only
+// serial chain per column is  update -> reciprocal -> barrier -> rank-1 update.  The 16-column groups
+// are unrolled so that all register indices and the dead-row / dead-column tests are static.
+// The right-hand side rides along as one more column (threads tx == 0 hold y of their rows):
+// y_t -= l_t y_col is the forward substitution L y' = y.
+// L = value * (1 / d) as TooN's Cholesky does.  Result: `a` holds L (strict lower) and D (diagonal),
+// `ysh` the forward-substituted right-hand side, `dinv` the reciprocals of D.
+constexpr int kPanelThreads = 256;
+constexpr int kPanelRows = 64;  // rows of the panel solved per CTA (threads 0..63; more CTAs beat fuller CTAs here)
+#ifdef PTAM_PANEL_DEBUG
+__device__ long long g_dbg[8];
+#define DBG_T(k) if (blockIdx.x == 0 && threadIdx.x == 0) { const long long now = clock64(); atomicAdd((unsigned long long*)&g_dbg[k], (unsigned long long)(now - t_prev)); t_prev = now; }
+#else
+#define DBG_T(k)
+#endif
+constexpr int kLda = kNB + 2;  // even row pitch: (row, even column) pairs are 16-byte aligned
+
+template <int JC>
+PTAM_DEV void block_ldlt64_group(double (&ar)[4][4], double (&yr)[4], double (*ucol)[kNB], double (*piv)[2], double* dinv, int nb) {
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+#pragma unroll 1
+  for (int cc = 0; cc < 16; cc++) {
+    const int col = 16 * JC + cc;
+    if (col >= nb) break;
+    const int buf = col & 1;
+    if (tx == cc) {  // owners of column col: rows t = ty + 16 i, i >= JC (entries with t <= col are unused)
+#pragma unroll
+      for (int i = JC; i < 4; i++) ucol[buf][ty + 16 * i] = ar[i][JC];
+      if (ty == cc) {  // pivot (col, col) = slot (i = JC, j = JC) of thread (ty = cc, tx = cc)
+        const double r = 1.0 / ar[JC][JC];
+        piv[buf][0] = r;
+        dinv[col] = r;
+      }
     }
-    __syncwarp();
-    if (t > col && t < nb) a[t][col] = l;
-    __syncwarp();
+    if (tx == 0 && ty == cc) piv[buf][1] = yr[JC];  // y'_col is final once the previous columns are done
+    __syncthreads();
+    const double di = piv[buf][0], ycol = piv[buf][1];
+    // Dead rows (t <= col or t >= nb) get l = 0 and dead columns (c <= col) get u = 0, so the rank-1
+    // update below needs no per-element tests.  It also touches the strict upper triangle (c > t) of
+    // the register tile, which is never read.
+    double uc[4], lt[4];
+#pragma unroll
+    for (int j = JC; j < 4; j++) {
+      const double v = ucol[buf][tx + 16 * j];
+      uc[j] = (j > JC || tx > cc) ? v : 0.0;
+    }
+#pragma unroll
+    for (int i = JC; i < 4; i++) {
+      const int t = ty + 16 * i;
+      const double v = ucol[buf][t] * di;
+      lt[i] = ((i > JC || ty > cc) && t < nb) ? v : 0.0;
+    }
+#pragma unroll
+    for (int i = JC; i < 4; i++) {
+#pragma unroll
+      for (int j = JC; j < 4; j++) ar[i][j] -= lt[i] * uc[j];
+      if (tx == 0) yr[i] -= lt[i] * ycol;
+      if (tx == cc && (i > JC || ty > cc)) ar[i][JC] = lt[i];
+    }
   }
-  for (int r = 0; r < nb; r++) if (t < nb && t <= r) A[(size_t)(k0 + r) * n + k0 + t] = a[r][t];
 }
 
-__global__ void __launch_bounds__(128) k_ldlt_panel(double* A, double* Wp, int n, int k0) {
-  __shared__ double L[kNB][kNB + 1];
-  __shared__ double Dg[kNB];
-  const int nb = min(kNB, n - k0);
-  for (int i = threadIdx.x; i < nb * nb; i += blockDim.x) {
-    const int r = i / nb, c = i % nb;
-    L[r][c] = c <= r ? A[(size_t)(k0 + r) * n + k0 + c] : 0.0;
+PTAM_DEV void block_ldlt64(double (*a)[kLda], double (*ucol)[kNB], double (*piv)[2], double* dinv, double* ysh, int nb) {
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  double ar[4][4], yr[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) ar[i][j] = a[ty + 16 * i][tx + 16 * j];
+    yr[i] = ysh[ty + 16 * i];
+  }
+  if (tid < kNB) dinv[tid] = 1.0;
+  __syncthreads();
+  block_ldlt64_group<0>(ar, yr, ucol, piv, dinv, nb);
+  block_ldlt64_group<1>(ar, yr, ucol, piv, dinv, nb);
+  block_ldlt64_group<2>(ar, yr, ucol, piv, dinv, nb);
+  block_ldlt64_group<3>(ar, yr, ucol, piv, dinv, nb);
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) a[ty + 16 * i][tx + 16 * j] = ar[i][j];
+    if (tx == 0) ysh[ty + 16 * i] = yr[i];
   }
   __syncthreads();
-  if (threadIdx.x < nb) Dg[threadIdx.x] = L[threadIdx.x][threadIdx.x];
+}
+
+__global__ void __launch_bounds__(kPanelThreads) k_ldlt_panel(double* A, double* Wp, double* y, int n, int k0) {
+  __shared__ __align__(16) double a[kNB][kLda];
+  __shared__ double ucol[2][kNB];
+  __shared__ double piv[2][2];
+  __shared__ double y1[kNB];
+  __shared__ double dinv[kNB];
+  const int nb = min(kNB, n - k0);
+  const int tid = threadIdx.x;
+#ifdef PTAM_PANEL_DEBUG
+  long long t_prev = clock64();
+#endif
+  for (int i = tid; i < kNB * kNB; i += blockDim.x) {
+    const int r = i / kNB, c = i % kNB;
+    a[r][c] = (r < nb && c <= r) ? A[(size_t)(k0 + r) * n + k0 + c] : (r == c ? 1.0 : 0.0);
+  }
+  if (tid < kNB) y1[tid] = tid < nb ? y[k0 + tid] : 0.0;
   __syncthreads();
-  const int row = k0 + nb + blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= n) return;
+  DBG_T(0)
+  block_ldlt64(a, ucol, piv, dinv, y1, nb);
+  DBG_T(1)
+  if (blockIdx.x == 0) {
+    for (int i = tid; i < nb * nb; i += blockDim.x) {
+      const int r = i / nb, c = i % nb;
+      if (c <= r) A[(size_t)(k0 + r) * n + k0 + c] = a[r][c];
+    }
+    if (tid < nb) y[k0 + tid] = y1[tid];
+  }
+  DBG_T(2)
+  // ---- rows below the block: one thread per row
+  const int row = k0 + nb + blockIdx.x * kPanelRows + tid;
+  if (tid >= kPanelRows || row >= n) return;  // nb < kNB only on the last panel, which has no rows below it
   double x[kNB];
   double* Ar = A + (size_t)row * n + k0;
 #pragma unroll
-  for (int c = 0; c < kNB; c++) x[c] = c < nb ? Ar[c] : 0.0;
-  // solve w L11^T = a  (w = L21 D1), forward over columns
+  for (int c = 0; c < kNB; c += 2) { const double2 v = *reinterpret_cast<const double2*>(Ar + c); x[c] = v.x; x[c + 1] = v.y; }
+  DBG_T(3)
+  // w L11^T = a, two columns at a time (right-looking: independent updates, one 16-byte broadcast
+  // load of (L[c2][c], L[c2][c+1]) per two FMAs)
 #pragma unroll
-  for (int c = 0; c < kNB; c++) {
-    if (c < nb) {
-      double v = x[c];
+  for (int c = 0; c < kNB; c += 2) {
+    const double xc0 = x[c];
+    x[c + 1] -= xc0 * a[c + 1][c];
+    const double xc1 = x[c + 1];
 #pragma unroll
-      for (int q = 0; q < kNB; q++) if (q < c) v -= x[q] * L[c][q];
-      x[c] = v;  // = (L21 D1)[row][c]
+    for (int c2 = c + 2; c2 < kNB; c2++) {
+      const double2 l = *reinterpret_cast<const double2*>(&a[c2][c]);
+      x[c2] -= xc0 * l.x + xc1 * l.y;
     }
   }
-  double* Wr = Wp + (size_t)row * kNB;
+  DBG_T(4)
+  double* Wr = Wp + (size_t)row * kNB;  // holds -(L21 D1): the update kernel accumulates C += Wp L21^T
+  double dot = 0.0;
 #pragma unroll
-  for (int c = 0; c < kNB; c++) {
-    if (c < nb) { Wr[c] = x[c]; Ar[c] = x[c] / Dg[c]; } else Wr[c] = 0.0;
+  for (int c = 0; c < kNB; c += 2) {
+    *reinterpret_cast<double2*>(Wr + c) = make_double2(-x[c], -x[c + 1]);
+    const double l0 = x[c] * dinv[c], l1 = x[c + 1] * dinv[c + 1];  // value * (1 / d), as TooN does
+    *reinterpret_cast<double2*>(Ar + c) = make_double2(l0, l1);
+    dot += l0 * y1[c] + l1 * y1[c + 1];
+  }
+  y[row] -= dot;
+  DBG_T(5)
+}
+
+PTAM_DEV unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(256, 2) k_ldlt_update(double* A, const double* Wp, int n, int k0) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sW = reinterpret_cast<double*>(smem_raw);            // [kUTM][kLds]  -(L21 D1) rows of the i-tile
+  double* sL = sW + kUTM * kLds;                                // [kUTN][kLds]  L21 rows of the j-tile
+  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(sL + kUTN * kLds);
+  const int r0 = k0 + kNB;
+  // linear tile index -> (bi, bj): row block bi (128 rows) has column blocks bj = 0 .. 2 bi + 1 (64 columns)
+  int bi = (int)((sqrt(4.0 * blockIdx.x + 1.0) - 1.0) * 0.5);
+  while (bi * (bi + 1) > (int)blockIdx.x) bi--;
+  while ((bi + 1) * (bi + 2) <= (int)blockIdx.x) bi++;
+  const int bj = blockIdx.x - bi * (bi + 1);
+  const int i0 = r0 + bi * kUTM, j0 = r0 + bj * kUTN;
+  if (j0 >= n) return;  // the last row block may be short of its second diagonal column block
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned mbar_a = smem_u32(mbar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_a));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // ---- TMA-engine staging: one 512-byte bulk copy per tile row (192 rows, threads 0..191)
+  {
+    const int rows_i = min(kUTM, n - i0), rows_j = min(kUTN, n - j0);
+    if (tid == 0) {
+      const unsigned bytes = (unsigned)(rows_i + rows_j) * kNB * (unsigned)sizeof(double);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_a), "r"(bytes) : "memory");
+    }
+    if (tid < kUTM + kUTN) {
+      const double* src = nullptr;
+      double* dst;
+      if (tid < kUTM) { dst = sW + tid * kLds; if (tid < rows_i) src = Wp + (size_t)(i0 + tid) * kNB; }
+      else { const int r = tid - kUTM; dst = sL + r * kLds; if (r < rows_j) src = A + (size_t)(j0 + r) * n + k0; }
+      if (src) {
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(dst)), "l"(src), "r"((unsigned)(kNB * sizeof(double))), "r"(mbar_a) : "memory");
+      } else {
+        for (int c = 0; c < kNB; c++) dst[c] = 0.0;  // rows past the matrix: defined operands, results never stored
+      }
+    }
+  }
+  // ---- accumulators start as the C tile (prefetched while the operand tiles are in flight)
+  // 8 warps = 4 (32-row slabs) x 2 (32-column slabs); 4 x 4 m8n8k4 tiles per warp
+  const int wm = warp & 3, wn = warp >> 2;
+  const bool active = !(j0 + wn * 32 > i0 + wm * 32 + 31);  // warp tile not entirely above the diagonal
+  double acc[4][4][2];
+  if (active) {
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++) {
+      const int i = i0 + wm * 32 + mi * 8 + (lane >> 2);
+      const double* Ci = A + (size_t)min(i, n - 1) * n;
+#pragma unroll
+      for (int ni = 0; ni < 4; ni++) {
+        const int j = j0 + wn * 32 + ni * 8 + 2 * (lane & 3);
+        double2 v = make_double2(0.0, 0.0);
+        if (i < n && j + 1 <= i) v = *reinterpret_cast<const double2*>(Ci + j);
+        else if (i < n && j <= i) v.x = Ci[j];
+        acc[mi][ni][0] = v.x; acc[mi][ni][1] = v.y;
+      }
+    }
+  }
+  {
+    unsigned ok = 0;
+    while (!ok)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(ok) : "r"(mbar_a) : "memory");
+  }
+  __syncthreads();  // also covers the plain zero-fill stores
+  if (!active) return;
+  const double* pa = sW + (wm * 32 + (lane >> 2)) * kLds + (lane & 3);
+  const double* pb = sL + (wn * 32 + (lane >> 2)) * kLds + (lane & 3);
+#pragma unroll 4
+  for (int kk = 0; kk < kNB; kk += 4) {
+    double fa[4], fb[4];
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++) fa[mi] = pa[mi * 8 * kLds + kk];
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++) fb[ni] = pb[ni * 8 * kLds + kk];
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+      for (int ni = 0; ni < 4; ni++)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(acc[mi][ni][0]), "+d"(acc[mi][ni][1]) : "d"(fa[mi]), "d"(fb[ni]));
+  }
+#pragma unroll
+  for (int mi = 0; mi < 4; mi++) {
+    const int i = i0 + wm * 32 + mi * 8 + (lane >> 2);
+    if (i >= n) continue;
+    double* Ci = A + (size_t)i * n;
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++) {
+      const int j = j0 + wn * 32 + ni * 8 + 2 * (lane & 3);
+      if (j + 1 <= i) *reinterpret_cast<double2*>(Ci + j) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+      else if (j <= i) Ci[j] = acc[mi][ni][0];
+    }
   }
 }
 
-constexpr int kUT = 64;  // update tile
-__global__ void __launch_bounds__(256) k_ldlt_update(double* A, const double* Wp, int n, int k0) {
-  // tile (bi, bj) with bj <= bi of the trailing matrix starting at r0 = k0 + nb
-  __shared__ double sW[kUT][kNB + 1];  // (L21 D1) rows of the i-tile
-  __shared__ double sL[kUT][kNB + 1];  // L21 rows of the j-tile
+// Backward substitution  L^T x = D^-1 y, one launch per 64-row panel from the bottom up.  Every CTA
+// first solves the panel's 64x64 block itself (x_p = L11^-T z_p; z_p is complete by then), CTA 0
+// stores it in x, then each CTA applies the panel to its slice of the rows above:
+// z[i] -= sum_c L[k0 + c][i] x[k0 + c], i < k0 (coalesced along i).  `z` must hold D^-1 y (k_ldlt_scale).
+__global__ void __launch_bounds__(256) k_ldlt_scale(const double* A, const double* y, double* z, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) z[i] = y[i] / A[(size_t)i * n + i];
+}
+
+__global__ void __launch_bounds__(256) k_ldlt_back(const double* A, double* z, double* x, int n, int k0) {
+  __shared__ double a[kNB][kNB + 1];
+  __shared__ double xs[kNB];
   const int nb = min(kNB, n - k0);
-  const int r0 = k0 + nb;
-  // linear tile index -> (bi, bj)
-  int bi = (int)((sqrt(8.0 * blockIdx.x + 1.0) - 1.0) * 0.5);
-  while (bi * (bi + 1) / 2 > (int)blockIdx.x) bi--;
-  while ((bi + 1) * (bi + 2) / 2 <= (int)blockIdx.x) bi++;
-  const int bj = blockIdx.x - bi * (bi + 1) / 2;
-  const int i0 = r0 + bi * kUT, j0 = r0 + bj * kUT;
-  for (int t = threadIdx.x; t < kUT * kNB; t += blockDim.x) {
-    const int r = t / kNB, c = t % kNB;
-    sW[r][c] = (i0 + r < n) ? Wp[(size_t)(i0 + r) * kNB + c] : 0.0;
-    sL[r][c] = (j0 + r < n && c < nb) ? A[(size_t)(j0 + r) * n + k0 + c] : 0.0;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < kNB * kNB; i += blockDim.x) {
+    const int r = i / kNB, c = i % kNB;
+    a[r][c] = (r < nb && c < r) ? A[(size_t)(k0 + r) * n + k0 + c] : 0.0;
   }
   __syncthreads();
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16x16 threads, 4x4 each
-  double acc[4][4];
-#pragma unroll
-  for (int a = 0; a < 4; a++)
-#pragma unroll
-    for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
-#pragma unroll 8
-  for (int c = 0; c < kNB; c++) {
-    double w[4], l[4];
-#pragma unroll
-    for (int a = 0; a < 4; a++) { w[a] = sW[ty + 16 * a][c]; l[a] = sL[tx + 16 * a][c]; }
-#pragma unroll
-    for (int a = 0; a < 4; a++)
-#pragma unroll
-      for (int b = 0; b < 4; b++) acc[a][b] += w[a] * l[b];
-  }
-#pragma unroll
-  for (int a = 0; a < 4; a++)
-#pragma unroll
-    for (int b = 0; b < 4; b++) {
-      const int i = i0 + ty + 16 * a, j = j0 + tx + 16 * b;
-      if (i < n && j <= i) A[(size_t)i * n + j] -= acc[a][b];
+  if (tid < 32) {  // L11^T x = z inside the block: lane r holds rows r and r + 32, pivots travel by shuffle
+    double x0 = tid < nb ? z[k0 + tid] : 0.0, x1 = tid + 32 < nb ? z[k0 + tid + 32] : 0.0;
+    for (int c = kNB - 1; c >= 32; c--) {
+      const double xc = __shfl_sync(kFull, x1, c - 32);
+      x0 -= a[c][tid] * xc;
+      if (tid + 32 < c) x1 -= a[c][tid + 32] * xc;
     }
-}
-
-// x = (L D L^T)^-1 b, one CTA; blocked by 32 columns.
-__global__ void __launch_bounds__(1024) k_ldlt_solve(const double* A, const double* b, double* x, int n) {
-  extern __shared__ double y[];  // n
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = blockDim.x >> 5;
-  for (int i = t; i < n; i += blockDim.x) y[i] = b[i];
+    for (int c = 31; c >= 0; c--) {
+      const double xc = __shfl_sync(kFull, x0, c);
+      if (tid < c) x0 -= a[c][tid] * xc;
+    }
+    xs[tid] = x0; xs[tid + 32] = x1;
+  }
   __syncthreads();
-  // forward: L y = b
-  for (int k0 = 0; k0 < n; k0 += 32) {
-    const int nb = min(32, n - k0);
-    if (warp == 0) {
-      for (int c = 0; c < nb; c++) {
-        const double yc = y[k0 + c];
-        if (lane > c && lane < nb) y[k0 + lane] -= A[(size_t)(k0 + lane) * n + k0 + c] * yc;
-        __syncwarp();
-      }
+  if (blockIdx.x == 0 && tid < nb) x[k0 + tid] = xs[tid];  // z itself stays untouched: late CTAs still read it
+  const int i = blockIdx.x * blockDim.x + tid;
+  if (i >= k0) return;
+  double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+  const double* Ac = A + (size_t)k0 * n + i;
+#pragma unroll 4
+  for (int c = 0; c < kNB; c += 4) {  // rows past nb are never touched: xs is zero there, but stay in bounds
+    if (c + 3 < nb) {
+      v0 += Ac[(size_t)c * n] * xs[c]; v1 += Ac[(size_t)(c + 1) * n] * xs[c + 1];
+      v2 += Ac[(size_t)(c + 2) * n] * xs[c + 2]; v3 += Ac[(size_t)(c + 3) * n] * xs[c + 3];
+    } else {
+      for (int q = c; q < nb; q++) v0 += Ac[(size_t)q * n] * xs[q];
     }
-    __syncthreads();
-    for (int i = k0 + nb + warp; i < n; i += nw) {
-      double v = lane < nb ? A[(size_t)i * n + k0 + lane] * y[k0 + lane] : 0.0;
-      v = warp_sum(v);
-      if (lane == 0) y[i] -= v;
-    }
-    __syncthreads();
   }
-  for (int i = t; i < n; i += blockDim.x) y[i] /= A[(size_t)i * n + i];
-  __syncthreads();
-  // backward: L^T x = y
-  for (int k1 = n; k1 > 0; k1 -= 32) {
-    const int k0 = max(0, k1 - 32), nb = k1 - k0;
-    if (warp == 0) {
-      for (int c = nb - 1; c >= 0; c--) {
-        const double xc = y[k0 + c];
-        if (lane < c) y[k0 + lane] -= A[(size_t)(k0 + c) * n + k0 + lane] * xc;
-        __syncwarp();
-      }
-    }
-    __syncthreads();
-    // y[i] -= sum_c L[k0+c][i] * x[k0+c] for i < k0: threads over i (coalesced along i)
-    for (int i = t; i < k0; i += blockDim.x) {
-      double v = 0;
-      for (int c = 0; c < nb; c++) v += A[(size_t)(k0 + c) * n + i] * y[k0 + c];
-      y[i] -= v;
-    }
-    __syncthreads();
-  }
-  for (int i = t; i < n; i += blockDim.x) x[i] = y[i];
+  z[i] -= (v0 + v1) + (v2 + v3);
 }
 
 // ---------------------------------------------------------------------------------------------
