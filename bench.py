@@ -205,10 +205,11 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--streams", type=int, default=128, help="independent tracker streams per GPU (batch)")
+    ap.add_argument("--streams", type=int, default=296, help="independent tracker streams per GPU (batch)")
     ap.add_argument("--frames", type=int, default=64, help="distinct synthetic frames per trajectory")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ba", action="store_true")
+    ap.add_argument("--no-ba-large", action="store_true", help="skip the C4 bundle adjustment (500 x 100k x 600k)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -301,16 +302,20 @@ def main():
     base = host_frames.data_ptr()
     init_streams(trk, poses, offsets, F)
 
-    def e2e_step(i):
-        ptrs = [base + pingpong(o + i, F) * FRAME_BYTES for o in offsets]
-        return trk.track_frames_ptrs(ptrs, W, want_results=True)
+    def frame_ptrs(i):
+        return [base + pingpong(o + i, F) * FRAME_BYTES for o in offsets]
 
     for i in range(Wm):
-        e2e_step(i)
+        trk.track_frames_ptrs(frame_ptrs(i), W, want_results=True)
     barrier()
+    # pipelined public API: submit (H2D of this step's frames + kernels) / collect (D2H of its results);
+    # at most two steps in flight, so the copy of step i+1 overlaps the kernels of step i
     t0 = time.perf_counter()
-    for i in range(Wm, n_steps):
-        res = e2e_step(i)
+    trk.submit_ptrs(frame_ptrs(Wm), W)
+    for i in range(Wm + 1, n_steps):
+        trk.submit_ptrs(frame_ptrs(i), W)
+        res = trk.collect()
+    res = trk.collect()
     trk.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
@@ -389,24 +394,41 @@ def main():
                    "mean_found_per_frame": found, "mean_attempted_per_frame": attempted,
                    "mean_corners_per_frame": n_corners},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": S * FRAME_BYTES,
-                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * float(te.item()) / K},
+                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * float(te.item()) / K,
+                "api": "ptam_tracker_submit_frames / ptam_tracker_collect, pinned host frames, 2 steps in flight"},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
         "roofline": rl, "roofline_a1_group": rl_a1, "kernels": per_kernel,
         "single_stream_latency_ms": lat_ms,
     }
 
-    # ================= BA (config C3) =================
-    if rank == 0 and not args.no_ba and prod.has("bundle_create"):
+    # ================= BA (configs C3 / C4) =================
+    # N = 1: Bundle::Compute on C3 and C4 on this GPU.  N > 1: C4 sharded over all ranks (points
+    # partitioned, NCCL all-reduce of the reduced camera system per lambda trial) - collective, so
+    # every rank runs it; rank 0 reports.
+    if not args.no_ba and prod.has("bundle_create"):
+        ba = {}
         try:
             from ptam_cg_b200.bench_ba import bench_ba
             cpu_lib = None
-            if not args.no_cpu_baseline:
+            if rank == 0 and not args.no_cpu_baseline:
                 from oracle.binding import oracle_lib
                 cpu_lib = oracle_lib()
-            out["ba"] = bench_ba(prod, local, cpu_lib=cpu_lib)
+            if world == 1:
+                ba["C3"] = bench_ba(prod, local, "C3", reps=4, cpu_lib=cpu_lib)
+                if not args.no_ba_large:
+                    ba["C4"] = bench_ba(prod, local, "C4", reps=3, cpu_lib=cpu_lib, cpu_trials=1)
+            else:
+                uid = torch.tensor(list(capi.nccl_unique_id(prod) if rank == 0 else bytes(capi.NCCL_UNIQUE_ID_BYTES)),
+                                   dtype=torch.uint8, device="cuda")
+                dist.broadcast(uid, 0)
+                r = bench_ba(prod, local, "C4", reps=3, shard=(rank, world, bytes(uid.cpu().tolist())))
+                r["sharding"] = f"points partitioned over {world} ranks, ncclAllReduce of S ({r['reduced_system_n']}^2 f64) + vE per lambda trial"
+                ba["C4_sharded"] = r
         except Exception as e:  # the tracker line must still be printed
-            out["ba"] = {"error": repr(e)}
+            ba["error"] = repr(e)
+        if rank == 0:
+            out["ba"] = ba
 
     if rank == 0 and not args.no_cpu_baseline:
         from oracle.binding import oracle_lib

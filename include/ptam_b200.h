@@ -147,6 +147,14 @@ int ptam_tracker_track_frames(ptam_tracker* t, const uint8_t* const* images, int
 int ptam_tracker_track_frames_device(ptam_tracker* t, const uint8_t* d_images,
                                      size_t frame_pitch_bytes, int stride,
                                      ptam_track_result* results);
+/* Pipelined form of ptam_tracker_track_frames for sustained streaming: submit enqueues the H2D copy
+ * of this batch on a copy stream (into one of two landing buffers) and the tracking kernels behind
+ * it, then returns; collect blocks until the OLDEST submitted batch is done and hands out its
+ * results.  At most two batches may be in flight, so the copy of batch i+1 overlaps the kernels of
+ * batch i.  Host frame buffers must stay valid until the matching collect (page-locked buffers are
+ * read by DMA; pageable ones are staged inside submit). */
+int ptam_tracker_submit_frames(ptam_tracker* t, const uint8_t* const* images, int stride);
+int ptam_tracker_collect(ptam_tracker* t, ptam_track_result* results);
 int ptam_tracker_synchronize(ptam_tracker* t);
 /* cudaStream_t of the handle, as an opaque pointer (for CUDA-event timing by the caller). */
 void* ptam_tracker_cuda_stream(ptam_tracker* t);

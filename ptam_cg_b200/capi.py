@@ -83,7 +83,7 @@ BUNDLE_SYMBOLS = [
 ]
 # exported by the product only (CUDA plumbing)
 PRODUCT_ONLY_SYMBOLS = [
-    "global_last_error", "tracker_track_frames_device", "tracker_cuda_stream",
+    "global_last_error", "tracker_track_frames_device", "tracker_submit_frames", "tracker_collect", "tracker_cuda_stream",
     "tracker_launch_count", "tracker_set_profiling", "tracker_get_kernel_times",
     "bundle_cuda_stream", "bundle_launch_count",
     "nccl_unique_id", "bundle_init_shard", "bundle_shard_plan",
@@ -148,6 +148,8 @@ class Lib:
             "tracker_make_keyframes": (i, [vp, P(vp), i]),
             "tracker_track_frames": (i, [vp, P(vp), i, P(TrackResult)]),
             "tracker_track_frames_device": (i, [vp, vp, C.c_size_t, i, P(TrackResult)]),
+            "tracker_submit_frames": (i, [vp, P(vp), i]),
+            "tracker_collect": (i, [vp, P(TrackResult)]),
             "tracker_synchronize": (i, [vp]),
             "tracker_cuda_stream": (vp, [vp]),
             "tracker_launch_count": (C.c_int64, [vp]),
@@ -345,6 +347,16 @@ class Tracker:
         arr = (C.c_void_p * self.S)(*ptrs)
         res = (TrackResult * self.S)() if want_results else None
         self._chk(self.lib.fn("tracker_track_frames")(self.h, arr, stride, res))
+        return list(res) if want_results else None
+
+    def submit_ptrs(self, ptrs, stride):
+        """Pipelined track_frames: enqueue H2D + kernels for one batch of raw host pointers."""
+        arr = (C.c_void_p * self.S)(*ptrs)
+        self._chk(self.lib.fn("tracker_submit_frames")(self.h, arr, stride))
+
+    def collect(self, want_results=True):
+        res = (TrackResult * self.S)() if want_results else None
+        self._chk(self.lib.fn("tracker_collect")(self.h, res))
         return list(res) if want_results else None
 
     def level_size(self, level):

@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstring>
 #include <numeric>
+#include <type_traits>
 #include <vector>
 
 using namespace ptam;
@@ -66,17 +67,11 @@ ptam::CamModel ptam_make_cam_model(const double* p, double W, double H);
 void ptam_set_global_error(const std::string& e);
 
 namespace {
+// A typed view into the handle's device arena (one cudaMalloc per graph size, reused by later
+// Compute() calls on the same handle; MapMaker builds a Bundle per adjustment, Bundle.cc:35).
 template <class T>
 struct Buf {
   T* p = nullptr;
-  cudaError_t alloc(size_t n) {
-    release();
-    if (!n) n = 1;
-    cudaError_t e = cudaMalloc(&p, n * sizeof(T));
-    if (e == cudaSuccess) e = cudaMemset(p, 0, n * sizeof(T));
-    return e;
-  }
-  void release() { if (p) cudaFree(p); p = nullptr; }
 };
 }  // namespace
 
@@ -115,6 +110,8 @@ struct ptam_bundle {
   bool shards_dirty = false, abort_seen = false;
   std::vector<int> h_outliers;       // merged (point, camera) pairs in the reference's erase order
   int n_meas_local = 0;
+  unsigned char* arena = nullptr;
+  size_t arena_cap = 0;
   // optional per-phase device timing (CUDA events on the handle's stream around each phase)
   bool profiling = false;
   cudaEvent_t prof_ev[2 * PTAM_BA_PHASES] = {};
@@ -135,13 +132,8 @@ struct ptam_bundle {
   ~ptam_bundle() {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
-    for (auto* b : {&cam_se3, &cam_se3_new, &U, &epsA, &pt_pos, &pt_pos_new, &V, &epsB, &Vinv, &Ve, &m_found, &m_sin,
-                    &m_v3cam, &m_derivs, &m_eps, &m_e2, &m_W, &e2c, &S, &vE, &upd, &scal, &Wp})
-      b->release();
-    for (auto* b : {&cam_fixed, &cam_row, &pt_off, &pt_meas, &m_cam, &m_pt, &m_state, &counters, &outliers}) b->release();
-    for (auto* b : {&m_gid, &m_erase_step, &g_steps, &hist16}) b->release();
+    if (arena) cudaFree(arena);
     for (auto e : prof_ev) if (e) cudaEventDestroy(e);
-    sel_state.release();
     if (comm && own_comm) nccl_api().CommDestroy(comm);
     if (h_scal) cudaFreeHost(h_scal);
     if (h_cnt) cudaFreeHost(h_cnt);
@@ -213,18 +205,38 @@ struct ptam_bundle {
           if (l_mcam[idx[o]] == l_mcam[idx[o - 1]]) { set_error("duplicate (camera, point) measurement"); return PTAM_ERR_INVALID; }
       }
     }
-#define AL(buf, cnt) PTAM_CUDA_TRY(this, buf.alloc(cnt))
-    AL(cam_se3, 12 * (size_t)C); AL(cam_se3_new, 12 * (size_t)C); AL(U, 21 * (size_t)C); AL(epsA, 6 * (size_t)C);
-    AL(cam_fixed, C); AL(cam_row, C);
-    AL(pt_pos, 3 * (size_t)P); AL(pt_pos_new, 3 * (size_t)P); AL(V, 6 * (size_t)P); AL(epsB, 3 * (size_t)P);
-    AL(Vinv, 9 * (size_t)P); AL(Ve, 3 * (size_t)P); AL(pt_off, P + 1); AL(pt_meas, M);
-    AL(m_cam, M); AL(m_pt, M); AL(m_found, 2 * (size_t)M); AL(m_sin, M); AL(m_state, M); AL(m_v3cam, 3 * (size_t)M);
-    AL(m_derivs, 4 * (size_t)M); AL(m_eps, 2 * (size_t)M); AL(m_e2, M); AL(m_W, 18 * (size_t)M); AL(e2c, M);
-    AL(S, (size_t)n * n); AL(vE, n); AL(upd, n); AL(scal, 8); AL(counters, 4); AL(outliers, 2 * (size_t)M);
-    AL(Wp, (size_t)n * kNB);
-    AL(m_gid, M); AL(m_erase_step, M); AL(hist16, 65536); AL(sel_state, 2);
-    if (world > 1) AL(g_steps, MG);
+    // one arena for everything: two passes over the same layout (measure, then assign)
+    size_t need = 0;
+    for (int pass = 0; pass < 2; pass++) {
+      size_t off = 0;
+      auto take = [&](auto& buf, size_t cnt) {
+        using T = std::remove_pointer_t<decltype(buf.p)>;
+        if (pass) buf.p = reinterpret_cast<T*>(arena + off);
+        off += (std::max<size_t>(cnt, 1) * sizeof(T) + 255) & ~(size_t)255;
+      };
+#define AL(buf, cnt) take(buf, (size_t)(cnt))
+      AL(cam_se3, 12 * (size_t)C); AL(cam_se3_new, 12 * (size_t)C); AL(U, 21 * (size_t)C); AL(epsA, 6 * (size_t)C);
+      AL(cam_fixed, C); AL(cam_row, C);
+      AL(pt_pos, 3 * (size_t)P); AL(pt_pos_new, 3 * (size_t)P); AL(V, 6 * (size_t)P); AL(epsB, 3 * (size_t)P);
+      AL(Vinv, 9 * (size_t)P); AL(Ve, 3 * (size_t)P); AL(pt_off, P + 1); AL(pt_meas, M);
+      AL(m_cam, M); AL(m_pt, M); AL(m_found, 2 * (size_t)M); AL(m_sin, M); AL(m_state, M); AL(m_v3cam, 3 * (size_t)M);
+      AL(m_derivs, 4 * (size_t)M); AL(m_eps, 2 * (size_t)M); AL(m_e2, M); AL(m_W, 18 * (size_t)M); AL(e2c, M);
+      AL(S, (size_t)n * n); AL(vE, n); AL(upd, n); AL(scal, 8); AL(counters, 4); AL(outliers, 2 * (size_t)M);
+      AL(Wp, (size_t)n * kNB);
+      AL(m_gid, M); AL(m_erase_step, M); AL(hist16, 65536); AL(sel_state, 2);
+      AL(g_steps, world > 1 ? MG : 0);
 #undef AL
+      if (!pass) {
+        need = off;
+        if (need > arena_cap) {
+          if (arena) { cudaStreamSynchronize(stream); cudaFree(arena); arena = nullptr; arena_cap = 0; }
+          PTAM_CUDA_TRY(this, cudaMalloc(&arena, need));
+          arena_cap = need;
+        }
+      }
+    }
+    PTAM_CUDA_TRY(this, cudaMemsetAsync(arena, 0, need, stream));
+    PTAM_CUDA_TRY(this, cudaStreamSynchronize(stream));
 #define UP(buf, vec) if (!vec.empty()) PTAM_CUDA_TRY(this, cudaMemcpy(buf.p, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice))
     UP(cam_se3, h_cam_se3); UP(cam_fixed, h_cam_fixed); UP(cam_row, h_cam_row); UP(pt_pos, h_pts);
     UP(pt_off, off); UP(pt_meas, idx); UP(m_cam, l_mcam); UP(m_pt, l_mpt); UP(m_found, l_found); UP(m_sin, l_sin);

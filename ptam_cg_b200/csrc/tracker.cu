@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstring>
 #include <mutex>
+#include <unordered_map>
 #include <vector>
 
 using namespace ptam;
@@ -91,6 +92,12 @@ struct ptam_tracker {
   double prof_ms[8] = {};
   int64_t prof_n[8] = {};
   int max_h = 0;
+  // pipelined submit / collect: two frame landing buffers, a copy stream, per-slot events and results
+  cudaStream_t cstream = nullptr;
+  DevBuf<uint8_t> l0slot[2];
+  StreamCtl* h_ctl_slot[2] = {nullptr, nullptr};
+  cudaEvent_t ev_h2d[2] = {}, ev_done[2] = {};
+  long long n_submit = 0, n_collect = 0;
 
   void set_error(const std::string& e) { err = e; g_last_error = e; }
 
@@ -105,6 +112,13 @@ struct ptam_tracker {
     pvs.free(); iter_idx.free(); center.free(); tmpl.free();
     if (stage_ev) cudaEventDestroy(stage_ev);
     for (auto e : prof_ev) if (e) cudaEventDestroy(e);
+    for (int k = 0; k < 2; k++) {
+      l0slot[k].free();
+      if (h_ctl_slot[k]) cudaFreeHost(h_ctl_slot[k]);
+      if (ev_h2d[k]) cudaEventDestroy(ev_h2d[k]);
+      if (ev_done[k]) cudaEventDestroy(ev_done[k]);
+    }
+    if (cstream) cudaStreamDestroy(cstream);
     if (h_stage) cudaFreeHost(h_stage);
     if (h_ctl) cudaFreeHost(h_ctl);
     if (stream) cudaStreamDestroy(stream);
@@ -204,21 +218,47 @@ struct ptam_tracker {
     return cudaSuccess;
   }
 
-  static bool is_pinned(const void* p) {
+  // cudaPointerGetAttributes costs tens of microseconds per host pointer; frame buffers come from a
+  // small ring in practice, so the answer is cached per pointer.  A stale "pinned" entry is harmless
+  // (cudaMemcpyAsync from pageable memory is still correct, only synchronous).
+  std::unordered_map<const void*, bool> pinned_cache;
+  std::vector<void*> batch_dst, batch_src;
+  std::vector<size_t> batch_size;
+  bool is_pinned(const void* p) {
+    auto it = pinned_cache.find(p);
+    if (it != pinned_cache.end()) return it->second;
     cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return a.type == cudaMemoryTypeHost;
+    bool pinned = false;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) cudaGetLastError();
+    else pinned = a.type == cudaMemoryTypeHost;
+    if (pinned_cache.size() > 8192) pinned_cache.clear();
+    pinned_cache.emplace(p, pinned);
+    return pinned;
   }
 
-  int upload_images(const uint8_t* const* images, int stride, uint8_t* dst, size_t dst_stream_pitch, int n) {
+  int upload_images(const uint8_t* const* images, int stride, uint8_t* dst, size_t dst_stream_pitch, int n, cudaStream_t st = nullptr) {
+    if (!st) st = stream;
     const LevelDesc& L0 = dev.g.lev[0];
     // page-locked caller buffers (cudaHostAlloc / cudaHostRegister): DMA straight from them
     bool pinned = true;
     for (int s = 0; s < n && pinned; s++) pinned = is_pinned(images[s]);
     if (pinned) {
-      for (int s = 0; s < n; s++)
-        PTAM_CUDA_TRY(this, cudaMemcpy2DAsync(dst + (size_t)s * dst_stream_pitch, L0.pitch, images[s], stride, W, H,
-                                              cudaMemcpyHostToDevice, stream));
+      const bool dense = stride == W && L0.pitch == W;  // whole frame is one contiguous run on both sides
+      if (dense && n > 1) {  // one driver call for the whole batch instead of n copy submissions
+        batch_dst.resize(n); batch_src.resize(n); batch_size.assign(n, (size_t)W * H);
+        for (int s = 0; s < n; s++) { batch_dst[s] = dst + (size_t)s * dst_stream_pitch; batch_src[s] = const_cast<uint8_t*>(images[s]); }
+        cudaMemcpyAttributes at{};
+        at.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+        size_t attr_idx = 0, fail_idx = 0;
+        if (cudaMemcpyBatchAsync(batch_dst.data(), batch_src.data(), batch_size.data(), (size_t)n, &at, &attr_idx, 1, &fail_idx, st) == cudaSuccess)
+          return PTAM_OK;
+        cudaGetLastError();  // not available on this driver: fall back to one copy per frame
+      }
+      for (int s = 0; s < n; s++) {
+        if (dense) PTAM_CUDA_TRY(this, cudaMemcpyAsync(dst + (size_t)s * dst_stream_pitch, images[s], (size_t)W * H, cudaMemcpyHostToDevice, st));
+        else PTAM_CUDA_TRY(this, cudaMemcpy2DAsync(dst + (size_t)s * dst_stream_pitch, L0.pitch, images[s], stride, W, H,
+                                                   cudaMemcpyHostToDevice, st));
+      }
       return PTAM_OK;
     }
     // pageable memory: pack into the pinned staging buffer with the library pitch, then async H2D
@@ -229,8 +269,8 @@ struct ptam_tracker {
     }
     for (int s = 0; s < n; s++)
       PTAM_CUDA_TRY(this, cudaMemcpyAsync(dst + (size_t)s * dst_stream_pitch, h_stage + (size_t)s * dst_stream_pitch,
-                                          (size_t)L0.pitch * H, cudaMemcpyHostToDevice, stream));
-    PTAM_CUDA_TRY(this, cudaEventRecord(stage_ev, stream));
+                                          (size_t)L0.pitch * H, cudaMemcpyHostToDevice, st));
+    PTAM_CUDA_TRY(this, cudaEventRecord(stage_ev, st));
     return PTAM_OK;
   }
 
@@ -287,8 +327,25 @@ struct ptam_tracker {
   int fetch_results(ptam_track_result* results) {
     PTAM_CUDA_TRY(this, cudaMemcpyAsync(h_ctl, ctl.p, sizeof(StreamCtl) * S, cudaMemcpyDeviceToHost, stream));
     PTAM_CUDA_TRY(this, cudaStreamSynchronize(stream));
+    convert_results(h_ctl, results);
+    return PTAM_OK;
+  }
+
+  int ensure_pipeline() {
+    if (cstream) return PTAM_OK;
+    PTAM_CUDA_TRY(this, cudaStreamCreateWithFlags(&cstream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+      PTAM_CUDA_TRY(this, l0slot[k].alloc((size_t)dev.g.lev[0].pitch * H * S));
+      PTAM_CUDA_TRY(this, cudaMallocHost(&h_ctl_slot[k], sizeof(StreamCtl) * S));
+      PTAM_CUDA_TRY(this, cudaEventCreateWithFlags(&ev_h2d[k], cudaEventDisableTiming));
+      PTAM_CUDA_TRY(this, cudaEventCreateWithFlags(&ev_done[k], cudaEventDisableTiming));
+    }
+    return PTAM_OK;
+  }
+
+  void convert_results(const StreamCtl* hc, ptam_track_result* results) {
     for (int s = 0; s < S; s++) {
-      const StreamCtl& c = h_ctl[s];
+      const StreamCtl& c = hc[s];
       ptam_track_result& r = results[s];
       std::memcpy(r.se3_cam_from_world, c.st.se3_cam_from_world, sizeof(double) * 12);
       r.scene_depth_mean = c.st.scene_depth_mean; r.scene_depth_sigma = c.st.scene_depth_sigma;
@@ -300,7 +357,6 @@ struct ptam_tracker {
       r.tracking_quality = c.st.tracking_quality; r.quality_needs_kf_distance = c.needs_kf_distance;
       r.reserved = 0;
     }
-    return PTAM_OK;
   }
 };
 
@@ -437,6 +493,39 @@ int ptam_tracker_track_frames_device(ptam_tracker* t, const uint8_t* d_images, s
   int rc = t->launch_track(d);
   if (rc) return rc;
   if (results) return t->fetch_results(results);
+  return PTAM_OK;
+}
+
+int ptam_tracker_submit_frames(ptam_tracker* t, const uint8_t* const* images, int stride) {
+  cudaSetDevice(t->device);
+  if (t->n_submit - t->n_collect >= 2) { t->set_error("two frame batches are already in flight: collect one first"); return PTAM_ERR_CAPACITY; }
+  int rc = t->ensure_pipeline();
+  if (rc) return rc;
+  const int k = (int)(t->n_submit & 1);
+  const size_t pitch = (size_t)t->dev.g.lev[0].pitch * t->H;
+  // the slot's previous batch was collected (its ev_done has fired), so the landing buffer is free
+  rc = t->upload_images(images, stride, t->l0slot[k].p, pitch, t->S, t->cstream);
+  if (rc) return rc;
+  PTAM_CUDA_TRY(t, cudaEventRecord(t->ev_h2d[k], t->cstream));
+  PTAM_CUDA_TRY(t, cudaStreamWaitEvent(t->stream, t->ev_h2d[k], 0));
+  TrackerDev d = t->dev;
+  d.src.l0 = t->l0slot[k].p; d.src.stream_pitch = pitch; d.src.pitch = d.g.lev[0].pitch;
+  t->dev.src = d.src;
+  rc = t->launch_track(d);
+  if (rc) return rc;
+  PTAM_CUDA_TRY(t, cudaMemcpyAsync(t->h_ctl_slot[k], t->ctl.p, sizeof(StreamCtl) * t->S, cudaMemcpyDeviceToHost, t->stream));
+  PTAM_CUDA_TRY(t, cudaEventRecord(t->ev_done[k], t->stream));
+  t->n_submit++;
+  return PTAM_OK;
+}
+
+int ptam_tracker_collect(ptam_tracker* t, ptam_track_result* results) {
+  cudaSetDevice(t->device);
+  if (t->n_collect >= t->n_submit) { t->set_error("nothing in flight"); return PTAM_ERR_INVALID; }
+  const int k = (int)(t->n_collect & 1);
+  PTAM_CUDA_TRY(t, cudaEventSynchronize(t->ev_done[k]));
+  if (results) t->convert_results(t->h_ctl_slot[k], results);
+  t->n_collect++;
   return PTAM_OK;
 }
 

@@ -182,3 +182,36 @@ def test_empty_map_and_no_cuda_fallback(product):
     r = t.track_frames([im, im])
     assert sum(r[0].meas_attempted) == 0 and r[0].tracking_quality == 0
     assert t.launch_count() > 0
+
+
+@pytest.mark.gpu
+def test_pipelined_submit_collect_matches_blocking(product, seq640, map640):
+    """ptam_tracker_submit_frames / _collect (two batches in flight) gives the same results as the
+    blocking ptam_tracker_track_frames on the same frames."""
+    frames, poses = seq640
+    kfs, m = map640
+    S = 3
+    trackers = []
+    for _ in range(2):
+        t = Tracker(product, 640, 480, S)
+        for k in kfs:
+            t.add_keyframe(k)
+        for s in range(S):
+            t.set_map(s, m)
+            t.set_state(s, pose12=synth.perturb_pose(poses[2 + s], np.random.default_rng(s)), velocity=np.zeros(6), msd=0.0)
+        trackers.append(t)
+    a, b = trackers
+    batches = [[np.ascontiguousarray(frames[2 + s + i]) for s in range(S)] for i in range(5)]
+    ref = [a.track_frames(bt) for bt in batches]
+    out = []
+    b.submit_ptrs([im.ctypes.data for im in batches[0]], 640)
+    for i in range(1, 5):
+        b.submit_ptrs([im.ctypes.data for im in batches[i]], 640)
+        out.append(b.collect())
+    out.append(b.collect())
+    with pytest.raises(Exception):
+        b.collect()
+    for r_step, o_step in zip(ref, out):
+        for r, o in zip(r_step, o_step):
+            assert list(r.se3_cam_from_world) == list(o.se3_cam_from_world)
+            assert list(r.meas_found) == list(o.meas_found) and list(r.n_corners) == list(o.n_corners)
