@@ -291,6 +291,8 @@ def main():
     found = float(np.mean([sum(r.meas_found) for r in last]))
     attempted = float(np.mean([sum(r.meas_attempted) for r in last]))
     n_corners = float(np.mean([sum(r.n_corners) for r in last]))
+    n_cand = float(np.mean([r.n_candidates for r in last]))
+    n_searched = float(np.mean([r.n_coarse + r.n_level3 + r.n_fine for r in last]))
     tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -305,8 +307,9 @@ def main():
     def frame_ptrs(i):
         return [base + pingpong(o + i, F) * FRAME_BYTES for o in offsets]
 
-    for i in range(Wm):
-        trk.track_frames_ptrs(frame_ptrs(i), W, want_results=True)
+    for i in range(Wm):  # warm-up through the same pipelined calls (first use allocates the landing buffers)
+        trk.submit_ptrs(frame_ptrs(i), W)
+        trk.collect()
     barrier()
     # pipelined public API: submit (H2D of this step's frames + kernels) / collect (D2H of its results);
     # at most two steps in flight, so the copy of step i+1 overlaps the kernels of step i
@@ -340,6 +343,11 @@ def main():
         "k_pyramid": S * pyr_px,
         "k_fast": S * (pyr_px + pyr_px // 8),
         "k_compact": S * (pyr_px // 8 + 8 * n_corners + 4 * sum(H >> l for l in range(4))),
+        # 64 B template per searched point + (64 B window + 8 B corner) per candidate;
+        # coarse and fine launches share the frame's candidate count pro rata to their point counts
+        "k_search_fine": S * (64 * attempted + 72 * n_cand),
+        # a10: 136 B per found point per Gauss-Newton iteration, ten iterations
+        "k_pose_fine": S * 10 * 136 * found,
     }
     per_kernel = {}
     for k, (tot, n) in kt.items():
@@ -392,7 +400,7 @@ def main():
                    "l2": f"inputs > L2: every step reads a distinct {S}x{FRAME_BYTES} B batch out of a "
                          f"{n_steps * S * FRAME_BYTES / 1e6:.0f} MB resident set",
                    "mean_found_per_frame": found, "mean_attempted_per_frame": attempted,
-                   "mean_corners_per_frame": n_corners},
+                   "mean_corners_per_frame": n_corners, "mean_zmssd_candidates_per_frame": n_cand},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": S * FRAME_BYTES,
                 "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * float(te.item()) / K,
                 "api": "ptam_tracker_submit_frames / ptam_tracker_collect, pinned host frames, 2 steps in flight"},

@@ -100,7 +100,7 @@ typedef struct ptam_track_result {
   int32_t quality_needs_kf_distance;   /* 1: reference would consult MapMaker::ClosestKeyFrame
                                           (Tracker.cc:1095-1099); left to the caller */
   int32_t n_pvs[PTAM_LEVELS];          /* PVS size per level before selection */
-  int32_t reserved;
+  int32_t n_candidates;                /* ZMSSD windows evaluated (FindPatchCoarse candidates, PatchFinder.cc:193-200) */
 } ptam_track_result;
 
 typedef struct ptam_tracker ptam_tracker;

@@ -576,7 +576,7 @@ struct Tracker {
     }
     r.did_coarse = s.did_coarse;
     r.tracking_quality = s.st.tracking_quality;
-    r.reserved = 0;
+    r.n_candidates = 0;  // product-only diagnostic (roofline accounting); not part of the parity contract
   }
 };
 

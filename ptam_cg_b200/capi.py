@@ -46,7 +46,7 @@ class TrackResult(C.Structure):
         ("meas_found", C.c_int32 * 4), ("n_corners", C.c_int32 * 4), ("did_coarse", C.c_int32),
         ("n_coarse", C.c_int32), ("n_level3", C.c_int32), ("n_fine", C.c_int32),
         ("tracking_quality", C.c_int32), ("quality_needs_kf_distance", C.c_int32),
-        ("n_pvs", C.c_int32 * 4), ("reserved", C.c_int32),
+        ("n_pvs", C.c_int32 * 4), ("n_candidates", C.c_int32),
     ]
 
 

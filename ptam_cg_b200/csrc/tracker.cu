@@ -81,6 +81,7 @@ struct ptam_tracker {
   DevBuf<double> world, right, down, last_warp, m2buf, v3cam, v2image, derivs, warp_inv, v2found, sin_, J, e2;
   DevBuf<int> src_kf, src_level, tsum, tsumsq, flags, level, search_level, outliers, inliers, pvs, iter_idx;
   DevBuf<int2> center;
+  DevBuf<int4> geo;
   DevBuf<uint8_t> tmpl;
   // pinned staging
   uint8_t* h_stage = nullptr;
@@ -106,7 +107,7 @@ struct ptam_tracker {
     if (stream) cudaStreamSynchronize(stream);
     for (auto p : kf_bufs) cudaFree(p);
     pyr.free(); corners.free(); lut.free(); mask.free(); ctl.free(); pt_count.free(); kf_ptrs.free();
-    world.free(); right.free(); down.free(); last_warp.free(); m2buf.free(); v3cam.free(); v2image.free(); derivs.free();
+    world.free(); right.free(); down.free(); last_warp.free(); m2buf.free(); geo.free(); v3cam.free(); v2image.free(); derivs.free();
     warp_inv.free(); v2found.free(); sin_.free(); J.free(); e2.free(); src_kf.free(); src_level.free();
     tsum.free(); tsumsq.free(); flags.free(); level.free(); search_level.free(); outliers.free(); inliers.free();
     pvs.free(); iter_idx.free(); center.free(); tmpl.free();
@@ -201,7 +202,7 @@ struct ptam_tracker {
     const int nc = std::max(n, cap * 2);
     cudaError_t e = cudaSuccess;
 #define RG(buf, k) if (e == cudaSuccess) e = regrow(buf, k, cap, nc)
-    RG(world, 3); RG(right, 3); RG(down, 3); RG(last_warp, 4); RG(m2buf, 4); RG(v3cam, 3); RG(v2image, 2); RG(derivs, 4);
+    RG(world, 3); RG(right, 3); RG(down, 3); RG(last_warp, 4); RG(m2buf, 4); RG(geo, 2); RG(v3cam, 3); RG(v2image, 2); RG(derivs, 4);
     RG(warp_inv, 4); RG(v2found, 2); RG(sin_, 1); RG(J, 12); RG(e2, 1); RG(src_kf, 1); RG(src_level, 1);
     RG(tsum, 1); RG(tsumsq, 1); RG(flags, 1); RG(level, 1); RG(search_level, 1); RG(outliers, 1); RG(inliers, 1);
     RG(pvs, 4); RG(iter_idx, 1); RG(center, 1); RG(tmpl, 64);
@@ -210,7 +211,7 @@ struct ptam_tracker {
     cap = nc;
     PointArrays& p = dev.p;
     p.world = world.p; p.right = right.p; p.down = down.p; p.src_kf = src_kf.p; p.src_level = src_level.p; p.center = center.p;
-    p.tmpl = tmpl.p; p.tsum = tsum.p; p.tsumsq = tsumsq.p; p.last_warp = last_warp.p; p.m2 = m2buf.p;
+    p.tmpl = tmpl.p; p.tsum = tsum.p; p.tsumsq = tsumsq.p; p.last_warp = last_warp.p; p.m2 = m2buf.p; p.geo = geo.p;
     p.flags = flags.p; p.level = level.p; p.search_level = search_level.p;
     p.v3cam = v3cam.p; p.v2image = v2image.p; p.derivs = derivs.p; p.warp_inv = warp_inv.p;
     p.v2found = v2found.p; p.sqrt_inv_noise = sin_.p; p.J = J.p; p.outliers = outliers.p; p.inliers = inliers.p;
@@ -355,7 +356,7 @@ struct ptam_tracker {
       }
       r.did_coarse = c.did_coarse; r.n_coarse = c.n_coarse; r.n_level3 = c.n_l3; r.n_fine = c.n_fine;
       r.tracking_quality = c.st.tracking_quality; r.quality_needs_kf_distance = c.needs_kf_distance;
-      r.reserved = 0;
+      r.n_candidates = c.n_cand;
     }
   }
 };

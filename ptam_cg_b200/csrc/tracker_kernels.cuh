@@ -51,7 +51,7 @@ struct StreamCtl {
   int try_coarse, coarse_range, did_coarse;
   int n_corners[kLevels];
   int needs_kf_distance;
-  int pad;
+  int n_cand;  // ZMSSD windows evaluated this frame (coarse + fine), for the roofline accounting
 };
 
 // frame-scoped point flags (low byte) and persistent flags (high bits)
@@ -68,6 +68,7 @@ struct PointArrays {
   const int* src_kf; const int* src_level; const int2* center;
   // template cache
   uint8_t* tmpl; int* tsum; int* tsumsq; double* last_warp; double* m2;
+  int4* geo;      // per point, 2 x int4: (posx, posy, r, -), (i0, i1, -, -) of FindPatchCoarse, written by k_search_prep
   // frame state
   int* flags; int* level; int* search_level;
   double* v3cam; double* v2image; double* derivs; double* warp_inv;
@@ -437,6 +438,7 @@ __global__ void __launch_bounds__(1024) k_pvs_select(TrackerDev d) {
     se3_mul(ex, ctl.start_pose, np);
     for (int i = 0; i < 12; i++) { pose[i] = np[i]; ctl.pose[i] = np[i]; }
     for (int l = 0; l < kLevels; l++) { running[l] = 0; ctl.attempted[l] = 0; ctl.found[l] = 0; }
+    ctl.n_cand = 0;
   }
   __syncthreads();
   int* pvs = d.p.pvs + (size_t)s * kLevels * cap;
@@ -607,6 +609,26 @@ __global__ void __launch_bounds__(128) k_search_prep(TrackerDev d, int stage) {
     for (int q = 0; q < 4; q++) d.p.m2[4 * g + q] = m2[q];
   }
   d.p.flags[g] = fl;
+  // ---- FindPatchCoarse, the scalar part (PatchFinder.cc:160-191): search centre and range in level
+  // coordinates (ir() truncation, C++ integer division), candidate index range from the row LUT
+  {
+    const unsigned range = stage == 0 ? (unsigned)ctl.coarse_range : (ctl.did_coarse ? 5u : 10u);
+    const int scale = 1 << sl;
+    const int posx = (int)d.p.v2image[2 * g] / scale, posy = (int)d.p.v2image[2 * g + 1] / scale;
+    const unsigned r = (range + scale - 1) / scale;
+    int top = posy - (int)r;
+    const int bot1 = posy + (int)r + 1;
+    const LevelDesc& L = d.g.lev[sl];
+    if (top < 0) top = 0;
+    int i0 = 0, i1 = 0;
+    if (!(top >= L.h) && !(bot1 <= 0)) {
+      const int* lut = d.lut + (size_t)s * d.g.lut_stride + L.lut_off;
+      i0 = lut[top];
+      i1 = bot1 >= L.h ? ctl.n_corners[sl] : lut[bot1];
+    }
+    d.p.geo[2 * g] = make_int4(posx, posy, (int)r, 0);
+    d.p.geo[2 * g + 1] = make_int4(i0, i1, 0, 0);
+  }
 }
 
 __global__ void __launch_bounds__(128) k_search(TrackerDev d, int stage) {
@@ -698,27 +720,21 @@ __global__ void __launch_bounds__(128) k_search(TrackerDev d, int stage) {
   bool found = false;
   double coarse[2] = {0, 0};
   {
-    const int scale = 1 << sl;
-    const int posx = (int)v2image[0] / scale, posy = (int)v2image[1] / scale;
-    const unsigned r = (range + scale - 1) / scale;
-    int top = posy - (int)r;
-    const int bot1 = posy + (int)r + 1;
+    const int4 g0 = d.p.geo[2 * g], g1 = d.p.geo[2 * g + 1];
+    const int posx = g0.x, posy = g0.y;
+    const unsigned r = (unsigned)g0.z;
     const int left = posx - (int)r, right = posx + (int)r;
     const LevelDesc& L = d.g.lev[sl];
     int pitch;
     const uint8_t* im = level_image(d, s, sl, pitch);
-    if (top < 0) top = 0;
-    if (!(top >= L.h) && !(bot1 <= 0)) {
-      const int* lut = d.lut + (size_t)s * d.g.lut_stride + L.lut_off;
+    const int i0 = g1.x, i1 = g1.y;
+    if (i1 > i0) {
       const int2* corners = d.corners + (size_t)s * d.g.corner_stride + L.corner_off;
-      const int i0 = lut[top];
-      const int i1 = bot1 >= L.h ? ctl.n_corners[sl] : lut[bot1];
       // Candidates (disc test + 4-px border, PatchFinder.cc:193-196, ImageProcess.cc:134) are queued per
       // warp; ZMSSD then runs four candidates at a time, eight lanes per candidate, one 8-pixel window
       // row per lane: three aligned 32-bit loads + byte_perm, six dp4a, group reduction.  The winner is
       // the minimum of (ssd, corner index), i.e. the first minimum in raster order (PatchFinder.cc:198).
       const int sub = lane & 7, grp = lane >> 3;
-      const unsigned gmask = 0xFFu << (8 * grp);
       const unsigned tw0 = *reinterpret_cast<const unsigned*>(&stmpl[warp][8 * sub]);
       const unsigned tw1 = *reinterpret_cast<const unsigned*>(&stmpl[warp][8 * sub + 4]);
       int best_ssd = kMaxSSD + 1, best_idx = 0x7fffffff;
@@ -737,16 +753,19 @@ __global__ void __launch_bounds__(128) k_search(TrackerDev d, int stage) {
           int isum = (int)__dp4a(v0, 0x01010101u, __dp4a(v1, 0x01010101u, 0u));
           int isq = (int)__dp4a(v0, v0, __dp4a(v1, v1, 0u));
           int cross = (int)__dp4a(v0, tw0, __dp4a(v1, tw1, 0u));
-          isum = __reduce_add_sync(gmask, isum);
-          isq = __reduce_add_sync(gmask, isq);
-          cross = __reduce_add_sync(gmask, cross);
+#pragma unroll
+          for (int o = 4; o > 0; o >>= 1) {  // sum over the 8 lanes (window rows) of the group
+            isum += __shfl_xor_sync(kFull, isum, o);
+            isq += __shfl_xor_sync(kFull, isq, o);
+            cross += __shfl_xor_sync(kFull, cross, o);
+          }
           const int SA = tsum, SB = isum;
           const int ssd = ((2 * SA * SB - SA * SA - SB * SB) / 64 + isq + tsumsq - 2 * cross);  // C++ truncating division
           if (valid && (ssd < best_ssd || (ssd == best_ssd && e.y < best_idx))) { best_ssd = ssd; best_idx = e.y; }
         }
         __syncwarp();
       };
-      int qn = 0;
+      int qn = 0, n_eval = 0;
       const unsigned lt = (1u << lane) - 1u;
       for (int b0 = i0; b0 < i1; b0 += 32) {
         const int i = b0 + lane;
@@ -762,10 +781,12 @@ __global__ void __launch_bounds__(128) k_search(TrackerDev d, int stage) {
         const unsigned m = __ballot_sync(kFull, pass);
         if (pass) squeue[warp][qn + __popc(m & lt)] = make_int2(c.x | (c.y << 16), i);
         qn += __popc(m);
+        n_eval += __popc(m);
         if (qn > 32) { __syncwarp(); process(qn); qn = 0; }
       }
       __syncwarp();
       process(qn);
+      if (lane == 0 && n_eval) atomicAdd(&ctl.n_cand, n_eval);
       {
         const int bs = __reduce_min_sync(kFull, best_ssd);
         best_idx = __reduce_min_sync(kFull, best_ssd == bs ? best_idx : 0x7fffffff);
