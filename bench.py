@@ -430,7 +430,9 @@ def main():
                 uid = torch.tensor(list(capi.nccl_unique_id(prod) if rank == 0 else bytes(capi.NCCL_UNIQUE_ID_BYTES)),
                                    dtype=torch.uint8, device="cuda")
                 dist.broadcast(uid, 0)
-                r = bench_ba(prod, local, "C4", reps=3, shard=(rank, world, bytes(uid.cpu().tolist())))
+                comm = capi.nccl_comm_create(prod, local, rank, world, bytes(uid.cpu().tolist()))
+                r = bench_ba(prod, local, "C4", reps=3, shard=(rank, world, comm))
+                prod.fn("nccl_comm_destroy")(comm)
                 r["sharding"] = f"points partitioned over {world} ranks, ncclAllReduce of S ({r['reduced_system_n']}^2 f64) + vE per lambda trial"
                 ba["C4_sharded"] = r
         except Exception as e:  # the tracker line must still be printed

@@ -245,6 +245,11 @@ int ptam_bundle_add_measurements(ptam_bundle* b, int n, const int32_t* cam, cons
 int ptam_nccl_unique_id(unsigned char id[PTAM_NCCL_UNIQUE_ID_BYTES]);
 int ptam_bundle_init_shard(ptam_bundle* b, int rank, int world, const unsigned char id[PTAM_NCCL_UNIQUE_ID_BYTES]);
 int ptam_bundle_set_shard(ptam_bundle* b, int rank, int world, void* nccl_comm);
+/* A communicator that outlives individual handles (MapMaker builds a new Bundle per adjustment,
+ * MapMaker.cc:840; a unique id can initialise only one communicator): create it once per process,
+ * hand it to every handle with ptam_bundle_set_shard, destroy it at shutdown.  NULL on failure. */
+void* ptam_nccl_comm_create(int device, int rank, int world, const unsigned char id[PTAM_NCCL_UNIQUE_ID_BYTES]);
+void ptam_nccl_comm_destroy(void* comm);
 /* Host-only: point_begin[world + 1], shard r owns points [point_begin[r], point_begin[r + 1]). */
 int ptam_bundle_shard_plan(int n_points, int n_meas, const int32_t* meas_point, int world, int32_t* point_begin);
 

@@ -26,7 +26,7 @@ def flops_per_trial(n):
 
 
 def bench_ba(prod, device=0, config="C3", reps=3, cpu_lib=None, shard=None, graph=None, cpu_trials=None):
-    """shard: None or (rank, world, nccl_unique_id_bytes).  cpu_lib: an already-loaded CPU library
+    """shard: None or (rank, world, ncclComm_t from capi.nccl_comm_create).  cpu_lib: an already-loaded CPU library
     exporting the same ABI (bench.py passes the oracle for the cpu_baseline leg; this package never
     loads it itself).  cpu_trials: cap on the CPU leg's lambda trials (bounded sample)."""
     import torch
@@ -38,7 +38,7 @@ def bench_ba(prod, device=0, config="C3", reps=3, cpu_lib=None, shard=None, grap
         b = Bundle(prod, g["width"], g["height"], device=device)
         b.add_graph(g)
         if shard is not None:
-            b.init_shard(*shard)
+            b.set_shard(*shard)
         if r == reps:
             b.set_profiling(True)  # last repetition: per-phase events (adds synchronisation, not the timed one)
         b.synchronize()

@@ -86,7 +86,7 @@ PRODUCT_ONLY_SYMBOLS = [
     "global_last_error", "tracker_track_frames_device", "tracker_submit_frames", "tracker_collect", "tracker_cuda_stream",
     "tracker_launch_count", "tracker_set_profiling", "tracker_get_kernel_times",
     "bundle_cuda_stream", "bundle_launch_count",
-    "nccl_unique_id", "bundle_init_shard", "bundle_shard_plan",
+    "nccl_unique_id", "nccl_comm_create", "nccl_comm_destroy", "bundle_init_shard", "bundle_shard_plan",
     "bundle_set_profiling", "bundle_get_phase_times",
 ]
 BUNDLE_PHASES = ["project", "select", "jacobian", "vinv_init", "schur", "allreduce", "solve", "update_newerror"]
@@ -173,6 +173,8 @@ class Lib:
             "bundle_add_measurements": (i, [vp, i, P(C.c_int32), P(C.c_int32), P(d), P(d)]),
             "bundle_set_shard": (i, [vp, i, i, vp]),
             "nccl_unique_id": (i, [P(C.c_ubyte)]),
+            "nccl_comm_create": (vp, [i, i, i, P(C.c_ubyte)]),
+            "nccl_comm_destroy": (None, [vp]),
             "bundle_init_shard": (i, [vp, i, i, P(C.c_ubyte)]),
             "bundle_shard_plan": (i, [i, i, P(C.c_int32), i, P(C.c_int32)]),
             "bundle_compute": (i, [vp, P(C.c_ubyte)]),
@@ -217,6 +219,15 @@ def nccl_unique_id(lib: Lib) -> bytes:
     if lib.fn("nccl_unique_id")(buf) != 0:
         raise PtamError(lib.fn("global_last_error")().decode())
     return bytes(buf)
+
+
+def nccl_comm_create(lib: Lib, device, rank, world, unique_id: bytes):
+    """One communicator per process, shared by every sharded Bundle (pass it to Bundle.set_shard)."""
+    buf = (C.c_ubyte * NCCL_UNIQUE_ID_BYTES).from_buffer_copy(unique_id)
+    comm = lib.fn("nccl_comm_create")(int(device), int(rank), int(world), buf)
+    if not comm:
+        raise PtamError(lib.fn("global_last_error")().decode())
+    return comm
 
 
 def shard_plan(lib: Lib, n_points, meas_point, world):

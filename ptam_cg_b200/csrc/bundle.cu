@@ -521,6 +521,21 @@ int ptam_bundle_init_shard(ptam_bundle* b, int rank, int world, const unsigned c
   return PTAM_OK;
 }
 
+void* ptam_nccl_comm_create(int device, int rank, int world, const unsigned char id[PTAM_NCCL_UNIQUE_ID_BYTES]) {
+  if (world < 1 || rank < 0 || rank >= world) { ptam_set_global_error("bad rank / world"); return nullptr; }
+  if (!nccl_api().load()) { ptam_set_global_error(nccl_api().err); return nullptr; }
+  if (cudaSetDevice(device) != cudaSuccess) { ptam_set_global_error("bad device index"); return nullptr; }
+  ncclUniqueId u;
+  std::memcpy(&u, id, sizeof(u));
+  ncclComm_t comm = nullptr;
+  const ncclResult_t r = nccl_api().CommInitRank(&comm, world, u, rank);
+  if (r != ncclSuccess) { ptam_set_global_error(std::string("ncclCommInitRank: ") + nccl_api().GetErrorString(r)); return nullptr; }
+  return comm;
+}
+void ptam_nccl_comm_destroy(void* comm) {
+  if (comm && nccl_api().load()) nccl_api().CommDestroy((ncclComm_t)comm);
+}
+
 int ptam_bundle_shard_plan(int n_points, int n_meas, const int32_t* meas_point, int world, int32_t* point_begin) {
   if (n_points < 0 || n_meas < 0 || world < 1 || !point_begin) return PTAM_ERR_INVALID;
   for (int m = 0; m < n_meas; m++) if (meas_point[m] < 0 || meas_point[m] >= n_points) return PTAM_ERR_INVALID;
