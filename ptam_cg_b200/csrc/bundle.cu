@@ -105,7 +105,7 @@ struct ptam_bundle {
   bool own_comm = false;
   int p_lo = 0, p_hi = 0;
   std::vector<int> l_gid;            // local measurement -> insertion index
-  Buf<int> m_gid, m_erase_step, g_steps, hist16;
+  Buf<int> m_gid, m_erase_step, g_steps, hist16, erase_cnt;
   Buf<unsigned long long> sel_state;
   bool shards_dirty = false, abort_seen = false;
   std::vector<int> h_outliers;       // merged (point, camera) pairs in the reference's erase order
@@ -223,7 +223,7 @@ struct ptam_bundle {
       AL(m_derivs, 4 * (size_t)M); AL(m_eps, 2 * (size_t)M); AL(m_e2, M); AL(m_W, 18 * (size_t)M); AL(e2c, M);
       AL(S, (size_t)n * n); AL(vE, n); AL(upd, n); AL(scal, 8); AL(counters, 4); AL(outliers, 2 * (size_t)M);
       AL(Wp, (size_t)n * kNB);
-      AL(m_gid, M); AL(m_erase_step, M); AL(hist16, 65536); AL(sel_state, 2);
+      AL(m_gid, M); AL(m_erase_step, M); AL(hist16, kSelBins); AL(erase_cnt, (M + 1023) / 1024 + 1); AL(sel_state, 2);
       AL(g_steps, world > 1 ? MG : 0);
 #undef AL
       if (!pass) {
@@ -299,12 +299,12 @@ struct ptam_bundle {
       }
       return PTAM_OK;
     }
-    for (int pass = 0; pass < 4; pass++) {
-      PTAM_CUDA_TRY(this, cudaMemsetAsync(hist16.p, 0, sizeof(int) * 65536, stream));
-      if (M > 0) { k_ba_hist16<<<std::min((M + 255) / 256, 148 * 8), 256, 0, stream>>>(d, pass); launches++; }
-      int rc = all_reduce(hist16.p, 65536, ncclInt32, ncclSum, "all-reduce of the select histogram");
+    for (int pass = 0; pass < kSelPasses; pass++) {
+      PTAM_CUDA_TRY(this, cudaMemsetAsync(hist16.p, 0, sizeof(int) * kSelBins, stream));
+      if (M > 0) { k_ba_hist<<<std::min((M + 255) / 256, 148 * 8), 256, 0, stream>>>(d, pass); launches++; }
+      int rc = all_reduce(hist16.p, kSelBins, ncclInt32, ncclSum, "all-reduce of the select histogram");
       if (rc) return rc;
-      k_ba_pick16<<<1, 1024, 0, stream>>>(d, pass, min_s2);
+      k_ba_pick<<<1, 1024, 0, stream>>>(d, pass, min_s2);
       launches++;
     }
     return PTAM_OK;
@@ -395,7 +395,14 @@ struct ptam_bundle {
                                             cudaMemcpyDeviceToDevice, stream));
       accepted++;
     }
-    if (M > 0) { k_ba_erase<<<1, 1024, 0, stream>>>(d, lm_steps); launches++; }
+    if (M > 0 && M < 65536) { k_ba_erase<<<1, 1024, 0, stream>>>(d, lm_steps); launches++; }
+    else if (M > 0) {
+      const int nblk = (M + 1023) / 1024;
+      k_ba_erase_count<<<nblk, 1024, 0, stream>>>(d, erase_cnt.p);
+      k_ba_erase_scan<<<1, 1024, 0, stream>>>(d, erase_cnt.p, nblk);
+      k_ba_erase_write<<<nblk, 1024, 0, stream>>>(d, erase_cnt.p, lm_steps);
+      launches += 3;
+    }
     PTAM_CUDA_TRY(this, cudaMemcpyAsync(h_cnt, counters.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, stream));
     PTAM_CUDA_TRY(this, cudaStreamSynchronize(stream));
     n_outliers = h_cnt[1];

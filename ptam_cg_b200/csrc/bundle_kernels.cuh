@@ -59,7 +59,7 @@ struct BundleDev {
   // scalars: 0 n_valid (as double), 1 sigma^2, 2 current error, 3 new error, 4 sum sq update,
   //          5 abort votes, 6 lambda, 7 median   (2..5 are the slots summed across shards)
   double* scal;
-  int* hist16;                   // [65536] digit histogram of the distributed radix select
+  int* hist16;                   // [2048] digit histogram of the distributed radix select
   unsigned long long* sel_state; // [0] key prefix found so far, [1] rank still to find inside it
   int* counters;  // 0 n_valid, 1 n_outliers_total, 2 n_bad_this_step
   int* outliers;  // [M][2] (point, camera) in erase order
@@ -164,33 +164,52 @@ __global__ void __launch_bounds__(1024) k_ba_select(BundleDev d, double min_sigm
 }
 
 // ---------------------------------------------------------------------------------------------
-// Exact order statistic for large or sharded problems: MSB-first radix select with 16-bit digits
-// (4 passes).  Every pass: k_ba_hist16 (all CTAs, global atomics into 65536 bins) -> [all-reduce of
-// the bins across shards] -> k_ba_pick16 (one CTA finds the bin holding the wanted rank).  After
-// the last pass the prefix IS the bit pattern of the floor(n/2)-th smallest squared error
-// (Tools.h:152-162 sorts and takes element n/2), identical on every shard.
+// Exact order statistic for large or sharded problems: MSB-first radix select over the IEEE bit
+// patterns, six passes with digit widths 11,11,11,11,11,9.  Every pass: k_ba_hist (all CTAs: digits
+// aggregated per warp with match.any, per-CTA histogram in shared memory, non-zero bins flushed with
+// global atomics) -> [all-reduce of the 2048 bins across shards] -> k_ba_pick (one CTA finds the bin
+// holding the wanted rank).  After the last pass the prefix IS the bit pattern of the floor(n/2)-th
+// smallest squared error (Tools.h:152-162 sorts and takes element n/2), identical on every shard.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_ba_hist16(BundleDev d, int pass) {
-  const int shift = 48 - 16 * pass;
+constexpr int kSelPasses = 6;
+constexpr int kSelBins = 2048;
+PTAM_HD int sel_shift(int pass) { return pass < 5 ? 53 - 11 * pass : 0; }
+PTAM_HD int sel_width(int pass) { return pass < 5 ? 11 : 9; }
+
+__global__ void __launch_bounds__(256) k_ba_hist(BundleDev d, int pass) {
+  __shared__ int h[kSelBins];
+  for (int i = threadIdx.x; i < kSelBins; i += blockDim.x) h[i] = 0;
+  __syncthreads();
+  const int shift = sel_shift(pass), width = sel_width(pass);
   const unsigned long long prefix = d.sel_state[0];
-  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < d.n_meas; m += gridDim.x * blockDim.x) {
-    if (d.m_state[m] != M_ALIVE) continue;
-    const unsigned long long key = (unsigned long long)__double_as_longlong(d.m_e2[m]);
-    if (pass == 0 || (key >> (shift + 16)) == (prefix >> (shift + 16))) atomicAdd(&d.hist16[(key >> shift) & 0xffff], 1);
+  const int lane = threadIdx.x & 31;
+  for (int m0 = blockIdx.x * blockDim.x; m0 < d.n_meas; m0 += gridDim.x * blockDim.x) {
+    const int m = m0 + threadIdx.x;
+    bool take = false;
+    unsigned digit = 0;
+    if (m < d.n_meas && d.m_state[m] == M_ALIVE) {
+      const unsigned long long key = (unsigned long long)__double_as_longlong(d.m_e2[m]);
+      take = pass == 0 || (key >> (shift + width)) == (prefix >> (shift + width));
+      digit = (unsigned)(key >> shift) & ((1u << width) - 1u);
+    }
+    const unsigned active = __ballot_sync(kFull, take);
+    if (take) {
+      const unsigned same = __match_any_sync(active, digit);
+      if (lane == __ffs(same) - 1) atomicAdd(&h[digit], __popc(same));
+    }
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kSelBins; i += blockDim.x)
+    if (h[i]) atomicAdd(&d.hist16[i], h[i]);
 }
 
-__global__ void __launch_bounds__(1024) k_ba_pick16(BundleDev d, int pass, double min_sigma_sq) {
+__global__ void __launch_bounds__(1024) k_ba_pick(BundleDev d, int pass, double min_sigma_sq) {
   __shared__ int wsum[32];
   __shared__ int total_s;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int shift = 48 - 16 * pass;
-  int tot = 0;
-  {
-    const int4* h4 = reinterpret_cast<const int4*>(d.hist16 + 64 * t);
-#pragma unroll 4
-    for (int q = 0; q < 16; q++) { const int4 v = h4[q]; tot += v.x + v.y + v.z + v.w; }
-  }
+  const int shift = sel_shift(pass);
+  const int c0 = d.hist16[2 * t], c1 = d.hist16[2 * t + 1];
+  const int tot = c0 + c1;
   int inc = tot;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -211,15 +230,15 @@ __global__ void __launch_bounds__(1024) k_ba_pick16(BundleDev d, int pass, doubl
   }
   __syncthreads();
   const int n_all = total_s;  // pass 0: number of valid measurements over all shards
-  long long kk = pass == 0 ? (long long)(n_all / 2) : (long long)d.sel_state[1];
+  const long long kk = pass == 0 ? (long long)(n_all / 2) : (long long)d.sel_state[1];
   const int excl = (warp ? wsum[warp - 1] : 0) + inc - tot;
   if (n_all > 0 && kk >= excl && kk < excl + tot) {  // exactly one thread
     int r = (int)(kk - excl), q = 0;
-    while (q < 63 && r >= d.hist16[64 * t + q]) { r -= d.hist16[64 * t + q]; q++; }
-    const unsigned long long prefix = (pass == 0 ? 0ull : d.sel_state[0]) | ((unsigned long long)(64 * t + q) << shift);
+    if (r >= c0) { r -= c0; q = 1; }
+    const unsigned long long prefix = (pass == 0 ? 0ull : d.sel_state[0]) | ((unsigned long long)(2 * t + q) << shift);
     d.sel_state[0] = prefix;
     d.sel_state[1] = (unsigned long long)r;
-    if (pass == 3) {
+    if (pass == kSelPasses - 1) {
       const double med = __longlong_as_double((long long)prefix);
       const long long n = (long long)d.scal[0];
       double s2 = mest_sigma_from_median(med, n, d.est);
@@ -864,6 +883,74 @@ __global__ void __launch_bounds__(1024) k_ba_erase(BundleDev d, int step) {
     __syncthreads();
   }
   if (threadIdx.x == 0) d.counters[1] = base_s;
+}
+
+// Large graphs: the same ordered erase with many CTAs.  k_ba_erase_count: bad measurements per
+// 1024-measurement block; k_ba_erase_scan: exclusive scan of the block counts (one CTA) on top of the
+// running total; k_ba_erase_write: ordered positions inside each block by ballot / popc.
+__global__ void __launch_bounds__(1024) k_ba_erase_count(BundleDev d, int* block_cnt) {
+  __shared__ int wcnt[32];
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool bad = m < d.n_meas && d.m_state[m] == M_BAD;
+  const unsigned b = __ballot_sync(kFull, bad);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) wcnt[warp] = __popc(b);
+  __syncthreads();
+  if (warp == 0) {
+    const int v = warp_sum_int(wcnt[lane]);
+    if (lane == 0) block_cnt[blockIdx.x] = v;
+  }
+}
+__global__ void __launch_bounds__(1024) k_ba_erase_scan(BundleDev d, int* block_cnt, int n_blocks) {
+  __shared__ int wsum[32];
+  __shared__ int carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = d.counters[1];
+  __syncthreads();
+  for (int base = 0; base < n_blocks; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int v = i < n_blocks ? block_cnt[i] : 0;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(kFull, inc, o);
+      if (lane >= o) inc += n;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      int ws = wsum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(kFull, ws, o);
+        if (lane >= o) ws += n;
+      }
+      wsum[lane] = ws;
+    }
+    __syncthreads();
+    if (i < n_blocks) block_cnt[i] = carry + (warp ? wsum[warp - 1] : 0) + inc - v;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += wsum[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) d.counters[1] = carry;
+}
+__global__ void __launch_bounds__(1024) k_ba_erase_write(BundleDev d, const int* block_cnt, int step) {
+  __shared__ int wcnt[32];
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool bad = m < d.n_meas && d.m_state[m] == M_BAD;
+  const unsigned b = __ballot_sync(kFull, bad);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) wcnt[warp] = __popc(b);
+  __syncthreads();
+  if (bad) {
+    int before = block_cnt[blockIdx.x];
+    for (int w = 0; w < warp; w++) before += wcnt[w];
+    const int o = before + __popc(b & ((1u << lane) - 1));
+    d.outliers[2 * o] = d.m_pt[m]; d.outliers[2 * o + 1] = d.m_cam[m];
+    d.m_state[m] = M_ERASED;
+    d.m_erase_step[m] = step;
+  }
 }
 
 // sharded handles: local erase marks -> global measurement order (merged with an all-reduce max)

@@ -4,9 +4,9 @@
     measurement-balanced point ranges, same answer on every rank;
   * the exchange step: the reduced camera system is additive over point shards, so the all-reduced
     sum of per-shard partial (S, vE) equals the oracle's full system;
-  * the distributed order statistic: a 4-pass 16-bit MSB radix select whose digit histograms are
+  * the distributed order statistic: a multi-pass MSB radix select whose digit histograms are
     all-reduced finds the exact floor(n/2)-th smallest of the union of the shards' errors (the
-    protocol k_ba_hist16 / k_ba_pick16 run on the device).
+    protocol k_ba_hist / k_ba_pick run on the device).
 The 2-GPU NCCL run of the same path is tests/test_bundle_sharded_gpu.py.
 """
 import os
@@ -40,10 +40,11 @@ def _radix_select_allreduce(local_vals, k_of_n):
     """exact k-th smallest of the union of all ranks' non-negative doubles; k_of_n(n) -> k."""
     keys = np.ascontiguousarray(local_vals, np.float64).view(np.uint64)
     prefix, k = np.uint64(0), None
-    for p in range(4):
-        shift = np.uint64(48 - 16 * p)
-        sel = keys if p == 0 else keys[(keys >> (shift + np.uint64(16))) == (prefix >> (shift + np.uint64(16)))]
-        hist = np.bincount(((sel >> shift) & np.uint64(0xffff)).astype(np.int64), minlength=65536)
+    for p in range(6):  # digit widths 11,11,11,11,11,9 as in k_ba_hist / k_ba_pick
+        shift = np.uint64(53 - 11 * p if p < 5 else 0)
+        width = np.uint64(11 if p < 5 else 9)
+        sel = keys if p == 0 else keys[(keys >> (shift + width)) == (prefix >> (shift + width))]
+        hist = np.bincount(((sel >> shift) & ((np.uint64(1) << width) - np.uint64(1))).astype(np.int64), minlength=2048)
         t = torch.from_numpy(hist.astype(np.int64))
         dist.all_reduce(t)
         hist = t.numpy()
