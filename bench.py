@@ -35,6 +35,14 @@ W, H = 640, 480
 FRAME_BYTES = W * H
 
 
+def workload_name():
+    if (W, H) == (640, 480):
+        return "C2: 640x480 4-level pyramid, ~1000-point map, full TrackFrame"
+    if (W, H) == (1280, 720):
+        return "C5: 1280x720 4-level pyramid, ~1000-point map, full TrackFrame, independent streams per GPU"
+    return f"{W}x{H} 4-level pyramid, ~1000-point map, full TrackFrame"
+
+
 def pingpong(i, n):
     p = i % (2 * n - 2)
     return p if p < n else 2 * n - 2 - p
@@ -193,7 +201,7 @@ def reference_arm(args, rank, world):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32/f64",
         "data": "synthetic",
-        "config": {"workload": "C2: 640x480 4-level pyramid, ~1000-point map, full TrackFrame", "map_points": int(len(m["src_kf"]))},
+        "config": {"workload": workload_name(), "map_points": int(len(m["src_kf"]))},
         "cpu_baseline": {"value": val, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
@@ -208,10 +216,14 @@ def main():
     ap.add_argument("--streams", type=int, default=296, help="independent tracker streams per GPU (batch)")
     ap.add_argument("--frames", type=int, default=64, help="distinct synthetic frames per trajectory")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--res", default="640x480", help="frame size; 1280x720 = BASELINE config C5 (one independent stream set per GPU)")
     ap.add_argument("--no-ba", action="store_true")
     ap.add_argument("--no-ba-large", action="store_true", help="skip the C4 bundle adjustment (500 x 100k x 600k)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    global W, H, FRAME_BYTES
+    W, H = (int(v) for v in args.res.lower().split("x"))
+    FRAME_BYTES = W * H
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -372,7 +384,7 @@ def main():
           "frac": per_kernel[top].get("frac_hbm"), "traffic": traffic, "peak_source": peak_src,
           "share_of_step": per_kernel[top]["avg_ms"] / step_kernel_ms}
     a1_ms = sum(per_kernel[k]["avg_ms"] for k in ("k_pyramid", "k_fast", "k_compact") if k in per_kernel)
-    a1_bytes = S * (411600 + 8 * n_corners)
+    a1_bytes = S * (pyr_px + 4 * sum(H >> l for l in range(4)) + 8 * n_corners)  # 411 600 + 8 N_c at 640x480
     rl_a1 = {"kernels": "k_pyramid+k_fast+k_compact (SURVEY a1: pyramid+FAST+LUT)", "alg_bytes": a1_bytes,
              "achieved": a1_bytes / (a1_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
              "frac": a1_bytes / (a1_ms * 1e-3) / 1e9 / peak}
@@ -395,7 +407,7 @@ def main():
         "metric": "tracker frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K,
         "warmup": Wm, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/int32/f64", "data": "synthetic",
-        "config": {"workload": "C2: 640x480 4-level pyramid, ~1000-point map, full TrackFrame",
+        "config": {"workload": workload_name(),
                    "streams_per_gpu": S, "map_points": int(len(m["src_kf"])), "frames_per_step": world * S,
                    "l2": f"inputs > L2: every step reads a distinct {S}x{FRAME_BYTES} B batch out of a "
                          f"{n_steps * S * FRAME_BYTES / 1e6:.0f} MB resident set",

@@ -77,7 +77,8 @@ struct Buf {
 
 struct ptam_bundle {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;
+  std::vector<cudaEvent_t> ev_panel, ev_tail;
   std::string err;
   int64_t launches = 0;
   ptam_bundle_params prm{};
@@ -137,6 +138,9 @@ struct ptam_bundle {
     if (comm && own_comm) nccl_api().CommDestroy(comm);
     if (h_scal) cudaFreeHost(h_scal);
     if (h_cnt) cudaFreeHost(h_cnt);
+    for (auto e : ev_panel) cudaEventDestroy(e);
+    for (auto e : ev_tail) cudaEventDestroy(e);
+    if (stream2) cudaStreamDestroy(stream2);
     if (stream) cudaStreamDestroy(stream);
   }
 
@@ -157,6 +161,7 @@ struct ptam_bundle {
     if (dev < 0 || dev >= ndev) { set_error("bad device index"); return PTAM_ERR_INVALID; }
     PTAM_CUDA_TRY(this, cudaSetDevice(dev));
     PTAM_CUDA_TRY(this, cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    PTAM_CUDA_TRY(this, cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
     PTAM_CUDA_TRY(this, cudaMallocHost(&h_scal, 8 * sizeof(double)));
     PTAM_CUDA_TRY(this, cudaMallocHost(&h_cnt, 4 * sizeof(int)));
     if (p) prm = *p; else ptam_bundle_default_params(&prm);
@@ -222,7 +227,7 @@ struct ptam_bundle {
       AL(m_cam, M); AL(m_pt, M); AL(m_found, 2 * (size_t)M); AL(m_sin, M); AL(m_state, M); AL(m_v3cam, 3 * (size_t)M);
       AL(m_derivs, 4 * (size_t)M); AL(m_eps, 2 * (size_t)M); AL(m_e2, M); AL(m_W, 18 * (size_t)M); AL(e2c, M);
       AL(S, (size_t)n * n); AL(vE, n); AL(upd, n); AL(scal, 8); AL(counters, 4); AL(outliers, 2 * (size_t)M);
-      AL(Wp, (size_t)n * kNB);
+      AL(Wp, 2 * (size_t)n * kNB);
       AL(m_gid, M); AL(m_erase_step, M); AL(hist16, kSelBins); AL(erase_cnt, (M + 1023) / 1024 + 1); AL(sel_state, 2);
       AL(g_steps, world > 1 ? MG : 0);
 #undef AL
@@ -260,21 +265,47 @@ struct ptam_bundle {
     return PTAM_OK;
   }
 
+  // Blocked LDL^T with one-panel look-ahead on two streams.  For panel k: the trailing update is split
+  // into its head U1(k) (the next panel's 64 columns) and its tail U2(k).  Main stream: panel(k),
+  // U1(k), panel(k+1), ...; second stream: U2(k) after panel(k).  U1(k) waits for U2(k-1) (same tiles,
+  // read-modify-write), so panel(k+1) overlaps U2(k).  Wp is double-buffered by panel parity.
   int solve_reduced() {
     const int n = d.n;
     if (n == 0) return PTAM_OK;
+    const int n_panels = (n + kNB - 1) / kNB;
+    if ((int)ev_panel.size() < n_panels) {
+      const size_t old = ev_panel.size();
+      ev_panel.resize(n_panels); ev_tail.resize(n_panels);
+      for (size_t k = old; k < ev_panel.size(); k++) {
+        PTAM_CUDA_TRY(this, cudaEventCreateWithFlags(&ev_panel[k], cudaEventDisableTiming));
+        PTAM_CUDA_TRY(this, cudaEventCreateWithFlags(&ev_tail[k], cudaEventDisableTiming));
+      }
+    }
     // vE is consumed in place as the right-hand side (forward substitution rides with the panels)
-    for (int k0 = 0; k0 < n; k0 += kNB) {
+    int last_tail = -1;
+    for (int k = 0, k0 = 0; k0 < n; k++, k0 += kNB) {
       const int nb = std::min(kNB, n - k0);
       const int rem = n - k0 - nb;
-      k_ldlt_panel<<<std::max(1, (rem + kPanelRows - 1) / kPanelRows), kPanelThreads, 0, stream>>>(d.S, Wp.p, d.vE, n, k0);
+      double* wp = Wp.p + (size_t)(k & 1) * n * kNB;
+      k_ldlt_panel<<<std::max(1, (rem + kPanelRows - 1) / kPanelRows), kPanelThreads, 0, stream>>>(d.S, wp, d.vE, n, k0);
       launches++;
       if (rem > 0) {
         const int nt = (rem + kUTM - 1) / kUTM;
-        k_ldlt_update<<<nt * (nt + 1), 256, kUpdateSmem, stream>>>(d.S, Wp.p, n, k0);
+        const int n_tail = nt * (nt + 1) - nt;
+        if (n_tail > 0) {
+          PTAM_CUDA_TRY(this, cudaEventRecord(ev_panel[k], stream));
+          PTAM_CUDA_TRY(this, cudaStreamWaitEvent(stream2, ev_panel[k], 0));
+          k_ldlt_update<<<n_tail, 256, kUpdateSmem, stream2>>>(d.S, wp, n, k0, 2);
+          PTAM_CUDA_TRY(this, cudaEventRecord(ev_tail[k], stream2));
+          launches++;
+        }
+        if (last_tail >= 0) PTAM_CUDA_TRY(this, cudaStreamWaitEvent(stream, ev_tail[last_tail], 0));
+        k_ldlt_update<<<nt, 256, kUpdateSmem, stream>>>(d.S, wp, n, k0, 1);
         launches++;
+        last_tail = n_tail > 0 ? k : -1;
       }
     }
+    if (last_tail >= 0) PTAM_CUDA_TRY(this, cudaStreamWaitEvent(stream, ev_tail[last_tail], 0));
     k_ldlt_scale<<<(n + 255) / 256, 256, 0, stream>>>(d.S, d.vE, d.vE, n);
     launches++;
     for (int k0 = ((n - 1) / kNB) * kNB; k0 >= 0; k0 -= kNB) {

@@ -636,17 +636,29 @@ __global__ void __launch_bounds__(kPanelThreads) k_ldlt_panel(double* A, double*
 
 PTAM_DEV unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(256, 2) k_ldlt_update(double* A, const double* Wp, int n, int k0) {
+// part 0: all tiles; part 1: only the first column block (the next panel's 64 columns: look-ahead
+// head); part 2: everything else (look-ahead tail, runs on the second stream).
+__global__ void __launch_bounds__(256, 2) k_ldlt_update(double* A, const double* Wp, int n, int k0, int part) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sW = reinterpret_cast<double*>(smem_raw);            // [kUTM][kLds]  -(L21 D1) rows of the i-tile
   double* sL = sW + kUTM * kLds;                                // [kUTN][kLds]  L21 rows of the j-tile
   unsigned long long* mbar = reinterpret_cast<unsigned long long*>(sL + kUTN * kLds);
   const int r0 = k0 + kNB;
-  // linear tile index -> (bi, bj): row block bi (128 rows) has column blocks bj = 0 .. 2 bi + 1 (64 columns)
-  int bi = (int)((sqrt(4.0 * blockIdx.x + 1.0) - 1.0) * 0.5);
-  while (bi * (bi + 1) > (int)blockIdx.x) bi--;
-  while ((bi + 1) * (bi + 2) <= (int)blockIdx.x) bi++;
-  const int bj = blockIdx.x - bi * (bi + 1);
+  int bi, bj;
+  if (part == 1) { bi = blockIdx.x; bj = 0; }
+  else if (part == 2) {
+    // row block bi has column blocks bj = 1 .. 2 bi + 1: 2 bi + 1 tiles, bi^2 before it
+    bi = (int)sqrt((double)blockIdx.x);
+    while (bi * bi > (int)blockIdx.x) bi--;
+    while ((bi + 1) * (bi + 1) <= (int)blockIdx.x) bi++;
+    bj = blockIdx.x - bi * bi + 1;
+  } else {
+    // row block bi (128 rows) has column blocks bj = 0 .. 2 bi + 1 (64 columns): bi (bi + 1) tiles before it
+    bi = (int)((sqrt(4.0 * blockIdx.x + 1.0) - 1.0) * 0.5);
+    while (bi * (bi + 1) > (int)blockIdx.x) bi--;
+    while ((bi + 1) * (bi + 2) <= (int)blockIdx.x) bi++;
+    bj = blockIdx.x - bi * (bi + 1);
+  }
   const int i0 = r0 + bi * kUTM, j0 = r0 + bj * kUTN;
   if (j0 >= n) return;  // the last row block may be short of its second diagonal column block
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

@@ -215,3 +215,30 @@ def test_pipelined_submit_collect_matches_blocking(product, seq640, map640):
         for r, o in zip(r_step, o_step):
             assert list(r.se3_cam_from_world) == list(o.se3_cam_from_world)
             assert list(r.meas_found) == list(o.meas_found) and list(r.n_corners) == list(o.n_corners)
+
+
+@pytest.mark.gpu
+def test_track_frames_1280x720(oracle, product):
+    """BASELINE config C5 geometry: full TrackFrame parity at 1280x720 (map built at that size)."""
+    from oracle.binding import detect_with
+    Wd, Hd = 1280, 720
+    frames, poses = synth.render_sequence(Wd, Hd, 6)
+    cam = synth.AtanCamera(Wd, Hd)
+    kfs, m = synth.build_map(frames, poses, detect_with(Tracker, oracle, Wd, Hd), cam, kf_indices=(0, 3), per_level=(300, 150, 60, 30))
+    trk = []
+    for lib in (oracle, product):
+        t = Tracker(lib, Wd, Hd, 1)
+        for k in kfs:
+            t.add_keyframe(k)
+        t.set_map(0, m)
+        t.set_state(0, pose12=synth.perturb_pose(poses[1], np.random.default_rng(1)), velocity=np.zeros(6), msd=0.0)
+        trk.append(t)
+    o, p = trk
+    for f in (1, 2, 4):
+        ro, rp = o.track_frames([frames[f]])[0], p.track_frames([frames[f]])[0]
+        _compare_levels(o, p)
+        po, pp = o.get_points(0), p.get_points(0)
+        assert np.array_equal(po["flags"], pp["flags"]) and np.array_equal(po["level"], pp["level"])
+        assert list(ro.meas_found) == list(rp.meas_found) and sum(rp.meas_found) > 100
+        assert np.allclose(np.array(ro.se3_cam_from_world), np.array(rp.se3_cam_from_world), atol=1e-9)
+        p.set_state(0, state=o.get_state(0))  # continue from identical state
