@@ -375,9 +375,11 @@ def main():
     top = max(per_kernel, key=lambda k: per_kernel[k]["avg_ms"])
     traffic = None
     tj = ROOT / "profiles" / "traffic.json"
-    if tj.exists():
+    if tj.exists():  # DRAM bytes per launch from the committed ncu --set full capture, scaled to this batch size
         try:
-            traffic = json.loads(tj.read_text()).get(top)
+            t = json.loads(tj.read_text())
+            if top in t.get("kernels", {}):
+                traffic = t["kernels"][top] * S / float(t["streams"])
         except Exception:
             traffic = None
     rl = {"kernel": top, "bound": "hbm", "achieved": per_kernel[top].get("gbs"), "peak": peak, "unit": "GB/s",
