@@ -178,6 +178,7 @@ struct ptam_tracker {
     dev.pt_count = pt_count.p;
     dev.kf_ptrs = nullptr; dev.n_kf = 0;
     PTAM_CUDA_TRY(this, ensure_points(1024));
+    PTAM_CUDA_TRY(this, cudaFuncSetAttribute(k_pose, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoseSmemBytes));
     if ((size_t)(max_h + 1) * sizeof(int) > 48 * 1024)
       PTAM_CUDA_TRY(this, cudaFuncSetAttribute(k_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (max_h + 1) * (int)sizeof(int)));
     return PTAM_OK;
@@ -313,14 +314,14 @@ struct ptam_tracker {
       k_search<<<dim3((coarse_items + 3) / 4, S), 128, 0, stream>>>(d, 0);
       pend(4); launches++; used |= 16u;
     }
-    pbegin(5); k_pose<<<S, kPoseThreads, 0, stream>>>(d, 0); pend(5);
+    pbegin(5); k_pose<<<S, kPoseThreads, kPoseSmemBytes, stream>>>(d, 0); pend(5);
     if (maxn > 0) {
       pbegin(6);
       k_search_prep<<<dim3((maxn + 127) / 128, S), 128, 0, stream>>>(d, 1);
       k_search<<<dim3((maxn + 3) / 4, S), 128, 0, stream>>>(d, 1);
       pend(6); launches++; used |= 64u;
     }
-    pbegin(7); k_pose<<<S, kPoseThreads, 0, stream>>>(d, 1); pend(7);
+    pbegin(7); k_pose<<<S, kPoseThreads, kPoseSmemBytes, stream>>>(d, 1); pend(7);
     PTAM_CUDA_TRY(this, cudaGetLastError());
     return pcollect(used);
   }

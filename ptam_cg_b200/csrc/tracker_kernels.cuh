@@ -957,19 +957,180 @@ PTAM_DEV void warp_transpose_sum32(double (&v)[32]) {
   }
 }
 
-constexpr int kPoseSmemPts = 2048;  // found sets up to this size take the shared-memory median path
+// Per-point working set of the Gauss-Newton loop.  Found sets of up to kPoseSmemPts points (the
+// tracker's MaxPatchesPerFrame default is 1000) keep it in shared memory for all ten iterations
+// (96 B per point, SoA by found index): v2Found, sqrt-inverse-noise, v2Image, v3Cam, the 2x2 camera
+// derivatives.  The 2x6 Jacobian is not stored: CalcJacobian (Tracker.h:125-136) is re-evaluated from
+// v3Cam / derivatives, which only change on the non-linear iterations, so LinearUpdate sees exactly
+// the Jacobian of the last non-linear iteration as in the reference.  Larger sets fall back to the
+// same code over the global arrays.
+constexpr int kPoseSmemPts = 1024;
+constexpr int kPoseSmemBytes = 12 * kPoseSmemPts * (int)sizeof(double);
+
+struct PoseStoreSmem {
+  double* base;  // [12][kPoseSmemPts]
+  PTAM_DEV double& found(int i, int k) const { return base[(0 + k) * kPoseSmemPts + i]; }
+  PTAM_DEV double& sn(int i) const { return base[2 * kPoseSmemPts + i]; }
+  PTAM_DEV double& image(int i, int k) const { return base[(3 + k) * kPoseSmemPts + i]; }
+  PTAM_DEV double& v3(int i, int k) const { return base[(5 + k) * kPoseSmemPts + i]; }
+  PTAM_DEV double& dv(int i, int k) const { return base[(8 + k) * kPoseSmemPts + i]; }
+};
+struct PoseStoreGlobal {
+  const PointArrays* p; size_t gb; const int* fidx;
+  PTAM_DEV double& found(int i, int k) const { return p->v2found[2 * (gb + fidx[i]) + k]; }
+  PTAM_DEV double& sn(int i) const { return p->sqrt_inv_noise[gb + fidx[i]]; }
+  PTAM_DEV double& image(int i, int k) const { return p->v2image[2 * (gb + fidx[i]) + k]; }
+  PTAM_DEV double& v3(int i, int k) const { return p->v3cam[3 * (gb + fidx[i]) + k]; }
+  PTAM_DEV double& dv(int i, int k) const { return p->derivs[4 * (gb + fidx[i]) + k]; }
+};
+
+// TrackerData::CalcJacobian (Tracker.h:125-136): rows of the 2x6 Jacobian w.r.t. the SE3 generators
+PTAM_DEV void calc_jacobian(double X, double Y, double Z, double dv0, double dv1, double dv2, double dv3, double* J0, double* J1) {
+  const double ooz = 1.0 / Z;
+  const double gx[6] = {1, 0, 0, 0, Z, -Y}, gy[6] = {0, 1, 0, -Z, 0, X}, gz[6] = {0, 0, 1, Y, -X, 0};
+#pragma unroll
+  for (int m = 0; m < 6; m++) {
+    const double a0 = (gx[m] - X * gz[m] * ooz) * ooz;
+    const double a1 = (gy[m] - Y * gz[m] * ooz) * ooz;
+    J0[m] = dv0 * a0 + dv1 * a1;
+    J1[m] = dv2 * a0 + dv3 * a1;
+  }
+}
+
+struct PoseShared {
+  double s_e2[kPoseSmemPts];
+  double pose[12];
+  double red[kPoseThreads / 32][27];
+  double mu_s[6];
+  int hist[512];
+  unsigned long long sh_prefix;
+  int sh_k;
+};
+
+// The ten iterations of Tracker.cc:552-568 (stage 0) / 614-643 (stage 1) over the found set.
+template <class Store>
+PTAM_DEV void pose_iterations(const TrackerDev& d, const Store& st, PoseShared& sh, int stage, int nf, size_t gb,
+                              const int* fidx, double* e2_global) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int est = d.prm.mestimator;
+  double* pose = sh.pose;
+  double last_mu[6] = {0, 0, 0, 0, 0, 0};
+  const bool e2_smem = nf <= kPoseSmemPts;
+  for (int it = 0; it < 10; it++) {
+    const bool nonlin = stage == 0 || it == 0 || it == 4 || it == 9;
+    const double override_sigma = it > 5 ? (stage == 0 ? 1.0 : 16.0) : 0.0;
+    const bool mark = stage == 1 && it == 9;
+    // per-point update: reprojection / linear update, scaled error
+    for (int i = threadIdx.x; i < nf; i += blockDim.x) {
+      double v2i[2] = {st.image(i, 0), st.image(i, 1)};
+      if (it != 0) {
+        if (nonlin) {  // ProjectAndDerivs (Tracker.h:89-94)
+          ProjOut o;
+          project_point(d, pose, d.p.world + 3 * (gb + fidx[i]), o);
+          st.v3(i, 0) = o.v3cam[0]; st.v3(i, 1) = o.v3cam[1]; st.v3(i, 2) = o.v3cam[2];
+          if (o.reached_cam) {
+            v2i[0] = o.v2image[0]; v2i[1] = o.v2image[1];
+            double dv[4];
+            cam_derivs(d.cam, o.q, dv);
+            for (int q = 0; q < 4; q++) st.dv(i, q) = dv[q];
+          }
+        } else {  // LinearUpdate (Tracker.h:139-142) with the Jacobian of the last non-linear iteration
+          double J0[6], J1[6];
+          calc_jacobian(st.v3(i, 0), st.v3(i, 1), st.v3(i, 2), st.dv(i, 0), st.dv(i, 1), st.dv(i, 2), st.dv(i, 3), J0, J1);
+          double a0 = 0, a1 = 0;
+          for (int q = 0; q < 6; q++) { a0 += J0[q] * last_mu[q]; a1 += J1[q] * last_mu[q]; }
+          v2i[0] += a0; v2i[1] += a1;
+        }
+        st.image(i, 0) = v2i[0]; st.image(i, 1) = v2i[1];
+      }
+      const double sn = st.sn(i);
+      const double e0 = sn * (st.found(i, 0) - v2i[0]), e1 = sn * (st.found(i, 1) - v2i[1]);
+      const double ee = e0 * e0 + e1 * e1;
+      if (e2_smem) sh.s_e2[i] = ee; else e2_global[fidx[i]] = ee;
+    }
+    __syncthreads();
+    double mu[6] = {0, 0, 0, 0, 0, 0};
+    if (nf > 0) {
+      double sigma2;
+      if (override_sigma > 0) sigma2 = override_sigma;
+      else {
+        double med;
+        if (e2_smem) med = block_select_kth([&](int i) { return sh.s_e2[i]; }, nf, nf / 2, sh.hist, &sh.sh_prefix, &sh.sh_k);
+        else med = block_select_kth([&](int i) { return e2_global[fidx[i]]; }, nf, nf / 2, sh.hist, &sh.sh_prefix, &sh.sh_k);
+        sigma2 = mest_sigma_from_median(med, nf, est);
+      }
+      // weighted normal equations (TooN WLS<6>::add_mJ twice per point)
+      double acc[32];
+#pragma unroll
+      for (int q = 0; q < 32; q++) acc[q] = 0;
+      for (int i = threadIdx.x; i < nf; i += blockDim.x) {
+        const double sn = st.sn(i);
+        const double e0 = sn * (st.found(i, 0) - st.image(i, 0)), e1 = sn * (st.found(i, 1) - st.image(i, 1));
+        const double es = e0 * e0 + e1 * e1;
+        const double wgt = mest_weight(es, sigma2, est);
+        if (wgt == 0.0) { if (mark) d.p.outliers[gb + fidx[i]]++; continue; }
+        if (mark) d.p.inliers[gb + fidx[i]]++;
+        double J0[6], J1[6];
+        calc_jacobian(st.v3(i, 0), st.v3(i, 1), st.v3(i, 2), st.dv(i, 0), st.dv(i, 1), st.dv(i, 2), st.dv(i, 3), J0, J1);
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+          double Jr[6], Jw[6];
+#pragma unroll
+          for (int q = 0; q < 6; q++) { Jr[q] = sn * (r ? J1[q] : J0[q]); Jw[q] = Jr[q] * wgt; }
+          const double er = r ? e1 : e0;
+          int c = 0;
+#pragma unroll
+          for (int a = 0; a < 6; a++) {
+#pragma unroll
+            for (int b = 0; b <= a; b++) acc[c++] += Jw[a] * Jr[b];
+          }
+#pragma unroll
+          for (int a = 0; a < 6; a++) acc[21 + a] += er * Jw[a];
+        }
+      }
+      warp_transpose_sum32(acc);
+      if (lane < 27) sh.red[warp][lane] = acc[0];
+      __syncthreads();
+      if (threadIdx.x < 27) {
+        double t = 0;
+        for (int wq = 0; wq < kPoseThreads / 32; wq++) t += sh.red[wq][threadIdx.x];
+        sh.red[0][threadIdx.x] = t;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double tot[27];
+        for (int q = 0; q < 27; q++) tot[q] = sh.red[0][q];
+        double C[36], b[6], x[6];
+        int c = 0;
+        for (int a = 0; a < 6; a++)
+          for (int bb = 0; bb <= a; bb++) { C[6 * a + bb] = tot[c]; C[6 * bb + a] = tot[c]; c++; }
+        for (int a = 0; a < 6; a++) { C[7 * a] += 100.0; b[a] = tot[21 + a]; }  // add_prior(100)
+        ldlt_factor<6>(C);
+        ldlt_backsub<6>(C, b, x);
+        for (int a = 0; a < 6; a++) sh.mu_s[a] = x[a];
+      }
+      __syncthreads();
+      for (int a = 0; a < 6; a++) mu[a] = sh.mu_s[a];
+    }
+    // mse3CamFromWorld = SE3<>::exp(v6Update) * mse3CamFromWorld
+    if (threadIdx.x == 0) {
+      double ex[12], np[12];
+      se3_exp(mu, ex);
+      se3_mul(ex, pose, np);
+      for (int i = 0; i < 12; i++) pose[i] = np[i];
+    }
+    for (int a = 0; a < 6; a++) last_mu[a] = mu[a];
+    __syncthreads();
+  }
+}
 
 __global__ void __launch_bounds__(kPoseThreads, 2) k_pose(TrackerDev d, int stage) {
-  __shared__ double s_e2[kPoseSmemPts];
-  __shared__ double pose[12];
-  __shared__ double red[kPoseThreads / 32][27];
-  __shared__ double mu_s[6];
-  __shared__ int hist[512];
-  __shared__ unsigned long long sh_prefix;
-  __shared__ int sh_k;
+  extern __shared__ __align__(16) unsigned char pose_dyn[];  // kPoseSmemBytes: the per-point working set
+  __shared__ PoseShared sh;
+  __shared__ double red2[kPoseThreads / 32][2];
   __shared__ int sh_cnt[kPoseThreads / 32];
   __shared__ int nfound_s;
-  __shared__ double sigma_s;
+  double* pose = sh.pose;
   const int s = blockIdx.x;
   StreamCtl& ctl = d.ctl[s];
   const int cap = d.p.cap;
@@ -979,7 +1140,6 @@ __global__ void __launch_bounds__(kPoseThreads, 2) k_pose(TrackerDev d, int stag
   int* fidx = d.p.pvs + (size_t)s * kLevels * cap;  // PVS lists are dead after selection: reuse as found-index scratch
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n_set = stage == 0 ? ctl.n_coarse : ctl.n_coarse + ctl.n_l3 + ctl.n_fine;
-  const int est = d.prm.mestimator;
 
   // compact the found entries (order preserved) once: the found set does not change during GN
   if (threadIdx.x == 0) nfound_s = 0;
@@ -1005,127 +1165,26 @@ __global__ void __launch_bounds__(kPoseThreads, 2) k_pose(TrackerDev d, int stag
     run = ctl.try_coarse && nf >= d.prm.coarse_min;
     if (threadIdx.x == 0) ctl.did_coarse = run ? 1 : 0;
   }
+  const bool in_smem = nf <= kPoseSmemPts;
+  const PoseStoreSmem ss{reinterpret_cast<double*>(pose_dyn)};
+  const PoseStoreGlobal sg{&d.p, gb, fidx};
   if (run) {
-    double last_mu[6] = {0, 0, 0, 0, 0, 0};
-    for (int it = 0; it < 10; it++) {
-      const bool nonlin = stage == 0 || it == 0 || it == 4 || it == 9;
-      const double override_sigma = it > 5 ? (stage == 0 ? 1.0 : 16.0) : 0.0;
-      const bool mark = stage == 1 && it == 9;
-      // per-point update: reprojection / linear update, Jacobian, scaled error
-      for (int i = threadIdx.x; i < nf; i += blockDim.x) {
-        const size_t g = gb + fidx[i];
-        double v2i[2] = {d.p.v2image[2 * g], d.p.v2image[2 * g + 1]};
-        if (it != 0) {
-          if (nonlin) {  // ProjectAndDerivs (Tracker.h:89-94)
-            ProjOut o;
-            project_point(d, pose, d.p.world + 3 * g, o);
-            d.p.v3cam[3 * g] = o.v3cam[0]; d.p.v3cam[3 * g + 1] = o.v3cam[1]; d.p.v3cam[3 * g + 2] = o.v3cam[2];
-            if (o.reached_cam) {
-              v2i[0] = o.v2image[0]; v2i[1] = o.v2image[1];
-              double dv[4];
-              cam_derivs(d.cam, o.q, dv);
-              for (int q = 0; q < 4; q++) d.p.derivs[4 * g + q] = dv[q];
-            }
-          } else {  // LinearUpdate (Tracker.h:139-142)
-            for (int r = 0; r < 2; r++) {
-              double a = 0;
-              for (int q = 0; q < 6; q++) a += d.p.J[12 * g + 6 * r + q] * last_mu[q];
-              v2i[r] += a;
-            }
-          }
-          d.p.v2image[2 * g] = v2i[0]; d.p.v2image[2 * g + 1] = v2i[1];
-        }
-        if (nonlin) {  // CalcJacobian (Tracker.h:125-136)
-          const double X = d.p.v3cam[3 * g], Y = d.p.v3cam[3 * g + 1], Z = d.p.v3cam[3 * g + 2];
-          const double ooz = 1.0 / Z;
-          const double dv0 = d.p.derivs[4 * g], dv1 = d.p.derivs[4 * g + 1], dv2 = d.p.derivs[4 * g + 2], dv3 = d.p.derivs[4 * g + 3];
-          const double gx[6] = {1, 0, 0, 0, Z, -Y}, gy[6] = {0, 1, 0, -Z, 0, X}, gz[6] = {0, 0, 1, Y, -X, 0};
-#pragma unroll
-          for (int m = 0; m < 6; m++) {
-            const double a0 = (gx[m] - X * gz[m] * ooz) * ooz;
-            const double a1 = (gy[m] - Y * gz[m] * ooz) * ooz;
-            d.p.J[12 * g + m] = dv0 * a0 + dv1 * a1;
-            d.p.J[12 * g + 6 + m] = dv2 * a0 + dv3 * a1;
-          }
-        }
-        const double sn = d.p.sqrt_inv_noise[g];
-        const double e0 = sn * (d.p.v2found[2 * g] - v2i[0]), e1 = sn * (d.p.v2found[2 * g + 1] - v2i[1]);
-        const double ee = e0 * e0 + e1 * e1;
-        if (nf <= kPoseSmemPts) s_e2[i] = ee; else e2[fidx[i]] = ee;
+    if (in_smem) {
+      for (int i = threadIdx.x; i < nf; i += blockDim.x) {  // gather the working set once
+        ss.found(i, 0) = sg.found(i, 0); ss.found(i, 1) = sg.found(i, 1); ss.sn(i) = sg.sn(i);
+        ss.image(i, 0) = sg.image(i, 0); ss.image(i, 1) = sg.image(i, 1);
+        for (int q = 0; q < 3; q++) ss.v3(i, q) = sg.v3(i, q);
+        for (int q = 0; q < 4; q++) ss.dv(i, q) = sg.dv(i, q);
       }
       __syncthreads();
-      double mu[6] = {0, 0, 0, 0, 0, 0};
-      if (nf > 0) {
-        double sigma2;
-        if (override_sigma > 0) sigma2 = override_sigma;
-        else {
-          double med;
-          if (nf <= kPoseSmemPts) med = block_select_kth([&](int i) { return s_e2[i]; }, nf, nf / 2, hist, &sh_prefix, &sh_k);
-          else med = block_select_kth([&](int i) { return e2[fidx[i]]; }, nf, nf / 2, hist, &sh_prefix, &sh_k);
-          sigma2 = mest_sigma_from_median(med, nf, est);
-        }
-        // weighted normal equations (TooN WLS<6>::add_mJ twice per point)
-        double acc[32];
-#pragma unroll
-        for (int q = 0; q < 32; q++) acc[q] = 0;
-        for (int i = threadIdx.x; i < nf; i += blockDim.x) {
-          const size_t g = gb + fidx[i];
-          const double sn = d.p.sqrt_inv_noise[g];
-          const double e0 = sn * (d.p.v2found[2 * g] - d.p.v2image[2 * g]), e1 = sn * (d.p.v2found[2 * g + 1] - d.p.v2image[2 * g + 1]);
-          const double es = e0 * e0 + e1 * e1;
-          const double wgt = mest_weight(es, sigma2, est);
-          if (wgt == 0.0) { if (mark) d.p.outliers[g]++; continue; }
-          if (mark) d.p.inliers[g]++;
-#pragma unroll
-          for (int r = 0; r < 2; r++) {
-            double Jr[6], Jw[6];
-#pragma unroll
-            for (int q = 0; q < 6; q++) { Jr[q] = sn * d.p.J[12 * g + 6 * r + q]; Jw[q] = Jr[q] * wgt; }
-            const double er = r ? e1 : e0;
-            int c = 0;
-#pragma unroll
-            for (int a = 0; a < 6; a++) {
-#pragma unroll
-              for (int b = 0; b <= a; b++) acc[c++] += Jw[a] * Jr[b];
-            }
-#pragma unroll
-            for (int a = 0; a < 6; a++) acc[21 + a] += er * Jw[a];
-          }
-        }
-        warp_transpose_sum32(acc);
-        if (lane < 27) red[warp][lane] = acc[0];
-        __syncthreads();
-        if (threadIdx.x < 27) {
-          double t = 0;
-          for (int wq = 0; wq < kPoseThreads / 32; wq++) t += red[wq][threadIdx.x];
-          red[0][threadIdx.x] = t;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-          double tot[27];
-          for (int q = 0; q < 27; q++) tot[q] = red[0][q];
-          double C[36], b[6], x[6];
-          int c = 0;
-          for (int a = 0; a < 6; a++)
-            for (int bb = 0; bb <= a; bb++) { C[6 * a + bb] = tot[c]; C[6 * bb + a] = tot[c]; c++; }
-          for (int a = 0; a < 6; a++) { C[7 * a] += 100.0; b[a] = tot[21 + a]; }  // add_prior(100)
-          ldlt_factor<6>(C);
-          ldlt_backsub<6>(C, b, x);
-          for (int a = 0; a < 6; a++) mu_s[a] = x[a];
-          (void)sigma_s;
-        }
-        __syncthreads();
-        for (int a = 0; a < 6; a++) mu[a] = mu_s[a];
+      pose_iterations(d, ss, sh, stage, nf, gb, fidx, e2);
+      for (int i = threadIdx.x; i < nf; i += blockDim.x) {  // what later stages and the getters read
+        sg.image(i, 0) = ss.image(i, 0); sg.image(i, 1) = ss.image(i, 1);
+        for (int q = 0; q < 3; q++) sg.v3(i, q) = ss.v3(i, q);
+        for (int q = 0; q < 4; q++) sg.dv(i, q) = ss.dv(i, q);
       }
-      // mse3CamFromWorld = SE3<>::exp(v6Update) * mse3CamFromWorld
-      if (threadIdx.x == 0) {
-        double ex[12], np[12];
-        se3_exp(mu, ex);
-        se3_mul(ex, pose, np);
-        for (int i = 0; i < 12; i++) pose[i] = np[i];
-      }
-      for (int a = 0; a < 6; a++) last_mu[a] = mu[a];
-      __syncthreads();
+    } else {
+      pose_iterations(d, sg, sh, stage, nf, gb, fidx, e2);
     }
   }
   if (threadIdx.x < 12) ctl.pose[threadIdx.x] = pose[threadIdx.x];
@@ -1139,12 +1198,12 @@ __global__ void __launch_bounds__(kPoseThreads, 2) k_pose(TrackerDev d, int stag
     }
     sum = warp_sum(sum); sumsq = warp_sum(sumsq);
     __syncthreads();
-    if (lane == 0) { red[warp][0] = sum; red[warp][1] = sumsq; }
+    if (lane == 0) { red2[warp][0] = sum; red2[warp][1] = sumsq; }
     __syncthreads();
   }
   if (threadIdx.x == 0) {
     double sum = 0, sumsq = 0;
-    for (int wq = 0; wq < kPoseThreads / 32; wq++) { sum += red[wq][0]; sumsq += red[wq][1]; }
+    for (int wq = 0; wq < kPoseThreads / 32; wq++) { sum += red2[wq][0]; sumsq += red2[wq][1]; }
     ptam_tracker_state& st = ctl.st;
     if (nf > 20) {
       st.scene_depth_mean = sum / nf;
