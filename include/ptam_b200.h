@@ -69,6 +69,10 @@ typedef struct ptam_tracker_params {
   double coarse_min_velocity;    /* Tracker.CoarseMinVelocity    = 0.006 */
   double quality_good;           /* Tracker.TrackingQualityGood  = 0.3  */
   double quality_lost;           /* Tracker.TrackingQualityLost  = 0.13 */
+  int32_t use_rotation_estimator; /* Tracker.UseRotationEstimator = 1 (Tracker.cc:96): SmallBlurryImage ESM rotation
+                                     replaces the rotational velocity in PredictPoseWithMotionModel */
+  int32_t reserved0;
+  double rotation_estimator_blur; /* Tracker.RotationEstimatorBlur = 0.75 (Tracker.cc:95) */
 } ptam_tracker_params;
 
 /* Tracker member state carried from frame to frame (Tracker.h:176-215). */
@@ -134,9 +138,9 @@ int ptam_tracker_get_state(ptam_tracker* t, int stream, ptam_tracker_state* s);
 /* KeyFrame::MakeKeyFrame_Lite only, for every stream: images[s] is stream s's W x H u8 frame. */
 int ptam_tracker_make_keyframes(ptam_tracker* t, const uint8_t* const* images, int stride);
 
-/* One TrackFrame per stream: MakeKeyFrame_Lite + PredictPoseWithMotionModel (velocity only; the
- * SmallBlurryImage rotation estimator is a "next" row) + TrackMap + UpdateMotionModel +
- * AssessTrackingQuality.  std::random_shuffle (Tracker.cc:483,601) is the identity permutation.
+/* One TrackFrame per stream: MakeKeyFrame_Lite + SmallBlurryImage update + PredictPoseWithMotionModel
+ * (with the SmallBlurryImage rotation estimator when use_rotation_estimator) + TrackMap +
+ * UpdateMotionModel + AssessTrackingQuality.  std::random_shuffle (Tracker.cc:483,601) is the identity permutation.
  * images: n_streams host pointers; results: n_streams structs (may be NULL). */
 int ptam_tracker_track_frames(ptam_tracker* t, const uint8_t* const* images, int stride,
                               ptam_track_result* results);
@@ -162,7 +166,7 @@ void* ptam_tracker_cuda_stream(ptam_tracker* t);
 int64_t ptam_tracker_launch_count(const ptam_tracker* t);
 /* Per-kernel device timing: when on, every launch is bracketed by CUDA events on the handle's
  * stream and each call synchronises to accumulate them.  Kernel ids: 0 k_pyramid, 1 k_fast,
- * 2 k_compact, 3 k_pvs_select, 4 k_search(coarse), 5 k_pose(coarse), 6 k_search(fine), 7 k_pose(fine).
+ * 2 k_compact, 3 k_sbi + k_pvs_select, 4 k_search(coarse), 5 k_pose(coarse), 6 k_search(fine), 7 k_pose(fine).
  * Turning it on or off resets the accumulators. */
 int ptam_tracker_set_profiling(ptam_tracker* t, int on);
 int ptam_tracker_get_kernel_times(ptam_tracker* t, double ms_total[8], int64_t launches[8]);
@@ -179,6 +183,10 @@ int ptam_tracker_level_size(const ptam_tracker* t, int level, int* w, int* h);
 int ptam_tracker_get_points(ptam_tracker* t, int stream, int32_t* flags, int32_t* level,
                             double* v2_found, double* v2_image, int32_t* outlier_count,
                             int32_t* inlier_count);
+/* SmallBlurryImage of the last frame of one stream (ImageProcess.cc:279-304): mimTemplate (w*h floats,
+ * at most cap), the rotation estimate CalcSBIRotation gave against the previous frame (so3 log, 3
+ * doubles) and its final ESM score.  Returns w*h of the small image ((W/8)/2 x (H/8)/2). */
+int ptam_tracker_get_sbi(ptam_tracker* t, int stream, float* tmpl, int cap, double rot3[3], double* score);
 /* Cached coarse templates of one stream: tmpl n*64 bytes, sums n*2 ints (sum, sum of squares). */
 int ptam_tracker_get_templates(ptam_tracker* t, int stream, uint8_t* tmpl, int32_t* sums);
 /* vIterationSet of the last frame in order (coarse set, level-3 set, fine set); returns its size. */

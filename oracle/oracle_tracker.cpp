@@ -148,8 +148,203 @@ struct TData {
 static inline double level_zero_pos(double p, int l) { return (p + 0.5) * (1 << l) - 0.5; }
 static inline double level_n_pos(double p, int l) { return (p + 0.5) / (1 << l) - 0.5; }
 
+// ---------------------------------------------------------------------------------------------
+// SmallBlurryImage + rotation estimator: SmallBlurryImage::MakeFromKF
+// (ImageProcess.cc:279-304), ImageProcess::MakeJacs (:170-191), IteratePosRelToTarget (:313-412),
+// SE3fromSE2 (:421-473), CalcSBIRotation (:482-494); used by Tracker::TrackFrame (Tracker.cc:95-108)
+// and PredictPoseWithMotionModel (:1012-1029).
+// libCVD pieces restated (PARITY UNPINNED): halfSample as above; convolveGaussian(float image,
+// sigma) as a separable FIR of radius ceil(3 sigma), taps exp(-i^2 / 2 sigma^2) normalised to unit
+// sum and rounded to float, replicated borders, float accumulation  centre, then (a + b) * tap
+// outwards, rows first then columns; CVD::transform with bilinear sample() evaluated in double and
+// rounded to float, positions accumulated across / down, default value -9e20f outside.
+// ---------------------------------------------------------------------------------------------
+struct SBI {
+  int w = 0, h = 0;
+  std::vector<float> tmpl;    // mimTemplate
+  std::vector<float> jx, jy;  // mimImageJacs (float differences, read as double)
+  bool valid = false;
+};
+
+static void sbi_gaussian_taps(double sigma, float* taps /*ksize+1*/, int& ksize) {
+  ksize = (int)std::ceil(3.0 * sigma);
+  float ksum = 0.f;
+  for (int i = 1; i <= ksize; i++) ksum += (taps[i] = (float)std::exp(-i * i / (2 * sigma * sigma)));
+  taps[0] = 1.f;
+  ksum = ksum * 2 + taps[0];
+  const double factor = 1.0 / ksum;
+  for (int i = 0; i <= ksize; i++) taps[i] = (float)(taps[i] * factor);
+}
+
+static void sbi_make(const KeyFrame& kf, double blur, SBI& o) {
+  const Level& L3 = kf.lev[3];
+  o.w = (L3.w / 2); o.h = (L3.h / 2);
+  // mirSize = aLevels[3].im.size() / 2 and halfSample(aLevels[3].im, mimSmall)
+  Level small;
+  half_sample(L3, small);
+  const int n = o.w * o.h;
+  unsigned sum = 0;
+  for (int i = 0; i < n; i++) sum += small.im[i];
+  const float mean = ((float)sum) / n;
+  std::vector<float> t(n), hrow(n);
+  for (int i = 0; i < n; i++) t[i] = small.im[i] - mean;
+  float taps[16];
+  int ks;
+  sbi_gaussian_taps(blur, taps, ks);
+  auto cl = [](int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); };
+  for (int y = 0; y < o.h; y++)
+    for (int x = 0; x < o.w; x++) {
+      float a = t[y * o.w + x] * taps[0];
+      for (int k = 1; k <= ks; k++) a += (t[y * o.w + cl(x - k, o.w - 1)] + t[y * o.w + cl(x + k, o.w - 1)]) * taps[k];
+      hrow[y * o.w + x] = a;
+    }
+  o.tmpl.assign(n, 0.f);
+  for (int y = 0; y < o.h; y++)
+    for (int x = 0; x < o.w; x++) {
+      float a = hrow[y * o.w + x] * taps[0];
+      for (int k = 1; k <= ks; k++) a += (hrow[cl(y - k, o.h - 1) * o.w + x] + hrow[cl(y + k, o.h - 1) * o.w + x]) * taps[k];
+      o.tmpl[y * o.w + x] = a;
+    }
+  o.jx.clear(); o.jy.clear();
+  o.valid = true;
+}
+
+static void sbi_make_jacs(SBI& s) {  // ImageProcess::MakeJacs
+  const int n = s.w * s.h;
+  s.jx.assign(n, 0.f); s.jy.assign(n, 0.f);
+  for (int y = 1; y < s.h - 1; y++)
+    for (int x = 1; x < s.w - 1; x++) {
+      s.jx[y * s.w + x] = s.tmpl[y * s.w + x + 1] - s.tmpl[y * s.w + x - 1];
+      s.jy[y * s.w + x] = s.tmpl[(y + 1) * s.w + x] - s.tmpl[(y - 1) * s.w + x];
+    }
+}
+
+struct SE2 { double c = 1, s = 0, t[2] = {0, 0}; };  // rotation [[c,-s],[s,c]] + translation
+static SE2 se2_mul(const SE2& a, const SE2& b) {
+  SE2 r;
+  r.c = a.c * b.c - a.s * b.s; r.s = a.s * b.c + a.c * b.s;
+  r.t[0] = a.t[0] + (a.c * b.t[0] - a.s * b.t[1]);
+  r.t[1] = a.t[1] + (a.s * b.t[0] + a.c * b.t[1]);
+  return r;
+}
+
+// IteratePosRelToTarget: ESM alignment of `cur` against `other` (which has its jacs made)
+static SE2 sbi_iterate(const SBI& cur, const SBI& other, int n_its, double& final_score) {
+  const int w = cur.w, h = cur.h;
+  const int cx = w / 2, cy = h / 2;
+  SE2 c2c;
+  std::vector<float> warped(w * h);
+  double mean_offset = 0.0;
+  final_score = 0.0;
+  for (int it = 0; it < n_its; it++) {
+    final_score = 0.0;
+    double acc[4] = {0, 0, 0, 0}, tri[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    // se2XForm = se2WfromC * se2CtoC * se2WfromC.inverse()
+    SE2 wfc; wfc.t[0] = cx; wfc.t[1] = cy;
+    SE2 wfc_inv; wfc_inv.t[0] = -(double)cx; wfc_inv.t[1] = -(double)cy;
+    const SE2 xf = se2_mul(se2_mul(wfc, c2c), wfc_inv);
+    // CVD::transform(mimTemplate, imWarped, R, t, zero, -9e20f)
+    {
+      const double across[2] = {xf.c, xf.s}, down[2] = {-xf.s, xf.c};
+      double pp[2] = {xf.t[0], xf.t[1]};
+      const double cr[2] = {down[0] - w * across[0], down[1] - w * across[1]};
+      const double xb = w - 1, yb = h - 1;
+      for (int i = 0; i < h; i++, pp[0] += cr[0], pp[1] += cr[1])
+        for (int j = 0; j < w; j++, pp[0] += across[0], pp[1] += across[1]) {
+          if (0 <= pp[0] && 0 <= pp[1] && pp[0] < xb && pp[1] < yb) {
+            double x = pp[0], y = pp[1];
+            const int lx = (int)x, ly = (int)y;
+            x -= lx; y -= ly;
+            const float* r0 = &cur.tmpl[ly * w + lx];
+            const float* r1 = r0 + w;
+            warped[i * w + j] = (float)((1 - y) * ((1 - x) * r0[0] + x * r0[1]) + y * ((1 - x) * r1[0] + x * r1[1]));
+          } else warped[i * w + j] = -9e20f;
+        }
+    }
+    for (int y = 1; y < h - 1; y++)
+      for (int x = 1; x < w - 1; x++) {
+        const float l = warped[y * w + x - 1], r = warped[y * w + x + 1], u = warped[(y - 1) * w + x], dn = warped[(y + 1) * w + x];
+        const float here = warped[y * w + x];
+        if (l + r + u + dn + here < -9999.9) continue;
+        const double g0 = r - l, g1 = dn - u;
+        const double sg0 = 0.25 * (g0 + (double)other.jx[y * w + x]), sg1 = 0.25 * (g1 + (double)other.jy[y * w + x]);
+        double J[4];
+        J[0] = sg0; J[1] = sg1; J[2] = -(y - cy) * sg0 + (x - cx) * sg1; J[3] = 1.0;
+        const double diff = here - other.tmpl[y * w + x] + mean_offset;
+        final_score += diff * diff;
+        for (int q = 0; q < 4; q++) acc[q] += diff * J[q];
+        tri[0] += J[0] * J[0]; tri[1] += J[1] * J[0]; tri[2] += J[1] * J[1];
+        tri[3] += J[2] * J[0]; tri[4] += J[2] * J[1]; tri[5] += J[2] * J[2];
+        tri[6] += J[0]; tri[7] += J[1]; tri[8] += J[2]; tri[9] += 1.0;
+      }
+    double M[16], upd[4];
+    int v = 0;
+    for (int j = 0; j < 4; j++)
+      for (int i = 0; i <= j; i++) M[4 * j + i] = M[4 * i + j] = tri[v++];
+    ldlt_factor(M, 4, 4);
+    ldlt_backsub(M, 4, 4, acc, upd);
+    SE2 u;
+    u.t[0] = -upd[0]; u.t[1] = -upd[1];
+    u.c = std::cos(-upd[2]); u.s = std::sin(-upd[2]);
+    c2c = se2_mul(c2c, u);
+    mean_offset -= upd[3];
+  }
+  return c2c;
+}
+
+// SE3fromSE2: the camera rotation that produces the image-plane rotation (returns so3 as a matrix)
+static void sbi_so3_from_se2(const SE2& se2, const Camera& cam_small, int w, int h, double* R /*9*/) {
+  const double cx = w / 2, cy = h / 2;
+  double turned[2][2], orig[2][3];
+  const double off[2] = {5.0, -5.0};
+  for (int i = 0; i < 2; i++) {
+    turned[i][0] = cx + (se2.c * off[i] + se2.t[0]);
+    turned[i][1] = cy + (se2.s * off[i] + se2.t[1]);
+    const double im[2] = {cx + off[i], cy};
+    double c2[2];
+    cam_small.unproject(im, c2);
+    orig[i][0] = c2[0]; orig[i][1] = c2[1]; orig[i][2] = 1.0;
+  }
+  for (int i = 0; i < 9; i++) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  for (int it = 0; it < 3; it++) {
+    double C[9] = {10, 0, 0, 0, 10, 0, 0, 0, 10}, b[3] = {0, 0, 0};  // WLS<3>, add_prior(10)
+    for (int i = 0; i < 2; i++) {
+      double vc[3];
+      for (int r = 0; r < 3; r++) vc[r] = R[3 * r] * orig[i][0] + R[3 * r + 1] * orig[i][1] + R[3 * r + 2] * orig[i][2];
+      const double ip[2] = {vc[0] / vc[2], vc[1] / vc[2]};
+      const Camera::Proj q = cam_small.project(ip);
+      const double err[2] = {turned[i][0] - q.im[0], turned[i][1] - q.im[1]};
+      double dv[4];
+      cam_small.derivs(q, dv);
+      const double ooz = 1.0 / vc[2];
+      // SO3 generator_field(m, v3Cam): m=0: (0,-z,y), 1: (z,0,-x), 2: (-y,x,0)
+      const double gen[3][3] = {{0, -vc[2], vc[1]}, {vc[2], 0, -vc[0]}, {-vc[1], vc[0], 0}};
+      double Jr[2][3];
+      for (int m = 0; m < 3; m++) {
+        const double a0 = (gen[m][0] - vc[0] * gen[m][2] * ooz) * ooz, a1 = (gen[m][1] - vc[1] * gen[m][2] * ooz) * ooz;
+        Jr[0][m] = dv[0] * a0 + dv[1] * a1;
+        Jr[1][m] = dv[2] * a0 + dv[3] * a1;
+      }
+      for (int r = 0; r < 2; r++)
+        for (int a = 0; a < 3; a++) {
+          for (int c = 0; c < 3; c++) C[3 * a + c] += Jr[r][a] * Jr[r][c];
+          b[a] += err[r] * Jr[r][a];
+        }
+    }
+    double x[3];
+    ldlt_factor(C, 3, 3);
+    ldlt_backsub(C, 3, 3, b, x);
+    double E[9], N[9];
+    so3_exp(x, E);
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) N[3 * r + c] = E[3 * r] * R[c] + E[3 * r + 1] * R[3 + c] + E[3 * r + 2] * R[6 + c];
+    for (int i = 0; i < 9; i++) R[i] = N[i];
+  }
+}
+
 struct Tracker {
   Camera cam;
+  Camera cam_small;  // ATANCamera at the SmallBlurryImage size (SE3fromSE2, ImageProcess.cc:423)
   int W, H, S;
   ptam_tracker_params prm;
   std::vector<KeyFrame> store;
@@ -163,6 +358,8 @@ struct Tracker {
     bool did_coarse = false;
     std::vector<int> iter_set;
     ptam_track_result res;
+    SBI sbi_this, sbi_last;      // mpSBIThisFrame / mpSBILastFrame (Tracker.cc:97-108)
+    double sbi_rot[3] = {0, 0, 0}, sbi_score = 0;
   };
   std::vector<Stream> streams;
   std::string err;
@@ -532,11 +729,29 @@ struct Tracker {
 
   void track_frame(Stream& s, const uint8_t* im, int stride) {
     make_keyframe_lite(s.cur, im, W, H, stride);
+    // Update the small images for the rotation estimator (Tracker.cc:95-108)
+    if (!s.sbi_this.valid) { sbi_make(s.cur, prm.rotation_estimator_blur, s.sbi_this); s.sbi_last = s.sbi_this; }
+    else { s.sbi_last = s.sbi_this; sbi_make(s.cur, prm.rotation_estimator_blur, s.sbi_this); }
     s.st.frame++;
     s.pose = SE3::from12(s.st.se3_cam_from_world);
-    // PredictPoseWithMotionModel (Tracker.cc:1012-1029), mbUseSBIInit = false
+    // PredictPoseWithMotionModel (Tracker.cc:1012-1029)
     s.start = s.pose;
-    s.pose = se3_mul(se3_exp(s.st.velocity), s.start);
+    double vpred[6];
+    for (int k = 0; k < 6; k++) vpred[k] = s.st.velocity[k];
+    {
+      sbi_make_jacs(s.sbi_last);
+      const SE2 se2 = sbi_iterate(s.sbi_this, s.sbi_last, 6, s.sbi_score);  // CalcSBIRotation, nIterations = 6
+      SE3 rot;
+      sbi_so3_from_se2(se2, cam_small, s.sbi_this.w, s.sbi_this.h, rot.R);
+      double ln6[6];
+      se3_ln(rot, ln6);
+      for (int k = 0; k < 3; k++) s.sbi_rot[k] = ln6[3 + k];
+    }
+    if (prm.use_rotation_estimator) {
+      for (int k = 0; k < 3; k++) vpred[3 + k] = s.sbi_rot[k];
+      vpred[0] = 0.0; vpred[1] = 0.0;
+    }
+    s.pose = se3_mul(se3_exp(vpred), s.start);
     track_map(s);
     // UpdateMotionModel (Tracker.cc:1035-1056)
     double motion[6];
@@ -590,11 +805,13 @@ void orc_tracker_default_params(ptam_tracker_params* p) {
   p->coarse_min = 20; p->coarse_max = 60; p->coarse_range = 30; p->coarse_subpix_its = 8;
   p->disable_coarse = 0; p->max_patches_per_frame = 1000; p->mestimator = 0; p->use_constant_velocity = 1;
   p->coarse_min_velocity = 0.006; p->quality_good = 0.3; p->quality_lost = 0.13;
+  p->use_rotation_estimator = 1; p->reserved0 = 0; p->rotation_estimator_blur = 0.75;  // Tracker.cc:95-96
 }
 
 void* orc_tracker_create(int, const double* cam_params, int width, int height, int n_streams, const ptam_tracker_params* params) {
   Tracker* t = new Tracker;
   t->cam.init(cam_params, width, height);
+  t->cam_small.init(cam_params, ((width / 8) / 2), ((height / 8) / 2));
   t->W = width; t->H = height; t->S = n_streams;
   if (params) t->prm = *params; else orc_tracker_default_params(&t->prm);
   t->streams.resize(n_streams);
@@ -716,6 +933,16 @@ int orc_tracker_get_iteration_set(void* tp, int stream, int32_t* idx, int cap) {
 
 // ---- unit-level helpers used only by tests -------------------------------------------------
 double orc_atan(double x) { return orc::spec_atan(x); }
+int orc_tracker_get_sbi(void* tp, int stream, float* tmpl, int cap, double* rot3, double* score) {
+  Tracker* t = (Tracker*)tp;
+  if (stream < 0 || stream >= t->S) return PTAM_ERR_INVALID;
+  const auto& s = t->streams[stream];
+  const int n = s.sbi_this.w * s.sbi_this.h;
+  if (tmpl) for (int i = 0; i < n && i < cap; i++) tmpl[i] = s.sbi_this.tmpl[i];
+  if (rot3) for (int k = 0; k < 3; k++) rot3[k] = s.sbi_rot[k];
+  if (score) *score = s.sbi_score;
+  return n;
+}
 void orc_se3_exp(const double* mu, double* out12) { orc::se3_exp(mu).to12(out12); }
 void orc_se3_ln(const double* in12, double* out6) { orc::se3_ln(orc::SE3::from12(in12), out6); }
 void orc_cam_project(const double* params, int w, int h, const double* cam_xy, double* im_xy, double* derivs4, int* invalid) {

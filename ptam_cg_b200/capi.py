@@ -27,6 +27,7 @@ class TrackerParams(C.Structure):
         ("max_patches_per_frame", C.c_int32), ("mestimator", C.c_int32),
         ("use_constant_velocity", C.c_int32), ("coarse_min_velocity", C.c_double),
         ("quality_good", C.c_double), ("quality_lost", C.c_double),
+        ("use_rotation_estimator", C.c_int32), ("reserved0", C.c_int32), ("rotation_estimator_blur", C.c_double),
     ]
 
 
@@ -70,7 +71,7 @@ TRACKER_SYMBOLS = [
     "tracker_default_params", "tracker_create", "tracker_destroy", "tracker_last_error",
     "tracker_add_keyframe", "tracker_set_map", "tracker_set_state", "tracker_get_state",
     "tracker_make_keyframes", "tracker_track_frames", "tracker_synchronize", "tracker_get_level",
-    "tracker_level_size", "tracker_get_points", "tracker_get_templates",
+    "tracker_level_size", "tracker_get_points", "tracker_get_templates", "tracker_get_sbi",
     "tracker_get_iteration_set",
 ]
 BUNDLE_SYMBOLS = [
@@ -90,7 +91,7 @@ PRODUCT_ONLY_SYMBOLS = [
     "bundle_set_profiling", "bundle_get_phase_times",
 ]
 BUNDLE_PHASES = ["project", "select", "jacobian", "vinv_init", "schur", "allreduce", "solve", "update_newerror"]
-TRACKER_KERNELS = ["k_pyramid", "k_fast", "k_compact", "k_pvs_select", "k_search_coarse", "k_pose_coarse",
+TRACKER_KERNELS = ["k_pyramid", "k_fast", "k_compact", "k_sbi+k_pvs_select", "k_search_coarse", "k_pose_coarse",
                    "k_search_fine", "k_pose_fine"]
 
 
@@ -159,6 +160,7 @@ class Lib:
             "tracker_level_size": (i, [vp, i, P(i), P(i)]),
             "tracker_get_points": (i, [vp, i, P(C.c_int32), P(C.c_int32), P(d), P(d), P(C.c_int32), P(C.c_int32)]),
             "tracker_get_templates": (i, [vp, i, P(C.c_uint8), P(C.c_int32)]),
+            "tracker_get_sbi": (i, [vp, i, P(C.c_float), i, P(d), P(d)]),
             "tracker_get_iteration_set": (i, [vp, i, P(C.c_int32), i]),
             "global_last_error": (C.c_char_p, []),
             "bundle_default_params": (None, [P(BundleParams)]),
@@ -365,6 +367,20 @@ class Tracker:
         arr = (C.c_void_p * self.S)(*ptrs)
         self._chk(self.lib.fn("tracker_submit_frames")(self.h, arr, stride))
 
+    def ptr_array(self, ptrs):
+        """ctypes pointer array for submit_array (build once per batch, outside any timed loop)."""
+        return (C.c_void_p * self.S)(*ptrs)
+
+    def submit_array(self, arr, stride):
+        self._chk(self.lib.fn("tracker_submit_frames")(self.h, arr, stride))
+
+    def result_buffer(self):
+        return (TrackResult * self.S)()
+
+    def collect_into(self, res):
+        self._chk(self.lib.fn("tracker_collect")(self.h, res))
+        return res
+
     def collect(self, want_results=True):
         res = (TrackResult * self.S)() if want_results else None
         self._chk(self.lib.fn("tracker_collect")(self.h, res))
@@ -397,6 +413,14 @@ class Tracker:
         t, s = np.zeros((n, 64), np.uint8), np.zeros((n, 2), np.int32)
         self._chk(self.lib.fn("tracker_get_templates")(self.h, stream, _bp(t), _ip(s)))
         return t, s
+
+    def get_sbi(self, stream):
+        """(mimTemplate as (h, w) float32, so3 rotation estimate (3,), final ESM score) of the last frame."""
+        n = self.lib.fn("tracker_get_sbi")(self.h, stream, None, 0, None, None)
+        tmpl, rot, score = np.zeros(max(n, 1), np.float32), np.zeros(3), C.c_double()
+        self._chk(self.lib.fn("tracker_get_sbi")(self.h, stream, tmpl.ctypes.data_as(C.POINTER(C.c_float)), n, _dp(rot), C.byref(score)))
+        w3, h3 = self.level_size(3)
+        return tmpl[:n].reshape(h3 // 2, w3 // 2), rot, score.value
 
     def get_iteration_set(self, stream):
         n = self.n_points[stream]

@@ -82,6 +82,8 @@ struct ptam_tracker {
   DevBuf<int> src_kf, src_level, tsum, tsumsq, flags, level, search_level, outliers, inliers, pvs, iter_idx;
   DevBuf<int2> center;
   DevBuf<int4> geo;
+  DevBuf<float> sbi_tmpl;
+  size_t sbi_smem = 0;
   DevBuf<uint8_t> tmpl;
   // pinned staging
   uint8_t* h_stage = nullptr;
@@ -107,7 +109,7 @@ struct ptam_tracker {
     if (stream) cudaStreamSynchronize(stream);
     for (auto p : kf_bufs) cudaFree(p);
     pyr.free(); corners.free(); lut.free(); mask.free(); ctl.free(); pt_count.free(); kf_ptrs.free();
-    world.free(); right.free(); down.free(); last_warp.free(); m2buf.free(); geo.free(); v3cam.free(); v2image.free(); derivs.free();
+    world.free(); right.free(); down.free(); last_warp.free(); m2buf.free(); geo.free(); sbi_tmpl.free(); v3cam.free(); v2image.free(); derivs.free();
     warp_inv.free(); v2found.free(); sin_.free(); J.free(); e2.free(); src_kf.free(); src_level.free();
     tsum.free(); tsumsq.free(); flags.free(); level.free(); search_level.free(); outliers.free(); inliers.free();
     pvs.free(); iter_idx.free(); center.free(); tmpl.free();
@@ -156,6 +158,23 @@ struct ptam_tracker {
     max_h = h;
     dev.cam = make_cam(cam_params, w, h);
     if (prm) dev.prm = *prm; else ptam_tracker_default_params(&dev.prm);
+    {  // SmallBlurryImage geometry and Gaussian taps (ImageProcess.cc:279-304; libCVD convolveGaussian)
+      SbiDev& sb = dev.sbi;
+      sb.w = g.lev[3].w / 2; sb.h = g.lev[3].h / 2; sb.n = sb.w * sb.h;
+      const double sigma = dev.prm.rotation_estimator_blur;
+      sb.ks = (int)std::ceil(3.0 * sigma);
+      if (sb.ks < 0 || sb.ks > 7 || !(sigma > 0)) { set_error("rotation_estimator_blur out of range (0, 7/3]"); return PTAM_ERR_INVALID; }
+      float ksum = 0.f;
+      for (int i = 0; i < 8; i++) sb.taps[i] = 0.f;
+      for (int i = 1; i <= sb.ks; i++) ksum += (sb.taps[i] = (float)std::exp(-i * i / (2 * sigma * sigma)));
+      sb.taps[0] = 1.f;
+      ksum = ksum * 2 + sb.taps[0];
+      const double factor = 1.0 / ksum;
+      for (int i = 0; i <= sb.ks; i++) sb.taps[i] = (float)(sb.taps[i] * factor);
+      sb.cam_small = make_cam(cam_params, sb.w, sb.h);
+      if (sb.n < 9) { set_error("image too small for the rotation estimator"); return PTAM_ERR_INVALID; }
+      sbi_smem = (size_t)sb.n * (7 * sizeof(float) + 1) + 16;
+    }
     dev.S = S;
     PTAM_CUDA_TRY(this, pyr.alloc(g.pyr_bytes * S));
     PTAM_CUDA_TRY(this, corners.alloc(g.corner_stride * S));
@@ -178,6 +197,9 @@ struct ptam_tracker {
     dev.pt_count = pt_count.p;
     dev.kf_ptrs = nullptr; dev.n_kf = 0;
     PTAM_CUDA_TRY(this, ensure_points(1024));
+    PTAM_CUDA_TRY(this, sbi_tmpl.alloc((size_t)2 * S * dev.sbi.n));
+    dev.sbi.tmpl = sbi_tmpl.p;
+    if (sbi_smem > 48 * 1024) PTAM_CUDA_TRY(this, cudaFuncSetAttribute(k_sbi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbi_smem));
     PTAM_CUDA_TRY(this, cudaFuncSetAttribute(k_pose, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoseSmemBytes));
     if ((size_t)(max_h + 1) * sizeof(int) > 48 * 1024)
       PTAM_CUDA_TRY(this, cudaFuncSetAttribute(k_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (max_h + 1) * (int)sizeof(int)));
@@ -306,7 +328,10 @@ struct ptam_tracker {
     int maxn = 0;
     for (int s = 0; s < S; s++) maxn = std::max(maxn, h_pt_count[s]);
     unsigned used = 7u | 8u | 32u | 128u;
-    pbegin(3); k_pvs_select<<<S, 1024, 0, stream>>>(d); pend(3);
+    pbegin(3);
+    k_sbi<<<S, 256, sbi_smem, stream>>>(d);
+    k_pvs_select<<<S, 1024, 0, stream>>>(d);
+    pend(3); launches++;
     const int coarse_items = std::min(maxn, 2 * std::max(0, d.prm.coarse_max));
     if (coarse_items > 0) {
       pbegin(4);
@@ -368,6 +393,7 @@ void ptam_tracker_default_params(ptam_tracker_params* p) {
   p->coarse_min = 20; p->coarse_max = 60; p->coarse_range = 30; p->coarse_subpix_its = 8;
   p->disable_coarse = 0; p->max_patches_per_frame = 1000; p->mestimator = 0; p->use_constant_velocity = 1;
   p->coarse_min_velocity = 0.006; p->quality_good = 0.3; p->quality_lost = 0.13;
+  p->use_rotation_estimator = 1; p->reserved0 = 0; p->rotation_estimator_blur = 0.75;
 }
 
 const char* ptam_global_last_error(void) { return g_last_error.c_str(); }
@@ -611,6 +637,22 @@ int ptam_tracker_get_points(ptam_tracker* t, int stream, int32_t* flags, int32_t
     if (v2_found && !fnd) v2_found[2 * i] = v2_found[2 * i + 1] = 0;
     if (v2_image && !(f & F_IN_PVS)) v2_image[2 * i] = v2_image[2 * i + 1] = 0;
   }
+  return n;
+}
+
+int ptam_tracker_get_sbi(ptam_tracker* t, int stream, float* tmpl, int cap, double* rot3, double* score) {
+  cudaSetDevice(t->device);
+  if (stream < 0 || stream >= t->S) { t->set_error("bad stream"); return PTAM_ERR_INVALID; }
+  PTAM_CUDA_TRY(t, cudaStreamSynchronize(t->stream));
+  StreamCtl c;
+  PTAM_CUDA_TRY(t, cudaMemcpy(&c, &t->ctl.p[stream], sizeof(c), cudaMemcpyDeviceToHost));
+  const int n = t->dev.sbi.n;
+  if (tmpl && cap > 0) {
+    if (!c.sbi_valid) std::memset(tmpl, 0, sizeof(float) * std::min(n, cap));
+    else PTAM_CUDA_TRY(t, cudaMemcpy(tmpl, t->sbi_tmpl.p + ((size_t)c.sbi_idx * t->S + stream) * n, sizeof(float) * std::min(n, cap), cudaMemcpyDeviceToHost));
+  }
+  if (rot3) for (int k = 0; k < 3; k++) rot3[k] = c.sbi_rot[k];
+  if (score) *score = c.sbi_score;
   return n;
 }
 

@@ -52,6 +52,9 @@ struct StreamCtl {
   int n_corners[kLevels];
   int needs_kf_distance;
   int n_cand;  // ZMSSD windows evaluated this frame (coarse + fine), for the roofline accounting
+  // SmallBlurryImage rotation estimator (Tracker.cc:95-108,1012-1029)
+  int sbi_valid, sbi_idx;   // a previous small image exists / which of the two buffers holds it
+  double sbi_rot[3], sbi_score;
 };
 
 // frame-scoped point flags (low byte) and persistent flags (high bits)
@@ -86,9 +89,17 @@ struct FrameSrc {
   int pitch;             // bytes between rows
 };
 
+struct SbiDev {
+  int w, h, n, ks;       // small image size ((W/8)/2 x (H/8)/2), Gaussian radius
+  float taps[8];         // normalised taps, computed on the host (ImageProcess.cc:303, sigma = RotationEstimatorBlur)
+  float* tmpl;           // [2][S][n] mimTemplate of this / the previous frame
+  CamModel cam_small;    // the camera at the small image size (ImageProcess.cc:423)
+};
+
 struct TrackerDev {
   Geom g;
   CamModel cam;
+  SbiDev sbi;
   ptam_tracker_params prm;
   FrameSrc src;
   uint8_t* pyr;          // [S] pyramids (levels 1..3 used; level 0 when frames come from the host)
@@ -396,6 +407,213 @@ __global__ void __launch_bounds__(1024) k_compact(TrackerDev d) {
 }
 
 // =============================================================================================
+// k_sbi — one CTA per stream: SmallBlurryImage::MakeFromKF of the current frame (halfSample of level 3,
+// zero mean, Gaussian blur; ImageProcess.cc:279-304), MakeJacs of the previous one (:170-191), six
+// ESM iterations of IteratePosRelToTarget (:313-412) and SE3fromSE2 (:421-473).  Result: the so3
+// rotation vector PredictPoseWithMotionModel substitutes for the rotational velocity.
+// Float arithmetic follows the specification in oracle/oracle_tracker.cpp operation by operation
+// (no FMA contraction), so the small image is bit-identical; the ESM sums are reduced in parallel
+// (different order), and warp positions are evaluated directly instead of accumulated.
+// =============================================================================================
+struct Se2 { double c, s, tx, ty; };
+PTAM_DEV Se2 se2_mul(const Se2& a, const Se2& b) {
+  Se2 r;
+  r.c = a.c * b.c - a.s * b.s; r.s = a.s * b.c + a.c * b.s;
+  r.tx = a.tx + (a.c * b.tx - a.s * b.ty);
+  r.ty = a.ty + (a.s * b.tx + a.c * b.ty);
+  return r;
+}
+
+__global__ void __launch_bounds__(256) k_sbi(TrackerDev d) {
+  extern __shared__ __align__(16) unsigned char sbi_raw[];
+  __shared__ double red[8][16];
+  __shared__ double fin[16];
+  __shared__ unsigned usum[8];
+  __shared__ Se2 c2c_s;
+  __shared__ double mean_off_s;
+  const SbiDev& sb = d.sbi;
+  const int n = sb.n, w = sb.w, h = sb.h, ks = sb.ks;
+  float* t = reinterpret_cast<float*>(sbi_raw);
+  float* hrow = t + n; float* cur = hrow + n; float* prev = cur + n;
+  float* jx = prev + n; float* jy = jx + n; float* warped = jy + n;
+  uint8_t* small = reinterpret_cast<uint8_t*>(warped + n);
+  const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  StreamCtl& ctl = d.ctl[s];
+  int pitch;
+  const uint8_t* l3 = level_image(d, s, 3, pitch);
+  // ---- halfSample(level 3) and its sum
+  unsigned part = 0;
+  for (int i = tid; i < n; i += blockDim.x) {
+    const int y = i / w, x = i - y * w;
+    const uint8_t* r0 = l3 + (size_t)(2 * y) * pitch + 2 * x;
+    const uint8_t* r1 = r0 + pitch;
+    const int v = ((int)r0[0] + r0[1] + r1[0] + r1[1]) / 4;
+    small[i] = (uint8_t)v;
+    part += (unsigned)v;
+  }
+  part = __reduce_add_sync(kFull, part);
+  if (lane == 0) usum[warp] = part;
+  __syncthreads();
+  unsigned total = 0;
+  for (int q = 0; q < 8; q++) total += usum[q];
+  const float mean = ((float)total) / (float)n;
+  for (int i = tid; i < n; i += blockDim.x) t[i] = (float)small[i] - mean;
+  __syncthreads();
+  // ---- Gaussian blur: rows, then columns; replicated borders
+  for (int i = tid; i < n; i += blockDim.x) {
+    const int y = i / w, x = i - y * w;
+    float a = t[i] * sb.taps[0];
+    for (int k = 1; k <= ks; k++) a += (t[y * w + max(x - k, 0)] + t[y * w + min(x + k, w - 1)]) * sb.taps[k];
+    hrow[i] = a;
+  }
+  __syncthreads();
+  const int idx_prev = ctl.sbi_idx, has_prev = ctl.sbi_valid;
+  float* g_cur = sb.tmpl + ((size_t)(1 - idx_prev) * d.S + s) * n;
+  const float* g_prev = sb.tmpl + ((size_t)idx_prev * d.S + s) * n;
+  for (int i = tid; i < n; i += blockDim.x) {
+    const int y = i / w, x = i - y * w;
+    float a = hrow[i] * sb.taps[0];
+    for (int k = 1; k <= ks; k++) a += (hrow[max(y - k, 0) * w + x] + hrow[min(y + k, h - 1) * w + x]) * sb.taps[k];
+    cur[i] = a;
+    g_cur[i] = a;
+    prev[i] = has_prev ? g_prev[i] : a;  // first frame: both small images are made from it (Tracker.cc:99-100)
+  }
+  __syncthreads();
+  // ---- MakeJacs of the previous small image
+  for (int i = tid; i < n; i += blockDim.x) {
+    const int y = i / w, x = i - y * w;
+    float gx = 0.f, gy = 0.f;
+    if (x >= 1 && y >= 1 && x < w - 1 && y < h - 1) { gx = prev[i + 1] - prev[i - 1]; gy = prev[i + w] - prev[i - w]; }
+    jx[i] = gx; jy[i] = gy;
+  }
+  if (tid == 0) { c2c_s.c = 1.0; c2c_s.s = 0.0; c2c_s.tx = 0.0; c2c_s.ty = 0.0; mean_off_s = 0.0; }
+  __syncthreads();
+  // ---- IteratePosRelToTarget, nIterations = 6
+  const int cx = w / 2, cy = h / 2;
+  double final_score = 0.0;
+  for (int it = 0; it < 6; it++) {
+    const Se2 c2c = c2c_s;
+    const double mean_off = mean_off_s;
+    Se2 wfc{1.0, 0.0, (double)cx, (double)cy}, wfc_inv{1.0, 0.0, -(double)cx, -(double)cy};
+    const Se2 xf = se2_mul(se2_mul(wfc, c2c), wfc_inv);
+    const double xb = w - 1, yb = h - 1;
+    for (int i = tid; i < n; i += blockDim.x) {
+      const int y = i / w, x = i - y * w;
+      const double px = xf.tx + ((double)x * xf.c + (double)y * (-xf.s));
+      const double py = xf.ty + ((double)x * xf.s + (double)y * xf.c);
+      float v = -9e20f;
+      if (0 <= px && 0 <= py && px < xb && py < yb) {
+        const int lx = (int)px, ly = (int)py;
+        const double fx = px - lx, fy = py - ly;
+        const float* r0 = cur + ly * w + lx;
+        const float* r1 = r0 + w;
+        v = (float)((1 - fy) * ((1 - fx) * (double)r0[0] + fx * (double)r0[1]) + fy * ((1 - fx) * (double)r1[0] + fx * (double)r1[1]));
+      }
+      warped[i] = v;
+    }
+    __syncthreads();
+    double a[15];
+#pragma unroll
+    for (int q = 0; q < 15; q++) a[q] = 0.0;
+    for (int i = tid; i < n; i += blockDim.x) {
+      const int y = i / w, x = i - y * w;
+      if (!(x >= 1 && y >= 1 && x < w - 1 && y < h - 1)) continue;
+      const float l = warped[i - 1], r = warped[i + 1], u = warped[i - w], dn = warped[i + w], here = warped[i];
+      if (l + r + u + dn + here < -9999.9) continue;
+      const double g0 = r - l, g1 = dn - u;
+      const double sg0 = 0.25 * (g0 + (double)jx[i]), sg1 = 0.25 * (g1 + (double)jy[i]);
+      const double J0 = sg0, J1 = sg1, J2 = -(y - cy) * sg0 + (x - cx) * sg1;
+      const double diff = here - prev[i] + mean_off;
+      a[14] += diff * diff;
+      a[0] += diff * J0; a[1] += diff * J1; a[2] += diff * J2; a[3] += diff;
+      a[4] += J0 * J0; a[5] += J1 * J0; a[6] += J1 * J1; a[7] += J2 * J0; a[8] += J2 * J1; a[9] += J2 * J2;
+      a[10] += J0; a[11] += J1; a[12] += J2; a[13] += 1.0;
+    }
+#pragma unroll
+    for (int q = 0; q < 15; q++) a[q] = warp_sum(a[q]);
+    if (lane == 0)
+#pragma unroll
+      for (int q = 0; q < 15; q++) red[warp][q] = a[q];
+    __syncthreads();
+    if (tid < 15) {
+      double v = 0;
+      for (int q = 0; q < 8; q++) v += red[q][tid];
+      fin[tid] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double M[16], upd[4];
+      int v = 0;
+      for (int j = 0; j < 4; j++)
+        for (int i = 0; i <= j; i++) { M[4 * j + i] = fin[4 + v]; M[4 * i + j] = fin[4 + v]; v++; }
+      ldlt_factor<4>(M);
+      ldlt_backsub<4>(M, fin, upd);
+      Se2 u;
+      u.tx = -upd[0]; u.ty = -upd[1];
+      u.c = cos(-upd[2]); u.s = sin(-upd[2]);
+      c2c_s = se2_mul(c2c, u);
+      mean_off_s = mean_off - upd[3];
+      final_score = fin[14];
+    }
+    __syncthreads();
+  }
+  if (tid != 0) return;
+  // ---- SE3fromSE2 (ImageProcess.cc:421-473) and its logarithm
+  const Se2 se2 = c2c_s;
+  const CamModel& cam = sb.cam_small;
+  double turned[2][2], orig[2][3];
+  const double off[2] = {5.0, -5.0};
+  for (int i = 0; i < 2; i++) {
+    turned[i][0] = (double)cx + (se2.c * off[i] + se2.tx);
+    turned[i][1] = (double)cy + (se2.s * off[i] + se2.ty);
+    const double d0 = (((double)cx + off[i]) - cam.center[0]) * cam.inv_focal[0];
+    const double d1 = ((double)cy - cam.center[1]) * cam.inv_focal[1];
+    const double dr = sqrt(d0 * d0 + d1 * d1);
+    const double rr = cam.w == 0.0 ? dr : tan(dr * cam.w) * cam.one_over_tan2;  // invrtrans (ATANCamera.h:151-157)
+    const double f = dr > 0.01 ? rr / dr : 1.0;
+    orig[i][0] = f * d0; orig[i][1] = f * d1; orig[i][2] = 1.0;
+  }
+  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  for (int it = 0; it < 3; it++) {
+    double C[9] = {10, 0, 0, 0, 10, 0, 0, 0, 10}, b[3] = {0, 0, 0};
+    for (int i = 0; i < 2; i++) {
+      double vc[3];
+      so3_rotate(R, orig[i], vc);
+      const CamProj q = cam_project(cam, vc[0] / vc[2], vc[1] / vc[2]);
+      const double err[2] = {turned[i][0] - q.im[0], turned[i][1] - q.im[1]};
+      double dv[4];
+      cam_derivs(cam, q, dv);
+      const double ooz = 1.0 / vc[2];
+      const double gen[3][3] = {{0, -vc[2], vc[1]}, {vc[2], 0, -vc[0]}, {-vc[1], vc[0], 0}};
+      double Jr[2][3];
+      for (int m = 0; m < 3; m++) {
+        const double a0 = (gen[m][0] - vc[0] * gen[m][2] * ooz) * ooz, a1 = (gen[m][1] - vc[1] * gen[m][2] * ooz) * ooz;
+        Jr[0][m] = dv[0] * a0 + dv[1] * a1;
+        Jr[1][m] = dv[2] * a0 + dv[3] * a1;
+      }
+      for (int r = 0; r < 2; r++)
+        for (int aa = 0; aa < 3; aa++) {
+          for (int c = 0; c < 3; c++) C[3 * aa + c] += Jr[r][aa] * Jr[r][c];
+          b[aa] += err[r] * Jr[r][aa];
+        }
+    }
+    double x[3], E[9], N[9];
+    ldlt_factor<3>(C);
+    ldlt_backsub<3>(C, b, x);
+    so3_exp(x, E);
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) N[3 * r + c] = E[3 * r] * R[c] + E[3 * r + 1] * R[3 + c] + E[3 * r + 2] * R[6 + c];
+    for (int i = 0; i < 9; i++) R[i] = N[i];
+  }
+  double rot[3];
+  so3_ln(R, rot);
+  ctl.sbi_rot[0] = rot[0]; ctl.sbi_rot[1] = rot[1]; ctl.sbi_rot[2] = rot[2];
+  ctl.sbi_score = final_score;
+  ctl.sbi_idx = 1 - idx_prev;
+  ctl.sbi_valid = 1;
+}
+
+// =============================================================================================
 // Projection helpers (TrackerData::Project, Tracker.h:70-86)
 // =============================================================================================
 struct ProjOut { double v3cam[3]; double v2image[2]; bool in_image; bool reached_cam; CamProj q; };
@@ -430,11 +648,17 @@ __global__ void __launch_bounds__(1024) k_pvs_select(TrackerDev d) {
   const size_t gb = (size_t)s * cap;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
-    // mnFrame++, PredictPoseWithMotionModel (Tracker.cc:1012-1029, velocity only)
+    // mnFrame++, PredictPoseWithMotionModel (Tracker.cc:1012-1029)
     ctl.st.frame++;
     double ex[12], np[12];
     for (int i = 0; i < 12; i++) ctl.start_pose[i] = ctl.st.se3_cam_from_world[i];
-    se3_exp(ctl.st.velocity, ex);
+    double v6[6];
+    for (int i = 0; i < 6; i++) v6[i] = ctl.st.velocity[i];
+    if (d.prm.use_rotation_estimator) {  // mbUseSBIInit (Tracker.cc:1016-1027): rotation from k_sbi
+      v6[3] = ctl.sbi_rot[0]; v6[4] = ctl.sbi_rot[1]; v6[5] = ctl.sbi_rot[2];
+      v6[0] = 0.0; v6[1] = 0.0;
+    }
+    se3_exp(v6, ex);
     se3_mul(ex, ctl.start_pose, np);
     for (int i = 0; i < 12; i++) { pose[i] = np[i]; ctl.pose[i] = np[i]; }
     for (int l = 0; l < kLevels; l++) { running[l] = 0; ctl.attempted[l] = 0; ctl.found[l] = 0; }

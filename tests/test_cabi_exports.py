@@ -36,7 +36,7 @@ def test_oracle_mirrors_the_abi(oracle):
 
 def test_struct_layouts_match_header_sizes():
     import ctypes
-    assert ctypes.sizeof(capi.TrackerParams) == 8 * 4 + 3 * 8
+    assert ctypes.sizeof(capi.TrackerParams) == 8 * 4 + 3 * 8 + 2 * 4 + 8
     assert ctypes.sizeof(capi.TrackerState) == 21 * 8 + 4 * 4
     assert ctypes.sizeof(capi.TrackResult) == 14 * 8 + 24 * 4
     assert ctypes.sizeof(capi.BundleParams) == 2 * 4 + 2 * 8

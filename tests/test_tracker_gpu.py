@@ -50,6 +50,12 @@ def test_keyframe_batch_streams(oracle, product, seq640):
 
 
 def _setup(lib, kfs, m, S=1, **prm):
+    """The bit-exact per-frame comparisons below run with the velocity-only motion model: with the
+    SmallBlurryImage rotation estimator on, the predicted pose carries the ~1e-13 difference of the
+    estimator's parallel sums, and the bilinear->byte truncation of the coarse templates can then flip
+    a byte (the sensitivity test_libm_atan_variant_* documents).  The estimator has its own parity test
+    (test_sbi_rotation_estimator_matches_oracle) and is on by default everywhere else."""
+    prm.setdefault("use_rotation_estimator", 0)
     t = Tracker(lib, 640, 480, S, **prm)
     for k in kfs:
         t.add_keyframe(k)
@@ -227,7 +233,7 @@ def test_track_frames_1280x720(oracle, product):
     kfs, m = synth.build_map(frames, poses, detect_with(Tracker, oracle, Wd, Hd), cam, kf_indices=(0, 3), per_level=(300, 150, 60, 30))
     trk = []
     for lib in (oracle, product):
-        t = Tracker(lib, Wd, Hd, 1)
+        t = Tracker(lib, Wd, Hd, 1, use_rotation_estimator=0)
         for k in kfs:
             t.add_keyframe(k)
         t.set_map(0, m)
@@ -242,3 +248,30 @@ def test_track_frames_1280x720(oracle, product):
         assert list(ro.meas_found) == list(rp.meas_found) and sum(rp.meas_found) > 100
         assert np.allclose(np.array(ro.se3_cam_from_world), np.array(rp.se3_cam_from_world), atol=1e-9)
         p.set_state(0, state=o.get_state(0))  # continue from identical state
+
+
+@pytest.mark.gpu
+def test_sbi_rotation_estimator_matches_oracle(oracle, product, seq640, map640):
+    """k_sbi: the small blurry image is bit-identical to the oracle's, the ESM rotation estimate and
+    the pose predicted from it agree to 1e-9 (parallel sums), frame after frame."""
+    frames, poses = seq640
+    kfs, m = map640
+    trk = []
+    for lib in (oracle, product):
+        t = Tracker(lib, 640, 480, 1)
+        for k in kfs:
+            t.add_keyframe(k)
+        t.set_map(0, m)
+        t.set_state(0, pose12=synth.perturb_pose(poses[3], np.random.default_rng(9)), velocity=np.zeros(6), msd=0.0)
+        trk.append(t)
+    o, p = trk
+    for f in range(3, 9):
+        ro, rp = o.track_frames([frames[f]])[0], p.track_frames([frames[f]])[0]
+        (to, roto, so), (tp, rotp, sp) = o.get_sbi(0), p.get_sbi(0)
+        assert np.array_equal(to, tp), "small blurry image differs"
+        assert np.allclose(roto, rotp, atol=1e-9) and abs(so - sp) <= 1e-9 * max(1.0, abs(so))
+        assert np.allclose(np.array(ro.se3_cam_from_world), np.array(rp.se3_cam_from_world), atol=1e-9)
+        p.set_state(0, state=o.get_state(0))
+    # the estimator can be switched off (the velocity-only model of the kernel-only numbers)
+    t0 = Tracker(product, 640, 480, 1, use_rotation_estimator=0)
+    assert t0.params.use_rotation_estimator == 0
