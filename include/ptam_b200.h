@@ -183,6 +183,16 @@ int ptam_tracker_level_size(const ptam_tracker* t, int level, int* w, int* h);
 int ptam_tracker_get_points(ptam_tracker* t, int stream, int32_t* flags, int32_t* level,
                             double* v2_found, double* v2_image, int32_t* outlier_count,
                             int32_t* inlier_count);
+/* KeyFrame::MakeKeyFrame_Rest (KeyFrame.cc:61-82) for the current frame of one stream — what the map
+ * maker needs when the frame becomes a keyframe: fast_nonmax(im, vCorners, 10, vMaxCorners) on every
+ * level, then the Shi-Tomasi candidates (ImageProcess.cc:20-47; in_image_with_border 10, score >
+ * min_shi_tomasi_score = MapMaker.CandidateMinShiTomasiScore, 70 in code, 400 in settings.cfg:27).
+ * (The relocaliser's SmallBlurryImage of that function is the one ptam_tracker_get_sbi returns.)
+ * get_level_rest: vMaxCorners as (x,y) pairs in raster order (returns their number), vCandidates as
+ * irLevelPos pairs + dSTScore (their number in *n_cand). */
+int ptam_tracker_keyframe_rest(ptam_tracker* t, int stream, double min_shi_tomasi_score);
+int ptam_tracker_get_level_rest(ptam_tracker* t, int stream, int level, int32_t* max_corners_xy, int max_cap,
+                                int32_t* cand_xy, double* cand_score, int cand_cap, int* n_cand);
 /* SmallBlurryImage of the last frame of one stream (ImageProcess.cc:279-304): mimTemplate (w*h floats,
  * at most cap), the rotation estimate CalcSBIRotation gave against the previous frame (so3 log, 3
  * doubles) and its final ESM score.  Returns w*h of the small image ((W/8)/2 x (H/8)/2). */

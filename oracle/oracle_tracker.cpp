@@ -25,6 +25,9 @@ struct Level {
   std::vector<uint8_t> im;
   std::vector<IRef> corners;
   std::vector<int> lut;
+  std::vector<IRef> max_corners;           // vMaxCorners (KeyFrame.h:62)
+  std::vector<IRef> cand_pos;              // vCandidates[i].irLevelPos (KeyFrame.h:36-41,77)
+  std::vector<double> cand_score;          // vCandidates[i].dSTScore
   const uint8_t* row(int y) const { return im.data() + (size_t)y * w; }
   bool in_image_with_border(int x, int y, int b) const { return x >= b && y >= b && x < w - b && y < h - b; }
 };
@@ -147,6 +150,82 @@ struct TData {
 
 static inline double level_zero_pos(double p, int l) { return (p + 0.5) * (1 << l) - 0.5; }
 static inline double level_n_pos(double p, int l) { return (p + 0.5) / (1 << l) - 0.5; }
+
+// ---------------------------------------------------------------------------------------------
+// KeyFrame::MakeKeyFrame_Rest (KeyFrame.cc:61-82), SURVEY 8f rank 2: fast_nonmax(im, vCorners, 10,
+// vMaxCorners) and the Shi-Tomasi candidates.  (Its last two lines build the relocaliser's
+// SmallBlurryImage, which is sbi_make / sbi_make_jacs above.)
+// libCVD pieces restated (PARITY UNPINNED): fast_nonmax = fast_corner_score_9 followed by
+// nonmax_suppression.  The score is found by bisection on the threshold b in [barrier, 255): the
+// largest b at which the pixel is still a FAST-9 corner (>= 9 contiguous ring pixels all > p + b or
+// all < p - b); a corner is suppressed when one of its 8 neighbours is a corner with a strictly
+// greater score (equal scores both survive); output keeps raster order.
+// ---------------------------------------------------------------------------------------------
+static bool is_fast_corner_n(const Level& L, int x, int y, int b, int arc) {
+  static const int dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+  static const int dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+  const int p = L.row(y)[x];
+  for (int start = 0; start < 16; start++) {
+    bool allb = true, alld = true;
+    for (int k = 0; k < arc && (allb || alld); k++) {
+      const int v = L.row(y + dy[(start + k) & 15])[x + dx[(start + k) & 15]];
+      if (!(v > p + b)) allb = false;
+      if (!(v < p - b)) alld = false;
+    }
+    if (allb || alld) return true;
+  }
+  return false;
+}
+static int fast_corner_score_9(const Level& L, IRef c, int barrier) {
+  int bmin = barrier, bmax = 255, b = (bmax + bmin) / 2;
+  for (;;) {
+    if (is_fast_corner_n(L, c.x, c.y, b, 9)) bmin = b; else bmax = b;
+    if (bmin == bmax - 1 || bmin == bmax) return bmin;
+    b = (bmin + bmax) / 2;
+  }
+}
+// ImageProcess::ShiTomasiScoreAtPoint (ImageProcess.cc:20-47)
+static double shi_tomasi_score(const Level& L, int half, IRef c) {
+  double dXX = 0, dYY = 0, dXY = 0;
+  for (int y = c.y - half; y <= c.y + half; y++)
+    for (int x = c.x - half; x <= c.x + half; x++) {
+      const double dx = (double)L.row(y)[x + 1] - (double)L.row(y)[x - 1];
+      const double dy = (double)L.row(y + 1)[x] - (double)L.row(y - 1)[x];
+      dXX += dx * dx; dYY += dy * dy; dXY += dx * dy;
+    }
+  const int n = (2 * half + 1) * (2 * half + 1);
+  dXX = dXX / (2.0 * n); dYY = dYY / (2.0 * n); dXY = dXY / (2.0 * n);
+  return 0.5 * (dXX + dYY - std::sqrt((dXX + dYY) * (dXX + dYY) - 4 * (dXX * dYY - dXY * dXY)));
+}
+static void make_keyframe_rest(KeyFrame& kf, double min_st_score) {
+  for (int l = 0; l < PTAM_LEVELS; l++) {
+    Level& L = kf.lev[l];
+    const size_t n = L.corners.size();
+    std::vector<int> score(n);
+    std::vector<int> smap((size_t)L.w * L.h, -1);
+    for (size_t i = 0; i < n; i++) {
+      score[i] = fast_corner_score_9(L, L.corners[i], 10);
+      smap[(size_t)L.corners[i].y * L.w + L.corners[i].x] = score[i];
+    }
+    L.max_corners.clear(); L.cand_pos.clear(); L.cand_score.clear();
+    for (size_t i = 0; i < n; i++) {
+      const IRef c = L.corners[i];
+      bool keep = true;
+      for (int dy = -1; dy <= 1 && keep; dy++)
+        for (int dx = -1; dx <= 1; dx++) {
+          if (!dx && !dy) continue;
+          const int x = c.x + dx, y = c.y + dy;
+          if (x < 0 || y < 0 || x >= L.w || y >= L.h) continue;
+          if (smap[(size_t)y * L.w + x] > score[i]) { keep = false; break; }
+        }
+      if (!keep) continue;
+      L.max_corners.push_back(c);
+      if (!L.in_image_with_border(c.x, c.y, 10)) continue;
+      const double st = shi_tomasi_score(L, 3, c);
+      if (st > min_st_score) { L.cand_pos.push_back(c); L.cand_score.push_back(st); }
+    }
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // SmallBlurryImage + rotation estimator: SmallBlurryImage::MakeFromKF
@@ -887,6 +966,26 @@ int orc_tracker_get_level(void* tp, int stream, int level, uint8_t* pixels, int3
     for (size_t i = 0; i < L.corners.size() && (int)i < cap; i++) { corners_xy[2 * i] = L.corners[i].x; corners_xy[2 * i + 1] = L.corners[i].y; }
   if (row_lut) for (size_t i = 0; i < L.lut.size(); i++) row_lut[i] = L.lut[i];
   return (int)L.corners.size();
+}
+int orc_tracker_keyframe_rest(void* tp, int stream, double min_shi_tomasi_score) {
+  Tracker* t = (Tracker*)tp;
+  if (stream < 0 || stream >= t->S) return PTAM_ERR_INVALID;
+  orc::make_keyframe_rest(t->streams[stream].cur, min_shi_tomasi_score);
+  return PTAM_OK;
+}
+int orc_tracker_get_level_rest(void* tp, int stream, int level, int32_t* max_xy, int max_cap, int32_t* cand_xy, double* cand_score,
+                               int cand_cap, int* n_cand) {
+  Tracker* t = (Tracker*)tp;
+  if (stream < 0 || stream >= t->S || level < 0 || level >= PTAM_LEVELS) return PTAM_ERR_INVALID;
+  const orc::Level& L = t->streams[stream].cur.lev[level];
+  if (max_xy)
+    for (size_t i = 0; i < L.max_corners.size() && (int)i < max_cap; i++) { max_xy[2 * i] = L.max_corners[i].x; max_xy[2 * i + 1] = L.max_corners[i].y; }
+  for (size_t i = 0; i < L.cand_pos.size() && (int)i < cand_cap; i++) {
+    if (cand_xy) { cand_xy[2 * i] = L.cand_pos[i].x; cand_xy[2 * i + 1] = L.cand_pos[i].y; }
+    if (cand_score) cand_score[i] = L.cand_score[i];
+  }
+  if (n_cand) *n_cand = (int)L.cand_pos.size();
+  return (int)L.max_corners.size();
 }
 int orc_tracker_get_points(void* tp, int stream, int32_t* flags, int32_t* level, double* v2_found, double* v2_image,
                            int32_t* outl, int32_t* inl) {

@@ -72,6 +72,7 @@ TRACKER_SYMBOLS = [
     "tracker_add_keyframe", "tracker_set_map", "tracker_set_state", "tracker_get_state",
     "tracker_make_keyframes", "tracker_track_frames", "tracker_synchronize", "tracker_get_level",
     "tracker_level_size", "tracker_get_points", "tracker_get_templates", "tracker_get_sbi",
+    "tracker_keyframe_rest", "tracker_get_level_rest",
     "tracker_get_iteration_set",
 ]
 BUNDLE_SYMBOLS = [
@@ -161,6 +162,8 @@ class Lib:
             "tracker_get_points": (i, [vp, i, P(C.c_int32), P(C.c_int32), P(d), P(d), P(C.c_int32), P(C.c_int32)]),
             "tracker_get_templates": (i, [vp, i, P(C.c_uint8), P(C.c_int32)]),
             "tracker_get_sbi": (i, [vp, i, P(C.c_float), i, P(d), P(d)]),
+            "tracker_keyframe_rest": (i, [vp, i, d]),
+            "tracker_get_level_rest": (i, [vp, i, i, P(C.c_int32), i, P(C.c_int32), P(d), i, P(i)]),
             "tracker_get_iteration_set": (i, [vp, i, P(C.c_int32), i]),
             "global_last_error": (C.c_char_p, []),
             "bundle_default_params": (None, [P(BundleParams)]),
@@ -413,6 +416,19 @@ class Tracker:
         t, s = np.zeros((n, 64), np.uint8), np.zeros((n, 2), np.int32)
         self._chk(self.lib.fn("tracker_get_templates")(self.h, stream, _bp(t), _ip(s)))
         return t, s
+
+    def keyframe_rest(self, stream, min_shi_tomasi_score=70.0):
+        """KeyFrame::MakeKeyFrame_Rest for the stream's current frame; returns per level
+        (vMaxCorners (n,2) int32, candidate positions (m,2) int32, candidate Shi-Tomasi scores (m,))."""
+        self._chk(self.lib.fn("tracker_keyframe_rest")(self.h, stream, float(min_shi_tomasi_score)))
+        out = []
+        for l in range(LEVELS):
+            nc = C.c_int()
+            nm = self._chk(self.lib.fn("tracker_get_level_rest")(self.h, stream, l, None, 0, None, None, 0, C.byref(nc)))
+            mx, cx, cs = np.zeros((max(nm, 1), 2), np.int32), np.zeros((max(nc.value, 1), 2), np.int32), np.zeros(max(nc.value, 1))
+            self._chk(self.lib.fn("tracker_get_level_rest")(self.h, stream, l, _ip(mx), nm, _ip(cx), _dp(cs), nc.value, C.byref(nc)))
+            out.append((mx[:nm], cx[:nc.value], cs[:nc.value]))
+        return out
 
     def get_sbi(self, stream):
         """(mimTemplate as (h, w) float32, so3 rotation estimate (3,), final ESM score) of the last frame."""

@@ -83,6 +83,12 @@ struct ptam_tracker {
   DevBuf<int2> center;
   DevBuf<int4> geo;
   DevBuf<float> sbi_tmpl;
+  // MakeKeyFrame_Rest scratch (one stream at a time; allocated on first use)
+  DevBuf<uint8_t> rest_smap;
+  DevBuf<int2> rest_max, rest_cand;
+  DevBuf<double> rest_cand_score;
+  DevBuf<int> rest_counts;
+  int rest_stream = -1;
   size_t sbi_smem = 0;
   DevBuf<uint8_t> tmpl;
   // pinned staging
@@ -109,7 +115,7 @@ struct ptam_tracker {
     if (stream) cudaStreamSynchronize(stream);
     for (auto p : kf_bufs) cudaFree(p);
     pyr.free(); corners.free(); lut.free(); mask.free(); ctl.free(); pt_count.free(); kf_ptrs.free();
-    world.free(); right.free(); down.free(); last_warp.free(); m2buf.free(); geo.free(); sbi_tmpl.free(); v3cam.free(); v2image.free(); derivs.free();
+    world.free(); right.free(); down.free(); last_warp.free(); m2buf.free(); geo.free(); sbi_tmpl.free(); rest_smap.free(); rest_max.free(); rest_cand.free(); rest_cand_score.free(); rest_counts.free(); v3cam.free(); v2image.free(); derivs.free();
     warp_inv.free(); v2found.free(); sin_.free(); J.free(); e2.free(); src_kf.free(); src_level.free();
     tsum.free(); tsumsq.free(); flags.free(); level.free(); search_level.free(); outliers.free(); inliers.free();
     pvs.free(); iter_idx.free(); center.free(); tmpl.free();
@@ -313,6 +319,7 @@ struct ptam_tracker {
   }
 
   int launch_keyframe(const TrackerDev& d, bool collect = true) {
+    rest_stream = -1;  // MakeKeyFrame_Rest results belong to the previous frame
     const LevelDesc& L0 = d.g.lev[0];
     dim3 gp((L0.w + 63) / 64, (L0.h + 63) / 64, S);
     pbegin(0); k_pyramid<<<gp, 256, 0, stream>>>(d); pend(0);
@@ -638,6 +645,53 @@ int ptam_tracker_get_points(ptam_tracker* t, int stream, int32_t* flags, int32_t
     if (v2_image && !(f & F_IN_PVS)) v2_image[2 * i] = v2_image[2 * i + 1] = 0;
   }
   return n;
+}
+
+int ptam_tracker_keyframe_rest(ptam_tracker* t, int stream, double min_shi_tomasi_score) {
+  cudaSetDevice(t->device);
+  if (stream < 0 || stream >= t->S) { t->set_error("bad stream"); return PTAM_ERR_INVALID; }
+  if (!t->dev.src.l0) { t->set_error("no frame processed yet"); return PTAM_ERR_INVALID; }
+  const Geom& g = t->dev.g;
+  if (!t->rest_smap.p) {
+    PTAM_CUDA_TRY(t, t->rest_smap.alloc(g.pyr_bytes));
+    PTAM_CUDA_TRY(t, t->rest_max.alloc(g.corner_stride));
+    PTAM_CUDA_TRY(t, t->rest_cand.alloc(g.corner_stride));
+    PTAM_CUDA_TRY(t, t->rest_cand_score.alloc(g.corner_stride));
+    PTAM_CUDA_TRY(t, t->rest_counts.alloc(8));
+  }
+  RestDev r{t->rest_smap.p, t->rest_max.p, t->rest_cand.p, t->rest_cand_score.p, t->rest_counts.p, min_shi_tomasi_score};
+  PTAM_CUDA_TRY(t, cudaMemsetAsync(t->rest_smap.p, 0, g.pyr_bytes, t->stream));
+  // the corner counts live on the device; this call is not on the per-frame path, so read them back
+  StreamCtl c;
+  PTAM_CUDA_TRY(t, cudaMemcpyAsync(&c, &t->ctl.p[stream], sizeof(c), cudaMemcpyDeviceToHost, t->stream));
+  PTAM_CUDA_TRY(t, cudaStreamSynchronize(t->stream));
+  for (int l = 0; l < kLevels; l++)
+    if (c.n_corners[l] > 0) { k_rest_score<<<(c.n_corners[l] + 255) / 256, 256, 0, t->stream>>>(t->dev, r, stream, l); t->launches++; }
+  k_rest_select<<<kLevels, 1024, 0, t->stream>>>(t->dev, r, stream);
+  t->launches++;
+  PTAM_CUDA_TRY(t, cudaGetLastError());
+  PTAM_CUDA_TRY(t, cudaStreamSynchronize(t->stream));
+  t->rest_stream = stream;
+  return PTAM_OK;
+}
+
+int ptam_tracker_get_level_rest(ptam_tracker* t, int stream, int level, int32_t* max_xy, int max_cap, int32_t* cand_xy,
+                                double* cand_score, int cand_cap, int* n_cand) {
+  cudaSetDevice(t->device);
+  if (stream < 0 || stream >= t->S || level < 0 || level >= kLevels) { t->set_error("bad stream / level"); return PTAM_ERR_INVALID; }
+  if (t->rest_stream != stream) { t->set_error("ptam_tracker_keyframe_rest has not been run for this stream's current frame"); return PTAM_ERR_INVALID; }
+  int counts[8];
+  PTAM_CUDA_TRY(t, cudaMemcpy(counts, t->rest_counts.p, sizeof(counts), cudaMemcpyDeviceToHost));
+  const LevelDesc& L = t->dev.g.lev[level];
+  const int nm = counts[level], nc = counts[4 + level];
+  if (max_xy && max_cap > 0 && nm > 0)
+    PTAM_CUDA_TRY(t, cudaMemcpy(max_xy, t->rest_max.p + L.corner_off, sizeof(int2) * std::min(nm, max_cap), cudaMemcpyDeviceToHost));
+  if (cand_xy && cand_cap > 0 && nc > 0)
+    PTAM_CUDA_TRY(t, cudaMemcpy(cand_xy, t->rest_cand.p + L.corner_off, sizeof(int2) * std::min(nc, cand_cap), cudaMemcpyDeviceToHost));
+  if (cand_score && cand_cap > 0 && nc > 0)
+    PTAM_CUDA_TRY(t, cudaMemcpy(cand_score, t->rest_cand_score.p + L.corner_off, sizeof(double) * std::min(nc, cand_cap), cudaMemcpyDeviceToHost));
+  if (n_cand) *n_cand = nc;
+  return nm;
 }
 
 int ptam_tracker_get_sbi(ptam_tracker* t, int stream, float* tmpl, int cap, double* rot3, double* score) {

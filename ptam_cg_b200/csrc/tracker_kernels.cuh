@@ -614,6 +614,118 @@ __global__ void __launch_bounds__(256) k_sbi(TrackerDev d) {
 }
 
 // =============================================================================================
+// KeyFrame::MakeKeyFrame_Rest (KeyFrame.cc:61-82) for one stream's current frame:
+//   k_rest_score   thread per FAST corner: libCVD fast_corner_score_9 in closed form — the largest
+//                  threshold b in [10, 255) at which the pixel is still a FAST-9 corner is
+//                  max over the 16 arcs of 9 of min(ring - p) (or of min(p - ring)), minus one —
+//                  written to a per-pixel score map (score + 1; 0 = no corner);
+//   k_rest_select  one CTA per level, corners in raster order: nonmax_suppression (dropped when an
+//                  8-neighbour corner has a strictly greater score), then ShiTomasiScoreAtPoint
+//                  (ImageProcess.cc:20-47) for the survivors 10 px inside the image; both lists are
+//                  compacted in order.
+// =============================================================================================
+struct RestDev {
+  uint8_t* smap;        // score map, pyramid geometry (LevelDesc::img_off / pitch)
+  int2* max_corners;    // per level at LevelDesc::corner_off
+  int2* cand_pos;
+  double* cand_score;
+  int* counts;          // [0..3] n_max per level, [4..7] n_candidates per level
+  double min_st_score;
+};
+
+__global__ void __launch_bounds__(256) k_rest_score(TrackerDev d, RestDev r, int s, int l) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.ctl[s].n_corners[l]) return;
+  const LevelDesc& L = d.g.lev[l];
+  int pitch;
+  const uint8_t* im = level_image(d, s, l, pitch);
+  const int2 c = d.corners[(size_t)s * d.g.corner_stride + L.corner_off + i];
+  const uint8_t* pc = im + (size_t)c.y * pitch + c.x;
+  const int p = *pc;
+  const int dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+  const int dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+  int db[16];
+#pragma unroll
+  for (int j = 0; j < 16; j++) db[j] = (int)pc[dy[j] * pitch + dx[j]] - p;
+  int mb = -256, md = -256;
+#pragma unroll
+  for (int st = 0; st < 16; st++) {
+    int lo = 256, hi = -256;
+#pragma unroll
+    for (int k = 0; k < 9; k++) { const int v = db[(st + k) & 15]; lo = min(lo, v); hi = max(hi, v); }
+    mb = max(mb, lo);    // brightest arc: all ring - p >= lo
+    md = max(md, -hi);   // darkest arc: all p - ring >= -hi
+  }
+  int score = max(mb, md) - 1;
+  score = max(10, min(score, 254));  // the bisection of fast_corner_score_9 never leaves [barrier, 254]
+  r.smap[L.img_off + (size_t)c.y * L.pitch + c.x] = (uint8_t)(score + 1);
+}
+
+__global__ void __launch_bounds__(1024) k_rest_select(TrackerDev d, RestDev r, int s) {
+  __shared__ int wk[32], wc[32];
+  __shared__ int base_k, base_c;
+  const int l = blockIdx.x;
+  const LevelDesc& L = d.g.lev[l];
+  int pitch;
+  const uint8_t* im = level_image(d, s, l, pitch);
+  const int n = d.ctl[s].n_corners[l];
+  const int2* corners = d.corners + (size_t)s * d.g.corner_stride + L.corner_off;
+  const uint8_t* smap = r.smap + L.img_off;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { base_k = 0; base_c = 0; }
+  __syncthreads();
+  for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+    const int i = i0 + threadIdx.x;
+    bool keep = false, cand = false;
+    int2 c = make_int2(0, 0);
+    double st = 0.0;
+    if (i < n) {
+      c = corners[i];
+      const int own = smap[(size_t)c.y * L.pitch + c.x];
+      keep = true;
+#pragma unroll
+      for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+        for (int dx = -1; dx <= 1; dx++) {
+          if (!dx && !dy) continue;
+          const int x = c.x + dx, y = c.y + dy;
+          if (x < 0 || y < 0 || x >= L.w || y >= L.h) continue;
+          if ((int)smap[(size_t)y * L.pitch + x] > own) keep = false;
+        }
+      if (keep && c.x >= 10 && c.y >= 10 && c.x < L.w - 10 && c.y < L.h - 10) {
+        double dXX = 0, dYY = 0, dXY = 0;
+        for (int y = c.y - 3; y <= c.y + 3; y++)
+          for (int x = c.x - 3; x <= c.x + 3; x++) {
+            const uint8_t* q = im + (size_t)y * pitch + x;
+            const double gx = (double)q[1] - (double)q[-1];
+            const double gy = (double)q[pitch] - (double)q[-pitch];
+            dXX += gx * gx; dYY += gy * gy; dXY += gx * gy;
+          }
+        dXX = dXX / (2.0 * 49); dYY = dYY / (2.0 * 49); dXY = dXY / (2.0 * 49);
+        st = 0.5 * (dXX + dYY - sqrt((dXX + dYY) * (dXX + dYY) - 4 * (dXX * dYY - dXY * dXY)));
+        cand = st > r.min_st_score;
+      }
+    }
+    const unsigned bk = __ballot_sync(kFull, keep), bc = __ballot_sync(kFull, cand);
+    if (lane == 0) { wk[warp] = __popc(bk); wc[warp] = __popc(bc); }
+    __syncthreads();
+    int ok = base_k, oc = base_c;
+    for (int q = 0; q < warp; q++) { ok += wk[q]; oc += wc[q]; }
+    const unsigned lt = (1u << lane) - 1u;
+    if (keep) r.max_corners[L.corner_off + ok + __popc(bk & lt)] = c;
+    if (cand) { const int o = oc + __popc(bc & lt); r.cand_pos[L.corner_off + o] = c; r.cand_score[L.corner_off + o] = st; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tk = 0, tc = 0;
+      for (int q = 0; q < (int)(blockDim.x >> 5); q++) { tk += wk[q]; tc += wc[q]; }
+      base_k += tk; base_c += tc;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { r.counts[l] = base_k; r.counts[4 + l] = base_c; }
+}
+
+// =============================================================================================
 // Projection helpers (TrackerData::Project, Tracker.h:70-86)
 // =============================================================================================
 struct ProjOut { double v3cam[3]; double v2image[2]; bool in_image; bool reached_cam; CamProj q; };

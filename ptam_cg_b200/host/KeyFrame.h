@@ -27,10 +27,18 @@ struct Measurement {  // KeyFrame.h:44-50
   enum { SRC_TRACKER, SRC_REFIND, SRC_ROOT, SRC_TRAIL, SRC_EPIPOLAR } Source;
 };
 
+struct Candidate {  // KeyFrame.h:36-41
+  CVD::ImageRef irLevelPos;
+  TooN::Vector<2> v2RootPos;
+  double dSTScore;
+};
+
 struct Level {  // KeyFrame.h:55-125
   CVD::Image<CVD::byte> im;
   std::vector<CVD::ImageRef> vCorners;
   std::vector<int> vCornerRowLUT;
+  std::vector<CVD::ImageRef> vMaxCorners;
+  std::vector<Candidate> vCandidates;
   static int LevelScale(int nLevel) { return 1 << nLevel; }
   static double LevelZeroPos(double dLevelPos, int nLevel) { return (dLevelPos + 0.5) * LevelScale(nLevel) - 0.5; }
   static double LevelNPos(double dRootPos, int nLevel) { return (dRootPos + 0.5) / LevelScale(nLevel) - 0.5; }
@@ -82,6 +90,30 @@ struct KeyFrame {  // KeyFrame.h:130-150
     const uint8_t* ptrs[1] = {im.data()};
     if (ptam_tracker_make_keyframes(t, ptrs, im.row_stride()) != PTAM_OK) throw std::runtime_error(ptam_tracker_last_error(t));
     for (int l = 0; l < LEVELS; l++) FetchLevel(t, 0, l);
+  }
+
+  // KeyFrame.cc:61-82: FAST non-max suppression and Shi-Tomasi candidates on the device
+  // (MapMaker.CandidateMinShiTomasiScore: 70 in code, 400 in the shipped settings.cfg:27).
+  // The level-0 image is sent again: the keyframe context may have processed other frames since.
+  void MakeKeyFrame_Rest(double dCandidateMinSTScore = 70.0) {
+    CVD::Image<CVD::byte>& im0 = aLevels[0].im;
+    ptam_tracker* t = keyframe_context(im0.size().x, im0.size().y);
+    const uint8_t* ptrs[1] = {im0.data()};
+    if (ptam_tracker_make_keyframes(t, ptrs, im0.row_stride()) != PTAM_OK) throw std::runtime_error(ptam_tracker_last_error(t));
+    if (ptam_tracker_keyframe_rest(t, 0, dCandidateMinSTScore) != PTAM_OK) throw std::runtime_error(ptam_tracker_last_error(t));
+    for (int l = 0; l < LEVELS; l++) {
+      Level& L = aLevels[l];
+      int nc = 0;
+      const int nm = ptam_tracker_get_level_rest(t, 0, l, nullptr, 0, nullptr, nullptr, 0, &nc);
+      if (nm < 0) throw std::runtime_error(ptam_tracker_last_error(t));
+      L.vMaxCorners.resize(nm);
+      std::vector<CVD::ImageRef> cpos(nc);
+      std::vector<double> cscore(nc);
+      ptam_tracker_get_level_rest(t, 0, l, reinterpret_cast<int32_t*>(L.vMaxCorners.data()), nm,
+                                  reinterpret_cast<int32_t*>(cpos.data()), cscore.data(), nc, &nc);
+      L.vCandidates.resize(nc);
+      for (int i = 0; i < nc; i++) { L.vCandidates[i].irLevelPos = cpos[i]; L.vCandidates[i].dSTScore = cscore[i]; }
+    }
   }
 };
 

@@ -105,6 +105,10 @@ static void run_tracker(const std::string& dir) {
   // corners of source keyframe 0, level 0 (raster order) for a bit-exact check
   std::vector<int32_t> c0;
   for (auto& c : kfs[0].aLevels[0].vCorners) { c0.push_back(c.x); c0.push_back(c.y); }
+  kfs[0].MakeKeyFrame_Rest();  // KeyFrame.cc:61-82 through the device
+  std::vector<int32_t> rest = {(int32_t)kfs[0].aLevels[0].vMaxCorners.size(), (int32_t)kfs[0].aLevels[0].vCandidates.size()};
+  for (auto& c : kfs[0].aLevels[0].vCandidates) { rest.push_back(c.irLevelPos.x); rest.push_back(c.irLevelPos.y); }
+  wr(dir, "trk_out_kf0_rest.i32", rest);
   wr(dir, "trk_out_poses.f64", poses); wr(dir, "trk_out_found.i32", counts); wr(dir, "trk_out_last.i32", last); wr(dir, "trk_out_kf0_corners.i32", c0);
   std::printf("tracker: %d frames, last frame %zu measurements\n", nfr, kf.mMeasurements.size());
 }

@@ -81,3 +81,6 @@ def test_host_classes_match_capi(product, tmp_path):
     assert list(last[1:]) == [len(t.get_level(0, l)[1]) for l in range(4)]
     det.make_keyframes([kfs[0]])
     assert np.array_equal(np.fromfile(tmp_path / "trk_out_kf0_corners.i32", np.int32).reshape(-1, 2), det.get_level(0, 0)[1])
+    mx, cx, _ = det.keyframe_rest(0)[0]
+    rest = np.fromfile(tmp_path / "trk_out_kf0_rest.i32", np.int32)
+    assert rest[0] == len(mx) and rest[1] == len(cx) and np.array_equal(rest[2:].reshape(-1, 2), cx)

@@ -285,3 +285,43 @@ def test_sbi_rotation_estimator_known_answers(oracle):
         t2.track_frames([f])
     assert np.allclose(np.array(t2.get_state(0).se3_cam_from_world), np.array(Tracker(oracle, W, H, 1).get_state(0).se3_cam_from_world))
     assert not np.allclose(np.array(st.se3_cam_from_world)[:9], np.eye(3).reshape(9), atol=1e-4)
+
+
+def test_keyframe_rest_known_answers(oracle):
+    """fast_nonmax + Shi-Tomasi candidates: max corners are a subset of the FAST
+    corners in raster order, no kept corner has a stronger FAST corner among its 8 neighbours, an
+    isolated corner survives, candidates are max corners >= 10 px inside with score above the threshold,
+    and the Shi-Tomasi score equals a numpy evaluation of ImageProcess.cc:20-47."""
+    W, H = 320, 240
+    tex = synth.make_texture(seed=5)
+    im = tex[300:300 + H, 500:500 + W].copy()
+    t = Tracker(oracle, W, H, 1)
+    t.make_keyframes([im])
+    rest = t.keyframe_rest(0, 70.0)
+    for l in range(4):
+        pix, corners, _ = t.get_level(0, l)
+        mx, cx, cs = rest[l]
+        cset = {tuple(c) for c in corners.tolist()}
+        assert all(tuple(c) in cset for c in mx.tolist())
+        order = [y * 100000 + x for x, y in mx.tolist()]
+        assert order == sorted(order)
+        mset = {tuple(c) for c in mx.tolist()}
+        assert all(tuple(c) in mset for c in cx.tolist())
+        hh, ww = pix.shape
+        for (x, y), sc in zip(cx.tolist(), cs.tolist()):
+            assert 10 <= x < ww - 10 and 10 <= y < hh - 10 and sc > 70.0
+            win = pix.astype(np.float64)
+            gx = win[y - 3:y + 4, x - 2:x + 5] - win[y - 3:y + 4, x - 4:x + 3]
+            gy = win[y - 2:y + 5, x - 3:x + 4] - win[y - 4:y + 3, x - 3:x + 4]
+            xx, yy, xy = (gx * gx).sum() / 98.0, (gy * gy).sum() / 98.0, (gx * gy).sum() / 98.0
+            ref = 0.5 * (xx + yy - np.sqrt((xx + yy) ** 2 - 4 * (xx * yy - xy * xy)))
+            assert abs(ref - sc) <= 1e-9 * max(1.0, abs(ref))
+        assert len(mx) <= len(corners) and (len(corners) == 0 or len(mx) > 0)
+    # an isolated bright square corner on a flat background is its own maximum
+    flat = np.full((64, 64), 50, np.uint8)
+    flat[30:, 30:] = 200
+    t2 = Tracker(oracle, 64, 64, 1)
+    t2.make_keyframes([flat])
+    c0 = t2.get_level(0, 0)[1]
+    m0 = t2.keyframe_rest(0, 0.0)[0][0]
+    assert 0 < len(m0) <= len(c0)

@@ -275,3 +275,23 @@ def test_sbi_rotation_estimator_matches_oracle(oracle, product, seq640, map640):
     # the estimator can be switched off (the velocity-only model of the kernel-only numbers)
     t0 = Tracker(product, 640, 480, 1, use_rotation_estimator=0)
     assert t0.params.use_rotation_estimator == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(640, 480), (200, 67)])
+def test_keyframe_rest_matches_oracle(oracle, product, shape):
+    """KeyFrame::MakeKeyFrame_Rest: vMaxCorners and Shi-Tomasi candidates bit-exact (positions, order,
+    f64 scores) on textured, random and flat images."""
+    w, h = shape
+    rng = np.random.default_rng(11)
+    tex = synth.make_texture(seed=3)
+    imgs = [tex[100:100 + h, 200:200 + w].copy(), rng.integers(0, 256, (h, w), dtype=np.uint8), np.full((h, w), 9, np.uint8)]
+    o, p = Tracker(oracle, w, h), Tracker(product, w, h)
+    for im in imgs:
+        o.make_keyframes([im]); p.make_keyframes([im])
+        for thr in (70.0, 400.0):
+            ro, rp = o.keyframe_rest(0, thr), p.keyframe_rest(0, thr)
+            for l in range(4):
+                assert np.array_equal(ro[l][0], rp[l][0]), f"vMaxCorners differ on level {l}"
+                assert np.array_equal(ro[l][1], rp[l][1]) and np.array_equal(ro[l][2], rp[l][2]), f"candidates differ on level {l}"
+    assert len(rp[0][0]) == 0  # flat image: nothing
