@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(1024) k_ba_select(BundleDev d, double min_sigm
         if (lane >= o) inc += v;
       }
       const int k0 = kk;
+      __syncwarp();  // every lane has read kk before the one owner rewrites it
       const int excl = inc - tot;
       if (k0 >= excl && k0 < inc) {
         int r = k0 - excl, q = 0;

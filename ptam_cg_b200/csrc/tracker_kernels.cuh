@@ -1262,6 +1262,7 @@ PTAM_DEV double block_select_kth(At at, int n, int kth, int* hist /*2 x 256*/, u
         if (lane >= o) inc += v;
       }
       const int kk = *sh_k;
+      __syncwarp();  // every lane has read *sh_k before the one owner rewrites it
       const int excl = inc - tot;
       if (kk >= excl && kk < inc) {  // exactly one lane
         int r = kk - excl, q = 0;
