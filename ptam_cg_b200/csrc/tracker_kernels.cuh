@@ -1363,7 +1363,13 @@ PTAM_DEV void pose_iterations(const TrackerDev& d, const Store& st, PoseShared& 
       if (it != 0) {
         if (nonlin) {  // ProjectAndDerivs (Tracker.h:89-94)
           ProjOut o;
-          project_point(d, pose, d.p.world + 3 * (gb + fidx[i]), o);
+          const size_t g = gb + fidx[i];
+          project_point(d, pose, d.p.world + 3 * g, o);
+          {  // Project() leaves bInImage behind (Tracker.h:72,85)
+            const int fl = d.p.flags[g];
+            const int nfl = o.in_image ? (fl | F_IN_IMAGE) : (fl & ~F_IN_IMAGE);
+            if (nfl != fl) d.p.flags[g] = nfl;
+          }
           st.v3(i, 0) = o.v3cam[0]; st.v3(i, 1) = o.v3cam[1]; st.v3(i, 2) = o.v3cam[2];
           if (o.reached_cam) {
             v2i[0] = o.v2image[0]; v2i[1] = o.v2image[1];

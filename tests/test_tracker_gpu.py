@@ -295,3 +295,32 @@ def test_keyframe_rest_matches_oracle(oracle, product, shape):
                 assert np.array_equal(ro[l][0], rp[l][0]), f"vMaxCorners differ on level {l}"
                 assert np.array_equal(ro[l][1], rp[l][1]) and np.array_equal(ro[l][2], rp[l][2]), f"candidates differ on level {l}"
     assert len(rp[0][0]) == 0  # flat image: nothing
+
+
+@pytest.mark.gpu
+def test_ragged_streams_and_large_found_set(oracle, product, seq640, map640):
+    """Streams of one batch with different map sizes (empty, small, and a 2000-point map whose found set
+    exceeds the 1024-point shared-memory working set of k_pose, so the global-memory path runs), with
+    MaxPatchesPerFrame raised accordingly."""
+    frames, poses = seq640
+    kfs, m = map640
+    n = len(m["src_kf"])
+    empty = {k: v[:0] for k, v in m.items()}
+    small = {k: v[:300] for k, v in m.items()}
+    big = {k: np.concatenate([v, v]) for k, v in m.items()}  # every point twice: 2n points
+    maps = [empty, small, big]
+    o = Tracker(oracle, 640, 480, 3, use_rotation_estimator=0, max_patches_per_frame=3000)
+    p = Tracker(product, 640, 480, 3, use_rotation_estimator=0, max_patches_per_frame=3000)
+    start = synth.perturb_pose(poses[6], np.random.default_rng(4))
+    for t in (o, p):
+        for k in kfs:
+            t.add_keyframe(k)
+        for s in range(3):
+            t.set_map(s, maps[s])
+            t.set_state(s, pose12=start, velocity=np.zeros(6), msd=0.0)
+    ims = [frames[6]] * 3
+    ro, rp = o.track_frames(ims), p.track_frames(ims)
+    assert sum(rp[0].meas_attempted) == 0
+    assert sum(rp[2].meas_found) > 1024, sum(rp[2].meas_found)
+    for s in range(3):
+        _compare_frame(o, p, ro[s], rp[s], s)
