@@ -366,8 +366,15 @@ int orc_bundle_add_measurements(void* b, int n, const int32_t* cam, const int32_
   return 0;
 }
 int orc_bundle_set_shard(void*, int, int world, void*) { return world == 1 ? 0 : PTAM_ERR_INVALID; }
-int orc_bundle_compute(void* b, const volatile unsigned char* abort_flag) { return ((Bundle*)b)->compute(abort_flag); }
-int orc_bundle_begin(void* b) { ((Bundle*)b)->begin(); return 0; }
+// the reference asserts on an empty measurement list (Tools.h:155); both libraries report it as an error
+int orc_bundle_compute(void* b, const volatile unsigned char* abort_flag) {
+  if (((Bundle*)b)->meas.empty()) { ((Bundle*)b)->err = "no measurements"; return PTAM_ERR_INVALID; }
+  return ((Bundle*)b)->compute(abort_flag);
+}
+int orc_bundle_begin(void* b) {
+  if (((Bundle*)b)->meas.empty()) { ((Bundle*)b)->err = "no measurements"; return PTAM_ERR_INVALID; }
+  ((Bundle*)b)->begin(); return 0;
+}
 int orc_bundle_lm_step(void* b, const volatile unsigned char* abort_flag) { return ((Bundle*)b)->lm_step(abort_flag) ? 0 : -1; }
 int orc_bundle_converged(const void* b) { return ((const Bundle*)b)->converged; }
 int orc_bundle_get_point(void* bp, int n, double* xyz) {

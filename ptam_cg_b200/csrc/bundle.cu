@@ -182,6 +182,7 @@ struct ptam_bundle {
     if (world > 1 && !comm) { set_error("sharded handle without a communicator: call ptam_bundle_init_shard first"); return PTAM_ERR_NCCL; }
     const int C = n_cams(), P = n_pts(), MG = n_meas();
     const int n = 6 * n_free;
+    if (MG == 0) { set_error("no measurements (the reference asserts on this, Tools.h:155)"); return PTAM_ERR_INVALID; }
     p_lo = 0; p_hi = P;
     if (world > 1) {
       std::vector<int32_t> plan(world + 1);

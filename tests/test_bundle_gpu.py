@@ -139,3 +139,46 @@ def test_bad_input_is_an_error(product):
     b.AddMeas(0, 0, [2, 2], 1.0)
     with pytest.raises(PtamError):
         b.Compute()
+
+
+def test_edge_graphs(oracle, product):
+    """Edges the reference code handles: several fixed cameras (MapMaker.cc:857-861), a point behind one
+    of its cameras (z <= 0 -> bad measurement, Bundle.cc:170-174), a NaN point (zeroed, Bundle.cc:70-74),
+    a point seen once, a camera without measurements, an all-fixed graph (no reduced system), an empty
+    graph (an error)."""
+    g = synth.make_ba_graph(8, 120, 480, seed=9)
+    g = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in g.items()}
+    g["cam_fixed"][[0, 3, 7]] = 1
+    g["points"][5] = np.nan                                   # zeroed on ingest
+    c0 = int(g["meas_cam"][g["meas_point"] == 9][0])
+    R, t = synth.se3_from12(g["cam_se3"][c0])
+    g["points"][9] = R.T @ (np.array([0.0, 0.0, -0.5]) - t)   # half a unit behind camera c0
+    keep = np.ones(len(g["meas_cam"]), bool)
+    idx11 = np.flatnonzero(g["meas_point"] == 11)
+    keep[idx11[1:]] = False                                   # point 11: a single observation
+    keep[g["meas_cam"] == 5] = False                          # camera 5: no measurements at all
+    for k in ("meas_cam", "meas_point", "meas_uv", "meas_sigma_sq"):
+        g[k] = g[k][keep]
+    o, p = _pair(oracle, product, g)
+    ao, ap = o.Compute(), p.Compute()
+    assert ao == ap
+    _same_stats(o.stats(), p.stats(), rtol=1e-7)
+    assert np.array_equal(o.GetOutlierMeasurements(), p.GetOutlierMeasurements())
+    np.testing.assert_allclose(p.get_points(), o.get_points(), atol=1e-6, equal_nan=True)
+    np.testing.assert_allclose(p.get_cameras(), o.get_cameras(), atol=1e-6)
+    for c in (0, 3, 7):
+        np.testing.assert_array_equal(p.GetCamera(c), g["cam_se3"][c])   # fixed cameras never move
+    # all cameras fixed: points still move, there is no reduced camera system
+    g2 = synth.make_ba_graph(4, 60, 200, seed=2)
+    g2 = dict(g2); g2["cam_fixed"] = np.ones(4, np.int32)
+    o, p = _pair(oracle, product, g2)
+    assert o.Compute() == p.Compute()
+    _same_stats(o.stats(), p.stats(), rtol=1e-7)
+    np.testing.assert_allclose(p.get_points(), o.get_points(), atol=1e-7)
+    # empty graph
+    for lib in (oracle, product):
+        b = Bundle(lib, 640, 480)
+        b.AddCamera(np.r_[np.eye(3).ravel(), 0, 0, 0], False)
+        b.AddPoint([0, 0, 1])
+        with pytest.raises(Exception):   # the reference asserts (Tools.h:155); here it is an error code
+            b.Compute()

@@ -324,3 +324,41 @@ def test_ragged_streams_and_large_found_set(oracle, product, seq640, map640):
     assert sum(rp[2].meas_found) > 1024, sum(rp[2].meas_found)
     for s in range(3):
         _compare_frame(o, p, ro[s], rp[s], s)
+
+
+@pytest.mark.gpu
+def test_scale_change_and_lost_frames(oracle, product, seq640, map640):
+    """Search-level selection / template rejection under a scale change (camera 2.2x higher and 0.55x
+    lower than the keyframes: det of the warp leaves [0.25, 3] for many points, PatchFinder.cc:70-81),
+    then frames of noise: tracking quality goes BAD and mnLostFrames counts up (Tracker.cc:1062-1107)."""
+    frames, poses = seq640
+    kfs, m = map640
+    tex = synth.make_texture()
+    cam = synth.AtanCamera(640, 480)
+    for scale in (2.2, 0.55):
+        R, t = synth.se3_from12(poses[8])
+        c = -R.T @ t
+        c2 = c.copy(); c2[2] *= scale
+        pose = synth.se3_to12(R, -R @ c2)
+        im = synth.render_frame(tex, cam, pose)
+        o, p = _setup(oracle, kfs, m), _setup(product, kfs, m)
+        for trk in (o, p):
+            trk.set_state(0, pose12=synth.perturb_pose(pose, np.random.default_rng(2)), velocity=np.zeros(6), msd=0.0)
+        ro, rp = o.track_frames([im])[0], p.track_frames([im])[0]
+        _compare_frame(o, p, ro, rp)
+        lv = o.get_points(0)["level"]
+        assert len(set(lv[lv >= 0].tolist())) >= 2      # several search levels in play
+        assert ((o.get_points(0)["flags"] & 32) != 0).sum() > 0   # some templates rejected
+    rng = np.random.default_rng(0)
+    o, p = _setup(oracle, kfs, m), _setup(product, kfs, m)
+    start = synth.perturb_pose(poses[5], np.random.default_rng(7))
+    for trk in (o, p):
+        trk.set_state(0, pose12=start, velocity=np.zeros(6), msd=0.0)
+    for k in range(4):
+        noise = rng.integers(0, 256, (480, 640), dtype=np.uint8)
+        ro, rp = o.track_frames([noise])[0], p.track_frames([noise])[0]
+        _compare_frame(o, p, ro, rp)
+        so, sp = o.get_state(0), p.get_state(0)
+        assert (so.tracking_quality, so.lost_frames) == (sp.tracking_quality, sp.lost_frames)
+        p.set_state(0, state=so)
+    assert so.tracking_quality == 0 and so.lost_frames >= 3
