@@ -183,6 +183,18 @@ int ptam_tracker_level_size(const ptam_tracker* t, int level, int* w, int* h);
 int ptam_tracker_get_points(ptam_tracker* t, int stream, int32_t* flags, int32_t* level,
                             double* v2_found, double* v2_image, int32_t* outlier_count,
                             int32_t* inlier_count);
+/* MapMaker::ReFindInSingleKeyFrame / ReFind_Common (MapMaker.cc:943-1040), one keyframe per stream:
+ * images[s] becomes stream s's current frame (MakeKeyFrame_Lite), se3 + 12 s is that keyframe's
+ * se3CfromW, and every point of stream s's map is looked for in it: projection, warp matrix and
+ * level, template (always re-made), FindPatchCoarse with search radius 4, sub-pixel refinement on
+ * levels > 0 (its convergence is not checked, as in the reference).  Results per point through
+ * ptam_tracker_get_points: PTAM_PT_FOUND / PTAM_PT_SUBPIX, level, v2_found (= Measurement::v2RootPos,
+ * Source SRC_REFIND); a projected point without PTAM_PT_FOUND is one the reference adds to
+ * sNeverRetryKFs.  The call overwrites the handle's per-point search state and template cache and
+ * leaves the tracking state (pose, velocity) alone: give the map maker a handle of its own, as the
+ * reference gives it its own PatchFinder (MapMaker.cc:977). */
+int ptam_tracker_refind_in_keyframes(ptam_tracker* t, const uint8_t* const* images, int stride,
+                                     const double* se3_cam_from_world /* n_streams * 12 */);
 /* KeyFrame::MakeKeyFrame_Rest (KeyFrame.cc:61-82) for the current frame of one stream — what the map
  * maker needs when the frame becomes a keyframe: fast_nonmax(im, vCorners, 10, vMaxCorners) on every
  * level, then the Shi-Tomasi candidates (ImageProcess.cc:20-47; in_image_with_border 10, score >

@@ -806,6 +806,47 @@ struct Tracker {
     }
   }
 
+  // MapMaker::ReFindInSingleKeyFrame / ReFind_Common (MapMaker.cc:943-1040): every map
+  // point of the stream is looked for in the keyframe that is the stream's current frame, whose pose
+  // is given.  The map maker's PatchFinder is its own (static, MapMaker.cc:977): consecutive calls are
+  // for different points, so the template is always re-made; the return value of
+  // CalcSearchLevelAndWarpMatrix is ignored there, only TemplateBad() after MakeTemplateCoarseCont
+  // (= source pixels outside the source image) rejects.  A point that is not found is one the
+  // reference puts into sNeverRetryKFs.
+  void refind(Stream& s, const SE3& pose) {
+    for (int i = 0; i < 4; i++) s.attempted[i] = s.found[i] = 0;
+    Camera::Proj last{};
+    for (size_t i = 0; i < s.pts.size(); i++) {
+      TData& d = s.td[i];
+      d.in_pvs = false; d.searched = false; d.found = false; d.did_subpix = false;
+      d.n_search_level = -1;
+      d.has_template = false; d.template_bad = false;
+      project(d, s.pts[i], pose, last);
+      if (!d.in_image) continue;
+      cam.derivs(last, d.derivs);
+      calc_search_level(d, s.pts[i], pose);
+      d.template_bad = false;
+      d.n_search_level = d.search_level;
+      d.in_pvs = true;
+      make_template(d, s.pts[i]);
+      if (d.template_bad) continue;
+      s.attempted[d.search_level]++;
+      const bool f = find_patch_coarse(d, IRef{(int)d.v2image[0], (int)d.v2image[1]}, s.cur, 4);  // very tight search radius
+      d.searched = true;
+      if (!f) continue;
+      d.found = true;
+      s.found[d.search_level]++;
+      if (d.search_level > 0) {
+        d.did_subpix = true;
+        make_subpix_template(d);
+        iterate_subpix_to_convergence(d, s.cur, 8);  // result not checked (MapMaker.cc:1005-1007)
+        d.v2found[0] = d.subpix[0]; d.v2found[1] = d.subpix[1];
+      } else {
+        d.v2found[0] = d.coarse[0]; d.v2found[1] = d.coarse[1];
+      }
+    }
+  }
+
   void track_frame(Stream& s, const uint8_t* im, int stride) {
     make_keyframe_lite(s.cur, im, W, H, stride);
     // Update the small images for the rotation estimator (Tracker.cc:95-108)
@@ -966,6 +1007,14 @@ int orc_tracker_get_level(void* tp, int stream, int level, uint8_t* pixels, int3
     for (size_t i = 0; i < L.corners.size() && (int)i < cap; i++) { corners_xy[2 * i] = L.corners[i].x; corners_xy[2 * i + 1] = L.corners[i].y; }
   if (row_lut) for (size_t i = 0; i < L.lut.size(); i++) row_lut[i] = L.lut[i];
   return (int)L.corners.size();
+}
+int orc_tracker_refind_in_keyframes(void* tp, const uint8_t* const* images, int stride, const double* se3) {
+  Tracker* t = (Tracker*)tp;
+  for (int s = 0; s < t->S; s++) {
+    orc::make_keyframe_lite(t->streams[s].cur, images[s], t->W, t->H, stride);
+    t->refind(t->streams[s], orc::SE3::from12(se3 + 12 * s));
+  }
+  return PTAM_OK;
 }
 int orc_tracker_keyframe_rest(void* tp, int stream, double min_shi_tomasi_score) {
   Tracker* t = (Tracker*)tp;

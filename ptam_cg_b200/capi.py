@@ -72,7 +72,7 @@ TRACKER_SYMBOLS = [
     "tracker_add_keyframe", "tracker_set_map", "tracker_set_state", "tracker_get_state",
     "tracker_make_keyframes", "tracker_track_frames", "tracker_synchronize", "tracker_get_level",
     "tracker_level_size", "tracker_get_points", "tracker_get_templates", "tracker_get_sbi",
-    "tracker_keyframe_rest", "tracker_get_level_rest",
+    "tracker_keyframe_rest", "tracker_get_level_rest", "tracker_refind_in_keyframes",
     "tracker_get_iteration_set",
 ]
 BUNDLE_SYMBOLS = [
@@ -163,6 +163,7 @@ class Lib:
             "tracker_get_templates": (i, [vp, i, P(C.c_uint8), P(C.c_int32)]),
             "tracker_get_sbi": (i, [vp, i, P(C.c_float), i, P(d), P(d)]),
             "tracker_keyframe_rest": (i, [vp, i, d]),
+            "tracker_refind_in_keyframes": (i, [vp, P(vp), i, P(d)]),
             "tracker_get_level_rest": (i, [vp, i, i, P(C.c_int32), i, P(C.c_int32), P(d), i, P(i)]),
             "tracker_get_iteration_set": (i, [vp, i, P(C.c_int32), i]),
             "global_last_error": (C.c_char_p, []),
@@ -416,6 +417,12 @@ class Tracker:
         t, s = np.zeros((n, 64), np.uint8), np.zeros((n, 2), np.int32)
         self._chk(self.lib.fn("tracker_get_templates")(self.h, stream, _bp(t), _ip(s)))
         return t, s
+
+    def refind_in_keyframes(self, images, poses12):
+        """MapMaker::ReFindInSingleKeyFrame, one keyframe (image, se3CfromW) per stream; results via get_points."""
+        imgs, arr = self._image_ptrs(images)
+        p = _f64(poses12).reshape(self.S, 12)
+        self._chk(self.lib.fn("tracker_refind_in_keyframes")(self.h, arr, self.W, _dp(p)))
 
     def keyframe_rest(self, stream, min_shi_tomasi_score=70.0):
         """KeyFrame::MakeKeyFrame_Rest for the stream's current frame; returns per level

@@ -83,6 +83,7 @@ struct ptam_tracker {
   DevBuf<int2> center;
   DevBuf<int4> geo;
   DevBuf<float> sbi_tmpl;
+  DevBuf<double> refind_pose;
   // MakeKeyFrame_Rest scratch (one stream at a time; allocated on first use)
   DevBuf<uint8_t> rest_smap;
   DevBuf<int2> rest_max, rest_cand;
@@ -115,7 +116,7 @@ struct ptam_tracker {
     if (stream) cudaStreamSynchronize(stream);
     for (auto p : kf_bufs) cudaFree(p);
     pyr.free(); corners.free(); lut.free(); mask.free(); ctl.free(); pt_count.free(); kf_ptrs.free();
-    world.free(); right.free(); down.free(); last_warp.free(); m2buf.free(); geo.free(); sbi_tmpl.free(); rest_smap.free(); rest_max.free(); rest_cand.free(); rest_cand_score.free(); rest_counts.free(); v3cam.free(); v2image.free(); derivs.free();
+    world.free(); right.free(); down.free(); last_warp.free(); m2buf.free(); geo.free(); sbi_tmpl.free(); refind_pose.free(); rest_smap.free(); rest_max.free(); rest_cand.free(); rest_cand_score.free(); rest_counts.free(); v3cam.free(); v2image.free(); derivs.free();
     warp_inv.free(); v2found.free(); sin_.free(); J.free(); e2.free(); src_kf.free(); src_level.free();
     tsum.free(); tsumsq.free(); flags.free(); level.free(); search_level.free(); outliers.free(); inliers.free();
     pvs.free(); iter_idx.free(); center.free(); tmpl.free();
@@ -645,6 +646,31 @@ int ptam_tracker_get_points(ptam_tracker* t, int stream, int32_t* flags, int32_t
     if (v2_image && !(f & F_IN_PVS)) v2_image[2 * i] = v2_image[2 * i + 1] = 0;
   }
   return n;
+}
+
+int ptam_tracker_refind_in_keyframes(ptam_tracker* t, const uint8_t* const* images, int stride, const double* se3) {
+  cudaSetDevice(t->device);
+  if (!t->refind_pose.p) PTAM_CUDA_TRY(t, t->refind_pose.alloc((size_t)12 * t->S));
+  TrackerDev d;
+  int rc = use_host_frames(t, images, stride, d);
+  if (rc) return rc;
+  PTAM_CUDA_TRY(t, cudaMemcpyAsync(t->refind_pose.p, se3, sizeof(double) * 12 * t->S, cudaMemcpyHostToDevice, t->stream));
+  rc = t->launch_keyframe(d, false);
+  if (rc) return rc;
+  d.mode = 1;
+  d.refind_pose = t->refind_pose.p;
+  int maxn = 0;
+  for (int s = 0; s < t->S; s++) maxn = std::max(maxn, t->h_pt_count[s]);
+  k_pvs_select<<<t->S, 1024, 0, t->stream>>>(d);
+  t->launches++;
+  if (maxn > 0) {
+    k_search_prep<<<dim3((maxn + 127) / 128, t->S), 128, 0, t->stream>>>(d, 1);
+    k_search<<<dim3((maxn + 3) / 4, t->S), 128, 0, t->stream>>>(d, 1);
+    t->launches += 2;
+  }
+  PTAM_CUDA_TRY(t, cudaGetLastError());
+  PTAM_CUDA_TRY(t, cudaStreamSynchronize(t->stream));
+  return PTAM_OK;
 }
 
 int ptam_tracker_keyframe_rest(ptam_tracker* t, int stream, double min_shi_tomasi_score) {

@@ -112,6 +112,8 @@ struct TrackerDev {
   const int* pt_count;   // [S]
   PointArrays p;
   int S;
+  int mode;                    // 0: TrackFrame; 1: MapMaker::ReFindInSingleKeyFrame (MapMaker.cc:943-1040)
+  const double* refind_pose;   // [S][12] keyframe poses for mode 1
 };
 
 PTAM_DEV const uint8_t* level_image(const TrackerDev& d, int s, int l, int& pitch) {
@@ -759,7 +761,12 @@ __global__ void __launch_bounds__(1024) k_pvs_select(TrackerDev d) {
   const int cap = d.p.cap;
   const size_t gb = (size_t)s * cap;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && d.mode == 1) {
+    // ReFind: the pose is the keyframe's se3CfromW; no motion model, tracker state untouched
+    for (int i = 0; i < 12; i++) { pose[i] = d.refind_pose[12 * s + i]; ctl.pose[i] = pose[i]; }
+    for (int l = 0; l < kLevels; l++) { running[l] = 0; ctl.attempted[l] = 0; ctl.found[l] = 0; }
+    ctl.n_cand = 0;
+  } else if (threadIdx.x == 0) {
     // mnFrame++, PredictPoseWithMotionModel (Tracker.cc:1012-1029)
     ctl.st.frame++;
     double ex[12], np[12];
@@ -807,7 +814,9 @@ __global__ void __launch_bounds__(1024) k_pvs_select(TrackerDev d) {
         int sl = 0;
         while (det > 3 && sl < kLevels - 1) { sl++; det *= 0.25; }
         d.p.search_level[g] = sl;
-        if (det > 3 || det < 0.25) fl |= F_TEMPLATE_BAD;
+        if (d.mode == 1) {  // ReFind_Common ignores the level verdict; the template is always re-made
+          lvl = sl; fl = F_IN_IMAGE | F_IN_PVS;
+        } else if (det > 3 || det < 0.25) fl |= F_TEMPLATE_BAD;
         else { lvl = sl; fl |= F_IN_PVS; }
       }
       d.p.flags[g] = fl;
@@ -837,7 +846,16 @@ __global__ void __launch_bounds__(1024) k_pvs_select(TrackerDev d) {
     __syncthreads();
   }
   // ---- selection (Tracker.cc:485-611), identity shuffle --------------------------------------
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && d.mode == 1) {  // ReFind: every projected point is searched, fine stage only
+    int dst = 0, ns = 0;
+    for (int l = kLevels - 1; l >= 0; l--) {
+      ctl.n_pvs[l] = running[l];
+      if (running[l]) { seg_src[ns] = l; seg_off[ns] = 0; seg_n[ns] = running[l]; seg_dst[ns] = dst; dst += running[l]; ns++; }
+    }
+    ctl.n_coarse = 0; ctl.n_l3 = 0; ctl.n_fine = dst;
+    ctl.try_coarse = 0; ctl.coarse_range = 0; ctl.did_coarse = 0;
+    nseg = ns;
+  } else if (threadIdx.x == 0) {
     int n3 = running[3], n2 = running[2], n1 = running[1], n0 = running[0];
     for (int l = 0; l < kLevels; l++) ctl.n_pvs[l] = running[l];
     unsigned coarse_max = d.prm.coarse_max, coarse_range = d.prm.coarse_range;
@@ -948,7 +966,7 @@ __global__ void __launch_bounds__(128) k_search_prep(TrackerDev d, int stage) {
   // ---- FindPatchCoarse, the scalar part (PatchFinder.cc:160-191): search centre and range in level
   // coordinates (ir() truncation, C++ integer division), candidate index range from the row LUT
   {
-    const unsigned range = stage == 0 ? (unsigned)ctl.coarse_range : (ctl.did_coarse ? 5u : 10u);
+    const unsigned range = d.mode == 1 ? 4u : (stage == 0 ? (unsigned)ctl.coarse_range : (ctl.did_coarse ? 5u : 10u));
     const int scale = 1 << sl;
     const int posx = (int)d.p.v2image[2 * g] / scale, posy = (int)d.p.v2image[2 * g + 1] / scale;
     const unsigned r = (range + scale - 1) / scale;
@@ -990,8 +1008,10 @@ __global__ void __launch_bounds__(128) k_search(TrackerDev d, int stage) {
     range = ctl.did_coarse ? 5 : 10;
     subpix_its = k < ctl.n_coarse + ctl.n_l3 ? 8 : 0;
   }
+  const bool refind = d.mode == 1;
   const double v2image[2] = {d.p.v2image[2 * g], d.p.v2image[2 * g + 1]};  // re-projected by k_search_prep
   const int sl = d.p.search_level[g];
+  if (refind) subpix_its = sl > 0 ? 8 : 0;  // MapMaker.cc:1003-1014
   const bool refresh = (fl & F_REFRESH) != 0;
   fl &= ~F_REFRESH;
   // lane owns template pixels (row = lane/4, cols 2*(lane%4), +1)
@@ -1207,7 +1227,7 @@ __global__ void __launch_bounds__(128) k_search(TrackerDev d, int stage) {
       const double uu = u0 * u0 + u1 * u1;
       if (uu < 0.03 * 0.03) { converged = true; break; }
     }
-    if (!converged) {  // Tracker.cc:898-903
+    if (!converged && !refind) {  // Tracker.cc:898-903 (ReFind_Common does not look at the result)
       fl &= ~F_FOUND;
       if (lane == 0) d.p.flags[g] = fl;
       return;

@@ -362,3 +362,35 @@ def test_scale_change_and_lost_frames(oracle, product, seq640, map640):
         assert (so.tracking_quality, so.lost_frames) == (sp.tracking_quality, sp.lost_frames)
         p.set_state(0, state=so)
     assert so.tracking_quality == 0 and so.lost_frames >= 3
+
+
+@pytest.mark.gpu
+def test_refind_in_keyframes_matches_oracle(oracle, product, seq640, map640):
+    """MapMaker::ReFindInSingleKeyFrame (SURVEY 8f rank 3): two keyframes at once (one per stream), all
+    map points searched with radius 4 around their projection; found / sub-pixel flags, levels and
+    coarse positions bit-exact, sub-pixel positions to 1e-9; most visible points are re-found close to
+    where they project."""
+    frames, poses = seq640
+    kfs, m = map640
+    S = 2
+    o, p = _setup(oracle, kfs, m, S), _setup(product, kfs, m, S)
+    ims = [frames[7], frames[30]]
+    kposes = np.stack([poses[7], poses[30]])
+    o.refind_in_keyframes(ims, kposes); p.refind_in_keyframes(ims, kposes)
+    for s in range(S):
+        _compare_levels(o, p, s)
+        po, pp = o.get_points(s), p.get_points(s)
+        mask = PT_FOUND | PT_SUBPIX | 2
+        assert np.array_equal(po["flags"] & mask, pp["flags"] & mask)
+        assert np.array_equal(po["level"], pp["level"])
+        found = (po["flags"] & PT_FOUND) != 0
+        sub = (po["flags"] & PT_SUBPIX) != 0
+        assert np.array_equal(po["v2_found"][found & ~sub], pp["v2_found"][found & ~sub])
+        np.testing.assert_allclose(pp["v2_found"][found & sub], po["v2_found"][found & sub], atol=1e-9, rtol=0)
+        in_pvs = (po["flags"] & 2) != 0
+        assert found.sum() > 0.5 * in_pvs.sum() > 100
+        err = np.abs(po["v2_found"][found] - po["v2_image"][found]).max(axis=1)
+        assert (err <= 4.0 * 2.0 ** po["level"][found] + 2.0 ** po["level"][found]).all()
+        assert (sub == (found & (po["level"] > 0))).all()   # sub-pixel exactly on levels > 0
+    # the tracking state of the handle is untouched
+    assert np.array_equal(np.array(p.get_state(0).se3_cam_from_world), np.array(Tracker(product, 640, 480, 1).get_state(0).se3_cam_from_world))
