@@ -229,23 +229,31 @@ __global__ void __launch_bounds__(256) k_fast(TrackerDev d) {
   const bool al16 = ((pitch & 15) == 0) && ((reinterpret_cast<uintptr_t>(im) & 15) == 0);
   if (threadIdx.x < kFastTH * 4) (&out_mask[0][0])[threadIdx.x] = 0u;
   if (threadIdx.x == 0) cand_count = 0;
-  // ---- stage rows y0-3 .. y0+34, bytes x0-16 .. x0+143 (zero outside the image)
-  for (int i = threadIdx.x; i < kFastSR * (kFastSW / 16); i += 256) {
-    const int r = i / (kFastSW / 16), c = i - r * (kFastSW / 16);
-    const int y = y0 - 3 + r, x = x0 - 16 + 16 * c;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (y >= 0 && y < L.h && x + 15 >= 0 && x < L.w) {
-      const uint8_t* p = im + (size_t)y * pitch + x;
-      if (al16 && x >= 0 && x + 15 < L.w) v = __ldg(reinterpret_cast<const uint4*>(p));
-      else {
-        unsigned w4[4] = {0u, 0u, 0u, 0u};
+  // ---- stage rows y0-3 .. y0+34, bytes x0-16 .. x0+143 (zero outside the image): thread -> one of the
+  // ten 16-byte column chunks and rows r0, r0 + 25, so the column tests are done once per thread
+  if (threadIdx.x < 25 * (kFastSW / 16)) {
+    const int r0 = threadIdx.x / (kFastSW / 16), c = threadIdx.x - r0 * (kFastSW / 16);
+    const int x = x0 - 16 + 16 * c;
+    const int xmode = (x + 15 < 0 || x >= L.w) ? 0 : ((al16 && x >= 0 && x + 15 < L.w) ? 1 : 2);
 #pragma unroll
-        for (int k = 0; k < 16; k++)
-          if (x + k >= 0 && x + k < L.w) w4[k >> 2] |= (unsigned)__ldg(p + k) << (8 * (k & 3));
-        v = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+    for (int rr = 0; rr < 2; rr++) {
+      const int r = r0 + 25 * rr;
+      if (r >= kFastSR) break;
+      const int y = y0 - 3 + r;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (xmode && y >= 0 && y < L.h) {
+        const uint8_t* p = im + (size_t)y * pitch + x;
+        if (xmode == 1) v = __ldg(reinterpret_cast<const uint4*>(p));
+        else {
+          unsigned w4[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+          for (int k = 0; k < 16; k++)
+            if (x + k >= 0 && x + k < L.w) w4[k >> 2] |= (unsigned)__ldg(p + k) << (8 * (k & 3));
+          v = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+        }
       }
+      *reinterpret_cast<uint4*>(&tile[r * kFastSW + 16 * c]) = v;
     }
-    *reinterpret_cast<uint4*>(&tile[r * kFastSW + 16 * c]) = v;
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -299,11 +307,11 @@ __global__ void __launch_bounds__(256) k_fast(TrackerDev d) {
     if (lane == 31 && inc > 0) base = atomicAdd(&cand_count, inc);
     base = __shfl_sync(kFull, base, 31);
     int o = base + inc - nc;
-    while (cand16) {
-      const int b = __ffs(cand16) - 1;
-      cand16 &= cand16 - 1;
-      cand_list[o++] = (uint16_t)(((4 * warp + (b >> 2)) << 7) | (4 * lane + (b & 3)));
-    }
+    // 16 predicated stores instead of a data-dependent loop: the loop ran for the busiest lane of the warp
+    const unsigned e0 = (unsigned)(((4 * warp) << 7) | (4 * lane));
+#pragma unroll
+    for (int b = 0; b < 16; b++)
+      if ((cand16 >> b) & 1u) cand_list[o++] = (uint16_t)(e0 + ((b >> 2) << 7) + (b & 3));
   }
   __syncthreads();
   // ---- phase 3: full ring test, one candidate per thread
