@@ -68,3 +68,22 @@ def fast10_bruteforce(im, t):
     n = lib.cdll.orc_fast10_bruteforce(im.ctypes.data_as(C.POINTER(C.c_uint8)), w, h, t,
                                        xy.ctypes.data_as(C.POINTER(C.c_int32)), cap)
     return xy[:n]
+
+
+REFERENCE_DIR = Path("/root/reference")
+
+
+def ref_lib():
+    """oracle/_ref/libref_ptam.so — the reference's OWN sources (Bundle.cc, ATANCamera.cc, ...) compiled
+    where they lie against the header stand-ins in oracle/shim/ (Makefile.ref).  Built when
+    /root/reference is present; on the GPU box only the prebuilt file is used.  None when neither."""
+    so = ORACLE_DIR / "_ref" / "libref_ptam.so"
+    if REFERENCE_DIR.exists():
+        r = subprocess.run(["make", "-C", str(ORACLE_DIR), "-f", "Makefile.ref"], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("building oracle/_ref failed:\n" + r.stdout[-3000:] + r.stderr[-3000:])
+    if not so.exists():
+        return None
+    if "ref" not in _lib:
+        _lib["ref"] = Lib(so, "ref_")
+    return _lib["ref"]
