@@ -1,0 +1,352 @@
+// TEST INFRASTRUCTURE — C ABI around the reference's OWN Tracker / MapMaker / KeyFrame / PatchFinder /
+// SmallBlurryImage classes (src/Tracker.cc, MapMaker.cc, KeyFrame.cc, PatchFinder.cc, ImageProcess.cc,
+// Map.cc, Relocaliser.cc, ATANCamera.cc ... compiled in place from /root/reference against the header
+// stand-ins in oracle/shim/), with the signatures of the oracle (orc_tracker_*) and the product
+// (ptam_tracker_*), prefix ref_.  tests/test_ref_pin_tracker.py drives the oracle and this library with
+// the same frames, maps and states and compares.  Nothing here ships.
+#include "Tracker.h"
+#include "MapMaker.h"
+#include "../include/ptam_b200.h"
+#include <gvars3/instances.h>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <string>
+
+namespace {
+std::function<void()> g_wait_hook;
+
+struct RefMapMaker : public MapMaker {
+  RefMapMaker(Map& m, const ATANCamera& c) : MapMaker(m, c) { mdWiggleScale = 1e30; mdWiggleScaleDepthNormalized = 1e30; }
+  using MapMaker::mbResetRequested;
+  using MapMaker::mdWiggleScale;
+  using MapMaker::mvpKeyFrameQueue;
+  void ResetNow() { if (mbResetRequested) Reset(); }
+  int ReFindAllIn(KeyFrame& k) { return ReFindInSingleKeyFrame(k); }
+};
+struct RefTracker : public Tracker {
+  RefTracker(CVD::ImageRef sz, const ATANCamera& c, Map& m, MapMaker& mm) : Tracker(sz, c, m, mm) {}
+  using Tracker::manMeasAttempted;
+  using Tracker::manMeasFound;
+  using Tracker::mbDidCoarse;
+  using Tracker::mbJustRecoveredSoUseCoarse;
+  using Tracker::mCurrentKF;
+  using Tracker::mdMSDScaledVelocityMagnitude;
+  using Tracker::mnFrame;
+  using Tracker::mnLostFrames;
+  using Tracker::mpSBIThisFrame;
+  using Tracker::mse3CamFromWorld;
+  using Tracker::mv6CameraVelocity;
+  void set_quality(int q) { mTrackingQuality = q == 0 ? BAD : GOOD; }
+  int get_quality() const { return mTrackingQuality == BAD ? 0 : 2; }
+};
+// SmallBlurryImage::mirSize is a process-wide static fixed by the first keyframe (ImageProcess.cc:281-282):
+// a handle of another resolution has to re-arm it
+struct SbiSize : public SmallBlurryImage { static void rearm() { mirSize = CVD::ImageRef(-1, -1); } };
+struct Stream {
+  Map map;
+  std::unique_ptr<RefMapMaker> mm;
+  std::unique_ptr<RefTracker> trk;
+  std::unique_ptr<KeyFrame> refind_kf;
+  ptam_track_result res;
+  bool refind_mode = false;
+};
+struct Handle {
+  int W = 0, H = 0, S = 0;
+  std::unique_ptr<ATANCamera> cam;
+  std::vector<KeyFrame*> store;
+  std::vector<std::unique_ptr<Stream>> streams;
+  std::string err;
+};
+
+TooN::SE3<> se3_from12(const double* p) {
+  TooN::Matrix<3> R;
+  for (int i = 0; i < 9; i++) R(i / 3, i % 3) = p[i];
+  return TooN::SE3<>(TooN::SE3<>::raw(R), TooN::makeVector(p[9], p[10], p[11]));
+}
+void se3_to12(const TooN::SE3<>& s, double* p) {
+  for (int i = 0; i < 9; i++) p[i] = s.get_rotation().get_matrix()(i / 3, i % 3);
+  for (int i = 0; i < 3; i++) p[9 + i] = s.get_translation()[i];
+}
+CVD::Image<CVD::byte> wrap_image(const uint8_t* im, int w, int h, int stride) {
+  CVD::Image<CVD::byte> out(CVD::ImageRef(w, h));
+  for (int y = 0; y < h; y++) std::memcpy(out[y], im + (size_t)y * stride, w);
+  return out;
+}
+const char* kEstimators[3] = {"Tukey", "Cauchy", "Huber"};
+}  // namespace
+
+#include <execinfo.h>
+#include <csignal>
+static void segv_handler(int) { void* bt[64]; int n = backtrace(bt, 64); backtrace_symbols_fd(bt, n, 2); _exit(139); }
+extern "C" void ref_debug_install_segv_handler() { signal(SIGSEGV, segv_handler); }
+extern "C" int ptam_ref_usleep(unsigned int) { if (g_wait_hook) g_wait_hook(); return 0; }
+
+extern "C" {
+
+void ref_tracker_default_params(ptam_tracker_params* p) {
+  p->coarse_min = 20; p->coarse_max = 60; p->coarse_range = 30; p->coarse_subpix_its = 8;
+  p->disable_coarse = 0; p->max_patches_per_frame = 1000; p->mestimator = 0; p->use_constant_velocity = 1;
+  p->coarse_min_velocity = 0.006; p->quality_good = 0.3; p->quality_lost = 0.13;
+  p->use_rotation_estimator = 1; p->reserved0 = 0; p->rotation_estimator_blur = 0.75;
+}
+
+void* ref_tracker_create(int, const double* cam_params, int width, int height, int n_streams, const ptam_tracker_params* params) {
+  using GVars3::GV3;
+  ptam_tracker_params p;
+  if (params) p = *params; else ref_tracker_default_params(&p);
+  TooN::Vector<5> cp;
+  for (int i = 0; i < 5; i++) cp[i] = cam_params[i];
+  GV3::set<TooN::Vector<5>>("Camera.Parameters", cp);
+  // the GVars3 keys Tracker.cc reads (Tracker.cc:95-96,491-496,596,931,1040,1088-1089)
+  GV3::set<unsigned int>("Tracker.CoarseMin", (unsigned)p.coarse_min);
+  GV3::set<unsigned int>("Tracker.CoarseMax", (unsigned)p.coarse_max);
+  GV3::set<unsigned int>("Tracker.CoarseRange", (unsigned)p.coarse_range);
+  GV3::set<int>("Tracker.CoarseSubPixIts", p.coarse_subpix_its);
+  GV3::set<int>("Tracker.DisableCoarse", p.disable_coarse);
+  GV3::set<double>("Tracker.CoarseMinVelocity", p.coarse_min_velocity);
+  GV3::set<int>("Tracker.MaxPatchesPerFrame", p.max_patches_per_frame);
+  GV3::set<std::string>("Tracker.MEstimator", kEstimators[p.mestimator >= 0 && p.mestimator < 3 ? p.mestimator : 0]);
+  GV3::set<int>("Tracker.UseConstantVelocity", p.use_constant_velocity);
+  GV3::set<double>("Tracker.TrackingQualityGood", p.quality_good);
+  GV3::set<double>("Tracker.TrackingQualityLost", p.quality_lost);
+  GV3::set<int>("Tracker.UseRotationEstimator", p.use_rotation_estimator);
+  GV3::set<double>("Tracker.RotationEstimatorBlur", p.rotation_estimator_blur);
+  GV3::set<int>("Tracker.DrawFASTCorners", 0);
+  SbiSize::rearm();
+  Handle* h = new Handle;
+  h->W = width; h->H = height; h->S = n_streams;
+  h->cam.reset(new ATANCamera("Camera"));
+  h->cam->SetImageSize(TooN::makeVector((double)width, (double)height));
+  for (int s = 0; s < n_streams; s++) {
+    std::unique_ptr<Stream> st(new Stream);
+    std::memset(&st->res, 0, sizeof st->res);
+    st->mm.reset(new RefMapMaker(st->map, *h->cam));
+    RefMapMaker* mm = st->mm.get();
+    g_wait_hook = [mm]() { mm->ResetNow(); };  // Tracker::Reset waits for the map-maker thread (Tracker.cc:71-74)
+    st->trk.reset(new RefTracker(CVD::ImageRef(width, height), *h->cam, st->map, *st->mm));
+    g_wait_hook = nullptr;
+    st->trk->set_quality(2);
+    h->streams.push_back(std::move(st));
+  }
+  return h;
+}
+void ref_tracker_destroy(void* hp) {
+  Handle* h = (Handle*)hp;
+  h->streams.clear();
+  for (KeyFrame* k : h->store) delete k;
+  delete h;
+}
+const char* ref_tracker_last_error(const void* h) { return ((const Handle*)h)->err.c_str(); }
+
+int ref_tracker_add_keyframe(void* hp, const uint8_t* image, int stride) {
+  Handle* h = (Handle*)hp;
+  CVD::Image<CVD::byte> im = wrap_image(image, h->W, h->H, stride);
+  KeyFrame* k = new KeyFrame;
+  k->bFixed = false;
+  k->dSceneDepthMean = 1.0; k->dSceneDepthSigma = 1.0;
+  k->MakeKeyFrame_Lite(im);
+  h->store.push_back(k);
+  for (auto& s : h->streams) s->map.vpKeyFrames = h->store;
+  return (int)h->store.size() - 1;
+}
+
+int ref_tracker_set_map(void* hp, int stream, int n, const double* world, const double* right, const double* down,
+                        const int32_t* src_kf, const int32_t* src_level, const int32_t* center) {
+  Handle* h = (Handle*)hp;
+  if (stream < 0 || stream >= h->S) return PTAM_ERR_INVALID;
+  Stream& s = *h->streams[stream];
+  for (MapPoint* p : s.map.vpPoints) { delete p->pTData; delete p->pMMData; delete p; }
+  s.map.vpPoints.clear();
+  for (int i = 0; i < n; i++) {
+    if (src_kf[i] < 0 || src_kf[i] >= (int)h->store.size() || src_level[i] < 0 || src_level[i] >= LEVELS) return PTAM_ERR_INVALID;
+    MapPoint* p = new MapPoint;
+    p->v3WorldPos = TooN::makeVector(world[3 * i], world[3 * i + 1], world[3 * i + 2]);
+    p->v3PixelRight_W = TooN::makeVector(right[3 * i], right[3 * i + 1], right[3 * i + 2]);
+    p->v3PixelDown_W = TooN::makeVector(down[3 * i], down[3 * i + 1], down[3 * i + 2]);
+    p->pPatchSourceKF = h->store[src_kf[i]];
+    p->nSourceLevel = src_level[i];
+    p->irCenter = CVD::ImageRef(center[2 * i], center[2 * i + 1]);
+    p->pMMData = new MapMakerData;
+    // the tracker allocates TrackerData lazily and leaves its flags uninitialised until the point first
+    // enters the image (Tracker.cc:457-458, Tracker.h:41-61): allocate it here with defined values
+    p->pTData = new TrackerData(p);
+    p->pTData->bInImage = p->pTData->bPotentiallyVisible = p->pTData->bSearched = p->pTData->bFound = p->pTData->bDidSubPix = false;
+    p->pTData->nSearchLevel = -1;
+    p->pTData->v2Found = TooN::Zeros; p->pTData->v2Image = TooN::Zeros;
+    s.map.vpPoints.push_back(p);
+  }
+  s.map.vpKeyFrames = h->store;
+  s.map.bGood = true;
+  return 0;
+}
+
+int ref_tracker_set_state(void* hp, int stream, const ptam_tracker_state* st) {
+  Handle* h = (Handle*)hp;
+  if (stream < 0 || stream >= h->S) return PTAM_ERR_INVALID;
+  RefTracker& t = *h->streams[stream]->trk;
+  t.mse3CamFromWorld = se3_from12(st->se3_cam_from_world);
+  for (int k = 0; k < 6; k++) t.mv6CameraVelocity[k] = st->velocity[k];
+  t.mdMSDScaledVelocityMagnitude = st->msd_scaled_velocity_magnitude;
+  t.mCurrentKF.dSceneDepthMean = st->scene_depth_mean;
+  t.mCurrentKF.dSceneDepthSigma = st->scene_depth_sigma;
+  t.mbJustRecoveredSoUseCoarse = st->just_recovered_so_use_coarse != 0;
+  t.set_quality(st->tracking_quality);
+  t.mnLostFrames = st->lost_frames;
+  t.mnFrame = st->frame;
+  return 0;
+}
+int ref_tracker_get_state(void* hp, int stream, ptam_tracker_state* st) {
+  Handle* h = (Handle*)hp;
+  if (stream < 0 || stream >= h->S) return PTAM_ERR_INVALID;
+  RefTracker& t = *h->streams[stream]->trk;
+  std::memset(st, 0, sizeof *st);
+  se3_to12(t.mse3CamFromWorld, st->se3_cam_from_world);
+  for (int k = 0; k < 6; k++) st->velocity[k] = t.mv6CameraVelocity[k];
+  st->msd_scaled_velocity_magnitude = t.mdMSDScaledVelocityMagnitude;
+  st->scene_depth_mean = t.mCurrentKF.dSceneDepthMean;
+  st->scene_depth_sigma = t.mCurrentKF.dSceneDepthSigma;
+  st->just_recovered_so_use_coarse = t.mbJustRecoveredSoUseCoarse;
+  st->tracking_quality = t.get_quality();
+  st->lost_frames = t.mnLostFrames;
+  st->frame = t.mnFrame;
+  return 0;
+}
+int ref_tracker_make_keyframes(void* hp, const uint8_t* const* images, int stride) {
+  Handle* h = (Handle*)hp;
+  for (int s = 0; s < h->S; s++) {
+    CVD::Image<CVD::byte> im = wrap_image(images[s], h->W, h->H, stride);
+    h->streams[s]->trk->mCurrentKF.MakeKeyFrame_Lite(im);
+    h->streams[s]->refind_mode = false;
+  }
+  return 0;
+}
+int ref_tracker_track_frames(void* hp, const uint8_t* const* images, int stride, ptam_track_result* results) {
+  Handle* h = (Handle*)hp;
+  for (int s = 0; s < h->S; s++) {
+    Stream& st = *h->streams[s];
+    RefTracker& t = *st.trk;
+    st.refind_mode = false;
+    st.mm->mvpKeyFrameQueue.clear();  // keyframes the tracker hands to the (absent) map-maker thread are dropped
+    CVD::Image<CVD::byte> im = wrap_image(images[s], h->W, h->H, stride);
+    t.TrackFrame(im, false);
+    ptam_track_result& r = st.res;
+    std::memset(&r, 0, sizeof r);
+    se3_to12(t.mse3CamFromWorld, r.se3_cam_from_world);
+    r.scene_depth_mean = t.mCurrentKF.dSceneDepthMean; r.scene_depth_sigma = t.mCurrentKF.dSceneDepthSigma;
+    for (int l = 0; l < LEVELS; l++) {
+      r.meas_attempted[l] = t.manMeasAttempted[l]; r.meas_found[l] = t.manMeasFound[l];
+      r.n_corners[l] = (int)t.mCurrentKF.aLevels[l].vCorners.size();
+    }
+    r.did_coarse = t.mbDidCoarse;
+    r.tracking_quality = t.get_quality();
+    if (results) results[s] = r;
+  }
+  return 0;
+}
+int ref_tracker_synchronize(void*) { return 0; }
+int ref_tracker_level_size(const void* hp, int level, int* w, int* h) {
+  const Handle* t = (const Handle*)hp;
+  int ww = t->W, hh = t->H;
+  for (int l = 0; l < level; l++) { ww /= 2; hh /= 2; }
+  *w = ww; *h = hh; return 0;
+}
+static KeyFrame& current_kf(Stream& s) { return s.refind_mode ? *s.refind_kf : s.trk->mCurrentKF; }
+int ref_tracker_get_level(void* hp, int stream, int level, uint8_t* pixels, int32_t* corners_xy, int cap, int32_t* row_lut) {
+  Handle* h = (Handle*)hp;
+  Level& L = current_kf(*h->streams[stream]).aLevels[level];
+  const CVD::ImageRef sz = L.im.size();
+  if (pixels) for (int y = 0; y < sz.y; y++) std::memcpy(pixels + (size_t)y * sz.x, L.im[y], sz.x);
+  if (corners_xy)
+    for (size_t i = 0; i < L.vCorners.size() && (int)i < cap; i++) { corners_xy[2 * i] = L.vCorners[i].x; corners_xy[2 * i + 1] = L.vCorners[i].y; }
+  if (row_lut) for (size_t i = 0; i < L.vCornerRowLUT.size(); i++) row_lut[i] = L.vCornerRowLUT[i];
+  return (int)L.vCorners.size();
+}
+// MapMaker::ReFindInSingleKeyFrame (MapMaker.cc:1028-1040) on a keyframe made from images[s] with pose se3 + 12 s
+int ref_tracker_refind_in_keyframes(void* hp, const uint8_t* const* images, int stride, const double* se3) {
+  Handle* h = (Handle*)hp;
+  for (int s = 0; s < h->S; s++) {
+    Stream& st = *h->streams[s];
+    st.refind_kf.reset(new KeyFrame);
+    st.refind_kf->bFixed = false;
+    CVD::Image<CVD::byte> im = wrap_image(images[s], h->W, h->H, stride);
+    st.refind_kf->MakeKeyFrame_Lite(im);
+    st.refind_kf->se3CfromW = se3_from12(se3 + 12 * s);
+    for (MapPoint* p : st.map.vpPoints) { p->pMMData->sMeasurementKFs.clear(); p->pMMData->sNeverRetryKFs.clear(); }
+    st.mm->ReFindAllIn(*st.refind_kf);
+    st.refind_mode = true;
+  }
+  return PTAM_OK;
+}
+int ref_tracker_keyframe_rest(void* hp, int stream, double min_shi_tomasi_score) {
+  Handle* h = (Handle*)hp;
+  if (stream < 0 || stream >= h->S) return PTAM_ERR_INVALID;
+  GVars3::GV3::set<double>("MapMaker.CandidateMinShiTomasiScore", min_shi_tomasi_score);
+  current_kf(*h->streams[stream]).MakeKeyFrame_Rest();
+  return PTAM_OK;
+}
+int ref_tracker_get_level_rest(void* hp, int stream, int level, int32_t* max_xy, int max_cap, int32_t* cand_xy, double* cand_score,
+                               int cand_cap, int* n_cand) {
+  Handle* h = (Handle*)hp;
+  if (stream < 0 || stream >= h->S || level < 0 || level >= LEVELS) return PTAM_ERR_INVALID;
+  Level& L = current_kf(*h->streams[stream]).aLevels[level];
+  if (max_xy)
+    for (size_t i = 0; i < L.vMaxCorners.size() && (int)i < max_cap; i++) { max_xy[2 * i] = L.vMaxCorners[i].x; max_xy[2 * i + 1] = L.vMaxCorners[i].y; }
+  for (size_t i = 0; i < L.vCandidates.size() && (int)i < cand_cap; i++) {
+    if (cand_xy) { cand_xy[2 * i] = L.vCandidates[i].irLevelPos.x; cand_xy[2 * i + 1] = L.vCandidates[i].irLevelPos.y; }
+    if (cand_score) cand_score[i] = L.vCandidates[i].dSTScore;
+  }
+  if (n_cand) *n_cand = (int)L.vCandidates.size();
+  return (int)L.vMaxCorners.size();
+}
+int ref_tracker_get_points(void* hp, int stream, int32_t* flags, int32_t* level, double* v2_found, double* v2_image,
+                           int32_t* outl, int32_t* inl) {
+  Handle* h = (Handle*)hp;
+  Stream& s = *h->streams[stream];
+  for (size_t i = 0; i < s.map.vpPoints.size(); i++) {
+    MapPoint* p = s.map.vpPoints[i];
+    int f = 0, lv = -1;
+    double fx = 0, fy = 0, ix = 0, iy = 0;
+    if (s.refind_mode) {
+      auto it = s.refind_kf->mMeasurements.find(p);
+      if (it != s.refind_kf->mMeasurements.end()) {
+        f |= PTAM_PT_FOUND | (it->second.bSubPix ? PTAM_PT_SUBPIX : 0);
+        lv = it->second.nLevel; fx = it->second.v2RootPos[0]; fy = it->second.v2RootPos[1];
+      }
+    } else if (p->pTData) {
+      // raw TrackerData fields.  The reference keeps no "entered the PVS this frame" flag
+      // (bPotentiallyVisible is never set), and bSearched / bFound / v2Found are stale for points that
+      // did not enter it: PTAM_PT_IN_PVS is never reported here, the test masks with the oracle's.
+      const TrackerData& d = *p->pTData;
+      if (d.bInImage) f |= PTAM_PT_IN_IMAGE;
+      if (d.bSearched) f |= PTAM_PT_SEARCHED;
+      if (d.bFound) f |= PTAM_PT_FOUND;
+      if (d.bFound && d.bDidSubPix) f |= PTAM_PT_SUBPIX;
+      lv = d.nSearchLevel;
+      fx = d.v2Found[0]; fy = d.v2Found[1];
+      ix = d.v2Image[0]; iy = d.v2Image[1];
+    }
+    if (flags) flags[i] = f;
+    if (level) level[i] = lv;
+    if (v2_found) { v2_found[2 * i] = fx; v2_found[2 * i + 1] = fy; }
+    if (v2_image) { v2_image[2 * i] = ix; v2_image[2 * i + 1] = iy; }
+    if (outl) outl[i] = p->nMEstimatorOutlierCount;
+    if (inl) inl[i] = p->nMEstimatorInlierCount;
+  }
+  return (int)s.map.vpPoints.size();
+}
+// PatchFinder keeps its template protected: not exported by the reference build
+int ref_tracker_get_templates(void*, int, uint8_t*, int32_t*) { return PTAM_ERR_INVALID; }
+int ref_tracker_get_iteration_set(void*, int, int32_t*, int) { return PTAM_ERR_INVALID; }  // a local of TrackMap
+int ref_tracker_get_sbi(void* hp, int stream, float* tmpl, int cap, double* rot3, double* score) {
+  Handle* h = (Handle*)hp;
+  if (stream < 0 || stream >= h->S) return PTAM_ERR_INVALID;
+  SmallBlurryImage* sbi = h->streams[stream]->trk->mpSBIThisFrame;
+  if (!sbi) return 0;
+  const CVD::ImageRef sz = sbi->mimTemplate.size();
+  if (tmpl) for (int y = 0, i = 0; y < sz.y; y++) for (int x = 0; x < sz.x && i < cap; x++, i++) tmpl[i] = sbi->mimTemplate[y][x];
+  if (rot3) rot3[0] = rot3[1] = rot3[2] = 0;  // not kept by the reference (a temporary of PredictPoseWithMotionModel)
+  if (score) *score = 0;
+  return sz.x * sz.y;
+}
+}  // extern "C"

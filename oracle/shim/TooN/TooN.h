@@ -18,8 +18,10 @@ namespace TooN {
 static const int Dynamic = -1;
 struct ZerosT {};
 static const ZerosT Zeros = ZerosT();
-struct IdentityT {};
+struct IdentityT { double s; IdentityT() : s(1) {} explicit IdentityT(double s_) : s(s_) {} };
 static const IdentityT Identity = IdentityT();
+inline IdentityT operator*(double k, const IdentityT& i) { return IdentityT(k * i.s); }
+inline IdentityT operator*(const IdentityT& i, double k) { return IdentityT(i.s * k); }
 
 struct vec_tag {};
 struct mat_tag {};
@@ -75,8 +77,11 @@ template <int N> struct VecView : vec_tag {
   VecView<Dynamic> slice(int s, int l) const { return VecView<Dynamic>(ptr + s * stride, l, stride); }
 };
 
+template <int R, int C> struct MatView;
 template <int N, class P> struct Vector : vec_tag {
   static const int Size = N;
+  MatView<N, 1> as_col() const;
+  MatView<1, N> as_row() const;
   Store<N> s;
   Vector() {}
   explicit Vector(int n_) : s(n_) {}
@@ -143,7 +148,7 @@ template <int R, int C, class P> struct Matrix : mat_tag {
   Matrix() : nr(R == Dynamic ? 0 : R), nc(C == Dynamic ? 0 : C) {}
   Matrix(int r, int c) : s(r * c), nr(r), nc(c) {}
   Matrix(const ZerosT&) : nr(R), nc(C) { static_assert(R != Dynamic && C != Dynamic, "sized"); for (int i = 0; i < nr * nc; i++) s.p()[i] = 0; }
-  Matrix(const IdentityT&) : nr(R), nc(C) { static_assert(R != Dynamic && C != Dynamic, "sized"); for (int r = 0; r < nr; r++) for (int c = 0; c < nc; c++) s.p()[r * nc + c] = r == c ? 1.0 : 0.0; }
+  Matrix(const IdentityT& id) : nr(R), nc(C) { static_assert(R != Dynamic && C != Dynamic, "sized"); for (int r = 0; r < nr; r++) for (int c = 0; c < nc; c++) s.p()[r * nc + c] = r == c ? id.s : 0.0; }
   template <class M, TOON_IF(is_mat<M>::value)> Matrix(const M& m) : s(m.num_rows() * m.num_cols()), nr(m.num_rows()), nc(m.num_cols()) {
     for (int r = 0; r < nr; r++) for (int c = 0; c < nc; c++) s.p()[r * nc + c] = m(r, c);
   }
@@ -164,7 +169,7 @@ template <int R, int C, class P> struct Matrix : mat_tag {
     return *this;
   }
   Matrix& operator=(const ZerosT&) { for (int i = 0; i < nr * nc; i++) s.p()[i] = 0; return *this; }
-  Matrix& operator=(const IdentityT&) { for (int r = 0; r < nr; r++) for (int c = 0; c < nc; c++) s.p()[r * nc + c] = r == c ? 1.0 : 0.0; return *this; }
+  Matrix& operator=(const IdentityT& id) { for (int r = 0; r < nr; r++) for (int c = 0; c < nc; c++) s.p()[r * nc + c] = r == c ? id.s : 0.0; return *this; }
   template <class M, TOON_IF(is_mat<M>::value)> Matrix& operator+=(const M& m) { for (int r = 0; r < nr; r++) for (int c = 0; c < nc; c++) (*this)(r, c) += m(r, c); return *this; }
   template <class M, TOON_IF(is_mat<M>::value)> Matrix& operator-=(const M& m) { for (int r = 0; r < nr; r++) for (int c = 0; c < nc; c++) (*this)(r, c) -= m(r, c); return *this; }
   Matrix& operator*=(double k) { for (int i = 0; i < nr * nc; i++) s.p()[i] *= k; return *this; }
@@ -174,6 +179,9 @@ template <int R, int C, class P> struct Matrix : mat_tag {
   MatView<Dynamic, Dynamic> slice(int r0, int c0, int nr_, int nc_) { return MatView<Dynamic, Dynamic>(s.p() + r0 * nc + c0, nr_, nc_, nc, 1); }
   MatView<Dynamic, Dynamic> slice(int r0, int c0, int nr_, int nc_) const { return MatView<Dynamic, Dynamic>(const_cast<double*>(s.p()) + r0 * nc + c0, nr_, nc_, nc, 1); }
 };
+
+template <int N, class P> inline MatView<N, 1> Vector<N, P>::as_col() const { return MatView<N, 1>(const_cast<double*>(s.p()), size(), 1, 1, 1); }
+template <int N, class P> inline MatView<1, N> Vector<N, P>::as_row() const { return MatView<1, N>(const_cast<double*>(s.p()), 1, size(), size(), 1); }
 
 // helpers to build result objects --------------------------------------------------------------
 template <int N> inline Vector<N> make_vec(int n) { return Vector<N>(n); }
@@ -295,3 +303,4 @@ template <class... T> inline Vector<(int)sizeof...(T)> makeVector(T... a) {
 }
 
 }  // namespace TooN
+#include "helpers.h"

@@ -17,6 +17,7 @@ template <class P = double> class SE3 {
     const orc::SE3 e = orc::se3_exp(m);
     return from_orc(e);
   }
+  static Vector<6> ln(const SE3& s) { return s.ln(); }
   Vector<6> ln() const { Vector<6> r; orc::se3_ln(to_orc(), r.get_data_ptr()); return r; }
   SE3 inverse() const { const SO3<P> Ri = R.inverse(); return SE3(Ri, -(Ri * t)); }
   SE3 operator*(const SE3& rhs) const { return SE3(R * rhs.R, t + R * rhs.t); }

@@ -38,6 +38,13 @@ template <class P = double> class SO3 {
     r((i + 2) % 3, (i + 1) % 3) = 1;
     return r;
   }
+  template <class V, TOON_IF(is_vec<V>::value)> static Vector<3> generator_field(int i, const V& pos) {
+    Vector<3> r;
+    r[i] = 0;
+    r[(i + 1) % 3] = -pos[(i + 2) % 3];
+    r[(i + 2) % 3] = pos[(i + 1) % 3];
+    return r;
+  }
  private:
   Matrix<3> m;
   template <class A, TOON_IF(is_vec<A>::value)> static void normalize(const A& v) { const double n = std::sqrt(v * v); for (int i = 0; i < v.size(); i++) v[i] = v[i] / n; }

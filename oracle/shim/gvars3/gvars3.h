@@ -4,6 +4,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <vector>
 namespace GVars3 {
 enum { SILENT = 1, HIDDEN = 2, FATAL_IF_NOT_DEFINED = 4 };
 template <class T> inline std::map<std::string, std::shared_ptr<T>>& gv_store() { static std::map<std::string, std::shared_ptr<T>> s; return s; }
@@ -37,6 +38,23 @@ struct GV3 {
 };
 struct GV2T {
   template <class T> void Register(gvar3<T>& g, const std::string& name, const T& def, int = 0) { g.p = gv_slot<T>(name, def); }
+  int GetInt(const std::string& name, int def = 0, int = 0) { return *gv_slot<int>(name, def); }
+  double GetDouble(const std::string& name, double def = 0, int = 0) { return *gv_slot<double>(name, def); }
+  std::string GetString(const std::string& name, const std::string& def = "", int = 0) { return *gv_slot<std::string>(name, def); }
 };
 static GV2T GV2;
+typedef void (*GUICallbackProc)(void* ptr, std::string sCommand, std::string sParams);
+struct GUIT {
+  void RegisterCommand(const std::string&, GUICallbackProc, void*) {}
+  void UnRegisterCommand(const std::string&) {}
+  void UnRegisterAllCommands(void*) {}
+  void ParseLine(const std::string&) {}
+};
+static GUIT GUI;
+inline std::vector<std::string> ChopAndUnquoteString(const std::string& s) {
+  std::vector<std::string> v; std::string cur;
+  for (char c : s) { if (c == ' ') { if (!cur.empty()) v.push_back(cur); cur.clear(); } else if (c != '"') cur += c; }
+  if (!cur.empty()) v.push_back(cur);
+  return v;
+}
 }  // namespace GVars3
