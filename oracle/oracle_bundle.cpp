@@ -1,5 +1,7 @@
 // TEST INFRASTRUCTURE — CPU oracle for PTAM path B (bundle adjuster).  NOT part of the product.
-// PARITY UNPINNED (the reference has no tests; TooN Cholesky / SE3 restated in oracle_math.h).
+// PINNED against the reference's own src/Bundle.cc + src/ATANCamera.cc compiled in place (oracle/_ref,
+// Makefile.ref): bit-identical runs (tests/test_ref_pin_bundle.py).  Restated, not pinned: TooN's own
+// arithmetic (LDL^T Cholesky, SE3::exp) in oracle_math.h — the library is absent from this image.
 // Faithful single-threaded restatement of class Bundle — src/Bundle.cc (all), include/Bundle.h:38-103
 // — including its data structures' cost: the dense [camera][point] measurement LUT
 // (Bundle.cc:558-567) and the O(cameras x points) scans (Bundle.cc:396,466) ARE the reference's CPU

@@ -2,12 +2,15 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg
 // may build, load or call anything under oracle/.
 //
-// PARITY UNPINNED: the reference (cggos/ptam_cg) ships no tests or golden vectors and its
-// arithmetic lives partly in three un-vendored libraries (TooN 2.2, libCVD 20150407, GVars3 3.0,
-// pinned only by URL in install_deps.sh:39-60) that are absent here, so the reference cannot be
-// compiled.  This file restates, in plain single-threaded C++, the published algorithms of the
-// TooN pieces the hot paths call (SE3/SO3 exp+ln, square-root-free LDL^T "Cholesky", WLS) and the
-// reference's own ATANCamera model.  Each function cites the reference call site it serves.
+// LIBRARY ARITHMETIC RESTATED, NOT PINNED: the reference (cggos/ptam_cg) ships no tests or golden vectors
+// and part of its arithmetic lives in three un-vendored libraries (TooN 2.2, libCVD 20150407, GVars3
+// 3.0, pinned only by URL in install_deps.sh:39-60) that are absent here.  This file restates, in plain
+// single-threaded C++, the published algorithms of the TooN pieces the hot paths call (SE3/SO3 exp+ln,
+// square-root-free LDL^T "Cholesky", WLS) and the reference's own ATANCamera model (the latter IS
+// pinned: oracle/_ref compiles src/ATANCamera.cc itself).  Each function cites the reference call site
+// it serves.  oracle/shim/TooN/{so3,se3,Cholesky}.h — the header stand-ins the reference's own sources
+// are compiled against for oracle/_ref — call these same functions, so that every difference between
+// oracle/_ref and the oracle comes from the reference's own code.
 //
 // Numeric contract shared (by specification, not by code) with the CUDA product:
 //   * IEEE-754 binary64, round-to-nearest, NO fused multiply-add (-ffp-contract=off here,

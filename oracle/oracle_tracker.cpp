@@ -1,6 +1,10 @@
 // TEST INFRASTRUCTURE — CPU oracle for PTAM path T (per-frame tracker).  NOT part of the product.
-// PARITY UNPINNED (no upstream tests/golden vectors; libCVD/TooN semantics restated from their
-// published behaviour — see oracle_math.h and DESIGN.md).  Single-threaded, faithful loop order.
+// PINNED against the reference's own Tracker.cc / MapMaker.cc / PatchFinder.cc / KeyFrame.cc /
+// ImageProcess.cc compiled in place (oracle/_ref, Makefile.ref): Tracker::TrackFrame sequences,
+// ReFindInSingleKeyFrame and MakeKeyFrame_Rest bit-identical (tests/test_ref_pin_tracker.py).
+// Restated, not pinned (the libraries are absent from this image; there are no upstream tests or
+// golden vectors): the arithmetic inside libCVD / TooN themselves — see oracle_math.h and DESIGN.md §2.
+// Single-threaded, faithful loop order.
 //
 // Restates:  KeyFrame::MakeKeyFrame_Lite        src/KeyFrame.cc:18-54
 //            CVD::halfSample / fast_corner_detect_10 / transform / sample   (libCVD 20150407)
@@ -155,7 +159,7 @@ static inline double level_n_pos(double p, int l) { return (p + 0.5) / (1 << l) 
 // KeyFrame::MakeKeyFrame_Rest (KeyFrame.cc:61-82), SURVEY 8f rank 2: fast_nonmax(im, vCorners, 10,
 // vMaxCorners) and the Shi-Tomasi candidates.  (Its last two lines build the relocaliser's
 // SmallBlurryImage, which is sbi_make / sbi_make_jacs above.)
-// libCVD pieces restated (PARITY UNPINNED): fast_nonmax = fast_corner_score_9 followed by
+// libCVD pieces restated (library arithmetic: not pinned): fast_nonmax = fast_corner_score_9 followed by
 // nonmax_suppression.  The score is found by bisection on the threshold b in [barrier, 255): the
 // largest b at which the pixel is still a FAST-9 corner (>= 9 contiguous ring pixels all > p + b or
 // all < p - b); a corner is suppressed when one of its 8 neighbours is a corner with a strictly
@@ -232,7 +236,7 @@ static void make_keyframe_rest(KeyFrame& kf, double min_st_score) {
 // (ImageProcess.cc:279-304), ImageProcess::MakeJacs (:170-191), IteratePosRelToTarget (:313-412),
 // SE3fromSE2 (:421-473), CalcSBIRotation (:482-494); used by Tracker::TrackFrame (Tracker.cc:95-108)
 // and PredictPoseWithMotionModel (:1012-1029).
-// libCVD pieces restated (PARITY UNPINNED): halfSample as above; convolveGaussian(float image,
+// libCVD pieces restated (library arithmetic: not pinned): halfSample as above; convolveGaussian(float image,
 // sigma) as a separable FIR of radius ceil(3 sigma), taps exp(-i^2 / 2 sigma^2) normalised to unit
 // sum and rounded to float, replicated borders, float accumulation  centre, then (a + b) * tap
 // outwards, rows first then columns; CVD::transform with bilinear sample() evaluated in double and

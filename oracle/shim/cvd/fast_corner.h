@@ -11,6 +11,11 @@ static const int dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1
 static const int dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
 inline bool is_corner(const BasicImage<byte>& im, int x, int y, int b, int arc) {
   const int p = im[y][x];
+  {  // any arc of >= 9 contiguous ring pixels contains at least two of the four compass pixels
+    int nb = 0, nd = 0;
+    for (int i = 0; i < 16; i += 4) { const int v = im[y + dy[i]][x + dx[i]]; nb += v > p + b; nd += v < p - b; }
+    if (nb < 2 && nd < 2) return false;
+  }
   int brighter = 0, darker = 0;  // bit i set: ring pixel i is brighter / darker
   for (int i = 0; i < 16; i++) {
     const int v = im[y + dy[i]][x + dx[i]];

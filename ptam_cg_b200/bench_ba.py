@@ -27,7 +27,7 @@ def flops_per_trial(n):
 
 def bench_ba(prod, device=0, config="C3", reps=3, cpu_lib=None, shard=None, graph=None, cpu_trials=None):
     """shard: None or (rank, world, ncclComm_t from capi.nccl_comm_create).  cpu_lib: an already-loaded CPU library
-    exporting the same ABI (bench.py passes the oracle for the cpu_baseline leg; this package never
+    exporting the same ABI, or (library, kind) (bench.py passes oracle/_ref or the oracle for the cpu_baseline leg; this package never
     loads it itself).  cpu_trials: cap on the CPU leg's lambda trials (bounded sample)."""
     import torch
     cfg = CONFIGS[config]
@@ -69,6 +69,7 @@ def bench_ba(prod, device=0, config="C3", reps=3, cpu_lib=None, shard=None, grap
     if sol[1]:
         out["solve_gflops"] = flops_per_trial(n) / (sol[0] / sol[1] * 1e-3) / 1e9
     if cpu_lib is not None:
+        cpu_lib, cpu_kind = cpu_lib if isinstance(cpu_lib, tuple) else (cpu_lib, "port")
         kw = dict(max_iterations=cpu_trials) if cpu_trials else {}
         o = Bundle(cpu_lib, g["width"], g["height"], **kw)
         o.add_graph(g)
@@ -76,7 +77,7 @@ def bench_ba(prod, device=0, config="C3", reps=3, cpu_lib=None, shard=None, grap
         acc_o = o.Compute()
         dto = time.perf_counter() - t0
         so = o.stats()
-        out["cpu_baseline"] = {"value": so.lambda_trials / dto, "unit": "lambda-trials/s", "cores": 1, "kind": "port",
+        out["cpu_baseline"] = {"value": so.lambda_trials / dto, "unit": "lambda-trials/s", "cores": 1, "kind": cpu_kind,
                                "sample": f"Compute() on the same graph capped at {so.lambda_trials} lambda trials "
                                          f"({acc_o} accepted), {dto * 1e3:.0f} ms"}
     return out
