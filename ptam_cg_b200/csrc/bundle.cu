@@ -189,26 +189,41 @@ struct ptam_bundle {
       shard_plan(P, MG, h_mpt.data(), world, plan.data());
       p_lo = plan[rank]; p_hi = plan[rank + 1];
     }
+    // a single-GPU handle uses the insertion-order arrays as they are; a shard copies out its own
     l_gid.clear();
     std::vector<int> l_mcam, l_mpt;
     std::vector<double> l_found, l_sin;
-    for (int m = 0; m < MG; m++) {
-      if (h_mpt[m] < p_lo || h_mpt[m] >= p_hi) continue;
-      l_gid.push_back(m); l_mcam.push_back(h_mcam[m]); l_mpt.push_back(h_mpt[m]);
-      l_found.push_back(h_found[2 * m]); l_found.push_back(h_found[2 * m + 1]); l_sin.push_back(h_sin[m]);
+    const bool whole = world == 1;
+    if (whole) {
+      l_gid.resize(MG);
+      std::iota(l_gid.begin(), l_gid.end(), 0);
+    } else {
+      for (int m = 0; m < MG; m++) {
+        if (h_mpt[m] < p_lo || h_mpt[m] >= p_hi) continue;
+        l_gid.push_back(m); l_mcam.push_back(h_mcam[m]); l_mpt.push_back(h_mpt[m]);
+        l_found.push_back(h_found[2 * m]); l_found.push_back(h_found[2 * m + 1]); l_sin.push_back(h_sin[m]);
+      }
     }
+    const std::vector<int>& v_mcam = whole ? h_mcam : l_mcam;
+    const std::vector<int>& v_mpt = whole ? h_mpt : l_mpt;
+    const std::vector<double>& v_found = whole ? h_found : l_found;
+    const std::vector<double>& v_sin = whole ? h_sin : l_sin;
     const int M = (int)l_gid.size();
     n_meas_local = M;
     std::vector<int> off(P + 1, 0), idx(M);
-    for (int m = 0; m < M; m++) off[l_mpt[m] + 1]++;
+    for (int m = 0; m < M; m++) off[v_mpt[m] + 1]++;
     for (int i = 0; i < P; i++) off[i + 1] += off[i];
     {
       std::vector<int> cur(off.begin(), off.end() - 1);
-      for (int m = 0; m < M; m++) idx[cur[l_mpt[m]]++] = m;
+      for (int m = 0; m < M; m++) idx[cur[v_mpt[m]]++] = m;
       for (int i = 0; i < P; i++) {
-        std::sort(idx.begin() + off[i], idx.begin() + off[i + 1], [&](int a, int b) { return l_mcam[a] < l_mcam[b]; });
+        // the bucket pass is stable: with the usual camera-major insertion (MapMaker.cc:871-882) every
+        // point's list is already ascending in camera id and the sort is skipped
+        bool sorted = true;
+        for (int o = off[i] + 1; o < off[i + 1]; o++) if (v_mcam[idx[o]] < v_mcam[idx[o - 1]]) { sorted = false; break; }
+        if (!sorted) std::sort(idx.begin() + off[i], idx.begin() + off[i + 1], [&](int a, int b) { return v_mcam[a] < v_mcam[b]; });
         for (int o = off[i] + 1; o < off[i + 1]; o++)
-          if (l_mcam[idx[o]] == l_mcam[idx[o - 1]]) { set_error("duplicate (camera, point) measurement"); return PTAM_ERR_INVALID; }
+          if (v_mcam[idx[o]] == v_mcam[idx[o - 1]]) { set_error("duplicate (camera, point) measurement"); return PTAM_ERR_INVALID; }
       }
     }
     // one arena for everything: two passes over the same layout (measure, then assign)
@@ -245,7 +260,7 @@ struct ptam_bundle {
     PTAM_CUDA_TRY(this, cudaStreamSynchronize(stream));
 #define UP(buf, vec) if (!vec.empty()) PTAM_CUDA_TRY(this, cudaMemcpy(buf.p, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice))
     UP(cam_se3, h_cam_se3); UP(cam_fixed, h_cam_fixed); UP(cam_row, h_cam_row); UP(pt_pos, h_pts);
-    UP(pt_off, off); UP(pt_meas, idx); UP(m_cam, l_mcam); UP(m_pt, l_mpt); UP(m_found, l_found); UP(m_sin, l_sin);
+    UP(pt_off, off); UP(pt_meas, idx); UP(m_cam, v_mcam); UP(m_pt, v_mpt); UP(m_found, v_found); UP(m_sin, v_sin);
     UP(m_gid, l_gid);
 #undef UP
     d.cam = cam; d.n_cams = C; d.n_pts = P; d.n_meas = M; d.n = n; d.est = prm.mestimator;
