@@ -195,6 +195,23 @@ int ptam_tracker_get_points(ptam_tracker* t, int stream, int32_t* flags, int32_t
  * reference gives it its own PatchFinder (MapMaker.cc:977). */
 int ptam_tracker_refind_in_keyframes(ptam_tracker* t, const uint8_t* const* images, int stride,
                                      const double* se3_cam_from_world /* n_streams * 12 */);
+/* MapMaker::AddPointEpipolar (MapMaker.cc:529-688) for a batch of candidates, up to the sub-pixel position in
+ * the target keyframe.  Source = stored keyframe src_kf (ptam_tracker_add_keyframe) with pose src_se3 and
+ * scene depth mean / sigma (KeyFrame::dSceneDepthMean/Sigma); target = stream's current frame (its FAST
+ * corners of `level` are the search set) with pose target_se3; cand_xy = Candidate::irLevelPos pairs in the
+ * source level (e.g. from ptam_tracker_get_level_rest); wiggle_scale = MapMaker::mdWiggleScale.
+ * Per candidate: the epipolar segment of its view ray over the depth range [max(wiggle, mean - sigma),
+ * min(40 wiggle, mean + sigma)] in the target's z = 1 plane, all target corners within OnePixelDist (4 +
+ * LevelScale) of it, un-warped 8x8 template (MakeTemplateCoarseNoWarp), first minimum ZMSSD <= mnMaxSSD,
+ * MakeSubPixTemplate + IterateSubPixToConvergence(10).  found[i] = 1 when all of that succeeded (the
+ * reference's `return true` apart from the triangulation), best_corner[i] = index of the winning corner in
+ * the target level's list (-1: none), sub_pos = Finder.GetSubPixPos() (level-zero pixels).  The
+ * triangulation and MapPoint construction that follow (a 4x4 SVD per accepted point, MapMaker.cc:648-687)
+ * stay with the caller. */
+int ptam_tracker_epipolar_search(ptam_tracker* t, int stream, int level, int src_kf, const double src_se3[12],
+                                 double src_depth_mean, double src_depth_sigma, const double target_se3[12],
+                                 double wiggle_scale, int n_cand, const int32_t* cand_xy, int32_t* found,
+                                 int32_t* best_corner, double* sub_pos);
 /* KeyFrame::MakeKeyFrame_Rest (KeyFrame.cc:61-82) for the current frame of one stream — what the map
  * maker needs when the frame becomes a keyframe: fast_nonmax(im, vCorners, 10, vMaxCorners) on every
  * level, then the Shi-Tomasi candidates (ImageProcess.cc:20-47; in_image_with_border 10, score >

@@ -300,7 +300,7 @@ struct Camera {
   double size[2];
   double focal[2], center[2], inv_focal[2];
   double w, winv, tan2, one_over_tan2, dist_enabled;
-  double largest_radius, max_r;
+  double largest_radius, max_r, one_pixel_dist;
 
   double invrtrans(double r) const { return w == 0.0 ? r : std::tan(r * w) * one_over_tan2; }
   double rtrans_factor(double r) const {
@@ -326,6 +326,13 @@ struct Camera {
     double v1 = std::max(p[3], 1.0 - p[3]) / p[1];
     largest_radius = invrtrans(std::sqrt(v0 * v0 + v1 * v1));
     max_r = 1.5 * largest_radius;
+    {  // mdOnePixelDist (ATANCamera.cc:59-64)
+      const double c[2] = {W / 2, H / 2}, a[2] = {W / 2 + 1.0, H / 2 + 1.0};
+      double uc[2], ua[2];
+      unproject(c, uc); unproject(a, ua);
+      const double d0 = uc[0] - ua[0], d1 = uc[1] - ua[1];
+      one_pixel_dist = std::sqrt(d0 * d0 + d1 * d1) / std::sqrt(2.0);
+    }
   }
   struct Proj { double im[2]; double cam[2]; double r; double factor; bool invalid; };
   Proj project(const double* cam) const {  // ATANCamera.cc:109-121

@@ -851,6 +851,102 @@ struct Tracker {
     }
   }
 
+  // MapMaker::AddPointEpipolar (MapMaker.cc:529-688; SURVEY 8f rank 3, second half) up to the sub-pixel
+  // position in the target keyframe: epipolar segment of the candidate's view ray in the target's z=1
+  // plane, scan of ALL target corners of that level against it, un-warped 8x8 template
+  // (MakeTemplateCoarseNoWarp), first minimum ZMSSD <= mnMaxSSD, sub-pixel refinement (10 iterations, must
+  // converge).  The target keyframe is the stream's current frame; the source a stored keyframe.
+  // The triangulation that follows (4x4 SVD per accepted point, MapMaker.cc:176-187) is left to the caller.
+  struct EpiLine { bool ok; double normal[2], along[2], norm_dist, min_len, max_len; };
+  EpiLine epipolar_line(int level, IRef cand, const SE3& src, double dmean, double dsigma, const SE3& tgt, double wiggle) const {
+    EpiLine e{};
+    const double root[2] = {level_zero_pos((double)cand.x, level), level_zero_pos((double)cand.y, level)};
+    double uc[2];
+    cam.unproject(root, uc);
+    double ray[3] = {uc[0], uc[1], 1.0};
+    const double nr = std::sqrt(ray[0] * ray[0] + ray[1] * ray[1] + ray[2] * ray[2]);
+    for (int i = 0; i < 3; i++) ray[i] = ray[i] / nr;
+    double ray_w[3], dirn[3];
+    for (int i = 0; i < 3; i++) ray_w[i] = src.R[i] * ray[0] + src.R[3 + i] * ray[1] + src.R[6 + i] * ray[2];  // R^T ray
+    tgt.rotate(ray_w, dirn);
+    const double d_start = std::max(wiggle, dmean - dsigma), d_end = std::min(40 * wiggle, dmean + dsigma);
+    double c_w[3], c_t[3];
+    for (int i = 0; i < 3; i++) c_w[i] = -(src.R[i] * src.t[0] + src.R[3 + i] * src.t[1] + src.R[6 + i] * src.t[2]);
+    tgt.apply(c_w, c_t);
+    double rs[3], re[3];
+    for (int i = 0; i < 3; i++) { rs[i] = c_t[i] + d_start * dirn[i]; re[i] = c_t[i] + d_end * dirn[i]; }
+    if (re[2] <= rs[2]) return e;
+    if (re[2] <= 0.0) return e;
+    if (rs[2] <= 0.0) {
+      const double k = 0.001 - rs[2] / dirn[2];
+      for (int i = 0; i < 3; i++) rs[i] += dirn[i] * k;
+    }
+    const double A[2] = {rs[0] / rs[2], rs[1] / rs[2]}, B[2] = {re[0] / re[2], re[1] / re[2]};
+    double al[2] = {A[0] - B[0], A[1] - B[1]};
+    if (al[0] * al[0] + al[1] * al[1] < 1e-8) return e;
+    const double na = std::sqrt(al[0] * al[0] + al[1] * al[1]);
+    al[0] = al[0] / na; al[1] = al[1] / na;
+    e.along[0] = al[0]; e.along[1] = al[1];
+    e.normal[0] = al[1]; e.normal[1] = -al[0];
+    e.norm_dist = A[0] * e.normal[0] + A[1] * e.normal[1];
+    if (std::fabs(e.norm_dist) > cam.largest_radius) return e;
+    const double la = al[0] * A[0] + al[1] * A[1], lb = al[0] * B[0] + al[1] * B[1];
+    e.min_len = std::min(la, lb) - 0.05;
+    e.max_len = std::max(la, lb) + 0.05;
+    if (e.min_len < -2.0) e.min_len = -2.0;
+    if (e.max_len < -2.0) e.max_len = -2.0;
+    if (e.min_len > 2.0) e.min_len = 2.0;
+    if (e.max_len > 2.0) e.max_len = 2.0;
+    e.ok = true;
+    return e;
+  }
+  void epipolar_search(Stream& s, int level, int src_kf, const SE3& src, double dmean, double dsigma, const SE3& tgt, double wiggle,
+                       int n, const int32_t* cand, int32_t* found, int32_t* best_corner, double* sub_pos) {
+    const Level& SL = store[src_kf].lev[level];
+    const Level& TL = s.cur.lev[level];
+    const int max_ssd = 8 * 8 * 500;
+    // vImplaneCorners: UnProject of the (truncated) level-zero position of every target corner (MapMaker.cc:608-614)
+    std::vector<double> implane(2 * TL.corners.size());
+    for (size_t i = 0; i < TL.corners.size(); i++) {
+      const double p[2] = {(double)(int)level_zero_pos((double)TL.corners[i].x, level), (double)(int)level_zero_pos((double)TL.corners[i].y, level)};
+      cam.unproject(p, &implane[2 * i]);
+    }
+    const double max_dist = cam.one_pixel_dist * (4.0 + 1.0 * (1 << level));
+    const double max_dist_sq = max_dist * max_dist;
+    for (int c = 0; c < n; c++) {
+      found[c] = 0; best_corner[c] = -1; sub_pos[2 * c] = sub_pos[2 * c + 1] = 0;
+      const IRef cp{cand[2 * c], cand[2 * c + 1]};
+      const EpiLine e = epipolar_line(level, cp, src, dmean, dsigma, tgt, wiggle);
+      if (!e.ok) continue;
+      TData d;
+      d.search_level = level;
+      if (!SL.in_image_with_border(cp.x, cp.y, 5)) continue;  // MakeTemplateCoarseNoWarp: template bad
+      int ts = 0, tss = 0;
+      for (int y = 0; y < 8; y++)
+        for (int x = 0; x < 8; x++) { const int b = SL.row(cp.y - 4 + y)[cp.x - 4 + x]; d.tmpl[8 * y + x] = (uint8_t)b; ts += b; tss += b * b; }
+      d.tsum = ts; d.tsumsq = tss;
+      int best = -1, best_ssd = max_ssd + 1;
+      for (size_t i = 0; i < TL.corners.size(); i++) {
+        const double* im = &implane[2 * i];
+        const double dd = e.norm_dist - (im[0] * e.normal[0] + im[1] * e.normal[1]);
+        if (dd * dd > max_dist_sq) continue;
+        const double al = im[0] * e.along[0] + im[1] * e.along[1];
+        if (al < e.min_len) continue;
+        if (al > e.max_len) continue;
+        const int ssd = zmssd_at_point(TL, TL.corners[i], d.tmpl, d.tsum, d.tsumsq, max_ssd);
+        if (ssd < best_ssd) { best = (int)i; best_ssd = ssd; }
+      }
+      if (best == -1) continue;
+      best_corner[c] = best;
+      d.coarse[0] = level_zero_pos((double)TL.corners[best].x, level);
+      d.coarse[1] = level_zero_pos((double)TL.corners[best].y, level);
+      make_subpix_template(d);
+      if (!iterate_subpix_to_convergence(d, s.cur, 10)) continue;
+      found[c] = 1;
+      sub_pos[2 * c] = d.subpix[0]; sub_pos[2 * c + 1] = d.subpix[1];
+    }
+  }
+
   void track_frame(Stream& s, const uint8_t* im, int stride) {
     make_keyframe_lite(s.cur, im, W, H, stride);
     // Update the small images for the rotation estimator (Tracker.cc:95-108)
@@ -1018,6 +1114,15 @@ int orc_tracker_refind_in_keyframes(void* tp, const uint8_t* const* images, int 
     orc::make_keyframe_lite(t->streams[s].cur, images[s], t->W, t->H, stride);
     t->refind(t->streams[s], orc::SE3::from12(se3 + 12 * s));
   }
+  return PTAM_OK;
+}
+int orc_tracker_epipolar_search(void* tp, int stream, int level, int src_kf, const double* src_se3, double src_depth_mean,
+                                double src_depth_sigma, const double* target_se3, double wiggle_scale, int n_cand,
+                                const int32_t* cand_xy, int32_t* found, int32_t* best_corner, double* sub_pos) {
+  Tracker* t = (Tracker*)tp;
+  if (stream < 0 || stream >= t->S || level < 0 || level >= PTAM_LEVELS || src_kf < 0 || src_kf >= (int)t->store.size()) return PTAM_ERR_INVALID;
+  t->epipolar_search(t->streams[stream], level, src_kf, orc::SE3::from12(src_se3), src_depth_mean, src_depth_sigma,
+                     orc::SE3::from12(target_se3), wiggle_scale, n_cand, cand_xy, found, best_corner, sub_pos);
   return PTAM_OK;
 }
 int orc_tracker_keyframe_rest(void* tp, int stream, double min_shi_tomasi_score) {

@@ -23,6 +23,7 @@ struct RefMapMaker : public MapMaker {
   using MapMaker::mvpKeyFrameQueue;
   void ResetNow() { if (mbResetRequested) Reset(); }
   int ReFindAllIn(KeyFrame& k) { return ReFindInSingleKeyFrame(k); }
+  bool Epipolar(KeyFrame& src, KeyFrame& tgt, int level, int cand) { return AddPointEpipolar(src, tgt, level, cand); }
 };
 struct RefTracker : public Tracker {
   RefTracker(CVD::ImageRef sz, const ATANCamera& c, Map& m, MapMaker& mm) : Tracker(sz, c, m, mm) {}
@@ -276,6 +277,48 @@ int ref_tracker_refind_in_keyframes(void* hp, const uint8_t* const* images, int 
     st.mm->ReFindAllIn(*st.refind_kf);
     st.refind_mode = true;
   }
+  return PTAM_OK;
+}
+// MapMaker::AddPointEpipolar (MapMaker.cc:529-688) for every candidate; source = stored keyframe, target =
+// the stream's current frame.  The new MapPoint the reference creates is read (sub-pixel target
+// position = kTarget.mMeasurements[pNew].v2RootPos, triangulated v3WorldPos) and removed again.
+// NB the reference caches UnProject of every pixel in a function-local static sized by the first call.
+int ref_tracker_epipolar_search(void* hp, int stream, int level, int src_kf, const double* src_se3, double src_depth_mean,
+                                double src_depth_sigma, const double* target_se3, double wiggle_scale, int n_cand,
+                                const int32_t* cand_xy, int32_t* found, int32_t* best_corner, double* sub_pos) {
+  Handle* h = (Handle*)hp;
+  if (stream < 0 || stream >= h->S || level < 0 || level >= LEVELS || src_kf < 0 || src_kf >= (int)h->store.size()) return PTAM_ERR_INVALID;
+  Stream& st = *h->streams[stream];
+  KeyFrame& src = *h->store[src_kf];
+  KeyFrame& tgt = current_kf(st);
+  src.se3CfromW = se3_from12(src_se3);
+  src.dSceneDepthMean = src_depth_mean; src.dSceneDepthSigma = src_depth_sigma;
+  tgt.se3CfromW = se3_from12(target_se3);
+  tgt.aLevels[level].bImplaneCornersCached = false;
+  tgt.aLevels[level].vImplaneCorners.clear();
+  st.mm->mdWiggleScale = wiggle_scale;
+  std::vector<Candidate> saved = src.aLevels[level].vCandidates;
+  src.aLevels[level].vCandidates.clear();
+  for (int c = 0; c < n_cand; c++) {
+    Candidate cd;
+    cd.irLevelPos = CVD::ImageRef(cand_xy[2 * c], cand_xy[2 * c + 1]);
+    cd.dSTScore = 0;
+    src.aLevels[level].vCandidates.push_back(cd);
+  }
+  for (int c = 0; c < n_cand; c++) {
+    found[c] = 0; best_corner[c] = -1; sub_pos[2 * c] = sub_pos[2 * c + 1] = 0;
+    const size_t before = st.map.vpPoints.size();
+    if (!st.mm->Epipolar(src, tgt, level, c)) continue;
+    MapPoint* p = st.map.vpPoints.back();
+    found[c] = 1;
+    const Measurement& m = tgt.mMeasurements[p];
+    sub_pos[2 * c] = m.v2RootPos[0]; sub_pos[2 * c + 1] = m.v2RootPos[1];
+    tgt.mMeasurements.erase(p); src.mMeasurements.erase(p);
+    st.map.vpPoints.resize(before);
+    delete p->pMMData; delete p;
+  }
+  src.aLevels[level].vCandidates = saved;
+  st.mm->mdWiggleScale = 1e30;
   return PTAM_OK;
 }
 int ref_tracker_keyframe_rest(void* hp, int stream, double min_shi_tomasi_score) {

@@ -73,7 +73,7 @@ TRACKER_SYMBOLS = [
     "tracker_make_keyframes", "tracker_track_frames", "tracker_synchronize", "tracker_get_level",
     "tracker_level_size", "tracker_get_points", "tracker_get_templates", "tracker_get_sbi",
     "tracker_keyframe_rest", "tracker_get_level_rest", "tracker_refind_in_keyframes",
-    "tracker_get_iteration_set",
+    "tracker_get_iteration_set", "tracker_epipolar_search",
 ]
 BUNDLE_SYMBOLS = [
     "bundle_default_params", "bundle_create", "bundle_destroy", "bundle_last_error",
@@ -166,6 +166,7 @@ class Lib:
             "tracker_refind_in_keyframes": (i, [vp, P(vp), i, P(d)]),
             "tracker_get_level_rest": (i, [vp, i, i, P(C.c_int32), i, P(C.c_int32), P(d), i, P(i)]),
             "tracker_get_iteration_set": (i, [vp, i, P(C.c_int32), i]),
+            "tracker_epipolar_search": (i, [vp, i, i, i, P(d), d, d, P(d), d, i, P(C.c_int32), P(C.c_int32), P(C.c_int32), P(d)]),
             "global_last_error": (C.c_char_p, []),
             "bundle_default_params": (None, [P(BundleParams)]),
             "bundle_create": (vp, [i, P(d), i, i, P(BundleParams)]),
@@ -423,6 +424,19 @@ class Tracker:
         imgs, arr = self._image_ptrs(images)
         p = _f64(poses12).reshape(self.S, 12)
         self._chk(self.lib.fn("tracker_refind_in_keyframes")(self.h, arr, self.W, _dp(p)))
+
+    def epipolar_search(self, stream, level, src_kf, src_pose12, src_depth_mean, src_depth_sigma, target_pose12, wiggle_scale, cand_xy):
+        """MapMaker::AddPointEpipolar up to the sub-pixel target position for every candidate (irLevelPos in the
+        stored source keyframe's level); target = the stream's current frame.  Returns (found (n,), best corner
+        index (n,), sub-pixel level-zero position in the target (n, 2))."""
+        c = _i32(cand_xy).reshape(-1, 2)
+        n = len(c)
+        found, best, sub = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32), np.zeros((max(n, 1), 2))
+        self._chk(self.lib.fn("tracker_epipolar_search")(self.h, stream, level, src_kf, _dp(_f64(src_pose12).reshape(12)),
+                                                        float(src_depth_mean), float(src_depth_sigma),
+                                                        _dp(_f64(target_pose12).reshape(12)), float(wiggle_scale), n, _ip(c),
+                                                        _ip(found), _ip(best), _dp(sub)))
+        return found[:n], best[:n], sub[:n]
 
     def keyframe_rest(self, stream, min_shi_tomasi_score=70.0):
         """KeyFrame::MakeKeyFrame_Rest for the stream's current frame; returns per level

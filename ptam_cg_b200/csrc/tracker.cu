@@ -90,6 +90,11 @@ struct ptam_tracker {
   DevBuf<double> rest_cand_score;
   DevBuf<int> rest_counts;
   int rest_stream = -1;
+  // AddPointEpipolar scratch (allocated / grown on first use)
+  DevBuf<int2> epi_cand;
+  DevBuf<double2> epi_implane;
+  DevBuf<int> epi_found, epi_best;
+  DevBuf<double> epi_sub;
   size_t sbi_smem = 0;
   DevBuf<uint8_t> tmpl;
   // pinned staging
@@ -120,6 +125,7 @@ struct ptam_tracker {
     warp_inv.free(); v2found.free(); sin_.free(); J.free(); e2.free(); src_kf.free(); src_level.free();
     tsum.free(); tsumsq.free(); flags.free(); level.free(); search_level.free(); outliers.free(); inliers.free();
     pvs.free(); iter_idx.free(); center.free(); tmpl.free();
+    epi_cand.free(); epi_implane.free(); epi_found.free(); epi_best.free(); epi_sub.free();
     if (stage_ev) cudaEventDestroy(stage_ev);
     for (auto e : prof_ev) if (e) cudaEventDestroy(e);
     for (int k = 0; k < 2; k++) {
@@ -698,6 +704,57 @@ int ptam_tracker_keyframe_rest(ptam_tracker* t, int stream, double min_shi_tomas
   PTAM_CUDA_TRY(t, cudaGetLastError());
   PTAM_CUDA_TRY(t, cudaStreamSynchronize(t->stream));
   t->rest_stream = stream;
+  return PTAM_OK;
+}
+
+int ptam_tracker_epipolar_search(ptam_tracker* t, int stream, int level, int src_kf, const double* src_se3, double src_depth_mean,
+                                 double src_depth_sigma, const double* target_se3, double wiggle_scale, int n_cand,
+                                 const int32_t* cand_xy, int32_t* found, int32_t* best_corner, double* sub_pos) {
+  cudaSetDevice(t->device);
+  if (stream < 0 || stream >= t->S || level < 0 || level >= kLevels) { t->set_error("bad stream / level"); return PTAM_ERR_INVALID; }
+  if (src_kf < 0 || src_kf >= (int)t->kf_bufs.size()) { t->set_error("unknown source keyframe"); return PTAM_ERR_INVALID; }
+  if (!t->dev.src.l0) { t->set_error("no current frame: run ptam_tracker_make_keyframes / track_frames first"); return PTAM_ERR_INVALID; }
+  if (n_cand <= 0) return PTAM_OK;
+  const Geom& g = t->dev.g;
+  if (!t->epi_implane.p) PTAM_CUDA_TRY(t, t->epi_implane.alloc(g.corner_stride));
+  if ((size_t)n_cand > t->epi_cand.n) {
+    t->epi_cand.free(); t->epi_found.free(); t->epi_best.free(); t->epi_sub.free();
+    PTAM_CUDA_TRY(t, t->epi_cand.alloc(n_cand)); PTAM_CUDA_TRY(t, t->epi_found.alloc(n_cand));
+    PTAM_CUDA_TRY(t, t->epi_best.alloc(n_cand)); PTAM_CUDA_TRY(t, t->epi_sub.alloc((size_t)2 * n_cand));
+  }
+  EpiDev e{};
+  e.stream = stream; e.level = level; e.src_kf = src_kf; e.n_cand = n_cand;
+  for (int i = 0; i < 12; i++) { e.src[i] = src_se3[i]; e.tgt[i] = target_se3[i]; }
+  e.d_start = std::max(wiggle_scale, src_depth_mean - src_depth_sigma);       // MapMaker.cc:552-556
+  e.d_end = std::min(40 * wiggle_scale, src_depth_mean + src_depth_sigma);
+  {  // mdOnePixelDist (ATANCamera.cc:59-64), on the host like the other derived camera parameters
+    const CamModel& c = t->dev.cam;
+    auto unproject = [&](double ix, double iy, double* o) {
+      const double d0 = (ix - c.center[0]) * c.inv_focal[0], d1 = (iy - c.center[1]) * c.inv_focal[1];
+      const double dr = std::sqrt(d0 * d0 + d1 * d1);
+      const double rr = c.w == 0.0 ? dr : std::tan(dr * c.w) * c.one_over_tan2;
+      const double f = dr > 0.01 ? rr / dr : 1.0;
+      o[0] = f * d0; o[1] = f * d1;
+    };
+    double uc[2], ua[2];
+    unproject(c.img_w / 2, c.img_h / 2, uc);
+    unproject(c.img_w / 2 + 1.0, c.img_h / 2 + 1.0, ua);
+    const double d0 = uc[0] - ua[0], d1 = uc[1] - ua[1];
+    const double one_pixel_dist = std::sqrt(d0 * d0 + d1 * d1) / std::sqrt(2.0);
+    const double md = one_pixel_dist * (4.0 + 1.0 * (1 << level));          // MapMaker.cc:618-619
+    e.max_dist_sq = md * md;
+  }
+  e.cand = t->epi_cand.p; e.implane = t->epi_implane.p; e.found = t->epi_found.p; e.best = t->epi_best.p; e.sub = t->epi_sub.p;
+  static_assert(sizeof(int2) == 2 * sizeof(int32_t), "candidate layout");
+  PTAM_CUDA_TRY(t, cudaMemcpyAsync(t->epi_cand.p, cand_xy, sizeof(int2) * n_cand, cudaMemcpyHostToDevice, t->stream));
+  k_epi_implane<<<(g.lev[level].corner_cap + 255) / 256, 256, 0, t->stream>>>(t->dev, e);
+  k_epi_search<<<(n_cand + 3) / 4, 128, 0, t->stream>>>(t->dev, e);
+  t->launches += 2;
+  PTAM_CUDA_TRY(t, cudaGetLastError());
+  PTAM_CUDA_TRY(t, cudaMemcpyAsync(found, t->epi_found.p, sizeof(int) * n_cand, cudaMemcpyDeviceToHost, t->stream));
+  PTAM_CUDA_TRY(t, cudaMemcpyAsync(best_corner, t->epi_best.p, sizeof(int) * n_cand, cudaMemcpyDeviceToHost, t->stream));
+  PTAM_CUDA_TRY(t, cudaMemcpyAsync(sub_pos, t->epi_sub.p, sizeof(double) * 2 * n_cand, cudaMemcpyDeviceToHost, t->stream));
+  PTAM_CUDA_TRY(t, cudaStreamSynchronize(t->stream));
   return PTAM_OK;
 }
 

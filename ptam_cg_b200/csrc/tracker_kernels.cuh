@@ -1614,4 +1614,237 @@ __global__ void __launch_bounds__(kPoseThreads, 2) k_pose(TrackerDev d, int stag
   }
 }
 
+// =============================================================================================
+// MapMaker::AddPointEpipolar (MapMaker.cc:529-688; SURVEY 8f rank 3, second half) up to the sub-pixel
+// position in the target keyframe.  Source = a stored keyframe, target = the stream's current frame.
+//   k_epi_implane  thread per target corner: vImplaneCorners (MapMaker.cc:608-614) = UnProject of the
+//                  truncated level-zero position.
+//   k_epi_search   warp per candidate: epipolar segment of the candidate's view ray in the target's
+//                  z = 1 plane (f64, every lane redundantly), un-warped 8x8 template
+//                  (MakeTemplateCoarseNoWarp), scan of ALL target corners of the level against the
+//                  segment (one corner per lane per pass), survivors queued per warp and scored four at
+//                  a time with the same 8-lane dp4a ZMSSD as k_search, first minimum <= mnMaxSSD, then
+//                  MakeSubPixTemplate + IterateSubPixToConvergence(10) in the same warp.
+// The triangulation that follows (a 4x4 SVD per accepted point, MapMaker.cc:176-187) stays with the caller.
+// =============================================================================================
+struct EpiDev {
+  int stream, level, src_kf, n_cand;
+  double src[12], tgt[12];   // se3CfromW of the source / target keyframe
+  double d_start, d_end;     // depth range along the ray (MapMaker.cc:552-556)
+  double max_dist_sq;        // (OnePixelDist (4 + LevelScale))^2
+  const int2* cand;          // irLevelPos of the candidates in the source level
+  double2* implane;          // [n_corners of the level]
+  int* found;                // 1: found and converged
+  int* best;                 // index of the best corner in the target level's list, -1 if none
+  double* sub;               // [n][2] sub-pixel level-zero position in the target
+};
+
+PTAM_DEV void cam_unproject(const CamModel& cam, double ix, double iy, double& ox, double& oy) {  // ATANCamera.cc:125-140
+  const double d0 = (ix - cam.center[0]) * cam.inv_focal[0];
+  const double d1 = (iy - cam.center[1]) * cam.inv_focal[1];
+  const double dr = sqrt(d0 * d0 + d1 * d1);
+  const double rr = cam.w == 0.0 ? dr : tan(dr * cam.w) * cam.one_over_tan2;
+  const double f = dr > 0.01 ? rr / dr : 1.0;
+  ox = f * d0; oy = f * d1;
+}
+
+__global__ void __launch_bounds__(256) k_epi_implane(TrackerDev d, EpiDev e) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nc = d.ctl[e.stream].n_corners[e.level];
+  if (i >= nc) return;
+  const int2 c = d.corners[(size_t)e.stream * d.g.corner_stride + d.g.lev[e.level].corner_off + i];
+  const double px = (double)(int)level_zero_pos((double)c.x, e.level), py = (double)(int)level_zero_pos((double)c.y, e.level);
+  double ox, oy;
+  cam_unproject(d.cam, px, py, ox, oy);
+  e.implane[i] = make_double2(ox, oy);
+}
+
+__global__ void __launch_bounds__(128) k_epi_search(TrackerDev d, EpiDev e) {
+  __shared__ __align__(8) uint8_t stmpl[4][64];
+  __shared__ int2 squeue[4][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ci = blockIdx.x * 4 + warp;
+  if (ci >= e.n_cand) return;
+  const int lv = e.level, s = e.stream;
+  const int2 cp = e.cand[ci];
+  auto fail = [&](int best_corner) {
+    if (lane == 0) { e.found[ci] = 0; e.best[ci] = best_corner; e.sub[2 * ci] = 0.0; e.sub[2 * ci + 1] = 0.0; }
+  };
+  // ---- epipolar segment (MapMaker.cc:541-596) ---------------------------------------------------
+  double normal[2], along[2], norm_dist, min_len, max_len;
+  {
+    double ux, uy;
+    cam_unproject(d.cam, level_zero_pos((double)cp.x, lv), level_zero_pos((double)cp.y, lv), ux, uy);
+    double ray[3] = {ux, uy, 1.0};
+    const double nr = sqrt(ray[0] * ray[0] + ray[1] * ray[1] + ray[2] * ray[2]);
+    for (int i = 0; i < 3; i++) ray[i] = ray[i] / nr;
+    double ray_w[3], dirn[3], c_w[3], c_t[3];
+    for (int i = 0; i < 3; i++) ray_w[i] = e.src[i] * ray[0] + e.src[3 + i] * ray[1] + e.src[6 + i] * ray[2];
+    for (int i = 0; i < 3; i++) dirn[i] = e.tgt[3 * i] * ray_w[0] + e.tgt[3 * i + 1] * ray_w[1] + e.tgt[3 * i + 2] * ray_w[2];
+    for (int i = 0; i < 3; i++) c_w[i] = -(e.src[i] * e.src[9] + e.src[3 + i] * e.src[10] + e.src[6 + i] * e.src[11]);
+    for (int i = 0; i < 3; i++) c_t[i] = (e.tgt[3 * i] * c_w[0] + e.tgt[3 * i + 1] * c_w[1] + e.tgt[3 * i + 2] * c_w[2]) + e.tgt[9 + i];
+    double rs[3], re[3];
+    for (int i = 0; i < 3; i++) { rs[i] = c_t[i] + e.d_start * dirn[i]; re[i] = c_t[i] + e.d_end * dirn[i]; }
+    if (re[2] <= rs[2] || re[2] <= 0.0) { fail(-1); return; }
+    if (rs[2] <= 0.0) {
+      const double k = 0.001 - rs[2] / dirn[2];
+      for (int i = 0; i < 3; i++) rs[i] += dirn[i] * k;
+    }
+    const double A[2] = {rs[0] / rs[2], rs[1] / rs[2]}, B[2] = {re[0] / re[2], re[1] / re[2]};
+    double al[2] = {A[0] - B[0], A[1] - B[1]};
+    if (al[0] * al[0] + al[1] * al[1] < 1e-8) { fail(-1); return; }
+    const double na = sqrt(al[0] * al[0] + al[1] * al[1]);
+    al[0] = al[0] / na; al[1] = al[1] / na;
+    along[0] = al[0]; along[1] = al[1];
+    normal[0] = al[1]; normal[1] = -al[0];
+    norm_dist = A[0] * normal[0] + A[1] * normal[1];
+    if (fabs(norm_dist) > d.cam.largest_radius) { fail(-1); return; }
+    const double la = al[0] * A[0] + al[1] * A[1], lb = al[0] * B[0] + al[1] * B[1];
+    min_len = fmin(la, lb) - 0.05;
+    max_len = fmax(la, lb) + 0.05;
+    if (min_len < -2.0) min_len = -2.0;
+    if (max_len < -2.0) max_len = -2.0;
+    if (min_len > 2.0) min_len = 2.0;
+    if (max_len > 2.0) max_len = 2.0;
+  }
+  // ---- MakeTemplateCoarseNoWarp (PatchFinder.cc:135-150): the 8x8 block around the candidate ------
+  const LevelDesc& L = d.g.lev[lv];
+  if (!(cp.x >= 5 && cp.y >= 5 && cp.x < L.w - 5 && cp.y < L.h - 5)) { fail(-1); return; }
+  int tsum, tsumsq;
+  {
+    const uint8_t* src = d.kf_ptrs[e.src_kf] + L.img_off;
+    const int trow = lane >> 2, tcol = (lane & 3) * 2;
+    const uint8_t* sp = src + (size_t)(cp.y - 4 + trow) * L.pitch + (cp.x - 4 + tcol);
+    const int t0 = sp[0], t1 = sp[1];
+    tsum = warp_sum_int(t0 + t1);
+    tsumsq = warp_sum_int(t0 * t0 + t1 * t1);
+    stmpl[warp][2 * lane] = (uint8_t)t0; stmpl[warp][2 * lane + 1] = (uint8_t)t1;
+  }
+  __syncwarp();
+  // ---- scan of all target corners (MapMaker.cc:616-636) ------------------------------------------
+  int pitch;
+  const uint8_t* im = level_image(d, s, lv, pitch);
+  const int nc = d.ctl[s].n_corners[lv];
+  const int2* corners = d.corners + (size_t)s * d.g.corner_stride + L.corner_off;
+  const int sub = lane & 7, grp = lane >> 3;
+  const unsigned tw0 = *reinterpret_cast<const unsigned*>(&stmpl[warp][8 * sub]);
+  const unsigned tw1 = *reinterpret_cast<const unsigned*>(&stmpl[warp][8 * sub + 4]);
+  int best_ssd = kMaxSSD + 1, best_idx = 0x7fffffff;
+  auto process = [&](int n) {
+    for (int r0 = 0; r0 < n; r0 += 4) {
+      const int kq = r0 + grp;
+      const bool valid = kq < n;
+      const int2 q = squeue[warp][valid ? kq : 0];
+      const int cx = q.x & 0xffff, cy = q.x >> 16;
+      const uint8_t* ip = im + (size_t)(cy - 4 + sub) * pitch + (cx - 4);
+      const unsigned a = (unsigned)(reinterpret_cast<uintptr_t>(ip) & 3);
+      const unsigned* wp = reinterpret_cast<const unsigned*>(ip - a);
+      const unsigned w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = a ? __ldg(wp + 2) : 0u;
+      const unsigned sel = 0x3210u + 0x1111u * a;
+      const unsigned v0 = __byte_perm(w0, w1, sel), v1 = __byte_perm(w1, w2, sel);
+      int isum = (int)__dp4a(v0, 0x01010101u, __dp4a(v1, 0x01010101u, 0u));
+      int isq = (int)__dp4a(v0, v0, __dp4a(v1, v1, 0u));
+      int cross = (int)__dp4a(v0, tw0, __dp4a(v1, tw1, 0u));
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        isum += __shfl_xor_sync(kFull, isum, o);
+        isq += __shfl_xor_sync(kFull, isq, o);
+        cross += __shfl_xor_sync(kFull, cross, o);
+      }
+      const int SA = tsum, SB = isum;
+      const int ssd = ((2 * SA * SB - SA * SA - SB * SB) / 64 + isq + tsumsq - 2 * cross);
+      if (valid && (ssd < best_ssd || (ssd == best_ssd && q.y < best_idx))) { best_ssd = ssd; best_idx = q.y; }
+    }
+    __syncwarp();
+  };
+  int qn = 0;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int b0 = 0; b0 < nc; b0 += 32) {
+    const int i = b0 + lane;
+    int2 c = make_int2(0, 0);
+    bool pass = false;
+    if (i < nc) {
+      const double2 ip = e.implane[i];
+      const double dd = norm_dist - (ip.x * normal[0] + ip.y * normal[1]);
+      if (!(dd * dd > e.max_dist_sq)) {
+        const double al = ip.x * along[0] + ip.y * along[1];
+        if (!(al < min_len) && !(al > max_len)) {
+          c = corners[i];
+          pass = c.x >= 4 && c.y >= 4 && c.x < L.w - 4 && c.y < L.h - 4;  // else ZMSSDAtPoint = mnMaxSSD + 1: never the best
+        }
+      }
+    }
+    const unsigned m = __ballot_sync(kFull, pass);
+    if (pass) squeue[warp][qn + __popc(m & lt)] = make_int2(c.x | (c.y << 16), i);
+    qn += __popc(m);
+    if (qn > 32) { __syncwarp(); process(qn); qn = 0; }
+  }
+  __syncwarp();
+  process(qn);
+  {
+    const int bs = __reduce_min_sync(kFull, best_ssd);
+    best_idx = __reduce_min_sync(kFull, best_ssd == bs ? best_idx : 0x7fffffff);
+    best_ssd = bs;
+  }
+  if (!(best_ssd < kMaxSSD + 1)) { fail(-1); return; }  // nBest == -1
+  const int2 bc = corners[best_idx];
+  // ---- MakeSubPixTemplate + IterateSubPixToConvergence(kTarget, 10) (MapMaker.cc:640-646) -------
+  float jx[2] = {0.f, 0.f}, jy[2] = {0.f, 0.f};
+  int tq[2] = {0, 0};
+  double h00 = 0, h01 = 0, h02 = 0, h11 = 0, h12 = 0, h22 = 0;
+#pragma unroll
+  for (int q = 0; q < 2; q++) {
+    const int pi = lane + 32 * q;
+    if (pi < 36) {
+      const int y = pi / 6 + 1, x = pi % 6 + 1;
+      const uint8_t* T = stmpl[warp];
+      const double gx = 0.5 * (double)((int)T[8 * y + x + 1] - (int)T[8 * y + x - 1]);
+      const double gy = 0.5 * (double)((int)T[8 * (y + 1) + x] - (int)T[8 * (y - 1) + x]);
+      jx[q] = (float)gx; jy[q] = (float)gy; tq[q] = T[8 * y + x];
+      h00 += gx * gx; h01 += gx * gy; h02 += gx; h11 += gy * gy; h12 += gy; h22 += 1.0;
+    }
+  }
+  double H[9], Hi[9];
+  H[0] = warp_sum(h00); H[1] = H[3] = warp_sum(h01); H[2] = H[6] = warp_sum(h02);
+  H[4] = warp_sum(h11); H[5] = H[7] = warp_sum(h12); H[8] = warp_sum(h22);
+  ldlt_inverse<3>(H, Hi);
+  double sp[2] = {level_zero_pos((double)bc.x, lv), level_zero_pos((double)bc.y, lv)};
+  double mean_diff = 0.0;
+  bool converged = false;
+  for (int it = 0; it < 10; it++) {
+    const double cx = level_n_pos(sp[0], lv), cy = level_n_pos(sp[1], lv);
+    const int rx = (int)(cx > 0.0 ? cx + 0.5 : cx - 0.5), ry = (int)(cy > 0.0 ? cy + 0.5 : cy - 0.5);
+    if (!(rx >= 5 && ry >= 5 && rx < L.w - 5 && ry < L.h - 5)) break;
+    const double bx = cx - 4, by = cy - 4;
+    const double dX = bx - floor(bx), dY = by - floor(by);
+    const float fTL = (float)((1.0 - dX) * (1.0 - dY));
+    const float fTR = (float)((dX) * (1.0 - dY));
+    const float fBL = (float)((1.0 - dX) * (dY));
+    const float fBR = (float)((dX) * (dY));
+    const int ibx = (int)bx, iby = (int)by;
+    double a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      const int pi = lane + 32 * q;
+      if (pi < 36) {
+        const int y = pi / 6 + 1, x = pi % 6 + 1;
+        const uint8_t* tl = im + (size_t)(iby + y) * pitch + ibx + x;
+        const float fp = fTL * (float)tl[0] + fTR * (float)tl[1] + fBL * (float)tl[pitch] + fBR * (float)tl[pitch + 1];
+        const double diff = (double)(fp - (float)tq[q]) + mean_diff;
+        a0 += diff * (double)jx[q]; a1 += diff * (double)jy[q]; a2 += diff;
+      }
+    }
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+    const double u0 = Hi[0] * a0 + Hi[1] * a1 + Hi[2] * a2;
+    const double u1 = Hi[3] * a0 + Hi[4] * a1 + Hi[5] * a2;
+    const double u2 = Hi[6] * a0 + Hi[7] * a1 + Hi[8] * a2;
+    sp[0] -= u0 * (double)(1 << lv);
+    sp[1] -= u1 * (double)(1 << lv);
+    mean_diff -= u2;
+    if (u0 * u0 + u1 * u1 < 0.03 * 0.03) { converged = true; break; }
+  }
+  if (!converged) { fail(best_idx); return; }
+  if (lane == 0) { e.found[ci] = 1; e.best[ci] = best_idx; e.sub[2 * ci] = sp[0]; e.sub[2 * ci + 1] = sp[1]; }
+}
+
 }  // namespace ptam

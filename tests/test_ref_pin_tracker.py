@@ -164,3 +164,45 @@ def test_keyframe_rest_matches_reference():
         assert np.array_equal(mo, mr) and np.array_equal(co, cr) and np.array_equal(so, sr)
         n += len(co)
     assert n > 50
+
+
+def _epipolar_case(lib, W, H, frames, poses, i_src, i_tgt, depth=(1.0, 0.3), wiggle=0.1):
+    """Candidates = Shi-Tomasi candidates of the source frame; returns per level (cand, found, best, sub)."""
+    t = Tracker(lib, W, H, 1)
+    kf = t.add_keyframe(frames[i_src])
+    t.make_keyframes([frames[i_src]])
+    rest = t.keyframe_rest(0, 70.0)
+    t.make_keyframes([frames[i_tgt]])
+    out = []
+    for l in range(4):
+        cand = rest[l][1]
+        out.append((cand,) + t.epipolar_search(0, l, kf, poses[i_src], depth[0], depth[1], poses[i_tgt], wiggle, cand))
+    return out
+
+
+@pytest.mark.parametrize("pair", [(0, 30), (10, 25), (30, 0)], ids=lambda p: f"src{p[0]}-tgt{p[1]}")
+def test_epipolar_search_matches_reference(pair):
+    """MapMaker::AddPointEpipolar (MapMaker.cc:529-688), SURVEY 8f rank 3: the same candidates accepted,
+    the same sub-pixel positions in the target keyframe."""
+    W, H = 320, 240  # NB AddPointEpipolar caches UnProject per pixel in a function-local static: one size per process
+    frames, poses = synth.render_sequence(W, H, 40)
+    o = _epipolar_case(oracle_lib(libm_atan=True), W, H, frames, poses, *pair)
+    r = _epipolar_case(REF, W, H, frames, poses, *pair)
+    total = 0
+    for (co, fo, bo, so), (cr, fr, br, sr) in zip(o, r):
+        assert np.array_equal(co, cr) and np.array_equal(fo, fr)
+        assert np.array_equal(so, sr)
+        total += int(fo.sum())
+    assert total > 200
+
+
+def test_epipolar_search_degenerate_geometry_matches_reference():
+    """Same pose for both keyframes (zero baseline: the projected segment collapses) and a depth range behind
+    the target: every early exit of AddPointEpipolar."""
+    W, H = 320, 240
+    frames, poses = synth.render_sequence(W, H, 40)
+    for args in [dict(i_src=5, i_tgt=5), dict(i_src=0, i_tgt=30, depth=(-3.0, 0.1), wiggle=-5.0), dict(i_src=0, i_tgt=30, depth=(50.0, 1.0))]:
+        o = _epipolar_case(oracle_lib(libm_atan=True), W, H, frames, poses, **args)
+        r = _epipolar_case(REF, W, H, frames, poses, **args)
+        for (co, fo, bo, so), (cr, fr, br, sr) in zip(o, r):
+            assert np.array_equal(fo, fr) and np.array_equal(so, sr)
