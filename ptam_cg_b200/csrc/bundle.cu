@@ -11,6 +11,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <type_traits>
@@ -79,6 +81,7 @@ struct ptam_bundle {
   int device = 0;
   cudaStream_t stream = nullptr, stream2 = nullptr;
   std::vector<cudaEvent_t> ev_panel, ev_tail;
+  std::vector<char> tail_of;  // panel k launched a tail update
   std::string err;
   int64_t launches = 0;
   ptam_bundle_params prm{};
@@ -167,6 +170,7 @@ struct ptam_bundle {
     if (p) prm = *p; else ptam_bundle_default_params(&prm);
     cam = ptam_make_cam_model(cam_params, w, h);
     PTAM_CUDA_TRY(this, cudaFuncSetAttribute(k_ldlt_update, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpdateSmem));
+    PTAM_CUDA_TRY(this, cudaFuncSetAttribute(k_ldlt_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPanelSmem));
     return PTAM_OK;
   }
 
@@ -281,17 +285,18 @@ struct ptam_bundle {
     return PTAM_OK;
   }
 
-  // Blocked LDL^T with one-panel look-ahead on two streams.  For panel k: the trailing update is split
-  // into its head U1(k) (the next panel's 64 columns) and its tail U2(k).  Main stream: panel(k),
-  // U1(k), panel(k+1), ...; second stream: U2(k) after panel(k).  U1(k) waits for U2(k-1) (same tiles,
-  // read-modify-write), so panel(k+1) overlaps U2(k).  Wp is double-buffered by panel parity.
+  // Blocked LDL^T on two streams.  Panel k's kernel first applies the part of panel k-1's trailing update
+  // that falls on its own 64 columns (fused: k_ldlt_panel), so the main stream is ONE kernel per panel;
+  // the rest of panel k's trailing update (column blocks from k+2 on: the tail) runs on the second stream
+  // after panel k.  Panel k+1 does not touch those tiles and overlaps it; panel k+2 waits for it (it reads
+  // tiles that tail updates and overwrites the Wp buffer it reads).  Wp is double-buffered by panel parity.
   int solve_reduced() {
     const int n = d.n;
     if (n == 0) return PTAM_OK;
     const int n_panels = (n + kNB - 1) / kNB;
     if ((int)ev_panel.size() < n_panels) {
       const size_t old = ev_panel.size();
-      ev_panel.resize(n_panels); ev_tail.resize(n_panels);
+      ev_panel.resize(n_panels); ev_tail.resize(n_panels); tail_of.resize(n_panels, false);
       for (size_t k = old; k < ev_panel.size(); k++) {
         PTAM_CUDA_TRY(this, cudaEventCreateWithFlags(&ev_panel[k], cudaEventDisableTiming));
         PTAM_CUDA_TRY(this, cudaEventCreateWithFlags(&ev_tail[k], cudaEventDisableTiming));
@@ -303,22 +308,22 @@ struct ptam_bundle {
       const int nb = std::min(kNB, n - k0);
       const int rem = n - k0 - nb;
       double* wp = Wp.p + (size_t)(k & 1) * n * kNB;
-      k_ldlt_panel<<<std::max(1, (rem + kPanelRows - 1) / kPanelRows), kPanelThreads, 0, stream>>>(d.S, wp, d.vE, n, k0);
+      const double* wprev = k > 0 ? Wp.p + (size_t)((k - 1) & 1) * n * kNB : nullptr;
+      // panel k reads tiles the tail of panel k-2 updated, and overwrites the Wp buffer that tail read
+      if (k >= 2 && tail_of[k - 2]) PTAM_CUDA_TRY(this, cudaStreamWaitEvent(stream, ev_tail[k - 2], 0));
+      k_ldlt_panel<<<std::max(1, (rem + kPanelRows - 1) / kPanelRows), kPanelThreads, kPanelSmem, stream>>>(d.S, wp, wprev, d.vE, n, k0);
       launches++;
-      if (rem > 0) {
+      tail_of[k] = false;
+      if (rem > kNB) {  // column blocks from k+2 on exist: the tail of the trailing update, on the second stream
         const int nt = (rem + kUTM - 1) / kUTM;
         const int n_tail = nt * (nt + 1) - nt;
-        if (n_tail > 0) {
-          PTAM_CUDA_TRY(this, cudaEventRecord(ev_panel[k], stream));
-          PTAM_CUDA_TRY(this, cudaStreamWaitEvent(stream2, ev_panel[k], 0));
-          k_ldlt_update<<<n_tail, 256, kUpdateSmem, stream2>>>(d.S, wp, n, k0, 2);
-          PTAM_CUDA_TRY(this, cudaEventRecord(ev_tail[k], stream2));
-          launches++;
-        }
-        if (last_tail >= 0) PTAM_CUDA_TRY(this, cudaStreamWaitEvent(stream, ev_tail[last_tail], 0));
-        k_ldlt_update<<<nt, 256, kUpdateSmem, stream>>>(d.S, wp, n, k0, 1);
+        PTAM_CUDA_TRY(this, cudaEventRecord(ev_panel[k], stream));
+        PTAM_CUDA_TRY(this, cudaStreamWaitEvent(stream2, ev_panel[k], 0));
+        k_ldlt_update<<<n_tail, 256, kUpdateSmem, stream2>>>(d.S, wp, n, k0, 2);
+        PTAM_CUDA_TRY(this, cudaEventRecord(ev_tail[k], stream2));
         launches++;
-        last_tail = n_tail > 0 ? k : -1;
+        tail_of[k] = true;
+        last_tail = k;
       }
     }
     if (last_tail >= 0) PTAM_CUDA_TRY(this, cudaStreamWaitEvent(stream, ev_tail[last_tail], 0));

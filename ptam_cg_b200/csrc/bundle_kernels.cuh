@@ -483,15 +483,18 @@ constexpr int kUTN = 64;    // trailing-update tile columns
 constexpr int kLds = kNB + 4;  // padded shared-memory row, doubles
 constexpr int kUpdateSmem = (kUTM + kUTN) * kLds * (int)sizeof(double) + 16;
 
-// LDL^T of a 64x64 block held in registers by 256 threads: thread (ty = tid / 16, tx = tid % 16) owns
-// rows ty + 16 i x columns tx + 16 j (i, j < 4).  One barrier per column: the owners of column `col`
-// publish it (double-buffered) and the owner of the pivot publishes its reciprocal, so the only
-// serial chain per column is  update -> reciprocal -> barrier -> rank-1 update.  The 16-column groups
-// are unrolled so that all register indices and the dead-row / dead-column tests are static.
-// The right-hand side rides along as one more column (threads tx == 0 hold y of their rows):
-// y_t -= l_t y_col is the forward substitution L y' = y.
-// L = value * (1 / d) as TooN's Cholesky does.  Result: `a` holds L (strict lower) and D (diagonal),
-// `ysh` the forward-substituted right-hand side, `dinv` the reciprocals of D.
+// LDL^T of a 64x64 block by 256 threads, eight sub-panels of eight columns.  The trailing matrix lives in
+// registers (thread (ty = tid / 16, tx = tid % 16) owns rows ty + 16 i x columns tx + 16 j, i, j < 4); the
+// current 64 x 8 sub-panel is handled by threads 0..63, one row each.  Every row thread factors the 8x8
+// diagonal block of the sub-panel REDUNDANTLY in its own registers (36 broadcast loads), so that pivots,
+// reciprocals and the L D values of the pivot rows need no exchange: the serial chain per pivot is
+// reciprocal -> multiply -> FMA, with the thread's own row riding along.  Then all warps apply the rank-8
+// update to their register tiles from shared memory (L in `a`, L D in `us`) and the owners of the next
+// eight columns hand them over: two block barriers per sub-panel, 16 per block instead of 64.
+// The right-hand side rides along with the row threads (y_r -= l_r y_col: the forward substitution L y' = y).
+// L = value * (1 / d) as TooN's Cholesky does, subtractions in ascending column order as in its
+// left-looking loop.  Result: `a` holds L (strict lower) and D (diagonal), `ysh` the forward-substituted
+// right-hand side, `dinv` the reciprocals of D.  Entries above the diagonal are scratch.
 constexpr int kPanelThreads = 256;
 constexpr int kPanelRows = 64;  // rows of the panel solved per CTA (threads 0..63; more CTAs beat fuller CTAs here)
 #ifdef PTAM_PANEL_DEBUG
@@ -502,95 +505,199 @@ __device__ long long g_dbg[8];
 #endif
 constexpr int kLda = kNB + 2;  // even row pitch: (row, even column) pairs are 16-byte aligned
 
-template <int JC>
-PTAM_DEV void block_ldlt64_group(double (&ar)[4][4], double (&yr)[4], double (*ucol)[kNB], double (*piv)[2], double* dinv, int nb) {
+PTAM_DEV void block_ldlt64(double (*a)[kLda], double (*us)[8], double* dinv, double* ysh, int nb) {
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-#pragma unroll 1
-  for (int cc = 0; cc < 16; cc++) {
-    const int col = 16 * JC + cc;
-    if (col >= nb) break;
-    const int buf = col & 1;
-    if (tx == cc) {  // owners of column col: rows t = ty + 16 i, i >= JC (entries with t <= col are unused)
+  double ar[4][4];
 #pragma unroll
-      for (int i = JC; i < 4; i++) ucol[buf][ty + 16 * i] = ar[i][JC];
-      if (ty == cc) {  // pivot (col, col) = slot (i = JC, j = JC) of thread (ty = cc, tx = cc)
-        const double r = 1.0 / ar[JC][JC];
-        piv[buf][0] = r;
-        dinv[col] = r;
-      }
-    }
-    if (tx == 0 && ty == cc) piv[buf][1] = yr[JC];  // y'_col is final once the previous columns are done
-    __syncthreads();
-    const double di = piv[buf][0], ycol = piv[buf][1];
-    // Dead rows (t <= col or t >= nb) get l = 0 and dead columns (c <= col) get u = 0, so the rank-1
-    // update below needs no per-element tests.  It also touches the strict upper triangle (c > t) of
-    // the register tile, which is never read.
-    double uc[4], lt[4];
-#pragma unroll
-    for (int j = JC; j < 4; j++) {
-      const double v = ucol[buf][tx + 16 * j];
-      uc[j] = (j > JC || tx > cc) ? v : 0.0;
-    }
-#pragma unroll
-    for (int i = JC; i < 4; i++) {
-      const int t = ty + 16 * i;
-      const double v = ucol[buf][t] * di;
-      lt[i] = ((i > JC || ty > cc) && t < nb) ? v : 0.0;
-    }
-#pragma unroll
-    for (int i = JC; i < 4; i++) {
-#pragma unroll
-      for (int j = JC; j < 4; j++) ar[i][j] -= lt[i] * uc[j];
-      if (tx == 0) yr[i] -= lt[i] * ycol;
-      if (tx == cc && (i > JC || ty > cc)) ar[i][JC] = lt[i];
-    }
-  }
-}
-
-PTAM_DEV void block_ldlt64(double (*a)[kLda], double (*ucol)[kNB], double (*piv)[2], double* dinv, double* ysh, int nb) {
-  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-  double ar[4][4], yr[4];
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
+  for (int i = 0; i < 4; i++)
 #pragma unroll
     for (int j = 0; j < 4; j++) ar[i][j] = a[ty + 16 * i][tx + 16 * j];
-    yr[i] = ysh[ty + 16 * i];
-  }
+  double yr = tid < kNB ? ysh[tid] : 0.0;  // threads 0..63 own one row of the current sub-panel each
   if (tid < kNB) dinv[tid] = 1.0;
   __syncthreads();
-  block_ldlt64_group<0>(ar, yr, ucol, piv, dinv, nb);
-  block_ldlt64_group<1>(ar, yr, ucol, piv, dinv, nb);
-  block_ldlt64_group<2>(ar, yr, ucol, piv, dinv, nb);
-  block_ldlt64_group<3>(ar, yr, ucol, piv, dinv, nb);
-  __syncthreads();
+#pragma unroll 1
+  for (int c0 = 0; c0 < kNB; c0 += 8) {
+    if (c0 >= nb) break;  // the identity padding of a short last block needs no work
+    if (tid < kNB) {
+      const int r = tid;
+      // the 8x8 diagonal block of the sub-panel and its right-hand side, redundantly in every row thread
+      // (broadcast loads): pivots, reciprocals and the L D values then need no exchange at all
+      double dg[8][8], yv[8], pv[8], uv[8];
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
+      for (int i = 0; i < 8; i++) {
 #pragma unroll
-    for (int j = 0; j < 4; j++) a[ty + 16 * i][tx + 16 * j] = ar[i][j];
-    if (tx == 0) ysh[ty + 16 * i] = yr[i];
+        for (int j = 0; j <= i; j++) dg[i][j] = a[c0 + i][c0 + j];
+        yv[i] = ysh[c0 + i];
+      }
+      {
+        const double2* row = reinterpret_cast<const double2*>(&a[r][c0]);
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) { const double2 v = row[j >> 1]; pv[j] = v.x; pv[j + 1] = v.y; }
+      }
+      // the two row warps have read the diagonal block before its owners overwrite it below
+      asm volatile("bar.sync 1, 64;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const double rcp = 1.0 / dg[j][j];
+        if (r == c0 + j) dinv[c0 + j] = rcp;
+        // own row (rows of the finished part and the pivot row itself stay as they are)
+        const bool below = r > c0 + j;
+        const double v = pv[j];
+        const double l = below ? v * rcp : 0.0;
+#pragma unroll
+        for (int q = j + 1; q < 8; q++) pv[q] -= l * dg[q][j];  // dg[q][j] still holds L D of row c0 + q
+        yr -= l * yv[j];
+        uv[j] = below ? v : 0.0;
+        if (below) pv[j] = l;
+        // the diagonal block itself
+#pragma unroll
+        for (int i = j + 1; i < 8; i++) {
+          const double li = dg[i][j] * rcp;
+#pragma unroll
+          for (int q = j + 1; q <= i; q++) dg[i][q] -= li * dg[q][j];
+          yv[i] -= li * yv[j];
+        }
+      }
+      if (r >= c0) {
+        double2* row = reinterpret_cast<double2*>(&a[r][c0]);
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) row[j >> 1] = make_double2(pv[j], pv[j + 1]);
+      }
+      double2* urow = reinterpret_cast<double2*>(&us[r][0]);
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) urow[j >> 1] = make_double2(uv[j], uv[j + 1]);
+      ysh[r] = yr;
+    }
+    __syncthreads();
+    const int t0 = c0 + 8;  // first row / column of the trailing matrix
+    if (t0 < kNB) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        if (16 * i + 15 < t0) continue;
+        double l[8];
+        {
+          const double2* row = reinterpret_cast<const double2*>(&a[ty + 16 * i][c0]);
+#pragma unroll
+          for (int q = 0; q < 8; q += 2) { const double2 v = row[q >> 1]; l[q] = v.x; l[q + 1] = v.y; }
+        }
+        if (ty + 16 * i < t0) {  // rows of the finished sub-panels: their entries here are scratch, keep them finite
+#pragma unroll
+          for (int q = 0; q < 8; q++) l[q] = 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j <= i; j++) {
+          if (16 * j + 15 < t0) continue;
+          const double2* urow = reinterpret_cast<const double2*>(&us[tx + 16 * j][0]);
+          double acc = ar[i][j];
+#pragma unroll
+          for (int q = 0; q < 8; q += 2) { const double2 v = urow[q >> 1]; acc -= l[q] * v.x; acc -= l[q + 1] * v.y; }
+          ar[i][j] = acc;
+        }
+      }
+      // the owners of the next eight columns hand them to warp 0 (rows >= t0)
+      const int jn = t0 >> 4;
+      if ((tx >> 3) == ((t0 >> 3) & 1)) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int r = ty + 16 * i;
+          if (r >= t0) {
+            // ar[i][jn] with a run-time jn: select without dynamic register indexing
+            const double v = jn == 0 ? ar[i][0] : jn == 1 ? ar[i][1] : jn == 2 ? ar[i][2] : ar[i][3];
+            a[r][tx + 16 * jn] = v;
+          }
+        }
+      }
+    }
+    __syncthreads();
   }
-  __syncthreads();
 }
 
-__global__ void __launch_bounds__(kPanelThreads) k_ldlt_panel(double* A, double* Wp, double* y, int n, int k0) {
-  __shared__ __align__(16) double a[kNB][kLda];
-  __shared__ double ucol[2][kNB];
-  __shared__ double piv[2][2];
-  __shared__ double y1[kNB];
-  __shared__ double dinv[kNB];
+// Shared memory of k_ldlt_panel (dynamic): the diagonal block, the rank-8 operand, the right-hand side and
+// the reciprocals, plus three 64x64 operands of the PENDING update (see below); the third is reused for
+// the updated rows of this CTA.
+constexpr int kPanelSmem = (4 * kNB * kLda + kNB * 8 + 2 * kNB) * (int)sizeof(double);
+
+// Panel k, fused with the head of panel k-1's trailing update.  The columns of panel k still miss the
+// contribution of panel k-1 (the tail kernel of panel k-1 only covers the column blocks from k+1 on), so
+// every CTA first applies it itself:  A[rows][cols k] += Wp_prev[rows] L_head^T  for the diagonal block
+// (all CTAs, redundantly, like the factorisation) and for its own 64 rows, 4x4 register tiles over K = 64.
+// That makes the chain one kernel per panel instead of panel -> head update -> panel.
+__global__ void __launch_bounds__(kPanelThreads) k_ldlt_panel(double* A, double* Wp, const double* Wprev, double* y, int n, int k0) {
+  extern __shared__ __align__(16) unsigned char panel_smem[];
+  double (*a)[kLda] = reinterpret_cast<double (*)[kLda]>(panel_smem);
+  double (*lh)[kLda] = a + kNB;    // L of the diagonal block's rows in panel k-1's columns
+  double (*wd)[kLda] = lh + kNB;   // Wp_prev rows of the diagonal block
+  double (*wo)[kLda] = wd + kNB;   // Wp_prev rows of this CTA, then the updated rows themselves
+  double (*us)[8] = reinterpret_cast<double (*)[8]>(wo + kNB);
+  double* y1 = reinterpret_cast<double*>(us + kNB);
+  double* dinv = y1 + kNB;
   const int nb = min(kNB, n - k0);
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int row0 = k0 + nb + blockIdx.x * kPanelRows;
+  const int rows_own = min(kPanelRows, n - row0);  // <= 0: the last panel's single CTA has no rows below the block
+  const bool pend = Wprev != nullptr;
 #ifdef PTAM_PANEL_DEBUG
   long long t_prev = clock64();
 #endif
   for (int i = tid; i < kNB * kNB; i += blockDim.x) {
     const int r = i / kNB, c = i % kNB;
     a[r][c] = (r < nb && c <= r) ? A[(size_t)(k0 + r) * n + k0 + c] : (r == c ? 1.0 : 0.0);
+    if (pend) {
+      lh[r][c] = r < nb ? A[(size_t)(k0 + r) * n + (k0 - kNB) + c] : 0.0;
+      wd[r][c] = r < nb ? Wprev[(size_t)(k0 + r) * kNB + c] : 0.0;
+      wo[r][c] = r < rows_own ? Wprev[(size_t)(row0 + r) * kNB + c] : 0.0;
+    }
   }
   if (tid < kNB) y1[tid] = tid < nb ? y[k0 + tid] : 0.0;
+  // this CTA's rows of the panel, as 4x4 register tiles (rows ty + 16 i, columns tx + 16 j)
+  double co[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int r = ty + 16 * i;
+      co[i][j] = r < rows_own ? A[(size_t)(row0 + r) * n + k0 + tx + 16 * j] : 0.0;
+    }
+  __syncthreads();
+  if (pend) {
+    double cd[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) cd[i][j] = a[ty + 16 * i][tx + 16 * j];
+#pragma unroll 2
+    for (int q = 0; q < kNB; q += 2) {
+      double2 vd[4], vo[4], vl[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        vd[i] = *reinterpret_cast<const double2*>(&wd[ty + 16 * i][q]);
+        vo[i] = *reinterpret_cast<const double2*>(&wo[ty + 16 * i][q]);
+        vl[i] = *reinterpret_cast<const double2*>(&lh[tx + 16 * i][q]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          cd[i][j] += vd[i].x * vl[j].x; cd[i][j] += vd[i].y * vl[j].y;
+          co[i][j] += vo[i].x * vl[j].x; co[i][j] += vo[i].y * vl[j].y;
+        }
+    }
+    __syncthreads();  // every thread is done with wd / wo / lh
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int r = ty + 16 * i, c = tx + 16 * j;
+        if (r < nb && c <= r) a[r][c] = cd[i][j];  // the identity padding of a short last block stays
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) wo[ty + 16 * i][tx + 16 * j] = co[i][j];
   __syncthreads();
   DBG_T(0)
-  block_ldlt64(a, ucol, piv, dinv, y1, nb);
+  block_ldlt64(a, us, dinv, y1, nb);
   DBG_T(1)
   if (blockIdx.x == 0) {
     for (int i = tid; i < nb * nb; i += blockDim.x) {
@@ -601,12 +708,12 @@ __global__ void __launch_bounds__(kPanelThreads) k_ldlt_panel(double* A, double*
   }
   DBG_T(2)
   // ---- rows below the block: one thread per row
-  const int row = k0 + nb + blockIdx.x * kPanelRows + tid;
+  const int row = row0 + tid;
   if (tid >= kPanelRows || row >= n) return;  // nb < kNB only on the last panel, which has no rows below it
   double x[kNB];
   double* Ar = A + (size_t)row * n + k0;
 #pragma unroll
-  for (int c = 0; c < kNB; c += 2) { const double2 v = *reinterpret_cast<const double2*>(Ar + c); x[c] = v.x; x[c + 1] = v.y; }
+  for (int c = 0; c < kNB; c += 2) { const double2 v = *reinterpret_cast<const double2*>(&wo[tid][c]); x[c] = v.x; x[c + 1] = v.y; }
   DBG_T(3)
   // w L11^T = a, two columns at a time (right-looking: independent updates, one 16-byte broadcast
   // load of (L[c2][c], L[c2][c+1]) per two FMAs)

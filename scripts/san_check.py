@@ -27,3 +27,8 @@ for f in (1, 2, 3):
     r = t.track_frames([frames[f], frames[f]])
 print("trk", sum(r[0].meas_found), r[0].did_coarse)
 print("rest", [len(x[0]) for x in t.keyframe_rest(1)])
+kf = t.add_keyframe(frames[0])
+t.make_keyframes([frames[0], frames[0]])
+cands = [x[1] for x in t.keyframe_rest(0)]
+t.make_keyframes([frames[5], frames[5]])
+print("epi", [int(t.epipolar_search(0, l, kf, poses[0], 1.0, 0.3, poses[5], 0.1, cands[l])[0].sum()) for l in range(4)])
