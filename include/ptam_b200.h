@@ -309,6 +309,16 @@ int ptam_bundle_compute(ptam_bundle* b, const volatile unsigned char* abort_flag
 int ptam_bundle_begin(ptam_bundle* b);
 int ptam_bundle_lm_step(ptam_bundle* b, const volatile unsigned char* abort_flag);
 
+/* Persistent graph.  The reference rebuilds a Bundle from the map for every
+ * MapMaker::BundleAdjust call (MapMaker.cc:852-882), although consecutive calls on the same keyframe set
+ * (BundleAdjustAll until converged, MapMaker.cc:67-77) feed back exactly what the previous Compute left
+ * behind: adjusted poses and points, measurement list minus the erased outliers.  That state stays on the
+ * device: ptam_bundle_recompute runs Bundle::Compute again on it (LM control reset as in Bundle.cc:121-126,
+ * outlier list restarted) without the host-side graph rebuild and upload; same return value as compute.
+ * ptam_bundle_update_camera / _point overwrite one pose / position of the resident graph in between. */
+int ptam_bundle_recompute(ptam_bundle* b, const volatile unsigned char* abort_flag);
+int ptam_bundle_update_camera(ptam_bundle* b, int n, const double se3_cam_from_world[12]);
+int ptam_bundle_update_point(ptam_bundle* b, int n, const double xyz[3]);
 int ptam_bundle_converged(const ptam_bundle* b);
 int ptam_bundle_get_point(ptam_bundle* b, int n, double xyz[3]);
 int ptam_bundle_get_camera(ptam_bundle* b, int n, double se3[12]);

@@ -378,6 +378,25 @@ int orc_bundle_begin(void* b) {
   ((Bundle*)b)->begin(); return 0;
 }
 int orc_bundle_lm_step(void* b, const volatile unsigned char* abort_flag) { return ((Bundle*)b)->lm_step(abort_flag) ? 0 : -1; }
+// persistent graph: Compute again on the state the previous Compute left (erased measurements stay erased)
+int orc_bundle_recompute(void* bp, const volatile unsigned char* abort_flag) {
+  Bundle* b = (Bundle*)bp;
+  if (b->meas.empty()) { b->err = "no measurements"; return PTAM_ERR_INVALID; }
+  b->outliers.clear();
+  return b->compute(abort_flag);
+}
+int orc_bundle_update_camera(void* bp, int n, const double* se3) {
+  Bundle* b = (Bundle*)bp;
+  if (n < 0 || n >= (int)b->cams.size()) return PTAM_ERR_INVALID;
+  b->cams[n].cfw = orc::SE3::from12(se3); return 0;
+}
+int orc_bundle_update_point(void* bp, int n, const double* xyz) {
+  Bundle* b = (Bundle*)bp;
+  if (n < 0 || n >= (int)b->pts.size()) return PTAM_ERR_INVALID;
+  double v[3] = {xyz[0], xyz[1], xyz[2]};
+  if (std::isnan(v[0] * v[0] + v[1] * v[1] + v[2] * v[2])) v[0] = v[1] = v[2] = 0;
+  std::memcpy(b->pts[n].pos, v, sizeof v); return 0;
+}
 int orc_bundle_converged(const void* b) { return ((const Bundle*)b)->converged; }
 int orc_bundle_get_point(void* bp, int n, double* xyz) {
   Bundle* b = (Bundle*)bp;

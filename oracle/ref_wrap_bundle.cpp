@@ -24,6 +24,7 @@ struct RefBundle : public Bundle {
 struct Handle {
   RefBundle* b = nullptr;
   int n_computes = 0;
+  size_t outlier_base = 0;  // mvOutlierMeasurementIdx is never cleared: outliers of earlier Compute calls
   std::string err;
   ~Handle() { delete b; }
 };
@@ -95,6 +96,23 @@ int ref_bundle_compute(void* h, const volatile unsigned char* abort_flag) {
   return hd->b->Compute(abort_flag ? (bool*)const_cast<unsigned char*>(abort_flag) : &never);
 }
 // Do_LM_Step is a protected template defined in Bundle.cc: the reference cannot be stepped from outside
+// the reference object can simply be computed again: Compute resets the LM control (Bundle.cc:121-126) and
+// the erased measurements are gone from mMeasList
+int ref_bundle_recompute(void* h, const volatile unsigned char* abort_flag) {
+  Handle* hd = (Handle*)h;
+  hd->outlier_base = hd->b->GetOutlierMeasurements().size();
+  return ref_bundle_compute(h, abort_flag);
+}
+int ref_bundle_update_camera(void* h, int n, const double* se3) {
+  Handle* hd = (Handle*)h;
+  if (n < 0 || n >= (int)hd->b->mvCameras.size()) return PTAM_ERR_INVALID;
+  hd->b->mvCameras[n].se3CfW = se3_from12(se3); return 0;
+}
+int ref_bundle_update_point(void* h, int n, const double* xyz) {
+  Handle* hd = (Handle*)h;
+  if (n < 0 || n >= (int)hd->b->mvPoints.size()) return PTAM_ERR_INVALID;
+  hd->b->mvPoints[n].v3Pos = TooN::makeVector(xyz[0], xyz[1], xyz[2]); return 0;
+}
 int ref_bundle_begin(void* h) { ((Handle*)h)->err = "the reference has no step-wise interface"; return PTAM_ERR_INVALID; }
 int ref_bundle_lm_step(void* h, const volatile unsigned char*) { ((Handle*)h)->err = "the reference has no step-wise interface"; return PTAM_ERR_INVALID; }
 int ref_bundle_converged(const void* h) { return ((const Handle*)h)->b->Converged(); }
@@ -125,15 +143,16 @@ int ref_bundle_get_cameras(void* h, double* se3) {
 }
 int ref_bundle_get_outliers(void* h, int32_t* pairs, int cap) {
   const std::vector<std::pair<int, int>> o = ((Handle*)h)->b->GetOutlierMeasurements();
-  for (size_t i = 0; i < o.size() && (int)i < cap; i++) { pairs[2 * i] = o[i].first; pairs[2 * i + 1] = o[i].second; }
-  return (int)o.size();
+  const size_t base = ((Handle*)h)->outlier_base;
+  for (size_t i = base; i < o.size() && (int)(i - base) < cap; i++) { pairs[2 * (i - base)] = o[i].first; pairs[2 * (i - base) + 1] = o[i].second; }
+  return (int)(o.size() - base);
 }
 int ref_bundle_get_stats(void* h, ptam_bundle_stats* s) {
   Handle* hd = (Handle*)h;
   std::memset(s, 0, sizeof *s);
   s->accepted = hd->b->mnAccepted; s->lambda_trials = hd->b->mnCounter; s->lm_steps = -1;  // not observable
   s->converged = hd->b->Converged(); s->hit_max_iterations = hd->b->mbHitMaxIterations;
-  s->n_outliers = (int)hd->b->GetOutlierMeasurements().size();
+  s->n_outliers = (int)(hd->b->GetOutlierMeasurements().size() - hd->outlier_base);
   s->sigma_squared = hd->b->mdSigmaSquared; s->lambda = hd->b->mdLambda;
   return 0;
 }

@@ -82,6 +82,7 @@ BUNDLE_SYMBOLS = [
     "bundle_begin", "bundle_lm_step", "bundle_converged", "bundle_get_point", "bundle_get_camera",
     "bundle_get_points", "bundle_get_cameras", "bundle_get_outliers", "bundle_get_stats",
     "bundle_get_reduced_system", "bundle_synchronize",
+    "bundle_recompute", "bundle_update_camera", "bundle_update_point",
 ]
 # exported by the product only (CUDA plumbing)
 PRODUCT_ONLY_SYMBOLS = [
@@ -186,6 +187,9 @@ class Lib:
             "bundle_shard_plan": (i, [i, i, P(C.c_int32), i, P(C.c_int32)]),
             "bundle_compute": (i, [vp, P(C.c_ubyte)]),
             "bundle_begin": (i, [vp]),
+            "bundle_recompute": (i, [vp, P(C.c_ubyte)]),
+            "bundle_update_camera": (i, [vp, i, P(d)]),
+            "bundle_update_point": (i, [vp, i, P(d)]),
             "bundle_lm_step": (i, [vp, P(C.c_ubyte)]),
             "bundle_converged": (i, [vp]),
             "bundle_get_point": (i, [vp, i, P(d)]),
@@ -535,6 +539,16 @@ class Bundle:
 
     def Compute(self, abort=None):
         return self._chk(self.lib.fn("bundle_compute")(self.h, abort))
+
+    def Recompute(self, abort=None):
+        """Bundle::Compute again on the resident graph (adjusted state, outliers erased): SURVEY 8f rank 4."""
+        return self._chk(self.lib.fn("bundle_recompute")(self.h, abort))
+
+    def update_camera(self, n, se3):
+        self._chk(self.lib.fn("bundle_update_camera")(self.h, int(n), _dp(_f64(se3).reshape(12))))
+
+    def update_point(self, n, xyz):
+        self._chk(self.lib.fn("bundle_update_point")(self.h, int(n), _dp(_f64(xyz).reshape(3))))
 
     def begin(self):
         self._chk(self.lib.fn("bundle_begin")(self.h))

@@ -618,6 +618,54 @@ int ptam_bundle_compute(ptam_bundle* b, const volatile unsigned char* abort_flag
   return b->accepted;
 }
 
+// Persistent graph.  MapMaker::BundleAdjust rebuilds a Bundle from the map for every call
+// (MapMaker.cc:852-882) although consecutive calls on the same keyframe set (BundleAdjustAll until
+// converged, MapMaker.cc:67-77) feed back exactly what the previous Compute left: the adjusted poses and
+// points and the measurement list without the erased outliers.  That state is resident on the device:
+// recompute restarts the LM control (Bundle.cc:121-126) on it without the host rebuild and upload.
+int ptam_bundle_recompute(ptam_bundle* b, const volatile unsigned char* abort_flag) {
+  cudaSetDevice(b->device);
+  if (!b->begun) { b->set_error("ptam_bundle_recompute needs a graph that has been computed (or begun) before"); return PTAM_ERR_INVALID; }
+  int rc = b->sync_shards();
+  if (rc) return rc;
+  b->lambda = 0.0001; b->lambda_factor = 2.0;
+  b->converged = false; b->hit_max = false; b->abort_seen = false;
+  b->counter = 0; b->accepted = 0; b->lm_steps = 0; b->n_outliers = 0;
+  b->h_outliers.clear();
+  PTAM_CUDA_TRY(b, cudaMemsetAsync(b->counters.p, 0, sizeof(int) * 4, b->stream));
+  if (b->d.n_meas > 0) PTAM_CUDA_TRY(b, cudaMemsetAsync(b->m_erase_step.p, 0, sizeof(int) * (size_t)b->d.n_meas, b->stream));
+  while (!b->converged && !b->hit_max && !(b->world > 1 ? b->abort_seen : (abort_flag && *abort_flag))) {
+    rc = b->lm_step(abort_flag);
+    if (rc) return rc;
+  }
+  rc = b->sync_shards();
+  if (rc) return rc;
+  return b->accepted;
+}
+// Overwrite one camera pose / point of the resident graph (e.g. the tracker's latest estimate) without a rebuild.
+int ptam_bundle_update_camera(ptam_bundle* b, int n, const double* se3) {
+  cudaSetDevice(b->device);
+  if (n < 0 || n >= b->n_cams()) { b->set_error("bad camera index"); return PTAM_ERR_INVALID; }
+  std::memcpy(&b->h_cam_se3[12 * (size_t)n], se3, sizeof(double) * 12);
+  if (b->begun) {
+    PTAM_CUDA_TRY(b, cudaMemcpyAsync(b->cam_se3.p + 12 * (size_t)n, &b->h_cam_se3[12 * (size_t)n], sizeof(double) * 12, cudaMemcpyHostToDevice, b->stream));
+    PTAM_CUDA_TRY(b, cudaStreamSynchronize(b->stream));
+  }
+  return PTAM_OK;
+}
+int ptam_bundle_update_point(ptam_bundle* b, int n, const double* xyz) {
+  cudaSetDevice(b->device);
+  if (n < 0 || n >= b->n_pts()) { b->set_error("bad point index"); return PTAM_ERR_INVALID; }
+  double v[3] = {xyz[0], xyz[1], xyz[2]};
+  if (std::isnan(v[0] * v[0] + v[1] * v[1] + v[2] * v[2])) v[0] = v[1] = v[2] = 0;
+  std::memcpy(&b->h_pts[3 * (size_t)n], v, sizeof v);
+  if (b->begun) {
+    PTAM_CUDA_TRY(b, cudaMemcpyAsync(b->pt_pos.p + 3 * (size_t)n, &b->h_pts[3 * (size_t)n], sizeof v, cudaMemcpyHostToDevice, b->stream));
+    PTAM_CUDA_TRY(b, cudaStreamSynchronize(b->stream));
+  }
+  return PTAM_OK;
+}
+
 int ptam_bundle_converged(const ptam_bundle* b) { return b->converged ? 1 : 0; }
 
 int ptam_bundle_get_points(ptam_bundle* b, double* xyz) {

@@ -46,6 +46,13 @@ class Bundle {
     static_assert(sizeof(bool) == 1, "abort flag is polled as one byte");
     return ptam_bundle_compute(h, reinterpret_cast<const volatile unsigned char*>(pbAbortSignal));
   }
+  // Not in the reference: Compute again on the device-resident graph — what
+  // MapMaker::BundleAdjustAll does by rebuilding an identical Bundle until it converges (MapMaker.cc:67-77).
+  int Recompute(bool* pbAbortSignal) {
+    return ptam_bundle_recompute(h, reinterpret_cast<const volatile unsigned char*>(pbAbortSignal));
+  }
+  void UpdateCamera(int n, TooN::SE3<> se3CamFromWorld) { double a[12]; se3_to_array(se3CamFromWorld, a); ptam_bundle_update_camera(h, n, a); }
+  void UpdatePoint(int n, TooN::Vector<3> v3Pos) { const double a[3] = {v3Pos[0], v3Pos[1], v3Pos[2]}; ptam_bundle_update_point(h, n, a); }
   bool Converged() { return ptam_bundle_converged(h) != 0; }
   TooN::Vector<3> GetPoint(int n) {
     double a[3] = {0, 0, 0};

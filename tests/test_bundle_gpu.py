@@ -182,3 +182,46 @@ def test_edge_graphs(oracle, product):
         b.AddPoint([0, 0, 1])
         with pytest.raises(Exception):   # the reference asserts (Tools.h:155); here it is an error code
             b.Compute()
+
+
+def test_persistent_graph_recompute(oracle, product):
+    """Compute again on the device-resident graph (ptam_bundle_recompute) = the oracle's
+    second Compute on the same object = a fresh handle built from the first run's outputs."""
+    prod, orc = product, oracle
+    g = synth.make_ba_graph(12, 500, 2500, seed=6)
+    res = []
+    for lib in (prod, orc):
+        b = Bundle(lib, g["width"], g["height"], max_iterations=4)
+        b.add_graph(g)
+        a1 = b.Compute()
+        o1 = b.GetOutlierMeasurements()
+        p1, c1 = b.get_points(), b.get_cameras()
+        b.update_point(7, p1[7] + 1e-3)
+        a2 = b.Recompute()
+        s = b.stats()
+        res.append((a1, o1, p1, c1, a2, s.lambda_trials, b.GetOutlierMeasurements(), b.get_points(), b.get_cameras()))
+        b.close()
+    p, o = res
+    assert p[0] == o[0] and np.array_equal(p[1], o[1])
+    assert (p[4], p[5]) == (o[4], o[5]) and np.array_equal(p[6], o[6])
+    np.testing.assert_allclose(p[7], o[7], rtol=0, atol=1e-7)
+    np.testing.assert_allclose(p[8], o[8], rtol=0, atol=1e-7)
+    # the same second run from a handle rebuilt on the host, as the reference's MapMaker does
+    keep = np.ones(len(g["meas_cam"]), bool)
+    gone = {(int(a), int(b_)) for a, b_ in p[1]}
+    for i, (c, pt) in enumerate(zip(g["meas_cam"], g["meas_point"])):
+        if (int(pt), int(c)) in gone:
+            keep[i] = False
+    g2 = dict(g)
+    g2["points"] = p[2].copy(); g2["points"][7] += 1e-3
+    g2["cam_se3"] = p[3]
+    for k in ("meas_cam", "meas_point", "meas_uv", "meas_sigma_sq"):
+        g2[k] = np.asarray(g[k])[keep]
+    b = Bundle(prod, g["width"], g["height"], max_iterations=4)
+    b.add_graph(g2)
+    a = b.Compute()
+    assert a == p[4] and b.stats().lambda_trials == p[5]
+    assert np.array_equal(b.GetOutlierMeasurements(), p[6])
+    np.testing.assert_allclose(b.get_points(), p[7], rtol=0, atol=1e-7)
+    np.testing.assert_allclose(b.get_cameras(), p[8], rtol=0, atol=1e-7)
+    b.close()

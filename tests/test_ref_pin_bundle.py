@@ -81,3 +81,27 @@ def test_edge_cases_match_reference():
     assert (o["acc"], o["trials"]) == (r["acc"], r["trials"])
     assert np.array_equal(o["outliers"], r["outliers"])
     assert np.array_equal(o["points"], r["points"], equal_nan=True) and np.array_equal(o["cams"], r["cams"], equal_nan=True)
+
+
+def test_recompute_on_the_same_object_matches_reference():
+    """Persistent graph: Compute, then Compute again on the state it left (adjusted
+    poses / points, outliers erased) — the reference object itself can be computed twice (built with
+    NDEBUG like a release build: GenerateOffDiagScripts asserts on the erased measurements otherwise)."""
+    g = synth.make_ba_graph(12, 500, 2500, seed=6)
+    out = []
+    for lib in (oracle_lib(libm_atan=True), REF):
+        b = Bundle(lib, g["width"], g["height"], max_iterations=4)
+        b.add_graph(g)
+        a1 = b.Compute()
+        o1 = b.GetOutlierMeasurements()
+        b.update_camera(3, b.GetCamera(3))            # a no-op update through the new entry points
+        p7 = b.GetPoint(7) + 1e-3
+        b.update_point(7, p7)
+        a2 = b.Recompute()
+        s = b.stats()
+        out.append((a1, o1, a2, s.lambda_trials, b.GetOutlierMeasurements(), b.get_points(), b.get_cameras()))
+        b.close()
+    o, r = out
+    assert o[0] == r[0] and np.array_equal(o[1], r[1]) and len(o[1]) > 0
+    assert (o[2], o[3]) == (r[2], r[3]) and np.array_equal(o[4], r[4])
+    assert np.array_equal(o[5], r[5]) and np.array_equal(o[6], r[6])
