@@ -105,6 +105,12 @@ typedef struct ptam_track_result {
                                           (Tracker.cc:1095-1099); left to the caller */
   int32_t n_pvs[PTAM_LEVELS];          /* PVS size per level before selection */
   int32_t n_candidates;                /* ZMSSD windows evaluated (FindPatchCoarse candidates, PatchFinder.cc:193-200) */
+  int32_t recovery;                    /* 0: tracked normally; 1: the frame arrived with mnLostFrames >= 3, the relocaliser
+                                          succeeded and TrackMap + AssessTrackingQuality ran from its pose (Tracker.cc:170-178);
+                                          2: the relocaliser's score was too high, nothing else was done this frame */
+  int32_t reloc_keyframe;              /* Relocaliser::mnBest (-1 when recovery == 0) */
+  int32_t reserved1;
+  double reloc_score;                  /* final ESM score of CalcSBIRotation against that keyframe (Relocaliser.cc:34-37) */
 } ptam_track_result;
 
 typedef struct ptam_tracker ptam_tracker;
@@ -132,6 +138,14 @@ int ptam_tracker_set_map(ptam_tracker* t, int stream, int n_points, const double
                          const double* pixel_right_w, const double* pixel_down_w,
                          const int32_t* src_kf, const int32_t* src_level, const int32_t* ir_center);
 
+/* Relocaliser (Relocaliser.cc:12-38, Tracker.cc:170-178,196-207).  Giving every stored
+ * keyframe its pose (KeyFrame::se3CfromW) switches the recovery branch of Tracker::TrackFrame on: a frame that
+ * arrives with mnLostFrames >= 3 is not tracked from the motion model; instead the SmallBlurryImage (blur 2.5)
+ * of the frame is compared (SSD) with that of every stored keyframe, the ESM rotation against the best one
+ * gives pose = rotation * keyframe pose, and if the final ESM score is below Reloc2.MaxScore (9e6) the pose,
+ * a zero velocity and mbJustRecoveredSoUseCoarse are installed and TrackMap + AssessTrackingQuality run.
+ * Without keyframe poses a lost stream keeps tracking from its motion model (the recovery branch is off). */
+int ptam_tracker_set_keyframe_pose(ptam_tracker* t, int keyframe, const double se3_cam_from_world[12]);
 int ptam_tracker_set_state(ptam_tracker* t, int stream, const ptam_tracker_state* s);
 int ptam_tracker_get_state(ptam_tracker* t, int stream, ptam_tracker_state* s);
 

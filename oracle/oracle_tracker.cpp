@@ -431,6 +431,15 @@ struct Tracker {
   int W, H, S;
   ptam_tracker_params prm;
   std::vector<KeyFrame> store;
+  // relocaliser (Relocaliser.cc): pose and SmallBlurryImage (blur 2.5, KeyFrame.cc:80-81) of every stored keyframe
+  std::vector<SE3> kf_pose;
+  std::vector<char> kf_has_pose;
+  std::vector<SBI> kf_sbi;
+  bool relocaliser_on() const {
+    if (store.empty()) return false;
+    for (char c : kf_has_pose) if (!c) return false;
+    return true;
+  }
   struct Stream {
     std::vector<MapPoint> pts;
     std::vector<TData> td;
@@ -954,6 +963,43 @@ struct Tracker {
     else { s.sbi_last = s.sbi_this; sbi_make(s.cur, prm.rotation_estimator_blur, s.sbi_this); }
     s.st.frame++;
     s.pose = SE3::from12(s.st.se3_cam_from_world);
+    s.res.recovery = 0; s.res.reloc_keyframe = -1; s.res.reloc_score = 0.0;
+    if (relocaliser_on() && s.st.lost_frames >= 3) {
+      // Tracker.cc:170-178: AttemptRecovery (Tracker.cc:196-207, Relocaliser.cc:12-38), then TrackMap and
+      // AssessTrackingQuality only — no motion model on this frame
+      SBI cur;
+      sbi_make(s.cur, 2.5, cur);  // kCurrent.pSBI = new SmallBlurryImage(kCurrent): default blur
+      double best_score = 99999999999999.9;
+      int best = -1;
+      for (size_t i = 0; i < store.size(); i++) {
+        double ssd = 0.0;  // SSDofImgs (ImageProcess.cc:88-105)
+        for (int k = 0; k < cur.w * cur.h; k++) { const double dd = cur.tmpl[k] - kf_sbi[i].tmpl[k]; ssd += dd * dd; }
+        if (ssd < best_score) { best_score = ssd; best = (int)i; }
+      }
+      double score = 0.0;
+      const SE2 se2 = sbi_iterate(cur, kf_sbi[best], 6, score);
+      SE3 rot;
+      sbi_so3_from_se2(se2, cam_small, cur.w, cur.h, rot.R);
+      const SE3 best_pose = se3_mul(rot, kf_pose[best]);
+      s.res.reloc_keyframe = best; s.res.reloc_score = score;
+      ptam_track_result& r = s.res;
+      if (!(score < 9e6)) {  // Reloc2.MaxScore
+        s.res.recovery = 2;
+        s.pose.to12(r.se3_cam_from_world);
+        r.scene_depth_mean = s.st.scene_depth_mean; r.scene_depth_sigma = s.st.scene_depth_sigma;
+        for (int i = 0; i < 4; i++) { r.meas_attempted[i] = r.meas_found[i] = 0; r.n_pvs[i] = 0; r.n_corners[i] = (int)s.cur.lev[i].corners.size(); }
+        r.did_coarse = 0; r.n_coarse = r.n_level3 = r.n_fine = 0; r.quality_needs_kf_distance = 0;
+        r.tracking_quality = s.st.tracking_quality; r.n_candidates = 0;
+        return;
+      }
+      s.res.recovery = 1;
+      s.pose = s.start = best_pose;
+      for (int k = 0; k < 6; k++) s.st.velocity[k] = 0.0;
+      s.st.just_recovered_so_use_coarse = 1;
+      track_map(s);
+      assess_and_report(s);
+      return;
+    }
     // PredictPoseWithMotionModel (Tracker.cc:1012-1029)
     s.start = s.pose;
     double vpred[6];
@@ -984,6 +1030,9 @@ struct Tracker {
     double m = 0;
     for (int k = 0; k < 6; k++) m += v6[k] * v6[k];
     s.st.msd_scaled_velocity_magnitude = std::sqrt(m);
+    assess_and_report(s);
+  }
+  void assess_and_report(Stream& s) {
     // AssessTrackingQuality (Tracker.cc:1062-1107)
     int ta = 0, tf = 0, la = 0, lf = 0;
     for (int i = 0; i < 4; i++) {
@@ -1051,7 +1100,17 @@ int orc_tracker_add_keyframe(void* tp, const uint8_t* image, int stride) {
   Tracker* t = (Tracker*)tp;
   t->store.emplace_back();
   orc::make_keyframe_lite(t->store.back(), image, t->W, t->H, stride, false);
+  t->kf_pose.emplace_back(); t->kf_has_pose.push_back(0);
+  t->kf_sbi.emplace_back();
+  orc::sbi_make(t->store.back(), 2.5, t->kf_sbi.back());   // MakeKeyFrame_Rest: pSBI = new SmallBlurryImage(*this); MakeJacs
+  orc::sbi_make_jacs(t->kf_sbi.back());
   return (int)t->store.size() - 1;
+}
+int orc_tracker_set_keyframe_pose(void* tp, int kf, const double* se3) {
+  Tracker* t = (Tracker*)tp;
+  if (kf < 0 || kf >= (int)t->store.size()) return PTAM_ERR_INVALID;
+  t->kf_pose[kf] = orc::SE3::from12(se3); t->kf_has_pose[kf] = 1;
+  return PTAM_OK;
 }
 
 int orc_tracker_set_map(void* tp, int stream, int n, const double* world, const double* right, const double* down,

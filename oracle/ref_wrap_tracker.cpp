@@ -38,6 +38,8 @@ struct RefTracker : public Tracker {
   using Tracker::mpSBIThisFrame;
   using Tracker::mse3CamFromWorld;
   using Tracker::mv6CameraVelocity;
+  struct RelocPeek : public Relocaliser { using Relocaliser::mnBest; };
+  int reloc_best() { return static_cast<RelocPeek&>(mRelocaliser).mnBest; }
   void set_quality(int q) { mTrackingQuality = q == 0 ? BAD : GOOD; }
   int get_quality() const { return mTrackingQuality == BAD ? 0 : 2; }
 };
@@ -147,6 +149,7 @@ int ref_tracker_add_keyframe(void* hp, const uint8_t* image, int stride) {
   k->bFixed = false;
   k->dSceneDepthMean = 1.0; k->dSceneDepthSigma = 1.0;
   k->MakeKeyFrame_Lite(im);
+  k->MakeKeyFrame_Rest();  // the relocaliser compares against KeyFrame::pSBI (KeyFrame.cc:80-81)
   h->store.push_back(k);
   for (auto& s : h->streams) s->map.vpKeyFrames = h->store;
   return (int)h->store.size() - 1;
@@ -182,6 +185,12 @@ int ref_tracker_set_map(void* hp, int stream, int n, const double* world, const 
   return 0;
 }
 
+int ref_tracker_set_keyframe_pose(void* hp, int kf, const double* se3) {
+  Handle* h = (Handle*)hp;
+  if (kf < 0 || kf >= (int)h->store.size()) return PTAM_ERR_INVALID;
+  h->store[kf]->se3CfromW = se3_from12(se3);
+  return PTAM_OK;
+}
 int ref_tracker_set_state(void* hp, int stream, const ptam_tracker_state* st) {
   Handle* h = (Handle*)hp;
   if (stream < 0 || stream >= h->S) return PTAM_ERR_INVALID;
@@ -230,9 +239,15 @@ int ref_tracker_track_frames(void* hp, const uint8_t* const* images, int stride,
     st.refind_mode = false;
     st.mm->mvpKeyFrameQueue.clear();  // keyframes the tracker hands to the (absent) map-maker thread are dropped
     CVD::Image<CVD::byte> im = wrap_image(images[s], h->W, h->H, stride);
+    const int lost_before = t.mnLostFrames;
     t.TrackFrame(im, false);
     ptam_track_result& r = st.res;
     std::memset(&r, 0, sizeof r);
+    r.reloc_keyframe = -1;
+    if (lost_before >= 3) {  // the recovery branch ran (Tracker.cc:170-178); AssessTrackingQuality moves mnLostFrames only on success
+      r.recovery = t.mnLostFrames != lost_before ? 1 : 2;
+      r.reloc_keyframe = t.reloc_best();
+    }
     se3_to12(t.mse3CamFromWorld, r.se3_cam_from_world);
     r.scene_depth_mean = t.mCurrentKF.dSceneDepthMean; r.scene_depth_sigma = t.mCurrentKF.dSceneDepthSigma;
     for (int l = 0; l < LEVELS; l++) {

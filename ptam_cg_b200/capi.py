@@ -48,6 +48,7 @@ class TrackResult(C.Structure):
         ("n_coarse", C.c_int32), ("n_level3", C.c_int32), ("n_fine", C.c_int32),
         ("tracking_quality", C.c_int32), ("quality_needs_kf_distance", C.c_int32),
         ("n_pvs", C.c_int32 * 4), ("n_candidates", C.c_int32),
+        ("recovery", C.c_int32), ("reloc_keyframe", C.c_int32), ("reserved1", C.c_int32), ("reloc_score", C.c_double),
     ]
 
 
@@ -73,7 +74,7 @@ TRACKER_SYMBOLS = [
     "tracker_make_keyframes", "tracker_track_frames", "tracker_synchronize", "tracker_get_level",
     "tracker_level_size", "tracker_get_points", "tracker_get_templates", "tracker_get_sbi",
     "tracker_keyframe_rest", "tracker_get_level_rest", "tracker_refind_in_keyframes",
-    "tracker_get_iteration_set", "tracker_epipolar_search",
+    "tracker_get_iteration_set", "tracker_epipolar_search", "tracker_set_keyframe_pose",
 ]
 BUNDLE_SYMBOLS = [
     "bundle_default_params", "bundle_create", "bundle_destroy", "bundle_last_error",
@@ -147,6 +148,7 @@ class Lib:
             "tracker_add_keyframe": (i, [vp, P(C.c_uint8), i]),
             "tracker_set_map": (i, [vp, i, i, P(d), P(d), P(d), P(C.c_int32), P(C.c_int32), P(C.c_int32)]),
             "tracker_set_state": (i, [vp, i, P(TrackerState)]),
+            "tracker_set_keyframe_pose": (i, [vp, i, P(d)]),
             "tracker_get_state": (i, [vp, i, P(TrackerState)]),
             "tracker_make_keyframes": (i, [vp, P(vp), i]),
             "tracker_track_frames": (i, [vp, P(vp), i, P(TrackResult)]),
@@ -297,6 +299,10 @@ class Tracker:
         image = np.ascontiguousarray(image, dtype=np.uint8)
         assert image.shape == (self.H, self.W)
         return self._chk(self.lib.fn("tracker_add_keyframe")(self.h, _bp(image), self.W))
+
+    def set_keyframe_pose(self, kf, pose12):
+        """KeyFrame::se3CfromW of a stored keyframe; once every keyframe has one the relocaliser branch is on."""
+        self._chk(self.lib.fn("tracker_set_keyframe_pose")(self.h, int(kf), _dp(_f64(pose12).reshape(12))))
 
     def set_map(self, stream, m):
         w, r, dn = _f64(m["world_pos"]), _f64(m["pixel_right_w"]), _f64(m["pixel_down_w"])

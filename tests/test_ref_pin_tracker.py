@@ -206,3 +206,52 @@ def test_epipolar_search_degenerate_geometry_matches_reference():
         r = _epipolar_case(REF, W, H, frames, poses, **args)
         for (co, fo, bo, so), (cr, fr, br, sr) in zip(o, r):
             assert np.array_equal(fo, fr) and np.array_equal(so, sr)
+
+
+def test_relocaliser_recovery_matches_reference():
+    """Tracker::TrackFrame's recovery branch (Tracker.cc:170-178,196-207; Relocaliser.cc:12-38; SURVEY 8f rank
+    4): three noise frames lose tracking, the next real frame is relocalised against the stored keyframes'
+    small blurry images and tracked from the recovered pose; then tracking continues normally."""
+    W, H = 320, 240
+    frames, poses, kfs, m = _scene(W, H, 14, (0, 6), (150, 80, 40, 20))
+    to, tr = (_tracker(lib, W, H, kfs, m) for lib in (oracle_lib(libm_atan=True), REF))
+    for t in (to, tr):
+        for i, k in enumerate((0, 6)):
+            t.set_keyframe_pose(i, poses[k])
+        t.set_state(0, pose12=poses[2], msd=0.02)
+    rng = np.random.default_rng(5)
+    noise = [rng.integers(0, 256, (H, W), dtype=np.uint8) for _ in range(3)]
+    seq = [frames[2], frames[3]] + noise + [frames[7], frames[8], frames[9]]
+    modes = []
+    for im in seq:
+        ro, rr = to.track_frames([im])[0], tr.track_frames([im])[0]
+        assert ro.recovery == rr.recovery
+        if ro.recovery:
+            assert ro.reloc_keyframe == rr.reloc_keyframe
+        _compare_frame(to, tr, ro, rr)
+        modes.append(ro.recovery)
+    assert modes == [0, 0, 0, 0, 0, 1, 0, 0]
+    assert to.get_state(0).lost_frames == 0 and sum(ro.meas_found) > 100  # back on track
+
+
+def test_relocaliser_failure_leaves_the_tracker_alone():
+    """A frame nothing like any keyframe: the ESM score stays above Reloc2.MaxScore and nothing is done."""
+    W, H = 320, 240
+    frames, poses, kfs, m = _scene(W, H, 8, (0, 6), (150, 80, 40, 20))
+    to, tr = (_tracker(lib, W, H, kfs, m) for lib in (oracle_lib(libm_atan=True), REF))
+    for t in (to, tr):
+        for i, k in enumerate((0, 6)):
+            t.set_keyframe_pose(i, poses[k])
+        t.set_state(0, pose12=poses[2], msd=0.02)
+    rng = np.random.default_rng(9)
+    checker = ((np.indices((H, W)).sum(0) // 8) % 2 * 255).astype(np.uint8)
+    seq = [frames[2]] + [rng.integers(0, 256, (H, W), dtype=np.uint8) for _ in range(3)] + [checker, 255 - checker]
+    modes = []
+    for im in seq:
+        ro, rr = to.track_frames([im])[0], tr.track_frames([im])[0]
+        assert ro.recovery == rr.recovery
+        so, sr = to.get_state(0), tr.get_state(0)
+        assert np.array_equal(np.array(so.se3_cam_from_world), np.array(sr.se3_cam_from_world))
+        assert (so.lost_frames, so.frame) == (sr.lost_frames, sr.frame)
+        modes.append(ro.recovery)
+    assert modes[:4] == [0, 0, 0, 0] and modes[4] in (1, 2)
