@@ -84,6 +84,11 @@ struct ptam_tracker {
   DevBuf<int4> geo;
   DevBuf<float> sbi_tmpl;
   DevBuf<double> refind_pose;
+  // relocaliser: keyframe poses (host copy + device table) and which of them have been given
+  DevBuf<double> kf_pose;
+  size_t kf_pose_cap = 0;
+  std::vector<double> h_kf_pose;
+  std::vector<char> h_kf_has_pose;
   // MakeKeyFrame_Rest scratch (one stream at a time; allocated on first use)
   DevBuf<uint8_t> rest_smap;
   DevBuf<int2> rest_max, rest_cand;
@@ -125,7 +130,7 @@ struct ptam_tracker {
     warp_inv.free(); v2found.free(); sin_.free(); J.free(); e2.free(); src_kf.free(); src_level.free();
     tsum.free(); tsumsq.free(); flags.free(); level.free(); search_level.free(); outliers.free(); inliers.free();
     pvs.free(); iter_idx.free(); center.free(); tmpl.free();
-    epi_cand.free(); epi_implane.free(); epi_found.free(); epi_best.free(); epi_sub.free();
+    epi_cand.free(); epi_implane.free(); epi_found.free(); epi_best.free(); epi_sub.free(); kf_pose.free();
     if (stage_ev) cudaEventDestroy(stage_ev);
     for (auto e : prof_ev) if (e) cudaEventDestroy(e);
     for (int k = 0; k < 2; k++) {
@@ -187,6 +192,18 @@ struct ptam_tracker {
       sb.cam_small = make_cam(cam_params, sb.w, sb.h);
       if (sb.n < 9) { set_error("image too small for the rotation estimator"); return PTAM_ERR_INVALID; }
       sbi_smem = (size_t)sb.n * (7 * sizeof(float) + 1) + 16;
+      // the relocaliser's small blurry images use SmallBlurryImage's default blur 2.5 (ImageProcess.h:54)
+      const double s25 = 2.5;
+      dev.ks25 = (int)std::ceil(3.0 * s25);
+      float k25 = 0.f;
+      for (int i = 0; i < 12; i++) dev.taps25[i] = 0.f;
+      for (int i = 1; i <= dev.ks25; i++) k25 += (dev.taps25[i] = (float)std::exp(-i * i / (2 * s25 * s25)));
+      dev.taps25[0] = 1.f;
+      k25 = k25 * 2 + dev.taps25[0];
+      const double f25 = 1.0 / k25;
+      for (int i = 0; i <= dev.ks25; i++) dev.taps25[i] = (float)(dev.taps25[i] * f25);
+      dev.kf_sbi_off = (g.pyr_bytes + 255) & ~(size_t)255;
+      dev.reloc_on = 0; dev.kf_pose = nullptr;
     }
     dev.S = S;
     PTAM_CUDA_TRY(this, pyr.alloc(g.pyr_bytes * S));
@@ -212,7 +229,11 @@ struct ptam_tracker {
     PTAM_CUDA_TRY(this, ensure_points(1024));
     PTAM_CUDA_TRY(this, sbi_tmpl.alloc((size_t)2 * S * dev.sbi.n));
     dev.sbi.tmpl = sbi_tmpl.p;
-    if (sbi_smem > 48 * 1024) PTAM_CUDA_TRY(this, cudaFuncSetAttribute(k_sbi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbi_smem));
+    if (sbi_smem > 48 * 1024) {
+      PTAM_CUDA_TRY(this, cudaFuncSetAttribute(k_sbi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbi_smem));
+      PTAM_CUDA_TRY(this, cudaFuncSetAttribute(k_kf_sbi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbi_smem));
+      PTAM_CUDA_TRY(this, cudaFuncSetAttribute(k_reloc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbi_smem));
+    }
     PTAM_CUDA_TRY(this, cudaFuncSetAttribute(k_pose, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoseSmemBytes));
     if ((size_t)(max_h + 1) * sizeof(int) > 48 * 1024)
       PTAM_CUDA_TRY(this, cudaFuncSetAttribute(k_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (max_h + 1) * (int)sizeof(int)));
@@ -344,6 +365,7 @@ struct ptam_tracker {
     unsigned used = 7u | 8u | 32u | 128u;
     pbegin(3);
     k_sbi<<<S, 256, sbi_smem, stream>>>(d);
+    if (d.reloc_on) { k_reloc<<<S, 256, sbi_smem, stream>>>(d); launches++; }
     k_pvs_select<<<S, 1024, 0, stream>>>(d);
     pend(3); launches++;
     const int coarse_items = std::min(maxn, 2 * std::max(0, d.prm.coarse_max));
@@ -397,6 +419,9 @@ struct ptam_tracker {
       r.did_coarse = c.did_coarse; r.n_coarse = c.n_coarse; r.n_level3 = c.n_l3; r.n_fine = c.n_fine;
       r.tracking_quality = c.st.tracking_quality; r.quality_needs_kf_distance = c.needs_kf_distance;
       r.n_candidates = c.n_cand;
+      const int fm = dev.reloc_on ? c.frame_mode : 0;
+      r.recovery = fm; r.reloc_keyframe = fm ? c.reloc_kf : -1; r.reserved1 = 0;
+      r.reloc_score = fm ? c.reloc_score : 0.0;
     }
   }
 };
@@ -428,8 +453,11 @@ const char* ptam_tracker_last_error(const ptam_tracker* t) { return t->err.c_str
 int ptam_tracker_add_keyframe(ptam_tracker* t, const uint8_t* image, int stride) {
   cudaSetDevice(t->device);
   uint8_t* buf = nullptr;
-  PTAM_CUDA_TRY(t, cudaMalloc(&buf, t->dev.g.pyr_bytes));
+  PTAM_CUDA_TRY(t, cudaMalloc(&buf, t->dev.kf_sbi_off + sizeof(float) * t->dev.sbi.n));  // pyramid + small blurry image
   t->kf_bufs.push_back(buf);
+  t->h_kf_pose.resize(12 * t->kf_bufs.size(), 0.0);
+  t->h_kf_has_pose.push_back(0);
+  t->dev.reloc_on = 0;  // until the new keyframe has a pose too
   const uint8_t* imgs[1] = {image};
   int rc = t->upload_images(imgs, stride, buf, t->dev.g.pyr_bytes, 1);
   if (rc) return rc;
@@ -448,7 +476,31 @@ int ptam_tracker_add_keyframe(ptam_tracker* t, const uint8_t* image, int stride)
   PTAM_CUDA_TRY(t, cudaMemcpy(t->kf_ptrs.p, t->kf_bufs.data(), sizeof(uint8_t*) * t->kf_bufs.size(), cudaMemcpyHostToDevice));
   t->dev.kf_ptrs = t->kf_ptrs.p;
   t->dev.n_kf = (int)t->kf_bufs.size();
+  k_kf_sbi<<<1, 256, t->sbi_smem, t->stream>>>(t->dev, t->dev.n_kf - 1);  // KeyFrame::pSBI (KeyFrame.cc:80-81)
+  t->launches++;
+  PTAM_CUDA_TRY(t, cudaGetLastError());
+  PTAM_CUDA_TRY(t, cudaStreamSynchronize(t->stream));
   return t->dev.n_kf - 1;
+}
+
+int ptam_tracker_set_keyframe_pose(ptam_tracker* t, int kf, const double* se3) {
+  cudaSetDevice(t->device);
+  if (kf < 0 || kf >= (int)t->kf_bufs.size()) { t->set_error("unknown keyframe"); return PTAM_ERR_INVALID; }
+  std::memcpy(&t->h_kf_pose[12 * (size_t)kf], se3, sizeof(double) * 12);
+  t->h_kf_has_pose[kf] = 1;
+  if (t->kf_bufs.size() > t->kf_pose_cap) {
+    PTAM_CUDA_TRY(t, cudaStreamSynchronize(t->stream));
+    t->kf_pose.free();
+    t->kf_pose_cap = std::max<size_t>(256, 2 * t->kf_bufs.size());
+    PTAM_CUDA_TRY(t, t->kf_pose.alloc(12 * t->kf_pose_cap));
+  }
+  PTAM_CUDA_TRY(t, cudaStreamSynchronize(t->stream));
+  PTAM_CUDA_TRY(t, cudaMemcpy(t->kf_pose.p, t->h_kf_pose.data(), sizeof(double) * t->h_kf_pose.size(), cudaMemcpyHostToDevice));
+  t->dev.kf_pose = t->kf_pose.p;
+  bool all = true;
+  for (char c : t->h_kf_has_pose) all = all && c;
+  t->dev.reloc_on = all ? 1 : 0;
+  return PTAM_OK;
 }
 
 int ptam_tracker_set_map(ptam_tracker* t, int stream, int n, const double* world, const double* right, const double* down,

@@ -55,6 +55,10 @@ struct StreamCtl {
   // SmallBlurryImage rotation estimator (Tracker.cc:95-108,1012-1029)
   int sbi_valid, sbi_idx;   // a previous small image exists / which of the two buffers holds it
   double sbi_rot[3], sbi_score;
+  // relocaliser (Tracker.cc:170-178): what k_reloc decided for this frame
+  int frame_mode;           // 0 normal; 1 relocalised, TrackMap + quality from the recovered pose; 2 relocalisation failed
+  int reloc_kf;             // Relocaliser::mnBest
+  double reloc_score;       // final ESM score against that keyframe
 };
 
 // frame-scoped point flags (low byte) and persistent flags (high bits)
@@ -114,6 +118,12 @@ struct TrackerDev {
   int S;
   int mode;                    // 0: TrackFrame; 1: MapMaker::ReFindInSingleKeyFrame (MapMaker.cc:943-1040)
   const double* refind_pose;   // [S][12] keyframe poses for mode 1
+  // relocaliser (Relocaliser.cc:12-38): on once every stored keyframe has a pose
+  int reloc_on;
+  size_t kf_sbi_off;           // byte offset of the keyframe's SmallBlurryImage (blur 2.5) in its buffer
+  const double* kf_pose;       // [n_kf][12] KeyFrame::se3CfromW
+  float taps25[12];            // Gaussian taps for sigma = 2.5 (SmallBlurryImage's default blur)
+  int ks25;
 };
 
 PTAM_DEV const uint8_t* level_image(const TrackerDev& d, int s, int l, int& pitch) {
@@ -434,23 +444,32 @@ PTAM_DEV Se2 se2_mul(const Se2& a, const Se2& b) {
   return r;
 }
 
-__global__ void __launch_bounds__(256) k_sbi(TrackerDev d) {
-  extern __shared__ __align__(16) unsigned char sbi_raw[];
-  __shared__ double red[8][16];
-  __shared__ double fin[16];
-  __shared__ unsigned usum[8];
-  __shared__ Se2 c2c_s;
-  __shared__ double mean_off_s;
-  const SbiDev& sb = d.sbi;
-  const int n = sb.n, w = sb.w, h = sb.h, ks = sb.ks;
-  float* t = reinterpret_cast<float*>(sbi_raw);
-  float* hrow = t + n; float* cur = hrow + n; float* prev = cur + n;
-  float* jx = prev + n; float* jy = jx + n; float* warped = jy + n;
-  uint8_t* small = reinterpret_cast<uint8_t*>(warped + n);
-  const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  StreamCtl& ctl = d.ctl[s];
-  int pitch;
-  const uint8_t* l3 = level_image(d, s, 3, pitch);
+struct SbiScratch {
+  float *t, *hrow, *cur, *prev, *jx, *jy, *warped;
+  uint8_t* small;
+  double (*red)[16];
+  double* fin;
+  unsigned* usum;
+  Se2* c2c;
+  double* mean_off;
+};
+
+PTAM_DEV SbiScratch sbi_scratch(unsigned char* raw, int n, double (*red)[16], double* fin, unsigned* usum, Se2* c2c, double* mean_off) {
+  SbiScratch m;
+  m.t = reinterpret_cast<float*>(raw);
+  m.hrow = m.t + n; m.cur = m.hrow + n; m.prev = m.cur + n;
+  m.jx = m.prev + n; m.jy = m.jx + n; m.warped = m.jy + n;
+  m.small = reinterpret_cast<uint8_t*>(m.warped + n);
+  m.red = red; m.fin = fin; m.usum = usum; m.c2c = c2c; m.mean_off = mean_off;
+  return m;
+}
+
+// SmallBlurryImage::MakeFromKF (ImageProcess.cc:279-304): halfSample of level 3, zero mean, Gaussian blur
+// with the given taps.  Whole CTA; the result is in m.cur (synchronised).
+PTAM_DEV void sbi_make_small(const SbiDev& sb, const float* taps, int ks, const uint8_t* l3, int pitch, const SbiScratch& m) {
+  const int n = sb.n, w = sb.w, h = sb.h;
+  float* t = m.t; float* hrow = m.hrow; float* cur = m.cur; uint8_t* small = m.small; unsigned* usum = m.usum;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // ---- halfSample(level 3) and its sum
   unsigned part = 0;
   for (int i = tid; i < n; i += blockDim.x) {
@@ -472,23 +491,28 @@ __global__ void __launch_bounds__(256) k_sbi(TrackerDev d) {
   // ---- Gaussian blur: rows, then columns; replicated borders
   for (int i = tid; i < n; i += blockDim.x) {
     const int y = i / w, x = i - y * w;
-    float a = t[i] * sb.taps[0];
-    for (int k = 1; k <= ks; k++) a += (t[y * w + max(x - k, 0)] + t[y * w + min(x + k, w - 1)]) * sb.taps[k];
+    float a = t[i] * taps[0];
+    for (int k = 1; k <= ks; k++) a += (t[y * w + max(x - k, 0)] + t[y * w + min(x + k, w - 1)]) * taps[k];
     hrow[i] = a;
   }
   __syncthreads();
-  const int idx_prev = ctl.sbi_idx, has_prev = ctl.sbi_valid;
-  float* g_cur = sb.tmpl + ((size_t)(1 - idx_prev) * d.S + s) * n;
-  const float* g_prev = sb.tmpl + ((size_t)idx_prev * d.S + s) * n;
   for (int i = tid; i < n; i += blockDim.x) {
     const int y = i / w, x = i - y * w;
-    float a = hrow[i] * sb.taps[0];
-    for (int k = 1; k <= ks; k++) a += (hrow[max(y - k, 0) * w + x] + hrow[min(y + k, h - 1) * w + x]) * sb.taps[k];
+    float a = hrow[i] * taps[0];
+    for (int k = 1; k <= ks; k++) a += (hrow[max(y - k, 0) * w + x] + hrow[min(y + k, h - 1) * w + x]) * taps[k];
     cur[i] = a;
-    g_cur[i] = a;
-    prev[i] = has_prev ? g_prev[i] : a;  // first frame: both small images are made from it (Tracker.cc:99-100)
   }
   __syncthreads();
+}
+
+// MakeJacs of m.prev (ImageProcess.cc:170-191), six ESM iterations of IteratePosRelToTarget of m.cur against
+// it (:313-412) and SE3fromSE2 (:421-473).  Whole CTA; thread 0 returns the rotation matrix and the final score.
+PTAM_DEV double sbi_esm_rotation(const SbiDev& sb, const SbiScratch& m, double* R) {
+  const int n = sb.n, w = sb.w, h = sb.h;
+  float* cur = m.cur; float* prev = m.prev; float* jx = m.jx; float* jy = m.jy; float* warped = m.warped;
+  double (*red)[16] = m.red; double* fin = m.fin;
+  Se2& c2c_s = *m.c2c; double& mean_off_s = *m.mean_off;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // ---- MakeJacs of the previous small image
   for (int i = tid; i < n; i += blockDim.x) {
     const int y = i / w, x = i - y * w;
@@ -567,7 +591,7 @@ __global__ void __launch_bounds__(256) k_sbi(TrackerDev d) {
     }
     __syncthreads();
   }
-  if (tid != 0) return;
+  if (tid != 0) return 0.0;
   // ---- SE3fromSE2 (ImageProcess.cc:421-473) and its logarithm
   const Se2 se2 = c2c_s;
   const CamModel& cam = sb.cam_small;
@@ -583,7 +607,7 @@ __global__ void __launch_bounds__(256) k_sbi(TrackerDev d) {
     const double f = dr > 0.01 ? rr / dr : 1.0;
     orig[i][0] = f * d0; orig[i][1] = f * d1; orig[i][2] = 1.0;
   }
-  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
   for (int it = 0; it < 3; it++) {
     double C[9] = {10, 0, 0, 0, 10, 0, 0, 0, 10}, b[3] = {0, 0, 0};
     for (int i = 0; i < 2; i++) {
@@ -615,12 +639,129 @@ __global__ void __launch_bounds__(256) k_sbi(TrackerDev d) {
       for (int c = 0; c < 3; c++) N[3 * r + c] = E[3 * r] * R[c] + E[3 * r + 1] * R[3 + c] + E[3 * r + 2] * R[6 + c];
     for (int i = 0; i < 9; i++) R[i] = N[i];
   }
+  return final_score;
+}
+
+__global__ void __launch_bounds__(256) k_sbi(TrackerDev d) {
+  extern __shared__ __align__(16) unsigned char sbi_raw[];
+  __shared__ double red[8][16];
+  __shared__ double fin[16];
+  __shared__ unsigned usum[8];
+  __shared__ Se2 c2c_s;
+  __shared__ double mean_off_s;
+  const SbiDev& sb = d.sbi;
+  const int n = sb.n;
+  const SbiScratch m = sbi_scratch(sbi_raw, n, red, fin, usum, &c2c_s, &mean_off_s);
+  const int s = blockIdx.x, tid = threadIdx.x;
+  StreamCtl& ctl = d.ctl[s];
+  int pitch;
+  const uint8_t* l3 = level_image(d, s, 3, pitch);
+  sbi_make_small(sb, sb.taps, sb.ks, l3, pitch, m);
+  const int idx_prev = ctl.sbi_idx, has_prev = ctl.sbi_valid;
+  float* g_cur = sb.tmpl + ((size_t)(1 - idx_prev) * d.S + s) * n;
+  const float* g_prev = sb.tmpl + ((size_t)idx_prev * d.S + s) * n;
+  for (int i = tid; i < n; i += blockDim.x) {
+    const float a = m.cur[i];
+    g_cur[i] = a;
+    m.prev[i] = has_prev ? g_prev[i] : a;  // first frame: both small images are made from it (Tracker.cc:99-100)
+  }
+  __syncthreads();
+  double R[9];
+  const double final_score = sbi_esm_rotation(sb, m, R);
+  if (tid != 0) return;
   double rot[3];
   so3_ln(R, rot);
   ctl.sbi_rot[0] = rot[0]; ctl.sbi_rot[1] = rot[1]; ctl.sbi_rot[2] = rot[2];
   ctl.sbi_score = final_score;
   ctl.sbi_idx = 1 - idx_prev;
   ctl.sbi_valid = 1;
+}
+
+// =============================================================================================
+// Relocaliser.
+//   k_kf_sbi   one CTA: the SmallBlurryImage (default blur 2.5) KeyFrame::MakeKeyFrame_Rest gives a keyframe
+//              (KeyFrame.cc:80-81), stored behind the keyframe's pyramid.
+//   k_reloc    one CTA per stream, a no-op unless the stream arrives with mnLostFrames >= 3 (Tracker.cc:133):
+//              Relocaliser::AttemptRecovery (Relocaliser.cc:12-38) — small blurry image of the current frame,
+//              SSD against every stored keyframe's (block-reduced in f64), first minimum, ESM rotation
+//              against it (the same code as k_sbi), pose = rotation * keyframe pose — and
+//              Tracker::AttemptRecovery (Tracker.cc:196-207): pose, zero velocity, mbJustRecoveredSoUseCoarse.
+//              k_pvs_select / k_pose then skip the motion model (frame_mode 1) or the whole frame (2).
+// =============================================================================================
+__global__ void __launch_bounds__(256) k_kf_sbi(TrackerDev d, int kf) {
+  extern __shared__ __align__(16) unsigned char sbi_raw[];
+  __shared__ double red[8][16];
+  __shared__ double fin[16];
+  __shared__ unsigned usum[8];
+  __shared__ Se2 c2c_s;
+  __shared__ double mean_off_s;
+  const SbiDev& sb = d.sbi;
+  const SbiScratch m = sbi_scratch(sbi_raw, sb.n, red, fin, usum, &c2c_s, &mean_off_s);
+  const uint8_t* base = d.kf_ptrs[kf];
+  sbi_make_small(sb, d.taps25, d.ks25, base + d.g.lev[3].img_off, d.g.lev[3].pitch, m);
+  float* out = reinterpret_cast<float*>(const_cast<uint8_t*>(base) + d.kf_sbi_off);
+  for (int i = threadIdx.x; i < sb.n; i += blockDim.x) out[i] = m.cur[i];
+}
+
+__global__ void __launch_bounds__(256) k_reloc(TrackerDev d) {
+  extern __shared__ __align__(16) unsigned char sbi_raw[];
+  __shared__ double red[8][16];
+  __shared__ double fin[16];
+  __shared__ unsigned usum[8];
+  __shared__ Se2 c2c_s;
+  __shared__ double mean_off_s;
+  __shared__ int best_s;
+  const SbiDev& sb = d.sbi;
+  const int n = sb.n;
+  const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  StreamCtl& ctl = d.ctl[s];
+  if (ctl.st.lost_frames < 3) {  // uniform: nothing below writes lost_frames
+    if (tid == 0) { ctl.frame_mode = 0; ctl.reloc_kf = -1; ctl.reloc_score = 0.0; }
+    return;
+  }
+  const SbiScratch m = sbi_scratch(sbi_raw, n, red, fin, usum, &c2c_s, &mean_off_s);
+  int pitch;
+  const uint8_t* l3 = level_image(d, s, 3, pitch);
+  sbi_make_small(sb, d.taps25, d.ks25, l3, pitch, m);  // kCurrent.pSBI = new SmallBlurryImage(kCurrent)
+  // SSDofImgs against every keyframe (ImageProcess.cc:88-105), strict '<': the first minimum wins
+  double best_score = 99999999999999.9;
+  int best = -1;
+  for (int kf = 0; kf < d.n_kf; kf++) {
+    const float* kt = reinterpret_cast<const float*>(d.kf_ptrs[kf] + d.kf_sbi_off);
+    double part = 0.0;
+    for (int i = tid; i < n; i += blockDim.x) { const double dd = m.cur[i] - kt[i]; part += dd * dd; }
+    part = warp_sum(part);
+    if (lane == 0) red[warp][0] = part;
+    __syncthreads();
+    if (tid == 0) {
+      double ssd = 0.0;
+      for (int q = 0; q < 8; q++) ssd += red[q][0];
+      if (ssd < best_score) { best_score = ssd; best = kf; }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) best_s = best;
+  __syncthreads();
+  best = best_s;
+  {
+    const float* kt = reinterpret_cast<const float*>(d.kf_ptrs[best] + d.kf_sbi_off);
+    for (int i = tid; i < n; i += blockDim.x) m.prev[i] = kt[i];
+  }
+  __syncthreads();
+  double R[9];
+  const double score = sbi_esm_rotation(sb, m, R);  // CalcSBIRotation(best keyframe's SBI, camera), 6 iterations
+  if (tid != 0) return;
+  ctl.reloc_kf = best; ctl.reloc_score = score;
+  if (!(score < 9e6)) { ctl.frame_mode = 2; return; }  // Reloc2.MaxScore (Relocaliser.cc:37)
+  double rot[12], np[12];
+  for (int i = 0; i < 9; i++) rot[i] = R[i];
+  rot[9] = 0.0; rot[10] = 0.0; rot[11] = 0.0;
+  se3_mul(rot, d.kf_pose + 12 * best, np);  // mse3Best = rotation * keyframe pose
+  ptam_tracker_state& st = ctl.st;
+  for (int i = 0; i < 12; i++) st.se3_cam_from_world[i] = np[i];
+  for (int i = 0; i < 6; i++) st.velocity[i] = 0.0;
+  st.just_recovered_so_use_coarse = 1;
+  ctl.frame_mode = 1;
 }
 
 // =============================================================================================
@@ -765,13 +906,23 @@ __global__ void __launch_bounds__(1024) k_pvs_select(TrackerDev d) {
   __shared__ int nseg;
   const int s = blockIdx.x;
   StreamCtl& ctl = d.ctl[s];
-  const int n = d.pt_count[s];
+  // a frame whose relocalisation failed is not tracked at all (frame_mode is written by k_reloc, before this kernel)
+  const int fmode = (d.mode == 0 && d.reloc_on) ? ctl.frame_mode : 0;
+  const bool skip_frame = fmode == 2;
+  const int n = skip_frame ? 0 : d.pt_count[s];
   const int cap = d.p.cap;
   const size_t gb = (size_t)s * cap;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0 && d.mode == 1) {
     // ReFind: the pose is the keyframe's se3CfromW; no motion model, tracker state untouched
     for (int i = 0; i < 12; i++) { pose[i] = d.refind_pose[12 * s + i]; ctl.pose[i] = pose[i]; }
+    for (int l = 0; l < kLevels; l++) { running[l] = 0; ctl.attempted[l] = 0; ctl.found[l] = 0; }
+    ctl.n_cand = 0;
+  } else if (threadIdx.x == 0 && fmode != 0) {
+    // recovery frame (Tracker.cc:170-178): mnFrame++; the pose is the relocaliser's (mode 1) or stays (mode 2,
+    // nothing is tracked); no motion model
+    ctl.st.frame++;
+    for (int i = 0; i < 12; i++) { ctl.start_pose[i] = ctl.st.se3_cam_from_world[i]; pose[i] = ctl.st.se3_cam_from_world[i]; ctl.pose[i] = pose[i]; }
     for (int l = 0; l < kLevels; l++) { running[l] = 0; ctl.attempted[l] = 0; ctl.found[l] = 0; }
     ctl.n_cand = 0;
   } else if (threadIdx.x == 0) {
@@ -869,7 +1020,7 @@ __global__ void __launch_bounds__(1024) k_pvs_select(TrackerDev d) {
     unsigned coarse_max = d.prm.coarse_max, coarse_range = d.prm.coarse_range;
     bool try_coarse = true;
     if (d.prm.disable_coarse || ctl.st.msd_scaled_velocity_magnitude < d.prm.coarse_min_velocity || coarse_max == 0) try_coarse = false;
-    if (ctl.st.just_recovered_so_use_coarse) {
+    if (ctl.st.just_recovered_so_use_coarse && !skip_frame) {
       try_coarse = true; coarse_max *= 2; coarse_range *= 2; ctl.st.just_recovered_so_use_coarse = 0;
     }
     int ns = 0, dst = 0;
@@ -1511,6 +1662,8 @@ __global__ void __launch_bounds__(kPoseThreads, 2) k_pose(TrackerDev d, int stag
   int* fidx = d.p.pvs + (size_t)s * kLevels * cap;  // PVS lists are dead after selection: reuse as found-index scratch
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n_set = stage == 0 ? ctl.n_coarse : ctl.n_coarse + ctl.n_l3 + ctl.n_fine;
+  const int fmode = (d.mode == 0 && d.reloc_on) ? ctl.frame_mode : 0;
+  if (fmode == 2) return;  // relocalisation failed: the reference does nothing else this frame
 
   // compact the found entries (order preserved) once: the found set does not change during GN
   if (threadIdx.x == 0) nfound_s = 0;
@@ -1580,20 +1733,22 @@ __global__ void __launch_bounds__(kPoseThreads, 2) k_pose(TrackerDev d, int stag
       st.scene_depth_mean = sum / nf;
       st.scene_depth_sigma = sqrt((sumsq / nf) - st.scene_depth_mean * st.scene_depth_mean);
     }
-    // UpdateMotionModel (Tracker.cc:1035-1056)
-    double inv[12], rel[12], motion[6];
-    se3_inverse(ctl.start_pose, inv);
-    se3_mul(pose, inv, rel);
-    se3_ln(rel, motion);
-    if (d.prm.use_constant_velocity) for (int q = 0; q < 6; q++) st.velocity[q] = motion[q];
-    else for (int q = 0; q < 6; q++) st.velocity[q] = 0.9 * (0.5 * motion[q] + 0.5 * st.velocity[q]);
-    double m = 0;
-    for (int q = 0; q < 6; q++) {
-      double v = st.velocity[q];
-      if (q < 3) v *= 1.0 / st.scene_depth_mean;
-      m += v * v;
+    if (fmode == 0) {  // a recovery frame runs TrackMap and AssessTrackingQuality only (Tracker.cc:174-177)
+      // UpdateMotionModel (Tracker.cc:1035-1056)
+      double inv[12], rel[12], motion[6];
+      se3_inverse(ctl.start_pose, inv);
+      se3_mul(pose, inv, rel);
+      se3_ln(rel, motion);
+      if (d.prm.use_constant_velocity) for (int q = 0; q < 6; q++) st.velocity[q] = motion[q];
+      else for (int q = 0; q < 6; q++) st.velocity[q] = 0.9 * (0.5 * motion[q] + 0.5 * st.velocity[q]);
+      double m = 0;
+      for (int q = 0; q < 6; q++) {
+        double v = st.velocity[q];
+        if (q < 3) v *= 1.0 / st.scene_depth_mean;
+        m += v * v;
+      }
+      st.msd_scaled_velocity_magnitude = sqrt(m);
     }
-    st.msd_scaled_velocity_magnitude = sqrt(m);
     // AssessTrackingQuality (Tracker.cc:1062-1107)
     int ta = 0, tf = 0, la = 0, lf = 0;
     for (int l = 0; l < kLevels; l++) {
