@@ -38,7 +38,7 @@ def test_struct_layouts_match_header_sizes():
     import ctypes
     assert ctypes.sizeof(capi.TrackerParams) == 8 * 4 + 3 * 8 + 2 * 4 + 8
     assert ctypes.sizeof(capi.TrackerState) == 21 * 8 + 4 * 4
-    assert ctypes.sizeof(capi.TrackResult) == 14 * 8 + 24 * 4 + 3 * 4 + 4 + 8  # ... + recovery, reloc_keyframe, reserved1, (pad), reloc_score
+    assert ctypes.sizeof(capi.TrackResult) == 14 * 8 + 26 * 4 + 8  # 23 ints + recovery, reloc_keyframe, reserved1; reloc_score
     assert ctypes.sizeof(capi.BundleParams) == 2 * 4 + 2 * 8
     assert ctypes.sizeof(capi.BundleStats) == 6 * 4 + 4 * 8
 
