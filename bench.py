@@ -230,10 +230,20 @@ def reference_arm(args, rank, world):
         "config": {"workload": workload_name(), "map_points": int(len(m["src_kf"]))},
         "cpu_baseline": {"value": val, "unit": "frames/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    }), file=JSON_OUT, flush=True)
+
+
+def _claim_stdout():
+    """The reference's own code (oracle/_ref) writes progress text to fd 1 ("Waiting for mapmaker to die..").
+    Keep the real stdout for the one JSON line and send everything else written to fd 1 to stderr."""
+    global JSON_OUT
+    sys.stdout.flush()
+    JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
@@ -485,7 +495,7 @@ def main():
     if rank == 0 and not args.no_cpu_baseline:
         out["cpu_baseline"] = run_cpu_baseline(cpu_reference_lib(), kfs, m, frames, poses)
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        print(json.dumps(out), file=JSON_OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
