@@ -329,10 +329,8 @@ struct ptam_bundle {
     if (last_tail >= 0) PTAM_CUDA_TRY(this, cudaStreamWaitEvent(stream, ev_tail[last_tail], 0));
     k_ldlt_scale<<<(n + 255) / 256, 256, 0, stream>>>(d.S, d.vE, d.vE, n);
     launches++;
-    for (int k0 = ((n - 1) / kNB) * kNB; k0 >= 0; k0 -= kNB) {
-      k_ldlt_back<<<std::max(1, (k0 + 255) / 256), 256, 0, stream>>>(d.S, d.vE, d.upd, n, k0);
-      launches++;
-    }
+    k_ldlt_back<<<kBackCtas, kBackThreads, 0, stream>>>(d.S, d.vE, d.upd, n);  // one cluster, all panels
+    launches++;
     PTAM_CUDA_TRY(this, cudaGetLastError());
     return PTAM_OK;
   }

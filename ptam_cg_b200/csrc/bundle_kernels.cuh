@@ -333,9 +333,14 @@ __global__ void __launch_bounds__(128) k_ba_jacobian(BundleDev d) {
     }
   }
   // camera accumulators U (lower, packed 21) and epsA (6)
+  // Lanes without a contribution (erased / outlier measurements, fixed cameras: A and eps are zero there)
+  // ride along in the warp sums: the warp is uniform when all CONTRIBUTING lanes share one camera, which
+  // leaves only the ~3 % of warps that straddle a camera boundary on the per-lane path.
   const int c_acc = (active && cam_free) ? c : -1;
-  const int c0 = __shfl_sync(kFull, c_acc, 0);
-  const bool uniform = __all_sync(kFull, c_acc == c0);
+  if (c_acc < 0) { eps[0] = 0.0; eps[1] = 0.0; }  // 0 x inf of a wild outlier must not reach the sums
+  const unsigned contrib = __ballot_sync(kFull, c_acc >= 0);
+  const int c0 = contrib ? __shfl_sync(kFull, c_acc, __ffs(contrib) - 1) : -1;
+  const bool uniform = __all_sync(kFull, c_acc < 0 || c_acc == c0);
   if (uniform) {
     if (c0 >= 0) {
       int o = 0;
@@ -475,7 +480,7 @@ __global__ void __launch_bounds__(256) k_ba_mirror(double* S, int n) {
 //                  operand tiles are staged in shared memory by the TMA engine (one 512-byte
 //                  cp.async.bulk per row, completion on an mbarrier), rows padded to 68 doubles so
 //                  that fragment loads are bank-conflict free.
-//   k_ldlt_back    z = D^-1 y,  L^T x = z  (one CTA, 32-column blocks).
+//   k_ldlt_back    z = D^-1 y (k_ldlt_scale),  L^T x = z: all panels in one launch by an 8-CTA cluster.
 // ---------------------------------------------------------------------------------------------
 constexpr int kNB = 64;     // panel width
 constexpr int kUTM = 128;   // trailing-update tile rows
@@ -854,55 +859,83 @@ __global__ void __launch_bounds__(256, 2) k_ldlt_update(double* A, const double*
   }
 }
 
-// Backward substitution  L^T x = D^-1 y, one launch per 64-row panel from the bottom up.  Every CTA
-// first solves the panel's 64x64 block itself (x_p = L11^-T z_p; z_p is complete by then), CTA 0
-// stores it in x, then each CTA applies the panel to its slice of the rows above:
-// z[i] -= sum_c L[k0 + c][i] x[k0 + c], i < k0 (coalesced along i).  `z` must hold D^-1 y (k_ldlt_scale).
+// Backward substitution  L^T x = D^-1 y  in ONE launch.  The panels are walked from the bottom up by a
+// thread-block cluster of kBackCtas CTAs; the steps are separated by the hardware cluster barrier
+// (arrive.release / wait.acquire, which also orders the z updates in global memory between the CTAs)
+// instead of 47 kernel boundaries (C4: 47 x 11 us before).  Per 64-row panel every CTA first solves the
+// panel's 64x64 block itself (x_p = L11^-T z_p; z_p is complete by then), CTA 0 stores it in x, then each
+// CTA applies the panel to its slice of the rows above:  z[i] -= sum_c L[k0 + c][i] x[k0 + c], i < k0
+// (coalesced along i).  The next panel's diagonal block is fetched into registers while the current one
+// is being solved.  `z` must hold D^-1 y (k_ldlt_scale).
 __global__ void __launch_bounds__(256) k_ldlt_scale(const double* A, const double* y, double* z, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) z[i] = y[i] / A[(size_t)i * n + i];
 }
 
-__global__ void __launch_bounds__(256) k_ldlt_back(const double* A, double* z, double* x, int n, int k0) {
+constexpr int kBackCtas = 8;       // portable cluster size
+constexpr int kBackThreads = 512;  // 4096 threads: one row of z per thread up to n = 4160
+
+__global__ void __cluster_dims__(kBackCtas, 1, 1) __launch_bounds__(kBackThreads, 1) k_ldlt_back(const double* A, double* z, double* x, int n) {
   __shared__ double a[kNB][kNB + 1];
   __shared__ double xs[kNB];
-  const int nb = min(kNB, n - k0);
   const int tid = threadIdx.x;
-  for (int i = tid; i < kNB * kNB; i += blockDim.x) {
-    const int r = i / kNB, c = i % kNB;
-    a[r][c] = (r < nb && c < r) ? A[(size_t)(k0 + r) * n + k0 + c] : 0.0;
-  }
-  __syncthreads();
-  if (tid < 32) {  // L11^T x = z inside the block: lane r holds rows r and r + 32, pivots travel by shuffle
-    double x0 = tid < nb ? z[k0 + tid] : 0.0, x1 = tid + 32 < nb ? z[k0 + tid + 32] : 0.0;
-    for (int c = kNB - 1; c >= 32; c--) {
-      const double xc = __shfl_sync(kFull, x1, c - 32);
-      x0 -= a[c][tid] * xc;
-      if (tid + 32 < c) x1 -= a[c][tid + 32] * xc;
+  unsigned rank;
+  asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  constexpr int kPer = kNB * kNB / kBackThreads;
+  double nxt[kPer];
+  auto fetch = [&](int k0) {  // strict lower triangle of the diagonal block at k0, zero elsewhere
+    const int nb = min(kNB, n - k0);
+#pragma unroll
+    for (int q = 0; q < kPer; q++) {
+      const int i = tid + q * kBackThreads, r = i / kNB, c = i % kNB;
+      nxt[q] = (r < nb && c < r) ? A[(size_t)(k0 + r) * n + k0 + c] : 0.0;
     }
-    for (int c = 31; c >= 0; c--) {
-      const double xc = __shfl_sync(kFull, x0, c);
-      if (tid < c) x0 -= a[c][tid] * xc;
+  };
+  const int np = (n + kNB - 1) / kNB;
+  fetch((np - 1) * kNB);
+  for (int p = np - 1; p >= 0; p--) {
+    const int k0 = p * kNB, nb = min(kNB, n - k0);
+#pragma unroll
+    for (int q = 0; q < kPer; q++) {
+      const int i = tid + q * kBackThreads;
+      a[i / kNB][i % kNB] = nxt[q];
     }
-    xs[tid] = x0; xs[tid + 32] = x1;
-  }
-  __syncthreads();
-  if (blockIdx.x == 0 && tid < nb) x[k0 + tid] = xs[tid];  // z itself stays untouched: late CTAs still read it
-  const int i = blockIdx.x * blockDim.x + tid;
-  if (i >= k0) return;
-  double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-  const double* Ac = A + (size_t)k0 * n + i;
+    __syncthreads();
+    if (p > 0) fetch(k0 - kNB);
+    if (tid < 32) {  // L11^T x = z inside the block: lane r holds rows r and r + 32, pivots travel by shuffle
+      double x0 = tid < nb ? __ldcg(&z[k0 + tid]) : 0.0, x1 = tid + 32 < nb ? __ldcg(&z[k0 + tid + 32]) : 0.0;
+      for (int c = kNB - 1; c >= 32; c--) {
+        const double xc = __shfl_sync(kFull, x1, c - 32);
+        x0 -= a[c][tid] * xc;
+        if (tid + 32 < c) x1 -= a[c][tid + 32] * xc;
+      }
+      for (int c = 31; c >= 0; c--) {
+        const double xc = __shfl_sync(kFull, x0, c);
+        if (tid < c) x0 -= a[c][tid] * xc;
+      }
+      xs[tid] = x0; xs[tid + 32] = x1;
+    }
+    __syncthreads();
+    if (rank == 0 && tid < nb) x[k0 + tid] = xs[tid];
+    for (int i = (int)rank * kBackThreads + tid; i < k0; i += kBackCtas * kBackThreads) {
+      double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+      const double* Ac = A + (size_t)k0 * n + i;
 #pragma unroll 4
-  for (int c = 0; c < kNB; c += 4) {  // rows past nb are never touched: xs is zero there, but stay in bounds
-    if (c + 3 < nb) {
-      v0 += Ac[(size_t)c * n] * xs[c]; v1 += Ac[(size_t)(c + 1) * n] * xs[c + 1];
-      v2 += Ac[(size_t)(c + 2) * n] * xs[c + 2]; v3 += Ac[(size_t)(c + 3) * n] * xs[c + 3];
-    } else {
-      for (int q = c; q < nb; q++) v0 += Ac[(size_t)q * n] * xs[q];
+      for (int c = 0; c < kNB; c += 4) {  // rows past nb are never touched: xs is zero there, but stay in bounds
+        if (c + 3 < nb) {
+          v0 += Ac[(size_t)c * n] * xs[c]; v1 += Ac[(size_t)(c + 1) * n] * xs[c + 1];
+          v2 += Ac[(size_t)(c + 2) * n] * xs[c + 2]; v3 += Ac[(size_t)(c + 3) * n] * xs[c + 3];
+        } else {
+          for (int q = c; q < nb; q++) v0 += Ac[(size_t)q * n] * xs[q];
+        }
+      }
+      __stcg(&z[i], __ldcg(&z[i]) - ((v0 + v1) + (v2 + v3)));
     }
+    // every CTA of the cluster is done with this panel (and with a / xs) before the next one starts
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   }
-  z[i] -= (v0 + v1) + (v2 + v3);
 }
+
 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_ba_point_update(BundleDev d) {

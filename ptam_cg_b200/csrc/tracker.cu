@@ -111,7 +111,6 @@ struct ptam_tracker {
   cudaEvent_t prof_ev[16] = {};
   double prof_ms[8] = {};
   int64_t prof_n[8] = {};
-  int max_h = 0;
   // pipelined submit / collect: two frame landing buffers, a copy stream, per-slot events and results
   cudaStream_t cstream = nullptr;
   DevBuf<uint8_t> l0slot[2];
@@ -173,7 +172,6 @@ struct ptam_tracker {
       lw /= 2; lh /= 2;
     }
     g.pyr_bytes = img; g.corner_stride = cor; g.lut_stride = lut_o; g.mask_stride = msk; g.fast_tiles = tiles;
-    max_h = h;
     dev.cam = make_cam(cam_params, w, h);
     if (prm) dev.prm = *prm; else ptam_tracker_default_params(&dev.prm);
     {  // SmallBlurryImage geometry and Gaussian taps (ImageProcess.cc:279-304; libCVD convolveGaussian)
@@ -235,8 +233,6 @@ struct ptam_tracker {
       PTAM_CUDA_TRY(this, cudaFuncSetAttribute(k_reloc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbi_smem));
     }
     PTAM_CUDA_TRY(this, cudaFuncSetAttribute(k_pose, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoseSmemBytes));
-    if ((size_t)(max_h + 1) * sizeof(int) > 48 * 1024)
-      PTAM_CUDA_TRY(this, cudaFuncSetAttribute(k_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (max_h + 1) * (int)sizeof(int)));
     return PTAM_OK;
   }
 
@@ -352,7 +348,7 @@ struct ptam_tracker {
     dim3 gp((L0.w + 63) / 64, (L0.h + 63) / 64, S);
     pbegin(0); k_pyramid<<<gp, 256, 0, stream>>>(d); pend(0);
     pbegin(1); k_fast<<<dim3(d.g.fast_tiles, S), 256, 0, stream>>>(d); pend(1);
-    pbegin(2); k_compact<<<dim3(kLevels, S), 1024, (max_h + 1) * sizeof(int), stream>>>(d); pend(2);
+    pbegin(2); k_compact<<<dim3(kLevels, S), 1024, 0, stream>>>(d); pend(2);
     PTAM_CUDA_TRY(this, cudaGetLastError());
     return collect ? pcollect(7u) : PTAM_OK;
   }

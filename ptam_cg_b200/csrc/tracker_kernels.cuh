@@ -352,78 +352,57 @@ __global__ void __launch_bounds__(256) k_fast(TrackerDev d) {
 }
 
 // =============================================================================================
-// k_compact — one CTA per (level, stream): row counts by popc, exclusive scan = the row LUT
-// (LUT[y] = number of corners in rows < y, KeyFrame.cc:46-52), then corners written in raster order.
+// k_compact — one CTA per (level, stream).  The corner mask of a level is one contiguous array of
+// words (rows x nwords), so raster order is word order: a block-wide exclusive scan of the popcounts,
+// 1024 words per round, gives every word the index of its first corner; the word that starts row y
+// also holds LUT[y] = number of corners in rows < y (KeyFrame.cc:46-52).
 // =============================================================================================
 __global__ void __launch_bounds__(1024) k_compact(TrackerDev d) {
-  extern __shared__ int rowbase[];  // h + 1 ints
   __shared__ int wsum[32];
-  __shared__ int carry;
   const int l = blockIdx.x, s = blockIdx.y;
   const LevelDesc& L = d.g.lev[l];
   const uint32_t* mask = d.mask + (size_t)s * d.g.mask_stride + L.mask_off;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int y = warp; y < L.h; y += nwarps) {
-    int c = 0;
-    for (int wi = lane; wi < L.nwords; wi += 32) c += __popc(mask[(size_t)y * L.nwords + wi]);
-    c = warp_sum_int(c);
-    if (lane == 0) rowbase[y] = c;
-  }
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  // block-wide exclusive scan over rows, 1024 rows per round
-  for (int base = 0; base < L.h; base += blockDim.x) {
-    const int y = base + threadIdx.x;
-    const int v = y < L.h ? rowbase[y] : 0;
-    int inc = v;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nw = L.nwords, total = L.h * nw;
+  int* lut = d.lut + (size_t)s * d.g.lut_stride + L.lut_off;
+  int2* out = d.corners + (size_t)s * d.g.corner_stride + L.corner_off;
+  int carry = 0;  // corners in the words of earlier rounds (the same in every thread)
+  for (int base = 0; base < total; base += 1024) {
+    const int w = base + (int)threadIdx.x;
+    unsigned m = w < total ? mask[w] : 0u;
+    const int c = __popc(m);
+    int inc = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int n = __shfl_up_sync(kFull, inc, o);
-      if (lane >= o) inc += n;
+      const int v = __shfl_up_sync(kFull, inc, o);
+      if (lane >= o) inc += v;
     }
     if (lane == 31) wsum[warp] = inc;
     __syncthreads();
     if (warp == 0) {
-      int ws = lane < nwarps ? wsum[lane] : 0;
+      int ws = wsum[lane];
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        const int n = __shfl_up_sync(kFull, ws, o);
-        if (lane >= o) ws += n;
+        const int v = __shfl_up_sync(kFull, ws, o);
+        if (lane >= o) ws += v;
       }
       wsum[lane] = ws;
     }
     __syncthreads();
-    const int excl = carry + (warp ? wsum[warp - 1] : 0) + inc - v;
-    if (y < L.h) rowbase[y] = excl;
-    __syncthreads();
-    if (threadIdx.x == 0) carry += wsum[nwarps - 1];
-    __syncthreads();
-  }
-  int* lut = d.lut + (size_t)s * d.g.lut_stride + L.lut_off;
-  for (int y = threadIdx.x; y < L.h; y += blockDim.x) lut[y] = rowbase[y];
-  if (threadIdx.x == 0) d.ctl[s].n_corners[l] = carry;
-  int2* out = d.corners + (size_t)s * d.g.corner_stride + L.corner_off;
-  for (int y = warp; y < L.h; y += nwarps) {
-    int pos = rowbase[y];
-    for (int w0 = 0; w0 < L.nwords; w0 += 32) {
-      const int wi = w0 + lane;
-      unsigned m = wi < L.nwords ? mask[(size_t)y * L.nwords + wi] : 0u;
-      const int c = __popc(m);
-      int inc = c;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int n = __shfl_up_sync(kFull, inc, o);
-        if (lane >= o) inc += n;
-      }
-      int o = pos + inc - c;
+    int o = carry + (warp ? wsum[warp - 1] : 0) + inc - c;
+    carry += wsum[31];
+    if (w < total) {
+      const int y = w / nw, wi = w - y * nw;
+      if (wi == 0) lut[y] = o;
       while (m) {
         const int b = __ffs(m) - 1;
         m &= m - 1;
         out[o++] = make_int2(wi * 32 + b, y);
       }
-      pos += __shfl_sync(kFull, inc, 31);
     }
+    __syncthreads();  // wsum is rewritten by the next round
   }
+  if (threadIdx.x == 0) d.ctl[s].n_corners[l] = carry;
 }
 
 // =============================================================================================
@@ -1144,7 +1123,7 @@ __global__ void __launch_bounds__(128) k_search_prep(TrackerDev d, int stage) {
   }
 }
 
-__global__ void __launch_bounds__(128) k_search(TrackerDev d, int stage) {
+__global__ void __launch_bounds__(128, 8) k_search(TrackerDev d, int stage) {
   __shared__ __align__(8) uint8_t stmpl[4][64];
   __shared__ int2 squeue[4][64];
   const int s = blockIdx.y;

@@ -225,3 +225,56 @@ def test_persistent_graph_recompute(oracle, product):
     np.testing.assert_allclose(b.get_points(), p[7], rtol=0, atol=1e-7)
     np.testing.assert_allclose(b.get_cameras(), p[8], rtol=0, atol=1e-7)
     b.close()
+
+
+def test_full_size_c4_step_parity_and_run_properties(oracle, product):
+    """BASELINE config C4 at its full size (500 keyframes x 100 000 points x 600 000 measurements, reduced
+    system n = 2 994).  The first LM step starts from bit-identical state, so it is compared with the
+    oracle directly (sigma^2, errors, outlier list, S, vE, every camera and point); the rest of the run is
+    checked through size-independent properties of Bundle::Compute (Bundle.cc:116-158, 512-533)."""
+    g = synth.make_ba_graph(500, 100000, 600000, seed=43)
+    o, p = _pair(oracle, product, g)
+    o.begin(); p.begin()
+    o.lm_step(); p.lm_step()
+    so, sp = o.stats(), p.stats()
+    _same_stats(so, sp, rtol=1e-10)
+    assert sp.accepted == 1 and sp.last_new_error < sp.last_error
+    n = 6 * int((g["cam_fixed"] == 0).sum())
+    assert n == 2994
+    So, eo = o.reduced_system(n)
+    Sp, ep = p.reduced_system(n)
+    np.testing.assert_allclose(Sp, So, atol=1e-12 * np.abs(So).max(), rtol=0)
+    np.testing.assert_allclose(ep, eo, atol=1e-12 * np.abs(eo).max(), rtol=0)
+    assert np.array_equal(Sp, Sp.T)
+    del So, Sp
+    assert np.array_equal(o.GetOutlierMeasurements(), p.GetOutlierMeasurements())
+    # delta = S^-1 vE through a 2 994 x 2 994 LDL^T: the reordered sums (DMMA tiles, atomics) are amplified
+    # by the conditioning of S, hence 1e-9 rather than the 1e-10 of the small graphs
+    np.testing.assert_allclose(p.get_points(), o.get_points(), atol=1e-9, rtol=0)
+    np.testing.assert_allclose(p.get_cameras(), o.get_cameras(), atol=1e-9, rtol=0)
+    o.close()
+    # ---- the rest of the run on the device: LM invariants
+    errs = [sp.last_new_error]
+    trials = sp.lambda_trials
+    for _ in range(40):
+        s = p.stats()
+        if s.converged or s.hit_max_iterations:
+            break
+        p.lm_step()
+        s2 = p.stats()
+        assert s2.lambda_trials > trials and s2.lambda_trials <= 20  # Bundle.MaxIterations
+        if s2.accepted > s.accepted:  # an accepted step never raises the robust error
+            assert s2.last_new_error < s2.last_error
+            errs.append(s2.last_new_error)
+        trials = s2.lambda_trials
+    s = p.stats()
+    assert s.converged or s.hit_max_iterations
+    assert s.accepted >= 5 and len(errs) == s.accepted
+    out = p.GetOutlierMeasurements()
+    assert len(out) == s.n_outliers and len({(int(a), int(b)) for a, b in out}) == len(out)
+    # ~2 % gross outliers were planted; Tukey must find most of them and not much else
+    assert 0.5 * 0.02 * 600000 < len(out) < 2.0 * 0.02 * 600000
+    np.testing.assert_array_equal(p.get_cameras()[0], g["cam_se3"][0])  # gauge: the fixed camera never moves
+    assert np.isfinite(p.get_points()).all() and np.isfinite(p.get_cameras()).all()
+    assert np.abs(p.get_points() - g["true_points"]).mean() < 0.6 * np.abs(g["points"] - g["true_points"]).mean()
+    p.close()
