@@ -410,7 +410,10 @@ struct ptam_bundle {
         launches += 2;
       }
       pend(3);
-      pbegin(4); if (PO > 0) { k_ba_schur<<<(PO + 7) / 8, 256, 0, stream>>>(d); launches++; } pend(4);
+      pbegin(4);
+      if (M > 0 && n > 0) { k_ba_schur_diag<<<(M + 127) / 128, 128, 0, stream>>>(d); launches++; }
+      if (PO > 0 && n > 0) { k_ba_schur<<<(PO + 7) / 8, 256, 0, stream>>>(d); launches++; }
+      pend(4);
       s_mirrored = false;
       pbegin(5);
       if (n > 0) {  // the cross-camera J^T J reduction: partial S, vE of every shard -> total on every shard
@@ -736,11 +739,12 @@ int ptam_bundle_get_reduced_system(ptam_bundle* b, double* S, double* vE, int ca
   if (PO > 0) k_ba_vinv<<<(PO + 255) / 256, 256, 0, b->stream>>>(b->d);
   k_ba_init_s<<<std::min<size_t>(((size_t)n * n + 255) / 256, 148 * 8), 256, 0, b->stream>>>(b->d);
   k_ba_init_diag<<<b->d.n_cams, 64, 0, b->stream>>>(b->d);
+  if (b->d.n_meas > 0) k_ba_schur_diag<<<(b->d.n_meas + 127) / 128, 128, 0, b->stream>>>(b->d);
   if (PO > 0) k_ba_schur<<<(PO + 7) / 8, 256, 0, b->stream>>>(b->d);
   { int rc = b->all_reduce(b->d.S, (size_t)n * n, ncclDouble, ncclSum, "all-reduce of S"); if (rc) return rc;
     rc = b->all_reduce(b->d.vE, n, ncclDouble, ncclSum, "all-reduce of vE"); if (rc) return rc; }
   k_ba_mirror<<<std::min<size_t>(((size_t)n * n + 255) / 256, 148 * 8), 256, 0, b->stream>>>(b->d.S, n);
-  b->launches += 5;
+  b->launches += 6;
   PTAM_CUDA_TRY(b, cudaGetLastError());
   PTAM_CUDA_TRY(b, cudaStreamSynchronize(b->stream));
   PTAM_CUDA_TRY(b, cudaMemcpy2D(S, sizeof(double) * cap_n, b->S.p, sizeof(double) * n, sizeof(double) * n, n, cudaMemcpyDeviceToHost));

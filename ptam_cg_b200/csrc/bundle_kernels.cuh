@@ -413,23 +413,91 @@ __global__ void __launch_bounds__(64) k_ba_init_diag(BundleDev d) {
   } else if (t < 42) d.vE[row + t - 36] = d.epsA[6 * c + t - 36];
 }
 
-// warp per point: all camera pairs (j >= k) observing it, both cameras free, both measurements good
+// Schur complement (Bundle.cc:365-453), two kernels.
+// k_ba_schur_diag — the diagonal blocks and vE: one thread per observation in list order,
+//   S_jj -= W_ij V*_i^-1 W_ij^T (lower triangle, 21 values),  vE_j -= W_ij V*_i^-1 epsB_i.
+// The list is usually camera-major, so a warp mostly shares one camera: the 27 values are summed over the
+// warp and added with one atomic each (as k_ba_jacobian does for U / epsA) instead of 1 200 atomics per
+// address and camera at C4; warps that straddle a camera boundary use per-lane atomics.
+__global__ void __launch_bounds__(128) k_ba_schur_diag(BundleDev d) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  int jrow = -1;
+  double D[21], e[6];
+#pragma unroll
+  for (int q = 0; q < 21; q++) D[q] = 0.0;
+#pragma unroll
+  for (int q = 0; q < 6; q++) e[q] = 0.0;
+  if (m < d.n_meas && d.m_state[m] == M_ALIVE) {
+    jrow = d.cam_row[d.m_cam[m]];
+    if (jrow >= 0) {
+      const int i = d.m_pt[m];
+      const double* Vi = d.Vinv + 9 * (size_t)i;
+      const double* ve = d.Ve + 3 * (size_t)i;
+      const double* W = d.m_W + 18 * (size_t)m;
+      double Wr[18], WV[18];
+#pragma unroll
+      for (int q = 0; q < 18; q++) Wr[q] = W[q];
+#pragma unroll
+      for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) WV[3 * r + c] = Wr[3 * r] * Vi[c] + Wr[3 * r + 1] * Vi[3 + c] + Wr[3 * r + 2] * Vi[6 + c];
+      int o = 0;
+#pragma unroll
+      for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int c = 0; c <= r; c++) D[o++] = -(WV[3 * r] * Wr[3 * c] + WV[3 * r + 1] * Wr[3 * c + 1] + WV[3 * r + 2] * Wr[3 * c + 2]);
+#pragma unroll
+      for (int r = 0; r < 6; r++) e[r] = -(Wr[3 * r] * ve[0] + Wr[3 * r + 1] * ve[1] + Wr[3 * r + 2] * ve[2]);
+    }
+  }
+  const unsigned contrib = __ballot_sync(kFull, jrow >= 0);
+  if (!contrib) return;
+  const int j0 = __shfl_sync(kFull, jrow, __ffs(contrib) - 1);
+  const bool uniform = __all_sync(kFull, jrow < 0 || jrow == j0);
+  if (uniform) {
+    int o = 0;
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+      for (int c = 0; c <= r; c++) {
+        const double v = warp_sum(D[o++]);
+        if (lane == 0) atomicAdd(&d.S[(size_t)(j0 + r) * d.n + j0 + c], v);
+      }
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+      const double v = warp_sum(e[r]);
+      if (lane == 0) atomicAdd(&d.vE[j0 + r], v);
+    }
+  } else if (jrow >= 0) {
+    int o = 0;
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+      for (int c = 0; c <= r; c++) atomicAdd(&d.S[(size_t)(jrow + r) * d.n + jrow + c], D[o++]);
+#pragma unroll
+    for (int r = 0; r < 6; r++) atomicAdd(&d.vE[jrow + r], e[r]);
+  }
+}
+
+// k_ba_schur — the off-diagonal blocks: warp per point, lane per camera pair (j > k) observing it, both
+// cameras free, both measurements good:  S_jk -= W_ij V*_i^-1 W_ik^T  (36 f64 atomics into the lower S).
 __global__ void __launch_bounds__(256) k_ba_schur(BundleDev d) {
   const int i = d.p_lo + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= d.p_hi) return;
   const int lane = threadIdx.x & 31;
   const int o0 = d.pt_off[i], k = d.pt_off[i + 1] - o0;
-  if (k == 0) return;
+  if (k < 2) return;
   double Vi[9];
 #pragma unroll
   for (int q = 0; q < 9; q++) Vi[q] = d.Vinv[9 * i + q];
-  const int npairs = k * (k + 1) / 2;
+  const int npairs = k * (k - 1) / 2;
   for (int pr = lane; pr < npairs; pr += 32) {
-    // pr -> (a, b), b <= a
-    int a = (int)((sqrt(8.0 * pr + 1.0) - 1.0) * 0.5);
-    while (a * (a + 1) / 2 > pr) a--;
-    while ((a + 1) * (a + 2) / 2 <= pr) a++;
-    const int b = pr - a * (a + 1) / 2;
+    // pr -> (a, b), b < a:  pr = a (a - 1) / 2 + b
+    int a = (int)((sqrt(8.0 * pr + 1.0) + 1.0) * 0.5);
+    while (a * (a - 1) / 2 > pr) a--;
+    while ((a + 1) * a / 2 <= pr) a++;
+    const int b = pr - a * (a - 1) / 2;
     const int mj = d.pt_meas[o0 + a], mk = d.pt_meas[o0 + b];
     if (d.m_state[mj] != M_ALIVE || d.m_state[mk] != M_ALIVE) continue;
     const int jrow = d.cam_row[d.m_cam[mj]], krow = d.cam_row[d.m_cam[mk]];
@@ -449,11 +517,6 @@ __global__ void __launch_bounds__(256) k_ba_schur(BundleDev d) {
         const double v = WV[3 * r] * Wk[3 * c] + WV[3 * r + 1] * Wk[3 * c + 1] + WV[3 * r + 2] * Wk[3 * c + 2];
         atomicAdd(&Sb[(size_t)r * d.n + c], -v);
       }
-    if (a == b) {
-      const double* ve = d.Ve + 3 * i;
-#pragma unroll
-      for (int r = 0; r < 6; r++) atomicAdd(&d.vE[jrow + r], -(Wj[3 * r] * ve[0] + Wj[3 * r + 1] * ve[1] + Wj[3 * r + 2] * ve[2]));
-    }
   }
 }
 

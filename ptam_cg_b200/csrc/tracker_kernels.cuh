@@ -1123,7 +1123,7 @@ __global__ void __launch_bounds__(128) k_search_prep(TrackerDev d, int stage) {
   }
 }
 
-__global__ void __launch_bounds__(128, 8) k_search(TrackerDev d, int stage) {
+__global__ void __launch_bounds__(128, 12) k_search(TrackerDev d, int stage) {
   __shared__ __align__(8) uint8_t stmpl[4][64];
   __shared__ int2 squeue[4][64];
   const int s = blockIdx.y;
