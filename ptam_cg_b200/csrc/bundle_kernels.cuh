@@ -564,7 +564,7 @@ constexpr int kUpdateSmem = (kUTM + kUTN) * kLds * (int)sizeof(double) + 16;
 // left-looking loop.  Result: `a` holds L (strict lower) and D (diagonal), `ysh` the forward-substituted
 // right-hand side, `dinv` the reciprocals of D.  Entries above the diagonal are scratch.
 constexpr int kPanelThreads = 256;
-constexpr int kPanelRows = 64;  // rows of the panel solved per CTA (threads 0..63; more CTAs beat fuller CTAs here)
+constexpr int kPanelRows = 64;  // rows of the panel solved per CTA (four threads per row; more CTAs beat fuller CTAs here)
 #ifdef PTAM_PANEL_DEBUG
 __device__ long long g_dbg[8];
 #define DBG_T(k) if (blockIdx.x == 0 && threadIdx.x == 0) { const long long now = clock64(); atomicAdd((unsigned long long*)&g_dbg[k], (unsigned long long)(now - t_prev)); t_prev = now; }
@@ -775,38 +775,50 @@ __global__ void __launch_bounds__(kPanelThreads) k_ldlt_panel(double* A, double*
     if (tid < nb) y[k0 + tid] = y1[tid];
   }
   DBG_T(2)
-  // ---- rows below the block: one thread per row
-  const int row = row0 + tid;
-  if (tid >= kPanelRows || row >= n) return;  // nb < kNB only on the last panel, which has no rows below it
-  double x[kNB];
-  double* Ar = A + (size_t)row * n + k0;
+  // ---- rows below the block, w L11^T = a: FOUR threads per row (r = tid / 4), thread q = tid % 4 owns the 16
+  // columns c = q (mod 4).  Right-looking, two columns per step as before (same expressions, same order per
+  // element): the two pivots of the step travel by shuffle from their owners, then every thread updates its
+  // own columns to the right with one 16-byte broadcast load of (L[c2][c], L[c2][c+1]) per column.  All 256
+  // threads work (the serial chain per row is 32 steps of shuffle -> FMA -> shuffle -> FMA), and a thread
+  // holds 16 values instead of 64.
+  const int r = tid >> 2, q = tid & 3, lane = tid & 31;
+  const int row = row0 + r;
+  double x[kNB / 4];
 #pragma unroll
-  for (int c = 0; c < kNB; c += 2) { const double2 v = *reinterpret_cast<const double2*>(&wo[tid][c]); x[c] = v.x; x[c + 1] = v.y; }
+  for (int j = 0; j < kNB / 4; j++) x[j] = wo[r][4 * j + q];
   DBG_T(3)
-  // w L11^T = a, two columns at a time (right-looking: independent updates, one 16-byte broadcast
-  // load of (L[c2][c], L[c2][c+1]) per two FMAs)
 #pragma unroll
   for (int c = 0; c < kNB; c += 2) {
-    const double xc0 = x[c];
-    x[c + 1] -= xc0 * a[c + 1][c];
-    const double xc1 = x[c + 1];
+    const int jc = c >> 2;  // the owners of columns c and c + 1 hold them in x[jc]
+    const double xc0 = __shfl_sync(kFull, x[jc], (lane & ~3) | (c & 3));
+    if (q == ((c + 1) & 3)) x[jc] -= xc0 * a[c + 1][c];
+    const double xc1 = __shfl_sync(kFull, x[jc], (lane & ~3) | ((c + 1) & 3));
 #pragma unroll
-    for (int c2 = c + 2; c2 < kNB; c2++) {
-      const double2 l = *reinterpret_cast<const double2*>(&a[c2][c]);
-      x[c2] -= xc0 * l.x + xc1 * l.y;
+    for (int j = jc; j < kNB / 4; j++) {
+      const int c2 = 4 * j + q;
+      if (j > jc || c2 > c + 1) {
+        const double2 l = *reinterpret_cast<const double2*>(&a[c2][c]);
+        x[j] -= xc0 * l.x + xc1 * l.y;
+      }
     }
   }
   DBG_T(4)
-  double* Wr = Wp + (size_t)row * kNB;  // holds -(L21 D1): the update kernel accumulates C += Wp L21^T
   double dot = 0.0;
+  if (row < n) {
+    double* Ar = A + (size_t)row * n + k0;
+    double* Wr = Wp + (size_t)row * kNB;  // holds -(L21 D1): the update kernel accumulates C += Wp L21^T
 #pragma unroll
-  for (int c = 0; c < kNB; c += 2) {
-    *reinterpret_cast<double2*>(Wr + c) = make_double2(-x[c], -x[c + 1]);
-    const double l0 = x[c] * dinv[c], l1 = x[c + 1] * dinv[c + 1];  // value * (1 / d), as TooN does
-    *reinterpret_cast<double2*>(Ar + c) = make_double2(l0, l1);
-    dot += l0 * y1[c] + l1 * y1[c + 1];
+    for (int j = 0; j < kNB / 4; j++) {
+      const int c = 4 * j + q;
+      Wr[c] = -x[j];
+      const double l = x[j] * dinv[c];  // value * (1 / d), as TooN does
+      Ar[c] = l;
+      dot += l * y1[c];
+    }
   }
-  y[row] -= dot;
+  dot += __shfl_xor_sync(kFull, dot, 1);
+  dot += __shfl_xor_sync(kFull, dot, 2);
+  if (q == 0 && row < n) y[row] -= dot;
   DBG_T(5)
 }
 
