@@ -683,7 +683,7 @@ PTAM_DEV void block_ldlt64(double (*a)[kLda], double (*us)[8], double* dinv, dou
 // Shared memory of k_ldlt_panel (dynamic): the diagonal block, the rank-8 operand, the right-hand side and
 // the reciprocals, plus three 64x64 operands of the PENDING update (see below); the third is reused for
 // the updated rows of this CTA.
-constexpr int kPanelSmem = (4 * kNB * kLda + kNB * 8 + 2 * kNB) * (int)sizeof(double);
+constexpr int kPanelSmem = (4 * kNB * kLda + kNB * 8 + 2 * kNB) * (int)sizeof(double) + 16;  // + the mbarrier of the bulk loads
 
 // Panel k, fused with the head of panel k-1's trailing update.  The columns of panel k still miss the
 // contribution of panel k-1 (the tail kernel of panel k-1 only covers the column blocks from k+1 on), so
@@ -707,16 +707,52 @@ __global__ void __launch_bounds__(kPanelThreads) k_ldlt_panel(double* A, double*
 #ifdef PTAM_PANEL_DEBUG
   long long t_prev = clock64();
 #endif
-  for (int i = tid; i < kNB * kNB; i += blockDim.x) {
-    const int r = i / kNB, c = i % kNB;
-    a[r][c] = (r < nb && c <= r) ? A[(size_t)(k0 + r) * n + k0 + c] : (r == c ? 1.0 : 0.0);
-    if (pend) {
-      lh[r][c] = r < nb ? A[(size_t)(k0 + r) * n + (k0 - kNB) + c] : 0.0;
-      wd[r][c] = r < nb ? Wprev[(size_t)(k0 + r) * kNB + c] : 0.0;
-      wo[r][c] = r < rows_own ? Wprev[(size_t)(row0 + r) * kNB + c] : 0.0;
+  if (nb == kNB) {
+    // full panel: the four 64x64 operands arrive as 512-byte rows through the TMA engine (one cp.async.bulk
+    // per row and thread, completion on an mbarrier) while the threads fetch their register tiles below.
+    // `a` then also holds S's (finite, never used) values above the diagonal: block_ldlt64 treats them as scratch.
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(dinv + kNB);
+    const unsigned mbar_a = (unsigned)__cvta_generic_to_shared(mbar);
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_a));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    __syncthreads();
+    const int rows_w = max(0, rows_own);
+    if (tid == 0) {
+      const unsigned bytes = (unsigned)(kNB + (pend ? 2 * kNB + rows_w : 0)) * kNB * (unsigned)sizeof(double);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_a), "r"(bytes) : "memory");
+    }
+    {
+      const int which = tid >> 6, r = tid & 63;  // 0: a, 1: lh, 2: wd, 3: wo
+      const double* src = nullptr;
+      double* dst = which == 0 ? a[r] : which == 1 ? lh[r] : which == 2 ? wd[r] : wo[r];
+      if (which == 0) src = A + (size_t)(k0 + r) * n + k0;
+      else if (pend) {
+        if (which == 1) src = A + (size_t)(k0 + r) * n + (k0 - kNB);
+        else if (which == 2) src = Wprev + (size_t)(k0 + r) * kNB;
+        else if (r < rows_w) src = Wprev + (size_t)(row0 + r) * kNB;
+      }
+      if (src) {
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"((unsigned)(kNB * sizeof(double))), "r"(mbar_a) : "memory");
+      } else if (pend && which == 3) {
+        for (int c = 0; c < kNB; c++) dst[c] = 0.0;  // rows past the matrix
+      }
+    }
+    if (tid < kNB) y1[tid] = y[k0 + tid];
+  } else {
+    for (int i = tid; i < kNB * kNB; i += blockDim.x) {  // the short last panel (identity padding, no rows below it)
+      const int r = i / kNB, c = i % kNB;
+      a[r][c] = (r < nb && c <= r) ? A[(size_t)(k0 + r) * n + k0 + c] : (r == c ? 1.0 : 0.0);
+      if (pend) {
+        lh[r][c] = r < nb ? A[(size_t)(k0 + r) * n + (k0 - kNB) + c] : 0.0;
+        wd[r][c] = r < nb ? Wprev[(size_t)(k0 + r) * kNB + c] : 0.0;
+        wo[r][c] = r < rows_own ? Wprev[(size_t)(row0 + r) * kNB + c] : 0.0;
+      }
+    }
+    if (tid < kNB) y1[tid] = tid < nb ? y[k0 + tid] : 0.0;
   }
-  if (tid < kNB) y1[tid] = tid < nb ? y[k0 + tid] : 0.0;
   // this CTA's rows of the panel, as 4x4 register tiles (rows ty + 16 i, columns tx + 16 j)
   double co[4][4];
 #pragma unroll
@@ -726,7 +762,15 @@ __global__ void __launch_bounds__(kPanelThreads) k_ldlt_panel(double* A, double*
       const int r = ty + 16 * i;
       co[i][j] = r < rows_own ? A[(size_t)(row0 + r) * n + k0 + tx + 16 * j] : 0.0;
     }
-  __syncthreads();
+  if (nb == kNB) {
+    const unsigned mbar_a = (unsigned)__cvta_generic_to_shared(dinv + kNB);
+    unsigned ok = 0;
+    while (!ok)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(ok) : "r"(mbar_a) : "memory");
+  }
+  __syncthreads();  // also covers the plain stores
+  DBG_T(0)
   if (pend) {
     double cd[4][4];
 #pragma unroll
@@ -764,9 +808,9 @@ __global__ void __launch_bounds__(kPanelThreads) k_ldlt_panel(double* A, double*
 #pragma unroll
     for (int j = 0; j < 4; j++) wo[ty + 16 * i][tx + 16 * j] = co[i][j];
   __syncthreads();
-  DBG_T(0)
-  block_ldlt64(a, us, dinv, y1, nb);
   DBG_T(1)
+  block_ldlt64(a, us, dinv, y1, nb);
+  DBG_T(2)
   if (blockIdx.x == 0) {
     for (int i = tid; i < nb * nb; i += blockDim.x) {
       const int r = i / nb, c = i % nb;
@@ -774,19 +818,19 @@ __global__ void __launch_bounds__(kPanelThreads) k_ldlt_panel(double* A, double*
     }
     if (tid < nb) y[k0 + tid] = y1[tid];
   }
-  DBG_T(2)
+  DBG_T(3)
   // ---- rows below the block, w L11^T = a: FOUR threads per row (r = tid / 4), thread q = tid % 4 owns the 16
-  // columns c = q (mod 4).  Right-looking, two columns per step as before (same expressions, same order per
-  // element): the two pivots of the step travel by shuffle from their owners, then every thread updates its
-  // own columns to the right with one 16-byte broadcast load of (L[c2][c], L[c2][c+1]) per column.  All 256
-  // threads work (the serial chain per row is 32 steps of shuffle -> FMA -> shuffle -> FMA), and a thread
-  // holds 16 values instead of 64.
+  // columns c = q (mod 4).  Right-looking, two columns per step (same expressions, same order per element as
+  // a thread-per-row loop): the two pivots of the step travel by shuffle from their owners, then every thread
+  // updates its own columns to the right with one 16-byte broadcast load of (L[c2][c], L[c2][c+1]) per
+  // column.  All 256 threads work and a thread holds 16 values instead of 64 (6.0 -> 4.95 us per panel; a
+  // four-columns-per-step variant with the 4x4 triangle solved redundantly was slower, 5.85 us).
   const int r = tid >> 2, q = tid & 3, lane = tid & 31;
   const int row = row0 + r;
   double x[kNB / 4];
 #pragma unroll
   for (int j = 0; j < kNB / 4; j++) x[j] = wo[r][4 * j + q];
-  DBG_T(3)
+  DBG_T(4)
 #pragma unroll
   for (int c = 0; c < kNB; c += 2) {
     const int jc = c >> 2;  // the owners of columns c and c + 1 hold them in x[jc]
@@ -802,7 +846,7 @@ __global__ void __launch_bounds__(kPanelThreads) k_ldlt_panel(double* A, double*
       }
     }
   }
-  DBG_T(4)
+  DBG_T(5)
   double dot = 0.0;
   if (row < n) {
     double* Ar = A + (size_t)row * n + k0;
@@ -819,7 +863,7 @@ __global__ void __launch_bounds__(kPanelThreads) k_ldlt_panel(double* A, double*
   dot += __shfl_xor_sync(kFull, dot, 1);
   dot += __shfl_xor_sync(kFull, dot, 2);
   if (q == 0 && row < n) y[row] -= dot;
-  DBG_T(5)
+  DBG_T(6)
 }
 
 PTAM_DEV unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }

@@ -5,7 +5,7 @@ from ptam_cg_b200 import synth
 from ptam_cg_b200.capi import Bundle, product_lib
 from ptam_cg_b200.bench_ba import CONFIGS
 prod = product_lib()
-names = ["load diag", "factor", "store diag", "load rows", "row solve", "store W/L"]
+names = ["load", "pending update", "factor", "store diag", "load rows", "row solve", "store W/L"]
 for cfg in ("C3", "C4"):
     g = synth.make_ba_graph(**CONFIGS[cfg])
     b = Bundle(prod, g["width"], g["height"]); b.add_graph(g)
