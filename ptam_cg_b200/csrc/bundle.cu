@@ -170,6 +170,7 @@ struct ptam_bundle {
     if (p) prm = *p; else ptam_bundle_default_params(&prm);
     cam = ptam_make_cam_model(cam_params, w, h);
     PTAM_CUDA_TRY(this, cudaFuncSetAttribute(k_ldlt_update, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpdateSmem));
+    PTAM_CUDA_TRY(this, cudaFuncSetAttribute(k_ldlt_step, cudaFuncAttributeMaxDynamicSharedMemorySize, kPanelSmem));
     PTAM_CUDA_TRY(this, cudaFuncSetAttribute(k_ldlt_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPanelSmem));
     return PTAM_OK;
   }
@@ -290,6 +291,9 @@ struct ptam_bundle {
   // the rest of panel k's trailing update (column blocks from k+2 on: the tail) runs on the second stream
   // after panel k.  Panel k+1 does not touch those tiles and overlaps it; panel k+2 waits for it (it reads
   // tiles that tail updates and overwrites the Wp buffer it reads).  Wp is double-buffered by panel parity.
+  // Once the tail is small (<= kFuseTailTiles tiles) it is not launched on its own: it rides in the NEXT
+  // panel's launch (k_ldlt_step: panel k + tail k-1 in one grid), so the late, latency-bound part of the
+  // factorisation is a plain sequence of kernels on one stream without event records / waits in between.
   int solve_reduced() {
     const int n = d.n;
     if (n == 0) return PTAM_OK;
@@ -304,26 +308,38 @@ struct ptam_bundle {
     }
     // vE is consumed in place as the right-hand side (forward substitution rides with the panels)
     int last_tail = -1;
+    bool deferred = false;      // the tail of panel k-1 waits to be launched together with panel k (k_ldlt_step)
     for (int k = 0, k0 = 0; k0 < n; k++, k0 += kNB) {
       const int nb = std::min(kNB, n - k0);
       const int rem = n - k0 - nb;
       double* wp = Wp.p + (size_t)(k & 1) * n * kNB;
-      const double* wprev = k > 0 ? Wp.p + (size_t)((k - 1) & 1) * n * kNB : nullptr;
+      double* wprev = k > 0 ? Wp.p + (size_t)((k - 1) & 1) * n * kNB : nullptr;
+      const int n_ctas = std::max(1, (rem + kPanelRows - 1) / kPanelRows);
       // panel k reads tiles the tail of panel k-2 updated, and overwrites the Wp buffer that tail read
       if (k >= 2 && tail_of[k - 2]) PTAM_CUDA_TRY(this, cudaStreamWaitEvent(stream, ev_tail[k - 2], 0));
-      k_ldlt_panel<<<std::max(1, (rem + kPanelRows - 1) / kPanelRows), kPanelThreads, kPanelSmem, stream>>>(d.S, wp, wprev, d.vE, n, k0);
+      if (deferred) {
+        const int nt = (n - k0 + kUTM - 1) / kUTM;  // tail of panel k-1: its trailing matrix starts at k0
+        k_ldlt_step<<<n_ctas + nt * nt, kPanelThreads, kPanelSmem, stream>>>(d.S, wp, wprev, d.vE, n, k0, n_ctas);
+      } else {
+        k_ldlt_panel<<<n_ctas, kPanelThreads, kPanelSmem, stream>>>(d.S, wp, wprev, d.vE, n, k0);
+      }
       launches++;
       tail_of[k] = false;
-      if (rem > kNB) {  // column blocks from k+2 on exist: the tail of the trailing update, on the second stream
+      deferred = false;
+      if (rem > kNB) {  // column blocks from k+2 on exist: the tail of the trailing update
         const int nt = (rem + kUTM - 1) / kUTM;
         const int n_tail = nt * (nt + 1) - nt;
-        PTAM_CUDA_TRY(this, cudaEventRecord(ev_panel[k], stream));
-        PTAM_CUDA_TRY(this, cudaStreamWaitEvent(stream2, ev_panel[k], 0));
-        k_ldlt_update<<<n_tail, 256, kUpdateSmem, stream2>>>(d.S, wp, n, k0, 2);
-        PTAM_CUDA_TRY(this, cudaEventRecord(ev_tail[k], stream2));
-        launches++;
-        tail_of[k] = true;
-        last_tail = k;
+        if (n_tail <= kFuseTailTiles) {
+          deferred = true;  // small enough to hide behind panel k+1 at one CTA per SM: same launch, same stream
+        } else {            // large: its own launch (two CTAs per SM) on the second stream
+          PTAM_CUDA_TRY(this, cudaEventRecord(ev_panel[k], stream));
+          PTAM_CUDA_TRY(this, cudaStreamWaitEvent(stream2, ev_panel[k], 0));
+          k_ldlt_update<<<n_tail, 256, kUpdateSmem, stream2>>>(d.S, wp, n, k0, 2);
+          PTAM_CUDA_TRY(this, cudaEventRecord(ev_tail[k], stream2));
+          launches++;
+          tail_of[k] = true;
+          last_tail = k;
+        }
       }
     }
     if (last_tail >= 0) PTAM_CUDA_TRY(this, cudaStreamWaitEvent(stream, ev_tail[last_tail], 0));

@@ -564,6 +564,7 @@ constexpr int kUpdateSmem = (kUTM + kUTN) * kLds * (int)sizeof(double) + 16;
 // left-looking loop.  Result: `a` holds L (strict lower) and D (diagonal), `ysh` the forward-substituted
 // right-hand side, `dinv` the reciprocals of D.  Entries above the diagonal are scratch.
 constexpr int kPanelThreads = 256;
+constexpr int kFuseTailTiles = 256;  // tails of at most this many 128x64 tiles ride in the next panel's launch (k_ldlt_step)
 constexpr int kPanelRows = 64;  // rows of the panel solved per CTA (four threads per row; more CTAs beat fuller CTAs here)
 #ifdef PTAM_PANEL_DEBUG
 __device__ long long g_dbg[8];
@@ -690,7 +691,7 @@ constexpr int kPanelSmem = (4 * kNB * kLda + kNB * 8 + 2 * kNB) * (int)sizeof(do
 // every CTA first applies it itself:  A[rows][cols k] += Wp_prev[rows] L_head^T  for the diagonal block
 // (all CTAs, redundantly, like the factorisation) and for its own 64 rows, 4x4 register tiles over K = 64.
 // That makes the chain one kernel per panel instead of panel -> head update -> panel.
-__global__ void __launch_bounds__(kPanelThreads) k_ldlt_panel(double* A, double* Wp, const double* Wprev, double* y, int n, int k0) {
+PTAM_DEV void ldlt_panel_body(double* A, double* Wp, const double* Wprev, double* y, int n, int k0, int block) {
   extern __shared__ __align__(16) unsigned char panel_smem[];
   double (*a)[kLda] = reinterpret_cast<double (*)[kLda]>(panel_smem);
   double (*lh)[kLda] = a + kNB;    // L of the diagonal block's rows in panel k-1's columns
@@ -701,7 +702,7 @@ __global__ void __launch_bounds__(kPanelThreads) k_ldlt_panel(double* A, double*
   double* dinv = y1 + kNB;
   const int nb = min(kNB, n - k0);
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-  const int row0 = k0 + nb + blockIdx.x * kPanelRows;
+  const int row0 = k0 + nb + block * kPanelRows;
   const int rows_own = min(kPanelRows, n - row0);  // <= 0: the last panel's single CTA has no rows below the block
   const bool pend = Wprev != nullptr;
 #ifdef PTAM_PANEL_DEBUG
@@ -811,7 +812,7 @@ __global__ void __launch_bounds__(kPanelThreads) k_ldlt_panel(double* A, double*
   DBG_T(1)
   block_ldlt64(a, us, dinv, y1, nb);
   DBG_T(2)
-  if (blockIdx.x == 0) {
+  if (block == 0) {
     for (int i = tid; i < nb * nb; i += blockDim.x) {
       const int r = i / nb, c = i % nb;
       if (c <= r) A[(size_t)(k0 + r) * n + k0 + c] = a[r][c];
@@ -866,30 +867,34 @@ __global__ void __launch_bounds__(kPanelThreads) k_ldlt_panel(double* A, double*
   DBG_T(6)
 }
 
+__global__ void __launch_bounds__(kPanelThreads) k_ldlt_panel(double* A, double* Wp, const double* Wprev, double* y, int n, int k0) {
+  ldlt_panel_body(A, Wp, Wprev, y, n, k0, (int)blockIdx.x);
+}
+
 PTAM_DEV unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 // part 0: all tiles; part 1: only the first column block (the next panel's 64 columns: look-ahead
 // head); part 2: everything else (look-ahead tail, runs on the second stream).
-__global__ void __launch_bounds__(256, 2) k_ldlt_update(double* A, const double* Wp, int n, int k0, int part) {
+PTAM_DEV void ldlt_update_body(double* A, const double* Wp, int n, int k0, int part, int block) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sW = reinterpret_cast<double*>(smem_raw);            // [kUTM][kLds]  -(L21 D1) rows of the i-tile
   double* sL = sW + kUTM * kLds;                                // [kUTN][kLds]  L21 rows of the j-tile
   unsigned long long* mbar = reinterpret_cast<unsigned long long*>(sL + kUTN * kLds);
   const int r0 = k0 + kNB;
   int bi, bj;
-  if (part == 1) { bi = blockIdx.x; bj = 0; }
+  if (part == 1) { bi = block; bj = 0; }
   else if (part == 2) {
     // row block bi has column blocks bj = 1 .. 2 bi + 1: 2 bi + 1 tiles, bi^2 before it
-    bi = (int)sqrt((double)blockIdx.x);
-    while (bi * bi > (int)blockIdx.x) bi--;
-    while ((bi + 1) * (bi + 1) <= (int)blockIdx.x) bi++;
-    bj = blockIdx.x - bi * bi + 1;
+    bi = (int)sqrt((double)block);
+    while (bi * bi > block) bi--;
+    while ((bi + 1) * (bi + 1) <= block) bi++;
+    bj = block - bi * bi + 1;
   } else {
     // row block bi (128 rows) has column blocks bj = 0 .. 2 bi + 1 (64 columns): bi (bi + 1) tiles before it
-    bi = (int)((sqrt(4.0 * blockIdx.x + 1.0) - 1.0) * 0.5);
-    while (bi * (bi + 1) > (int)blockIdx.x) bi--;
-    while ((bi + 1) * (bi + 2) <= (int)blockIdx.x) bi++;
-    bj = blockIdx.x - bi * (bi + 1);
+    bi = (int)((sqrt(4.0 * block + 1.0) - 1.0) * 0.5);
+    while (bi * (bi + 1) > block) bi--;
+    while ((bi + 1) * (bi + 2) <= block) bi++;
+    bj = block - bi * (bi + 1);
   }
   const int i0 = r0 + bi * kUTM, j0 = r0 + bj * kUTN;
   if (j0 >= n) return;  // the last row block may be short of its second diagonal column block
@@ -976,6 +981,21 @@ __global__ void __launch_bounds__(256, 2) k_ldlt_update(double* A, const double*
       else if (j <= i) Ci[j] = acc[mi][ni][0];
     }
   }
+}
+
+__global__ void __launch_bounds__(256, 2) k_ldlt_update(double* A, const double* Wp, int n, int k0, int part) {
+  ldlt_update_body(A, Wp, n, k0, part, (int)blockIdx.x);
+}
+
+// One launch per step of the late factorisation: the CTAs of panel k (blocks 0 .. n_panel_ctas-1, dispatched
+// first: they are the chain) and, behind them, the tail of panel k-1's trailing update (column blocks from
+// k+1 on), which only depends on panel k-1 and touches nothing panel k reads or writes.  With both in one
+// grid the chain is a single stream of back-to-back kernels: no second stream, no event record / wait
+// between the panels (those cost ~9 us per panel).  Used once the tail is small enough to hide behind the
+// panel at one CTA per SM; the early, large tails keep their own two-CTAs-per-SM launches on the second stream.
+__global__ void __launch_bounds__(256) k_ldlt_step(double* A, double* Wp_cur, double* Wp_prev, double* y, int n, int k0, int n_panel_ctas) {
+  if ((int)blockIdx.x < n_panel_ctas) ldlt_panel_body(A, Wp_cur, Wp_prev, y, n, k0, (int)blockIdx.x);
+  else ldlt_update_body(A, Wp_prev, n, k0 - kNB, 2, (int)blockIdx.x - n_panel_ctas);
 }
 
 // Backward substitution  L^T x = D^-1 y  in ONE launch.  The panels are walked from the bottom up by a
