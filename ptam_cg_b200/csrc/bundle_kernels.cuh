@@ -564,7 +564,7 @@ constexpr int kUpdateSmem = (kUTM + kUTN) * kLds * (int)sizeof(double) + 16;
 // left-looking loop.  Result: `a` holds L (strict lower) and D (diagonal), `ysh` the forward-substituted
 // right-hand side, `dinv` the reciprocals of D.  Entries above the diagonal are scratch.
 constexpr int kPanelThreads = 256;
-constexpr int kFuseTailTiles = 256;  // tails of at most this many 128x64 tiles ride in the next panel's launch (k_ldlt_step)
+constexpr int kFuseTailTiles = 576;  // tails of at most this many 128x64 tiles ride in the next panel's launch (k_ldlt_step)
 constexpr int kPanelRows = 64;  // rows of the panel solved per CTA (four threads per row; more CTAs beat fuller CTAs here)
 #ifdef PTAM_PANEL_DEBUG
 __device__ long long g_dbg[8];
