@@ -67,6 +67,7 @@ class ClockSampler:
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
         self._t = None
+        self._active = False
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -85,6 +86,9 @@ class ClockSampler:
             getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
         }
         while not self._stop.is_set():
+            if not self._active:
+                time.sleep(0.0005)
+                continue
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 try:
@@ -96,15 +100,25 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.004)
 
-    def __enter__(self):
-        if self.nv:
+    def start(self):
+        if os.environ.get("PTAM_BENCH_NO_SAMPLER"):
+            self.nv = None
+        """Start the polling thread ahead of the timed region (thread start-up and the first NVML call are
+        not free); it only samples between __enter__ and __exit__."""
+        if self.nv and self._t is None:
             self._t = threading.Thread(target=self._run, daemon=True)
             self._t.start()
         return self
 
+    def __enter__(self):
+        self.start()
+        self._active = True
+        return self
+
     def __exit__(self, *a):
+        self._active = False
         self._stop.set()
         if self._t:
             self._t.join()
@@ -292,7 +306,11 @@ def main():
             return [det_trk.get_level(0, l)[:2] for l in range(4)]
         return detect
 
-    frames, poses, kfs, m = build_workload(detect_factory, F, 20260101 + rank)
+    # weak scaling = the same work on every GPU: the C2 replicas all track the seed-20260101 sequence (their
+    # streams, maps and states are their own); C5 (--res 1280x720) uses seed 20260101 + g for GPU g,
+    # whose scenes differ in corner count by ~15 %, which the max-over-ranks time then reflects
+    c5 = (W, H) == (1280, 720)
+    frames, poses, kfs, m = build_workload(detect_factory, F, 20260101 + (rank if c5 else 0))
     trk = Tracker(prod, W, H, S, device=local)
     for k in kfs:
         trk.add_keyframe(k)
@@ -324,13 +342,16 @@ def main():
     for i in range(Wm):
         trk.track_frames_device(batches[i].data_ptr(), FRAME_BYTES, W)
     trk.synchronize()
+    sampler = ClockSampler(local).start()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = trk.launch_count()
-    with ClockSampler(local) as clk:
+    with sampler as clk:
         ev0.record(ext)
+        th0 = time.perf_counter()
         for i in range(Wm, n_steps):
             trk.track_frames_device(batches[i].data_ptr(), FRAME_BYTES, W)
+        host_launch_ms = (time.perf_counter() - th0) * 1e3 / K  # host time to queue one step (the device runs behind)
         ev1.record(ext)
         trk.synchronize()
         torch.cuda.synchronize()
@@ -344,7 +365,13 @@ def main():
     n_cand = float(np.mean([r.n_candidates for r in last]))
     n_searched = float(np.mean([r.n_coarse + r.n_level3 + r.n_fine for r in last]))
     tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    per_rank = None
     if world > 1:
+        # every rank's own device time and median SM clock, so that a slow replica is visible in the line
+        mine = torch.tensor([ms, float(clk.summary()["sm_mhz"] or 0.0)], device="cuda", dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"ms_per_step": [float(a[0].item()) / K for a in allr], "sm_mhz": [float(a[1].item()) for a in allr]}
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms_max = float(tms.item())
     value = world * S * K / (ms_max * 1e-3)
@@ -458,6 +485,7 @@ def main():
         "vs_baseline": None, "dtype": "u8/int32/f64", "data": "synthetic",
         "config": {"workload": workload_name(),
                    "streams_per_gpu": S, "map_points": int(len(m["src_kf"])), "frames_per_step": world * S,
+                   "replicas": ("seed 20260101 + g on GPU g" if c5 else "every GPU tracks its own streams of the seed-20260101 sequence (per-GPU work fixed)"),
                    "l2": f"inputs > L2: every step reads a distinct {S}x{FRAME_BYTES} B batch out of a "
                          f"{n_steps * S * FRAME_BYTES / 1e6:.0f} MB resident set",
                    "mean_found_per_frame": found, "mean_attempted_per_frame": attempted,
@@ -465,11 +493,13 @@ def main():
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": S * FRAME_BYTES,
                 "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * float(te.item()) / K,
                 "api": "ptam_tracker_submit_frames / ptam_tracker_collect, pinned host frames, 2 steps in flight"},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches), "host_launch_ms_per_step": host_launch_ms,
         "clocks": clk.summary(),
         "roofline": rl, "roofline_a1_group": rl_a1, "kernels": per_kernel,
         "single_stream_latency_ms": lat_ms,
     }
+    if per_rank:
+        out["per_rank"] = per_rank
 
     # ================= BA (configs C3 / C4) =================
     # N = 1: Bundle::Compute on C3 and C4 on this GPU.  N > 1: C4 sharded over all ranks (points
