@@ -268,6 +268,9 @@ struct ptam_bundle {
     UP(pt_off, off); UP(pt_meas, idx); UP(m_cam, v_mcam); UP(m_pt, v_mpt); UP(m_found, v_found); UP(m_sin, v_sin);
     UP(m_gid, l_gid);
 #undef UP
+    // pageable H2D copies return once staged; the handle's streams are non-blocking (no implicit ordering with
+    // the legacy stream the copies ran on), so finish them before the first kernel is queued
+    PTAM_CUDA_TRY(this, cudaStreamSynchronize(cudaStreamLegacy));
     d.cam = cam; d.n_cams = C; d.n_pts = P; d.n_meas = M; d.n = n; d.est = prm.mestimator;
     d.p_lo = p_lo; d.p_hi = p_hi; d.add_cam_update = rank == 0 ? 1 : 0;
     d.cam_se3 = cam_se3.p; d.cam_se3_new = cam_se3_new.p; d.cam_fixed = cam_fixed.p; d.cam_row = cam_row.p;

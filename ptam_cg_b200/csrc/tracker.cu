@@ -26,6 +26,10 @@ struct DevBuf {
     if (!count) return cudaSuccess;
     cudaError_t e = cudaMalloc(&p, count * sizeof(T));
     if (e == cudaSuccess) e = cudaMemset(p, 0, count * sizeof(T));
+    // cudaMemset runs on the legacy default stream, which the library's non-blocking streams do not
+    // synchronise with: without this a kernel queued right after a late allocation (the epipolar / re-find /
+    // MakeKeyFrame_Rest buffers) could see its output zeroed behind its back
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);
     return e;
   }
   void free() { if (p) cudaFree(p); p = nullptr; n = 0; }
@@ -221,6 +225,7 @@ struct ptam_tracker {
       st.scene_depth_mean = 1.0; st.scene_depth_sigma = 1.0;
     }
     PTAM_CUDA_TRY(this, cudaMemcpy(ctl.p, h_ctl, sizeof(StreamCtl) * S, cudaMemcpyHostToDevice));
+    PTAM_CUDA_TRY(this, cudaStreamSynchronize(cudaStreamLegacy));
     dev.pyr = pyr.p; dev.corners = corners.p; dev.lut = lut.p; dev.mask = mask.p; dev.ctl = ctl.p;
     dev.pt_count = pt_count.p;
     dev.kf_ptrs = nullptr; dev.n_kf = 0;
@@ -470,6 +475,7 @@ int ptam_tracker_add_keyframe(ptam_tracker* t, const uint8_t* image, int stride)
   }
   PTAM_CUDA_TRY(t, cudaStreamSynchronize(t->stream));
   PTAM_CUDA_TRY(t, cudaMemcpy(t->kf_ptrs.p, t->kf_bufs.data(), sizeof(uint8_t*) * t->kf_bufs.size(), cudaMemcpyHostToDevice));
+  PTAM_CUDA_TRY(t, cudaStreamSynchronize(cudaStreamLegacy));  // pageable H2D: the DMA may still be in flight on return
   t->dev.kf_ptrs = t->kf_ptrs.p;
   t->dev.n_kf = (int)t->kf_bufs.size();
   k_kf_sbi<<<1, 256, t->sbi_smem, t->stream>>>(t->dev, t->dev.n_kf - 1);  // KeyFrame::pSBI (KeyFrame.cc:80-81)
@@ -492,6 +498,7 @@ int ptam_tracker_set_keyframe_pose(ptam_tracker* t, int kf, const double* se3) {
   }
   PTAM_CUDA_TRY(t, cudaStreamSynchronize(t->stream));
   PTAM_CUDA_TRY(t, cudaMemcpy(t->kf_pose.p, t->h_kf_pose.data(), sizeof(double) * t->h_kf_pose.size(), cudaMemcpyHostToDevice));
+  PTAM_CUDA_TRY(t, cudaStreamSynchronize(cudaStreamLegacy));
   t->dev.kf_pose = t->kf_pose.p;
   bool all = true;
   for (char c : t->h_kf_has_pose) all = all && c;
@@ -524,6 +531,7 @@ int ptam_tracker_set_map(ptam_tracker* t, int stream, int n, const double* world
   PTAM_CUDA_TRY(t, cudaMemset(t->level.p + o, 0xff, sizeof(int) * t->cap));
   t->h_pt_count[stream] = n;
   PTAM_CUDA_TRY(t, cudaMemcpy(t->pt_count.p, t->h_pt_count.data(), sizeof(int) * t->S, cudaMemcpyHostToDevice));
+  PTAM_CUDA_TRY(t, cudaStreamSynchronize(cudaStreamLegacy));  // the uploads and memsets above ran on the legacy stream
   return PTAM_OK;
 }
 
@@ -532,6 +540,7 @@ int ptam_tracker_set_state(ptam_tracker* t, int stream, const ptam_tracker_state
   if (stream < 0 || stream >= t->S) { t->set_error("bad stream"); return PTAM_ERR_INVALID; }
   PTAM_CUDA_TRY(t, cudaStreamSynchronize(t->stream));
   PTAM_CUDA_TRY(t, cudaMemcpy(&t->ctl.p[stream].st, s, sizeof(*s), cudaMemcpyHostToDevice));
+  PTAM_CUDA_TRY(t, cudaStreamSynchronize(cudaStreamLegacy));
   return PTAM_OK;
 }
 int ptam_tracker_get_state(ptam_tracker* t, int stream, ptam_tracker_state* s) {

@@ -278,3 +278,23 @@ def test_full_size_c4_step_parity_and_run_properties(oracle, product):
     assert np.isfinite(p.get_points()).all() and np.isfinite(p.get_cameras()).all()
     assert np.abs(p.get_points() - g["true_points"]).mean() < 0.6 * np.abs(g["points"] - g["true_points"]).mean()
     p.close()
+
+
+def test_large_reduced_system_two_stream_solve(oracle, product):
+    """n = 3 354 (560 keyframes): the first trailing-update tails have more than 576 tiles and run as their own
+    launches on the second stream, the later ones ride in the next panel's launch — the hand-over between the
+    two schedules of the blocked LDL^T (csrc/bundle.cu solve_reduced) is on this path, and nowhere at C4."""
+    g = synth.make_ba_graph(560, 20000, 120000, seed=44)
+    o, p = _pair(oracle, product, g)
+    o.begin(); p.begin()
+    o.lm_step(); p.lm_step()
+    _same_stats(o.stats(), p.stats(), rtol=1e-10)
+    assert p.stats().accepted == 1
+    assert np.array_equal(o.GetOutlierMeasurements(), p.GetOutlierMeasurements())
+    np.testing.assert_allclose(p.get_points(), o.get_points(), atol=1e-9, rtol=0)
+    np.testing.assert_allclose(p.get_cameras(), o.get_cameras(), atol=1e-9, rtol=0)
+    o.close()
+    p.lm_step()   # a second step through the same solve (event reuse across solves)
+    s = p.stats()
+    assert s.lambda_trials >= 2 and np.isfinite(p.get_cameras()).all() and np.isfinite(p.get_points()).all()
+    p.close()
