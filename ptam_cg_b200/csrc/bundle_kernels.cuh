@@ -533,16 +533,19 @@ __global__ void __launch_bounds__(256) k_ba_mirror(double* S, int n) {
 // Dense solve  delta_a = S^-1 vE  (Bundle.cc:457-458, TooN Cholesky<>: square-root-free LDL^T, no
 // pivoting, no failure path — a non-positive-definite S yields inf/NaN exactly as in the reference).
 // Right-looking blocked factorisation, panel width 64, with the forward substitution folded in:
-//   k_ldlt_panel   every CTA factors the 64x64 diagonal block in shared memory (redundantly: it is
-//                  8 us of work and saves a launch and a dependency), then solves 128 rows of the
-//                  panel below it, one thread per row:  w = a L11^-T  (= L21 D1),  L21 = w D1^-1,
-//                  and applies the panel to the right-hand side:  y2 -= L21 y1.
-//   k_ldlt_update  trailing update  A22 -= (L21 D1) L21^T  on the lower triangle, 128x128 tiles,
+//   k_ldlt_panel   every CTA applies the previous panel's pending update to the panel's 64 columns (its
+//                  diagonal block and its own 64 rows), factors the 64x64 diagonal block in shared memory
+//                  (redundantly: it saves a launch and a dependency), then solves its 64 rows of the panel,
+//                  four threads per row:  w = a L11^-T  (= L21 D1),  L21 = w D1^-1, and applies the panel
+//                  to the right-hand side:  y2 -= L21 y1.  Operands arrive by cp.async.bulk + mbarrier.
+//   k_ldlt_update  trailing update  A22 -= (L21 D1) L21^T  on the lower triangle, 128x64 tiles,
 //                  K = 64: the one genuine dense contraction of either hot path.  FP64 has no
 //                  tcgen05 form, so it runs on the f64 tensor pipe (DMMA, mma.sync m8n8k4);
 //                  operand tiles are staged in shared memory by the TMA engine (one 512-byte
 //                  cp.async.bulk per row, completion on an mbarrier), rows padded to 68 doubles so
 //                  that fragment loads are bank-conflict free.
+//   k_ldlt_step    panel k and the tail of panel k-1's trailing update in one grid (the late, latency-bound
+//                  part of the factorisation as back-to-back launches on one stream).
 //   k_ldlt_back    z = D^-1 y (k_ldlt_scale),  L^T x = z: all panels in one launch by an 8-CTA cluster.
 // ---------------------------------------------------------------------------------------------
 constexpr int kNB = 64;     // panel width
