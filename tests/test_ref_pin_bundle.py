@@ -105,3 +105,20 @@ def test_recompute_on_the_same_object_matches_reference():
     assert o[0] == r[0] and np.array_equal(o[1], r[1]) and len(o[1]) > 0
     assert (o[2], o[3]) == (r[2], r[3]) and np.array_equal(o[4], r[4])
     assert np.array_equal(o[5], r[5]) and np.array_equal(o[6], r[6])
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13, 14, 15, 16])
+def test_seed_sweep_bit_identical_to_reference(seed):
+    """Different shapes, outlier fractions and M-estimators per seed: the oracle must follow the reference's own
+    Bundle.cc bit for bit on every one of them (decisions, outlier order, every state)."""
+    rng = np.random.default_rng(seed)
+    n_cams = int(rng.integers(4, 25))
+    n_points = int(rng.integers(80, 900))
+    n_meas = int(n_points * rng.uniform(2.2, 4.5))
+    g = synth.make_ba_graph(n_cams, n_points, n_meas, seed=seed, outlier_frac=float(rng.choice([0.0, 0.02, 0.1])))
+    prm = dict(mestimator=int(rng.integers(0, 3)), max_iterations=int(rng.integers(3, 21)))
+    o, r = _run(oracle_lib(libm_atan=True), g, **prm), _run(REF, g, **prm)
+    for k in ("acc", "trials", "converged", "hit_max", "sigma", "lam"):
+        assert o[k] == r[k], k
+    assert np.array_equal(o["outliers"], r["outliers"])
+    assert np.array_equal(o["points"], r["points"]) and np.array_equal(o["cams"], r["cams"])

@@ -255,3 +255,19 @@ def test_relocaliser_failure_leaves_the_tracker_alone():
         assert (so.lost_frames, so.frame) == (sr.lost_frames, sr.frame)
         modes.append(ro.recovery)
     assert modes[:4] == [0, 0, 0, 0] and modes[4] in (1, 2)
+
+
+@pytest.mark.parametrize("seed", [20260102, 20260103, 20260104])
+def test_other_scenes_bit_identical_to_reference(seed):
+    """The C5 stream seeds (seed 20260101 + g): other textures, other corner sets, other candidate
+    lists — the oracle must still follow the reference's TrackFrame bit for bit, with other settings too."""
+    W, H = 320, 240
+    frames, poses, kfs, m = _scene(W, H, 10, (0, 5), (120, 60, 30, 15), seed=seed)
+    prm = dict(use_rotation_estimator=seed & 1, mestimator=seed % 3, coarse_min_velocity=0.0 if seed % 2 else 0.006)
+    to, tr = (_tracker(lib, W, H, kfs, m, **prm) for lib in (oracle_lib(libm_atan=True), REF))
+    start = synth.perturb_pose(poses[1], np.random.default_rng(seed))
+    for t in (to, tr):
+        t.set_state(0, pose12=start, msd=0.02)
+    for f in range(1, 8):
+        ro, rr = to.track_frames([frames[f]])[0], tr.track_frames([frames[f]])[0]
+        assert _compare_frame(to, tr, ro, rr) > 60
