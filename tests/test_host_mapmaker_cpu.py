@@ -1,0 +1,50 @@
+"""The MapMaker host mirror (ptam_cg_b200/host/MapMaker.h: BundleAdjustAll / BundleAdjustRecent / BundleAdjust,
+reference src/MapMaker.cc:767-933) checked WITHOUT a GPU: mapmaker_check.cc is compiled against the CPU oracle,
+which exports the product's ABI under another prefix (tests/orc_alias.h), and the map it leaves behind is compared
+with what the reference's control flow must produce, computed in Python over the same ABI (tests/mapmaker_util.py).
+The GPU run of the same binary against the CUDA library is tests/test_zz_host_mapmaker_gpu.py."""
+import subprocess
+from pathlib import Path
+
+import pytest
+
+import mapmaker_util as mu
+from oracle.binding import oracle_lib
+
+ROOT = Path(__file__).resolve().parent.parent
+HOST = ROOT / "ptam_cg_b200" / "host"
+
+
+@pytest.fixture(scope="module")
+def orc_binary(tmp_path_factory):
+    out = tmp_path_factory.mktemp("mm") / "mapmaker_check_orc"
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-I", str(HOST), "-include", str(ROOT / "tests" / "orc_alias.h"),
+           str(HOST / "mapmaker_check.cc"), "-o", str(out), "-L", str(ROOT / "oracle"), "-loracle",
+           "-Wl,-rpath," + str(ROOT / "oracle")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return out
+
+
+@pytest.mark.parametrize("mode", [0, 1], ids=["BundleAdjustAll", "BundleAdjustRecent"])
+def test_mapmaker_mirror_follows_the_reference_control_flow(orc_binary, tmp_path, mode):
+    g = mu.make_map()
+    mu.write_map(g, tmp_path, mode, 20)
+    r = subprocess.run([str(orc_binary), str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = mu.read_map(tmp_path, len(g["cam_fixed"]), len(g["points"]))
+    exp = mu.expected(oracle_lib(), g, mode, 20)
+    assert exp["accepted"] > 0
+    mu.compare(got, exp, tol=0.0)  # same library, same call order: bit for bit
+    assert got["bad"].sum() + len(got["queue"]) + len(got["never"]) > 0  # the outlier bookkeeping was exercised
+
+
+def test_recent_adjustment_needs_eight_keyframes(orc_binary, tmp_path):
+    g = mu.make_map(n_cams=6, n_points=150, n_meas=600, seed=5)
+    mu.write_map(g, tmp_path, 1, 20)
+    r = subprocess.run([str(orc_binary), str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = mu.read_map(tmp_path, 6, 150)
+    import numpy as np
+    assert np.array_equal(got["points"], g["points"]) and np.array_equal(got["cams"], g["cam_se3"])  # MapMaker.cc:789-792
+    assert list(got["flags"][:2]) == [1, 1]
