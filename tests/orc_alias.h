@@ -25,6 +25,13 @@
 #define ptam_tracker_make_keyframes orc_tracker_make_keyframes
 #define ptam_tracker_keyframe_rest orc_tracker_keyframe_rest
 #define ptam_tracker_get_level_rest orc_tracker_get_level_rest
+#define ptam_tracker_default_params orc_tracker_default_params
+#define ptam_tracker_add_keyframe orc_tracker_add_keyframe
+#define ptam_tracker_set_map orc_tracker_set_map
+#define ptam_tracker_set_state orc_tracker_set_state
+#define ptam_tracker_get_state orc_tracker_get_state
+#define ptam_tracker_get_points orc_tracker_get_points
+#define ptam_tracker_track_frames orc_tracker_track_frames
 #define ptam_global_last_error orc_test_global_last_error
 #ifdef __cplusplus
 extern "C"
