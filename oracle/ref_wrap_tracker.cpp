@@ -298,6 +298,15 @@ int ref_tracker_refind_in_keyframes(void* hp, const uint8_t* const* images, int 
 // the stream's current frame.  The new MapPoint the reference creates is read (sub-pixel target
 // position = kTarget.mMeasurements[pNew].v2RootPos, triangulated v3WorldPos) and removed again.
 // NB the reference caches UnProject of every pixel in a function-local static sized by the first call.
+// world position + pixel-right / pixel-down vectors (9 doubles) of every point the last ref_tracker_epipolar_search
+// added, in candidate order: what MapMaker.cc:648-672 (Triangulate, RefreshPixelVectors) computed.  Test hook for
+// the host mirror's MapMaker::AddPointsEpipolar; not part of the shared ABI.
+static std::vector<double> g_last_epi_points;
+int ref_tracker_epipolar_last_points(double* out, int cap_points) {
+  const int n = (int)g_last_epi_points.size() / 9;
+  if (out) std::memcpy(out, g_last_epi_points.data(), sizeof(double) * 9 * (size_t)std::min(n, cap_points));
+  return n;
+}
 int ref_tracker_epipolar_search(void* hp, int stream, int level, int src_kf, const double* src_se3, double src_depth_mean,
                                 double src_depth_sigma, const double* target_se3, double wiggle_scale, int n_cand,
                                 const int32_t* cand_xy, int32_t* found, int32_t* best_corner, double* sub_pos) {
@@ -314,6 +323,7 @@ int ref_tracker_epipolar_search(void* hp, int stream, int level, int src_kf, con
   st.mm->mdWiggleScale = wiggle_scale;
   std::vector<Candidate> saved = src.aLevels[level].vCandidates;
   src.aLevels[level].vCandidates.clear();
+  g_last_epi_points.clear();
   for (int c = 0; c < n_cand; c++) {
     Candidate cd;
     cd.irLevelPos = CVD::ImageRef(cand_xy[2 * c], cand_xy[2 * c + 1]);
@@ -326,6 +336,9 @@ int ref_tracker_epipolar_search(void* hp, int stream, int level, int src_kf, con
     if (!st.mm->Epipolar(src, tgt, level, c)) continue;
     MapPoint* p = st.map.vpPoints.back();
     found[c] = 1;
+    for (int k = 0; k < 3; k++) g_last_epi_points.push_back(p->v3WorldPos[k]);   // the point the reference's own
+    for (int k = 0; k < 3; k++) g_last_epi_points.push_back(p->v3PixelRight_W[k]);  // Triangulate / RefreshPixelVectors made
+    for (int k = 0; k < 3; k++) g_last_epi_points.push_back(p->v3PixelDown_W[k]);
     const Measurement& m = tgt.mMeasurements[p];
     sub_pos[2 * c] = m.v2RootPos[0]; sub_pos[2 * c + 1] = m.v2RootPos[1];
     tgt.mMeasurements.erase(p); src.mMeasurements.erase(p);

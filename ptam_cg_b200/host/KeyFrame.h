@@ -4,6 +4,7 @@
 // FAST-10 corners in raster order and the row LUT are computed on the device and copied back into
 // the same members the reference fills (Level::im, vCorners, vCornerRowLUT).
 #pragma once
+#include <cmath>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -117,14 +118,32 @@ struct KeyFrame {  // KeyFrame.h:130-150
   }
 };
 
-struct MapPoint {  // Map.h:46-98 (the fields the tracker reads and writes)
+struct MapPoint {  // Map.h:46-98 (the fields the tracker and the map maker's hot paths read and write)
   TooN::Vector<3> v3WorldPos;
   bool bBad = false;
   KeyFrame* pPatchSourceKF = nullptr;
   int nSourceLevel = 0;
   CVD::ImageRef irCenter;
+  // the source patch's plane: unit view rays of its centre and of one level-pixel right / down of it, and
+  // the plane normal, all in the source keyframe's camera frame (Map.h:68-75)
+  TooN::Vector<3> v3Center_NC, v3OneDownFromCenter_NC, v3OneRightFromCenter_NC, v3Normal_NC;
   TooN::Vector<3> v3PixelDown_W, v3PixelRight_W;
   int nMEstimatorOutlierCount = 0, nMEstimatorInlierCount = 0;
+
+  // Map.cc:40-65: world-frame steps of one source-level pixel right / down on the patch's plane
+  void RefreshPixelVectors() {
+    const KeyFrame& k = *pPatchSourceKF;
+    const TooN::Vector<3> on_plane_c = k.se3CfromW * v3WorldPos;
+    const double height = std::fabs(on_plane_c * v3Normal_NC);
+    auto hit = [&](const TooN::Vector<3>& ray) {  // (ray * height) / rate, in the reference's order of operations
+      const double rate = std::fabs(ray * v3Normal_NC);
+      return TooN::makeVector(ray[0] * height / rate, ray[1] * height / rate, ray[2] * height / rate);
+    };
+    const TooN::Vector<3> c = hit(v3Center_NC), r = hit(v3OneRightFromCenter_NC), d = hit(v3OneDownFromCenter_NC);
+    const TooN::SO3<> Rwc = k.se3CfromW.get_rotation().inverse();
+    v3PixelRight_W = Rwc * (r - c);
+    v3PixelDown_W = Rwc * (d - c);
+  }
 };
 
 struct Map {  // Map.h:28-44

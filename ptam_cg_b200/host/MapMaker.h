@@ -1,5 +1,6 @@
-// Host mirror of the bundle-adjustment side of class MapMaker (reference include/MapMaker.h:38-160): the only
-// caller of Bundle.  BundleAdjustAll / BundleAdjustRecent choose the keyframe and point sets
+// Host mirror of class MapMaker (reference include/MapMaker.h:38-160) on the hot paths: the bundle-adjustment
+// side — MapMaker is the only caller of Bundle — and the epipolar search for new map points
+// (AddPointsEpipolar).  BundleAdjustAll / BundleAdjustRecent choose the keyframe and point sets
 // (src/MapMaker.cc:767-836), BundleAdjust marshals them into a Bundle, runs it and writes the adjusted state
 // and the outlier bookkeeping back into the map (src/MapMaker.cc:838-933).  Same member names, argument
 // meaning and side effects as the reference; the arithmetic runs behind ptam_bundle_* (host/Bundle.h).
@@ -11,7 +12,10 @@
 #include <algorithm>
 #include <cmath>
 #include <map>
+#include <memory>
 #include <set>
+#include <stdexcept>
+#include <string>
 #include <utility>
 #include <vector>
 #include "Bundle.h"
@@ -32,6 +36,127 @@ class MapMaker {
   MapMaker(Map& m, const ATANCamera& cam, int device = 0, const ptam_bundle_params* params = nullptr)
       : mMap(m), mCamera(cam), mnDevice(device) {
     if (params) { mParams = *params; mbHaveParams = true; }
+  }
+  ~MapMaker() { if (mpAssoc) ptam_tracker_destroy(mpAssoc); }
+  MapMaker(const MapMaker&) = delete;
+  MapMaker& operator=(const MapMaker&) = delete;
+
+  // MapMaker.cc:172-187: the point seen at v2A / v2B (z = 1 plane coordinates in frames A / B), in frame B: the
+  // right singular vector of the smallest singular value of the 4x4 DLT matrix (the reference asks TooN's
+  // LAPACK-backed SVD<4>; here a one-sided Jacobi SVD, which needs no library)
+  static TooN::Vector<3> Triangulate(const TooN::SE3<>& se3AfromB, const TooN::Vector<2>& v2A, const TooN::Vector<2>& v2B) {
+    double P[3][4];
+    for (int r = 0; r < 3; r++) {
+      for (int c = 0; c < 3; c++) P[r][c] = se3AfromB.get_rotation().get_matrix()(r, c);
+      P[r][3] = se3AfromB.get_translation()[r];
+    }
+    double A[4][4] = {{-1.0, 0.0, v2B[0], 0.0}, {0.0, -1.0, v2B[1], 0.0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+    for (int c = 0; c < 4; c++) { A[2][c] = v2A[0] * P[2][c] - P[0][c]; A[3][c] = v2A[1] * P[2][c] - P[1][c]; }
+    // Hestenes: rotate pairs of columns of A until they are orthogonal, accumulating the rotations in V
+    double V[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
+    for (int sweep = 0; sweep < 60; sweep++) {
+      double off = 0.0;
+      for (int p = 0; p < 3; p++)
+        for (int q = p + 1; q < 4; q++) {
+          double a = 0, b = 0, g = 0;
+          for (int k = 0; k < 4; k++) { a += A[k][p] * A[k][p]; b += A[k][q] * A[k][q]; g += A[k][p] * A[k][q]; }
+          if (g == 0.0) continue;
+          off = std::max(off, std::fabs(g) / std::sqrt(a * b));
+          const double zeta = (b - a) / (2.0 * g);
+          const double t = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+          const double cs = 1.0 / std::sqrt(1.0 + t * t), sn = cs * t;
+          for (int k = 0; k < 4; k++) {
+            const double ap = A[k][p], aq = A[k][q];
+            A[k][p] = cs * ap - sn * aq; A[k][q] = sn * ap + cs * aq;
+            const double vp = V[k][p], vq = V[k][q];
+            V[k][p] = cs * vp - sn * vq; V[k][q] = sn * vp + cs * vq;
+          }
+        }
+      if (off < 1e-15) break;
+    }
+    int smallest = 0;
+    double best = -1.0;
+    for (int c = 0; c < 4; c++) {
+      double n2 = 0;
+      for (int k = 0; k < 4; k++) n2 += A[k][c] * A[k][c];
+      if (best < 0 || n2 < best) { best = n2; smallest = c; }
+    }
+    double w = V[3][smallest];
+    if (w == 0.0) w = 0.00001;
+    return TooN::makeVector(V[0][smallest] / w, V[1][smallest] / w, V[2][smallest] / w);
+  }
+
+  // The candidate loop of MapMaker::AddSomeMapPoints (MapMaker.cc:496-527) with MapMaker::AddPointEpipolar
+  // (MapMaker.cc:529-688) for every candidate of kSrc's level: the epipolar search up to the sub-pixel position
+  // in kTarget runs on the device for all candidates at once (ptam_tracker_epipolar_search); triangulation,
+  // MapPoint construction and the two measurements follow here as in the reference (MapMaker.cc:648-687).
+  // Both keyframes must have been made (MakeKeyFrame_Lite; kSrc also MakeKeyFrame_Rest for its candidates).
+  // Returns the number of points added to the map; they are also appended to mvpNewQueue (mqNewQueue).
+  int AddPointsEpipolar(KeyFrame& kSrc, KeyFrame& kTarget, int nLevel) {
+    const std::vector<Candidate>& cands = kSrc.aLevels[nLevel].vCandidates;
+    const int n = (int)cands.size();
+    if (n == 0) return 0;
+    ptam_tracker* t = Assoc(kSrc.aLevels[0].im.size());
+    auto stored = mStoreId.find(&kSrc);
+    if (stored == mStoreId.end()) {
+      const int id = ptam_tracker_add_keyframe(t, kSrc.aLevels[0].im.data(), kSrc.aLevels[0].im.row_stride());
+      if (id < 0) throw std::runtime_error(ptam_tracker_last_error(t));
+      stored = mStoreId.emplace(&kSrc, id).first;
+    }
+    const uint8_t* target_image[1] = {kTarget.aLevels[0].im.data()};
+    if (ptam_tracker_make_keyframes(t, target_image, kTarget.aLevels[0].im.row_stride()) != PTAM_OK)
+      throw std::runtime_error(ptam_tracker_last_error(t));
+    std::vector<int32_t> xy(2 * (size_t)n), found(n), best(n);
+    std::vector<double> sub(2 * (size_t)n);
+    for (int i = 0; i < n; i++) { xy[2 * i] = cands[i].irLevelPos.x; xy[2 * i + 1] = cands[i].irLevelPos.y; }
+    double src12[12], tgt12[12];
+    se3_to_array(kSrc.se3CfromW, src12);
+    se3_to_array(kTarget.se3CfromW, tgt12);
+    if (ptam_tracker_epipolar_search(t, 0, nLevel, stored->second, src12, kSrc.dSceneDepthMean, kSrc.dSceneDepthSigma, tgt12,
+                                     mdWiggleScale, n, xy.data(), found.data(), best.data(), sub.data()) != PTAM_OK)
+      throw std::runtime_error(ptam_tracker_last_error(t));
+    const int nLevelScale = Level::LevelScale(nLevel);
+    const TooN::SE3<> se3SrcfromTarget = kSrc.se3CfromW * kTarget.se3CfromW.inverse();
+    const TooN::SE3<> se3WfromTarget = kTarget.se3CfromW.inverse();
+    auto unit_ray = [&](const TooN::Vector<2>& im) {
+      const TooN::Vector<2> p = mCamera.UnProject(im);
+      const double nrm = std::sqrt(p[0] * p[0] + p[1] * p[1] + 1.0);
+      return TooN::makeVector(p[0] / nrm, p[1] / nrm, 1.0 / nrm);
+    };
+    int added = 0;
+    for (int i = 0; i < n; i++) {
+      if (!found[i]) continue;
+      const TooN::Vector<2> v2RootPos = Level::LevelZeroPos(cands[i].irLevelPos, nLevel);
+      const TooN::Vector<2> v2SubPosTarget = TooN::makeVector(sub[2 * i], sub[2 * i + 1]);
+      mOwnedPoints.emplace_back(new MapPoint);  // the reference's Map owns its points; here their maker does
+      MapPoint* pNew = mOwnedPoints.back().get();
+      pNew->v3WorldPos = se3WfromTarget * Triangulate(se3SrcfromTarget, mCamera.UnProject(v2RootPos), mCamera.UnProject(v2SubPosTarget));
+      pNew->pPatchSourceKF = &kSrc;
+      pNew->nSourceLevel = nLevel;
+      pNew->v3Normal_NC = TooN::makeVector(0.0, 0.0, -1.0);
+      pNew->irCenter = cands[i].irLevelPos;
+      pNew->v3Center_NC = unit_ray(v2RootPos);
+      pNew->v3OneRightFromCenter_NC = unit_ray(v2RootPos + TooN::makeVector((double)nLevelScale, 0.0));
+      pNew->v3OneDownFromCenter_NC = unit_ray(v2RootPos + TooN::makeVector(0.0, (double)nLevelScale));
+      pNew->RefreshPixelVectors();
+      mMap.vpPoints.push_back(pNew);
+      mMap.nRevision++;
+      mvpNewQueue.push_back(pNew);
+      Measurement m;
+      m.Source = Measurement::SRC_ROOT;
+      m.v2RootPos = v2RootPos;
+      m.nLevel = nLevel;
+      m.bSubPix = true;
+      kSrc.mMeasurements[pNew] = m;
+      m.Source = Measurement::SRC_EPIPOLAR;
+      m.v2RootPos = v2SubPosTarget;
+      kTarget.mMeasurements[pNew] = m;
+      MapMakerData& md = MMData(pNew);
+      md.sMeasurementKFs.insert(&kSrc);
+      md.sMeasurementKFs.insert(&kTarget);
+      added++;
+    }
+    return added;
   }
 
   // bookkeeping of a point, created on first use (the reference allocates pMMData when the point is made)
@@ -162,8 +287,24 @@ class MapMaker {
   bool mbBundleRunning = false, mbBundleRunningIsRecent = false;
   bool mbBundleAbortRequested = false, mbResetRequested = false;
   std::vector<std::pair<KeyFrame*, MapPoint*> > mvFailureQueue;
+  std::vector<MapPoint*> mvpNewQueue;  // mqNewQueue (MapMaker.h:130): points waiting to be re-found in older keyframes
+  double mdWiggleScale = 0.1;          // MapMaker.WiggleScale (MapMaker.cc:225), the stereo baseline in map units
 
  private:
+  // the map maker's own data-association handle (the reference gives it its own PatchFinder, MapMaker.cc:977),
+  // created with this camera on first use
+  ptam_tracker* Assoc(CVD::ImageRef size) {
+    if (!mpAssoc) {
+      double p[5];
+      for (int i = 0; i < 5; i++) p[i] = mCamera.GetParams()[i];
+      mpAssoc = ptam_tracker_create(mnDevice, p, size.x, size.y, 1, nullptr);
+      if (!mpAssoc) throw std::runtime_error(std::string("ptam_tracker_create: ") + ptam_global_last_error());
+    }
+    return mpAssoc;
+  }
+  ptam_tracker* mpAssoc = nullptr;
+  std::map<KeyFrame*, int> mStoreId;  // keyframes already resident in the handle's keyframe store
+  std::vector<std::unique_ptr<MapPoint> > mOwnedPoints;
   Map& mMap;
   ATANCamera mCamera;
   int mnDevice;

@@ -30,10 +30,59 @@ static void wr(const std::string& dir, const char* name, const std::vector<T>& v
   f.write(reinterpret_cast<const char*>(v.data()), v.size() * sizeof(T));
 }
 
+// MapMaker::AddPointsEpipolar between two keyframes made from raw images: the new map points (world position,
+// pixel-right / pixel-down vectors) and their two measurements, level by level.
+static int run_epipolar(const std::string& dir) {
+  auto dims = rd<int32_t>(dir, "epi_dims.i32");  // W, H
+  const int W = dims[0], H = dims[1];
+  auto src_im = rd<uint8_t>(dir, "epi_src.u8");
+  auto tgt_im = rd<uint8_t>(dir, "epi_tgt.u8");
+  auto src_pose = rd<double>(dir, "epi_src_pose.f64");
+  auto tgt_pose = rd<double>(dir, "epi_tgt_pose.f64");
+  auto depth = rd<double>(dir, "epi_depth.f64");  // source scene depth mean, sigma, wiggle scale
+  ATANCamera cam("Camera", makeVector(1.0803, 1.43987, 0.519983, 0.548655, 0.244943), CVD::ImageRef(W, H));
+  KeyFrame kSrc, kTgt;
+  CVD::BasicImage<CVD::byte> is(src_im.data(), CVD::ImageRef(W, H)), it(tgt_im.data(), CVD::ImageRef(W, H));
+  kSrc.MakeKeyFrame_Lite(is);
+  kSrc.MakeKeyFrame_Rest();     // candidates (KeyFrame.cc:61-82)
+  kTgt.MakeKeyFrame_Lite(it);
+  kSrc.se3CfromW = se3_from_array(src_pose.data());
+  kTgt.se3CfromW = se3_from_array(tgt_pose.data());
+  kSrc.dSceneDepthMean = depth[0]; kSrc.dSceneDepthSigma = depth[1];
+  Map map;
+  map.vpKeyFrames = {&kSrc, &kTgt};
+  MapMaker mm(map, cam);
+  mm.mdWiggleScale = depth[2];
+  std::vector<int32_t> counts, ncand;
+  for (int l = 0; l < LEVELS; l++) {
+    ncand.push_back((int32_t)kSrc.aLevels[l].vCandidates.size());
+    counts.push_back(mm.AddPointsEpipolar(kSrc, kTgt, l));
+  }
+  std::vector<double> pts, meas;
+  std::vector<int32_t> levels;
+  for (MapPoint* p : map.vpPoints) {
+    for (int k = 0; k < 3; k++) pts.push_back(p->v3WorldPos[k]);
+    for (int k = 0; k < 3; k++) pts.push_back(p->v3PixelRight_W[k]);
+    for (int k = 0; k < 3; k++) pts.push_back(p->v3PixelDown_W[k]);
+    const Measurement& ms = kSrc.mMeasurements[p];
+    const Measurement& mt = kTgt.mMeasurements[p];
+    meas.insert(meas.end(), {ms.v2RootPos[0], ms.v2RootPos[1], mt.v2RootPos[0], mt.v2RootPos[1]});
+    levels.push_back(p->nSourceLevel);
+    if (ms.Source != Measurement::SRC_ROOT || mt.Source != Measurement::SRC_EPIPOLAR || p->pPatchSourceKF != &kSrc ||
+        mm.MMData(p).GoodMeasCount() != 2) { std::cerr << "bad bookkeeping of a new point\n"; return 1; }
+  }
+  if (mm.mvpNewQueue.size() != map.vpPoints.size()) { std::cerr << "new-point queue out of step\n"; return 1; }
+  wr(dir, "epi_out_counts.i32", counts); wr(dir, "epi_out_ncand.i32", ncand); wr(dir, "epi_out_points.f64", pts);
+  wr(dir, "epi_out_meas.f64", meas); wr(dir, "epi_out_levels.i32", levels);
+  std::printf("epipolar: %zu new points from %d + %d + %d + %d candidates\n", map.vpPoints.size(), ncand[0], ncand[1], ncand[2], ncand[3]);
+  return 0;
+}
+
 int main(int argc, char** argv) {
-  if (argc < 2) { std::cerr << "usage: mapmaker_check <dir>\n"; return 2; }
+  if (argc < 2) { std::cerr << "usage: mapmaker_check <dir> [ba|epi]\n"; return 2; }
   const std::string dir = argv[1];
   try {
+    if (argc > 2 && std::string(argv[2]) == "epi") return run_epipolar(dir);
     auto cams = rd<double>(dir, "mm_cams.f64");
     auto fixed = rd<int32_t>(dir, "mm_fixed.i32");
     auto pts = rd<double>(dir, "mm_pts.f64");

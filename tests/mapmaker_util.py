@@ -135,3 +135,59 @@ def compare(got, exp, tol):
     assert np.array_equal(got["queue"], exp["queue"]), "failure queue (order included)"
     assert np.array_equal(got["never"], exp["never"])
     assert np.array_equal(got["flags"], exp["flags"])
+
+
+# ---- MapMaker::AddPointsEpipolar (host mirror) against the reference's own AddPointEpipolar ---------------------
+def write_epipolar_case(d, W, H, frames, poses, i_src, i_tgt, depth=(1.0, 0.3), wiggle=0.1):
+    np.array([W, H], np.int32).tofile(d / "epi_dims.i32")
+    np.ascontiguousarray(frames[i_src], np.uint8).tofile(d / "epi_src.u8")
+    np.ascontiguousarray(frames[i_tgt], np.uint8).tofile(d / "epi_tgt.u8")
+    np.ascontiguousarray(poses[i_src], np.float64).tofile(d / "epi_src_pose.f64")
+    np.ascontiguousarray(poses[i_tgt], np.float64).tofile(d / "epi_tgt_pose.f64")
+    np.array([depth[0], depth[1], wiggle], np.float64).tofile(d / "epi_depth.f64")
+
+
+def read_epipolar_out(d):
+    return dict(counts=np.fromfile(d / "epi_out_counts.i32", np.int32), ncand=np.fromfile(d / "epi_out_ncand.i32", np.int32),
+                points=np.fromfile(d / "epi_out_points.f64").reshape(-1, 9), meas=np.fromfile(d / "epi_out_meas.f64").reshape(-1, 4),
+                levels=np.fromfile(d / "epi_out_levels.i32", np.int32))
+
+
+def epipolar_expected(search_lib, W, H, frames, poses, i_src, i_tgt, depth=(1.0, 0.3), wiggle=0.1, ref=None):
+    """Candidates, accepted set and sub-pixel positions through `search_lib`'s C ABI; when `ref` (oracle/_ref) is
+    given, also the world positions / pixel vectors the reference's own Triangulate + RefreshPixelVectors made."""
+    import ctypes as C
+    from ptam_cg_b200.capi import Tracker
+    out = dict(counts=[], ncand=[], meas=[], levels=[], points=[])
+    t = Tracker(search_lib, W, H, 1)
+    kf = t.add_keyframe(frames[i_src])
+    t.make_keyframes([frames[i_src]])
+    cands = [r[1] for r in t.keyframe_rest(0, 70.0)]
+    t.make_keyframes([frames[i_tgt]])
+    if ref is not None:
+        tr = Tracker(ref, W, H, 1)
+        kfr = tr.add_keyframe(frames[i_src])
+        tr.make_keyframes([frames[i_tgt]])
+        last = ref.cdll.ref_tracker_epipolar_last_points
+        last.restype = C.c_int
+    for l in range(4):
+        found, best, sub = t.epipolar_search(0, l, kf, poses[i_src], depth[0], depth[1], poses[i_tgt], wiggle, cands[l])
+        out["ncand"].append(len(cands[l]))
+        out["counts"].append(int(found.sum()))
+        scale = 1 << l
+        for i in np.flatnonzero(found):
+            root = (np.asarray(cands[l][i], np.float64) + 0.5) * scale - 0.5   # Level::LevelZeroPos
+            out["meas"].append([root[0], root[1], sub[i][0], sub[i][1]])
+            out["levels"].append(l)
+        if ref is not None:
+            fr, _, subr = tr.epipolar_search(0, l, kfr, poses[i_src], depth[0], depth[1], poses[i_tgt], wiggle, cands[l])
+            assert np.array_equal(fr, found)
+            n = last(None, 0)
+            buf = np.zeros((max(n, 1), 9))
+            last(buf.ctypes.data_as(C.POINTER(C.c_double)), n)
+            assert n == int(found.sum())
+            out["points"].extend(buf[:n].tolist())
+    out = {k: np.array(v) for k, v in out.items()}
+    out["meas"] = out["meas"].reshape(-1, 4)
+    out["points"] = out["points"].reshape(-1, 9)
+    return out

@@ -32,6 +32,7 @@
 #define ptam_tracker_get_state orc_tracker_get_state
 #define ptam_tracker_get_points orc_tracker_get_points
 #define ptam_tracker_track_frames orc_tracker_track_frames
+#define ptam_tracker_epipolar_search orc_tracker_epipolar_search
 #define ptam_global_last_error orc_test_global_last_error
 #ifdef __cplusplus
 extern "C"

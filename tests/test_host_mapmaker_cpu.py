@@ -48,3 +48,42 @@ def test_recent_adjustment_needs_eight_keyframes(orc_binary, tmp_path):
     import numpy as np
     assert np.array_equal(got["points"], g["points"]) and np.array_equal(got["cams"], g["cam_se3"])  # MapMaker.cc:789-792
     assert list(got["flags"][:2]) == [1, 1]
+
+
+@pytest.fixture(scope="module")
+def orc_libm_binary(tmp_path_factory):
+    """mapmaker_check against liboracle_libm.so (platform atan: the variant pinned bit for bit against oracle/_ref)."""
+    out = tmp_path_factory.mktemp("mm") / "mapmaker_check_orc_libm"
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-I", str(HOST), "-include", str(ROOT / "tests" / "orc_alias.h"),
+           str(HOST / "mapmaker_check.cc"), "-o", str(out), "-L", str(ROOT / "oracle"), "-loracle_libm",
+           "-Wl,-rpath," + str(ROOT / "oracle")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return out
+
+
+@pytest.mark.parametrize("pair", [(0, 30), (10, 25)], ids=lambda p: f"src{p[0]}-tgt{p[1]}")
+def test_add_points_epipolar_matches_the_reference(orc_libm_binary, tmp_path, pair):
+    """MapMaker::AddPointsEpipolar of the host mirror (device search + host triangulation and MapPoint construction)
+    against the reference's own MapMaker::AddPointEpipolar compiled in place (oracle/_ref): same accepted
+    candidates, same measurements, and the triangulated world position / pixel vectors of every new point
+    (the reference asks an SVD<4> of the DLT matrix; the mirror runs a one-sided Jacobi SVD)."""
+    import numpy as np
+    from ptam_cg_b200 import synth
+    from oracle.binding import ref_lib
+    ref = ref_lib()
+    if ref is None or not hasattr(ref.cdll, "ref_tracker_epipolar_last_points"):
+        pytest.skip("oracle/_ref not built")
+    W, H = 320, 240
+    frames, poses = synth.render_sequence(W, H, 40)
+    mu.write_epipolar_case(tmp_path, W, H, frames, poses, *pair)
+    r = subprocess.run([str(orc_libm_binary), str(tmp_path), "epi"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = mu.read_epipolar_out(tmp_path)
+    exp = mu.epipolar_expected(oracle_lib(libm_atan=True), W, H, frames, poses, *pair, ref=ref)
+    assert np.array_equal(got["ncand"], exp["ncand"]) and np.array_equal(got["counts"], exp["counts"])
+    assert got["counts"].sum() > 100
+    assert np.array_equal(got["levels"], exp["levels"])
+    assert np.array_equal(got["meas"], exp["meas"])                      # root position and sub-pixel target position
+    np.testing.assert_allclose(got["points"][:, :3], exp["points"][:, :3], rtol=0, atol=1e-9)   # v3WorldPos
+    np.testing.assert_allclose(got["points"][:, 3:], exp["points"][:, 3:], rtol=0, atol=1e-10)  # v3PixelRight_W / Down_W

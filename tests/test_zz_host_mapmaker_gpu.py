@@ -29,3 +29,34 @@ def test_mapmaker_mirror_on_the_device(product, tmp_path, mode):
     exp = mu.expected(product, g, mode, 20)
     assert exp["accepted"] > 0
     mu.compare(got, exp, tol=1e-7)
+
+
+def test_add_points_epipolar_on_the_device(product, oracle, tmp_path):
+    """MapMaker::AddPointsEpipolar of the host mirror with the CUDA library behind it, against the same source
+    compiled over the CPU oracle's ABI (which tests/test_host_mapmaker_cpu.py holds against the reference's own
+    MapMaker::AddPointEpipolar): same accepted candidates, measurements to 1e-9 px, new points to 1e-6."""
+    import numpy as np
+    from ptam_cg_b200 import synth
+    r = subprocess.run(["make", "-C", str(HOST)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    orc_bin = tmp_path / "mapmaker_check_orc"
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-I", str(HOST), "-include", str(ROOT / "tests" / "orc_alias.h"),
+           str(HOST / "mapmaker_check.cc"), "-o", str(orc_bin), "-L", str(ROOT / "oracle"), "-loracle", "-Wl,-rpath," + str(ROOT / "oracle")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    W, H = 320, 240
+    frames, poses = synth.render_sequence(W, H, 40)
+    outs = []
+    for binary, sub in ((HOST / "mapmaker_check", "gpu"), (orc_bin, "cpu")):
+        d = tmp_path / sub
+        d.mkdir()
+        mu.write_epipolar_case(d, W, H, frames, poses, 0, 30)
+        r = subprocess.run([str(binary), str(d), "epi"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.append(mu.read_epipolar_out(d))
+    g, c = outs
+    assert np.array_equal(g["ncand"], c["ncand"]) and np.array_equal(g["counts"], c["counts"]) and g["counts"].sum() > 100
+    assert np.array_equal(g["levels"], c["levels"])
+    assert np.array_equal(g["meas"][:, :2], c["meas"][:, :2])
+    np.testing.assert_allclose(g["meas"][:, 2:], c["meas"][:, 2:], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(g["points"], c["points"], rtol=0, atol=1e-6)
