@@ -159,6 +159,44 @@ class MapMaker {
     return added;
   }
 
+  // MapMaker.cc:1026-1040 with ReFind_Common (MapMaker.cc:943-1018) for every map point: the data association of
+  // a keyframe the tracker handed over.  Projection, warp / template, the radius-4 coarse search and the
+  // sub-pixel refinement of all points run on the device in one call (ptam_tracker_refind_in_keyframes); the
+  // reference's bookkeeping follows here: points already measured in k, or given up on, are left alone; a point
+  // that was not found (for whatever reason: behind the camera, off the image, bad template, no match) is never
+  // retried in k; a found one gets its Measurement (SRC_REFIND) in k.  Returns the number of new measurements.
+  int ReFindInSingleKeyFrame(KeyFrame& k) {
+    const size_t n = mMap.vpPoints.size();
+    if (n == 0) return 0;
+    ptam_tracker* t = Assoc(k.aLevels[0].im.size());
+    SyncAssocMap(t);
+    const uint8_t* image[1] = {k.aLevels[0].im.data()};
+    double se3[12];
+    se3_to_array(k.se3CfromW, se3);
+    if (ptam_tracker_refind_in_keyframes(t, image, k.aLevels[0].im.row_stride(), se3) != PTAM_OK)
+      throw std::runtime_error(ptam_tracker_last_error(t));
+    std::vector<int32_t> flags(n), level(n);
+    std::vector<double> found(2 * n);
+    if (ptam_tracker_get_points(t, 0, flags.data(), level.data(), found.data(), nullptr, nullptr, nullptr) < 0)
+      throw std::runtime_error(ptam_tracker_last_error(t));
+    int nFoundNow = 0;
+    for (size_t i = 0; i < n; i++) {
+      MapPoint* p = mMap.vpPoints[i];
+      MapMakerData& md = MMData(p);
+      if (md.sMeasurementKFs.count(&k) || md.sNeverRetryKFs.count(&k)) continue;
+      if (!(flags[i] & PTAM_PT_FOUND)) { md.sNeverRetryKFs.insert(&k); continue; }
+      Measurement m;
+      m.nLevel = level[i];
+      m.Source = Measurement::SRC_REFIND;
+      m.bSubPix = level[i] > 0;
+      m.v2RootPos = TooN::makeVector(found[2 * i], found[2 * i + 1]);
+      k.mMeasurements[p] = m;
+      md.sMeasurementKFs.insert(&k);
+      nFoundNow++;
+    }
+    return nFoundNow;
+  }
+
   // bookkeeping of a point, created on first use (the reference allocates pMMData when the point is made)
   MapMakerData& MMData(MapPoint* p) { return mMMData[p]; }
 
@@ -302,7 +340,32 @@ class MapMaker {
     }
     return mpAssoc;
   }
+  // the whole map as the handle's point set (source keyframes go to its keyframe store on first sight)
+  void SyncAssocMap(ptam_tracker* t) {
+    if (mbAssocMapValid && mnAssocRevision == mMap.nRevision && mnAssocPoints == mMap.vpPoints.size()) return;
+    const size_t n = mMap.vpPoints.size();
+    std::vector<double> world(3 * n), right(3 * n), down(3 * n);
+    std::vector<int32_t> kf(n), lvl(n), ctr(2 * n);
+    for (size_t i = 0; i < n; i++) {
+      const MapPoint& p = *mMap.vpPoints[i];
+      auto it = mStoreId.find(p.pPatchSourceKF);
+      if (it == mStoreId.end()) {
+        Level& L0 = p.pPatchSourceKF->aLevels[0];
+        const int id = ptam_tracker_add_keyframe(t, L0.im.data(), L0.im.row_stride());
+        if (id < 0) throw std::runtime_error(ptam_tracker_last_error(t));
+        it = mStoreId.emplace(p.pPatchSourceKF, id).first;
+      }
+      for (int c = 0; c < 3; c++) { world[3 * i + c] = p.v3WorldPos[c]; right[3 * i + c] = p.v3PixelRight_W[c]; down[3 * i + c] = p.v3PixelDown_W[c]; }
+      kf[i] = it->second; lvl[i] = p.nSourceLevel; ctr[2 * i] = p.irCenter.x; ctr[2 * i + 1] = p.irCenter.y;
+    }
+    if (ptam_tracker_set_map(t, 0, (int)n, world.data(), right.data(), down.data(), kf.data(), lvl.data(), ctr.data()) != PTAM_OK)
+      throw std::runtime_error(ptam_tracker_last_error(t));
+    mnAssocRevision = mMap.nRevision; mnAssocPoints = n; mbAssocMapValid = true;
+  }
   ptam_tracker* mpAssoc = nullptr;
+  unsigned mnAssocRevision = 0;
+  size_t mnAssocPoints = 0;
+  bool mbAssocMapValid = false;
   std::map<KeyFrame*, int> mStoreId;  // keyframes already resident in the handle's keyframe store
   std::vector<std::unique_ptr<MapPoint> > mOwnedPoints;
   Map& mMap;

@@ -78,11 +78,78 @@ static int run_epipolar(const std::string& dir) {
   return 0;
 }
 
+// MapMaker::ReFindInSingleKeyFrame: a map (source keyframes, points) and a new keyframe; some points already have
+// a measurement in it or are on its never-retry list.  Output per point: measurement (level, sub-pixel flag,
+// root position) and never-retry flag.
+static int run_refind(const std::string& dir) {
+  auto dims = rd<int32_t>(dir, "trk_dims.i32");  // W, H, n_kf, n_pts
+  const int W = dims[0], H = dims[1], nkf = dims[2], npts = dims[3];
+  auto kfim = rd<uint8_t>(dir, "trk_kf.u8");
+  auto world = rd<double>(dir, "trk_world.f64");
+  auto right = rd<double>(dir, "trk_right.f64");
+  auto down = rd<double>(dir, "trk_down.f64");
+  auto skf = rd<int32_t>(dir, "trk_srckf.i32");
+  auto slv = rd<int32_t>(dir, "trk_srclevel.i32");
+  auto ctr = rd<int32_t>(dir, "trk_center.i32");
+  auto newim = rd<uint8_t>(dir, "rf_image.u8");
+  auto newpose = rd<double>(dir, "rf_pose.f64");
+  auto pre = rd<int32_t>(dir, "rf_pre.i32");  // per point: 0 nothing, 1 already measured in k, 2 never retry in k
+  ATANCamera cam("Camera", makeVector(1.0803, 1.43987, 0.519983, 0.548655, 0.244943), CVD::ImageRef(W, H));
+  Map map;
+  std::vector<KeyFrame> kfs(nkf);
+  for (int k = 0; k < nkf; k++) {
+    CVD::BasicImage<CVD::byte> im(kfim.data() + (size_t)k * W * H, CVD::ImageRef(W, H));
+    kfs[k].MakeKeyFrame_Lite(im);
+    map.vpKeyFrames.push_back(&kfs[k]);
+  }
+  std::vector<MapPoint> points(npts);
+  for (int i = 0; i < npts; i++) {
+    MapPoint& p = points[i];
+    p.v3WorldPos = makeVector(world[3 * i], world[3 * i + 1], world[3 * i + 2]);
+    p.v3PixelRight_W = makeVector(right[3 * i], right[3 * i + 1], right[3 * i + 2]);
+    p.v3PixelDown_W = makeVector(down[3 * i], down[3 * i + 1], down[3 * i + 2]);
+    p.pPatchSourceKF = &kfs[skf[i]];
+    p.nSourceLevel = slv[i];
+    p.irCenter = CVD::ImageRef(ctr[2 * i], ctr[2 * i + 1]);
+    map.vpPoints.push_back(&p);
+  }
+  map.bGood = true; map.nRevision++;
+  KeyFrame k;
+  CVD::BasicImage<CVD::byte> im(newim.data(), CVD::ImageRef(W, H));
+  k.MakeKeyFrame_Lite(im);
+  k.se3CfromW = se3_from_array(newpose.data());
+  MapMaker mm(map, cam);
+  for (int i = 0; i < npts; i++) {
+    if (pre[i] == 1) {
+      Measurement m; m.nLevel = 0; m.bSubPix = false; m.v2RootPos = makeVector(-1.0, -1.0); m.Source = Measurement::SRC_TRACKER;
+      k.mMeasurements[&points[i]] = m;
+      mm.MMData(&points[i]).sMeasurementKFs.insert(&k);
+    } else if (pre[i] == 2) {
+      mm.MMData(&points[i]).sNeverRetryKFs.insert(&k);
+    }
+  }
+  const int nFound = mm.ReFindInSingleKeyFrame(k);
+  const int nAgain = mm.ReFindInSingleKeyFrame(k);  // everything is now measured or given up on: nothing changes
+  std::vector<int32_t> out;   // per point: has measurement, source, level, subpix, never retry
+  std::vector<double> pos;
+  for (int i = 0; i < npts; i++) {
+    auto it = k.mMeasurements.find(&points[i]);
+    const bool has = it != k.mMeasurements.end();
+    out.insert(out.end(), {has ? 1 : 0, has ? (int32_t)it->second.Source : -1, has ? it->second.nLevel : -1, has && it->second.bSubPix ? 1 : 0,
+                           (int32_t)mm.MMData(&points[i]).sNeverRetryKFs.count(&k)});
+    pos.push_back(has ? it->second.v2RootPos[0] : 0.0); pos.push_back(has ? it->second.v2RootPos[1] : 0.0);
+  }
+  wr(dir, "rf_out_points.i32", out); wr(dir, "rf_out_pos.f64", pos); wr(dir, "rf_out_counts.i32", std::vector<int32_t>{nFound, nAgain});
+  std::printf("refind: %d new measurements among %d points (second pass %d)\n", nFound, npts, nAgain);
+  return 0;
+}
+
 int main(int argc, char** argv) {
-  if (argc < 2) { std::cerr << "usage: mapmaker_check <dir> [ba|epi]\n"; return 2; }
+  if (argc < 2) { std::cerr << "usage: mapmaker_check <dir> [ba|epi|refind]\n"; return 2; }
   const std::string dir = argv[1];
   try {
     if (argc > 2 && std::string(argv[2]) == "epi") return run_epipolar(dir);
+    if (argc > 2 && std::string(argv[2]) == "refind") return run_refind(dir);
     auto cams = rd<double>(dir, "mm_cams.f64");
     auto fixed = rd<int32_t>(dir, "mm_fixed.i32");
     auto pts = rd<double>(dir, "mm_pts.f64");

@@ -33,6 +33,7 @@
 #define ptam_tracker_get_points orc_tracker_get_points
 #define ptam_tracker_track_frames orc_tracker_track_frames
 #define ptam_tracker_epipolar_search orc_tracker_epipolar_search
+#define ptam_tracker_refind_in_keyframes orc_tracker_refind_in_keyframes
 #define ptam_global_last_error orc_test_global_last_error
 #ifdef __cplusplus
 extern "C"

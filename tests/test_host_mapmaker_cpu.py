@@ -87,3 +87,64 @@ def test_add_points_epipolar_matches_the_reference(orc_libm_binary, tmp_path, pa
     assert np.array_equal(got["meas"], exp["meas"])                      # root position and sub-pixel target position
     np.testing.assert_allclose(got["points"][:, :3], exp["points"][:, :3], rtol=0, atol=1e-9)   # v3WorldPos
     np.testing.assert_allclose(got["points"][:, 3:], exp["points"][:, 3:], rtol=0, atol=1e-10)  # v3PixelRight_W / Down_W
+
+
+def _refind_case(tmp_path, lib):
+    """A 320x240 map from two source keyframes and a third frame to re-find the points in; a few points are
+    marked as already measured / never to be retried in it.  Returns the expected per-point outcome from `lib`'s
+    C ABI + the reference's bookkeeping (MapMaker.cc:943-1018)."""
+    import numpy as np
+    from ptam_cg_b200 import synth
+    from ptam_cg_b200.capi import Tracker, PT_FOUND
+    from oracle.binding import detect_with
+    W, H = 320, 240
+    frames, poses = synth.render_sequence(W, H, 10)
+    cam = synth.AtanCamera(W, H)
+    kfs, m = synth.build_map(frames, poses, detect_with(Tracker, oracle_lib(), W, H), cam, kf_indices=(0, 8), per_level=(150, 80, 40, 20))
+    n = len(m["src_kf"])
+    np.array([W, H, len(kfs), n], np.int32).tofile(tmp_path / "trk_dims.i32")
+    np.ascontiguousarray(np.stack(kfs), np.uint8).tofile(tmp_path / "trk_kf.u8")
+    for name, key, dt in (("trk_world.f64", "world_pos", np.float64), ("trk_right.f64", "pixel_right_w", np.float64),
+                          ("trk_down.f64", "pixel_down_w", np.float64), ("trk_srckf.i32", "src_kf", np.int32),
+                          ("trk_srclevel.i32", "src_level", np.int32), ("trk_center.i32", "ir_center", np.int32)):
+        np.ascontiguousarray(m[key], dt).tofile(tmp_path / name)
+    f = 4
+    np.ascontiguousarray(frames[f], np.uint8).tofile(tmp_path / "rf_image.u8")
+    np.ascontiguousarray(poses[f], np.float64).tofile(tmp_path / "rf_pose.f64")
+    pre = np.zeros(n, np.int32)
+    pre[::7] = 1
+    pre[3::11] = 2
+    pre.tofile(tmp_path / "rf_pre.i32")
+    t = Tracker(lib, W, H, 1)
+    for k in kfs:
+        t.add_keyframe(k)
+    t.set_map(0, m)
+    t.refind_in_keyframes([frames[f]], [poses[f]])
+    pts = t.get_points(0)
+    found = (pts["flags"] & PT_FOUND) != 0
+    exp = np.zeros((n, 5), np.int32)
+    pos = np.zeros((n, 2))
+    for i in range(n):
+        if pre[i] == 1:
+            exp[i] = (1, 0, 0, 0, 0); pos[i] = (-1.0, -1.0)       # the measurement it already had (SRC_TRACKER = 0)
+        elif pre[i] == 2:
+            exp[i] = (0, -1, -1, 0, 1)
+        elif found[i]:
+            exp[i] = (1, 1, pts["level"][i], int(pts["level"][i] > 0), 0)   # SRC_REFIND = 1
+            pos[i] = pts["v2_found"][i]
+        else:
+            exp[i] = (0, -1, -1, 0, 1)
+    return n, exp, pos, int((found & (pre == 0)).sum())
+
+
+def test_refind_in_single_keyframe_bookkeeping(orc_binary, tmp_path):
+    import numpy as np
+    n, exp, pos, n_new = _refind_case(tmp_path, oracle_lib())
+    r = subprocess.run([str(orc_binary), str(tmp_path), "refind"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = np.fromfile(tmp_path / "rf_out_points.i32", np.int32).reshape(n, 5)
+    gpos = np.fromfile(tmp_path / "rf_out_pos.f64").reshape(n, 2)
+    counts = np.fromfile(tmp_path / "rf_out_counts.i32", np.int32)
+    assert list(counts) == [n_new, 0] and n_new > 100
+    assert np.array_equal(got, exp)
+    assert np.array_equal(gpos, pos)

@@ -60,3 +60,21 @@ def test_add_points_epipolar_on_the_device(product, oracle, tmp_path):
     assert np.array_equal(g["meas"][:, :2], c["meas"][:, :2])
     np.testing.assert_allclose(g["meas"][:, 2:], c["meas"][:, 2:], rtol=0, atol=1e-9)
     np.testing.assert_allclose(g["points"], c["points"], rtol=0, atol=1e-6)
+
+
+def test_refind_in_single_keyframe_on_the_device(product, tmp_path):
+    """MapMaker::ReFindInSingleKeyFrame of the host mirror with the CUDA library behind it, against the same C ABI
+    driven from Python + the reference's bookkeeping (the CPU twin is in tests/test_host_mapmaker_cpu.py)."""
+    import numpy as np
+    from test_host_mapmaker_cpu import _refind_case
+    r = subprocess.run(["make", "-C", str(HOST)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    n, exp, pos, n_new = _refind_case(tmp_path, product)
+    r = subprocess.run([str(HOST / "mapmaker_check"), str(tmp_path), "refind"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = np.fromfile(tmp_path / "rf_out_points.i32", np.int32).reshape(n, 5)
+    gpos = np.fromfile(tmp_path / "rf_out_pos.f64").reshape(n, 2)
+    counts = np.fromfile(tmp_path / "rf_out_counts.i32", np.int32)
+    assert list(counts) == [n_new, 0] and n_new > 100
+    assert np.array_equal(got, exp)
+    np.testing.assert_allclose(gpos, pos, rtol=0, atol=1e-9)
