@@ -165,7 +165,36 @@ class MapMaker {
   // reference's bookkeeping follows here: points already measured in k, or given up on, are left alone; a point
   // that was not found (for whatever reason: behind the camera, off the image, bad template, no match) is never
   // retried in k; a found one gets its Measurement (SRC_REFIND) in k.  Returns the number of new measurements.
-  int ReFindInSingleKeyFrame(KeyFrame& k) {
+  int ReFindInSingleKeyFrame(KeyFrame& k) { return ReFindIn(k, nullptr); }
+
+  // MapMaker.cc:1046-1065: the points made since the last call get their chance in every keyframe of the map
+  // (ReFind_Common per keyframe and point; the pairs are independent, so the device call per keyframe covers all
+  // queued points at once).  The reference also stops when a keyframe arrives from the tracker; the mirror has no
+  // keyframe queue, the caller simply calls again.
+  int ReFindNewlyMade() {
+    std::set<MapPoint*> fresh;
+    for (MapPoint* p : mvpNewQueue)
+      if (!p->bBad) fresh.insert(p);
+    mvpNewQueue.clear();
+    int nFound = 0;
+    if (!fresh.empty())
+      for (KeyFrame* kf : mMap.vpKeyFrames) nFound += ReFindIn(*kf, &fresh);
+    return nFound;
+  }
+
+  // MapMaker.cc:1070-1082: measurements bundle adjustment threw out get a second chance
+  int ReFindFromFailureQueue() {
+    std::map<KeyFrame*, std::set<MapPoint*> > by_keyframe;
+    for (auto& kp : mvFailureQueue) by_keyframe[kp.first].insert(kp.second);
+    mvFailureQueue.clear();
+    int nFound = 0;
+    for (auto& ks : by_keyframe) nFound += ReFindIn(*ks.first, &ks.second);
+    return nFound;
+  }
+
+ private:
+  // ReFind_Common for the points of `only` (all map points when null) in keyframe k
+  int ReFindIn(KeyFrame& k, const std::set<MapPoint*>* only) {
     const size_t n = mMap.vpPoints.size();
     if (n == 0) return 0;
     ptam_tracker* t = Assoc(k.aLevels[0].im.size());
@@ -182,6 +211,7 @@ class MapMaker {
     int nFoundNow = 0;
     for (size_t i = 0; i < n; i++) {
       MapPoint* p = mMap.vpPoints[i];
+      if (only && !only->count(p)) continue;
       MapMakerData& md = MMData(p);
       if (md.sMeasurementKFs.count(&k) || md.sNeverRetryKFs.count(&k)) continue;
       if (!(flags[i] & PTAM_PT_FOUND)) { md.sNeverRetryKFs.insert(&k); continue; }
@@ -196,6 +226,8 @@ class MapMaker {
     }
     return nFoundNow;
   }
+
+ public:
 
   // bookkeeping of a point, created on first use (the reference allocates pMMData when the point is made)
   MapMakerData& MMData(MapPoint* p) { return mMMData[p]; }

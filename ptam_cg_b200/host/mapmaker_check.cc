@@ -72,6 +72,32 @@ static int run_epipolar(const std::string& dir) {
         mm.MMData(p).GoodMeasCount() != 2) { std::cerr << "bad bookkeeping of a new point\n"; return 1; }
   }
   if (mm.mvpNewQueue.size() != map.vpPoints.size()) { std::cerr << "new-point queue out of step\n"; return 1; }
+  // a third keyframe joins the map: MapMaker::ReFindNewlyMade looks for the new points in every keyframe (the two
+  // they were made from already measure them)
+  {
+    std::ifstream third(dir + "/epi_third.u8", std::ios::binary);
+    if (third) {
+      auto im3 = rd<uint8_t>(dir, "epi_third.u8");
+      auto pose3 = rd<double>(dir, "epi_third_pose.f64");
+      static KeyFrame k3;
+      CVD::BasicImage<CVD::byte> i3(im3.data(), CVD::ImageRef(W, H));
+      k3.MakeKeyFrame_Lite(i3);
+      k3.se3CfromW = se3_from_array(pose3.data());
+      map.vpKeyFrames.push_back(&k3);
+      const int nRefound = mm.ReFindNewlyMade();
+      std::vector<int32_t> r3 = {nRefound, (int32_t)mm.mvpNewQueue.size()};
+      std::vector<double> p3;
+      for (MapPoint* p : map.vpPoints) {
+        auto it = k3.mMeasurements.find(p);
+        const bool has = it != k3.mMeasurements.end();
+        r3.push_back(has ? 1 : 0); r3.push_back(has ? it->second.nLevel : -1);
+        r3.push_back((int32_t)mm.MMData(p).sNeverRetryKFs.count(&k3)); r3.push_back(mm.MMData(p).GoodMeasCount());
+        p3.push_back(has ? it->second.v2RootPos[0] : 0.0); p3.push_back(has ? it->second.v2RootPos[1] : 0.0);
+      }
+      wr(dir, "epi_out_third.i32", r3); wr(dir, "epi_out_third_pos.f64", p3);
+      std::printf("epipolar: %d of the new points re-found in the third keyframe\n", nRefound);
+    }
+  }
   wr(dir, "epi_out_counts.i32", counts); wr(dir, "epi_out_ncand.i32", ncand); wr(dir, "epi_out_points.f64", pts);
   wr(dir, "epi_out_meas.f64", meas); wr(dir, "epi_out_levels.i32", levels);
   std::printf("epipolar: %zu new points from %d + %d + %d + %d candidates\n", map.vpPoints.size(), ncand[0], ncand[1], ncand[2], ncand[3]);
@@ -130,6 +156,25 @@ static int run_refind(const std::string& dir) {
   }
   const int nFound = mm.ReFindInSingleKeyFrame(k);
   const int nAgain = mm.ReFindInSingleKeyFrame(k);  // everything is now measured or given up on: nothing changes
+  // what MapMaker::BundleAdjust does to an outlier measurement that came from the tracker (MapMaker.cc:923-929),
+  // for every fifth re-found point; MapMaker::ReFindFromFailureQueue must bring exactly those back, unchanged
+  std::map<MapPoint*, Measurement> before;
+  for (int i = 0; i < npts; i += 5) {
+    auto it = k.mMeasurements.find(&points[i]);
+    if (it == k.mMeasurements.end() || it->second.Source != Measurement::SRC_REFIND) continue;
+    before[&points[i]] = it->second;
+    mm.mvFailureQueue.emplace_back(&k, &points[i]);
+    k.mMeasurements.erase(it);
+    mm.MMData(&points[i]).sMeasurementKFs.erase(&k);
+  }
+  const int nQueued = (int)mm.mvFailureQueue.size();
+  const int nSecondChance = mm.ReFindFromFailureQueue();
+  int nSame = 0;
+  for (auto& pm : before) {
+    auto it = k.mMeasurements.find(pm.first);
+    if (it != k.mMeasurements.end() && it->second.nLevel == pm.second.nLevel && it->second.v2RootPos[0] == pm.second.v2RootPos[0] &&
+        it->second.v2RootPos[1] == pm.second.v2RootPos[1]) nSame++;
+  }
   std::vector<int32_t> out;   // per point: has measurement, source, level, subpix, never retry
   std::vector<double> pos;
   for (int i = 0; i < npts; i++) {
@@ -139,7 +184,7 @@ static int run_refind(const std::string& dir) {
                            (int32_t)mm.MMData(&points[i]).sNeverRetryKFs.count(&k)});
     pos.push_back(has ? it->second.v2RootPos[0] : 0.0); pos.push_back(has ? it->second.v2RootPos[1] : 0.0);
   }
-  wr(dir, "rf_out_points.i32", out); wr(dir, "rf_out_pos.f64", pos); wr(dir, "rf_out_counts.i32", std::vector<int32_t>{nFound, nAgain});
+  wr(dir, "rf_out_points.i32", out); wr(dir, "rf_out_pos.f64", pos); wr(dir, "rf_out_counts.i32", std::vector<int32_t>{nFound, nAgain, nQueued, nSecondChance, nSame, (int32_t)mm.mvFailureQueue.size()});
   std::printf("refind: %d new measurements among %d points (second pass %d)\n", nFound, npts, nAgain);
   return 0;
 }

@@ -145,6 +145,48 @@ def test_refind_in_single_keyframe_bookkeeping(orc_binary, tmp_path):
     got = np.fromfile(tmp_path / "rf_out_points.i32", np.int32).reshape(n, 5)
     gpos = np.fromfile(tmp_path / "rf_out_pos.f64").reshape(n, 2)
     counts = np.fromfile(tmp_path / "rf_out_counts.i32", np.int32)
-    assert list(counts) == [n_new, 0] and n_new > 100
-    assert np.array_equal(got, exp)
+    assert list(counts[:2]) == [n_new, 0] and n_new > 100
+    assert np.array_equal(got, exp)     # (the failure-queue round trip below restores every measurement it removed)
     assert np.array_equal(gpos, pos)
+    # MapMaker::ReFindFromFailureQueue: every queued (keyframe, point) pair re-found, unchanged; queue emptied
+    n_queued, n_second, n_same, left = counts[2:]
+    assert n_queued > 10 and n_second == n_queued and n_same == n_queued and left == 0
+
+
+def test_refind_newly_made_points_in_a_third_keyframe(orc_binary, tmp_path):
+    """AddPointsEpipolar between frames 0 and 30, then a third keyframe joins the map and MapMaker::ReFindNewlyMade
+    (MapMaker.cc:1046-1065) looks for the new points in it.  Expected: the same C ABI driven from Python on the map
+    the mirror made (its points are checked against the reference in test_add_points_epipolar_matches_the_reference)."""
+    import numpy as np
+    from ptam_cg_b200 import synth
+    from ptam_cg_b200.capi import Tracker, PT_FOUND
+    W, H = 320, 240
+    frames, poses = synth.render_sequence(W, H, 40)
+    mu.write_epipolar_case(tmp_path, W, H, frames, poses, 0, 30)
+    np.ascontiguousarray(frames[15], np.uint8).tofile(tmp_path / "epi_third.u8")
+    np.ascontiguousarray(poses[15], np.float64).tofile(tmp_path / "epi_third_pose.f64")
+    r = subprocess.run([str(orc_binary), str(tmp_path), "epi"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = mu.read_epipolar_out(tmp_path)
+    n = len(got["points"])
+    third = np.fromfile(tmp_path / "epi_out_third.i32", np.int32)
+    pos3 = np.fromfile(tmp_path / "epi_out_third_pos.f64").reshape(n, 2)
+    n_refound, queue_left = third[:2]
+    per = third[2:].reshape(n, 4)   # measured in k3, level, never-retry in k3, GoodMeasCount
+    # the same search through the C ABI: the new points as a map whose source keyframe is frame 0
+    scale = (1 << got["levels"]).astype(np.float64)
+    centre = np.round((got["meas"][:, :2] + 0.5) / scale[:, None] - 0.5).astype(np.int32)   # Candidate::irLevelPos
+    m = dict(world_pos=got["points"][:, :3], pixel_right_w=got["points"][:, 3:6], pixel_down_w=got["points"][:, 6:9],
+             src_kf=np.zeros(n, np.int32), src_level=got["levels"], ir_center=centre)
+    t = Tracker(oracle_lib(), W, H, 1)
+    t.add_keyframe(frames[0])
+    t.set_map(0, m)
+    t.refind_in_keyframes([frames[15]], [poses[15]])
+    pts = t.get_points(0)
+    found = (pts["flags"] & PT_FOUND) != 0
+    assert n_refound == found.sum() and queue_left == 0 and found.sum() > 50
+    assert np.array_equal(per[:, 0], found.astype(np.int32))
+    assert np.array_equal(per[found, 1], pts["level"][found])
+    assert np.array_equal(per[:, 2], (~found).astype(np.int32))
+    assert np.array_equal(per[:, 3], 2 + found.astype(np.int32))       # source + target (+ the third keyframe)
+    assert np.array_equal(pos3[found], pts["v2_found"][found])

@@ -75,6 +75,8 @@ def test_refind_in_single_keyframe_on_the_device(product, tmp_path):
     got = np.fromfile(tmp_path / "rf_out_points.i32", np.int32).reshape(n, 5)
     gpos = np.fromfile(tmp_path / "rf_out_pos.f64").reshape(n, 2)
     counts = np.fromfile(tmp_path / "rf_out_counts.i32", np.int32)
-    assert list(counts) == [n_new, 0] and n_new > 100
+    assert list(counts[:2]) == [n_new, 0] and n_new > 100
     assert np.array_equal(got, exp)
     np.testing.assert_allclose(gpos, pos, rtol=0, atol=1e-9)
+    n_queued, n_second, n_same, left = counts[2:]   # ReFindFromFailureQueue round trip
+    assert n_queued > 10 and n_second == n_queued and n_same == n_queued and left == 0
