@@ -66,3 +66,22 @@ def test_first_lm_step_seed_sweep(oracle, product, seed):
     assert np.array_equal(o.GetOutlierMeasurements(), p.GetOutlierMeasurements())
     np.testing.assert_allclose(p.get_points(), o.get_points(), atol=1e-9, rtol=0)
     np.testing.assert_allclose(p.get_cameras(), o.get_cameras(), atol=1e-9, rtol=0)
+
+
+@pytest.mark.parametrize("n_cams", [33, 65], ids=["n192", "n384"])
+def test_reduced_system_of_whole_panels(oracle, product, n_cams):
+    """6 x (n_cams - 1) free-camera rows = a multiple of the 64-wide LDL^T panel: the last panel is a full one with
+    nothing below it (bulk-copied operands, no rows to solve) — a shape no other graph in the suite has."""
+    g = synth.make_ba_graph(n_cams, 1500, 6000, seed=50 + n_cams)
+    n = 6 * int((g["cam_fixed"] == 0).sum())
+    assert n % 64 == 0
+    o, p = Bundle(oracle, g["width"], g["height"]), Bundle(product, g["width"], g["height"])
+    o.add_graph(g); p.add_graph(g)
+    o.begin(); p.begin()
+    o.lm_step(); p.lm_step()
+    so, sp = o.stats(), p.stats()
+    assert (so.accepted, so.lambda_trials, so.n_outliers) == (sp.accepted, sp.lambda_trials, sp.n_outliers)
+    np.testing.assert_allclose(sp.last_new_error, so.last_new_error, rtol=1e-10)
+    assert np.array_equal(o.GetOutlierMeasurements(), p.GetOutlierMeasurements())
+    np.testing.assert_allclose(p.get_points(), o.get_points(), atol=1e-9, rtol=0)
+    np.testing.assert_allclose(p.get_cameras(), o.get_cameras(), atol=1e-9, rtol=0)
