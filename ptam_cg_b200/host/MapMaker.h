@@ -252,6 +252,77 @@ class MapMaker {
     return out;
   }
 
+  // MapMaker.cc:738-752: the keyframe of the map nearest to k (not k itself)
+  KeyFrame* ClosestKeyFrame(KeyFrame& k) {
+    KeyFrame* best = nullptr;
+    double best_dist = 9999999999.9;
+    for (KeyFrame* other : mMap.vpKeyFrames) {
+      if (other == &k) continue;
+      const double d = KeyFrameLinearDist(k, *other);
+      if (d < best_dist) { best_dist = d; best = other; }
+    }
+    if (!best) throw std::logic_error("ClosestKeyFrame: the map has no other keyframe");
+    return best;
+  }
+
+  // MapMaker.cc:413-441: drop the candidates of one level that sit within 10 level-pixels of a point the keyframe
+  // already measures on that level or the next coarser one
+  static void ThinCandidates(KeyFrame& k, int nLevel) {
+    std::vector<CVD::ImageRef> busy;
+    const int scale = Level::LevelScale(nLevel);
+    auto rounded = [](double v) { return (int)(v > 0.0 ? v + 0.5 : v - 0.5); };  // CVD::ir_rounded
+    for (auto& pm : k.mMeasurements)
+      if (pm.second.nLevel == nLevel || pm.second.nLevel == nLevel + 1)
+        busy.emplace_back(rounded(pm.second.v2RootPos[0] / scale), rounded(pm.second.v2RootPos[1] / scale));
+    std::vector<Candidate>& cands = k.aLevels[nLevel].vCandidates;
+    std::vector<Candidate> kept;
+    for (const Candidate& c : cands) {
+      bool clear = true;
+      for (const CVD::ImageRef& b : busy) {
+        const int dx = b.x - c.irLevelPos.x, dy = b.y - c.irLevelPos.y;
+        if ((unsigned)(dx * dx + dy * dy) < 100u) { clear = false; break; }
+      }
+      if (clear) kept.push_back(c);
+    }
+    cands.swap(kept);
+  }
+
+  // MapMaker.cc:449-458: new points for the newest keyframe on one level, by epipolar search in its nearest neighbour
+  int AddSomeMapPoints(int nLevel) {
+    KeyFrame& kSrc = *mMap.vpKeyFrames.back();
+    KeyFrame& kTarget = *ClosestKeyFrame(kSrc);
+    ThinCandidates(kSrc, nLevel);
+    return AddPointsEpipolar(kSrc, kTarget, nLevel);
+  }
+
+  // MapMaker.cc:480-488: the tracker hands over a keyframe (it is copied; an ongoing adjustment is asked to stop)
+  void AddKeyFrame(KeyFrame& k) {
+    mOwnedKeyFrames.emplace_back(new KeyFrame(k));
+    mvpKeyFrameQueue.push_back(mOwnedKeyFrames.back().get());
+    if (mbBundleRunning) mbBundleAbortRequested = true;
+  }
+
+  // MapMaker.cc:493-519: candidates of the oldest queued keyframe, its measurements entered into the points'
+  // bookkeeping, the points the tracker missed re-found, new points on levels 3, 0, 1, 2
+  void AddKeyFrameFromTopOfQueue() {
+    if (mvpKeyFrameQueue.empty()) return;
+    KeyFrame* pK = mvpKeyFrameQueue.front();
+    mvpKeyFrameQueue.erase(mvpKeyFrameQueue.begin());
+    pK->MakeKeyFrame_Rest(mdCandidateMinSTScore);
+    mMap.vpKeyFrames.push_back(pK);
+    for (auto& pm : pK->mMeasurements) {
+      MMData(pm.first).sMeasurementKFs.insert(pK);
+      pm.second.Source = Measurement::SRC_TRACKER;
+    }
+    ReFindInSingleKeyFrame(*pK);
+    AddSomeMapPoints(3);
+    AddSomeMapPoints(0);
+    AddSomeMapPoints(1);
+    AddSomeMapPoints(2);
+    mbBundleConverged_Full = false;
+    mbBundleConverged_Recent = false;
+  }
+
   // MapMaker.cc:767-782: every keyframe, every point
   void BundleAdjustAll() {
     std::set<KeyFrame*> adjust, fixed;
@@ -358,6 +429,8 @@ class MapMaker {
   bool mbBundleAbortRequested = false, mbResetRequested = false;
   std::vector<std::pair<KeyFrame*, MapPoint*> > mvFailureQueue;
   std::vector<MapPoint*> mvpNewQueue;  // mqNewQueue (MapMaker.h:130): points waiting to be re-found in older keyframes
+  std::vector<KeyFrame*> mvpKeyFrameQueue;   // keyframes from the tracker waiting to be processed (MapMaker.h:128)
+  double mdCandidateMinSTScore = 70.0;       // MapMaker.CandidateMinShiTomasiScore (KeyFrame.cc:63)
   double mdWiggleScale = 0.1;          // MapMaker.WiggleScale (MapMaker.cc:225), the stereo baseline in map units
 
  private:
@@ -400,6 +473,7 @@ class MapMaker {
   bool mbAssocMapValid = false;
   std::map<KeyFrame*, int> mStoreId;  // keyframes already resident in the handle's keyframe store
   std::vector<std::unique_ptr<MapPoint> > mOwnedPoints;
+  std::vector<std::unique_ptr<KeyFrame> > mOwnedKeyFrames;
   Map& mMap;
   ATANCamera mCamera;
   int mnDevice;

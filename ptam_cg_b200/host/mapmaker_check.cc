@@ -189,12 +189,108 @@ static int run_refind(const std::string& dir) {
   return 0;
 }
 
+static int ClosestIndex(MapMaker& mm, KeyFrame& k, std::vector<KeyFrame>& kfs) { return (int)(mm.ClosestKeyFrame(k) - kfs.data()); }
+
+// MapMaker::AddKeyFrame + AddKeyFrameFromTopOfQueue: a map of two keyframes and their points, and a keyframe
+// from the tracker with some measurements.  Output: the thinned candidate lists the epipolar searches ran on,
+// the measurements the keyframe ended up with, the new points.
+static int run_add_keyframe(const std::string& dir) {
+  auto dims = rd<int32_t>(dir, "trk_dims.i32");  // W, H, n_kf, n_pts
+  const int W = dims[0], H = dims[1], nkf = dims[2], npts = dims[3];
+  auto kfim = rd<uint8_t>(dir, "trk_kf.u8");
+  auto kfpose = rd<double>(dir, "ak_kf_poses.f64");
+  auto world = rd<double>(dir, "trk_world.f64");
+  auto right = rd<double>(dir, "trk_right.f64");
+  auto down = rd<double>(dir, "trk_down.f64");
+  auto skf = rd<int32_t>(dir, "trk_srckf.i32");
+  auto slv = rd<int32_t>(dir, "trk_srclevel.i32");
+  auto ctr = rd<int32_t>(dir, "trk_center.i32");
+  auto newim = rd<uint8_t>(dir, "rf_image.u8");
+  auto newpose = rd<double>(dir, "rf_pose.f64");
+  auto depth = rd<double>(dir, "ak_depth.f64");     // scene depth mean, sigma of the new keyframe; wiggle scale
+  auto tm_idx = rd<int32_t>(dir, "ak_meas_idx.i32");  // the tracker's measurements in the new keyframe: point, level
+  auto tm_pos = rd<double>(dir, "ak_meas_pos.f64");
+  ATANCamera cam("Camera", makeVector(1.0803, 1.43987, 0.519983, 0.548655, 0.244943), CVD::ImageRef(W, H));
+  Map map;
+  std::vector<KeyFrame> kfs(nkf);
+  std::vector<MapPoint> points(npts);
+  MapMaker mm(map, cam);
+  mm.mdWiggleScale = depth[2];
+  for (int k = 0; k < nkf; k++) {
+    CVD::BasicImage<CVD::byte> im(kfim.data() + (size_t)k * W * H, CVD::ImageRef(W, H));
+    kfs[k].MakeKeyFrame_Lite(im);
+    kfs[k].se3CfromW = se3_from_array(&kfpose[12 * k]);
+    map.vpKeyFrames.push_back(&kfs[k]);
+  }
+  for (int i = 0; i < npts; i++) {
+    MapPoint& p = points[i];
+    p.v3WorldPos = makeVector(world[3 * i], world[3 * i + 1], world[3 * i + 2]);
+    p.v3PixelRight_W = makeVector(right[3 * i], right[3 * i + 1], right[3 * i + 2]);
+    p.v3PixelDown_W = makeVector(down[3 * i], down[3 * i + 1], down[3 * i + 2]);
+    p.pPatchSourceKF = &kfs[skf[i]];
+    p.nSourceLevel = slv[i];
+    p.irCenter = CVD::ImageRef(ctr[2 * i], ctr[2 * i + 1]);
+    map.vpPoints.push_back(&p);
+    Measurement root;
+    root.nLevel = slv[i]; root.bSubPix = true; root.Source = Measurement::SRC_ROOT;
+    root.v2RootPos = Level::LevelZeroPos(p.irCenter, slv[i]);
+    kfs[skf[i]].mMeasurements[&p] = root;
+    mm.MMData(&p).sMeasurementKFs.insert(&kfs[skf[i]]);
+  }
+  map.bGood = true; map.nRevision++;
+  KeyFrame fromTracker;
+  CVD::BasicImage<CVD::byte> im(newim.data(), CVD::ImageRef(W, H));
+  fromTracker.MakeKeyFrame_Lite(im);
+  fromTracker.se3CfromW = se3_from_array(newpose.data());
+  fromTracker.dSceneDepthMean = depth[0]; fromTracker.dSceneDepthSigma = depth[1];
+  for (size_t j = 0; j < tm_idx.size() / 2; j++) {
+    Measurement m;
+    m.nLevel = tm_idx[2 * j + 1]; m.bSubPix = m.nLevel > 0; m.Source = Measurement::SRC_REFIND;  // the hand-over resets it
+    m.v2RootPos = makeVector(tm_pos[2 * j], tm_pos[2 * j + 1]);
+    fromTracker.mMeasurements[&points[tm_idx[2 * j]]] = m;
+  }
+  mm.mbBundleConverged_Full = mm.mbBundleConverged_Recent = true;
+  mm.AddKeyFrame(fromTracker);
+  if (mm.mvpKeyFrameQueue.size() != 1 || map.vpKeyFrames.size() != (size_t)nkf) { std::cerr << "AddKeyFrame must only queue\n"; return 1; }
+  mm.AddKeyFrameFromTopOfQueue();
+  if (!mm.mvpKeyFrameQueue.empty() || map.vpKeyFrames.size() != (size_t)nkf + 1 || mm.mbBundleConverged_Full || mm.mbBundleConverged_Recent) {
+    std::cerr << "queue / map / convergence flags after AddKeyFrameFromTopOfQueue\n"; return 1;
+  }
+  KeyFrame& k = *map.vpKeyFrames.back();
+  if (&k == &fromTracker) { std::cerr << "the keyframe must be copied\n"; return 1; }
+  std::vector<int32_t> cand, meas, newpts;
+  std::vector<double> meas_pos;
+  for (int l = 0; l < LEVELS; l++) {
+    cand.push_back((int32_t)k.aLevels[l].vCandidates.size());
+    for (auto& c : k.aLevels[l].vCandidates) { cand.push_back(c.irLevelPos.x); cand.push_back(c.irLevelPos.y); }
+  }
+  for (int i = 0; i < npts; i++) {
+    auto it = k.mMeasurements.find(&points[i]);
+    const bool has = it != k.mMeasurements.end();
+    meas.insert(meas.end(), {has ? 1 : 0, has ? (int32_t)it->second.Source : -1, has ? it->second.nLevel : -1,
+                             (int32_t)mm.MMData(&points[i]).sMeasurementKFs.count(&k), (int32_t)mm.MMData(&points[i]).sNeverRetryKFs.count(&k)});
+    meas_pos.push_back(has ? it->second.v2RootPos[0] : 0.0); meas_pos.push_back(has ? it->second.v2RootPos[1] : 0.0);
+  }
+  int per_level[LEVELS] = {0, 0, 0, 0};
+  for (size_t i = npts; i < map.vpPoints.size(); i++) {
+    MapPoint* p = map.vpPoints[i];
+    per_level[p->nSourceLevel]++;
+    if (p->pPatchSourceKF != &k || !k.mMeasurements.count(p)) { std::cerr << "new point not rooted in the new keyframe\n"; return 1; }
+  }
+  for (int l = 0; l < LEVELS; l++) newpts.push_back(per_level[l]);
+  newpts.push_back((int32_t)(ClosestIndex(mm, k, kfs)));
+  wr(dir, "ak_out_cand.i32", cand); wr(dir, "ak_out_meas.i32", meas); wr(dir, "ak_out_meas_pos.f64", meas_pos); wr(dir, "ak_out_new.i32", newpts);
+  std::printf("add keyframe: %zu new points (levels %d %d %d %d)\n", map.vpPoints.size() - npts, per_level[0], per_level[1], per_level[2], per_level[3]);
+  return 0;
+}
+
 int main(int argc, char** argv) {
-  if (argc < 2) { std::cerr << "usage: mapmaker_check <dir> [ba|epi|refind]\n"; return 2; }
+  if (argc < 2) { std::cerr << "usage: mapmaker_check <dir> [ba|epi|refind|addkf]\n"; return 2; }
   const std::string dir = argv[1];
   try {
     if (argc > 2 && std::string(argv[2]) == "epi") return run_epipolar(dir);
     if (argc > 2 && std::string(argv[2]) == "refind") return run_refind(dir);
+    if (argc > 2 && std::string(argv[2]) == "addkf") return run_add_keyframe(dir);
     auto cams = rd<double>(dir, "mm_cams.f64");
     auto fixed = rd<int32_t>(dir, "mm_fixed.i32");
     auto pts = rd<double>(dir, "mm_pts.f64");

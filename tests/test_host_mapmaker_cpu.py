@@ -190,3 +190,98 @@ def test_refind_newly_made_points_in_a_third_keyframe(orc_binary, tmp_path):
     assert np.array_equal(per[:, 2], (~found).astype(np.int32))
     assert np.array_equal(per[:, 3], 2 + found.astype(np.int32))       # source + target (+ the third keyframe)
     assert np.array_equal(pos3[found], pts["v2_found"][found])
+
+
+def _add_keyframe_case(tmp_path, lib):
+    """Inputs for `mapmaker_check <dir> addkf` and what MapMaker::AddKeyFrameFromTopOfQueue (MapMaker.cc:493-519) must
+    produce, from `lib`'s C ABI and the reference's glue (ThinCandidates :413-441, ClosestKeyFrame :738-752,
+    AddSomeMapPoints :449-458 on levels 3, 0, 1, 2)."""
+    import numpy as np
+    from ptam_cg_b200 import synth
+    from ptam_cg_b200.capi import Tracker, PT_FOUND
+    from oracle.binding import detect_with
+    W, H = 320, 240
+    frames, poses = synth.render_sequence(W, H, 12)
+    cam = synth.AtanCamera(W, H)
+    kf_idx = (0, 8)
+    kfs, m = synth.build_map(frames, poses, detect_with(Tracker, oracle_lib(), W, H), cam, kf_indices=kf_idx, per_level=(150, 80, 40, 20))
+    n, f = len(m["src_kf"]), 5   # nearer to keyframe 8 than to keyframe 0 (frame 4 would be a tie)
+    depth, wiggle = (1.0, 0.3), 0.1
+    np.array([W, H, len(kfs), n], np.int32).tofile(tmp_path / "trk_dims.i32")
+    np.ascontiguousarray(np.stack(kfs), np.uint8).tofile(tmp_path / "trk_kf.u8")
+    for name, key, dt in (("trk_world.f64", "world_pos", np.float64), ("trk_right.f64", "pixel_right_w", np.float64),
+                          ("trk_down.f64", "pixel_down_w", np.float64), ("trk_srckf.i32", "src_kf", np.int32),
+                          ("trk_srclevel.i32", "src_level", np.int32), ("trk_center.i32", "ir_center", np.int32)):
+        np.ascontiguousarray(m[key], dt).tofile(tmp_path / name)
+    np.ascontiguousarray([poses[i] for i in kf_idx], np.float64).tofile(tmp_path / "ak_kf_poses.f64")
+    np.ascontiguousarray(frames[f], np.uint8).tofile(tmp_path / "rf_image.u8")
+    np.ascontiguousarray(poses[f], np.float64).tofile(tmp_path / "rf_pose.f64")
+    np.array([depth[0], depth[1], wiggle], np.float64).tofile(tmp_path / "ak_depth.f64")
+    # what a search of every map point in the new frame finds; the tracker is given every other one of them
+    t = Tracker(lib, W, H, 1)
+    for k in kfs:
+        t.add_keyframe(k)
+    t.set_map(0, m)
+    t.refind_in_keyframes([frames[f]], [poses[f]])
+    pts = t.get_points(0)
+    found = (pts["flags"] & PT_FOUND) != 0
+    given = np.flatnonzero(found)[::2]
+    np.ascontiguousarray(np.column_stack([given, pts["level"][given]]), np.int32).tofile(tmp_path / "ak_meas_idx.i32")
+    np.ascontiguousarray(pts["v2_found"][given], np.float64).tofile(tmp_path / "ak_meas_pos.f64")
+    meas = np.zeros((n, 5), np.int32)
+    pos = np.zeros((n, 2))
+    is_given = np.zeros(n, bool); is_given[given] = True
+    for i in range(n):
+        if found[i]:
+            meas[i] = (1, 0 if is_given[i] else 1, pts["level"][i], 1, 0)   # SRC_TRACKER = 0, SRC_REFIND = 1
+            pos[i] = pts["v2_found"][i]
+        else:
+            meas[i] = (0, -1, -1, 0, 1)
+    # candidates of the new keyframe, the nearest keyframe, then levels 3, 0, 1, 2: thin, search, remember the roots
+    t.make_keyframes([frames[f]])
+    cands = [np.asarray(r[1], np.int32).reshape(-1, 2) for r in t.keyframe_rest(0, 70.0)]
+    centre = lambda p: -synth.se3_from12(p)[0].T @ synth.se3_from12(p)[1]
+    closest = int(np.argmin([np.linalg.norm(centre(poses[i]) - centre(poses[f])) for i in kf_idx]))
+    t2 = Tracker(lib, W, H, 1)
+    src_id = t2.add_keyframe(frames[f])
+    t2.make_keyframes([frames[kf_idx[closest]]])
+    busy_meas = [(int(pts["level"][i]), pts["v2_found"][i]) for i in np.flatnonzero(found)]
+    rnd = lambda v: int(v + 0.5) if v > 0 else int(v - 0.5)
+    thinned, new_counts = {}, {}
+    for l in (3, 0, 1, 2):
+        scale = 1 << l
+        busy = [(rnd(p[0] / scale), rnd(p[1] / scale)) for lv, p in busy_meas if lv in (l, l + 1)]
+        keep = [c for c in cands[l] if all((b[0] - c[0]) ** 2 + (b[1] - c[1]) ** 2 >= 100 for b in busy)]
+        thinned[l] = np.array(keep, np.int32).reshape(-1, 2)
+        if len(keep):
+            fnd, _, _ = t2.epipolar_search(0, l, src_id, poses[f], depth[0], depth[1], poses[kf_idx[closest]], wiggle, thinned[l])
+        else:
+            fnd = np.zeros(0, np.int32)
+        new_counts[l] = int(fnd.sum())
+        for c in thinned[l][fnd != 0]:
+            busy_meas.append((l, (np.asarray(c, np.float64) + 0.5) * scale - 0.5))
+    return n, meas, pos, thinned, new_counts, closest
+
+
+def _check_add_keyframe(tmp_path, n, meas, pos, thinned, new_counts, closest, tol):
+    import numpy as np
+    got_meas = np.fromfile(tmp_path / "ak_out_meas.i32", np.int32).reshape(n, 5)
+    got_pos = np.fromfile(tmp_path / "ak_out_meas_pos.f64").reshape(n, 2)
+    cand = np.fromfile(tmp_path / "ak_out_cand.i32", np.int32)
+    new = np.fromfile(tmp_path / "ak_out_new.i32", np.int32)
+    assert np.array_equal(got_meas, meas)
+    np.testing.assert_allclose(got_pos, pos, rtol=0, atol=tol)
+    o = 0
+    for l in range(4):
+        k = int(cand[o]); o += 1
+        assert np.array_equal(cand[o:o + 2 * k].reshape(-1, 2), thinned[l]), f"thinned candidates of level {l}"
+        o += 2 * k
+    assert list(new[:4]) == [new_counts[l] for l in range(4)] and sum(new[:4]) > 50
+    assert new[4] == closest
+
+
+def test_add_keyframe_from_top_of_queue(orc_binary, tmp_path):
+    case = _add_keyframe_case(tmp_path, oracle_lib())
+    r = subprocess.run([str(orc_binary), str(tmp_path), "addkf"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    _check_add_keyframe(tmp_path, *case, tol=0.0)

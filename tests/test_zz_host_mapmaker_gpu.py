@@ -80,3 +80,16 @@ def test_refind_in_single_keyframe_on_the_device(product, tmp_path):
     np.testing.assert_allclose(gpos, pos, rtol=0, atol=1e-9)
     n_queued, n_second, n_same, left = counts[2:]   # ReFindFromFailureQueue round trip
     assert n_queued > 10 and n_second == n_queued and n_same == n_queued and left == 0
+
+
+def test_add_keyframe_from_top_of_queue_on_the_device(product, tmp_path):
+    """MapMaker::AddKeyFrame + AddKeyFrameFromTopOfQueue of the host mirror (re-find, ThinCandidates, epipolar search
+    on levels 3, 0, 1, 2 in the nearest keyframe) with the CUDA library behind it; expectation from the same C ABI
+    driven from Python (CPU twin: tests/test_host_mapmaker_cpu.py::test_add_keyframe_from_top_of_queue)."""
+    from test_host_mapmaker_cpu import _add_keyframe_case, _check_add_keyframe
+    r = subprocess.run(["make", "-C", str(HOST)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    case = _add_keyframe_case(tmp_path, product)
+    r = subprocess.run([str(HOST / "mapmaker_check"), str(tmp_path), "addkf"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    _check_add_keyframe(tmp_path, *case, tol=1e-9)
