@@ -24,6 +24,7 @@ struct RefMapMaker : public MapMaker {
   void ResetNow() { if (mbResetRequested) Reset(); }
   int ReFindAllIn(KeyFrame& k) { return ReFindInSingleKeyFrame(k); }
   bool Epipolar(KeyFrame& src, KeyFrame& tgt, int level, int cand) { return AddPointEpipolar(src, tgt, level, cand); }
+  void TopOfQueue() { AddKeyFrameFromTopOfQueue(); }
 };
 struct RefTracker : public Tracker {
   RefTracker(CVD::ImageRef sz, const ATANCamera& c, Map& m, MapMaker& mm) : Tracker(sz, c, m, mm) {}
@@ -298,6 +299,81 @@ int ref_tracker_refind_in_keyframes(void* hp, const uint8_t* const* images, int 
 // the stream's current frame.  The new MapPoint the reference creates is read (sub-pixel target
 // position = kTarget.mMeasurements[pNew].v2RootPos, triangulated v3WorldPos) and removed again.
 // NB the reference caches UnProject of every pixel in a function-local static sized by the first call.
+// Test hook (not part of the shared ABI): the reference's own MapMaker::AddKeyFrame + AddKeyFrameFromTopOfQueue
+// (MapMaker.cc:480-519: MakeKeyFrame_Rest, ReFindInSingleKeyFrame, ThinCandidates / ClosestKeyFrame / AddPointEpipolar on
+// levels 3, 0, 1, 2) on the stream's map.  The stored keyframes must have poses (ref_tracker_set_keyframe_pose) and the
+// map must be set; every existing point gets its root measurement in its source keyframe first.  The keyframe from the
+// "tracker" = image, pose, scene depth and n_meas measurements (point, level | position).  Outputs, in the layout of
+// ptam_cg_b200/host/mapmaker_check.cc (addkf): per old point (has measurement, Source, level, in sMeasurementKFs,
+// in sNeverRetryKFs) + position; the thinned candidate lists (count, then x y pairs, per level); new points per level
+// and the index of the closest stored keyframe.
+int ref_mapmaker_add_keyframe(void* hp, int stream, const uint8_t* image, int stride, const double* se3, double depth_mean,
+                              double depth_sigma, double wiggle, int n_meas, const int32_t* meas_pt_level, const double* meas_pos,
+                              int32_t* out_meas, double* out_pos, int32_t* out_cand, int cand_cap, int32_t* out_new) {
+  Handle* h = (Handle*)hp;
+  if (stream < 0 || stream >= h->S) return PTAM_ERR_INVALID;
+  Stream& st = *h->streams[stream];
+  const size_t n_old = st.map.vpPoints.size();
+  for (KeyFrame* k : h->store) k->mMeasurements.clear();
+  for (MapPoint* p : st.map.vpPoints) {
+    p->pMMData->sMeasurementKFs.clear(); p->pMMData->sNeverRetryKFs.clear();
+    Measurement root;
+    root.nLevel = p->nSourceLevel; root.bSubPix = true; root.Source = Measurement::SRC_ROOT;
+    root.v2RootPos = Level::LevelZeroPos(p->irCenter, p->nSourceLevel);
+    p->pPatchSourceKF->mMeasurements[p] = root;
+    p->pMMData->sMeasurementKFs.insert(p->pPatchSourceKF);
+  }
+  st.map.vpKeyFrames = h->store;
+  GVars3::GV3::set<double>("MapMaker.CandidateMinShiTomasiScore", 70.0);
+  KeyFrame from_tracker;
+  from_tracker.bFixed = false;
+  CVD::Image<CVD::byte> im = wrap_image(image, h->W, h->H, stride);
+  from_tracker.MakeKeyFrame_Lite(im);
+  from_tracker.se3CfromW = se3_from12(se3);
+  from_tracker.dSceneDepthMean = depth_mean; from_tracker.dSceneDepthSigma = depth_sigma;
+  for (int j = 0; j < n_meas; j++) {
+    Measurement m;
+    m.nLevel = meas_pt_level[2 * j + 1]; m.bSubPix = m.nLevel > 0; m.Source = Measurement::SRC_REFIND;
+    m.v2RootPos = TooN::makeVector(meas_pos[2 * j], meas_pos[2 * j + 1]);
+    from_tracker.mMeasurements[st.map.vpPoints[meas_pt_level[2 * j]]] = m;
+  }
+  st.mm->mdWiggleScale = wiggle;
+  st.mm->AddKeyFrame(from_tracker);
+  st.mm->TopOfQueue();
+  st.mm->mdWiggleScale = 1e30;
+  KeyFrame& k = *st.map.vpKeyFrames.back();
+  for (size_t i = 0; i < n_old; i++) {
+    MapPoint* p = st.map.vpPoints[i];
+    auto it = k.mMeasurements.find(p);
+    const bool has = it != k.mMeasurements.end();
+    out_meas[5 * i] = has; out_meas[5 * i + 1] = has ? (int)it->second.Source : -1; out_meas[5 * i + 2] = has ? it->second.nLevel : -1;
+    out_meas[5 * i + 3] = (int)p->pMMData->sMeasurementKFs.count(&k); out_meas[5 * i + 4] = (int)p->pMMData->sNeverRetryKFs.count(&k);
+    out_pos[2 * i] = has ? it->second.v2RootPos[0] : 0.0; out_pos[2 * i + 1] = has ? it->second.v2RootPos[1] : 0.0;
+  }
+  int o = 0;
+  for (int l = 0; l < LEVELS; l++) {
+    const auto& v = k.aLevels[l].vCandidates;
+    if (o + 1 + 2 * (int)v.size() > cand_cap) return PTAM_ERR_CAPACITY;
+    out_cand[o++] = (int)v.size();
+    for (const auto& c : v) { out_cand[o++] = c.irLevelPos.x; out_cand[o++] = c.irLevelPos.y; }
+  }
+  for (int l = 0; l < LEVELS; l++) out_new[l] = 0;
+  for (size_t i = n_old; i < st.map.vpPoints.size(); i++) out_new[st.map.vpPoints[i]->nSourceLevel]++;
+  double best = 1e300; int closest = -1;
+  for (size_t c = 0; c < h->store.size(); c++) {
+    const TooN::Vector<3> d = h->store[c]->se3CfromW.inverse().get_translation() - k.se3CfromW.inverse().get_translation();
+    if (std::sqrt(d * d) < best) { best = std::sqrt(d * d); closest = (int)c; }
+  }
+  out_new[4] = closest;
+  // take the new keyframe and its points out again: the handle's other entry points expect the map as it was set
+  for (size_t i = n_old; i < st.map.vpPoints.size(); i++) { MapPoint* p = st.map.vpPoints[i]; delete p->pMMData; delete p; }
+  st.map.vpPoints.resize(n_old);
+  for (MapPoint* p : st.map.vpPoints) { p->pMMData->sMeasurementKFs.clear(); p->pMMData->sNeverRetryKFs.clear(); }
+  for (KeyFrame* kk : h->store) kk->mMeasurements.clear();
+  st.map.vpKeyFrames = h->store;
+  delete &k;
+  return o;
+}
 // world position + pixel-right / pixel-down vectors (9 doubles) of every point the last ref_tracker_epipolar_search
 // added, in candidate order: what MapMaker.cc:648-672 (Triangulate, RefreshPixelVectors) computed.  Test hook for
 // the host mirror's MapMaker::AddPointsEpipolar; not part of the shared ABI.

@@ -285,3 +285,59 @@ def test_add_keyframe_from_top_of_queue(orc_binary, tmp_path):
     r = subprocess.run([str(orc_binary), str(tmp_path), "addkf"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     _check_add_keyframe(tmp_path, *case, tol=0.0)
+
+
+def test_add_keyframe_from_top_of_queue_matches_the_reference_itself(orc_libm_binary, tmp_path):
+    """The same hand-over through the reference's OWN MapMaker::AddKeyFrame + AddKeyFrameFromTopOfQueue, compiled in
+    place (oracle/_ref, test hook ref_mapmaker_add_keyframe): the measurements the keyframe ends up with, the
+    never-retry marks, the thinned candidate lists, the new points per level and the nearest keyframe must equal
+    what the host mirror leaves behind (over the libm-atan oracle, which is pinned bit for bit against oracle/_ref)."""
+    import ctypes as C
+    import numpy as np
+    from ptam_cg_b200 import synth
+    from ptam_cg_b200.capi import Tracker
+    from oracle.binding import ref_lib
+    ref = ref_lib()
+    if ref is None or not hasattr(ref.cdll, "ref_mapmaker_add_keyframe"):
+        pytest.skip("oracle/_ref not built")
+    n, meas, pos, thinned, new_counts, closest = _add_keyframe_case(tmp_path, oracle_lib(libm_atan=True))
+    r = subprocess.run([str(orc_libm_binary), str(tmp_path), "addkf"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    # ---- the reference, on the same files
+    dims = np.fromfile(tmp_path / "trk_dims.i32", np.int32)
+    W, H, nkf = int(dims[0]), int(dims[1]), int(dims[2])
+    kfim = np.fromfile(tmp_path / "trk_kf.u8", np.uint8).reshape(nkf, H, W)
+    kfpose = np.fromfile(tmp_path / "ak_kf_poses.f64").reshape(nkf, 12)
+    m = dict(world_pos=np.fromfile(tmp_path / "trk_world.f64").reshape(n, 3), pixel_right_w=np.fromfile(tmp_path / "trk_right.f64").reshape(n, 3),
+             pixel_down_w=np.fromfile(tmp_path / "trk_down.f64").reshape(n, 3), src_kf=np.fromfile(tmp_path / "trk_srckf.i32", np.int32),
+             src_level=np.fromfile(tmp_path / "trk_srclevel.i32", np.int32), ir_center=np.fromfile(tmp_path / "trk_center.i32", np.int32).reshape(n, 2))
+    t = Tracker(ref, W, H, 1)
+    for k in range(nkf):
+        t.add_keyframe(kfim[k])
+        assert ref.cdll.ref_tracker_set_keyframe_pose(C.c_void_p(t.h), k, kfpose[k].ctypes.data_as(C.POINTER(C.c_double))) == 0
+    t.set_map(0, m)
+    image = np.fromfile(tmp_path / "rf_image.u8", np.uint8)
+    pose = np.fromfile(tmp_path / "rf_pose.f64")
+    depth = np.fromfile(tmp_path / "ak_depth.f64")
+    tm_idx = np.fromfile(tmp_path / "ak_meas_idx.i32", np.int32)
+    tm_pos = np.fromfile(tmp_path / "ak_meas_pos.f64")
+    out_meas, out_pos = np.zeros((n, 5), np.int32), np.zeros((n, 2))
+    out_cand, out_new = np.zeros(20000, np.int32), np.zeros(5, np.int32)
+    fn = ref.cdll.ref_mapmaker_add_keyframe
+    fn.restype = C.c_int
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    rc = fn(C.c_void_p(t.h), 0, image.ctypes.data_as(C.POINTER(C.c_uint8)), W, pose.ctypes.data_as(dp), C.c_double(depth[0]),
+            C.c_double(depth[1]), C.c_double(depth[2]), len(tm_idx) // 2, tm_idx.ctypes.data_as(ip), tm_pos.ctypes.data_as(dp),
+            out_meas.ctypes.data_as(ip), out_pos.ctypes.data_as(dp), out_cand.ctypes.data_as(ip), len(out_cand), out_new.ctypes.data_as(ip))
+    assert rc > 0
+    # ---- mirror == reference
+    got_meas = np.fromfile(tmp_path / "ak_out_meas.i32", np.int32).reshape(n, 5)
+    got_pos = np.fromfile(tmp_path / "ak_out_meas_pos.f64").reshape(n, 2)
+    got_cand = np.fromfile(tmp_path / "ak_out_cand.i32", np.int32)
+    got_new = np.fromfile(tmp_path / "ak_out_new.i32", np.int32)
+    assert np.array_equal(got_meas, out_meas)
+    assert np.array_equal(got_pos, out_pos)
+    assert np.array_equal(got_cand, out_cand[:rc])
+    assert np.array_equal(got_new, out_new) and got_new[:4].sum() > 50
+    # and both equal the glue restated in Python
+    _check_add_keyframe(tmp_path, n, meas, pos, thinned, new_counts, closest, tol=0.0)
