@@ -25,6 +25,12 @@ struct RefMapMaker : public MapMaker {
   int ReFindAllIn(KeyFrame& k) { return ReFindInSingleKeyFrame(k); }
   bool Epipolar(KeyFrame& src, KeyFrame& tgt, int level, int cand) { return AddPointEpipolar(src, tgt, level, cand); }
   void TopOfQueue() { AddKeyFrameFromTopOfQueue(); }
+  using MapMaker::mbBundleConverged_Full;
+  using MapMaker::mbBundleConverged_Recent;
+  using MapMaker::mbBundleRunning;
+  using MapMaker::mvFailureQueue;
+  void AdjustAll() { BundleAdjustAll(); }
+  void AdjustRecent() { BundleAdjustRecent(); }
 };
 struct RefTracker : public Tracker {
   RefTracker(CVD::ImageRef sz, const ATANCamera& c, Map& m, MapMaker& mm) : Tracker(sz, c, m, mm) {}
@@ -299,6 +305,62 @@ int ref_tracker_refind_in_keyframes(void* hp, const uint8_t* const* images, int 
 // the stream's current frame.  The new MapPoint the reference creates is read (sub-pixel target
 // position = kTarget.mMeasurements[pNew].v2RootPos, triangulated v3WorldPos) and removed again.
 // NB the reference caches UnProject of every pixel in a function-local static sized by the first call.
+// Test hook (not part of the shared ABI): the reference's own MapMaker::BundleAdjustAll / BundleAdjustRecent
+// (MapMaker.cc:767-933) on a map given as arrays: keyframes (pose, fixed), points, measurements (keyframe, point, root
+// position, level, Source).  Keyframes and points live in arrays, so pointer order = index order, as in
+// ptam_cg_b200/host/mapmaker_check.cc.  Outputs in that program's layout.  Returns the failure-queue length, or < 0.
+int ref_mapmaker_bundle_adjust(void* hp, int stream, int mode, int max_iterations, int C, const double* cams, const int32_t* fixed, int P,
+                               const double* pts, int M, const int32_t* mcam, const int32_t* mpt, const double* uv, const int32_t* level,
+                               const int32_t* src, double* out_pts, double* out_cams, int32_t* out_bad, int32_t* out_nmeas,
+                               int32_t* out_queue, int32_t* out_never, int never_cap, int32_t* out_n_never, int32_t* out_flags) {
+  Handle* h = (Handle*)hp;
+  if (stream < 0 || stream >= h->S) return PTAM_ERR_INVALID;
+  Stream& st = *h->streams[stream];
+  GVars3::GV3::set<int>("Bundle.MaxIterations", max_iterations);   // the Bundle keys are process-wide: pin them all
+  GVars3::GV3::set<double>("Bundle.UpdateSquaredConvergenceLimit", 1e-6);
+  GVars3::GV3::set<double>("Bundle.MinTukeySigma", 0.4);
+  GVars3::GV3::set<std::string>("Bundle.MEstimator", "Tukey");
+  GVars3::GV3::set<int>("Bundle.Cout", 0);
+  std::unique_ptr<KeyFrame[]> kfs(new KeyFrame[C]);
+  std::unique_ptr<MapPoint[]> points(new MapPoint[P]);
+  std::vector<KeyFrame*> saved_kfs = st.map.vpKeyFrames;
+  std::vector<MapPoint*> saved_pts = st.map.vpPoints;
+  st.map.vpKeyFrames.clear(); st.map.vpPoints.clear();
+  for (int c = 0; c < C; c++) { kfs[c].se3CfromW = se3_from12(cams + 12 * c); kfs[c].bFixed = fixed[c] != 0; st.map.vpKeyFrames.push_back(&kfs[c]); }
+  for (int p = 0; p < P; p++) {
+    points[p].v3WorldPos = TooN::makeVector(pts[3 * p], pts[3 * p + 1], pts[3 * p + 2]);
+    points[p].pMMData = new MapMakerData;
+    st.map.vpPoints.push_back(&points[p]);
+  }
+  for (int m = 0; m < M; m++) {
+    Measurement me;
+    me.nLevel = level[m]; me.bSubPix = false; me.v2RootPos = TooN::makeVector(uv[2 * m], uv[2 * m + 1]);
+    me.Source = static_cast<decltype(me.Source)>(src[m]);
+    kfs[mcam[m]].mMeasurements[&points[mpt[m]]] = me;
+    points[mpt[m]].pMMData->sMeasurementKFs.insert(&kfs[mcam[m]]);
+  }
+  st.mm->mbBundleConverged_Full = true; st.mm->mbBundleConverged_Recent = true;
+  st.mm->mvFailureQueue.clear();
+  if (mode == 0) st.mm->AdjustAll(); else st.mm->AdjustRecent();
+  int n_never = 0;
+  for (int p = 0; p < P; p++) {
+    for (int k = 0; k < 3; k++) out_pts[3 * p + k] = points[p].v3WorldPos[k];
+    out_bad[p] = points[p].bBad ? 1 : 0;
+    for (KeyFrame* kf : points[p].pMMData->sNeverRetryKFs)
+      if (n_never < never_cap) { out_never[2 * n_never] = (int)(kf - kfs.get()); out_never[2 * n_never + 1] = p; n_never++; }
+  }
+  *out_n_never = n_never;
+  for (int c = 0; c < C; c++) { se3_to12(kfs[c].se3CfromW, out_cams + 12 * c); out_nmeas[c] = (int)kfs[c].mMeasurements.size(); }
+  const int nq = (int)st.mm->mvFailureQueue.size();
+  for (int q = 0; q < nq; q++) { out_queue[2 * q] = (int)(st.mm->mvFailureQueue[q].first - kfs.get()); out_queue[2 * q + 1] = (int)(st.mm->mvFailureQueue[q].second - points.get()); }
+  out_flags[0] = st.mm->mbBundleConverged_Full; out_flags[1] = st.mm->mbBundleConverged_Recent;
+  out_flags[2] = st.mm->mbResetRequested; out_flags[3] = st.mm->mbBundleRunning;
+  st.mm->mvFailureQueue.clear();
+  for (int p = 0; p < P; p++) delete points[p].pMMData;
+  st.map.vpKeyFrames = saved_kfs; st.map.vpPoints = saved_pts;
+  GVars3::GV3::set<int>("Bundle.MaxIterations", 20);
+  return nq;
+}
 // Test hook (not part of the shared ABI): the reference's own MapMaker::AddKeyFrame + AddKeyFrameFromTopOfQueue
 // (MapMaker.cc:480-519: MakeKeyFrame_Rest, ReFindInSingleKeyFrame, ThinCandidates / ClosestKeyFrame / AddPointEpipolar on
 // levels 3, 0, 1, 2) on the stream's map.  The stored keyframes must have poses (ref_tracker_set_keyframe_pose) and the

@@ -341,3 +341,45 @@ def test_add_keyframe_from_top_of_queue_matches_the_reference_itself(orc_libm_bi
     assert np.array_equal(got_new, out_new) and got_new[:4].sum() > 50
     # and both equal the glue restated in Python
     _check_add_keyframe(tmp_path, n, meas, pos, thinned, new_counts, closest, tol=0.0)
+
+
+@pytest.mark.parametrize("mode", [0, 1], ids=["BundleAdjustAll", "BundleAdjustRecent"])
+def test_bundle_adjust_matches_the_reference_itself(orc_libm_binary, tmp_path, mode):
+    """The reference's OWN MapMaker::BundleAdjustAll / BundleAdjustRecent over its own Bundle (oracle/_ref, test hook
+    ref_mapmaker_bundle_adjust) on the same map: adjusted points and keyframes, bad flags, surviving measurements,
+    failure queue (order included), never-retry sets and convergence flags must equal the host mirror's, bit for bit
+    (the mirror runs over the libm-atan oracle, whose Bundle is pinned bit for bit against the reference's)."""
+    import ctypes as C
+    import numpy as np
+    from ptam_cg_b200.capi import Tracker
+    from oracle.binding import ref_lib
+    ref = ref_lib()
+    if ref is None or not hasattr(ref.cdll, "ref_mapmaker_bundle_adjust"):
+        pytest.skip("oracle/_ref not built")
+    g = mu.make_map()
+    mu.write_map(g, tmp_path, mode, 20)
+    r = subprocess.run([str(orc_libm_binary), str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    Cn, Pn, Mn = len(g["cam_fixed"]), len(g["points"]), len(g["meas_cam"])
+    got = mu.read_map(tmp_path, Cn, Pn)
+    t = Tracker(ref, g["width"], g["height"], 1)   # lends its MapMaker and camera (640x480)
+    f64 = lambda a: np.ascontiguousarray(a, np.float64)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    cams, fixed, pts = f64(g["cam_se3"]), i32(g["cam_fixed"]), f64(g["points"])
+    mcam, mpt, uv, lvl, src = i32(g["meas_cam"]), i32(g["meas_point"]), f64(g["meas_uv"]), i32(g["meas_level"]), i32(g["meas_src"])
+    o_pts, o_cams = np.zeros((Pn, 3)), np.zeros((Cn, 12))
+    o_bad, o_nmeas = np.zeros(Pn, np.int32), np.zeros(Cn, np.int32)
+    o_queue, o_never, o_nn, o_flags = np.zeros((Mn, 2), np.int32), np.zeros((Mn, 2), np.int32), np.zeros(1, np.int32), np.zeros(4, np.int32)
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    D, I = (lambda a: a.ctypes.data_as(dp)), (lambda a: a.ctypes.data_as(ip))
+    fn = ref.cdll.ref_mapmaker_bundle_adjust
+    fn.restype = C.c_int
+    nq = fn(C.c_void_p(t.h), 0, mode, 20, Cn, D(cams), I(fixed), Pn, D(pts), Mn, I(mcam), I(mpt), D(uv), I(lvl), I(src),
+            D(o_pts), D(o_cams), I(o_bad), I(o_nmeas), I(o_queue), I(o_never), Mn, I(o_nn), I(o_flags))
+    assert nq >= 0
+    assert np.array_equal(got["points"], o_pts) and np.array_equal(got["cams"], o_cams)
+    assert np.array_equal(got["bad"], o_bad) and np.array_equal(got["nmeas"], o_nmeas)
+    assert np.array_equal(got["queue"], o_queue[:nq])
+    assert np.array_equal(got["never"], o_never[:int(o_nn[0])])
+    assert np.array_equal(got["flags"], o_flags)
+    assert not np.array_equal(o_pts, pts)   # the adjustment did move the map
