@@ -10,6 +10,7 @@
 #include <iostream>
 #include <string>
 #include "MapMaker.h"
+#include "Tracker.h"
 
 using namespace ptam_b200;
 using namespace TooN;
@@ -284,13 +285,98 @@ static int run_add_keyframe(const std::string& dir) {
   return 0;
 }
 
+// The two threads of the reference in one loop (System.cc:94 + MapMaker::run, MapMaker.cc:87-160): the Tracker mirror
+// follows a sequence; one of its frames becomes a keyframe and goes through MapMaker::AddKeyFrame /
+// AddKeyFrameFromTopOfQueue (new points by epipolar search), the tracker carries on with the enlarged map; at the end
+// the new points are re-found in the older keyframes and the whole map is bundle-adjusted.
+static int run_loop(const std::string& dir) {
+  auto dims = rd<int32_t>(dir, "trk_dims.i32");  // W, H, n_kf, n_pts, n_frames, frame to hand over
+  const int W = dims[0], H = dims[1], nkf = dims[2], npts = dims[3], nfr = dims[4], hand_over = dims[5];
+  auto kfim = rd<uint8_t>(dir, "trk_kf.u8");
+  auto kfpose = rd<double>(dir, "ak_kf_poses.f64");
+  auto frames = rd<uint8_t>(dir, "trk_frames.u8");
+  auto world = rd<double>(dir, "trk_world.f64");
+  auto right = rd<double>(dir, "trk_right.f64");
+  auto down = rd<double>(dir, "trk_down.f64");
+  auto skf = rd<int32_t>(dir, "trk_srckf.i32");
+  auto slv = rd<int32_t>(dir, "trk_srclevel.i32");
+  auto ctr = rd<int32_t>(dir, "trk_center.i32");
+  auto pose0 = rd<double>(dir, "trk_pose0.f64");
+  ATANCamera cam("Camera", makeVector(1.0803, 1.43987, 0.519983, 0.548655, 0.244943), CVD::ImageRef(W, H));
+  Map map;
+  std::vector<KeyFrame> kfs(nkf);
+  std::vector<MapPoint> points(npts);
+  MapMaker mm(map, cam);
+  for (int k = 0; k < nkf; k++) {
+    CVD::BasicImage<CVD::byte> im(kfim.data() + (size_t)k * W * H, CVD::ImageRef(W, H));
+    kfs[k].MakeKeyFrame_Lite(im);
+    kfs[k].se3CfromW = se3_from_array(&kfpose[12 * k]);
+    kfs[k].bFixed = k == 0;  // the first keyframe holds the gauge (MapMaker.cc:304)
+    map.vpKeyFrames.push_back(&kfs[k]);
+  }
+  for (int i = 0; i < npts; i++) {
+    MapPoint& p = points[i];
+    p.v3WorldPos = makeVector(world[3 * i], world[3 * i + 1], world[3 * i + 2]);
+    p.v3PixelRight_W = makeVector(right[3 * i], right[3 * i + 1], right[3 * i + 2]);
+    p.v3PixelDown_W = makeVector(down[3 * i], down[3 * i + 1], down[3 * i + 2]);
+    p.pPatchSourceKF = &kfs[skf[i]];
+    p.nSourceLevel = slv[i];
+    p.irCenter = CVD::ImageRef(ctr[2 * i], ctr[2 * i + 1]);
+    map.vpPoints.push_back(&p);
+    Measurement root;
+    root.nLevel = slv[i]; root.bSubPix = true; root.Source = Measurement::SRC_ROOT;
+    root.v2RootPos = Level::LevelZeroPos(p.irCenter, slv[i]);
+    kfs[skf[i]].mMeasurements[&p] = root;
+    mm.MMData(&p).sMeasurementKFs.insert(&kfs[skf[i]]);
+  }
+  map.bGood = true; map.nRevision++;
+  Tracker trk(CVD::ImageRef(W, H), cam, map);
+  trk.SetCurrentPose(se3_from_array(pose0.data()));
+  std::vector<double> poses;
+  std::vector<int32_t> found, info;
+  CVD::Image<CVD::byte> frame(CVD::ImageRef(W, H));
+  for (int f = 0; f < nfr; f++) {
+    std::memcpy(frame.data(), frames.data() + (size_t)f * W * H, (size_t)W * H);
+    trk.TrackFrame(frame, false);
+    double a[12];
+    se3_to_array(trk.GetCurrentPose(), a);
+    poses.insert(poses.end(), a, a + 12);
+    const ptam_track_result& r = trk.LastResult();
+    found.push_back(r.meas_found[0] + r.meas_found[1] + r.meas_found[2] + r.meas_found[3]);
+    if (f == hand_over) {
+      const size_t before = map.vpPoints.size();
+      mm.AddKeyFrame(trk.CurrentKeyFrame());
+      mm.AddKeyFrameFromTopOfQueue();
+      info.push_back((int32_t)(map.vpPoints.size() - before));
+      info.push_back((int32_t)map.vpKeyFrames.back()->mMeasurements.size());
+    }
+  }
+  const int nRefound = mm.ReFindNewlyMade();
+  std::vector<double> before_ba;
+  for (MapPoint* p : map.vpPoints) for (int k = 0; k < 3; k++) before_ba.push_back(p->v3WorldPos[k]);
+  mm.BundleAdjustAll();
+  std::vector<double> after_ba;
+  int nBad = 0;
+  for (MapPoint* p : map.vpPoints) { for (int k = 0; k < 3; k++) after_ba.push_back(p->v3WorldPos[k]); nBad += p->bBad; }
+  info.insert(info.end(), {nRefound, (int32_t)map.vpPoints.size(), (int32_t)map.vpKeyFrames.size(), mm.mbResetRequested ? 1 : 0,
+                           mm.mbBundleConverged_Full ? 1 : 0, nBad, (int32_t)mm.mvFailureQueue.size()});
+  std::vector<double> kf0(12);
+  se3_to_array(kfs[0].se3CfromW, kf0.data());
+  wr(dir, "loop_out_poses.f64", poses); wr(dir, "loop_out_found.i32", found); wr(dir, "loop_out_info.i32", info);
+  wr(dir, "loop_out_before_ba.f64", before_ba); wr(dir, "loop_out_after_ba.f64", after_ba); wr(dir, "loop_out_kf0.f64", kf0);
+  std::printf("loop: %d frames, %d new points at the hand-over, %d re-found later, map of %zu points in %zu keyframes\n", nfr, info[0], nRefound,
+              map.vpPoints.size(), map.vpKeyFrames.size());
+  return 0;
+}
+
 int main(int argc, char** argv) {
-  if (argc < 2) { std::cerr << "usage: mapmaker_check <dir> [ba|epi|refind|addkf]\n"; return 2; }
+  if (argc < 2) { std::cerr << "usage: mapmaker_check <dir> [ba|epi|refind|addkf|loop]\n"; return 2; }
   const std::string dir = argv[1];
   try {
     if (argc > 2 && std::string(argv[2]) == "epi") return run_epipolar(dir);
     if (argc > 2 && std::string(argv[2]) == "refind") return run_refind(dir);
     if (argc > 2 && std::string(argv[2]) == "addkf") return run_add_keyframe(dir);
+    if (argc > 2 && std::string(argv[2]) == "loop") return run_loop(dir);
     auto cams = rd<double>(dir, "mm_cams.f64");
     auto fixed = rd<int32_t>(dir, "mm_fixed.i32");
     auto pts = rd<double>(dir, "mm_pts.f64");

@@ -383,3 +383,59 @@ def test_bundle_adjust_matches_the_reference_itself(orc_libm_binary, tmp_path, m
     assert np.array_equal(got["never"], o_never[:int(o_nn[0])])
     assert np.array_equal(got["flags"], o_flags)
     assert not np.array_equal(o_pts, pts)   # the adjustment did move the map
+
+
+def _loop_case(tmp_path):
+    """Inputs for `mapmaker_check <dir> loop`: a two-keyframe map, a short sequence, the frame that becomes a keyframe."""
+    import numpy as np
+    from ptam_cg_b200 import synth
+    from ptam_cg_b200.capi import Tracker
+    from oracle.binding import detect_with
+    W, H, first, nfr, hand_over = 320, 240, 2, 8, 3
+    frames, poses = synth.render_sequence(W, H, 16)
+    cam = synth.AtanCamera(W, H)
+    kf_idx = (0, 12)
+    kfs, m = synth.build_map(frames, poses, detect_with(Tracker, oracle_lib(), W, H), cam, kf_indices=kf_idx, per_level=(150, 80, 40, 20))
+    n = len(m["src_kf"])
+    np.array([W, H, len(kfs), n, nfr, hand_over], np.int32).tofile(tmp_path / "trk_dims.i32")
+    np.ascontiguousarray(np.stack(kfs), np.uint8).tofile(tmp_path / "trk_kf.u8")
+    np.ascontiguousarray([poses[i] for i in kf_idx], np.float64).tofile(tmp_path / "ak_kf_poses.f64")
+    np.ascontiguousarray(frames[first:first + nfr], np.uint8).tofile(tmp_path / "trk_frames.u8")
+    for name, key, dt in (("trk_world.f64", "world_pos", np.float64), ("trk_right.f64", "pixel_right_w", np.float64),
+                          ("trk_down.f64", "pixel_down_w", np.float64), ("trk_srckf.i32", "src_kf", np.int32),
+                          ("trk_srclevel.i32", "src_level", np.int32), ("trk_center.i32", "ir_center", np.int32)):
+        np.ascontiguousarray(m[key], dt).tofile(tmp_path / name)
+    np.ascontiguousarray(synth.perturb_pose(poses[first], np.random.default_rng(3)), np.float64).tofile(tmp_path / "trk_pose0.f64")
+    return n, nfr, hand_over, [poses[first + i] for i in range(nfr)], m
+
+
+def _check_loop(tmp_path, n, nfr, hand_over, truth, m):
+    import numpy as np
+    from ptam_cg_b200 import synth
+    poses = np.fromfile(tmp_path / "loop_out_poses.f64").reshape(nfr, 12)
+    found = np.fromfile(tmp_path / "loop_out_found.i32", np.int32)
+    new_pts, kf_meas, refound, n_points, n_kfs, reset, converged, n_bad, queue = np.fromfile(tmp_path / "loop_out_info.i32", np.int32)
+    for f in range(nfr):   # the tracker follows the ground truth throughout, before and after the map grew
+        assert np.abs(poses[f][9:] - synth.se3_from12(truth[f])[1]).max() < 5e-3, f
+    assert new_pts > 50 and n_points == n + new_pts and n_kfs == 3
+    assert kf_meas >= found[hand_over] + new_pts          # the tracker's measurements + re-found ones + the new points' roots
+    assert found[hand_over + 1:].min() > found[:hand_over + 1].max() + new_pts // 2   # the new points are tracked at once
+    # (with three keyframes most points have two measurements, and an outlier measurement of such a point makes it
+    # bad, MapMaker.cc:919-920: a quarter of this young map goes that way under the Tukey estimator)
+    assert refound > 20 and reset == 0 and queue >= 0 and n_bad < n_points // 2
+    before = np.fromfile(tmp_path / "loop_out_before_ba.f64").reshape(n_points, 3)
+    after = np.fromfile(tmp_path / "loop_out_after_ba.f64").reshape(n_points, 3)
+    assert np.isfinite(after).all() and not np.array_equal(before, after)      # the adjustment ran and moved the map ...
+    assert np.abs(after - before).max() < 0.05                                  # ... a little: it was consistent already
+    # the planar scene: every point, old and new, sits on z = 0 (the new ones were triangulated, not intersected)
+    assert np.abs(after[:, 2]).mean() < 5e-3
+    assert np.array_equal(np.fromfile(tmp_path / "loop_out_kf0.f64"), np.fromfile(tmp_path / "ak_kf_poses.f64")[:12])  # gauge
+
+
+def test_tracker_and_mapmaker_loop(orc_binary, tmp_path):
+    """Both mirrors in the reference's loop: track, hand a keyframe to the map maker, track on with the enlarged map,
+    re-find the new points, bundle-adjust everything (see run_loop in host/mapmaker_check.cc)."""
+    case = _loop_case(tmp_path)
+    r = subprocess.run([str(orc_binary), str(tmp_path), "loop"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    _check_loop(tmp_path, *case)

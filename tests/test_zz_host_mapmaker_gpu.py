@@ -93,3 +93,15 @@ def test_add_keyframe_from_top_of_queue_on_the_device(product, tmp_path):
     r = subprocess.run([str(HOST / "mapmaker_check"), str(tmp_path), "addkf"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     _check_add_keyframe(tmp_path, *case, tol=1e-9)
+
+
+def test_tracker_and_mapmaker_loop_on_the_device(product, tmp_path):
+    """Both host mirrors in the reference's loop with the CUDA library behind them (track, hand a keyframe over, new
+    points by epipolar search, track on, re-find, bundle-adjust): same invariants as the CPU twin."""
+    from test_host_mapmaker_cpu import _loop_case, _check_loop
+    r = subprocess.run(["make", "-C", str(HOST)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    case = _loop_case(tmp_path)
+    r = subprocess.run([str(HOST / "mapmaker_check"), str(tmp_path), "loop"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    _check_loop(tmp_path, *case)
