@@ -60,6 +60,7 @@ struct Stream {
   std::unique_ptr<KeyFrame> refind_kf;
   ptam_track_result res;
   bool refind_mode = false;
+  bool keep_queue = false;   // test hook: let the tracker's keyframes pile up in MapMaker::mvpKeyFrameQueue
 };
 struct Handle {
   int W = 0, H = 0, S = 0;
@@ -244,7 +245,7 @@ int ref_tracker_track_frames(void* hp, const uint8_t* const* images, int stride,
     Stream& st = *h->streams[s];
     RefTracker& t = *st.trk;
     st.refind_mode = false;
-    st.mm->mvpKeyFrameQueue.clear();  // keyframes the tracker hands to the (absent) map-maker thread are dropped
+    if (!st.keep_queue) st.mm->mvpKeyFrameQueue.clear();  // keyframes the tracker hands to the (absent) map-maker thread are dropped
     CVD::Image<CVD::byte> im = wrap_image(images[s], h->W, h->H, stride);
     const int lost_before = t.mnLostFrames;
     t.TrackFrame(im, false);
@@ -305,6 +306,20 @@ int ref_tracker_refind_in_keyframes(void* hp, const uint8_t* const* images, int 
 // the stream's current frame.  The new MapPoint the reference creates is read (sub-pixel target
 // position = kTarget.mMeasurements[pNew].v2RootPos, triangulated v3WorldPos) and removed again.
 // NB the reference caches UnProject of every pixel in a function-local static sized by the first call.
+// Test hook (not part of the shared ABI): the stream's map maker as the reference's tracker sees it — sets
+// MapMaker::mdWiggleScale (wiggle_scale >= 0; the wrapper otherwise keeps it at 1e30 so that the distance branch of
+// Tracker::AssessTrackingQuality never fires), optionally drops the keyframes the tracker queued (clear_queue: 1 once,
+// 2 once and keep the queue across frames from now on, 3 back to dropping it every frame), returns MapMaker::QueueSize().
+int ref_tracker_mapmaker_ctl(void* hp, int stream, double wiggle_scale, int clear_queue) {
+  Handle* h = (Handle*)hp;
+  if (stream < 0 || stream >= h->S) return PTAM_ERR_INVALID;
+  Stream& st = *h->streams[stream];
+  if (wiggle_scale >= 0) st.mm->mdWiggleScale = wiggle_scale;
+  if (clear_queue) { for (KeyFrame* k : st.mm->mvpKeyFrameQueue) delete k; st.mm->mvpKeyFrameQueue.clear(); }
+  if (clear_queue == 2) st.keep_queue = true;    // ... and from now on keep what the tracker queues
+  if (clear_queue == 3) st.keep_queue = false;
+  return st.mm->QueueSize();
+}
 // Test hook (not part of the shared ABI): the reference's own MapMaker::BundleAdjustAll / BundleAdjustRecent
 // (MapMaker.cc:767-933) on a map given as arrays: keyframes (pose, fixed), points, measurements (keyframe, point, root
 // position, level, Source).  Keyframes and points live in arrays, so pointer order = index order, as in

@@ -252,6 +252,15 @@ class MapMaker {
     return out;
   }
 
+  int QueueSize() const { return (int)mvpKeyFrameQueue.size(); }   // MapMaker.h:52
+  double GetWiggleScale() const { return mdWiggleScale; }           // MapMaker.h:57
+
+  // MapMaker.cc:754-764: is the camera far enough from every keyframe, relative to the scene depth, for a new one?
+  bool IsNeedNewKeyFrame(KeyFrame& kCurrent) {
+    const double dist = KeyFrameLinearDist(kCurrent, *ClosestKeyFrame(kCurrent)) * (1.0 / kCurrent.dSceneDepthMean);
+    return dist > mdMaxKFDistWiggleMult * mdWiggleScaleDepthNormalized;
+  }
+
   // MapMaker.cc:738-752: the keyframe of the map nearest to k (not k itself)
   KeyFrame* ClosestKeyFrame(KeyFrame& k) {
     KeyFrame* best = nullptr;
@@ -431,6 +440,8 @@ class MapMaker {
   std::vector<MapPoint*> mvpNewQueue;  // mqNewQueue (MapMaker.h:130): points waiting to be re-found in older keyframes
   std::vector<KeyFrame*> mvpKeyFrameQueue;   // keyframes from the tracker waiting to be processed (MapMaker.h:128)
   double mdCandidateMinSTScore = 70.0;       // MapMaker.CandidateMinShiTomasiScore (KeyFrame.cc:63)
+  double mdWiggleScaleDepthNormalized = 0.1; // mdWiggleScale / the first keyframe's scene depth (MapMaker.cc:392)
+  double mdMaxKFDistWiggleMult = 0.05;       // MapMaker.MaxKFDistWiggleMult (MapMaker.cc:760)
   double mdWiggleScale = 0.1;          // MapMaker.WiggleScale (MapMaker.cc:225), the stereo baseline in map units
 
  private:

@@ -7,6 +7,7 @@
 #pragma once
 #include <map>
 #include "KeyFrame.h"
+#include "MapMaker.h"
 
 namespace ptam_b200 {
 
@@ -36,7 +37,14 @@ class Tracker {
     mCurrentKF.dSceneDepthMean = mLast.scene_depth_mean;
     mCurrentKF.dSceneDepthSigma = mLast.scene_depth_sigma;
     mbKFCurrent = false;
+    mnFrame++;
+    if (mpMapMaker && mMap.IsGood() && mLast.recovery == 0) ConsultMapMaker();
   }
+
+  // reference: the fourth constructor argument (MapMaker &mm).  With a map maker attached TrackFrame also does
+  // the two things the reference's tracker asks it for: the last branch of AssessTrackingQuality
+  // (Tracker.cc:1094-1099) and the keyframe hand-over heuristic (Tracker.cc:146-166).
+  void SetMapMaker(MapMaker* mm) { mpMapMaker = mm; }
   TooN::SE3<> GetCurrentPose() { return mse3CamFromWorld; }
 
   // Sets mse3CamFromWorld (and zero velocity) — what the reference does after stereo initialisation
@@ -101,15 +109,55 @@ class Tracker {
     }
     if (ptam_tracker_set_map(h, 0, (int)n, world.data(), right.data(), down.data(), kf.data(), lvl.data(), ctr.data()) != PTAM_OK)
       throw std::runtime_error(ptam_tracker_last_error(h));
+    // every keyframe of the map with its current pose: what the relocaliser compares a lost frame against
+    // (Relocaliser.cc:12-38 walks mMap.vpKeyFrames); bundle adjustment moves the poses, a revision bump brings them here
+    for (KeyFrame* k : mMap.vpKeyFrames) {
+      auto it = mKFIds.find(k);
+      if (it == mKFIds.end()) {
+        if (k->aLevels[0].im.size() != mirSize) continue;   // not made yet
+        const int id = ptam_tracker_add_keyframe(h, k->aLevels[0].im.data(), k->aLevels[0].im.row_stride());
+        if (id < 0) throw std::runtime_error(ptam_tracker_last_error(h));
+        it = mKFIds.emplace(k, id).first;
+      }
+      double pose[12];
+      se3_to_array(k->se3CfromW, pose);
+      if (ptam_tracker_set_keyframe_pose(h, it->second, pose) != PTAM_OK) throw std::runtime_error(ptam_tracker_last_error(h));
+    }
     mvUploaded = mMap.vpPoints;
     mnRevision = mMap.nRevision;
     mbMapUploaded = true;
+  }
+
+  void ConsultMapMaker() {
+    // AssessTrackingQuality left the quality as it was because the found fractions were inconclusive: far from
+    // every keyframe means lost (the device cannot know: the keyframe poses live with the map maker)
+    if (mLast.quality_needs_kf_distance && !mMap.vpKeyFrames.empty()) {
+      KeyFrame* closest = mpMapMaker->ClosestKeyFrame(mCurrentKF);
+      if (MapMaker::KeyFrameLinearDist(mCurrentKF, *closest) > mpMapMaker->GetWiggleScale() * 10.0) {
+        ptam_tracker_state st;
+        if (ptam_tracker_get_state(h, 0, &st) != PTAM_OK) throw std::runtime_error(ptam_tracker_last_error(h));
+        if (st.tracking_quality != 0) {   // BAD now: the first lost frame (mnLostFrames was reset while the quality was not BAD)
+          st.tracking_quality = 0;
+          st.lost_frames = 1;
+          if (ptam_tracker_set_state(h, 0, &st) != PTAM_OK) throw std::runtime_error(ptam_tracker_last_error(h));
+        }
+        mLast.tracking_quality = 0;
+      }
+    }
+    // a good, well-separated frame becomes a keyframe unless the map maker is already behind (isNeedFrame is
+    // computed but not used by the reference, Tracker.cc:160)
+    if (mLast.tracking_quality == 2 && mnFrame - mnLastKeyFrameDropped > 20 && mpMapMaker->QueueSize() < 3) {
+      mpMapMaker->AddKeyFrame(CurrentKeyFrame());
+      mnLastKeyFrameDropped = mnFrame;
+    }
   }
 
   Map& mMap;
   ATANCamera mCamera;
   CVD::ImageRef mirSize;
   ptam_tracker* h = nullptr;
+  MapMaker* mpMapMaker = nullptr;
+  int mnFrame = 0, mnLastKeyFrameDropped = -20;   // Tracker.cc:62-63
   KeyFrame mCurrentKF;
   TooN::SE3<> mse3CamFromWorld;
   ptam_track_result mLast{};

@@ -369,14 +369,75 @@ static int run_loop(const std::string& dir) {
   return 0;
 }
 
+// The tracker with a map maker attached: per frame the tracking quality and lost-frame counter after the last branch
+// of Tracker::AssessTrackingQuality (Tracker.cc:1094-1099), and the map maker's queue after the keyframe hand-over
+// heuristic (Tracker.cc:146-166).
+static int run_heuristics(const std::string& dir) {
+  auto dims = rd<int32_t>(dir, "trk_dims.i32");  // W, H, n_kf, n_pts, n_frames
+  const int W = dims[0], H = dims[1], nkf = dims[2], npts = dims[3], nfr = dims[4];
+  auto kfim = rd<uint8_t>(dir, "trk_kf.u8");
+  auto kfpose = rd<double>(dir, "ak_kf_poses.f64");
+  auto frames = rd<uint8_t>(dir, "trk_frames.u8");
+  auto world = rd<double>(dir, "trk_world.f64");
+  auto right = rd<double>(dir, "trk_right.f64");
+  auto down = rd<double>(dir, "trk_down.f64");
+  auto skf = rd<int32_t>(dir, "trk_srckf.i32");
+  auto slv = rd<int32_t>(dir, "trk_srclevel.i32");
+  auto ctr = rd<int32_t>(dir, "trk_center.i32");
+  auto pose0 = rd<double>(dir, "trk_pose0.f64");
+  auto hp = rd<double>(dir, "hq_params.f64");  // TrackingQualityGood, TrackingQualityLost, wiggle scale
+  ATANCamera cam("Camera", makeVector(1.0803, 1.43987, 0.519983, 0.548655, 0.244943), CVD::ImageRef(W, H));
+  Map map;
+  std::vector<KeyFrame> kfs(nkf);
+  std::vector<MapPoint> points(npts);
+  for (int k = 0; k < nkf; k++) {
+    CVD::BasicImage<CVD::byte> im(kfim.data() + (size_t)k * W * H, CVD::ImageRef(W, H));
+    kfs[k].MakeKeyFrame_Lite(im);
+    kfs[k].se3CfromW = se3_from_array(&kfpose[12 * k]);
+    map.vpKeyFrames.push_back(&kfs[k]);
+  }
+  for (int i = 0; i < npts; i++) {
+    MapPoint& p = points[i];
+    p.v3WorldPos = makeVector(world[3 * i], world[3 * i + 1], world[3 * i + 2]);
+    p.v3PixelRight_W = makeVector(right[3 * i], right[3 * i + 1], right[3 * i + 2]);
+    p.v3PixelDown_W = makeVector(down[3 * i], down[3 * i + 1], down[3 * i + 2]);
+    p.pPatchSourceKF = &kfs[skf[i]];
+    p.nSourceLevel = slv[i];
+    p.irCenter = CVD::ImageRef(ctr[2 * i], ctr[2 * i + 1]);
+    map.vpPoints.push_back(&p);
+  }
+  map.bGood = true; map.nRevision++;
+  MapMaker mm(map, cam);
+  mm.mdWiggleScale = hp[2];
+  ptam_tracker_params prm;
+  ptam_tracker_default_params(&prm);
+  prm.quality_good = hp[0]; prm.quality_lost = hp[1];
+  Tracker trk(CVD::ImageRef(W, H), cam, map, 0, &prm);
+  trk.SetMapMaker(&mm);
+  trk.SetCurrentPose(se3_from_array(pose0.data()));
+  std::vector<int32_t> out;
+  CVD::Image<CVD::byte> frame(CVD::ImageRef(W, H));
+  for (int f = 0; f < nfr; f++) {
+    std::memcpy(frame.data(), frames.data() + (size_t)f * W * H, (size_t)W * H);
+    trk.TrackFrame(frame, false);
+    ptam_tracker_state st;
+    ptam_tracker_get_state(trk.handle(), 0, &st);
+    out.insert(out.end(), {st.tracking_quality, st.lost_frames, mm.QueueSize(), trk.LastResult().quality_needs_kf_distance});
+  }
+  wr(dir, "hq_out.i32", out);
+  std::printf("heuristics: %d frames, %d keyframes queued\n", nfr, mm.QueueSize());
+  return 0;
+}
+
 int main(int argc, char** argv) {
-  if (argc < 2) { std::cerr << "usage: mapmaker_check <dir> [ba|epi|refind|addkf|loop]\n"; return 2; }
+  if (argc < 2) { std::cerr << "usage: mapmaker_check <dir> [ba|epi|refind|addkf|loop|heur]\n"; return 2; }
   const std::string dir = argv[1];
   try {
     if (argc > 2 && std::string(argv[2]) == "epi") return run_epipolar(dir);
     if (argc > 2 && std::string(argv[2]) == "refind") return run_refind(dir);
     if (argc > 2 && std::string(argv[2]) == "addkf") return run_add_keyframe(dir);
     if (argc > 2 && std::string(argv[2]) == "loop") return run_loop(dir);
+    if (argc > 2 && std::string(argv[2]) == "heur") return run_heuristics(dir);
     auto cams = rd<double>(dir, "mm_cams.f64");
     auto fixed = rd<int32_t>(dir, "mm_fixed.i32");
     auto pts = rd<double>(dir, "mm_pts.f64");

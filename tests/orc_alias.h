@@ -28,6 +28,7 @@
 #define ptam_tracker_default_params orc_tracker_default_params
 #define ptam_tracker_add_keyframe orc_tracker_add_keyframe
 #define ptam_tracker_set_map orc_tracker_set_map
+#define ptam_tracker_set_keyframe_pose orc_tracker_set_keyframe_pose
 #define ptam_tracker_set_state orc_tracker_set_state
 #define ptam_tracker_get_state orc_tracker_get_state
 #define ptam_tracker_get_points orc_tracker_get_points

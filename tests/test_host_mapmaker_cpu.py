@@ -439,3 +439,86 @@ def test_tracker_and_mapmaker_loop(orc_binary, tmp_path):
     r = subprocess.run([str(orc_binary), str(tmp_path), "loop"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     _check_loop(tmp_path, *case)
+
+
+@pytest.mark.parametrize("params", [(0.3, 0.13, 0.1), (0.999, 0.0, 0.0005), (0.999, 0.0, 0.5)],
+                         ids=["defaults-keyframe-drops", "far-from-keyframes-lost", "inconclusive-but-near"])
+def test_tracker_consults_the_map_maker_like_the_reference(orc_libm_binary, tmp_path, params):
+    """With a map maker attached the Tracker mirror also runs the last branch of AssessTrackingQuality
+    (Tracker.cc:1094-1099: far from every keyframe = lost) and the keyframe hand-over heuristic (Tracker.cc:146-166).
+    Against the reference's OWN Tracker + MapMaker (oracle/_ref; hook ref_tracker_mapmaker_ctl sets mdWiggleScale and
+    reads QueueSize): tracking quality, lost-frame counter and queue length after every frame must be equal.
+    Parameter sets: the defaults (quality good: keyframes are dropped at frames 1, 22, 43 until three wait); a
+    quality threshold nothing reaches with a tiny / a large wiggle scale (the distance branch decides every frame)."""
+    import ctypes as C
+    import numpy as np
+    from ptam_cg_b200 import synth
+    from ptam_cg_b200.capi import Tracker
+    from oracle.binding import detect_with, ref_lib
+    ref = ref_lib()
+    if ref is None or not hasattr(ref.cdll, "ref_tracker_mapmaker_ctl"):
+        pytest.skip("oracle/_ref not built")
+    good, lost, wiggle = params
+    W, H, first, nfr, frames, poses, kf_idx, kfs, m, pose0 = _heuristics_case(tmp_path, params)
+    r = subprocess.run([str(orc_libm_binary), str(tmp_path), "heur"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = np.fromfile(tmp_path / "hq_out.i32", np.int32).reshape(nfr, 4)
+    _check_heuristics_against_reference(ref, params, W, H, first, nfr, frames, poses, kf_idx, kfs, m, pose0, got)
+
+
+def _heuristics_case(tmp_path, params):
+    import numpy as np
+    from ptam_cg_b200 import synth
+    from ptam_cg_b200.capi import Tracker
+    from oracle.binding import detect_with
+    good, lost, wiggle = params
+    W, H, first, nfr = 320, 240, 1, 46
+    frames, poses = synth.render_sequence(W, H, 48)
+    cam = synth.AtanCamera(W, H)
+    kf_idx = (0, 40)
+    kfs, m = synth.build_map(frames, poses, detect_with(Tracker, oracle_lib(), W, H), cam, kf_indices=kf_idx, per_level=(150, 80, 40, 20))
+    n = len(m["src_kf"])
+    np.array([W, H, len(kfs), n, nfr], np.int32).tofile(tmp_path / "trk_dims.i32")
+    np.ascontiguousarray(np.stack(kfs), np.uint8).tofile(tmp_path / "trk_kf.u8")
+    np.ascontiguousarray([poses[i] for i in kf_idx], np.float64).tofile(tmp_path / "ak_kf_poses.f64")
+    np.ascontiguousarray(frames[first:first + nfr], np.uint8).tofile(tmp_path / "trk_frames.u8")
+    for name, key, dt in (("trk_world.f64", "world_pos", np.float64), ("trk_right.f64", "pixel_right_w", np.float64),
+                          ("trk_down.f64", "pixel_down_w", np.float64), ("trk_srckf.i32", "src_kf", np.int32),
+                          ("trk_srclevel.i32", "src_level", np.int32), ("trk_center.i32", "ir_center", np.int32)):
+        np.ascontiguousarray(m[key], dt).tofile(tmp_path / name)
+    pose0 = synth.perturb_pose(poses[first], np.random.default_rng(3))
+    np.ascontiguousarray(pose0, np.float64).tofile(tmp_path / "trk_pose0.f64")
+    np.array([good, lost, wiggle], np.float64).tofile(tmp_path / "hq_params.f64")
+    return W, H, first, nfr, frames, poses, kf_idx, kfs, m, pose0
+
+
+def _check_heuristics_against_reference(ref, params, W, H, first, nfr, frames, poses, kf_idx, kfs, m, pose0, got):
+    import ctypes as C
+    import numpy as np
+    from ptam_cg_b200.capi import Tracker
+    good, lost, wiggle = params
+    # ---- the reference's own tracker and map maker
+    t = Tracker(ref, W, H, 1, quality_good=good, quality_lost=lost)
+    ctl = ref.cdll.ref_tracker_mapmaker_ctl
+    ctl.restype = C.c_int
+    for k, im in enumerate(kfs):
+        t.add_keyframe(im)
+        pk = np.ascontiguousarray(poses[kf_idx[k]], np.float64)
+        assert ref.cdll.ref_tracker_set_keyframe_pose(C.c_void_p(t.h), k, pk.ctypes.data_as(C.POINTER(C.c_double))) == 0
+    t.set_map(0, m)
+    t.set_state(0, pose12=pose0, velocity=np.zeros(6), msd=0.0)
+    assert ctl(C.c_void_p(t.h), 0, C.c_double(wiggle), 2) == 0   # keep the queue: no map-maker thread drains it here
+    exp = []
+    for f in range(nfr):
+        t.track_frames([frames[first + f]])
+        st = t.get_state(0)
+        exp.append((st.tracking_quality, st.lost_frames, ctl(C.c_void_p(t.h), 0, C.c_double(-1.0), 0)))
+    exp = np.array(exp, np.int32)
+    ctl(C.c_void_p(t.h), 0, C.c_double(1e30), 3)
+    assert np.array_equal(got[:, :3], exp), (got[:8], exp[:8])
+    if good < 0.5:
+        assert list(np.flatnonzero(np.diff(np.r_[0, got[:, 2]]))) == [0, 21, 42] and got[-1, 2] == 3   # frames 1, 22, 43
+    elif wiggle < 0.01:
+        assert got[:, 3].sum() > 0 and got[:, 1].max() >= 1      # the distance branch fired and declared the tracker lost
+    else:
+        assert got[:, 3].sum() > 0 and (got[:, 0] == 2).all() and (got[:, 1] == 0).all() and got[0, 2] == 1

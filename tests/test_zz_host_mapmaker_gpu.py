@@ -105,3 +105,24 @@ def test_tracker_and_mapmaker_loop_on_the_device(product, tmp_path):
     r = subprocess.run([str(HOST / "mapmaker_check"), str(tmp_path), "loop"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     _check_loop(tmp_path, *case)
+
+
+def test_tracker_consults_the_map_maker_on_the_device(product, tmp_path):
+    """The Tracker mirror with a map maker attached and the CUDA library behind it: tracking quality, lost-frame
+    counter and keyframe queue after every frame, against the reference's OWN Tracker + MapMaker (oracle/_ref), with
+    the default thresholds (discrete outcomes far from their thresholds on this sequence)."""
+    import numpy as np
+    from oracle.binding import ref_lib
+    from test_host_mapmaker_cpu import _heuristics_case, _check_heuristics_against_reference
+    ref = ref_lib()
+    if ref is None or not hasattr(ref.cdll, "ref_tracker_mapmaker_ctl"):
+        pytest.skip("oracle/_ref not present")
+    r = subprocess.run(["make", "-C", str(HOST)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    params = (0.3, 0.13, 0.1)
+    case = _heuristics_case(tmp_path, params)
+    nfr = case[3]
+    r = subprocess.run([str(HOST / "mapmaker_check"), str(tmp_path), "heur"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = np.fromfile(tmp_path / "hq_out.i32", np.int32).reshape(nfr, 4)
+    _check_heuristics_against_reference(ref, params, *case, got)
