@@ -148,6 +148,12 @@ struct MapPoint {  // Map.h:46-98 (the fields the tracker and the map maker's ho
 
 struct Map {  // Map.h:28-44
   std::vector<MapPoint*> vpPoints;
+  std::vector<MapPoint*> vpPointsTrash;
+  // Map.cc:20-30 (whoever owns the points empties the trash: the tracker may still hold a pointer for a frame)
+  void MoveBadPointsToTrash() {
+    for (int i = (int)vpPoints.size() - 1; i >= 0; i--)
+      if (vpPoints[i]->bBad) { vpPointsTrash.push_back(vpPoints[i]); vpPoints.erase(vpPoints.begin() + i); nRevision++; }
+  }
   std::vector<KeyFrame*> vpKeyFrames;
   bool bGood = false;
   // bumped by whoever edits vpPoints / point geometry, so that the Tracker re-uploads the map

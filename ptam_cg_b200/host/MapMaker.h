@@ -332,6 +332,30 @@ class MapMaker {
     mbBundleConverged_Recent = false;
   }
 
+  // MapMaker.cc:131-153: points the tracker's M-estimator rejected more often than not become bad; every bad
+  // point loses its measurements and leaves the map
+  void HandleBadPoints() {
+    for (MapPoint* p : mMap.vpPoints)
+      if (p->nMEstimatorOutlierCount > 20 && p->nMEstimatorOutlierCount > p->nMEstimatorInlierCount) p->bBad = true;
+    for (MapPoint* p : mMap.vpPoints)
+      if (p->bBad)
+        for (KeyFrame* kf : mMap.vpKeyFrames) kf->mMeasurements.erase(p);
+    mMap.MoveBadPointsToTrash();
+  }
+
+  // One pass of the map-maker thread's priority list (MapMaker::run, MapMaker.cc:83-116), for callers without the
+  // reference's thread.  The reference gives the failure queue its second chance on a 1-in-20 draw of rand();
+  // here the caller decides.
+  void RunOnce(bool bRefindFailures = false) {
+    if (!mMap.IsGood()) return;
+    if (!mbBundleConverged_Recent && QueueSize() == 0) BundleAdjustRecent();
+    if (mbBundleConverged_Recent && QueueSize() == 0) ReFindNewlyMade();
+    if (mbBundleConverged_Recent && !mbBundleConverged_Full && QueueSize() == 0) BundleAdjustAll();
+    if (mbBundleConverged_Recent && mbBundleConverged_Full && bRefindFailures && QueueSize() == 0) ReFindFromFailureQueue();
+    HandleBadPoints();
+    if (QueueSize() > 0) AddKeyFrameFromTopOfQueue();
+  }
+
   // MapMaker.cc:767-782: every keyframe, every point
   void BundleAdjustAll() {
     std::set<KeyFrame*> adjust, fixed;

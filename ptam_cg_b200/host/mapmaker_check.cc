@@ -351,15 +351,35 @@ static int run_loop(const std::string& dir) {
       info.push_back((int32_t)map.vpKeyFrames.back()->mMeasurements.size());
     }
   }
-  const int nRefound = mm.ReFindNewlyMade();
+  // the map-maker thread's priority list until it has nothing left to do (MapMaker::run): with fewer than eight
+  // keyframes the local adjustment is skipped, the new points are re-found in the older keyframes, the whole map is
+  // adjusted (again and again until it converges), outlier measurements get their second chance, bad points leave
+  const std::vector<MapPoint*> all_points = map.vpPoints;   // before any of them is moved to the trash
   std::vector<double> before_ba;
-  for (MapPoint* p : map.vpPoints) for (int k = 0; k < 3; k++) before_ba.push_back(p->v3WorldPos[k]);
-  mm.BundleAdjustAll();
+  for (MapPoint* p : all_points) for (int k = 0; k < 3; k++) before_ba.push_back(p->v3WorldPos[k]);
+  const size_t new_queue = mm.mvpNewQueue.size();
+  int passes = 0;
+  do { mm.RunOnce(true); passes++; } while (passes < 12 && !(mm.mbBundleConverged_Full && mm.mbBundleConverged_Recent && mm.QueueSize() == 0));
   std::vector<double> after_ba;
-  int nBad = 0;
-  for (MapPoint* p : map.vpPoints) { for (int k = 0; k < 3; k++) after_ba.push_back(p->v3WorldPos[k]); nBad += p->bBad; }
-  info.insert(info.end(), {nRefound, (int32_t)map.vpPoints.size(), (int32_t)map.vpKeyFrames.size(), mm.mbResetRequested ? 1 : 0,
-                           mm.mbBundleConverged_Full ? 1 : 0, nBad, (int32_t)mm.mvFailureQueue.size()});
+  int nBad = 0, nDangling = 0;
+  for (MapPoint* p : all_points) { for (int k = 0; k < 3; k++) after_ba.push_back(p->v3WorldPos[k]); nBad += p->bBad; }
+  for (MapPoint* p : map.vpPoints) nDangling += p->bBad;                       // a bad point still in the map
+  for (KeyFrame* kf : map.vpKeyFrames)
+    for (auto& pm : kf->mMeasurements) nDangling += pm.first->bBad;            // a measurement of a point that left
+  const int nRefound = (int)new_queue - (int)mm.mvpNewQueue.size();
+  info.insert(info.end(), {nRefound, (int32_t)all_points.size(), (int32_t)map.vpKeyFrames.size(), mm.mbResetRequested ? 1 : 0,
+                           mm.mbBundleConverged_Full ? 1 : 0, nBad, (int32_t)mm.mvFailureQueue.size(), passes, nDangling,
+                           (int32_t)map.vpPoints.size(), (int32_t)map.vpPointsTrash.size()});
+  // and the tracker carries on with the cleaned-up, adjusted map
+  std::memcpy(frame.data(), frames.data() + (size_t)(nfr - 1) * W * H, (size_t)W * H);
+  trk.TrackFrame(frame, false);
+  {
+    double a[12];
+    se3_to_array(trk.GetCurrentPose(), a);
+    poses.insert(poses.end(), a, a + 12);
+    const ptam_track_result& r = trk.LastResult();
+    found.push_back(r.meas_found[0] + r.meas_found[1] + r.meas_found[2] + r.meas_found[3]);
+  }
   std::vector<double> kf0(12);
   se3_to_array(kfs[0].se3CfromW, kf0.data());
   wr(dir, "loop_out_poses.f64", poses); wr(dir, "loop_out_found.i32", found); wr(dir, "loop_out_info.i32", info);

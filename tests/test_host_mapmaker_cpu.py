@@ -412,17 +412,23 @@ def _loop_case(tmp_path):
 def _check_loop(tmp_path, n, nfr, hand_over, truth, m):
     import numpy as np
     from ptam_cg_b200 import synth
-    poses = np.fromfile(tmp_path / "loop_out_poses.f64").reshape(nfr, 12)
+    poses = np.fromfile(tmp_path / "loop_out_poses.f64").reshape(nfr + 1, 12)
     found = np.fromfile(tmp_path / "loop_out_found.i32", np.int32)
-    new_pts, kf_meas, refound, n_points, n_kfs, reset, converged, n_bad, queue = np.fromfile(tmp_path / "loop_out_info.i32", np.int32)
+    (new_pts, kf_meas, refound, n_points, n_kfs, reset, converged, n_bad, queue, passes, dangling, n_live,
+     n_trash) = np.fromfile(tmp_path / "loop_out_info.i32", np.int32)
     for f in range(nfr):   # the tracker follows the ground truth throughout, before and after the map grew
         assert np.abs(poses[f][9:] - synth.se3_from12(truth[f])[1]).max() < 5e-3, f
+    # MapMaker::RunOnce until the thread's priority list is empty: converged, bad points gone with their measurements
+    assert converged == 1 and passes < 12 and dangling == 0 and n_live + n_trash == n_points and n_trash == n_bad
+    # ... and the tracker re-tracks the last frame on the adjusted, cleaned-up map (it was re-uploaded)
+    assert np.abs(poses[nfr][9:] - synth.se3_from12(truth[nfr - 1])[1]).max() < 5e-3 and found[nfr] > 0.5 * found[nfr - 1]
+    found = found[:nfr]
     assert new_pts > 50 and n_points == n + new_pts and n_kfs == 3
     assert kf_meas >= found[hand_over] + new_pts          # the tracker's measurements + re-found ones + the new points' roots
     assert found[hand_over + 1:].min() > found[:hand_over + 1].max() + new_pts // 2   # the new points are tracked at once
     # (with three keyframes most points have two measurements, and an outlier measurement of such a point makes it
     # bad, MapMaker.cc:919-920: a quarter of this young map goes that way under the Tukey estimator)
-    assert refound > 20 and reset == 0 and queue >= 0 and n_bad < n_points // 2
+    assert refound == new_pts and reset == 0 and queue == 0 and n_bad < n_points // 2   # the new-point queue was worked off
     before = np.fromfile(tmp_path / "loop_out_before_ba.f64").reshape(n_points, 3)
     after = np.fromfile(tmp_path / "loop_out_after_ba.f64").reshape(n_points, 3)
     assert np.isfinite(after).all() and not np.array_equal(before, after)      # the adjustment ran and moved the map ...
