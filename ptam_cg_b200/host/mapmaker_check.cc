@@ -89,11 +89,11 @@ static int run_epipolar(const std::string& dir) {
       std::vector<int32_t> r3 = {nRefound, (int32_t)mm.mvpNewQueue.size()};
       std::vector<double> p3;
       for (MapPoint* p : map.vpPoints) {
-        auto it = k3.mMeasurements.find(p);
-        const bool has = it != k3.mMeasurements.end();
-        r3.push_back(has ? 1 : 0); r3.push_back(has ? it->second.nLevel : -1);
+        auto m3 = k3.mMeasurements.find(p);
+        const bool has = m3 != k3.mMeasurements.end();
+        r3.push_back(has ? 1 : 0); r3.push_back(has ? m3->second.nLevel : -1);
         r3.push_back((int32_t)mm.MMData(p).sNeverRetryKFs.count(&k3)); r3.push_back(mm.MMData(p).GoodMeasCount());
-        p3.push_back(has ? it->second.v2RootPos[0] : 0.0); p3.push_back(has ? it->second.v2RootPos[1] : 0.0);
+        p3.push_back(has ? m3->second.v2RootPos[0] : 0.0); p3.push_back(has ? m3->second.v2RootPos[1] : 0.0);
       }
       wr(dir, "epi_out_third.i32", r3); wr(dir, "epi_out_third_pos.f64", p3);
       std::printf("epipolar: %d of the new points re-found in the third keyframe\n", nRefound);
