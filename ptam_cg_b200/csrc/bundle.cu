@@ -4,6 +4,7 @@
 // lambda trial (new error, squared update) to take the accept / reject / converge decisions exactly
 // where the reference takes them; everything else stays on the device.
 #include "bundle_kernels.cuh"
+#include "ldlt.h"
 
 #include <dlfcn.h>
 #include <nccl.h>  // types and enums only: the symbols are resolved with dlopen (torch's bundled
@@ -79,9 +80,8 @@ struct Buf {
 
 struct ptam_bundle {
   int device = 0;
-  cudaStream_t stream = nullptr, stream2 = nullptr;
-  std::vector<cudaEvent_t> ev_panel, ev_tail;
-  std::vector<char> tail_of;  // panel k launched a tail update
+  cudaStream_t stream = nullptr;
+  LdltSolver ldlt;
   std::string err;
   int64_t launches = 0;
   ptam_bundle_params prm{};
@@ -99,8 +99,10 @@ struct ptam_bundle {
   // device
   BundleDev d{};
   Buf<double> cam_se3, cam_se3_new, U, epsA, pt_pos, pt_pos_new, V, epsB, Vinv, Ve, m_found, m_sin, m_v3cam, m_derivs,
-      m_eps, m_e2, m_W, e2c, S, vE, upd, scal, Wp;
-  Buf<int> cam_fixed, cam_row, pt_off, pt_meas, m_cam, m_pt, m_state, counters, outliers;
+      m_eps, m_e2, m_W, m_B, e2c, S, vE, upd, scal, Wp, err_cam, partials;
+  Buf<int> cam_fixed, cam_row, pt_off, pt_meas, pt_meas_ins, pt_cam, cam_off, cam_meas_ins, cam_meas_pt, blk_off, blk_cnt, pr_mj, pr_mk, nz_blocks, pair_info, free_cam,
+      m_cam, m_pt, m_state, counters, outliers;
+  Buf<unsigned> tickets;
   double* h_scal = nullptr;  // pinned
   int* h_cnt = nullptr;      // pinned
   // multi-GPU shard: points [p_lo, p_hi) and their measurements live here; cameras are replicated
@@ -141,9 +143,7 @@ struct ptam_bundle {
     if (comm && own_comm) nccl_api().CommDestroy(comm);
     if (h_scal) cudaFreeHost(h_scal);
     if (h_cnt) cudaFreeHost(h_cnt);
-    for (auto e : ev_panel) cudaEventDestroy(e);
-    for (auto e : ev_tail) cudaEventDestroy(e);
-    if (stream2) cudaStreamDestroy(stream2);
+    ldlt.destroy();
     if (stream) cudaStreamDestroy(stream);
   }
 
@@ -164,14 +164,13 @@ struct ptam_bundle {
     if (dev < 0 || dev >= ndev) { set_error("bad device index"); return PTAM_ERR_INVALID; }
     PTAM_CUDA_TRY(this, cudaSetDevice(dev));
     PTAM_CUDA_TRY(this, cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    PTAM_CUDA_TRY(this, cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
     PTAM_CUDA_TRY(this, cudaMallocHost(&h_scal, 8 * sizeof(double)));
     PTAM_CUDA_TRY(this, cudaMallocHost(&h_cnt, 4 * sizeof(int)));
     if (p) prm = *p; else ptam_bundle_default_params(&prm);
     cam = ptam_make_cam_model(cam_params, w, h);
-    PTAM_CUDA_TRY(this, cudaFuncSetAttribute(k_ldlt_update, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpdateSmem));
-    PTAM_CUDA_TRY(this, cudaFuncSetAttribute(k_ldlt_step, cudaFuncAttributeMaxDynamicSharedMemorySize, kPanelSmem));
-    PTAM_CUDA_TRY(this, cudaFuncSetAttribute(k_ldlt_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPanelSmem));
+    PTAM_CUDA_TRY(this, cudaFuncSetAttribute(k_ba_acc_cam, cudaFuncAttributeMaxDynamicSharedMemorySize, kAccCamSmem));
+    PTAM_CUDA_TRY(this, cudaFuncSetAttribute(k_ba_schur_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, kSchurDiagSmem));
+    if (ldlt.init(stream) != cudaSuccess) { set_error("dense solver set-up failed: " + ldlt.err); return PTAM_ERR_CUDA; }
     return PTAM_OK;
   }
 
@@ -215,22 +214,53 @@ struct ptam_bundle {
     const std::vector<double>& v_sin = whole ? h_sin : l_sin;
     const int M = (int)l_gid.size();
     n_meas_local = M;
-    std::vector<int> off(P + 1, 0), idx(M);
+    // CSR by point.  The bucket pass is stable, so `idx` first holds every point's measurements in LIST order
+    // (the order V_i / epsB_i are summed in); the off-diagonal scripts want them by ascending camera id.  With
+    // the usual camera-major insertion (MapMaker.cc:871-882) the two orders agree and nothing is sorted.
+    std::vector<int> off(P + 1, 0), idx(M), idx_ins;
     for (int m = 0; m < M; m++) off[v_mpt[m] + 1]++;
     for (int i = 0; i < P; i++) off[i + 1] += off[i];
+    long long n_pairs_max = 0;
     {
       std::vector<int> cur(off.begin(), off.end() - 1);
       for (int m = 0; m < M; m++) idx[cur[v_mpt[m]]++] = m;
       for (int i = 0; i < P; i++) {
-        // the bucket pass is stable: with the usual camera-major insertion (MapMaker.cc:871-882) every
-        // point's list is already ascending in camera id and the sort is skipped
         bool sorted = true;
         for (int o = off[i] + 1; o < off[i + 1]; o++) if (v_mcam[idx[o]] < v_mcam[idx[o - 1]]) { sorted = false; break; }
-        if (!sorted) std::sort(idx.begin() + off[i], idx.begin() + off[i + 1], [&](int a, int b) { return v_mcam[a] < v_mcam[b]; });
+        if (!sorted) {
+          if (idx_ins.empty()) idx_ins = idx;
+          std::sort(idx.begin() + off[i], idx.begin() + off[i + 1], [&](int a, int b) { return v_mcam[a] < v_mcam[b]; });
+        }
         for (int o = off[i] + 1; o < off[i + 1]; o++)
           if (v_mcam[idx[o]] == v_mcam[idx[o - 1]]) { set_error("duplicate (camera, point) measurement"); return PTAM_ERR_INVALID; }
+        const long long k = off[i + 1] - off[i];
+        n_pairs_max += k * (k - 1) / 2;
       }
     }
+    std::vector<int> ptcam(M);
+    for (int o = 0; o < M; o++) ptcam[o] = v_mcam[idx[o]];
+    // CSR by camera: list order (U_j / epsA_j) and ascending point id (S_jj, the pair list); again one array
+    // when the list is point-ordered inside every camera
+    std::vector<int> coff(C + 1, 0), cidx(M), cidx_pt;
+    for (int m = 0; m < M; m++) coff[v_mcam[m] + 1]++;
+    for (int j = 0; j < C; j++) coff[j + 1] += coff[j];
+    {
+      std::vector<int> cur(coff.begin(), coff.end() - 1);
+      for (int m = 0; m < M; m++) cidx[cur[v_mcam[m]]++] = m;
+      for (int j = 0; j < C; j++) {
+        bool sorted = true;
+        for (int o = coff[j] + 1; o < coff[j + 1]; o++) if (v_mpt[cidx[o]] < v_mpt[cidx[o - 1]]) { sorted = false; break; }
+        if (!sorted) {
+          if (cidx_pt.empty()) cidx_pt = cidx;
+          std::sort(cidx_pt.begin() + coff[j], cidx_pt.begin() + coff[j + 1], [&](int a, int b) { return v_mpt[a] < v_mpt[b]; });
+        }
+      }
+    }
+    std::vector<int> freecam;
+    for (int j = 0; j < C; j++) if (!h_cam_fixed[j]) freecam.push_back(j);
+    const long long n_blocks = (long long)n_free * (n_free - 1) / 2;
+    if (n_pairs_max > 0x7fffffffLL || n_blocks > 0x7ffffff0LL) { set_error("graph too dense for the pair list (more than 2^31 camera pairs / co-visible triples)"); return PTAM_ERR_INVALID; }
+    const int grid_max = std::max({(M + 255) / 256, (P + 255) / 256, 1});
     // one arena for everything: two passes over the same layout (measure, then assign)
     size_t need = 0;
     for (int pass = 0; pass < 2; pass++) {
@@ -245,10 +275,13 @@ struct ptam_bundle {
       AL(cam_fixed, C); AL(cam_row, C);
       AL(pt_pos, 3 * (size_t)P); AL(pt_pos_new, 3 * (size_t)P); AL(V, 6 * (size_t)P); AL(epsB, 3 * (size_t)P);
       AL(Vinv, 9 * (size_t)P); AL(Ve, 3 * (size_t)P); AL(pt_off, P + 1); AL(pt_meas, M);
+      AL(pt_meas_ins, idx_ins.empty() ? 0 : M); AL(pt_cam, M); AL(cam_off, C + 1); AL(cam_meas_ins, M);
+      AL(cam_meas_pt, cidx_pt.empty() ? 0 : M); AL(blk_off, n_blocks + 1); AL(blk_cnt, n_blocks); AL(nz_blocks, n_blocks); AL(pair_info, 4); AL(free_cam, n_free); AL(pr_mj, n_pairs_max); AL(pr_mk, n_pairs_max);
+      AL(m_B, 6 * (size_t)M); AL(err_cam, C); AL(partials, grid_max); AL(tickets, 4);
       AL(m_cam, M); AL(m_pt, M); AL(m_found, 2 * (size_t)M); AL(m_sin, M); AL(m_state, M); AL(m_v3cam, 3 * (size_t)M);
       AL(m_derivs, 4 * (size_t)M); AL(m_eps, 2 * (size_t)M); AL(m_e2, M); AL(m_W, 18 * (size_t)M); AL(e2c, M);
       AL(S, (size_t)n * n); AL(vE, n); AL(upd, n); AL(scal, 8); AL(counters, 4); AL(outliers, 2 * (size_t)M);
-      AL(Wp, 2 * (size_t)n * kNB);
+      AL(Wp, ldlt_workspace_doubles(n));
       AL(m_gid, M); AL(m_erase_step, M); AL(hist16, kSelBins); AL(erase_cnt, (M + 1023) / 1024 + 1); AL(sel_state, 2);
       AL(g_steps, world > 1 ? MG : 0);
 #undef AL
@@ -266,7 +299,7 @@ struct ptam_bundle {
 #define UP(buf, vec) if (!vec.empty()) PTAM_CUDA_TRY(this, cudaMemcpy(buf.p, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice))
     UP(cam_se3, h_cam_se3); UP(cam_fixed, h_cam_fixed); UP(cam_row, h_cam_row); UP(pt_pos, h_pts);
     UP(pt_off, off); UP(pt_meas, idx); UP(m_cam, v_mcam); UP(m_pt, v_mpt); UP(m_found, v_found); UP(m_sin, v_sin);
-    UP(m_gid, l_gid);
+    UP(m_gid, l_gid); UP(pt_meas_ins, idx_ins); UP(pt_cam, ptcam); UP(cam_off, coff); UP(cam_meas_ins, cidx); UP(cam_meas_pt, cidx_pt); UP(free_cam, freecam);
 #undef UP
     // pageable H2D copies return once staged; the handle's streams are non-blocking (no implicit ordering with
     // the legacy stream the copies ran on), so finish them before the first kernel is queued
@@ -280,6 +313,19 @@ struct ptam_bundle {
     d.m_eps = m_eps.p; d.m_e2 = m_e2.p; d.m_W = m_W.p; d.e2_compact = e2c.p; d.S = S.p; d.vE = vE.p; d.upd = upd.p;
     d.scal = scal.p; d.counters = counters.p; d.outliers = outliers.p;
     d.hist16 = hist16.p; d.sel_state = sel_state.p; d.m_erase_step = m_erase_step.p;
+    d.m_B = m_B.p; d.pt_meas_ins = idx_ins.empty() ? pt_meas.p : pt_meas_ins.p; d.pt_cam = pt_cam.p;
+    d.cam_off = cam_off.p; d.cam_meas_ins = cam_meas_ins.p; d.cam_meas_pt = cidx_pt.empty() ? cam_meas_ins.p : cam_meas_pt.p;
+    d.n_blocks = n_blocks; d.blk_off = blk_off.p; d.pr_mj = pr_mj.p; d.pr_mk = pr_mk.p;
+    d.err_cam = err_cam.p; d.partials = partials.p; d.tickets = tickets.p;
+    d.nz_blocks = nz_blocks.p; d.pair_info = pair_info.p; d.free_cam = free_cam.p;
+    // the pair-major list of the off-diagonal blocks (GenerateOffDiagScripts, Bundle.cc:572-599), on the device
+    if (n_blocks > 0 && p_hi > p_lo) {
+      k_ba_pair_count<<<(p_hi - p_lo + 255) / 256, 256, 0, stream>>>(d, blk_cnt.p);
+      k_ba_pair_scan<<<1, 1024, 0, stream>>>(blk_cnt.p, blk_off.p, nz_blocks.p, pair_info.p, n_blocks);
+      k_ba_pair_fill<<<148 * 8, 128, 0, stream>>>(d, pr_mj.p, pr_mk.p);
+      launches += 3;
+      PTAM_CUDA_TRY(this, cudaGetLastError());
+    }
     lambda = 0.0001; lambda_factor = 2.0;
     converged = false; hit_max = false; abort_seen = false;
     counter = 0; accepted = 0; lm_steps = 0; n_outliers = 0;
@@ -289,67 +335,24 @@ struct ptam_bundle {
     return PTAM_OK;
   }
 
-  // Blocked LDL^T on two streams.  Panel k's kernel first applies the part of panel k-1's trailing update
-  // that falls on its own 64 columns (fused: k_ldlt_panel), so the main stream is ONE kernel per panel;
-  // the rest of panel k's trailing update (column blocks from k+2 on: the tail) runs on the second stream
-  // after panel k.  Panel k+1 does not touch those tiles and overlaps it; panel k+2 waits for it (it reads
-  // tiles that tail updates and overwrites the Wp buffer it reads).  Wp is double-buffered by panel parity.
-  // Once the tail is small (<= kFuseTailTiles tiles) it is not launched on its own: it rides in the NEXT
-  // panel's launch (k_ldlt_step: panel k + tail k-1 in one grid), so the late, latency-bound part of the
-  // factorisation is a plain sequence of kernels on one stream without event records / waits in between.
-  int solve_reduced() {
-    const int n = d.n;
-    if (n == 0) return PTAM_OK;
-    const int n_panels = (n + kNB - 1) / kNB;
-    if ((int)ev_panel.size() < n_panels) {
-      const size_t old = ev_panel.size();
-      ev_panel.resize(n_panels); ev_tail.resize(n_panels); tail_of.resize(n_panels, false);
-      for (size_t k = old; k < ev_panel.size(); k++) {
-        PTAM_CUDA_TRY(this, cudaEventCreateWithFlags(&ev_panel[k], cudaEventDisableTiming));
-        PTAM_CUDA_TRY(this, cudaEventCreateWithFlags(&ev_tail[k], cudaEventDisableTiming));
-      }
-    }
-    // vE is consumed in place as the right-hand side (forward substitution rides with the panels)
-    int last_tail = -1;
-    bool deferred = false;      // the tail of panel k-1 waits to be launched together with panel k (k_ldlt_step)
-    for (int k = 0, k0 = 0; k0 < n; k++, k0 += kNB) {
-      const int nb = std::min(kNB, n - k0);
-      const int rem = n - k0 - nb;
-      double* wp = Wp.p + (size_t)(k & 1) * n * kNB;
-      double* wprev = k > 0 ? Wp.p + (size_t)((k - 1) & 1) * n * kNB : nullptr;
-      const int n_ctas = std::max(1, (rem + kPanelRows - 1) / kPanelRows);
-      // panel k reads tiles the tail of panel k-2 updated, and overwrites the Wp buffer that tail read
-      if (k >= 2 && tail_of[k - 2]) PTAM_CUDA_TRY(this, cudaStreamWaitEvent(stream, ev_tail[k - 2], 0));
-      if (deferred) {
-        const int nt = (n - k0 + kUTM - 1) / kUTM;  // tail of panel k-1: its trailing matrix starts at k0
-        k_ldlt_step<<<n_ctas + nt * nt, kPanelThreads, kPanelSmem, stream>>>(d.S, wp, wprev, d.vE, n, k0, n_ctas);
-      } else {
-        k_ldlt_panel<<<n_ctas, kPanelThreads, kPanelSmem, stream>>>(d.S, wp, wprev, d.vE, n, k0);
-      }
+  int solve_reduced() {  // Cholesky<>(mS).backsub(vE), Bundle.cc:457-458
+    const int64_t l0 = ldlt.launches;
+    const cudaError_t e = ldlt.solve(d.S, d.vE, d.upd, Wp.p, d.n);
+    launches += ldlt.launches - l0;
+    if (e != cudaSuccess) { set_error("dense solve: " + ldlt.err + ": " + cudaGetErrorString(e)); return PTAM_ERR_CUDA; }
+    return PTAM_OK;
+  }
+
+  // S and vE of the current lambda (Bundle.cc:365-453): every block of the lower triangle is written whole
+  int build_reduced() {
+    if (d.n == 0) return PTAM_OK;
+    k_ba_zero_lower<<<148 * 4, 256, 0, stream>>>(d.S, d.n, d.tickets + 3);
+    k_ba_schur_diag<<<d.n_cams, kSegThreads, kSchurDiagSmem, stream>>>(d);
+    launches += 2;
+    if (d.n_blocks > 0) {
+      k_ba_schur_off<<<148 * 4, kOffThreads, 0, stream>>>(d);
       launches++;
-      tail_of[k] = false;
-      deferred = false;
-      if (rem > kNB) {  // column blocks from k+2 on exist: the tail of the trailing update
-        const int nt = (rem + kUTM - 1) / kUTM;
-        const int n_tail = nt * (nt + 1) - nt;
-        if (n_tail <= kFuseTailTiles) {
-          deferred = true;  // small enough to hide behind panel k+1 at one CTA per SM: same launch, same stream
-        } else {            // large: its own launch (two CTAs per SM) on the second stream
-          PTAM_CUDA_TRY(this, cudaEventRecord(ev_panel[k], stream));
-          PTAM_CUDA_TRY(this, cudaStreamWaitEvent(stream2, ev_panel[k], 0));
-          k_ldlt_update<<<n_tail, 256, kUpdateSmem, stream2>>>(d.S, wp, n, k0, 2);
-          PTAM_CUDA_TRY(this, cudaEventRecord(ev_tail[k], stream2));
-          launches++;
-          tail_of[k] = true;
-          last_tail = k;
-        }
-      }
     }
-    if (last_tail >= 0) PTAM_CUDA_TRY(this, cudaStreamWaitEvent(stream, ev_tail[last_tail], 0));
-    k_ldlt_scale<<<(n + 255) / 256, 256, 0, stream>>>(d.S, d.vE, d.vE, n);
-    launches++;
-    k_ldlt_back<<<kBackCtas, kBackThreads, 0, stream>>>(d.S, d.vE, d.upd, n);  // one cluster, all panels
-    launches++;
     PTAM_CUDA_TRY(this, cudaGetLastError());
     return PTAM_OK;
   }
@@ -392,16 +395,16 @@ struct ptam_bundle {
     int rc;
     lm_steps++;
     shards_dirty = true;
-    // ClearAccumulators + error / counter scalars
-    PTAM_CUDA_TRY(this, cudaMemsetAsync(U.p, 0, sizeof(double) * 21 * C, stream));
-    PTAM_CUDA_TRY(this, cudaMemsetAsync(epsA.p, 0, sizeof(double) * 6 * C, stream));
-    PTAM_CUDA_TRY(this, cudaMemsetAsync(V.p, 0, sizeof(double) * 6 * P, stream));
-    PTAM_CUDA_TRY(this, cudaMemsetAsync(epsB.p, 0, sizeof(double) * 3 * P, stream));
+    // error / counter scalars (the accumulators are written whole by k_ba_acc_cam / k_ba_acc_pt, not summed into)
     PTAM_CUDA_TRY(this, cudaMemsetAsync(scal.p, 0, sizeof(double) * 8, stream));
     PTAM_CUDA_TRY(this, cudaMemsetAsync(counters.p, 0, sizeof(int), stream));
     pbegin(0); if (M > 0) { k_ba_project<<<(M + 255) / 256, 256, 0, stream>>>(d); launches++; } pend(0);
     pbegin(1); if ((rc = find_sigma_squared())) return rc; pend(1);
-    pbegin(2); if (M > 0) { k_ba_jacobian<<<(M + 127) / 128, 128, 0, stream>>>(d); launches++; } pend(2);
+    pbegin(2);
+    if (M > 0) { k_ba_jacobian<<<(M + 127) / 128, 128, 0, stream>>>(d); launches++; }
+    if (C > 0) { k_ba_acc_cam<<<C, kSegThreads, kAccCamSmem, stream>>>(d); launches++; }
+    if (PO > 0) { k_ba_acc_pt<<<(PO + 255) / 256, 256, 0, stream>>>(d); launches++; }
+    pend(2);
     PTAM_CUDA_TRY(this, cudaGetLastError());
     if (world > 1) {
       h_scal[5] = local_abort() ? 1.0 : 0.0;
@@ -423,15 +426,9 @@ struct ptam_bundle {
       PTAM_CUDA_TRY(this, cudaMemcpyAsync(scal.p + 3, h_scal + 3, sizeof(double) * 4, cudaMemcpyHostToDevice, stream));
       pbegin(3);
       if (PO > 0) { k_ba_vinv<<<(PO + 255) / 256, 256, 0, stream>>>(d); launches++; }
-      if (n > 0) {
-        k_ba_init_s<<<std::min<size_t>(((size_t)n * n + 255) / 256, 148 * 8), 256, 0, stream>>>(d);
-        k_ba_init_diag<<<C, 64, 0, stream>>>(d);
-        launches += 2;
-      }
       pend(3);
       pbegin(4);
-      if (M > 0 && n > 0) { k_ba_schur_diag<<<(M + 127) / 128, 128, 0, stream>>>(d); launches++; }
-      if (PO > 0 && n > 0) { k_ba_schur<<<(PO + 7) / 8, 256, 0, stream>>>(d); launches++; }
+      if ((rc = build_reduced())) return rc;
       pend(4);
       s_mirrored = false;
       pbegin(5);
@@ -442,8 +439,8 @@ struct ptam_bundle {
       pend(5);
       pbegin(6); if ((rc = solve_reduced())) return rc; pend(6);
       pbegin(7);
+      k_ba_cam_update<<<1, 256, 0, stream>>>(d); launches++;  // first: it SETS the |delta|^2 slot, the points add to it
       if (PO > 0) { k_ba_point_update<<<(PO + 255) / 256, 256, 0, stream>>>(d); launches++; }
-      if (C > 0) { k_ba_cam_update<<<(C + 127) / 128, 128, 0, stream>>>(d); launches++; }
       if (M > 0) { k_ba_new_error<<<(M + 255) / 256, 256, 0, stream>>>(d); launches++; }
       pend(7);
       PTAM_CUDA_TRY(this, cudaGetLastError());
@@ -756,14 +753,11 @@ int ptam_bundle_get_reduced_system(ptam_bundle* b, double* S, double* vE, int ca
   PTAM_CUDA_TRY(b, cudaStreamSynchronize(b->stream));
   const int PO = b->d.p_hi - b->d.p_lo;
   if (PO > 0) k_ba_vinv<<<(PO + 255) / 256, 256, 0, b->stream>>>(b->d);
-  k_ba_init_s<<<std::min<size_t>(((size_t)n * n + 255) / 256, 148 * 8), 256, 0, b->stream>>>(b->d);
-  k_ba_init_diag<<<b->d.n_cams, 64, 0, b->stream>>>(b->d);
-  if (b->d.n_meas > 0) k_ba_schur_diag<<<(b->d.n_meas + 127) / 128, 128, 0, b->stream>>>(b->d);
-  if (PO > 0) k_ba_schur<<<(PO + 7) / 8, 256, 0, b->stream>>>(b->d);
+  { const int rc = b->build_reduced(); if (rc) return rc; }
   { int rc = b->all_reduce(b->d.S, (size_t)n * n, ncclDouble, ncclSum, "all-reduce of S"); if (rc) return rc;
     rc = b->all_reduce(b->d.vE, n, ncclDouble, ncclSum, "all-reduce of vE"); if (rc) return rc; }
   k_ba_mirror<<<std::min<size_t>(((size_t)n * n + 255) / 256, 148 * 8), 256, 0, b->stream>>>(b->d.S, n);
-  b->launches += 6;
+  b->launches += 2;
   PTAM_CUDA_TRY(b, cudaGetLastError());
   PTAM_CUDA_TRY(b, cudaStreamSynchronize(b->stream));
   PTAM_CUDA_TRY(b, cudaMemcpy2D(S, sizeof(double) * cap_n, b->S.p, sizeof(double) * n, sizeof(double) * n, n, cudaMemcpyDeviceToHost));

@@ -2,13 +2,13 @@
 //
 // per LM step      k_ba_project      ProjectAndFindSquaredError per measurement (Bundle.cc:219-225)
 //                  k_ba_select       exact order statistic of the squared errors (sigma^2, :230-237)
-//                  k_ba_jacobian     weights, A (2x6), B (2x3), W = A^T B, warp-aggregated f64 atomics
-//                                    into U / epsA (per camera) and V / epsB (per point) (:251-332)
+//                  k_ba_jacobian     weights, outlier marks, B (2x3), W = A^T B (:251-332)
+//                  k_ba_acc_cam      U_j, epsA_j, current error: warp per camera, IN LIST ORDER (no atomics)
+//                  k_ba_acc_pt       V_i, epsB_i: thread per point, in list order
 // per lambda trial k_ba_vinv         V*_i^-1 by 3x3 LDL^T (:341-359)
-//                  k_ba_init_s       S diagonal blocks <- U*, vE <- epsA (:374-392)
-//                  k_ba_schur        warp per point: S_jk -= W_ij V*^-1 W_ik^T, vE_j -= W_ij V*^-1 epsB
-//                                    (:396-446) with atomics into the dense lower triangle
-//                  k_ldlt_*          blocked square-root-free LDL^T of S (DMMA trailing update) + solve (:457-458)
+//                  k_ba_schur_diag   S_jj = U*_j - sum_i ..., vE_j: warp per camera, in point order (:374-406)
+//                  k_ba_schur_off    S_jk = - sum_i W_ij V*^-1 W_ik^T: warp per camera pair, in point order (:410-446)
+//                  (ldlt.cu)         blocked square-root-free LDL^T of S (DMMA trailing update) + solve (:457-458)
 //                  k_ba_point_update delta_b_i (:461-483), k_ba_cam_update exp(delta_a) (:496-504)
 //                  k_ba_new_error    FindNewError (:188-207)
 #pragma once
@@ -39,8 +39,22 @@ struct BundleDev {
   double* epsB;         // [P][3]
   double* Vinv;         // [P][9]
   double* Ve;           // [P][3]  V*^-1 epsB
-  const int* pt_off;    // [P+1] CSR by point (measurement ids sorted by camera id)
-  const int* pt_meas;   // [M]
+  const int* pt_off;    // [P+1] CSR by point
+  const int* pt_meas;   // [M] a point's measurements by ascending camera id (the reference's std::set<int> order)
+  const int* pt_meas_ins;  // [M] the same in list (insertion) order; aliases pt_meas when the two agree
+  const int* pt_cam;    // [M] camera id of pt_meas[o]
+  // CSR by camera
+  const int* cam_off;       // [C+1]
+  const int* cam_meas_ins;  // [M] a camera's measurements in list order
+  const int* cam_meas_pt;   // [M] the same by ascending point id; aliases cam_meas_ins when the two agree
+  // camera pairs (j > k, both free) in block order b = jf (jf - 1) / 2 + kf (jf, kf = start row / 6)
+  long long n_blocks;
+  const int* blk_off;   // [n_blocks + 1] triples of block b: [blk_off[b], blk_off[b + 1]), ascending point id
+  const int* pr_mj;     // measurement of the point in camera j
+  const int* pr_mk;     // ... and in camera k
+  const int* nz_blocks; // the pairs with common points, long ones (>= kLongBlock triples) first
+  const int* pair_info; // [0] number of such pairs, [1] long ones among them, [2] triples
+  const int* free_cam;  // [n / 6] camera id of free camera jf
   // measurements (insertion order)
   const int* m_cam; const int* m_pt;
   const double* m_found;  // [M][2]
@@ -51,6 +65,7 @@ struct BundleDev {
   double* m_eps;          // [M][2]
   double* m_e2;           // [M]
   double* m_W;            // [M][18]
+  double* m_B;            // [M][6]
   double* e2_compact;     // [M] squared errors of the non-bad measurements
   // reduced system
   double* S;   // [n][n] (lower triangle valid; mirrored on request)
@@ -64,6 +79,10 @@ struct BundleDev {
   int* counters;  // 0 n_valid, 1 n_outliers_total, 2 n_bad_this_step
   int* outliers;  // [M][2] (point, camera) in erase order
   int* m_erase_step;  // [M] LM step (1-based) at which the measurement was erased, 0 = still in the graph
+  // deterministic grid-wide sums
+  double* err_cam;    // [C] each camera's share of the current robust error
+  double* partials;   // [max grid] per-block partial sums of the kernel in flight
+  unsigned* tickets;  // [4] arrival counters (self-resetting)
 };
 
 PTAM_DEV double block_sum(double v, double* sh /*32*/) {
@@ -261,114 +280,201 @@ __global__ void __launch_bounds__(1024) k_ba_pick(BundleDev d, int pass, double 
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_ba_jacobian — one thread per observation.  Camera accumulators: measurements usually arrive
-// camera-major (MapMaker.cc:871-882), so a whole warp mostly shares one camera: warp-reduce the 27
-// values and issue one atomic per value; otherwise per-lane atomics.  Point accumulators: per-lane
-// atomics (a point's few observations are scattered over warps).
+// Deterministic accumulation.  Every sum of the reference that runs over measurements is taken IN THE
+// REFERENCE'S ORDER, one term after the other, with the reference's expressions (this file is compiled
+// without FMA contraction): no floating-point atomics anywhere on path B.
+//   U_j, epsA_j   over camera j's measurements in list order            (Bundle.cc:251-332)
+//   V_i, epsB_i   over point i's measurements in list order             (same loop)
+//   S_jj, vE_j    U*_j, epsA_j minus the terms of camera j's points in point order   (:374-406)
+//   S_jk          minus the terms of the points seen by both, in point order         (:410-446)
+// A segment (one camera's measurements, one camera pair's points) belongs to ONE WARP: 32 lanes compute the
+// terms of 32 consecutive items, stage them in shared memory (value-major, pitch 33: conflict-free both
+// ways), then lane v adds value v of the 32 items one after the other.  Items that contribute nothing
+// (erased / outlier measurements, the tail of the last chunk) stage +0.0, which leaves a sum unchanged.
 // ---------------------------------------------------------------------------------------------
+constexpr int kSegThreads = 256;  // items per round of the per-camera segment kernels (CTA per camera)
+constexpr int kOffThreads = 128;  // ... of the per-camera-pair kernel
+constexpr int kLongBlock = 512;   // camera pairs with at least this many common points are scheduled first
+
+// Every block stores its partial; the last block to arrive adds them in index order (lane-strided,
+// then the fixed xor tree): the same bits whatever the block schedule.  `t` is valid in thread 0.
+PTAM_DEV void grid_sum_finish(double t, double* partials, unsigned* ticket, double* out, bool add_to_out) {
+  __shared__ bool s_last;
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = t;
+    __threadfence();
+    s_last = atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1;  // wraps to 0: ready for the next launch
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x < 32) {
+    __threadfence();
+    double s = 0.0;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += 32) s += __ldcg(&partials[i]);
+    s = warp_sum(s);
+    if (threadIdx.x == 0) *out = add_to_out ? *out + s : s;
+  }
+}
+
+// One round of a segment sum: thread t has computed the NV terms of item t (zeros when it has none); they are
+// staged value-major (pitch R + 1: conflict-free both ways), then thread v < NV adds (or subtracts) value v of
+// the round's `cnt` items one after the other.
+template <int NV, int R>
+PTAM_DEV void seg_round(double* sv, const double* v, int cnt, double& acc, bool subtract) {
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int q = 0; q < NV; q++) sv[q * (R + 1) + t] = v[q];
+  __syncthreads();
+  if (t < NV) {
+    const double* row = sv + t * (R + 1);
+    if (subtract) {
+#pragma unroll 8
+      for (int i = 0; i < cnt; i++) acc -= row[i];
+    } else {
+#pragma unroll 8
+      for (int i = 0; i < cnt; i++) acc += row[i];
+    }
+  }
+  __syncthreads();
+}
+
+// A (2x6) of one measurement: meas.dSqrtInvNoise * m2CamDerivs * v2CamFrameMotion per generator (Bundle.cc:287-301)
+PTAM_DEV void ba_cam_jacobian(double X, double Y, double Z, double ooz, double d0, double d1, double d2, double d3, double* A) {
+  const double gx[6] = {1, 0, 0, 0, Z, -Y}, gy[6] = {0, 1, 0, -Z, 0, X}, gz[6] = {0, 0, 1, Y, -X, 0};
+#pragma unroll
+  for (int q = 0; q < 6; q++) {
+    const double a0 = (gx[q] - X * gz[q] * ooz) * ooz, a1 = (gy[q] - Y * gz[q] * ooz) * ooz;
+    A[q] = d0 * a0 + d1 * a1;
+    A[6 + q] = d2 * a0 + d3 * a1;
+  }
+}
+
+// k_ba_jacobian — one thread per observation: weight, outlier mark, B (2x3), W = A^T B (Bundle.cc:251-332).
+// The accumulators are summed by k_ba_acc_cam / k_ba_acc_pt.
 __global__ void __launch_bounds__(128) k_ba_jacobian(BundleDev d) {
-  __shared__ double sh[32];
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
+  if (m >= d.n_meas || d.m_state[m] != M_ALIVE) return;
   const double sigma2 = d.scal[1];
-  double err = 0.0;
-  bool active = false;
-  int c = -1;
-  double A[12], eps[2] = {0, 0};
+  const double e2 = d.m_e2[m];
+  const double w = mest_sqrt_weight(e2, sigma2, d.est);
+  const double eps0 = w * d.m_eps[2 * m], eps1 = w * d.m_eps[2 * m + 1];
+  d.m_eps[2 * m] = eps0; d.m_eps[2 * m + 1] = eps1;
+  if (w == 0) { d.m_state[m] = M_BAD; return; }
+  const int c = d.m_cam[m];
+  const double s = d.m_sin[m];
+  const double d0 = s * (w * d.m_derivs[4 * m]), d1 = s * (w * d.m_derivs[4 * m + 1]);
+  const double d2 = s * (w * d.m_derivs[4 * m + 2]), d3 = s * (w * d.m_derivs[4 * m + 3]);
+  const double X = d.m_v3cam[3 * m], Y = d.m_v3cam[3 * m + 1], Z = d.m_v3cam[3 * m + 2];
+  const double ooz = 1.0 / Z;
+  double A[12];
+  if (d.cam_fixed[c]) {
 #pragma unroll
-  for (int i = 0; i < 12; i++) A[i] = 0;
-  bool cam_free = false;
-  if (m < d.n_meas && d.m_state[m] != M_ERASED) {
-    if (d.m_state[m] == M_BAD) err = 1.0;
-    else {
-      const double e2 = d.m_e2[m];
-      const double w = mest_sqrt_weight(e2, sigma2, d.est);
-      eps[0] = w * d.m_eps[2 * m]; eps[1] = w * d.m_eps[2 * m + 1];
-      d.m_eps[2 * m] = eps[0]; d.m_eps[2 * m + 1] = eps[1];
-      if (w == 0) { d.m_state[m] = M_BAD; err = 1.0; }
-      else {
-        active = true;
-        err = mest_objective(e2, sigma2, d.est);
-        c = d.m_cam[m];
-        const int p = d.m_pt[m];
-        const double s = d.m_sin[m];
-        const double d0 = s * (w * d.m_derivs[4 * m]), d1 = s * (w * d.m_derivs[4 * m + 1]);
-        const double d2 = s * (w * d.m_derivs[4 * m + 2]), d3 = s * (w * d.m_derivs[4 * m + 3]);
-        const double X = d.m_v3cam[3 * m], Y = d.m_v3cam[3 * m + 1], Z = d.m_v3cam[3 * m + 2];
-        const double ooz = 1.0 / Z;
-        cam_free = !d.cam_fixed[c];
-        if (cam_free) {
-          const double gx[6] = {1, 0, 0, 0, Z, -Y}, gy[6] = {0, 1, 0, -Z, 0, X}, gz[6] = {0, 0, 1, Y, -X, 0};
+    for (int i = 0; i < 12; i++) A[i] = 0.0;
+  } else ba_cam_jacobian(X, Y, Z, ooz, d0, d1, d2, d3, A);
+  double B[6];
+  const double* R = d.cam_se3 + 12 * c;
 #pragma unroll
-          for (int q = 0; q < 6; q++) {
-            const double a0 = (gx[q] - X * gz[q] * ooz) * ooz, a1 = (gy[q] - Y * gz[q] * ooz) * ooz;
-            A[q] = d0 * a0 + d1 * a1;
-            A[6 + q] = d2 * a0 + d3 * a1;
-          }
+  for (int q = 0; q < 3; q++) {
+    const double a0 = (R[q] - X * R[6 + q] * ooz) * ooz, a1 = (R[3 + q] - Y * R[6 + q] * ooz) * ooz;
+    B[q] = d0 * a0 + d1 * a1;
+    B[3 + q] = d2 * a0 + d3 * a1;
+  }
+  double* Bm = d.m_B + 6 * (size_t)m;
+#pragma unroll
+  for (int q = 0; q < 6; q++) Bm[q] = B[q];
+  double* Wm = d.m_W + 18 * (size_t)m;  // W = A^T B (6x3), zero for a fixed camera
+#pragma unroll
+  for (int r = 0; r < 6; r++)
+#pragma unroll
+    for (int cc = 0; cc < 3; cc++) Wm[3 * r + cc] = A[r] * B[cc] + A[6 + r] * B[3 + cc];
+}
+
+// k_ba_acc_cam — CTA per camera, its measurements in list order: U_j (lower, packed 21), epsA_j (6) and the
+// camera's share of the robust error (value 27).  A is recomputed from the stored projection (76 B per
+// measurement instead of a 96-byte round trip).  The last block adds the per-camera errors in camera order.
+constexpr int kAccCamSmem = 28 * (kSegThreads + 1) * (int)sizeof(double);
+__global__ void __launch_bounds__(kSegThreads) k_ba_acc_cam(BundleDev d) {
+  extern __shared__ __align__(16) double seg_sv[];
+  __shared__ bool s_last;
+  const int c = blockIdx.x, t = threadIdx.x;
+  const double sigma2 = d.scal[1];
+  const bool cfree = !d.cam_fixed[c];
+  const int o0 = d.cam_off[c], o1 = d.cam_off[c + 1];
+  double acc = 0.0;
+  for (int base = o0; base < o1; base += kSegThreads) {
+    const int o = base + t;
+    double v[28];
+#pragma unroll
+    for (int q = 0; q < 28; q++) v[q] = 0.0;
+    if (o < o1) {
+      const int m = d.cam_meas_ins[o];
+      const int st = d.m_state[m];
+      if (st == M_BAD) v[27] = 1.0;
+      else if (st == M_ALIVE) {
+        const double e2 = d.m_e2[m];
+        v[27] = mest_objective(e2, sigma2, d.est);
+        if (cfree) {
+          const double w = mest_sqrt_weight(e2, sigma2, d.est);
+          const double s = d.m_sin[m];
+          const double d0 = s * (w * d.m_derivs[4 * m]), d1 = s * (w * d.m_derivs[4 * m + 1]);
+          const double d2 = s * (w * d.m_derivs[4 * m + 2]), d3 = s * (w * d.m_derivs[4 * m + 3]);
+          const double X = d.m_v3cam[3 * m], Y = d.m_v3cam[3 * m + 1], Z = d.m_v3cam[3 * m + 2];
+          double A[12];
+          ba_cam_jacobian(X, Y, Z, 1.0 / Z, d0, d1, d2, d3, A);
+          const double eps0 = d.m_eps[2 * m], eps1 = d.m_eps[2 * m + 1];  // already weighted
+          int q = 0;
+#pragma unroll
+          for (int r = 0; r < 6; r++)
+#pragma unroll
+            for (int cc = 0; cc <= r; cc++) v[q++] = A[r] * A[cc] + A[6 + r] * A[6 + cc];
+#pragma unroll
+          for (int r = 0; r < 6; r++) v[21 + r] = A[r] * eps0 + A[6 + r] * eps1;
         }
-        double B[6];
-        const double* R = d.cam_se3 + 12 * c;
-#pragma unroll
-        for (int q = 0; q < 3; q++) {
-          const double a0 = (R[q] - X * R[6 + q] * ooz) * ooz, a1 = (R[3 + q] - Y * R[6 + q] * ooz) * ooz;
-          B[q] = d0 * a0 + d1 * a1;
-          B[3 + q] = d2 * a0 + d3 * a1;
-        }
-        // V (lower, packed) and epsB: per-lane atomics
-        double* Vp = d.V + 6 * p;
-        int o = 0;
-#pragma unroll
-        for (int r = 0; r < 3; r++)
-#pragma unroll
-          for (int cc = 0; cc <= r; cc++) atomicAdd(&Vp[o++], B[r] * B[cc] + B[3 + r] * B[3 + cc]);
-#pragma unroll
-        for (int r = 0; r < 3; r++) atomicAdd(&d.epsB[3 * p + r], B[r] * eps[0] + B[3 + r] * eps[1]);
-        // W = A^T B (6x3), zero for a fixed camera
-        double* Wm = d.m_W + 18 * m;
-#pragma unroll
-        for (int r = 0; r < 6; r++)
-#pragma unroll
-          for (int cc = 0; cc < 3; cc++) Wm[3 * r + cc] = A[r] * B[cc] + A[6 + r] * B[3 + cc];
       }
     }
+    seg_round<28, kSegThreads>(seg_sv, v, min(kSegThreads, o1 - base), acc, false);
   }
-  // camera accumulators U (lower, packed 21) and epsA (6)
-  // Lanes without a contribution (erased / outlier measurements, fixed cameras: A and eps are zero there)
-  // ride along in the warp sums: the warp is uniform when all CONTRIBUTING lanes share one camera, which
-  // leaves only the ~3 % of warps that straddle a camera boundary on the per-lane path.
-  const int c_acc = (active && cam_free) ? c : -1;
-  if (c_acc < 0) { eps[0] = 0.0; eps[1] = 0.0; }  // 0 x inf of a wild outlier must not reach the sums
-  const unsigned contrib = __ballot_sync(kFull, c_acc >= 0);
-  const int c0 = contrib ? __shfl_sync(kFull, c_acc, __ffs(contrib) - 1) : -1;
-  const bool uniform = __all_sync(kFull, c_acc < 0 || c_acc == c0);
-  if (uniform) {
-    if (c0 >= 0) {
-      int o = 0;
-#pragma unroll
-      for (int r = 0; r < 6; r++)
-#pragma unroll
-        for (int cc = 0; cc <= r; cc++) {
-          const double v = warp_sum(A[r] * A[cc] + A[6 + r] * A[6 + cc]);
-          if (lane == 0) atomicAdd(&d.U[21 * c0 + o], v);
-          o++;
-        }
-#pragma unroll
-      for (int r = 0; r < 6; r++) {
-        const double v = warp_sum(A[r] * eps[0] + A[6 + r] * eps[1]);
-        if (lane == 0) atomicAdd(&d.epsA[6 * c0 + r], v);
-      }
-    }
-  } else if (c_acc >= 0) {
-    int o = 0;
-#pragma unroll
-    for (int r = 0; r < 6; r++)
-#pragma unroll
-      for (int cc = 0; cc <= r; cc++) atomicAdd(&d.U[21 * c_acc + o++], A[r] * A[cc] + A[6 + r] * A[6 + cc]);
-#pragma unroll
-    for (int r = 0; r < 6; r++) atomicAdd(&d.epsA[6 * c_acc + r], A[r] * eps[0] + A[6 + r] * eps[1]);
+  if (t < 21) d.U[21 * c + t] = cfree ? acc : 0.0;
+  else if (t < 27) d.epsA[6 * c + t - 21] = cfree ? acc : 0.0;
+  else if (t == 27) {
+    d.err_cam[c] = acc;
+    __threadfence();
+    s_last = atomicInc(d.tickets + 0, gridDim.x - 1) == gridDim.x - 1;
   }
-  const double t = block_sum(err, sh);
-  if (threadIdx.x == 0 && t != 0.0) atomicAdd(&d.scal[2], t);
+  __syncthreads();
+  if (s_last && t < 32) {  // current error = the cameras' shares, in camera order
+    __threadfence();
+    double s = 0.0;
+    for (int i = t; i < d.n_cams; i += 32) s += __ldcg(&d.err_cam[i]);
+    s = warp_sum(s);
+    if (t == 0) d.scal[2] = s;
+  }
+}
+
+// k_ba_acc_pt — thread per point, its measurements in list order: V_i (lower, packed), epsB_i.
+__global__ void __launch_bounds__(256) k_ba_acc_pt(BundleDev d) {
+  const int i = d.p_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.p_hi) return;
+  double V[6] = {0, 0, 0, 0, 0, 0}, eB[3] = {0, 0, 0};
+  for (int o = d.pt_off[i]; o < d.pt_off[i + 1]; o++) {
+    const int m = d.pt_meas_ins[o];
+    if (d.m_state[m] != M_ALIVE) continue;
+    const double* B = d.m_B + 6 * (size_t)m;
+    const double b0 = B[0], b1 = B[1], b2 = B[2], b3 = B[3], b4 = B[4], b5 = B[5];
+    const double eps0 = d.m_eps[2 * m], eps1 = d.m_eps[2 * m + 1];
+    V[0] += b0 * b0 + b3 * b3;
+    V[1] += b1 * b0 + b4 * b3;
+    V[2] += b1 * b1 + b4 * b4;
+    V[3] += b2 * b0 + b5 * b3;
+    V[4] += b2 * b1 + b5 * b4;
+    V[5] += b2 * b2 + b5 * b5;
+    eB[0] += b0 * eps0 + b3 * eps1;
+    eB[1] += b1 * eps0 + b4 * eps1;
+    eB[2] += b2 * eps0 + b5 * eps1;
+  }
+#pragma unroll
+  for (int q = 0; q < 6; q++) d.V[6 * (size_t)i + q] = V[q];
+#pragma unroll
+  for (int q = 0; q < 3; q++) d.epsB[3 * (size_t)i + q] = eB[q];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -376,7 +482,7 @@ __global__ void __launch_bounds__(256) k_ba_vinv(BundleDev d) {
   const int i = d.p_lo + blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= d.p_hi) return;
   const double lambda = d.scal[6];
-  const double* v = d.V + 6 * i;
+  const double* v = d.V + 6 * (size_t)i;
   double Vs[9] = {v[0], v[1], v[3], v[1], v[2], v[4], v[3], v[4], v[5]};
   double inv[9];
   if (Vs[0] * Vs[4] * Vs[8] == 0) {
@@ -387,136 +493,128 @@ __global__ void __launch_bounds__(256) k_ba_vinv(BundleDev d) {
     ldlt_inverse<3>(Vs, inv);
   }
 #pragma unroll
-  for (int k = 0; k < 9; k++) d.Vinv[9 * i + k] = inv[k];
-  const double* e = d.epsB + 3 * i;
+  for (int k = 0; k < 9; k++) d.Vinv[9 * (size_t)i + k] = inv[k];
+  const double* e = d.epsB + 3 * (size_t)i;
 #pragma unroll
-  for (int r = 0; r < 3; r++) d.Ve[3 * i + r] = inv[3 * r] * e[0] + inv[3 * r + 1] * e[1] + inv[3 * r + 2] * e[2];
+  for (int r = 0; r < 3; r++) d.Ve[3 * (size_t)i + r] = inv[3 * r] * e[0] + inv[3 * r + 1] * e[1] + inv[3 * r + 2] * e[2];
 }
 
-// S <- 0 except diagonal blocks U*_j (lambda-damped, both triangles); vE <- epsA
-__global__ void __launch_bounds__(256) k_ba_init_s(BundleDev d) {
-  const size_t tot = (size_t)d.n * d.n;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x) d.S[i] = 0.0;
+// Schur complement (Bundle.cc:365-453): k_ba_zero_lower clears the lower triangle (the solve left its factors
+// there), then two segment kernels write the diagonal blocks + vE and the camera pairs with common points.
+__global__ void __launch_bounds__(256) k_ba_zero_lower(double* S, int n, unsigned* work_counter) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *work_counter = 0u;  // k_ba_schur_off (next in the stream) fetches its pairs through it
+  for (int i = blockIdx.x; i < n; i += gridDim.x)
+    for (int j = threadIdx.x; j <= i; j += blockDim.x) S[(size_t)i * n + j] = 0.0;
 }
-__global__ void __launch_bounds__(64) k_ba_init_diag(BundleDev d) {
-  const int c = blockIdx.x;
+
+// k_ba_schur_diag — CTA per camera j: S_jj = U*_j - sum_i W_ij V*_i^-1 W_ij^T,  vE_j = epsA_j - sum_i W_ij V*_i^-1 epsB_i
+// over camera j's points in POINT order (the reference scans i = 0 .. P-1, Bundle.cc:396-405).
+constexpr int kSchurDiagSmem = 27 * (kSegThreads + 1) * (int)sizeof(double);
+__global__ void __launch_bounds__(kSegThreads) k_ba_schur_diag(BundleDev d) {
+  extern __shared__ __align__(16) double seg_sv[];
+  const int c = blockIdx.x, t = threadIdx.x;
   const int row = d.cam_row[c];
   if (row < 0) return;
   const double lambda = d.scal[6];
+  int r6 = 0, c6 = 0;  // t < 21: packed lower-triangle index -> (row, column)
+  if (t < 21) { while ((r6 + 1) * (r6 + 2) / 2 <= t) r6++; c6 = t - r6 * (r6 + 1) / 2; }
+  double acc = 0.0;
+  if (t < 21) { acc = d.U[21 * c + t]; if (r6 == c6) acc *= (1.0 + lambda); }
+  else if (t < 27) acc = d.epsA[6 * c + t - 21];
+  const int o0 = d.cam_off[c], o1 = d.cam_off[c + 1];
+  for (int base = o0; base < o1; base += kSegThreads) {
+    const int o = base + t;
+    double v[27];
+#pragma unroll
+    for (int q = 0; q < 27; q++) v[q] = 0.0;
+    if (o < o1) {
+      const int m = d.cam_meas_pt[o];
+      if (d.m_state[m] == M_ALIVE) {
+        const int i = d.m_pt[m];
+        const double* Vi = d.Vinv + 9 * (size_t)i;
+        const double* ve = d.Ve + 3 * (size_t)i;
+        const double* W = d.m_W + 18 * (size_t)m;
+        double Wr[18], WV[18];
+#pragma unroll
+        for (int q = 0; q < 18; q++) Wr[q] = W[q];
+#pragma unroll
+        for (int r = 0; r < 6; r++)
+#pragma unroll
+          for (int cc = 0; cc < 3; cc++) WV[3 * r + cc] = Wr[3 * r] * Vi[cc] + Wr[3 * r + 1] * Vi[3 + cc] + Wr[3 * r + 2] * Vi[6 + cc];
+        int q = 0;
+#pragma unroll
+        for (int r = 0; r < 6; r++)
+#pragma unroll
+          for (int cc = 0; cc <= r; cc++) v[q++] = WV[3 * r] * Wr[3 * cc] + WV[3 * r + 1] * Wr[3 * cc + 1] + WV[3 * r + 2] * Wr[3 * cc + 2];
+#pragma unroll
+        for (int r = 0; r < 6; r++) v[21 + r] = Wr[3 * r] * ve[0] + Wr[3 * r + 1] * ve[1] + Wr[3 * r + 2] * ve[2];
+      }
+    }
+    seg_round<27, kSegThreads>(seg_sv, v, min(kSegThreads, o1 - base), acc, true);
+  }
+  if (t < 21) {
+    d.S[(size_t)(row + r6) * d.n + row + c6] = acc;
+    d.S[(size_t)(row + c6) * d.n + row + r6] = acc;
+  } else if (t < 27) d.vE[row + t - 21] = acc;
+}
+
+// block index b = jf (jf - 1) / 2 + kf  ->  (jf, kf), kf < jf
+PTAM_DEV void pair_decode(long long b, int& jf, int& kf) {
+  jf = (int)((1.0 + sqrt(1.0 + 8.0 * (double)b)) * 0.5);
+  while ((long long)jf * (jf - 1) / 2 > b) jf--;
+  while ((long long)(jf + 1) * jf / 2 <= b) jf++;
+  kf = (int)(b - (long long)jf * (jf - 1) / 2);
+}
+
+// k_ba_schur_off — CTA per camera pair with common points (j > k, both free): S_jk = - sum_i W_ij V*_i^-1 W_ik^T
+// over the points seen by both, in POINT order (the reference walks the points and their scripts,
+// Bundle.cc:410-446).  The pair-major list (blk_off, pr_mj, pr_mk) and the list of non-empty pairs (longest
+// first) are built once per Compute.  Pairs are fetched through an atomic counter (the order of the fetches
+// does not matter: every block is written by exactly one CTA, in its own fixed order).
+__global__ void __launch_bounds__(kOffThreads) k_ba_schur_off(BundleDev d) {
+  __shared__ double sv[36 * (kOffThreads + 1)];
+  __shared__ int s_idx;
   const int t = threadIdx.x;
-  if (t < 36) {
-    const int r = t / 6, cc = t % 6;
-    const int a = r >= cc ? r : cc, b = r >= cc ? cc : r;
-    double v = d.U[21 * c + a * (a + 1) / 2 + b];
-    if (r == cc) v *= (1.0 + lambda);
-    d.S[(size_t)(row + r) * d.n + row + cc] = v;
-  } else if (t < 42) d.vE[row + t - 36] = d.epsA[6 * c + t - 36];
-}
-
-// Schur complement (Bundle.cc:365-453), two kernels.
-// k_ba_schur_diag — the diagonal blocks and vE: one thread per observation in list order,
-//   S_jj -= W_ij V*_i^-1 W_ij^T (lower triangle, 21 values),  vE_j -= W_ij V*_i^-1 epsB_i.
-// The list is usually camera-major, so a warp mostly shares one camera: the 27 values are summed over the
-// warp and added with one atomic each (as k_ba_jacobian does for U / epsA) instead of 1 200 atomics per
-// address and camera at C4; warps that straddle a camera boundary use per-lane atomics.
-__global__ void __launch_bounds__(128) k_ba_schur_diag(BundleDev d) {
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  int jrow = -1;
-  double D[21], e[6];
+  const int n_nz = d.pair_info[0];
+  while (true) {
+    if (t == 0) s_idx = (int)atomicAdd(d.tickets + 3, 1u);
+    __syncthreads();
+    const int idx = s_idx;
+    if (idx >= n_nz) break;
+    const int b = d.nz_blocks[idx];
+    int jf, kf;
+    pair_decode(b, jf, kf);
+    double acc = 0.0;
+    const int o0 = d.blk_off[b], o1 = d.blk_off[b + 1];
+    for (int base = o0; base < o1; base += kOffThreads) {
+      const int o = base + t;
+      double v[36];
 #pragma unroll
-  for (int q = 0; q < 21; q++) D[q] = 0.0;
+      for (int q = 0; q < 36; q++) v[q] = 0.0;
+      if (o < o1) {
+        const int mj = d.pr_mj[o], mk = d.pr_mk[o];
+        if (d.m_state[mj] == M_ALIVE && d.m_state[mk] == M_ALIVE) {
+          const double* Vi = d.Vinv + 9 * (size_t)d.m_pt[mj];
+          const double* Wj = d.m_W + 18 * (size_t)mj;
+          const double* Wk = d.m_W + 18 * (size_t)mk;
+          double WV[18];
 #pragma unroll
-  for (int q = 0; q < 6; q++) e[q] = 0.0;
-  if (m < d.n_meas && d.m_state[m] == M_ALIVE) {
-    jrow = d.cam_row[d.m_cam[m]];
-    if (jrow >= 0) {
-      const int i = d.m_pt[m];
-      const double* Vi = d.Vinv + 9 * (size_t)i;
-      const double* ve = d.Ve + 3 * (size_t)i;
-      const double* W = d.m_W + 18 * (size_t)m;
-      double Wr[18], WV[18];
+          for (int r = 0; r < 6; r++)
 #pragma unroll
-      for (int q = 0; q < 18; q++) Wr[q] = W[q];
+            for (int cc = 0; cc < 3; cc++) WV[3 * r + cc] = Wj[3 * r] * Vi[cc] + Wj[3 * r + 1] * Vi[3 + cc] + Wj[3 * r + 2] * Vi[6 + cc];
+          double wk[18];
 #pragma unroll
-      for (int r = 0; r < 6; r++)
+          for (int q = 0; q < 18; q++) wk[q] = Wk[q];
 #pragma unroll
-        for (int c = 0; c < 3; c++) WV[3 * r + c] = Wr[3 * r] * Vi[c] + Wr[3 * r + 1] * Vi[3 + c] + Wr[3 * r + 2] * Vi[6 + c];
-      int o = 0;
+          for (int r = 0; r < 6; r++)
 #pragma unroll
-      for (int r = 0; r < 6; r++)
-#pragma unroll
-        for (int c = 0; c <= r; c++) D[o++] = -(WV[3 * r] * Wr[3 * c] + WV[3 * r + 1] * Wr[3 * c + 1] + WV[3 * r + 2] * Wr[3 * c + 2]);
-#pragma unroll
-      for (int r = 0; r < 6; r++) e[r] = -(Wr[3 * r] * ve[0] + Wr[3 * r + 1] * ve[1] + Wr[3 * r + 2] * ve[2]);
-    }
-  }
-  const unsigned contrib = __ballot_sync(kFull, jrow >= 0);
-  if (!contrib) return;
-  const int j0 = __shfl_sync(kFull, jrow, __ffs(contrib) - 1);
-  const bool uniform = __all_sync(kFull, jrow < 0 || jrow == j0);
-  if (uniform) {
-    int o = 0;
-#pragma unroll
-    for (int r = 0; r < 6; r++)
-#pragma unroll
-      for (int c = 0; c <= r; c++) {
-        const double v = warp_sum(D[o++]);
-        if (lane == 0) atomicAdd(&d.S[(size_t)(j0 + r) * d.n + j0 + c], v);
+            for (int cc = 0; cc < 6; cc++) v[6 * r + cc] = WV[3 * r] * wk[3 * cc] + WV[3 * r + 1] * wk[3 * cc + 1] + WV[3 * r + 2] * wk[3 * cc + 2];
+        }
       }
-#pragma unroll
-    for (int r = 0; r < 6; r++) {
-      const double v = warp_sum(e[r]);
-      if (lane == 0) atomicAdd(&d.vE[j0 + r], v);
+      seg_round<36, kOffThreads>(sv, v, min(kOffThreads, o1 - base), acc, true);
     }
-  } else if (jrow >= 0) {
-    int o = 0;
-#pragma unroll
-    for (int r = 0; r < 6; r++)
-#pragma unroll
-      for (int c = 0; c <= r; c++) atomicAdd(&d.S[(size_t)(jrow + r) * d.n + jrow + c], D[o++]);
-#pragma unroll
-    for (int r = 0; r < 6; r++) atomicAdd(&d.vE[jrow + r], e[r]);
-  }
-}
-
-// k_ba_schur — the off-diagonal blocks: warp per point, lane per camera pair (j > k) observing it, both
-// cameras free, both measurements good:  S_jk -= W_ij V*_i^-1 W_ik^T  (36 f64 atomics into the lower S).
-__global__ void __launch_bounds__(256) k_ba_schur(BundleDev d) {
-  const int i = d.p_lo + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (i >= d.p_hi) return;
-  const int lane = threadIdx.x & 31;
-  const int o0 = d.pt_off[i], k = d.pt_off[i + 1] - o0;
-  if (k < 2) return;
-  double Vi[9];
-#pragma unroll
-  for (int q = 0; q < 9; q++) Vi[q] = d.Vinv[9 * i + q];
-  const int npairs = k * (k - 1) / 2;
-  for (int pr = lane; pr < npairs; pr += 32) {
-    // pr -> (a, b), b < a:  pr = a (a - 1) / 2 + b
-    int a = (int)((sqrt(8.0 * pr + 1.0) + 1.0) * 0.5);
-    while (a * (a - 1) / 2 > pr) a--;
-    while ((a + 1) * a / 2 <= pr) a++;
-    const int b = pr - a * (a - 1) / 2;
-    const int mj = d.pt_meas[o0 + a], mk = d.pt_meas[o0 + b];
-    if (d.m_state[mj] != M_ALIVE || d.m_state[mk] != M_ALIVE) continue;
-    const int jrow = d.cam_row[d.m_cam[mj]], krow = d.cam_row[d.m_cam[mk]];
-    if (jrow < 0 || krow < 0) continue;
-    const double* Wj = d.m_W + 18 * mj;
-    const double* Wk = d.m_W + 18 * mk;
-    double WV[18];
-#pragma unroll
-    for (int r = 0; r < 6; r++)
-#pragma unroll
-      for (int c = 0; c < 3; c++) WV[3 * r + c] = Wj[3 * r] * Vi[c] + Wj[3 * r + 1] * Vi[3 + c] + Wj[3 * r + 2] * Vi[6 + c];
-    double* Sb = d.S + (size_t)jrow * d.n + krow;
-#pragma unroll
-    for (int r = 0; r < 6; r++)
-#pragma unroll
-      for (int c = 0; c < 6; c++) {
-        const double v = WV[3 * r] * Wk[3 * c] + WV[3 * r + 1] * Wk[3 * c + 1] + WV[3 * r + 2] * Wk[3 * c + 2];
-        atomicAdd(&Sb[(size_t)r * d.n + c], -v);
-      }
+    if (t < 36) d.S[(size_t)(6 * jf + t / 6) * d.n + 6 * kf + t % 6] = acc;
+    __syncthreads();  // s_idx is rewritten next
   }
 }
 
@@ -530,554 +628,125 @@ __global__ void __launch_bounds__(256) k_ba_mirror(double* S, int n) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Dense solve  delta_a = S^-1 vE  (Bundle.cc:457-458, TooN Cholesky<>: square-root-free LDL^T, no
-// pivoting, no failure path — a non-positive-definite S yields inf/NaN exactly as in the reference).
-// Right-looking blocked factorisation, panel width 64, with the forward substitution folded in:
-//   k_ldlt_panel   every CTA applies the previous panel's pending update to the panel's 64 columns (its
-//                  diagonal block and its own 64 rows), factors the 64x64 diagonal block in shared memory
-//                  (redundantly: it saves a launch and a dependency), then solves its 64 rows of the panel,
-//                  four threads per row:  w = a L11^-T  (= L21 D1),  L21 = w D1^-1, and applies the panel
-//                  to the right-hand side:  y2 -= L21 y1.  Operands arrive by cp.async.bulk + mbarrier.
-//   k_ldlt_update  trailing update  A22 -= (L21 D1) L21^T  on the lower triangle, 128x64 tiles,
-//                  K = 64: the one genuine dense contraction of either hot path.  FP64 has no
-//                  tcgen05 form, so it runs on the f64 tensor pipe (DMMA, mma.sync m8n8k4);
-//                  operand tiles are staged in shared memory by the TMA engine (one 512-byte
-//                  cp.async.bulk per row, completion on an mbarrier), rows padded to 68 doubles so
-//                  that fragment loads are bank-conflict free.
-//   k_ldlt_step    panel k and the tail of panel k-1's trailing update in one grid (the late, latency-bound
-//                  part of the factorisation as back-to-back launches on one stream).
-//   k_ldlt_back    z = D^-1 y (k_ldlt_scale),  L^T x = z: all panels in one launch by an 8-CTA cluster.
+// The pair-major list behind k_ba_schur_off (GenerateOffDiagScripts regrouped by camera pair,
+// Bundle.cc:572-599), built on the device once per Compute, without a sort:
+//   k_ba_pair_count  thread per point: +1 (integer atomics: exact) for every pair of free cameras observing it
+//   k_ba_pair_scan   one CTA: blk_off = exclusive scan of the counts; the non-empty pairs, long ones first
+//   k_ba_pair_fill   CTA per non-empty pair (j, k): walks the shorter of the two cameras' point-ordered lists,
+//                    keeps the points the other camera observes too (a point's list has <= a few entries) and
+//                    compacts them in order: the triples of a pair come out by ascending point id by construction.
 // ---------------------------------------------------------------------------------------------
-constexpr int kNB = 64;     // panel width
-constexpr int kUTM = 128;   // trailing-update tile rows
-constexpr int kUTN = 64;    // trailing-update tile columns
-constexpr int kLds = kNB + 4;  // padded shared-memory row, doubles
-constexpr int kUpdateSmem = (kUTM + kUTN) * kLds * (int)sizeof(double) + 16;
-
-// LDL^T of a 64x64 block by 256 threads, eight sub-panels of eight columns.  The trailing matrix lives in
-// registers (thread (ty = tid / 16, tx = tid % 16) owns rows ty + 16 i x columns tx + 16 j, i, j < 4); the
-// current 64 x 8 sub-panel is handled by threads 0..63, one row each.  Every row thread factors the 8x8
-// diagonal block of the sub-panel REDUNDANTLY in its own registers (36 broadcast loads), so that pivots,
-// reciprocals and the L D values of the pivot rows need no exchange: the serial chain per pivot is
-// reciprocal -> multiply -> FMA, with the thread's own row riding along.  Then all warps apply the rank-8
-// update to their register tiles from shared memory (L in `a`, L D in `us`) and the owners of the next
-// eight columns hand them over: two block barriers per sub-panel, 16 per block instead of 64.
-// The right-hand side rides along with the row threads (y_r -= l_r y_col: the forward substitution L y' = y).
-// L = value * (1 / d) as TooN's Cholesky does, subtractions in ascending column order as in its
-// left-looking loop.  Result: `a` holds L (strict lower) and D (diagonal), `ysh` the forward-substituted
-// right-hand side, `dinv` the reciprocals of D.  Entries above the diagonal are scratch.
-constexpr int kPanelThreads = 256;
-constexpr int kFuseTailTiles = 576;  // tails of at most this many 128x64 tiles ride in the next panel's launch (k_ldlt_step)
-constexpr int kPanelRows = 64;  // rows of the panel solved per CTA (four threads per row; more CTAs beat fuller CTAs here)
-#ifdef PTAM_PANEL_DEBUG
-__device__ long long g_dbg[8];
-#define DBG_T(k) if (blockIdx.x == 0 && threadIdx.x == 0) { const long long now = clock64(); atomicAdd((unsigned long long*)&g_dbg[k], (unsigned long long)(now - t_prev)); t_prev = now; }
-#else
-#define DBG_T(k)
-#endif
-constexpr int kLda = kNB + 2;  // even row pitch: (row, even column) pairs are 16-byte aligned
-
-PTAM_DEV void block_ldlt64(double (*a)[kLda], double (*us)[8], double* dinv, double* ysh, int nb) {
-  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-  double ar[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; i++)
-#pragma unroll
-    for (int j = 0; j < 4; j++) ar[i][j] = a[ty + 16 * i][tx + 16 * j];
-  double yr = tid < kNB ? ysh[tid] : 0.0;  // threads 0..63 own one row of the current sub-panel each
-  if (tid < kNB) dinv[tid] = 1.0;
-  __syncthreads();
-#pragma unroll 1
-  for (int c0 = 0; c0 < kNB; c0 += 8) {
-    if (c0 >= nb) break;  // the identity padding of a short last block needs no work
-    if (tid < kNB) {
-      const int r = tid;
-      // the 8x8 diagonal block of the sub-panel and its right-hand side, redundantly in every row thread
-      // (broadcast loads): pivots, reciprocals and the L D values then need no exchange at all
-      double dg[8][8], yv[8], pv[8], uv[8];
-#pragma unroll
-      for (int i = 0; i < 8; i++) {
-#pragma unroll
-        for (int j = 0; j <= i; j++) dg[i][j] = a[c0 + i][c0 + j];
-        yv[i] = ysh[c0 + i];
-      }
-      {
-        const double2* row = reinterpret_cast<const double2*>(&a[r][c0]);
-#pragma unroll
-        for (int j = 0; j < 8; j += 2) { const double2 v = row[j >> 1]; pv[j] = v.x; pv[j + 1] = v.y; }
-      }
-      // the two row warps have read the diagonal block before its owners overwrite it below
-      asm volatile("bar.sync 1, 64;" ::: "memory");
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const double rcp = 1.0 / dg[j][j];  // (a MUFU seed + two Newton steps was measured slower: 15.6 -> 16.6 us per block)
-        if (r == c0 + j) dinv[c0 + j] = rcp;
-        // own row (rows of the finished part and the pivot row itself stay as they are)
-        const bool below = r > c0 + j;
-        const double v = pv[j];
-        const double l = below ? v * rcp : 0.0;
-#pragma unroll
-        for (int q = j + 1; q < 8; q++) pv[q] -= l * dg[q][j];  // dg[q][j] still holds L D of row c0 + q
-        yr -= l * yv[j];
-        uv[j] = below ? v : 0.0;
-        if (below) pv[j] = l;
-        // the diagonal block itself
-#pragma unroll
-        for (int i = j + 1; i < 8; i++) {
-          const double li = dg[i][j] * rcp;
-#pragma unroll
-          for (int q = j + 1; q <= i; q++) dg[i][q] -= li * dg[q][j];
-          yv[i] -= li * yv[j];
-        }
-      }
-      if (r >= c0) {
-        double2* row = reinterpret_cast<double2*>(&a[r][c0]);
-#pragma unroll
-        for (int j = 0; j < 8; j += 2) row[j >> 1] = make_double2(pv[j], pv[j + 1]);
-      }
-      double2* urow = reinterpret_cast<double2*>(&us[r][0]);
-#pragma unroll
-      for (int j = 0; j < 8; j += 2) urow[j >> 1] = make_double2(uv[j], uv[j + 1]);
-      ysh[r] = yr;
+__global__ void __launch_bounds__(256) k_ba_pair_count(BundleDev d, int* blk_cnt) {
+  const int i = d.p_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.p_hi) return;
+  const int o0 = d.pt_off[i], o1 = d.pt_off[i + 1];
+  for (int a = o0 + 1; a < o1; a++) {
+    const int jrow = d.cam_row[d.pt_cam[a]];
+    if (jrow < 0) continue;
+    const int jf = jrow / 6;
+    for (int b = o0; b < a; b++) {
+      const int krow = d.cam_row[d.pt_cam[b]];
+      if (krow >= 0) atomicAdd(&blk_cnt[(size_t)jf * (jf - 1) / 2 + krow / 6], 1);
     }
+  }
+}
+
+// info[0] = non-empty pairs, info[1] = long ones among them, info[2] = triples
+__global__ void __launch_bounds__(1024) k_ba_pair_scan(const int* cnt, int* off, int* nz, int* info, long long n) {
+  __shared__ int ws[3][32];
+  __shared__ int carry[3];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kPer = 8;
+  for (int pass = 0; pass < 2; pass++) {  // pass 0: offsets + long pairs; pass 1: the short pairs behind the long ones
+    if (threadIdx.x == 0) { carry[0] = 0; carry[1] = pass ? info[1] : 0; carry[2] = 0; }
     __syncthreads();
-    const int t0 = c0 + 8;  // first row / column of the trailing matrix
-    if (t0 < kNB) {
+    for (long long base = 0; base < n; base += (long long)blockDim.x * kPer) {
+      const long long i0 = base + (long long)threadIdx.x * kPer;
+      int c[kPer], s0 = 0, s1 = 0;
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        if (16 * i + 15 < t0) continue;
-        double l[8];
-        {
-          const double2* row = reinterpret_cast<const double2*>(&a[ty + 16 * i][c0]);
+      for (int q = 0; q < kPer; q++) {
+        c[q] = i0 + q < n ? cnt[i0 + q] : 0;
+        s0 += c[q];
+        s1 += pass ? (c[q] > 0 && c[q] < kLongBlock) : (c[q] >= kLongBlock);
+      }
+      int i0s = s0, i1s = s1;
 #pragma unroll
-          for (int q = 0; q < 8; q += 2) { const double2 v = row[q >> 1]; l[q] = v.x; l[q + 1] = v.y; }
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u0 = __shfl_up_sync(kFull, i0s, o), u1 = __shfl_up_sync(kFull, i1s, o);
+        if (lane >= o) { i0s += u0; i1s += u1; }
+      }
+      if (lane == 31) { ws[0][warp] = i0s; ws[1][warp] = i1s; }
+      __syncthreads();
+      if (warp == 0) {
+        int w0 = ws[0][lane], w1 = ws[1][lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int u0 = __shfl_up_sync(kFull, w0, o), u1 = __shfl_up_sync(kFull, w1, o);
+          if (lane >= o) { w0 += u0; w1 += u1; }
         }
-        if (ty + 16 * i < t0) {  // rows of the finished sub-panels: their entries here are scratch, keep them finite
+        ws[0][lane] = w0; ws[1][lane] = w1;
+      }
+      __syncthreads();
+      int e0 = carry[0] + (warp ? ws[0][warp - 1] : 0) + i0s - s0;
+      int e1 = carry[1] + (warp ? ws[1][warp - 1] : 0) + i1s - s1;
 #pragma unroll
-          for (int q = 0; q < 8; q++) l[q] = 0.0;
-        }
-#pragma unroll
-        for (int j = 0; j <= i; j++) {
-          if (16 * j + 15 < t0) continue;
-          const double2* urow = reinterpret_cast<const double2*>(&us[tx + 16 * j][0]);
-          double acc = ar[i][j];
-#pragma unroll
-          for (int q = 0; q < 8; q += 2) { const double2 v = urow[q >> 1]; acc -= l[q] * v.x; acc -= l[q + 1] * v.y; }
-          ar[i][j] = acc;
+      for (int q = 0; q < kPer; q++) {
+        if (i0 + q < n) {
+          if (!pass) off[i0 + q] = e0;
+          const bool take = pass ? (c[q] > 0 && c[q] < kLongBlock) : (c[q] >= kLongBlock);
+          if (take) nz[e1++] = (int)(i0 + q);
+          e0 += c[q];
         }
       }
-      // the owners of the next eight columns hand them to warp 0 (rows >= t0)
-      const int jn = t0 >> 4;
-      if ((tx >> 3) == ((t0 >> 3) & 1)) {
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const int r = ty + 16 * i;
-          if (r >= t0) {
-            // ar[i][jn] with a run-time jn: select without dynamic register indexing
-            const double v = jn == 0 ? ar[i][0] : jn == 1 ? ar[i][1] : jn == 2 ? ar[i][2] : ar[i][3];
-            a[r][tx + 16 * jn] = v;
-          }
-        }
-      }
+      __syncthreads();
+      if (threadIdx.x == 0) { carry[0] += ws[0][31]; carry[1] += ws[1][31]; }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      if (!pass) { off[n] = carry[0]; info[2] = carry[0]; info[1] = carry[1]; }
+      else info[0] = carry[1];
     }
     __syncthreads();
   }
 }
 
-// Shared memory of k_ldlt_panel (dynamic): the diagonal block, the rank-8 operand, the right-hand side and
-// the reciprocals, plus three 64x64 operands of the PENDING update (see below); the third is reused for
-// the updated rows of this CTA.
-constexpr int kPanelSmem = (4 * kNB * kLda + kNB * 8 + 2 * kNB) * (int)sizeof(double) + 16;  // + the mbarrier of the bulk loads
-
-// Panel k, fused with the head of panel k-1's trailing update.  The columns of panel k still miss the
-// contribution of panel k-1 (the tail kernel of panel k-1 only covers the column blocks from k+1 on), so
-// every CTA first applies it itself:  A[rows][cols k] += Wp_prev[rows] L_head^T  for the diagonal block
-// (all CTAs, redundantly, like the factorisation) and for its own 64 rows, 4x4 register tiles over K = 64.
-// That makes the chain one kernel per panel instead of panel -> head update -> panel.
-PTAM_DEV void ldlt_panel_body(double* A, double* Wp, const double* Wprev, double* y, int n, int k0, int block) {
-  extern __shared__ __align__(16) unsigned char panel_smem[];
-  double (*a)[kLda] = reinterpret_cast<double (*)[kLda]>(panel_smem);
-  double (*lh)[kLda] = a + kNB;    // L of the diagonal block's rows in panel k-1's columns
-  double (*wd)[kLda] = lh + kNB;   // Wp_prev rows of the diagonal block
-  double (*wo)[kLda] = wd + kNB;   // Wp_prev rows of this CTA, then the updated rows themselves
-  double (*us)[8] = reinterpret_cast<double (*)[8]>(wo + kNB);
-  double* y1 = reinterpret_cast<double*>(us + kNB);
-  double* dinv = y1 + kNB;
-  const int nb = min(kNB, n - k0);
-  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-  const int row0 = k0 + nb + block * kPanelRows;
-  const int rows_own = min(kPanelRows, n - row0);  // <= 0: the last panel's single CTA has no rows below the block
-  const bool pend = Wprev != nullptr;
-#ifdef PTAM_PANEL_DEBUG
-  long long t_prev = clock64();
-#endif
-  if (nb == kNB) {
-    // full panel: the four 64x64 operands arrive as 512-byte rows through the TMA engine (one cp.async.bulk
-    // per row and thread, completion on an mbarrier) while the threads fetch their register tiles below.
-    // `a` then also holds S's (finite, never used) values above the diagonal: block_ldlt64 treats them as scratch.
-    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(dinv + kNB);
-    const unsigned mbar_a = (unsigned)__cvta_generic_to_shared(mbar);
-    if (tid == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_a));
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const int rows_w = max(0, rows_own);
-    if (tid == 0) {
-      const unsigned bytes = (unsigned)(kNB + (pend ? 2 * kNB + rows_w : 0)) * kNB * (unsigned)sizeof(double);
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_a), "r"(bytes) : "memory");
-    }
-    {
-      const int which = tid >> 6, r = tid & 63;  // 0: a, 1: lh, 2: wd, 3: wo
-      const double* src = nullptr;
-      double* dst = which == 0 ? a[r] : which == 1 ? lh[r] : which == 2 ? wd[r] : wo[r];
-      if (which == 0) src = A + (size_t)(k0 + r) * n + k0;
-      else if (pend) {
-        if (which == 1) src = A + (size_t)(k0 + r) * n + (k0 - kNB);
-        else if (which == 2) src = Wprev + (size_t)(k0 + r) * kNB;
-        else if (r < rows_w) src = Wprev + (size_t)(row0 + r) * kNB;
+__global__ void __launch_bounds__(128) k_ba_pair_fill(BundleDev d, int* pr_mj, int* pr_mk) {
+  __shared__ int wcnt[4];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int n_nz = d.pair_info[0];
+  for (int idx = blockIdx.x; idx < n_nz; idx += gridDim.x) {
+    const int b = d.nz_blocks[idx];
+    int jf, kf;
+    pair_decode(b, jf, kf);
+    const int cj = d.free_cam[jf], ck = d.free_cam[kf];
+    const bool walk_j = d.cam_off[cj + 1] - d.cam_off[cj] <= d.cam_off[ck + 1] - d.cam_off[ck];
+    const int cw = walk_j ? cj : ck, co = walk_j ? ck : cj;  // walked camera, other camera
+    const int o0 = d.cam_off[cw], o1 = d.cam_off[cw + 1];
+    int at = d.blk_off[b];
+    for (int base = o0; base < o1; base += blockDim.x) {
+      int mw = -1, mo = -1;
+      if (base + t < o1) {
+        mw = d.cam_meas_pt[base + t];
+        const int i = d.m_pt[mw];
+        for (int o = d.pt_off[i]; o < d.pt_off[i + 1]; o++)
+          if (d.pt_cam[o] == co) { mo = d.pt_meas[o]; break; }
       }
-      if (src) {
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"((unsigned)(kNB * sizeof(double))), "r"(mbar_a) : "memory");
-      } else if (pend && which == 3) {
-        for (int c = 0; c < kNB; c++) dst[c] = 0.0;  // rows past the matrix
+      const unsigned bal = __ballot_sync(kFull, mo >= 0);
+      if (lane == 0) wcnt[warp] = __popc(bal);
+      __syncthreads();
+      int before = 0, total = 0;
+#pragma unroll
+      for (int w = 0; w < 4; w++) { if (w < warp) before += wcnt[w]; total += wcnt[w]; }
+      if (mo >= 0) {
+        const int p = at + before + __popc(bal & ((1u << lane) - 1));
+        pr_mj[p] = walk_j ? mw : mo;
+        pr_mk[p] = walk_j ? mo : mw;
       }
-    }
-    if (tid < kNB) y1[tid] = y[k0 + tid];
-  } else {
-    for (int i = tid; i < kNB * kNB; i += blockDim.x) {  // the short last panel (identity padding, no rows below it)
-      const int r = i / kNB, c = i % kNB;
-      a[r][c] = (r < nb && c <= r) ? A[(size_t)(k0 + r) * n + k0 + c] : (r == c ? 1.0 : 0.0);
-      if (pend) {
-        lh[r][c] = r < nb ? A[(size_t)(k0 + r) * n + (k0 - kNB) + c] : 0.0;
-        wd[r][c] = r < nb ? Wprev[(size_t)(k0 + r) * kNB + c] : 0.0;
-        wo[r][c] = r < rows_own ? Wprev[(size_t)(row0 + r) * kNB + c] : 0.0;
-      }
-    }
-    if (tid < kNB) y1[tid] = tid < nb ? y[k0 + tid] : 0.0;
-  }
-  // this CTA's rows of the panel, as 4x4 register tiles (rows ty + 16 i, columns tx + 16 j)
-  double co[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; i++)
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int r = ty + 16 * i;
-      co[i][j] = r < rows_own ? A[(size_t)(row0 + r) * n + k0 + tx + 16 * j] : 0.0;
-    }
-  if (nb == kNB) {
-    const unsigned mbar_a = (unsigned)__cvta_generic_to_shared(dinv + kNB);
-    unsigned ok = 0;
-    while (!ok)
-      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
-                   : "=r"(ok) : "r"(mbar_a) : "memory");
-  }
-  __syncthreads();  // also covers the plain stores
-  DBG_T(0)
-  if (pend) {
-    double cd[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-      for (int j = 0; j < 4; j++) cd[i][j] = a[ty + 16 * i][tx + 16 * j];
-#pragma unroll 2
-    for (int q = 0; q < kNB; q += 2) {
-      double2 vd[4], vo[4], vl[4];
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        vd[i] = *reinterpret_cast<const double2*>(&wd[ty + 16 * i][q]);
-        vo[i] = *reinterpret_cast<const double2*>(&wo[ty + 16 * i][q]);
-        vl[i] = *reinterpret_cast<const double2*>(&lh[tx + 16 * i][q]);
-      }
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          if (j <= i) { cd[i][j] += vd[i].x * vl[j].x; cd[i][j] += vd[i].y * vl[j].y; }  // tiles above the diagonal are never stored
-          co[i][j] += vo[i].x * vl[j].x; co[i][j] += vo[i].y * vl[j].y;
-        }
-    }
-    __syncthreads();  // every thread is done with wd / wo / lh
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int r = ty + 16 * i, c = tx + 16 * j;
-        if (r < nb && c <= r) a[r][c] = cd[i][j];  // the identity padding of a short last block stays
-      }
-  }
-#pragma unroll
-  for (int i = 0; i < 4; i++)
-#pragma unroll
-    for (int j = 0; j < 4; j++) wo[ty + 16 * i][tx + 16 * j] = co[i][j];
-  __syncthreads();
-  DBG_T(1)
-  block_ldlt64(a, us, dinv, y1, nb);
-  DBG_T(2)
-  if (block == 0) {
-    for (int i = tid; i < nb * nb; i += blockDim.x) {
-      const int r = i / nb, c = i % nb;
-      if (c <= r) A[(size_t)(k0 + r) * n + k0 + c] = a[r][c];
-    }
-    if (tid < nb) y[k0 + tid] = y1[tid];
-  }
-  DBG_T(3)
-  // ---- rows below the block, w L11^T = a: FOUR threads per row (r = tid / 4), thread q = tid % 4 owns the 16
-  // columns c = q (mod 4).  Right-looking, two columns per step (same expressions, same order per element as
-  // a thread-per-row loop): the two pivots of the step travel by shuffle from their owners, then every thread
-  // updates its own columns to the right with one 16-byte broadcast load of (L[c2][c], L[c2][c+1]) per
-  // column.  All 256 threads work and a thread holds 16 values instead of 64 (6.0 -> 4.95 us per panel; a
-  // four-columns-per-step variant with the 4x4 triangle solved redundantly was slower, 5.85 us).
-  const int r = tid >> 2, q = tid & 3, lane = tid & 31;
-  const int row = row0 + r;
-  double x[kNB / 4];
-#pragma unroll
-  for (int j = 0; j < kNB / 4; j++) x[j] = wo[r][4 * j + q];
-  DBG_T(4)
-#pragma unroll
-  for (int c = 0; c < kNB; c += 2) {
-    const int jc = c >> 2;  // the owners of columns c and c + 1 hold them in x[jc]
-    const double xc0 = __shfl_sync(kFull, x[jc], (lane & ~3) | (c & 3));
-    if (q == ((c + 1) & 3)) x[jc] -= xc0 * a[c + 1][c];
-    const double xc1 = __shfl_sync(kFull, x[jc], (lane & ~3) | ((c + 1) & 3));
-#pragma unroll
-    for (int j = jc; j < kNB / 4; j++) {
-      const int c2 = 4 * j + q;
-      if (j > jc || c2 > c + 1) {
-        const double2 l = *reinterpret_cast<const double2*>(&a[c2][c]);
-        x[j] -= xc0 * l.x + xc1 * l.y;
-      }
-    }
-  }
-  DBG_T(5)
-  double dot = 0.0;
-  if (row < n) {
-    double* Ar = A + (size_t)row * n + k0;
-    double* Wr = Wp + (size_t)row * kNB;  // holds -(L21 D1): the update kernel accumulates C += Wp L21^T
-#pragma unroll
-    for (int j = 0; j < kNB / 4; j++) {
-      const int c = 4 * j + q;
-      Wr[c] = -x[j];
-      const double l = x[j] * dinv[c];  // value * (1 / d), as TooN does
-      Ar[c] = l;
-      dot += l * y1[c];
-    }
-  }
-  dot += __shfl_xor_sync(kFull, dot, 1);
-  dot += __shfl_xor_sync(kFull, dot, 2);
-  if (q == 0 && row < n) y[row] -= dot;
-  DBG_T(6)
-}
-
-__global__ void __launch_bounds__(kPanelThreads) k_ldlt_panel(double* A, double* Wp, const double* Wprev, double* y, int n, int k0) {
-  ldlt_panel_body(A, Wp, Wprev, y, n, k0, (int)blockIdx.x);
-}
-
-PTAM_DEV unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-// part 0: all tiles; part 1: only the first column block (the next panel's 64 columns: look-ahead
-// head); part 2: everything else (look-ahead tail, runs on the second stream).
-PTAM_DEV void ldlt_update_body(double* A, const double* Wp, int n, int k0, int part, int block) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* sW = reinterpret_cast<double*>(smem_raw);            // [kUTM][kLds]  -(L21 D1) rows of the i-tile
-  double* sL = sW + kUTM * kLds;                                // [kUTN][kLds]  L21 rows of the j-tile
-  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(sL + kUTN * kLds);
-  const int r0 = k0 + kNB;
-  int bi, bj;
-  if (part == 1) { bi = block; bj = 0; }
-  else if (part == 2) {
-    // row block bi has column blocks bj = 1 .. 2 bi + 1: 2 bi + 1 tiles, bi^2 before it
-    bi = (int)sqrt((double)block);
-    while (bi * bi > block) bi--;
-    while ((bi + 1) * (bi + 1) <= block) bi++;
-    bj = block - bi * bi + 1;
-  } else {
-    // row block bi (128 rows) has column blocks bj = 0 .. 2 bi + 1 (64 columns): bi (bi + 1) tiles before it
-    bi = (int)((sqrt(4.0 * block + 1.0) - 1.0) * 0.5);
-    while (bi * (bi + 1) > block) bi--;
-    while ((bi + 1) * (bi + 2) <= block) bi++;
-    bj = block - bi * (bi + 1);
-  }
-  const int i0 = r0 + bi * kUTM, j0 = r0 + bj * kUTN;
-  if (j0 >= n) return;  // the last row block may be short of its second diagonal column block
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const unsigned mbar_a = smem_u32(mbar);
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_a));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  // ---- TMA-engine staging: one 512-byte bulk copy per tile row (192 rows, threads 0..191)
-  {
-    const int rows_i = min(kUTM, n - i0), rows_j = min(kUTN, n - j0);
-    if (tid == 0) {
-      const unsigned bytes = (unsigned)(rows_i + rows_j) * kNB * (unsigned)sizeof(double);
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_a), "r"(bytes) : "memory");
-    }
-    if (tid < kUTM + kUTN) {
-      const double* src = nullptr;
-      double* dst;
-      if (tid < kUTM) { dst = sW + tid * kLds; if (tid < rows_i) src = Wp + (size_t)(i0 + tid) * kNB; }
-      else { const int r = tid - kUTM; dst = sL + r * kLds; if (r < rows_j) src = A + (size_t)(j0 + r) * n + k0; }
-      if (src) {
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(dst)), "l"(src), "r"((unsigned)(kNB * sizeof(double))), "r"(mbar_a) : "memory");
-      } else {
-        for (int c = 0; c < kNB; c++) dst[c] = 0.0;  // rows past the matrix: defined operands, results never stored
-      }
-    }
-  }
-  // ---- accumulators start as the C tile (prefetched while the operand tiles are in flight)
-  // 8 warps = 4 (32-row slabs) x 2 (32-column slabs); 4 x 4 m8n8k4 tiles per warp
-  const int wm = warp & 3, wn = warp >> 2;
-  const bool active = !(j0 + wn * 32 > i0 + wm * 32 + 31);  // warp tile not entirely above the diagonal
-  double acc[4][4][2];
-  if (active) {
-#pragma unroll
-    for (int mi = 0; mi < 4; mi++) {
-      const int i = i0 + wm * 32 + mi * 8 + (lane >> 2);
-      const double* Ci = A + (size_t)min(i, n - 1) * n;
-#pragma unroll
-      for (int ni = 0; ni < 4; ni++) {
-        const int j = j0 + wn * 32 + ni * 8 + 2 * (lane & 3);
-        double2 v = make_double2(0.0, 0.0);
-        if (i < n && j + 1 <= i) v = *reinterpret_cast<const double2*>(Ci + j);
-        else if (i < n && j <= i) v.x = Ci[j];
-        acc[mi][ni][0] = v.x; acc[mi][ni][1] = v.y;
-      }
-    }
-  }
-  {
-    unsigned ok = 0;
-    while (!ok)
-      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
-                   : "=r"(ok) : "r"(mbar_a) : "memory");
-  }
-  __syncthreads();  // also covers the plain zero-fill stores
-  if (!active) return;
-  const double* pa = sW + (wm * 32 + (lane >> 2)) * kLds + (lane & 3);
-  const double* pb = sL + (wn * 32 + (lane >> 2)) * kLds + (lane & 3);
-#pragma unroll 4
-  for (int kk = 0; kk < kNB; kk += 4) {
-    double fa[4], fb[4];
-#pragma unroll
-    for (int mi = 0; mi < 4; mi++) fa[mi] = pa[mi * 8 * kLds + kk];
-#pragma unroll
-    for (int ni = 0; ni < 4; ni++) fb[ni] = pb[ni * 8 * kLds + kk];
-#pragma unroll
-    for (int mi = 0; mi < 4; mi++)
-#pragma unroll
-      for (int ni = 0; ni < 4; ni++)
-        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                     : "+d"(acc[mi][ni][0]), "+d"(acc[mi][ni][1]) : "d"(fa[mi]), "d"(fb[ni]));
-  }
-#pragma unroll
-  for (int mi = 0; mi < 4; mi++) {
-    const int i = i0 + wm * 32 + mi * 8 + (lane >> 2);
-    if (i >= n) continue;
-    double* Ci = A + (size_t)i * n;
-#pragma unroll
-    for (int ni = 0; ni < 4; ni++) {
-      const int j = j0 + wn * 32 + ni * 8 + 2 * (lane & 3);
-      if (j + 1 <= i) *reinterpret_cast<double2*>(Ci + j) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
-      else if (j <= i) Ci[j] = acc[mi][ni][0];
+      at += total;
+      __syncthreads();
     }
   }
 }
-
-__global__ void __launch_bounds__(256, 2) k_ldlt_update(double* A, const double* Wp, int n, int k0, int part) {
-  ldlt_update_body(A, Wp, n, k0, part, (int)blockIdx.x);
-}
-
-// One launch per step of the late factorisation: the CTAs of panel k (blocks 0 .. n_panel_ctas-1, dispatched
-// first: they are the chain) and, behind them, the tail of panel k-1's trailing update (column blocks from
-// k+1 on), which only depends on panel k-1 and touches nothing panel k reads or writes.  With both in one
-// grid the chain is a single stream of back-to-back kernels: no second stream, no event record / wait
-// between the panels (those cost ~9 us per panel).  Used once the tail is small enough to hide behind the
-// panel at one CTA per SM; the early, large tails keep their own two-CTAs-per-SM launches on the second stream.
-__global__ void __launch_bounds__(256) k_ldlt_step(double* A, double* Wp_cur, double* Wp_prev, double* y, int n, int k0, int n_panel_ctas) {
-  if ((int)blockIdx.x < n_panel_ctas) ldlt_panel_body(A, Wp_cur, Wp_prev, y, n, k0, (int)blockIdx.x);
-  else ldlt_update_body(A, Wp_prev, n, k0 - kNB, 2, (int)blockIdx.x - n_panel_ctas);
-}
-
-// Backward substitution  L^T x = D^-1 y  in ONE launch.  The panels are walked from the bottom up by a
-// thread-block cluster of kBackCtas CTAs; the steps are separated by the hardware cluster barrier
-// (arrive.release / wait.acquire, which also orders the z updates in global memory between the CTAs)
-// instead of 47 kernel boundaries (C4: 47 x 11 us before).  Per 64-row panel every CTA first solves the
-// panel's 64x64 block itself (x_p = L11^-T z_p; z_p is complete by then), CTA 0 stores it in x, then each
-// CTA applies the panel to its slice of the rows above:  z[i] -= sum_c L[k0 + c][i] x[k0 + c], i < k0
-// (coalesced along i).  The next panel's diagonal block is fetched into registers while the current one
-// is being solved.  `z` must hold D^-1 y (k_ldlt_scale).
-__global__ void __launch_bounds__(256) k_ldlt_scale(const double* A, const double* y, double* z, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) z[i] = y[i] / A[(size_t)i * n + i];
-}
-
-constexpr int kBackCtas = 8;       // portable cluster size
-constexpr int kBackThreads = 512;  // 4096 threads: one row of z per thread up to n = 4160
-
-__global__ void __cluster_dims__(kBackCtas, 1, 1) __launch_bounds__(kBackThreads, 1) k_ldlt_back(const double* A, double* z, double* x, int n) {
-  __shared__ double a[kNB][kNB + 1];
-  __shared__ double xs[kNB];
-  const int tid = threadIdx.x;
-  unsigned rank;
-  asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-  constexpr int kPer = kNB * kNB / kBackThreads;
-  double nxt[kPer];
-  auto fetch = [&](int k0) {  // strict lower triangle of the diagonal block at k0, zero elsewhere
-    const int nb = min(kNB, n - k0);
-#pragma unroll
-    for (int q = 0; q < kPer; q++) {
-      const int i = tid + q * kBackThreads, r = i / kNB, c = i % kNB;
-      nxt[q] = (r < nb && c < r) ? A[(size_t)(k0 + r) * n + k0 + c] : 0.0;
-    }
-  };
-  const int np = (n + kNB - 1) / kNB;
-  fetch((np - 1) * kNB);
-  for (int p = np - 1; p >= 0; p--) {
-    const int k0 = p * kNB, nb = min(kNB, n - k0);
-#pragma unroll
-    for (int q = 0; q < kPer; q++) {
-      const int i = tid + q * kBackThreads;
-      a[i / kNB][i % kNB] = nxt[q];
-    }
-    __syncthreads();
-    if (p > 0) fetch(k0 - kNB);
-    if (tid < 32) {  // L11^T x = z inside the block: lane r holds rows r and r + 32, pivots travel by shuffle
-      double x0 = tid < nb ? __ldcg(&z[k0 + tid]) : 0.0, x1 = tid + 32 < nb ? __ldcg(&z[k0 + tid + 32]) : 0.0;
-      for (int c = kNB - 1; c >= 32; c--) {
-        const double xc = __shfl_sync(kFull, x1, c - 32);
-        x0 -= a[c][tid] * xc;
-        if (tid + 32 < c) x1 -= a[c][tid + 32] * xc;
-      }
-      for (int c = 31; c >= 0; c--) {
-        const double xc = __shfl_sync(kFull, x0, c);
-        if (tid < c) x0 -= a[c][tid] * xc;
-      }
-      xs[tid] = x0; xs[tid + 32] = x1;
-    }
-    __syncthreads();
-    if (rank == 0 && tid < nb) x[k0 + tid] = xs[tid];
-    for (int i = (int)rank * kBackThreads + tid; i < k0; i += kBackCtas * kBackThreads) {
-      double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-      const double* Ac = A + (size_t)k0 * n + i;
-#pragma unroll 4
-      for (int c = 0; c < kNB; c += 4) {  // rows past nb are never touched: xs is zero there, but stay in bounds
-        if (c + 3 < nb) {
-          v0 += Ac[(size_t)c * n] * xs[c]; v1 += Ac[(size_t)(c + 1) * n] * xs[c + 1];
-          v2 += Ac[(size_t)(c + 2) * n] * xs[c + 2]; v3 += Ac[(size_t)(c + 3) * n] * xs[c + 3];
-        } else {
-          for (int q = c; q < nb; q++) v0 += Ac[(size_t)q * n] * xs[q];
-        }
-      }
-      __stcg(&z[i], __ldcg(&z[i]) - ((v0 + v1) + (v2 + v3)));
-    }
-    // every CTA of the cluster is done with this panel (and with a / xs) before the next one starts
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-  }
-}
-
 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_ba_point_update(BundleDev d) {
@@ -1110,14 +779,14 @@ __global__ void __launch_bounds__(256) k_ba_point_update(BundleDev d) {
     }
   }
   const double t = block_sum(ss, sh);
-  if (threadIdx.x == 0) atomicAdd(&d.scal[4], t);
+  grid_sum_finish(t, d.partials, d.tickets + 1, &d.scal[4], true);  // on top of the cameras' share (k_ba_cam_update)
 }
 
-__global__ void __launch_bounds__(128) k_ba_cam_update(BundleDev d) {
+// one CTA (launched before k_ba_point_update): the new camera poses and the cameras' share of |delta|^2
+__global__ void __launch_bounds__(256) k_ba_cam_update(BundleDev d) {
   __shared__ double sh[32];
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
   double ss = 0.0;
-  if (c < d.n_cams) {
+  for (int c = threadIdx.x; c < d.n_cams; c += blockDim.x) {
     const int row = d.cam_row[c];
     if (row < 0) {
       for (int k = 0; k < 12; k++) d.cam_se3_new[12 * c + k] = d.cam_se3[12 * c + k];
@@ -1130,7 +799,7 @@ __global__ void __launch_bounds__(128) k_ba_cam_update(BundleDev d) {
     }
   }
   const double t = block_sum(ss, sh);
-  if (threadIdx.x == 0) atomicAdd(&d.scal[4], t);
+  if (threadIdx.x == 0) d.scal[4] = t;
 }
 
 __global__ void __launch_bounds__(256) k_ba_new_error(BundleDev d) {
@@ -1149,7 +818,7 @@ __global__ void __launch_bounds__(256) k_ba_new_error(BundleDev d) {
     }
   }
   const double t = block_sum(e, sh);
-  if (threadIdx.x == 0) atomicAdd(&d.scal[3], t);
+  grid_sum_finish(t, d.partials, d.tickets + 2, &d.scal[3], false);
 }
 
 // end of an LM step: erase the bad measurements, appending (point, camera) in list order
