@@ -315,14 +315,12 @@ PTAM_DEV void grid_sum_finish(double t, double* partials, unsigned* ticket, doub
   }
 }
 
-// One round of a segment sum: thread t has computed the NV terms of item t (zeros when it has none); they are
-// staged value-major (pitch R + 1: conflict-free both ways), then thread v < NV adds (or subtracts) value v of
-// the round's `cnt` items one after the other.
+// One round of a segment sum: thread t has staged the NV terms of item t at sv[q * (R + 1) + t] (value-major,
+// pitch R + 1: conflict-free both ways; zeros when the item contributes nothing); thread v < NV then adds (or
+// subtracts) value v of the round's `cnt` items one after the other.
 template <int NV, int R>
-PTAM_DEV void seg_round(double* sv, const double* v, int cnt, double& acc, bool subtract) {
+PTAM_DEV void seg_accumulate(const double* sv, int cnt, double& acc, bool subtract) {
   const int t = threadIdx.x;
-#pragma unroll
-  for (int q = 0; q < NV; q++) sv[q * (R + 1) + t] = v[q];
   __syncthreads();
   if (t < NV) {
     const double* row = sv + t * (R + 1);
@@ -402,17 +400,19 @@ __global__ void __launch_bounds__(kSegThreads) k_ba_acc_cam(BundleDev d) {
   double acc = 0.0;
   for (int base = o0; base < o1; base += kSegThreads) {
     const int o = base + t;
-    double v[28];
-#pragma unroll
-    for (int q = 0; q < 28; q++) v[q] = 0.0;
+    double* sv = seg_sv + t;
+    constexpr int kP = kSegThreads + 1;
+    bool filled = false;
+    double err = 0.0;
     if (o < o1) {
       const int m = d.cam_meas_ins[o];
       const int st = d.m_state[m];
-      if (st == M_BAD) v[27] = 1.0;
+      if (st == M_BAD) err = 1.0;
       else if (st == M_ALIVE) {
         const double e2 = d.m_e2[m];
-        v[27] = mest_objective(e2, sigma2, d.est);
+        err = mest_objective(e2, sigma2, d.est);
         if (cfree) {
+          filled = true;
           const double w = mest_sqrt_weight(e2, sigma2, d.est);
           const double s = d.m_sin[m];
           const double d0 = s * (w * d.m_derivs[4 * m]), d1 = s * (w * d.m_derivs[4 * m + 1]);
@@ -425,13 +425,18 @@ __global__ void __launch_bounds__(kSegThreads) k_ba_acc_cam(BundleDev d) {
 #pragma unroll
           for (int r = 0; r < 6; r++)
 #pragma unroll
-            for (int cc = 0; cc <= r; cc++) v[q++] = A[r] * A[cc] + A[6 + r] * A[6 + cc];
+            for (int cc = 0; cc <= r; cc++) sv[kP * q++] = A[r] * A[cc] + A[6 + r] * A[6 + cc];
 #pragma unroll
-          for (int r = 0; r < 6; r++) v[21 + r] = A[r] * eps0 + A[6 + r] * eps1;
+          for (int r = 0; r < 6; r++) sv[kP * (21 + r)] = A[r] * eps0 + A[6 + r] * eps1;
         }
       }
     }
-    seg_round<28, kSegThreads>(seg_sv, v, min(kSegThreads, o1 - base), acc, false);
+    if (!filled) {
+#pragma unroll
+      for (int q = 0; q < 27; q++) sv[kP * q] = 0.0;
+    }
+    sv[kP * 27] = err;
+    seg_accumulate<28, kSegThreads>(seg_sv, min(kSegThreads, o1 - base), acc, false);
   }
   if (t < 21) d.U[21 * c + t] = cfree ? acc : 0.0;
   else if (t < 27) d.epsA[6 * c + t - 21] = cfree ? acc : 0.0;
@@ -524,12 +529,13 @@ __global__ void __launch_bounds__(kSegThreads) k_ba_schur_diag(BundleDev d) {
   const int o0 = d.cam_off[c], o1 = d.cam_off[c + 1];
   for (int base = o0; base < o1; base += kSegThreads) {
     const int o = base + t;
-    double v[27];
-#pragma unroll
-    for (int q = 0; q < 27; q++) v[q] = 0.0;
+    double* sv = seg_sv + t;
+    constexpr int kP = kSegThreads + 1;
+    bool filled = false;
     if (o < o1) {
       const int m = d.cam_meas_pt[o];
       if (d.m_state[m] == M_ALIVE) {
+        filled = true;
         const int i = d.m_pt[m];
         const double* Vi = d.Vinv + 9 * (size_t)i;
         const double* ve = d.Ve + 3 * (size_t)i;
@@ -545,12 +551,16 @@ __global__ void __launch_bounds__(kSegThreads) k_ba_schur_diag(BundleDev d) {
 #pragma unroll
         for (int r = 0; r < 6; r++)
 #pragma unroll
-          for (int cc = 0; cc <= r; cc++) v[q++] = WV[3 * r] * Wr[3 * cc] + WV[3 * r + 1] * Wr[3 * cc + 1] + WV[3 * r + 2] * Wr[3 * cc + 2];
+          for (int cc = 0; cc <= r; cc++) sv[kP * q++] = WV[3 * r] * Wr[3 * cc] + WV[3 * r + 1] * Wr[3 * cc + 1] + WV[3 * r + 2] * Wr[3 * cc + 2];
 #pragma unroll
-        for (int r = 0; r < 6; r++) v[21 + r] = Wr[3 * r] * ve[0] + Wr[3 * r + 1] * ve[1] + Wr[3 * r + 2] * ve[2];
+        for (int r = 0; r < 6; r++) sv[kP * (21 + r)] = Wr[3 * r] * ve[0] + Wr[3 * r + 1] * ve[1] + Wr[3 * r + 2] * ve[2];
       }
     }
-    seg_round<27, kSegThreads>(seg_sv, v, min(kSegThreads, o1 - base), acc, true);
+    if (!filled) {
+#pragma unroll
+      for (int q = 0; q < 27; q++) sv[kP * q] = 0.0;
+    }
+    seg_accumulate<27, kSegThreads>(seg_sv, min(kSegThreads, o1 - base), acc, true);
   }
   if (t < 21) {
     d.S[(size_t)(row + r6) * d.n + row + c6] = acc;
@@ -588,12 +598,13 @@ __global__ void __launch_bounds__(kOffThreads) k_ba_schur_off(BundleDev d) {
     const int o0 = d.blk_off[b], o1 = d.blk_off[b + 1];
     for (int base = o0; base < o1; base += kOffThreads) {
       const int o = base + t;
-      double v[36];
-#pragma unroll
-      for (int q = 0; q < 36; q++) v[q] = 0.0;
+      double* st = sv + t;
+      constexpr int kP = kOffThreads + 1;
+      bool filled = false;
       if (o < o1) {
         const int mj = d.pr_mj[o], mk = d.pr_mk[o];
         if (d.m_state[mj] == M_ALIVE && d.m_state[mk] == M_ALIVE) {
+          filled = true;
           const double* Vi = d.Vinv + 9 * (size_t)d.m_pt[mj];
           const double* Wj = d.m_W + 18 * (size_t)mj;
           const double* Wk = d.m_W + 18 * (size_t)mk;
@@ -608,10 +619,14 @@ __global__ void __launch_bounds__(kOffThreads) k_ba_schur_off(BundleDev d) {
 #pragma unroll
           for (int r = 0; r < 6; r++)
 #pragma unroll
-            for (int cc = 0; cc < 6; cc++) v[6 * r + cc] = WV[3 * r] * wk[3 * cc] + WV[3 * r + 1] * wk[3 * cc + 1] + WV[3 * r + 2] * wk[3 * cc + 2];
+            for (int cc = 0; cc < 6; cc++) st[kP * (6 * r + cc)] = WV[3 * r] * wk[3 * cc] + WV[3 * r + 1] * wk[3 * cc + 1] + WV[3 * r + 2] * wk[3 * cc + 2];
         }
       }
-      seg_round<36, kOffThreads>(sv, v, min(kOffThreads, o1 - base), acc, true);
+      if (!filled) {
+#pragma unroll
+        for (int q = 0; q < 36; q++) st[kP * q] = 0.0;
+      }
+      seg_accumulate<36, kOffThreads>(sv, min(kOffThreads, o1 - base), acc, true);
     }
     if (t < 36) d.S[(size_t)(6 * jf + t / 6) * d.n + 6 * kf + t % 6] = acc;
     __syncthreads();  // s_idx is rewritten next

@@ -1,6 +1,11 @@
 """GPU parity for path B: CUDA Bundle (through the C-ABI) against the CPU oracle.
-Integer outcomes (accepted steps, lambda trials, outlier list incl. order) must be equal; f64 states
-to the tolerances below (GPU uses FMA and atomics, so sums are reordered at the 1e-16 level)."""
+Integer outcomes (accepted steps, lambda trials, outlier list incl. order) must be equal.  The device takes
+every sum over measurements in the reference's order with the reference's expressions (no floating-point
+atomics, no FMA contraction in the passes), so from identical state sigma^2, S and vE are BIT-EQUAL to the
+oracle's and repeat runs are bit-identical; what differs from the reference arithmetic is the dense solve
+(blocked LDL^T with FMA / f64 tensor-core tiles), sin / cos in SE3::exp and the tree order of the scalar error
+sums — 1e-16-level differences that the LM iteration itself then amplifies (see
+test_whole_run_divergence_is_bounded_by_the_reference_sensitivity)."""
 import numpy as np
 import pytest
 
@@ -38,12 +43,13 @@ def test_compute_matches_oracle(oracle, product, shape):
     _same_stats(o.stats(), p.stats(), rtol=1e-5)
     assert o.Converged() == p.Converged()
     assert np.array_equal(o.GetOutlierMeasurements(), p.GetOutlierMeasurements())
-    # Whole-run state tolerance.  Only camera 0 is fixed (MapMaker.cc:304) and lambda decays to
-    # ~1e-10, so weakly constrained directions (global scale, 2-view points) are held by almost
-    # nothing: on the C3 graph the ORACLE ITSELF moves by 1e-4 when its input points are perturbed
-    # by 1e-14 (measured: tests/test_oracle_bundle.py::test_whole_run_sensitivity).  Per-step parity
-    # from identical state is the strict check (test_stepwise_and_reduced_system).
-    tol = STATE_TOL if nm < 20000 else 5e-3
+    # Whole-run state tolerance.  On the C3 graph the run does not converge in its 20 lambda trials (every step
+    # is accepted, sigma^2 and the outlier set keep moving) and the iteration amplifies any difference about
+    # 5x per LM step: the ORACLE ITSELF ends 1e-4 away when its input points are perturbed by 1e-14
+    # (tests/test_oracle_bundle.py::test_whole_run_sensitivity).  The step-by-step bound against that
+    # sensitivity is test_whole_run_divergence_is_bounded_by_the_reference_sensitivity below; per-step parity
+    # from identical state (bit-equal S, vE) is test_stepwise_and_reduced_system.
+    tol = STATE_TOL if nm < 20000 else 1e-3
     np.testing.assert_allclose(p.get_points(), o.get_points(), atol=tol, rtol=0)
     np.testing.assert_allclose(p.get_cameras(), o.get_cameras(), atol=tol, rtol=0)
     # the fixed camera never moves (gauge)
@@ -65,7 +71,10 @@ def test_stepwise_and_reduced_system(oracle, product):
         _same_stats(o.stats(), p.stats(), rtol=1e-11 if tight else 1e-6)
         So, eo = o.reduced_system(n)
         Sp, ep = p.reduced_system(n)
-        rel = 1e-12 if tight else 1e-6
+        if tight:  # identical state in: the reduced camera system is the oracle's bit for bit
+            assert np.array_equal(Sp, So) and np.array_equal(ep, eo)
+            assert o.stats().sigma_squared == p.stats().sigma_squared
+        rel = 1e-6
         np.testing.assert_allclose(Sp, So, atol=rel * np.abs(So).max(), rtol=0)
         np.testing.assert_allclose(ep, eo, atol=rel * np.abs(eo).max(), rtol=0)
         assert np.array_equal(Sp, Sp.T)
@@ -73,6 +82,122 @@ def test_stepwise_and_reduced_system(oracle, product):
         np.testing.assert_allclose(p.get_points(), o.get_points(), atol=tol, rtol=0)
         np.testing.assert_allclose(p.get_cameras(), o.get_cameras(), atol=tol, rtol=0)
         assert np.array_equal(o.GetOutlierMeasurements(), p.GetOutlierMeasurements())
+
+
+@pytest.mark.parametrize("shape", [(12, 600, 3000, 4), (50, 5000, 20000, 42)])
+def test_repeat_runs_are_bit_identical(product, shape):
+    """No floating-point atomics on path B: two Compute() calls on the same graph give the same bits
+    (states, error, sigma^2, outlier list), also with the measurement list shuffled out of camera-major order."""
+    nc, npts, nm, seed = shape
+    g = synth.make_ba_graph(nc, npts, nm, seed=seed)
+    perm = np.random.default_rng(1).permutation(nm)
+    g2 = dict(g)
+    for k in ("meas_cam", "meas_point", "meas_uv", "meas_sigma_sq"):
+        g2[k] = np.asarray(g[k])[perm]
+    for graph in (g, g2):
+        runs = []
+        for _ in range(2):
+            b = Bundle(product, graph["width"], graph["height"])
+            b.add_graph(graph)
+            acc = b.Compute()
+            st = b.stats()
+            runs.append((acc, st.lambda_trials, st.last_error, st.last_new_error, st.sigma_squared, b.GetOutlierMeasurements().copy(),
+                         b.get_points(), b.get_cameras()))
+            b.close()
+        a, b_ = runs
+        assert a[:5] == b_[:5]
+        assert all(np.array_equal(x, y) for x, y in zip(a[5:], b_[5:]))
+
+
+def test_shuffled_measurement_list_matches_oracle(oracle, product):
+    """List order is what the reference sums in (Bundle.cc:251-332): with the list shuffled the device still
+    follows it — S and vE bit-equal to the oracle fed the same shuffled list."""
+    g = synth.make_ba_graph(10, 500, 2500, seed=9)
+    perm = np.random.default_rng(2).permutation(2500)
+    g = dict(g)
+    for k in ("meas_cam", "meas_point", "meas_uv", "meas_sigma_sq"):
+        g[k] = np.asarray(g[k])[perm]
+    o, p = _pair(oracle, product, g)
+    o.begin(); p.begin()
+    o.lm_step(); p.lm_step()
+    n = 6 * int((g["cam_fixed"] == 0).sum())
+    So, eo = o.reduced_system(n)
+    Sp, ep = p.reduced_system(n)
+    assert np.array_equal(Sp, So) and np.array_equal(ep, eo)
+    assert np.array_equal(o.GetOutlierMeasurements(), p.GetOutlierMeasurements())
+    np.testing.assert_allclose(p.get_points(), o.get_points(), atol=STEP_TOL, rtol=0)
+
+
+def test_whole_run_divergence_is_bounded_by_the_reference_sensitivity(oracle, product):
+    """BASELINE config C3, LM step by LM step: the device's distance from the oracle never exceeds 20x what a
+    1e-14 perturbation of the input points does to the ORACLE ITSELF at the same step, and all integer outcomes
+    (trials, accepted, outliers so far) agree at every step.  This is the whole-run bar: the reference's LM loop
+    amplifies rounding-level differences (about 5x per step from step 5 on), so a fixed small tolerance on the
+    final state would test the graph's conditioning, not the implementation."""
+    g = synth.make_ba_graph(50, 5000, 20000, seed=42)
+    gp = dict(g)
+    gp["points"] = g["points"] + np.random.default_rng(0).normal(0, 1, g["points"].shape) * 1e-14
+    o, p = _pair(oracle, product, g)
+    q = Bundle(oracle, g["width"], g["height"]); q.add_graph(gp)
+    for b in (o, p, q):
+        b.begin()
+    worst_ref = 1e-13
+    for step in range(25):
+        for b in (o, p, q):
+            b.lm_step()
+        so, sp = o.stats(), p.stats()
+        assert (so.lambda_trials, so.accepted, so.n_outliers) == (sp.lambda_trials, sp.accepted, sp.n_outliers), step
+        d_ref = max(np.abs(o.get_points() - q.get_points()).max(), np.abs(o.get_cameras() - q.get_cameras()).max())
+        d_gpu = max(np.abs(o.get_points() - p.get_points()).max(), np.abs(o.get_cameras() - p.get_cameras()).max())
+        worst_ref = max(worst_ref, d_ref)
+        assert d_gpu <= 20 * worst_ref, (step, d_gpu, worst_ref)
+        if so.converged or so.hit_max_iterations:
+            break
+    assert np.array_equal(o.GetOutlierMeasurements(), p.GetOutlierMeasurements())
+
+
+def test_c4_whole_run_against_the_reference_fixture(product):
+    """BASELINE config C4 run to completion against tests/golden/bundle_c4_reference.npz = the reference's OWN
+    Bundle::Compute (src/Bundle.cc compiled in place, oracle/_ref) and the oracle on the same graph
+    (tests/golden/make_golden_c4.py).  The outlier list (13 953 pairs, erase order) equals the reference's; the
+    per-step trace (trials, accepted, outliers so far, sigma^2, errors, lambda) equals the oracle's, which shares the
+    device's numeric contract (specified atan).  The reference itself, with the platform's atan, takes ONE MORE
+    lambda trial (20 against 19: |delta|^2 crosses the 1e-6 convergence limit of Bundle.cc:488 one step later) — a
+    1-ulp difference in atan is enough — so trial counts are compared with the oracle and allowed +-1 against the
+    reference, and states must lie within 10x of the distance between those two."""
+    from pathlib import Path
+    fx = np.load(Path(__file__).parent / "golden" / "bundle_c4_reference.npz")
+    nc, npts, nm, seed = (int(v) for v in fx["config"])
+    g = synth.make_ba_graph(nc, npts, nm, seed=seed)
+    b = Bundle(product, g["width"], g["height"])
+    b.add_graph(g)
+    b.begin()
+    trace = []
+    while True:
+        b.lm_step()
+        st = b.stats()
+        trace.append((st.lambda_trials, st.accepted, st.n_outliers, st.sigma_squared, st.last_error, st.last_new_error, st.lambda_))
+        if st.converged or st.hit_max_iterations:
+            break
+    trace = np.array(trace)
+    ot = fx["orc_trace"]
+    assert trace.shape == ot.shape
+    assert np.array_equal(trace[:, :3], ot[:, :3])                        # trials, accepted, outliers so far: every step
+    np.testing.assert_allclose(trace[:, 3:6], ot[:, 3:6], rtol=1e-6)        # sigma^2, error, new error
+    np.testing.assert_allclose(trace[:, 6], ot[:, 6], rtol=1e-12)           # lambda schedule
+    assert (st.accepted, st.lambda_trials) == (int(fx["orc_accepted"]), int(fx["orc_lambda_trials"]))
+    assert abs(st.lambda_trials - int(fx["ref_lambda_trials"])) <= 1 and abs(st.accepted - int(fx["ref_accepted"])) <= 1
+    out = b.GetOutlierMeasurements()
+    assert np.array_equal(out, fx["ref_outliers"]) and np.array_equal(out, fx["orc_outliers"])   # incl. erase order
+    stride = int(fx["stride"])
+    pts, cams = b.get_points(), b.get_cameras()
+    ref_vs_orc = max(np.abs(fx["ref_cameras"] - fx["orc_cameras"]).max(), np.abs(fx["ref_points_sub"] - fx["orc_points_sub"]).max())
+    tol = 10 * max(ref_vs_orc, 1e-9)
+    for tag in ("ref", "orc"):
+        assert np.abs(cams - fx[tag + "_cameras"]).max() <= tol, (tag, tol)
+        assert np.abs(pts[::stride] - fx[tag + "_points_sub"]).max() <= tol, (tag, tol)
+        np.testing.assert_allclose(pts.sum(0), fx[tag + "_points_sum"], atol=tol * len(pts))
+    b.close()
 
 
 def test_individual_add_calls_and_getters(oracle, product):
@@ -243,12 +368,12 @@ def test_full_size_c4_step_parity_and_run_properties(oracle, product):
     assert n == 2994
     So, eo = o.reduced_system(n)
     Sp, ep = p.reduced_system(n)
-    np.testing.assert_allclose(Sp, So, atol=1e-12 * np.abs(So).max(), rtol=0)
-    np.testing.assert_allclose(ep, eo, atol=1e-12 * np.abs(eo).max(), rtol=0)
+    assert np.array_equal(Sp, So) and np.array_equal(ep, eo)   # 2 994 x 2 994 doubles, bit for bit
+    assert so.sigma_squared == sp.sigma_squared
     assert np.array_equal(Sp, Sp.T)
     del So, Sp
     assert np.array_equal(o.GetOutlierMeasurements(), p.GetOutlierMeasurements())
-    # delta = S^-1 vE through a 2 994 x 2 994 LDL^T: the reordered sums (DMMA tiles, atomics) are amplified
+    # delta = S^-1 vE through a 2 994 x 2 994 LDL^T: the reordered sums of the blocked solve (DMMA tiles) are amplified
     # by the conditioning of S, hence 1e-9 rather than the 1e-10 of the small graphs
     np.testing.assert_allclose(p.get_points(), o.get_points(), atol=1e-9, rtol=0)
     np.testing.assert_allclose(p.get_cameras(), o.get_cameras(), atol=1e-9, rtol=0)
