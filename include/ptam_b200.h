@@ -351,8 +351,11 @@ int64_t ptam_bundle_launch_count(const ptam_bundle* b);
 /* Per-phase device timing (CUDA events on the handle's stream).  Phase ids: 0 project (Bundle.cc:219-225),
  * 1 sigma-squared select (:230-237), 2 Jacobian/accumulate (:251-332), 3 V*^-1 + S/vE init (:341-392),
  * 4 Schur build (:396-446), 5 cross-shard all-reduce of S/vE, 6 dense LDL^T solve (:457-458),
- * 7 updates + FindNewError (:461-506).  Turning it on or off resets the accumulators. */
-#define PTAM_BA_PHASES 8
+ * 7 updates + FindNewError (:461-506), 8 reserved, 9 commit + outlier erase (:512-547) — device time per call;
+ * 10 set-up of Compute (host CSR build, upload, pair list: GenerateMeasLUTs / OffDiagScripts, :558-599) and
+ * 11 the rest of Compute's wall clock (host LM control, blocking scalar read-backs, launch gaps) — host wall
+ * clock, one entry per Compute.  Turning it on or off resets the accumulators. */
+#define PTAM_BA_PHASES 12
 int ptam_bundle_set_profiling(ptam_bundle* b, int on);
 int ptam_bundle_get_phase_times(ptam_bundle* b, double ms_total[PTAM_BA_PHASES], int64_t count[PTAM_BA_PHASES]);
 

@@ -17,6 +17,7 @@
 // include/ptam_b200.h so that tests drive oracle and product with the same code.
 #include "oracle_math.h"
 #include "../include/ptam_b200.h"
+#include <chrono>
 #include <cstdio>
 #include <string>
 
@@ -86,14 +87,29 @@ static void fast10(const Level& L, std::vector<IRef>& corners, int t) {
   }
 }
 
+// CPU cost split of TrackFrame for the bench's C1 record (BASELINE.md "Configs" row C1): seconds spent in
+// 0 image copy + halfSample, 1 FAST-10 + row LUT, 2 small blurry image + rotation estimator, 3 SearchForPoints
+// (warp, template, ZMSSD search, sub-pixel), 4 CalcPoseUpdate; 5 = frames.  Per thread.
+static thread_local double g_split[6] = {0, 0, 0, 0, 0, 0};
+struct SplitTimer {
+  int k;
+  std::chrono::steady_clock::time_point t0;
+  explicit SplitTimer(int k_) : k(k_), t0(std::chrono::steady_clock::now()) {}
+  ~SplitTimer() { g_split[k] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
 static void make_keyframe_lite(KeyFrame& kf, const uint8_t* im, int w, int h, int stride, bool detect = true) {
   static const int thr[4] = {10, 15, 15, 10};
-  kf.lev[0].w = w; kf.lev[0].h = h;
-  kf.lev[0].im.resize((size_t)w * h);
-  for (int y = 0; y < h; y++) std::memcpy(kf.lev[0].im.data() + (size_t)y * w, im + (size_t)y * stride, w);
+  {
+    SplitTimer tm(0);
+    kf.lev[0].w = w; kf.lev[0].h = h;
+    kf.lev[0].im.resize((size_t)w * h);
+    for (int y = 0; y < h; y++) std::memcpy(kf.lev[0].im.data() + (size_t)y * w, im + (size_t)y * stride, w);
+    for (int i = 1; i < PTAM_LEVELS; i++) half_sample(kf.lev[i - 1], kf.lev[i]);
+  }
+  SplitTimer tm(1);
   for (int i = 0; i < PTAM_LEVELS; i++) {
     Level& lev = kf.lev[i];
-    if (i != 0) half_sample(kf.lev[i - 1], lev);
     lev.corners.clear();
     lev.lut.clear();
     if (!detect) continue;
@@ -633,6 +649,7 @@ struct Tracker {
   }
   // Tracker::SearchForPoints (Tracker.cc:867-912)
   unsigned search_for_points(Stream& s, const std::vector<int>& v, unsigned range, int subpix_its) {
+    SplitTimer tm(3);
     unsigned nfound = 0;
     for (int idx : v) {
       TData& d = s.td[idx];
@@ -676,6 +693,7 @@ struct Tracker {
   }
   // Tracker::CalcPoseUpdate (Tracker.cc:928-1005) with TooN WLS<6>.
   void calc_pose_update(Stream& s, const std::vector<int>& v, double override_sigma, bool mark, double* mu) {
+    SplitTimer tm(4);
     const int est = prm.mestimator;
     std::vector<double> e2;
     for (int idx : v) {
@@ -958,9 +976,13 @@ struct Tracker {
 
   void track_frame(Stream& s, const uint8_t* im, int stride) {
     make_keyframe_lite(s.cur, im, W, H, stride);
+    g_split[5] += 1.0;
     // Update the small images for the rotation estimator (Tracker.cc:95-108)
-    if (!s.sbi_this.valid) { sbi_make(s.cur, prm.rotation_estimator_blur, s.sbi_this); s.sbi_last = s.sbi_this; }
-    else { s.sbi_last = s.sbi_this; sbi_make(s.cur, prm.rotation_estimator_blur, s.sbi_this); }
+    {
+      SplitTimer tm(2);
+      if (!s.sbi_this.valid) { sbi_make(s.cur, prm.rotation_estimator_blur, s.sbi_this); s.sbi_last = s.sbi_this; }
+      else { s.sbi_last = s.sbi_this; sbi_make(s.cur, prm.rotation_estimator_blur, s.sbi_this); }
+    }
     s.st.frame++;
     s.pose = SE3::from12(s.st.se3_cam_from_world);
     s.res.recovery = 0; s.res.reloc_keyframe = -1; s.res.reloc_score = 0.0;
@@ -1005,6 +1027,7 @@ struct Tracker {
     double vpred[6];
     for (int k = 0; k < 6; k++) vpred[k] = s.st.velocity[k];
     {
+      SplitTimer tm(2);
       sbi_make_jacs(s.sbi_last);
       const SE2 se2 = sbi_iterate(s.sbi_this, s.sbi_last, 6, s.sbi_score);  // CalcSBIRotation, nIterations = 6
       SE3 rot;
@@ -1152,6 +1175,10 @@ int orc_tracker_track_frames(void* tp, const uint8_t* const* images, int stride,
   return 0;
 }
 int orc_tracker_synchronize(void*) { return 0; }
+// test / bench infrastructure only (no product counterpart): this thread's CPU cost split, see g_split
+void orc_tracker_cpu_split(double out[6], int reset) {
+  for (int k = 0; k < 6; k++) { out[k] = orc::g_split[k]; if (reset) orc::g_split[k] = 0.0; }
+}
 int orc_tracker_level_size(const void* tp, int level, int* w, int* h) {
   const Tracker* t = (const Tracker*)tp;
   int ww = t->W, hh = t->H;

@@ -93,7 +93,8 @@ PRODUCT_ONLY_SYMBOLS = [
     "nccl_unique_id", "nccl_comm_create", "nccl_comm_destroy", "bundle_init_shard", "bundle_shard_plan",
     "bundle_set_profiling", "bundle_get_phase_times",
 ]
-BUNDLE_PHASES = ["project", "select", "jacobian", "vinv_init", "schur", "allreduce", "solve", "update_newerror"]
+BUNDLE_PHASES = ["project", "select", "jacobian", "vinv_init", "schur", "allreduce", "solve", "update_newerror", "reserved",
+                 "commit_erase", "begin_setup", "host_control_and_sync"]
 TRACKER_KERNELS = ["k_pyramid", "k_fast", "k_compact", "k_sbi+k_pvs_select", "k_search_coarse", "k_pose_coarse",
                    "k_search_fine", "k_pose_fine"]
 
@@ -615,6 +616,6 @@ class Bundle:
 
     def phase_times(self):
         """{phase: (total ms, count)} accumulated since set_profiling(True)."""
-        ms, n = (C.c_double * 8)(), (C.c_int64 * 8)()
+        ms, n = (C.c_double * len(BUNDLE_PHASES))(), (C.c_int64 * len(BUNDLE_PHASES))()
         self._chk(self.lib.fn("bundle_get_phase_times")(self.h, ms, n))
         return {k: (ms[j], n[j]) for j, k in enumerate(BUNDLE_PHASES)}

@@ -11,6 +11,7 @@
                    // libnccl.so.2 when the process already loaded it, else the system library)
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -124,6 +125,7 @@ struct ptam_bundle {
   double prof_ms[PTAM_BA_PHASES] = {};
   int64_t prof_n[PTAM_BA_PHASES] = {};
   unsigned prof_pending = 0;
+  double prof_begin_ms = 0, prof_wall_ms = 0;  // host wall clock: graph build + upload, whole Compute
   void pbegin(int k) { if (profiling) cudaEventRecord(prof_ev[2 * k], stream); }
   void pend(int k) { if (profiling) { cudaEventRecord(prof_ev[2 * k + 1], stream); prof_pending |= 1u << k; } }
   void pcollect() {  // call after a stream synchronisation
@@ -456,6 +458,7 @@ struct ptam_bundle {
       counter++;
       if (counter >= prm.max_iterations) hit_max = true;
     }
+    pbegin(9);
     if (new_err < cur_err) {  // ModifyLambda_GoodStep + commit
       lambda_factor = 2.0; lambda *= 0.3;
       PTAM_CUDA_TRY(this, cudaMemcpyAsync(cam_se3.p, cam_se3_new.p, sizeof(double) * 12 * C, cudaMemcpyDeviceToDevice, stream));
@@ -472,8 +475,10 @@ struct ptam_bundle {
       k_ba_erase_write<<<nblk, 1024, 0, stream>>>(d, erase_cnt.p, lm_steps);
       launches += 3;
     }
+    pend(9);
     PTAM_CUDA_TRY(this, cudaMemcpyAsync(h_cnt, counters.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, stream));
     PTAM_CUDA_TRY(this, cudaStreamSynchronize(stream));
+    pcollect();
     n_outliers = h_cnt[1];
     return PTAM_OK;
   }
@@ -623,8 +628,13 @@ int ptam_bundle_begin(ptam_bundle* b) { return b->begin(); }
 int ptam_bundle_lm_step(ptam_bundle* b, const volatile unsigned char* abort_flag) { return b->lm_step(abort_flag); }
 
 int ptam_bundle_compute(ptam_bundle* b, const volatile unsigned char* abort_flag) {  // Bundle.cc:116-158
+  const auto t0 = std::chrono::steady_clock::now();
   int rc = b->begin();
   if (rc) return rc;
+  if (b->profiling) {
+    cudaStreamSynchronize(b->stream);  // the pair-list kernels belong to the set-up
+    b->prof_begin_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  }
   // a sharded run acts on the reduced abort votes only, so that all ranks leave the loop together
   while (!b->converged && !b->hit_max && !(b->world > 1 ? b->abort_seen : (abort_flag && *abort_flag))) {
     rc = b->lm_step(abort_flag);
@@ -632,6 +642,7 @@ int ptam_bundle_compute(ptam_bundle* b, const volatile unsigned char* abort_flag
   }
   rc = b->sync_shards();
   if (rc) return rc;
+  if (b->profiling) b->prof_wall_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return b->accepted;
 }
 
@@ -776,10 +787,15 @@ int ptam_bundle_set_profiling(ptam_bundle* b, int on) {
   b->profiling = on != 0;
   b->prof_pending = 0;
   for (int k = 0; k < PTAM_BA_PHASES; k++) { b->prof_ms[k] = 0; b->prof_n[k] = 0; }
+  b->prof_begin_ms = 0; b->prof_wall_ms = 0;
   return PTAM_OK;
 }
 int ptam_bundle_get_phase_times(ptam_bundle* b, double* ms_total, int64_t* count) {
-  for (int k = 0; k < PTAM_BA_PHASES; k++) { ms_total[k] = b->prof_ms[k]; count[k] = b->prof_n[k]; }
+  double dev = 0;
+  for (int k = 0; k < PTAM_BA_PHASES; k++) { ms_total[k] = b->prof_ms[k]; count[k] = b->prof_n[k]; if (k < 10) dev += b->prof_ms[k]; }
+  ms_total[10] = b->prof_begin_ms; count[10] = b->prof_begin_ms > 0 ? 1 : 0;
+  // what is left of the wall clock of Compute: host LM control, the blocking read-backs, launch gaps
+  ms_total[11] = b->prof_wall_ms > 0 ? b->prof_wall_ms - dev - b->prof_begin_ms : 0; count[11] = b->prof_wall_ms > 0 ? 1 : 0;
   return PTAM_OK;
 }
 #ifdef PTAM_PANEL_DEBUG
