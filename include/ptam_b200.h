@@ -245,6 +245,34 @@ int ptam_tracker_get_templates(ptam_tracker* t, int stream, uint8_t* tmpl, int32
 /* vIterationSet of the last frame in order (coarse set, level-3 set, fine set); returns its size. */
 int ptam_tracker_get_iteration_set(ptam_tracker* t, int stream, int32_t* idx, int cap);
 
+/* ---- PatchFinder / CalcPoseUpdate unit entry points ---------------------------------------------
+ * The per-frame path runs PatchFinder and CalcPoseUpdate inside ptam_tracker_track_frames; these two calls expose
+ * the same device code one step at a time, for unit parity and for callers that hold their own pose (the host
+ * mirror ptam_cg_b200/host/PatchFinder.h is built on them).
+ *
+ * ptam_patch_search_batch = class PatchFinder, steps 1-5 (reference include/PatchFinder.h:54-98), for EVERY map
+ * point of every stream against the stream's current frame (pyramid + FAST corners of the last
+ * ptam_tracker_make_keyframes / _track_frames call), at the caller's poses se3[S][12], driven as
+ * Tracker::SearchForPoints drives them (src/Tracker.cc:867-912):
+ *   TrackerData::Project + GetProjectionDerivs (Tracker.h:70-94), CalcSearchLevelAndWarpMatrix
+ *   (PatchFinder.cc:52-84; level -1 rejects), MakeTemplateCoarseCont (:98-127, per-point template cache),
+ *   FindPatchCoarse(ir(v2Image), kf, range) (:160-211), and for subpix_its > 0 MakeSubPixTemplate +
+ *   IterateSubPixToConvergence(kf, subpix_its) (:219-318; a point that does not converge is not found).
+ * Tracker state (pose, velocity, counters of lost frames) is not touched.
+ * ptam_patch_get_results: level[n] (mnSearchLevel or -1), warp_inverse[n][4] (mm2WarpInverse row-major, zero for a
+ * point that does not project into the frame), template_bad[n] (TemplateBad() of the points that do), found[n], pos[n][2] (GetSubPixPos()
+ * if the sub-pixel step ran, else GetCoarsePosAsVector(); level-zero pixels), subpix_converged[n]; templates and
+ * their sums through ptam_tracker_get_templates.  Any output may be NULL; returns n.
+ *
+ * ptam_pose_update = Tracker::CalcPoseUpdate(vTD, dOverrideSigma, bMarkOutliers) (src/Tracker.cc:928-1005) once per
+ * stream over the points FOUND by the last ptam_patch_search_batch: CalcJacobian (Tracker.h:125-136) at that call's
+ * poses, sigma^2 from the M-estimator (Tools.h:128-254) unless override_sigma_squared > 0, WLS<6> with the 100 I
+ * prior.  mu6[S][6] = v6Update (the caller applies SE3::exp(mu) * pose, Tracker.cc:567,641), n_found[S]. */
+int ptam_patch_search_batch(ptam_tracker* t, const double* se3_cam_from_world, unsigned range, int subpix_its);
+int ptam_patch_get_results(ptam_tracker* t, int stream, int32_t* level, double* warp_inverse, int32_t* template_bad,
+                           int32_t* found, double* pos, int32_t* subpix_converged);
+int ptam_pose_update(ptam_tracker* t, double override_sigma_squared, int mark_outliers, double* mu6, int32_t* n_found);
+
 /* ------------------------------------------------------------------------------------------
  * Path B — bundle adjuster.  Replaces class Bundle (Bundle.h:105-156), whose only caller is
  * MapMaker::BundleAdjust (MapMaker.cc:838-933).

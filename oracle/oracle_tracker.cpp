@@ -166,6 +166,7 @@ struct TData {
   double sqrt_inv_noise = 1;
   double err[2];
   double J[12];  // 2x6 row-major
+  bool unit_projected = false;  // unit entry: the point projected into the frame, so warp_inv is this call's
 };
 
 static inline double level_zero_pos(double p, int l) { return (p + 0.5) * (1 << l) - 0.5; }
@@ -465,6 +466,7 @@ struct Tracker {
     int attempted[4], found[4];
     bool did_coarse = false;
     std::vector<int> iter_set;
+    std::vector<int> unit_set;   // the points the last patch_search searched (unit entry)
     ptam_track_result res;
     SBI sbi_this, sbi_last;      // mpSBIThisFrame / mpSBILastFrame (Tracker.cc:97-108)
     double sbi_rot[3] = {0, 0, 0}, sbi_score = 0;
@@ -878,6 +880,42 @@ struct Tracker {
     }
   }
 
+  // Unit entry (ptam_patch_search_batch): PatchFinder steps 1-5 (PatchFinder.h:54-98) for every map point
+  // against the stream's current frame, driven exactly as Tracker::SearchForPoints drives them
+  // (Tracker.cc:867-912): TrackerData::Project, GetProjectionDerivs, CalcSearchLevelAndWarpMatrix (a negative
+  // level rejects the point), MakeTemplateCoarseCont with the per-point template cache, FindPatchCoarse at the
+  // given range, and MakeSubPixTemplate + IterateSubPixToConvergence when subpix_its > 0.
+  void patch_search(Stream& s, const SE3& pose, unsigned range, int subpix_its) {
+    for (int i = 0; i < 4; i++) s.attempted[i] = s.found[i] = 0;
+    Camera::Proj last{};
+    std::vector<int> v;
+    for (size_t i = 0; i < s.pts.size(); i++) {
+      TData& d = s.td[i];
+      d.in_pvs = false; d.searched = false; d.found = false; d.did_subpix = false;
+      d.n_search_level = -1;
+      d.unit_projected = false;
+      project(d, s.pts[i], pose, last);
+      if (!d.in_image) continue;
+      d.unit_projected = true;
+      cam.derivs(last, d.derivs);
+      d.n_search_level = calc_search_level(d, s.pts[i], pose);
+      if (d.n_search_level == -1) continue;
+      d.in_pvs = true;
+      v.push_back((int)i);
+    }
+    search_for_points(s, v, range, subpix_its);
+    s.unit_set = v;
+  }
+  // Unit entry (ptam_pose_update): CalcJacobian (Tracker.h:125-136) + one Tracker::CalcPoseUpdate
+  // (Tracker.cc:928-1005) over the points the last patch_search found.
+  int pose_update(Stream& s, double override_sigma, bool mark, double* mu) {
+    int nf = 0;
+    for (int idx : s.unit_set)
+      if (s.td[idx].found) { calc_jacobian(s.td[idx]); nf++; }
+    calc_pose_update(s, s.unit_set, override_sigma, mark, mu);
+    return nf;
+  }
+
   // MapMaker::AddPointEpipolar (MapMaker.cc:529-688; SURVEY 8f rank 3, second half) up to the sub-pixel
   // position in the target keyframe: epipolar segment of the candidate's view ray in the target's z=1
   // plane, scan of ALL target corners of that level against it, un-warped 8x8 template
@@ -1199,6 +1237,42 @@ int orc_tracker_refind_in_keyframes(void* tp, const uint8_t* const* images, int 
   for (int s = 0; s < t->S; s++) {
     orc::make_keyframe_lite(t->streams[s].cur, images[s], t->W, t->H, stride);
     t->refind(t->streams[s], orc::SE3::from12(se3 + 12 * s));
+  }
+  return PTAM_OK;
+}
+int orc_patch_search_batch(void* tp, const double* se3, unsigned range, int subpix_its) {
+  Tracker* t = (Tracker*)tp;
+  if (!se3 || subpix_its < 0) return PTAM_ERR_INVALID;
+  for (int s = 0; s < t->S; s++) {
+    if (t->streams[s].cur.lev[0].im.empty()) return PTAM_ERR_INVALID;
+    t->patch_search(t->streams[s], orc::SE3::from12(se3 + 12 * s), range, subpix_its);
+  }
+  return PTAM_OK;
+}
+int orc_patch_get_results(void* tp, int stream, int32_t* level, double* warp_inverse, int32_t* template_bad, int32_t* found,
+                          double* pos, int32_t* subpix_converged) {
+  Tracker* t = (Tracker*)tp;
+  if (stream < 0 || stream >= t->S) return PTAM_ERR_INVALID;
+  auto& s = t->streams[stream];
+  for (size_t i = 0; i < s.pts.size(); i++) {
+    const orc::TData& d = s.td[i];
+    const bool fnd = d.in_pvs && d.found;
+    if (level) level[i] = d.n_search_level;
+    if (warp_inverse) for (int q = 0; q < 4; q++) warp_inverse[4 * i + q] = d.unit_projected ? d.warp_inv[q] : 0.0;
+    if (template_bad) template_bad[i] = (d.unit_projected && d.template_bad) ? 1 : 0;
+    if (found) found[i] = fnd ? 1 : 0;
+    if (pos) { pos[2 * i] = fnd ? d.v2found[0] : 0.0; pos[2 * i + 1] = fnd ? d.v2found[1] : 0.0; }
+    if (subpix_converged) subpix_converged[i] = (fnd && d.did_subpix) ? 1 : 0;
+  }
+  return (int)s.pts.size();
+}
+int orc_pose_update(void* tp, double override_sigma_squared, int mark_outliers, double* mu6, int32_t* n_found) {
+  Tracker* t = (Tracker*)tp;
+  for (int s = 0; s < t->S; s++) {
+    double mu[6];
+    const int nf = t->pose_update(t->streams[s], override_sigma_squared, mark_outliers != 0, mu);
+    if (mu6) for (int k = 0; k < 6; k++) mu6[6 * s + k] = mu[k];
+    if (n_found) n_found[s] = nf;
   }
   return PTAM_OK;
 }

@@ -45,6 +45,9 @@ struct RefTracker : public Tracker {
   using Tracker::mpSBIThisFrame;
   using Tracker::mse3CamFromWorld;
   using Tracker::mv6CameraVelocity;
+  using Tracker::mCamera;
+  using Tracker::SearchForPoints;
+  using Tracker::CalcPoseUpdate;
   struct RelocPeek : public Relocaliser { using Relocaliser::mnBest; };
   int reloc_best() { return static_cast<RelocPeek&>(mRelocaliser).mnBest; }
   void set_quality(int q) { mTrackingQuality = q == 0 ? BAD : GOOD; }
@@ -53,7 +56,18 @@ struct RefTracker : public Tracker {
 // SmallBlurryImage::mirSize is a process-wide static fixed by the first keyframe (ImageProcess.cc:281-282):
 // a handle of another resolution has to re-arm it
 struct SbiSize : public SmallBlurryImage { static void rearm() { mirSize = CVD::ImageRef(-1, -1); } };
+// the reference's PatchFinder keeps its working state protected: read it through a derived class
+struct PeekFinder : public PatchFinder {
+  using PatchFinder::mimTemplate;
+  using PatchFinder::mm2WarpInverse;
+  using PatchFinder::mnTemplateSum;
+  using PatchFinder::mnTemplateSumSq;
+  using PatchFinder::mpLastTemplateMapPoint;
+};
 struct Stream {
+  std::vector<TrackerData*> unit_set;      // what the last ref_patch_search_batch searched
+  std::vector<char> unit_projected;        // per map point: projected into the frame in that call
+  bool unit_mode = false;
   Map map;
   std::unique_ptr<RefMapMaker> mm;
   std::unique_ptr<RefTracker> trk;
@@ -559,8 +573,93 @@ int ref_tracker_get_points(void* hp, int stream, int32_t* flags, int32_t* level,
   }
   return (int)s.map.vpPoints.size();
 }
-// PatchFinder keeps its template protected: not exported by the reference build
-int ref_tracker_get_templates(void*, int, uint8_t*, int32_t*) { return PTAM_ERR_INVALID; }
+// The unit entry points on the reference's OWN classes: TrackerData::Project, ATANCamera::GetProjectionDerivs,
+// PatchFinder::CalcSearchLevelAndWarpMatrix as Tracker::TrackMap calls them (Tracker.cc:452-476), then the
+// reference's own Tracker::SearchForPoints (Tracker.cc:867-912) on that list against mCurrentKF.
+int ref_patch_search_batch(void* hp, const double* se3, unsigned range, int subpix_its) {
+  Handle* h = (Handle*)hp;
+  if (!se3 || subpix_its < 0) return PTAM_ERR_INVALID;
+  for (int s = 0; s < h->S; s++) {
+    Stream& st = *h->streams[s];
+    RefTracker& t = *st.trk;
+    st.refind_mode = false; st.unit_mode = true;
+    TooN::SE3<> pose = se3_from12(se3 + 12 * s);
+    st.unit_set.clear();
+    st.unit_projected.assign(st.map.vpPoints.size(), 0);
+    for (size_t i = 0; i < st.map.vpPoints.size(); i++) {
+      MapPoint& p = *st.map.vpPoints[i];
+      if (!p.pTData) p.pTData = new TrackerData(&p);
+      TrackerData& TD = *p.pTData;
+      TD.bSearched = TD.bFound = TD.bDidSubPix = false;
+      TD.nSearchLevel = -1;
+      TD.Project(pose, t.mCamera);
+      if (!TD.bInImage) continue;
+      st.unit_projected[i] = 1;
+      TD.m2CamDerivs = t.mCamera.GetProjectionDerivs();
+      TD.nSearchLevel = TD.Finder.CalcSearchLevelAndWarpMatrix(TD.Point, pose, TD.m2CamDerivs);
+      if (TD.nSearchLevel == -1) continue;
+      st.unit_set.push_back(&TD);
+    }
+    t.SearchForPoints(st.unit_set, range, subpix_its);
+  }
+  return PTAM_OK;
+}
+int ref_patch_get_results(void* hp, int stream, int32_t* level, double* warp_inverse, int32_t* template_bad, int32_t* found,
+                          double* pos, int32_t* subpix_converged) {
+  Handle* h = (Handle*)hp;
+  if (stream < 0 || stream >= h->S) return PTAM_ERR_INVALID;
+  Stream& st = *h->streams[stream];
+  for (size_t i = 0; i < st.map.vpPoints.size(); i++) {
+    MapPoint* p = st.map.vpPoints[i];
+    const bool have = p->pTData != nullptr;
+    const bool proj = have && i < st.unit_projected.size() && st.unit_projected[i];
+    const bool fnd = have && p->pTData->nSearchLevel >= 0 && p->pTData->bFound;
+    if (level) level[i] = have ? p->pTData->nSearchLevel : -1;
+    if (warp_inverse) {
+      for (int q = 0; q < 4; q++) warp_inverse[4 * i + q] = 0.0;
+      if (proj) { const TooN::Matrix<2>& m = static_cast<PeekFinder&>(p->pTData->Finder).mm2WarpInverse; for (int q = 0; q < 4; q++) warp_inverse[4 * i + q] = m(q / 2, q % 2); }
+    }
+    if (template_bad) template_bad[i] = proj && p->pTData->Finder.TemplateBad() ? 1 : 0;  // mbTemplateBad is not initialised before the first use
+    if (found) found[i] = fnd ? 1 : 0;
+    if (pos) { pos[2 * i] = fnd ? p->pTData->v2Found[0] : 0.0; pos[2 * i + 1] = fnd ? p->pTData->v2Found[1] : 0.0; }
+    if (subpix_converged) subpix_converged[i] = (fnd && p->pTData->bDidSubPix) ? 1 : 0;
+  }
+  return (int)st.map.vpPoints.size();
+}
+// CalcJacobian (Tracker.h:125-136) + the reference's own Tracker::CalcPoseUpdate (Tracker.cc:928-1005)
+int ref_pose_update(void* hp, double override_sigma_squared, int mark_outliers, double* mu6, int32_t* n_found) {
+  Handle* h = (Handle*)hp;
+  for (int s = 0; s < h->S; s++) {
+    Stream& st = *h->streams[s];
+    int nf = 0;
+    for (TrackerData* td : st.unit_set)
+      if (td->bFound) { td->CalcJacobian(); nf++; }
+    TooN::Vector<6> mu = st.trk->CalcPoseUpdate(st.unit_set, override_sigma_squared, mark_outliers != 0);
+    if (mu6) for (int k = 0; k < 6; k++) mu6[6 * s + k] = mu[k];
+    if (n_found) n_found[s] = nf;
+  }
+  return PTAM_OK;
+}
+// the coarse templates of the points' PatchFinders (protected in the reference: read through PeekFinder)
+int ref_tracker_get_templates(void* hp, int stream, uint8_t* tmpl, int32_t* sums) {
+  Handle* h = (Handle*)hp;
+  if (stream < 0 || stream >= h->S) return PTAM_ERR_INVALID;
+  Stream& st = *h->streams[stream];
+  for (size_t i = 0; i < st.map.vpPoints.size(); i++) {
+    MapPoint* p = st.map.vpPoints[i];
+    bool has = false;
+    if (p->pTData) {
+      PeekFinder& f = static_cast<PeekFinder&>(p->pTData->Finder);
+      has = f.mpLastTemplateMapPoint == p;  // a template has been made for this point (PatchFinder.cc:124)
+      if (has) {
+        if (tmpl) for (int y = 0; y < 8; y++) std::memcpy(tmpl + 64 * i + 8 * y, f.mimTemplate[y], 8);
+        if (sums) { sums[2 * i] = f.mnTemplateSum; sums[2 * i + 1] = f.mnTemplateSumSq; }
+      }
+    }
+    if (!has) { if (tmpl) std::memset(tmpl + 64 * i, 0, 64); if (sums) { sums[2 * i] = 0; sums[2 * i + 1] = 0; } }
+  }
+  return (int)st.map.vpPoints.size();
+}
 int ref_tracker_get_iteration_set(void*, int, int32_t*, int) { return PTAM_ERR_INVALID; }  // a local of TrackMap
 int ref_tracker_get_sbi(void* hp, int stream, float* tmpl, int cap, double* rot3, double* score) {
   Handle* h = (Handle*)hp;

@@ -75,6 +75,7 @@ TRACKER_SYMBOLS = [
     "tracker_level_size", "tracker_get_points", "tracker_get_templates", "tracker_get_sbi",
     "tracker_keyframe_rest", "tracker_get_level_rest", "tracker_refind_in_keyframes",
     "tracker_get_iteration_set", "tracker_epipolar_search", "tracker_set_keyframe_pose",
+    "patch_search_batch", "patch_get_results", "pose_update",
 ]
 BUNDLE_SYMBOLS = [
     "bundle_default_params", "bundle_create", "bundle_destroy", "bundle_last_error",
@@ -171,6 +172,9 @@ class Lib:
             "tracker_get_level_rest": (i, [vp, i, i, P(C.c_int32), i, P(C.c_int32), P(d), i, P(i)]),
             "tracker_get_iteration_set": (i, [vp, i, P(C.c_int32), i]),
             "tracker_epipolar_search": (i, [vp, i, i, i, P(d), d, d, P(d), d, i, P(C.c_int32), P(C.c_int32), P(C.c_int32), P(d)]),
+            "patch_search_batch": (i, [vp, P(d), C.c_uint, i]),
+            "patch_get_results": (i, [vp, i, P(C.c_int32), P(d), P(C.c_int32), P(C.c_int32), P(d), P(C.c_int32)]),
+            "pose_update": (i, [vp, d, i, P(d), P(C.c_int32)]),
             "global_last_error": (C.c_char_p, []),
             "bundle_default_params": (None, [P(BundleParams)]),
             "bundle_create": (vp, [i, P(d), i, i, P(BundleParams)]),
@@ -435,6 +439,28 @@ class Tracker:
         imgs, arr = self._image_ptrs(images)
         p = _f64(poses12).reshape(self.S, 12)
         self._chk(self.lib.fn("tracker_refind_in_keyframes")(self.h, arr, self.W, _dp(p)))
+
+    def patch_search_batch(self, poses12, search_range, subpix_its):
+        """PatchFinder steps 1-5 (PatchFinder.h:54-98) for every map point of every stream against the stream's
+        current frame at the given poses; results via patch_results / get_templates."""
+        p = _f64(poses12).reshape(self.S, 12)
+        self._chk(self.lib.fn("patch_search_batch")(self.h, _dp(p), int(search_range), int(subpix_its)))
+
+    def patch_results(self, stream):
+        n = self._chk(self.lib.fn("patch_get_results")(self.h, stream, None, None, None, None, None, None))
+        m = max(n, 1)
+        out = dict(level=np.zeros(m, np.int32), warp_inverse=np.zeros((m, 4)), template_bad=np.zeros(m, np.int32),
+                   found=np.zeros(m, np.int32), pos=np.zeros((m, 2)), subpix=np.zeros(m, np.int32))
+        self._chk(self.lib.fn("patch_get_results")(self.h, stream, _ip(out["level"]), _dp(out["warp_inverse"]), _ip(out["template_bad"]),
+                                                   _ip(out["found"]), _dp(out["pos"]), _ip(out["subpix"])))
+        return {k: v[:n] for k, v in out.items()}
+
+    def pose_update(self, override_sigma_squared=0.0, mark_outliers=False):
+        """Tracker::CalcPoseUpdate once per stream over the points found by the last patch_search_batch:
+        (mu (S, 6), n_found (S,))."""
+        mu, nf = np.zeros((self.S, 6)), np.zeros(self.S, np.int32)
+        self._chk(self.lib.fn("pose_update")(self.h, float(override_sigma_squared), int(bool(mark_outliers)), _dp(mu), _ip(nf)))
+        return mu, nf
 
     def epipolar_search(self, stream, level, src_kf, src_pose12, src_depth_mean, src_depth_sigma, target_pose12, wiggle_scale, cand_xy):
         """MapMaker::AddPointEpipolar up to the sub-pixel target position for every candidate (irLevelPos in the

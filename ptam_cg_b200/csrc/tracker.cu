@@ -87,7 +87,9 @@ struct ptam_tracker {
   DevBuf<int2> center;
   DevBuf<int4> geo;
   DevBuf<float> sbi_tmpl;
-  DevBuf<double> refind_pose;
+  DevBuf<double> refind_pose, unit_mu;
+  DevBuf<int> unit_nfound;
+  bool unit_searched = false;  // a ptam_patch_search_batch result is resident (what ptam_pose_update works on)
   // relocaliser: keyframe poses (host copy + device table) and which of them have been given
   DevBuf<double> kf_pose;
   size_t kf_pose_cap = 0;
@@ -129,7 +131,7 @@ struct ptam_tracker {
     if (stream) cudaStreamSynchronize(stream);
     for (auto p : kf_bufs) cudaFree(p);
     pyr.free(); corners.free(); lut.free(); mask.free(); ctl.free(); pt_count.free(); kf_ptrs.free();
-    world.free(); right.free(); down.free(); last_warp.free(); m2buf.free(); geo.free(); sbi_tmpl.free(); refind_pose.free(); rest_smap.free(); rest_max.free(); rest_cand.free(); rest_cand_score.free(); rest_counts.free(); v3cam.free(); v2image.free(); derivs.free();
+    world.free(); right.free(); down.free(); last_warp.free(); m2buf.free(); geo.free(); sbi_tmpl.free(); refind_pose.free(); unit_mu.free(); unit_nfound.free(); rest_smap.free(); rest_max.free(); rest_cand.free(); rest_cand_score.free(); rest_counts.free(); v3cam.free(); v2image.free(); derivs.free();
     warp_inv.free(); v2found.free(); sin_.free(); J.free(); e2.free(); src_kf.free(); src_level.free();
     tsum.free(); tsumsq.free(); flags.free(); level.free(); search_level.free(); outliers.free(); inliers.free();
     pvs.free(); iter_idx.free(); center.free(); tmpl.free();
@@ -880,6 +882,87 @@ int ptam_tracker_get_iteration_set(ptam_tracker* t, int stream, int32_t* idx, in
   if (idx && n && cap)
     PTAM_CUDA_TRY(t, cudaMemcpy(idx, t->iter_idx.p + (size_t)stream * t->cap, sizeof(int) * std::min(n, cap), cudaMemcpyDeviceToHost));
   return n;
+}
+
+// ---- PatchFinder / CalcPoseUpdate unit entry points (finer-grained entries for unit parity) ----
+// PatchFinder steps 1-5 (reference include/PatchFinder.h:54-98) for every map point of every stream, against the
+// streams' CURRENT frame (the pyramid + corners of the last make_keyframes / track call), at the given poses.
+int ptam_patch_search_batch(ptam_tracker* t, const double* se3, unsigned range, int subpix_its) {
+  cudaSetDevice(t->device);
+  if (!t->dev.src.l0) { t->set_error("no current frame: call ptam_tracker_make_keyframes (or track) first"); return PTAM_ERR_INVALID; }
+  if (!se3 || subpix_its < 0) { t->set_error("bad arguments"); return PTAM_ERR_INVALID; }
+  if (!t->refind_pose.p) PTAM_CUDA_TRY(t, t->refind_pose.alloc((size_t)12 * t->S));
+  PTAM_CUDA_TRY(t, cudaMemcpyAsync(t->refind_pose.p, se3, sizeof(double) * 12 * t->S, cudaMemcpyHostToDevice, t->stream));
+  TrackerDev d = t->dev;
+  d.mode = 2;
+  d.refind_pose = t->refind_pose.p;
+  d.unit_range = range; d.unit_subpix_its = subpix_its;
+  int maxn = 0;
+  for (int s = 0; s < t->S; s++) maxn = std::max(maxn, t->h_pt_count[s]);
+  k_pvs_select<<<t->S, 1024, 0, t->stream>>>(d);
+  t->launches++;
+  if (maxn > 0) {
+    k_search_prep<<<dim3((maxn + 127) / 128, t->S), 128, 0, t->stream>>>(d, 1);
+    k_search<<<dim3((maxn + 3) / 4, t->S), 128, 0, t->stream>>>(d, 1);
+    t->launches += 2;
+  }
+  PTAM_CUDA_TRY(t, cudaGetLastError());
+  PTAM_CUDA_TRY(t, cudaStreamSynchronize(t->stream));
+  t->unit_searched = true;
+  return PTAM_OK;
+}
+
+// Per-point results of the last ptam_patch_search_batch; any output may be NULL.  Returns the point count.
+int ptam_patch_get_results(ptam_tracker* t, int stream, int32_t* level, double* warp_inverse, int32_t* template_bad, int32_t* found,
+                           double* pos, int32_t* subpix_converged) {
+  cudaSetDevice(t->device);
+  if (stream < 0 || stream >= t->S) { t->set_error("bad stream"); return PTAM_ERR_INVALID; }
+  PTAM_CUDA_TRY(t, cudaStreamSynchronize(t->stream));
+  const int n = t->h_pt_count[stream];
+  const size_t o = (size_t)stream * t->cap;
+  if (!n) return 0;
+  std::vector<int> fl(n), lv(n);
+  std::vector<double> wi(4 * (size_t)n), vf(2 * (size_t)n);
+  PTAM_CUDA_TRY(t, cudaMemcpy(fl.data(), t->flags.p + o, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  PTAM_CUDA_TRY(t, cudaMemcpy(lv.data(), t->level.p + o, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  PTAM_CUDA_TRY(t, cudaMemcpy(wi.data(), t->warp_inv.p + 4 * o, sizeof(double) * 4 * n, cudaMemcpyDeviceToHost));
+  PTAM_CUDA_TRY(t, cudaMemcpy(vf.data(), t->v2found.p + 2 * o, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; i++) {
+    const int f = fl[i];
+    // projected into the frame in this call: it entered the PVS, or its warp was judged inappropriate (level -1, never searched)
+    const bool projected = lv[i] >= 0 || (f & F_IN_IMAGE);
+    const bool fnd = (f & F_IN_PVS) && (f & F_FOUND);
+    if (level) level[i] = lv[i];
+    if (warp_inverse) for (int q = 0; q < 4; q++) warp_inverse[4 * i + q] = projected ? wi[4 * (size_t)i + q] : 0.0;
+    if (template_bad) template_bad[i] = (projected && (f & F_TEMPLATE_BAD)) ? 1 : 0;
+    if (found) found[i] = fnd ? 1 : 0;
+    if (pos) { pos[2 * i] = fnd ? vf[2 * (size_t)i] : 0.0; pos[2 * i + 1] = fnd ? vf[2 * (size_t)i + 1] : 0.0; }
+    if (subpix_converged) subpix_converged[i] = (fnd && (f & F_SUBPIX)) ? 1 : 0;
+  }
+  return n;
+}
+
+// Tracker::CalcPoseUpdate (Tracker.cc:928-1005) once per stream over the points FOUND by the last
+// ptam_patch_search_batch, with the projections and Jacobians of that call's poses (Tracker.h:125-136).
+int ptam_pose_update(ptam_tracker* t, double override_sigma_squared, int mark_outliers, double* mu6, int32_t* n_found) {
+  cudaSetDevice(t->device);
+  if (!t->unit_searched) { t->set_error("ptam_pose_update works on the result of ptam_patch_search_batch: call it first"); return PTAM_ERR_INVALID; }
+  if (!t->unit_mu.p) {
+    PTAM_CUDA_TRY(t, t->unit_mu.alloc((size_t)6 * t->S));
+    PTAM_CUDA_TRY(t, t->unit_nfound.alloc((size_t)t->S));
+  }
+  TrackerDev d = t->dev;
+  d.mode = 2;
+  d.refind_pose = t->refind_pose.p;
+  d.unit_override_sigma = override_sigma_squared; d.unit_mark = mark_outliers ? 1 : 0;
+  d.unit_mu = t->unit_mu.p; d.unit_nfound = t->unit_nfound.p;
+  k_pose<<<t->S, kPoseThreads, kPoseSmemBytes, t->stream>>>(d, 1);
+  t->launches++;
+  PTAM_CUDA_TRY(t, cudaGetLastError());
+  PTAM_CUDA_TRY(t, cudaStreamSynchronize(t->stream));
+  if (mu6) PTAM_CUDA_TRY(t, cudaMemcpy(mu6, t->unit_mu.p, sizeof(double) * 6 * t->S, cudaMemcpyDeviceToHost));
+  if (n_found) PTAM_CUDA_TRY(t, cudaMemcpy(n_found, t->unit_nfound.p, sizeof(int) * t->S, cudaMemcpyDeviceToHost));
+  return PTAM_OK;
 }
 
 }  // extern "C"

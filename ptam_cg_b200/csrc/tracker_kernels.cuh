@@ -116,8 +116,15 @@ struct TrackerDev {
   const int* pt_count;   // [S]
   PointArrays p;
   int S;
-  int mode;                    // 0: TrackFrame; 1: MapMaker::ReFindInSingleKeyFrame (MapMaker.cc:943-1040)
-  const double* refind_pose;   // [S][12] keyframe poses for mode 1
+  int mode;                    // 0: TrackFrame; 1: MapMaker::ReFindInSingleKeyFrame (MapMaker.cc:943-1040);
+                               // 2: PatchFinder unit entry (ptam_patch_search_batch / ptam_pose_update)
+  const double* refind_pose;   // [S][12] keyframe poses for mode 1, the caller's poses for mode 2
+  unsigned unit_range;         // mode 2: FindPatchCoarse range (level-zero pixels)
+  int unit_subpix_its;         // mode 2: IterateSubPixToConvergence budget, 0 = no sub-pixel step
+  double unit_override_sigma;  // mode 2 pose update: dOverrideSigma (0 = M-estimator sigma)
+  int unit_mark;               // mode 2 pose update: bMarkOutliers
+  double* unit_mu;             // mode 2 pose update: [S][6] v6Update, [S] found counts behind them
+  int* unit_nfound;
   // relocaliser (Relocaliser.cc:12-38): on once every stored keyframe has a pose
   int reloc_on;
   size_t kf_sbi_off;           // byte offset of the keyframe's SmallBlurryImage (blur 2.5) in its buffer
@@ -892,8 +899,8 @@ __global__ void __launch_bounds__(1024) k_pvs_select(TrackerDev d) {
   const int cap = d.p.cap;
   const size_t gb = (size_t)s * cap;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0 && d.mode == 1) {
-    // ReFind: the pose is the keyframe's se3CfromW; no motion model, tracker state untouched
+  if (threadIdx.x == 0 && d.mode >= 1) {
+    // ReFind / PatchFinder unit entry: the pose is given (the keyframe's se3CfromW); no motion model, tracker state untouched
     for (int i = 0; i < 12; i++) { pose[i] = d.refind_pose[12 * s + i]; ctl.pose[i] = pose[i]; }
     for (int l = 0; l < kLevels; l++) { running[l] = 0; ctl.attempted[l] = 0; ctl.found[l] = 0; }
     ctl.n_cand = 0;
@@ -984,7 +991,7 @@ __global__ void __launch_bounds__(1024) k_pvs_select(TrackerDev d) {
     __syncthreads();
   }
   // ---- selection (Tracker.cc:485-611), identity shuffle --------------------------------------
-  if (threadIdx.x == 0 && d.mode == 1) {  // ReFind: every projected point is searched, fine stage only
+  if (threadIdx.x == 0 && d.mode >= 1) {  // ReFind / unit entry: every point of the PVS is searched, fine stage only
     int dst = 0, ns = 0;
     for (int l = kLevels - 1; l >= 0; l--) {
       ctl.n_pvs[l] = running[l];
@@ -1104,7 +1111,7 @@ __global__ void __launch_bounds__(128) k_search_prep(TrackerDev d, int stage) {
   // ---- FindPatchCoarse, the scalar part (PatchFinder.cc:160-191): search centre and range in level
   // coordinates (ir() truncation, C++ integer division), candidate index range from the row LUT
   {
-    const unsigned range = d.mode == 1 ? 4u : (stage == 0 ? (unsigned)ctl.coarse_range : (ctl.did_coarse ? 5u : 10u));
+    const unsigned range = d.mode == 1 ? 4u : d.mode == 2 ? d.unit_range : (stage == 0 ? (unsigned)ctl.coarse_range : (ctl.did_coarse ? 5u : 10u));
     const int scale = 1 << sl;
     const int posx = (int)d.p.v2image[2 * g] / scale, posy = (int)d.p.v2image[2 * g + 1] / scale;
     const unsigned r = (range + scale - 1) / scale;
@@ -1150,6 +1157,7 @@ __global__ void __launch_bounds__(128, 12) k_search(TrackerDev d, int stage) {
   const double v2image[2] = {d.p.v2image[2 * g], d.p.v2image[2 * g + 1]};  // re-projected by k_search_prep
   const int sl = d.p.search_level[g];
   if (refind) subpix_its = sl > 0 ? 8 : 0;  // MapMaker.cc:1003-1014
+  if (d.mode == 2) subpix_its = d.unit_subpix_its;
   const bool refresh = (fl & F_REFRESH) != 0;
   fl &= ~F_REFRESH;
   // lane owns template pixels (row = lane/4, cols 2*(lane%4), +1)
@@ -1511,10 +1519,11 @@ PTAM_DEV void pose_iterations(const TrackerDev& d, const Store& st, PoseShared& 
   double* pose = sh.pose;
   double last_mu[6] = {0, 0, 0, 0, 0, 0};
   const bool e2_smem = nf <= kPoseSmemPts;
-  for (int it = 0; it < 10; it++) {
+  const bool unit = d.mode == 2;  // ptam_pose_update: ONE CalcPoseUpdate at the projections of the patch search, not applied
+  for (int it = 0; it < (unit ? 1 : 10); it++) {
     const bool nonlin = stage == 0 || it == 0 || it == 4 || it == 9;
-    const double override_sigma = it > 5 ? (stage == 0 ? 1.0 : 16.0) : 0.0;
-    const bool mark = stage == 1 && it == 9;
+    const double override_sigma = unit ? d.unit_override_sigma : (it > 5 ? (stage == 0 ? 1.0 : 16.0) : 0.0);
+    const bool mark = unit ? d.unit_mark != 0 : (stage == 1 && it == 9);
     // per-point update: reprojection / linear update, scaled error
     for (int i = threadIdx.x; i < nf; i += blockDim.x) {
       double v2i[2] = {st.image(i, 0), st.image(i, 1)};
@@ -1613,6 +1622,10 @@ PTAM_DEV void pose_iterations(const TrackerDev& d, const Store& st, PoseShared& 
       __syncthreads();
       for (int a = 0; a < 6; a++) mu[a] = sh.mu_s[a];
     }
+    if (unit) {
+      if (threadIdx.x < 6) d.unit_mu[6 * blockIdx.x + threadIdx.x] = mu[threadIdx.x];
+      break;
+    }
     // mse3CamFromWorld = SE3<>::exp(v6Update) * mse3CamFromWorld
     if (threadIdx.x == 0) {
       double ex[12], np[12];
@@ -1689,6 +1702,11 @@ __global__ void __launch_bounds__(kPoseThreads, 2) k_pose(TrackerDev d, int stag
     } else {
       pose_iterations(d, sg, sh, stage, nf, gb, fidx, e2);
     }
+  }
+  if (d.mode == 2) {  // unit entry: nothing of the tracker's state moves
+    if (threadIdx.x == 0) d.unit_nfound[s] = nf;
+    if (nf == 0 && threadIdx.x < 6) d.unit_mu[6 * s + threadIdx.x] = 0.0;
+    return;
   }
   if (threadIdx.x < 12) ctl.pose[threadIdx.x] = pose[threadIdx.x];
   if (stage == 0) return;

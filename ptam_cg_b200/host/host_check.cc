@@ -8,6 +8,7 @@
 #include <string>
 #include "Bundle.h"
 #include "Tracker.h"
+#include "PatchFinder.h"
 
 using namespace ptam_b200;
 using namespace TooN;
@@ -105,6 +106,55 @@ static void run_tracker(const std::string& dir) {
   // corners of source keyframe 0, level 0 (raster order) for a bit-exact check
   std::vector<int32_t> c0;
   for (auto& c : kfs[0].aLevels[0].vCorners) { c0.push_back(c.x); c0.push_back(c.y); }
+  // ---- class PatchFinder, the reference's five steps method by method on the first points of the map, against
+  // the last frame at the pose the test gives (tests/host_util.py compares with ptam_patch_search_batch)
+  {
+    auto pf_pose = rd<double>(dir, "pf_pose.f64");
+    auto pf_cfg = rd<int32_t>(dir, "pf_cfg.i32");  // n points, range, sub-pixel iterations
+    KeyFrame target;
+    target.MakeKeyFrame_Lite(frame);
+    const SE3<> se3 = se3_from_array(pf_pose.data());
+    std::vector<int32_t> oi;   // per point: level, template bad, found coarse, coarse x, coarse y, template sum, sub-pixel converged
+    std::vector<double> od;    // per point: warp inverse (4), sub-pixel position (2)
+    std::vector<uint8_t> ot;   // per point: 64 template bytes
+    PatchFinder finder(cam, CVD::ImageRef(W, H));
+    for (int i = 0; i < pf_cfg[0] && i < npts; i++) {
+      MapPoint& p = points[i];
+      Matrix<2> derivs;
+      const int lvl = finder.CalcSearchLevelAndWarpMatrix(p, se3, derivs);
+      int bad = 0, found = 0, cx = 0, cy = 0, tsum = 0, conv = 0;
+      double sx = 0, sy = 0;
+      uint8_t tmpl[64] = {0};
+      if (lvl >= 0) {
+        finder.MakeTemplateCoarseCont(p);
+        bad = finder.TemplateBad();
+        if (!bad) {
+          tsum = finder.GetTemplateSum();
+          std::memcpy(tmpl, finder.GetTemplate().data(), 64);
+          Vector<3> v3 = se3 * p.v3WorldPos;
+          Vector<2> v2 = cam.Project(makeVector(v3[0] / v3[2], v3[1] / v3[2]));
+          found = finder.FindPatchCoarse(CVD::ImageRef((int)v2[0], (int)v2[1]), target, (unsigned)pf_cfg[1]);
+          if (found) {
+            cx = finder.GetCoarsePos().x; cy = finder.GetCoarsePos().y;
+            finder.MakeSubPixTemplate();
+            conv = finder.IterateSubPixToConvergence(target, pf_cfg[2]);
+            if (conv) { sx = finder.GetSubPixPos()[0]; sy = finder.GetSubPixPos()[1]; }
+          }
+        }
+      }
+      oi.insert(oi.end(), {lvl, bad, found, cx, cy, tsum, conv});
+      const Matrix<2>& wi = finder.GetWarpInverse();
+      od.insert(od.end(), {wi(0, 0), wi(0, 1), wi(1, 0), wi(1, 1), sx, sy});
+      ot.insert(ot.end(), tmpl, tmpl + 64);
+    }
+    wr(dir, "pf_out.i32", oi); wr(dir, "pf_out.f64", od); wr(dir, "pf_out_tmpl.u8", ot);
+    // and the batched form on all points
+    std::vector<int> lv; std::vector<char> fd; std::vector<Vector<2> > ps;
+    finder.SearchBatch(map.vpPoints, target, se3, (unsigned)pf_cfg[1], pf_cfg[2], &lv, &fd, &ps);
+    std::vector<int32_t> bi; std::vector<double> bd;
+    for (size_t i = 0; i < lv.size(); i++) { bi.push_back(lv[i]); bi.push_back(fd[i]); bd.push_back(ps[i][0]); bd.push_back(ps[i][1]); }
+    wr(dir, "pf_batch.i32", bi); wr(dir, "pf_batch.f64", bd);
+  }
   kfs[0].MakeKeyFrame_Rest();  // KeyFrame.cc:61-82 through the device
   std::vector<int32_t> rest = {(int32_t)kfs[0].aLevels[0].vMaxCorners.size(), (int32_t)kfs[0].aLevels[0].vCandidates.size()};
   for (auto& c : kfs[0].aLevels[0].vCandidates) { rest.push_back(c.irLevelPos.x); rest.push_back(c.irLevelPos.y); }

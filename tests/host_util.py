@@ -41,6 +41,10 @@ def check_host_classes(lib, binary, tmp_path):
                           ("trk_srclevel.i32", "src_level", np.int32), ("trk_center.i32", "ir_center", np.int32)):
         np.ascontiguousarray(m[key], dt).tofile(tmp_path / name)
     np.ascontiguousarray(pose0, np.float64).tofile(tmp_path / "trk_pose0.f64")
+    pf_pose = synth.perturb_pose(poses[NF], np.random.default_rng(5))   # for class PatchFinder: the last frame is frames[NF]
+    PF_N, PF_RANGE, PF_ITS = 60, 10, 8
+    np.ascontiguousarray(pf_pose, np.float64).tofile(tmp_path / "pf_pose.f64")
+    np.array([PF_N, PF_RANGE, PF_ITS], np.int32).tofile(tmp_path / "pf_cfg.i32")
     # ---- C++ classes
     r = subprocess.run([str(binary), str(tmp_path)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
@@ -68,6 +72,38 @@ def check_host_classes(lib, binary, tmp_path):
     pts = t.get_points(0)
     assert last[0] == int(((pts["flags"] & 8) != 0).sum())
     assert list(last[1:]) == [len(t.get_level(0, l)[1]) for l in range(4)]
+    # ---- class PatchFinder (host/PatchFinder.h), step by step, against the batched C-ABI entry on the same inputs
+    u = Tracker(product, W, H, 1)
+    for k in kfs:
+        u.add_keyframe(k)
+    u.set_map(0, m)
+    u.make_keyframes([frames[NF]])
+    u.patch_search_batch(np.asarray(pf_pose).reshape(1, 12), PF_RANGE, 0)
+    coarse = u.patch_results(0)
+    tmpl, sums = u.get_templates(0)
+    u.patch_search_batch(np.asarray(pf_pose).reshape(1, 12), PF_RANGE, PF_ITS)
+    fine = u.patch_results(0)
+    oi = np.fromfile(tmp_path / "pf_out.i32", np.int32).reshape(-1, 7)
+    od = np.fromfile(tmp_path / "pf_out.f64").reshape(-1, 6)
+    ot = np.fromfile(tmp_path / "pf_out_tmpl.u8", np.uint8).reshape(-1, 64)
+    n = len(oi)
+    assert n == PF_N
+    assert np.array_equal(oi[:, 0], coarse["level"][:n])
+    assert np.array_equal(od[:, :4], coarse["warp_inverse"][:n])
+    searched = (oi[:, 0] >= 0) & (oi[:, 1] == 0)
+    assert np.array_equal(oi[:, 1][oi[:, 0] >= 0], coarse["template_bad"][:n][oi[:, 0] >= 0])
+    assert np.array_equal(oi[:, 2][searched], coarse["found"][:n][searched])
+    fc = searched & (oi[:, 2] == 1)
+    assert fc.sum() > 10
+    assert np.array_equal(oi[fc][:, 3:5], coarse["pos"][:n][fc].astype(np.int32))
+    assert np.array_equal(ot[searched], tmpl[:n][searched]) and np.array_equal(oi[:, 5][searched], sums[:n, 0][searched])
+    assert np.array_equal(oi[:, 6][fc], fine["found"][:n][fc])
+    conv = fc & (oi[:, 6] == 1)
+    assert np.allclose(od[conv][:, 4:6], fine["pos"][:n][conv], atol=1e-9)
+    bi = np.fromfile(tmp_path / "pf_batch.i32", np.int32).reshape(-1, 2)
+    bd = np.fromfile(tmp_path / "pf_batch.f64").reshape(-1, 2)
+    assert np.array_equal(bi[:, 0], fine["level"]) and np.array_equal(bi[:, 1], fine["found"])
+    assert np.allclose(bd, fine["pos"], atol=1e-9)
     det.make_keyframes([kfs[0]])
     assert np.array_equal(np.fromfile(tmp_path / "trk_out_kf0_corners.i32", np.int32).reshape(-1, 2), det.get_level(0, 0)[1])
     mx, cx, _ = det.keyframe_rest(0)[0]

@@ -35,6 +35,10 @@
 #define ptam_tracker_track_frames orc_tracker_track_frames
 #define ptam_tracker_epipolar_search orc_tracker_epipolar_search
 #define ptam_tracker_refind_in_keyframes orc_tracker_refind_in_keyframes
+#define ptam_tracker_get_templates orc_tracker_get_templates
+#define ptam_patch_search_batch orc_patch_search_batch
+#define ptam_patch_get_results orc_patch_get_results
+#define ptam_pose_update orc_pose_update
 #define ptam_global_last_error orc_test_global_last_error
 #ifdef __cplusplus
 extern "C"

@@ -13,7 +13,7 @@ ROOT = Path(__file__).resolve().parent.parent
 
 def declared_symbols():
     text = (ROOT / "include" / "ptam_b200.h").read_text()
-    return sorted(set(re.findall(r"\b(ptam_(?:tracker|bundle|global|nccl)_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(ptam_(?:tracker|bundle|global|nccl|patch|pose)_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_header_symbols_are_exported(product):

@@ -113,6 +113,45 @@ def test_track_frame_from_identical_state(oracle, product, seq640, map640):
     assert n_coarse_frames > 5  # the coarse stage was exercised
 
 
+def test_default_settings_sequence_template_bytes(oracle, product, seq640, map640):
+    """The same per-frame comparison with the SHIPPED settings (Tracker.UseRotationEstimator = 1, what the bench and
+    the reference's default run use): every frame starts from the oracle's state, and all integer outputs are
+    asserted — levels, flags, iteration sets, per-level counts and the 8x8 template bytes + sums.  The predicted
+    pose then carries the rotation estimator's ~1e-13 summation-order difference (k_sbi sums its 15 ESM
+    accumulators by shuffle reduction, the reference pixel by pixel), and the bilinear -> byte truncation of
+    CVD::transform turns that into a different byte wherever a sample lies within ~1e-11 of an integer: over these
+    25 frames x 1000 points x 64 bytes a handful of bytes differ, each by exactly 1, and stay in the per-point
+    template cache until the warp moves.  Everything else (levels, flags, found sets, counts) stays equal."""
+    frames, poses = seq640
+    kfs, m = map640
+    o, p = _setup(oracle, kfs, m, use_rotation_estimator=1), _setup(product, kfs, m, use_rotation_estimator=1)
+    start = synth.perturb_pose(poses[5], np.random.default_rng(7))
+    o.set_state(0, pose12=start); p.set_state(0, pose12=start)
+    n_tmpl = 0
+    worst_diff = 0
+    for f in range(5, 30):
+        p.set_state(0, state=o.get_state(0))
+        ro = o.track_frames([frames[f]])[0]
+        rp = p.track_frames([frames[f]])[0]
+        for fld in ("meas_attempted", "meas_found", "n_corners", "n_pvs"):
+            assert list(getattr(ro, fld)) == list(getattr(rp, fld)), (f, fld)
+        assert (ro.did_coarse, ro.n_coarse, ro.n_level3, ro.n_fine) == (rp.did_coarse, rp.n_coarse, rp.n_level3, rp.n_fine)
+        assert np.array_equal(o.get_iteration_set(0), p.get_iteration_set(0))
+        po, pp = o.get_points(0), p.get_points(0)
+        assert np.array_equal(po["level"], pp["level"]) and np.array_equal(po["flags"], pp["flags"])
+        to, so = o.get_templates(0)
+        tp, sp = p.get_templates(0)
+        diff = to.astype(np.int32) - tp.astype(np.int32)
+        n_diff = int((diff != 0).sum())
+        worst_diff = max(worst_diff, n_diff)
+        assert n_diff <= 8 and (n_diff == 0 or np.abs(diff).max() == 1), (f, n_diff, np.abs(diff).max())
+        assert np.abs(so - sp).max() <= 2 * 255 * 8
+        n_tmpl += int((so[:, 1] > 0).sum())
+        np.testing.assert_allclose(np.array(rp.se3_cam_from_world), np.array(ro.se3_cam_from_world), atol=POSE_TOL, rtol=0)
+    assert n_tmpl > 5000
+    print("default settings: most template bytes differing in one frame:", worst_diff, "of", 64 * len(to))
+
+
 def test_track_sequence_free_running(oracle, product, seq640, map640):
     """Whole run without re-synchronising.  A 1e-15 pose difference (f64 summation order) can flip
     a discrete decision (template refresh at 0.07, ir() truncation, sub-pixel convergence) a few
