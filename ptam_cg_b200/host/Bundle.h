@@ -40,7 +40,10 @@ class Bundle {
     const double a[2] = {v2Pos[0], v2Pos[1]};
     // the reference asserts on bad ids (Bundle.cc:83-84); here it is an exception
     if (ptam_bundle_add_meas(h, nCam, nPoint, a, dSigmaSquared) != PTAM_OK) throw std::out_of_range(ptam_bundle_last_error(h));
+    mnMeas++;
   }
+  int NumMeasurements() const { return mnMeas; }                      // not in the reference: lets a caller skip an empty adjustment
+  const char* LastError() const { return ptam_bundle_last_error(h); } // not in the reference: text behind a negative Compute()
   // Returns the number of accepted update iterations, or negative on error (Bundle.h:114).
   int Compute(bool* pbAbortSignal) {
     static_assert(sizeof(bool) == 1, "abort flag is polled as one byte");
@@ -76,6 +79,7 @@ class Bundle {
 
  private:
   ptam_bundle* h = nullptr;
+  int mnMeas = 0;
 };
 
 }  // namespace ptam_b200

@@ -10,6 +10,7 @@
 // keyframe's std::map<MapPoint*, Measurement> (pointer order) for the measurements; so does this class.
 #pragma once
 #include <algorithm>
+#include <functional>
 #include <cmath>
 #include <map>
 #include <memory>
@@ -319,6 +320,7 @@ class MapMaker {
     mvpKeyFrameQueue.erase(mvpKeyFrameQueue.begin());
     pK->MakeKeyFrame_Rest(mdCandidateMinSTScore);
     mMap.vpKeyFrames.push_back(pK);
+    mMap.nRevision++;  // a new keyframe (and its pose) for the tracker's relocaliser
     for (auto& pm : pK->mMeasurements) {
       MMData(pm.first).sMeasurementKFs.insert(pK);
       pm.second.Source = Measurement::SRC_TRACKER;
@@ -335,6 +337,7 @@ class MapMaker {
   // MapMaker.cc:131-153: points the tracker's M-estimator rejected more often than not become bad; every bad
   // point loses its measurements and leaves the map
   void HandleBadPoints() {
+    if (mfnRefreshCounters) mfnRefreshCounters();  // the tracker's M-estimator counts live on the device between keyframes
     for (MapPoint* p : mMap.vpPoints)
       if (p->nMEstimatorOutlierCount > 20 && p->nMEstimatorOutlierCount > p->nMEstimatorInlierCount) p->bBad = true;
     for (MapPoint* p : mMap.vpPoints)
@@ -347,7 +350,7 @@ class MapMaker {
   // reference's thread.  The reference gives the failure queue its second chance on a 1-in-20 draw of rand();
   // here the caller decides.
   void RunOnce(bool bRefindFailures = false) {
-    if (!mMap.IsGood()) return;
+    if (mbResetRequested || !mMap.IsGood()) return;  // CHECK_RESET (MapMaker.cc:85): a requested reset is the caller's to carry out
     if (!mbBundleConverged_Recent && QueueSize() == 0) BundleAdjustRecent();
     if (mbBundleConverged_Recent && QueueSize() == 0) ReFindNewlyMade();
     if (mbBundleConverged_Recent && !mbBundleConverged_Full && QueueSize() == 0) BundleAdjustAll();
@@ -420,16 +423,28 @@ class MapMaker {
         b.AddMeas(v->second, p->second, pm.second.v2RootPos, s * s);
       }
     }
-    const int nAccepted = b.Compute(&mbBundleAbortRequested);
-    if (nAccepted < 0) {  // the reference ditches the map (MapMaker.cc:887-892)
-      mbResetRequested = true;
+    if (b.NumMeasurements() == 0) {  // nothing to adjust (a sparse map): the reference would assert in FindSigmaSquared (Tools.h:155)
+      mbBundleRunning = false;
+      mbBundleAbortRequested = false;
+      if (bRecent) mbBundleConverged_Recent = true; else mbBundleConverged_Full = true;
       return;
+    }
+    const int nAccepted = b.Compute(&mbBundleAbortRequested);
+    if (nAccepted < 0) {
+      // A negative count from the reference's Bundle means "the adjustment blew up": ditch the map
+      // (MapMaker.cc:887-892).  The library's negative codes are API / CUDA / NCCL errors instead: those are the
+      // caller's problem, not the map's.
+      mbBundleRunning = false;
+      mbBundleAbortRequested = false;
+      throw std::runtime_error(std::string("Bundle::Compute failed: ") + b.LastError());
     }
     if (nAccepted > 0) {
       for (auto& pi : id_of_point) pi.first->v3WorldPos = b.GetPoint(pi.second);
       for (auto& vi : id_of_view) vi.first->se3CfromW = b.GetCamera(vi.second);
       if (bRecent) mbBundleConverged_Recent = false;
       mbBundleConverged_Full = false;
+      // the reference's tracker reads the live map; here it holds a device copy, refreshed on a revision change
+      mMap.nRevision++;
     }
     if (b.Converged()) {
       mbBundleConverged_Recent = true;
@@ -460,6 +475,8 @@ class MapMaker {
   bool mbBundleConverged_Full = true, mbBundleConverged_Recent = true;
   bool mbBundleRunning = false, mbBundleRunningIsRecent = false;
   bool mbBundleAbortRequested = false, mbResetRequested = false;
+  // set by Tracker::SetMapMaker: brings MapPoint::nMEstimatorOutlierCount / InlierCount up to date from the device
+  std::function<void()> mfnRefreshCounters;
   std::vector<std::pair<KeyFrame*, MapPoint*> > mvFailureQueue;
   std::vector<MapPoint*> mvpNewQueue;  // mqNewQueue (MapMaker.h:130): points waiting to be re-found in older keyframes
   std::vector<KeyFrame*> mvpKeyFrameQueue;   // keyframes from the tracker waiting to be processed (MapMaker.h:128)

@@ -2,8 +2,9 @@
 // TrackFrame(CVD::Image<byte>&, bool) = MakeKeyFrame_Lite + PredictPoseWithMotionModel + TrackMap +
 // UpdateMotionModel + AssessTrackingQuality (src/Tracker.cc:86-188,442-698,1012-1107), all on the
 // device through ptam_tracker_track_frames; GetCurrentPose() as in Tracker.h:163.
-// Not mirrored (out of scope): trail tracking / stereo initialisation, GUI commands, GL
-// drawing, relocalisation, MapMaker::AddKeyFrame hand-off (the caller decides from LastResult()).
+// With SetMapMaker: the keyframe hand-over heuristic and the distance branch of AssessTrackingQuality; the
+// relocaliser runs on the device once every stored keyframe has a pose (LastResult().recovery reports it).
+// Not mirrored (out of scope): trail tracking / stereo initialisation, GUI commands, GL drawing.
 #pragma once
 #include <map>
 #include "KeyFrame.h"
@@ -44,7 +45,23 @@ class Tracker {
   // reference: the fourth constructor argument (MapMaker &mm).  With a map maker attached TrackFrame also does
   // the two things the reference's tracker asks it for: the last branch of AssessTrackingQuality
   // (Tracker.cc:1094-1099) and the keyframe hand-over heuristic (Tracker.cc:146-166).
-  void SetMapMaker(MapMaker* mm) { mpMapMaker = mm; }
+  void SetMapMaker(MapMaker* mm) {
+    mpMapMaker = mm;
+    if (mm) mm->mfnRefreshCounters = [this]() { RefreshPointCounters(); };
+  }
+  // MapPoint::nMEstimatorOutlierCount / InlierCount are lifetime counters in the reference (Tracker.cc:990-997
+  // increments the map's own objects).  The device counts from zero after every map upload, so the host keeps
+  // the counts at upload time and adds the device's since then.
+  void RefreshPointCounters() {
+    const size_t n = mvUploaded.size();
+    if (!n || !mbMapUploaded) return;
+    std::vector<int32_t> outl(n), inl(n);
+    if (ptam_tracker_get_points(h, 0, nullptr, nullptr, nullptr, nullptr, outl.data(), inl.data()) < 0) throw std::runtime_error(ptam_tracker_last_error(h));
+    for (size_t i = 0; i < n; i++) {
+      mvUploaded[i]->nMEstimatorOutlierCount = mvBaseOutl[i] + outl[i];
+      mvUploaded[i]->nMEstimatorInlierCount = mvBaseInl[i] + inl[i];
+    }
+  }
   TooN::SE3<> GetCurrentPose() { return mse3CamFromWorld; }
 
   // Sets mse3CamFromWorld (and zero velocity) — what the reference does after stereo initialisation
@@ -66,13 +83,12 @@ class Tracker {
     if (mbKFCurrent) return mCurrentKF;
     for (int l = 0; l < LEVELS; l++) mCurrentKF.FetchLevel(h, 0, l);
     const size_t n = mvUploaded.size();
-    std::vector<int32_t> flags(n), level(n), outl(n), inl(n);
+    std::vector<int32_t> flags(n), level(n);
     std::vector<double> found(2 * n);
-    if (n) ptam_tracker_get_points(h, 0, flags.data(), level.data(), found.data(), nullptr, outl.data(), inl.data());
+    if (n) ptam_tracker_get_points(h, 0, flags.data(), level.data(), found.data(), nullptr, nullptr, nullptr);
+    RefreshPointCounters();
     mCurrentKF.mMeasurements.clear();
     for (size_t i = 0; i < n; i++) {
-      mvUploaded[i]->nMEstimatorOutlierCount = outl[i];
-      mvUploaded[i]->nMEstimatorInlierCount = inl[i];
       if (!(flags[i] & PTAM_PT_FOUND)) continue;
       Measurement m;
       m.nLevel = level[i];
@@ -92,6 +108,9 @@ class Tracker {
   // (their level-0 pixels; the library rebuilds the pyramid), points as SoA.
   void SyncMap() {
     if (mbMapUploaded && mnRevision == mMap.nRevision && mvUploaded.size() == mMap.vpPoints.size()) return;
+    // the upload below zeroes the device's per-point counters: bank what they hold first.  Points that left the
+    // map are in its trash (Map::MoveBadPointsToTrash), still valid objects until their owner empties it.
+    RefreshPointCounters();
     const size_t n = mMap.vpPoints.size();
     std::vector<double> world(3 * n), right(3 * n), down(3 * n);
     std::vector<int32_t> kf(n), lvl(n), ctr(2 * n);
@@ -114,7 +133,7 @@ class Tracker {
     for (KeyFrame* k : mMap.vpKeyFrames) {
       auto it = mKFIds.find(k);
       if (it == mKFIds.end()) {
-        if (k->aLevels[0].im.size() != mirSize) continue;   // not made yet
+        if (k->aLevels[0].im.size() != mirSize) continue;   // not made yet: the relocaliser stays off until it is (LastResult().recovery stays 0)
         const int id = ptam_tracker_add_keyframe(h, k->aLevels[0].im.data(), k->aLevels[0].im.row_stride());
         if (id < 0) throw std::runtime_error(ptam_tracker_last_error(h));
         it = mKFIds.emplace(k, id).first;
@@ -124,6 +143,8 @@ class Tracker {
       if (ptam_tracker_set_keyframe_pose(h, it->second, pose) != PTAM_OK) throw std::runtime_error(ptam_tracker_last_error(h));
     }
     mvUploaded = mMap.vpPoints;
+    mvBaseOutl.resize(n); mvBaseInl.resize(n);
+    for (size_t i = 0; i < n; i++) { mvBaseOutl[i] = mvUploaded[i]->nMEstimatorOutlierCount; mvBaseInl[i] = mvUploaded[i]->nMEstimatorInlierCount; }
     mnRevision = mMap.nRevision;
     mbMapUploaded = true;
   }
@@ -163,6 +184,7 @@ class Tracker {
   ptam_track_result mLast{};
   std::map<KeyFrame*, int> mKFIds;
   std::vector<MapPoint*> mvUploaded;
+  std::vector<int> mvBaseOutl, mvBaseInl;  // the points' lifetime counts when they were uploaded
   unsigned mnRevision = 0;
   bool mbMapUploaded = false, mbKFCurrent = false;
 };

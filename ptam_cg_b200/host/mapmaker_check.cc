@@ -358,6 +358,17 @@ static int run_loop(const std::string& dir) {
   std::vector<double> before_ba;
   for (MapPoint* p : all_points) for (int k = 0; k < 3; k++) before_ba.push_back(p->v3WorldPos[k]);
   const size_t new_queue = mm.mvpNewQueue.size();
+  {
+    // a bundle adjustment that moves the map must reach the tracker's device copy even when no point is trashed:
+    // the revision has to change (the reference's tracker reads the live map)
+    const unsigned rev0 = map.nRevision;
+    const size_t n0 = map.vpPoints.size();
+    mm.BundleAdjustAll();
+    bool moved = false;
+    for (size_t i = 0; i < all_points.size() && !moved; i++)
+      for (int k = 0; k < 3; k++) moved = moved || all_points[i]->v3WorldPos[k] != before_ba[3 * i + k];
+    if (moved && map.vpPoints.size() == n0 && map.nRevision == rev0) { std::fprintf(stderr, "BundleAdjust moved the map without a revision bump\n"); return 1; }
+  }
   int passes = 0;
   do { mm.RunOnce(true); passes++; } while (passes < 12 && !(mm.mbBundleConverged_Full && mm.mbBundleConverged_Recent && mm.QueueSize() == 0));
   std::vector<double> after_ba;
