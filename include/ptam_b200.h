@@ -172,6 +172,13 @@ int ptam_tracker_track_frames_device(ptam_tracker* t, const uint8_t* d_images,
  * batch i.  Host frame buffers must stay valid until the matching collect (page-locked buffers are
  * read by DMA; pageable ones are staged inside submit). */
 int ptam_tracker_submit_frames(ptam_tracker* t, const uint8_t* const* images, int stride);
+/* The same for frames that already live in device memory (layout as ptam_tracker_track_frames_device).  The
+ * frames must be complete when `ready_event` (a cudaEvent_t, or NULL = complete now) has fired, and stay
+ * untouched until the matching collect.  Unlike ptam_tracker_track_frames_device the batch is NOT ordered
+ * behind the work already queued on the handle's stream: its pyramid / FAST / corner-list kernels run on a
+ * second stream beside the last Gauss-Newton iterations of the previous batch. */
+int ptam_tracker_submit_frames_device(ptam_tracker* t, const uint8_t* d_images, size_t frame_pitch_bytes, int stride,
+                                      void* ready_event);
 int ptam_tracker_collect(ptam_tracker* t, ptam_track_result* results);
 int ptam_tracker_synchronize(ptam_tracker* t);
 /* cudaStream_t of the handle, as an opaque pointer (for CUDA-event timing by the caller). */

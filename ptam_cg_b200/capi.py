@@ -88,7 +88,7 @@ BUNDLE_SYMBOLS = [
 ]
 # exported by the product only (CUDA plumbing)
 PRODUCT_ONLY_SYMBOLS = [
-    "global_last_error", "tracker_track_frames_device", "tracker_submit_frames", "tracker_collect", "tracker_cuda_stream",
+    "global_last_error", "tracker_track_frames_device", "tracker_submit_frames", "tracker_submit_frames_device", "tracker_collect", "tracker_cuda_stream",
     "tracker_launch_count", "tracker_set_profiling", "tracker_get_kernel_times",
     "bundle_cuda_stream", "bundle_launch_count",
     "nccl_unique_id", "nccl_comm_create", "nccl_comm_destroy", "bundle_init_shard", "bundle_shard_plan",
@@ -96,7 +96,7 @@ PRODUCT_ONLY_SYMBOLS = [
 ]
 BUNDLE_PHASES = ["project", "select", "jacobian", "vinv_init", "schur", "allreduce", "solve", "update_newerror", "reserved",
                  "commit_erase", "begin_setup", "host_control_and_sync"]
-TRACKER_KERNELS = ["k_pyramid", "k_fast", "k_compact", "k_sbi+k_pvs_select", "k_search_coarse", "k_pose_coarse",
+TRACKER_KERNELS = ["k_fast2_l0", "k_fast2_l123", "k_compact", "k_sbi+k_pvs_select", "k_search_coarse", "k_pose_coarse",
                    "k_search_fine", "k_pose_fine"]
 
 
@@ -156,6 +156,7 @@ class Lib:
             "tracker_track_frames": (i, [vp, P(vp), i, P(TrackResult)]),
             "tracker_track_frames_device": (i, [vp, vp, C.c_size_t, i, P(TrackResult)]),
             "tracker_submit_frames": (i, [vp, P(vp), i]),
+            "tracker_submit_frames_device": (i, [vp, vp, C.c_size_t, i, vp]),
             "tracker_collect": (i, [vp, P(TrackResult)]),
             "tracker_synchronize": (i, [vp]),
             "tracker_cuda_stream": (vp, [vp]),
@@ -225,7 +226,7 @@ def product_lib() -> Lib:
     """The CUDA product library. Raises if it has not been built — never falls back."""
     global _product
     if _product is None:
-        _product = Lib(LIB_PATH, "ptam_")
+        _product = Lib(os.environ.get("PTAM_B200_LIB", LIB_PATH), "ptam_")  # the override is for kernel experiments (scripts/lab)
     return _product
 
 
@@ -390,6 +391,11 @@ class Tracker:
     def ptr_array(self, ptrs):
         """ctypes pointer array for submit_array (build once per batch, outside any timed loop)."""
         return (C.c_void_p * self.S)(*ptrs)
+
+    def submit_device(self, dptr, frame_pitch, stride, ready_event=None):
+        """Pipelined track_frames_device: frames resident in device memory, complete now (or at ready_event)."""
+        self._chk(self.lib.fn("tracker_submit_frames_device")(self.h, C.c_void_p(dptr), frame_pitch, stride,
+                                                              C.c_void_p(ready_event) if ready_event else None))
 
     def submit_array(self, arr, stride):
         self._chk(self.lib.fn("tracker_submit_frames")(self.h, arr, stride))

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -123,6 +124,8 @@ struct ptam_tracker {
   StreamCtl* h_ctl_slot[2] = {nullptr, nullptr};
   cudaEvent_t ev_h2d[2] = {}, ev_done[2] = {};
   long long n_submit = 0, n_collect = 0;
+  cudaEvent_t dbg_ev[2][4] = {};  // PTAM_B200_DEBUG_TIMES: H2D begin / end, image work end, chain end per slot
+  bool dbg_times = false;
 
   void set_error(const std::string& e) { err = e; g_last_error = e; }
 
@@ -145,6 +148,8 @@ struct ptam_tracker {
       if (ev_done[k]) cudaEventDestroy(ev_done[k]);
     }
     if (cstream) cudaStreamDestroy(cstream);
+    if (istream) { cudaStreamSynchronize(istream); cudaStreamDestroy(istream); }
+    for (auto e : {ev_fork, ev_pyr, ev_img, ev_imgfree}) if (e) cudaEventDestroy(e);
     if (h_stage) cudaFreeHost(h_stage);
     if (h_ctl) cudaFreeHost(h_ctl);
     if (stream) cudaStreamDestroy(stream);
@@ -160,24 +165,7 @@ struct ptam_tracker {
     PTAM_CUDA_TRY(this, cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     PTAM_CUDA_TRY(this, cudaEventCreateWithFlags(&stage_ev, cudaEventDisableTiming));
     Geom& g = dev.g;
-    const int thr[4] = {10, 15, 15, 10};  // KeyFrame.cc:35-42
-    size_t img = 0, cor = 0, msk = 0;
-    int lut_o = 0, tiles = 0, lw = w, lh = h;
-    for (int l = 0; l < kLevels; l++) {
-      LevelDesc& L = g.lev[l];
-      L.w = lw; L.h = lh; L.pitch = (lw + 15) & ~15;
-      L.nwords = (lw + 31) / 32;
-      L.corner_cap = std::max(0, lw - 6) * std::max(0, lh - 6);
-      L.img_off = img; img += (size_t)L.pitch * lh; img = (img + 255) & ~(size_t)255;
-      L.corner_off = cor; cor += L.corner_cap;
-      L.lut_off = lut_o; lut_o += lh;
-      L.mask_off = msk; msk += (size_t)L.nwords * lh;
-      L.tiles_x = (lw + kFastTW - 1) / kFastTW; L.tiles_y = (lh + kFastTH - 1) / kFastTH;
-      L.tile_base = tiles; tiles += L.tiles_x * L.tiles_y;
-      g.thresholds[l] = thr[l];
-      lw /= 2; lh /= 2;
-    }
-    g.pyr_bytes = img; g.corner_stride = cor; g.lut_stride = lut_o; g.mask_stride = msk; g.fast_tiles = tiles;
+    make_geom(g, w, h);
     dev.cam = make_cam(cam_params, w, h);
     if (prm) dev.prm = *prm; else ptam_tracker_default_params(&dev.prm);
     {  // SmallBlurryImage geometry and Gaussian taps (ImageProcess.cc:279-304; libCVD convolveGaussian)
@@ -210,6 +198,8 @@ struct ptam_tracker {
       dev.reloc_on = 0; dev.kf_pose = nullptr;
     }
     dev.S = S;
+    dev.pose_ws_smem = 1;  // 0: k_pose works on the global arrays (measured: 0.149 -> 0.178 ms per 296 frames)
+    if (const char* e = std::getenv("PTAM_B200_POSE_SMEM")) dev.pose_ws_smem = std::atoi(e);
     PTAM_CUDA_TRY(this, pyr.alloc(g.pyr_bytes * S));
     PTAM_CUDA_TRY(this, corners.alloc(g.corner_stride * S));
     PTAM_CUDA_TRY(this, lut.alloc((size_t)g.lut_stride * S));
@@ -349,43 +339,101 @@ struct ptam_tracker {
     return PTAM_OK;
   }
 
+  // Image stream.  A frame batch is two chains: the image work (pyramid + FAST + corner lists) on `istream`, and
+  // the tracking work on the handle's stream.  Within a batch, k_sbi / k_pvs_select (latency-bound, one CTA per
+  // tracker) run beside the FAST of levels 1..3 and k_compact; across batches of the pipelined entry points
+  // (ptam_tracker_submit_frames[_device]) the image work of batch i+1 runs beside the ten fine Gauss-Newton
+  // iterations of batch i, which touch neither the frame nor the corner lists.  Ordering:
+  //   istream:  [wait: frames ready, ev_imgfree = fine search of the previous batch done]  k_fast2<true>  (ev_pyr)
+  //             k_fast2<false>  k_compact  (ev_img)
+  //   stream:   [wait ev_pyr]  k_sbi  k_reloc  k_pvs_select  [wait ev_img]  coarse search + pose, fine search
+  //             (ev_imgfree)  fine pose
+  // The handle's stream always waits for ev_img of its own batch, so once it has drained, istream has too.
+  cudaStream_t istream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_pyr = nullptr, ev_img = nullptr, ev_imgfree = nullptr;
+  bool imgfree_pending = false;  // ev_imgfree has been recorded (a batch went through the pipelined path)
+
+  int ensure_istream() {
+    if (istream) return PTAM_OK;
+    PTAM_CUDA_TRY(this, cudaStreamCreateWithFlags(&istream, cudaStreamNonBlocking));
+    for (cudaEvent_t* e : {&ev_fork, &ev_pyr, &ev_img, &ev_imgfree}) PTAM_CUDA_TRY(this, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    return PTAM_OK;
+  }
+
+  void queue_keyframe(const TrackerDev& d, cudaStream_t st, bool prof, cudaEvent_t after_l0 = nullptr) {
+    const LevelDesc& L0 = d.g.lev[0];
+    if (prof) pbegin(0);
+    k_fast2<true><<<dim3(L0.tiles_x, L0.tiles_y, S), 256, 0, st>>>(d);
+    if (prof) pend(0); else launches++;
+    if (after_l0) cudaEventRecord(after_l0, st);
+    if (prof) pbegin(1);
+    k_fast2<false><<<dim3(d.g.fast_tiles, S), 256, 0, st>>>(d);
+    if (prof) { pend(1); pbegin(2); } else launches++;
+    k_compact<<<dim3(kLevels, S), 1024, 0, st>>>(d);
+    if (prof) pend(2); else launches++;
+  }
+
   int launch_keyframe(const TrackerDev& d, bool collect = true) {
     rest_stream = -1;  // MakeKeyFrame_Rest results belong to the previous frame
-    const LevelDesc& L0 = d.g.lev[0];
-    dim3 gp((L0.w + 63) / 64, (L0.h + 63) / 64, S);
-    pbegin(0); k_pyramid<<<gp, 256, 0, stream>>>(d); pend(0);
-    pbegin(1); k_fast<<<dim3(d.g.fast_tiles, S), 256, 0, stream>>>(d); pend(1);
-    pbegin(2); k_compact<<<dim3(kLevels, S), 1024, 0, stream>>>(d); pend(2);
+    queue_keyframe(d, stream, profiling);
     PTAM_CUDA_TRY(this, cudaGetLastError());
     return collect ? pcollect(7u) : PTAM_OK;
   }
 
-  int launch_track(const TrackerDev& d) {
-    int rc = launch_keyframe(d, false);
-    if (rc) return rc;
+  // frames_ready: nullptr = the frames are ordered by the handle's stream (everything queued on it so far);
+  // otherwise an event the image stream waits for instead (pipelined entry points)
+  int launch_track(const TrackerDev& d, cudaEvent_t frames_ready = nullptr, bool pipelined = false) {
+    rest_stream = -1;
+    const bool prof = profiling;  // per-kernel event timing needs one serial chain
+    static const bool no_istream = std::getenv("PTAM_B200_ISTREAM") && std::atoi(std::getenv("PTAM_B200_ISTREAM")) == 0;
     int maxn = 0;
     for (int s = 0; s < S; s++) maxn = std::max(maxn, h_pt_count[s]);
     unsigned used = 7u | 8u | 32u | 128u;
-    pbegin(3);
+    if (prof) queue_keyframe(d, stream, true);
+    else if (no_istream) { queue_keyframe(d, stream, false); ensure_istream(); cudaEventRecord(ev_pyr, stream); cudaEventRecord(ev_img, stream); }
+    else {
+      int rc = ensure_istream();
+      if (rc) return rc;
+      if (!pipelined) {
+        PTAM_CUDA_TRY(this, cudaEventRecord(ev_fork, stream));
+        PTAM_CUDA_TRY(this, cudaStreamWaitEvent(istream, ev_fork, 0));
+      } else {
+        if (frames_ready) PTAM_CUDA_TRY(this, cudaStreamWaitEvent(istream, frames_ready, 0));
+        if (imgfree_pending) PTAM_CUDA_TRY(this, cudaStreamWaitEvent(istream, ev_imgfree, 0));
+      }
+      queue_keyframe(d, istream, false, ev_pyr);
+      PTAM_CUDA_TRY(this, cudaEventRecord(ev_img, istream));
+      PTAM_CUDA_TRY(this, cudaStreamWaitEvent(stream, ev_pyr, 0));
+    }
+    if (prof) pbegin(3);
     k_sbi<<<S, 256, sbi_smem, stream>>>(d);
     if (d.reloc_on) { k_reloc<<<S, 256, sbi_smem, stream>>>(d); launches++; }
     k_pvs_select<<<S, 1024, 0, stream>>>(d);
-    pend(3); launches++;
+    if (prof) pend(3); else launches++;
+    launches++;
+    if (!prof) PTAM_CUDA_TRY(this, cudaStreamWaitEvent(stream, ev_img, 0));
     const int coarse_items = std::min(maxn, 2 * std::max(0, d.prm.coarse_max));
     if (coarse_items > 0) {
-      pbegin(4);
+      if (prof) pbegin(4);
       k_search_prep<<<dim3((coarse_items + 127) / 128, S), 128, 0, stream>>>(d, 0);
       k_search<<<dim3((coarse_items + 3) / 4, S), 128, 0, stream>>>(d, 0);
-      pend(4); launches++; used |= 16u;
+      if (prof) pend(4); else launches++;
+      launches++; used |= 16u;
     }
-    pbegin(5); k_pose<<<S, kPoseThreads, kPoseSmemBytes, stream>>>(d, 0); pend(5);
+    if (prof) pbegin(5);
+    k_pose<<<S, kPoseThreads, d.pose_ws_smem ? kPoseSmemBytes : 0, stream>>>(d, 0);
+    if (prof) pend(5); else launches++;
     if (maxn > 0) {
-      pbegin(6);
+      if (prof) pbegin(6);
       k_search_prep<<<dim3((maxn + 127) / 128, S), 128, 0, stream>>>(d, 1);
       k_search<<<dim3((maxn + 3) / 4, S), 128, 0, stream>>>(d, 1);
-      pend(6); launches++; used |= 64u;
+      if (prof) pend(6); else launches++;
+      launches++; used |= 64u;
     }
-    pbegin(7); k_pose<<<S, kPoseThreads, kPoseSmemBytes, stream>>>(d, 1); pend(7);
+    if (!prof) { PTAM_CUDA_TRY(this, cudaEventRecord(ev_imgfree, stream)); imgfree_pending = true; }
+    if (prof) pbegin(7);
+    k_pose<<<S, kPoseThreads, d.pose_ws_smem ? kPoseSmemBytes : 0, stream>>>(d, 1);
+    if (prof) pend(7); else launches++;
     PTAM_CUDA_TRY(this, cudaGetLastError());
     return pcollect(used);
   }
@@ -397,11 +445,12 @@ struct ptam_tracker {
     return PTAM_OK;
   }
 
-  int ensure_pipeline() {
+  int ensure_pipeline(bool landing_buffers) {
+    if (landing_buffers && !l0slot[0].p)
+      for (int k = 0; k < 2; k++) PTAM_CUDA_TRY(this, l0slot[k].alloc((size_t)dev.g.lev[0].pitch * H * S));
     if (cstream) return PTAM_OK;
     PTAM_CUDA_TRY(this, cudaStreamCreateWithFlags(&cstream, cudaStreamNonBlocking));
     for (int k = 0; k < 2; k++) {
-      PTAM_CUDA_TRY(this, l0slot[k].alloc((size_t)dev.g.lev[0].pitch * H * S));
       PTAM_CUDA_TRY(this, cudaMallocHost(&h_ctl_slot[k], sizeof(StreamCtl) * S));
       PTAM_CUDA_TRY(this, cudaEventCreateWithFlags(&ev_h2d[k], cudaEventDisableTiming));
       PTAM_CUDA_TRY(this, cudaEventCreateWithFlags(&ev_done[k], cudaEventDisableTiming));
@@ -417,7 +466,7 @@ struct ptam_tracker {
       r.scene_depth_mean = c.st.scene_depth_mean; r.scene_depth_sigma = c.st.scene_depth_sigma;
       for (int l = 0; l < kLevels; l++) {
         r.meas_attempted[l] = c.attempted[l]; r.meas_found[l] = c.found[l];
-        r.n_corners[l] = c.n_corners[l]; r.n_pvs[l] = c.n_pvs[l];
+        r.n_corners[l] = c.res_n_corners[l]; r.n_pvs[l] = c.n_pvs[l];
       }
       r.did_coarse = c.did_coarse; r.n_coarse = c.n_coarse; r.n_level3 = c.n_l3; r.n_fine = c.n_fine;
       r.tracking_quality = c.st.tracking_quality; r.quality_needs_kf_distance = c.needs_kf_distance;
@@ -597,27 +646,53 @@ int ptam_tracker_track_frames_device(ptam_tracker* t, const uint8_t* d_images, s
   return PTAM_OK;
 }
 
+static int submit_common(ptam_tracker* t, const TrackerDev& d, cudaEvent_t frames_ready, int k) {
+  int rc = t->launch_track(d, frames_ready, true);
+  if (rc) return rc;
+  if (t->dbg_times && t->dbg_ev[k][0]) { cudaEventRecord(t->dbg_ev[k][2], t->istream ? t->istream : t->stream); cudaEventRecord(t->dbg_ev[k][3], t->stream); }
+  PTAM_CUDA_TRY(t, cudaMemcpyAsync(t->h_ctl_slot[k], t->ctl.p, sizeof(StreamCtl) * t->S, cudaMemcpyDeviceToHost, t->stream));
+  PTAM_CUDA_TRY(t, cudaEventRecord(t->ev_done[k], t->stream));
+  t->n_submit++;
+  return PTAM_OK;
+}
+
 int ptam_tracker_submit_frames(ptam_tracker* t, const uint8_t* const* images, int stride) {
   cudaSetDevice(t->device);
   if (t->n_submit - t->n_collect >= 2) { t->set_error("two frame batches are already in flight: collect one first"); return PTAM_ERR_CAPACITY; }
-  int rc = t->ensure_pipeline();
+  int rc = t->ensure_pipeline(true);
   if (rc) return rc;
   const int k = (int)(t->n_submit & 1);
   const size_t pitch = (size_t)t->dev.g.lev[0].pitch * t->H;
   // the slot's previous batch was collected (its ev_done has fired), so the landing buffer is free
+  static const bool dbg = std::getenv("PTAM_B200_DEBUG_TIMES") != nullptr;
+  t->dbg_times = dbg;
+  if (dbg) {
+    for (auto& e : t->dbg_ev[k]) if (!e) cudaEventCreate(&e);
+    cudaEventRecord(t->dbg_ev[k][0], t->cstream);
+  }
   rc = t->upload_images(images, stride, t->l0slot[k].p, pitch, t->S, t->cstream);
   if (rc) return rc;
+  if (dbg) cudaEventRecord(t->dbg_ev[k][1], t->cstream);
   PTAM_CUDA_TRY(t, cudaEventRecord(t->ev_h2d[k], t->cstream));
   PTAM_CUDA_TRY(t, cudaStreamWaitEvent(t->stream, t->ev_h2d[k], 0));
   TrackerDev d = t->dev;
   d.src.l0 = t->l0slot[k].p; d.src.stream_pitch = pitch; d.src.pitch = d.g.lev[0].pitch;
   t->dev.src = d.src;
-  rc = t->launch_track(d);
+  return submit_common(t, d, t->ev_h2d[k], k);
+}
+
+int ptam_tracker_submit_frames_device(ptam_tracker* t, const uint8_t* d_images, size_t frame_pitch_bytes, int stride, void* ready_event) {
+  cudaSetDevice(t->device);
+  if (!d_images || stride < t->W) { t->set_error("bad device frame description"); return PTAM_ERR_INVALID; }
+  if (t->n_submit - t->n_collect >= 2) { t->set_error("two frame batches are already in flight: collect one first"); return PTAM_ERR_CAPACITY; }
+  int rc = t->ensure_pipeline(false);
   if (rc) return rc;
-  PTAM_CUDA_TRY(t, cudaMemcpyAsync(t->h_ctl_slot[k], t->ctl.p, sizeof(StreamCtl) * t->S, cudaMemcpyDeviceToHost, t->stream));
-  PTAM_CUDA_TRY(t, cudaEventRecord(t->ev_done[k], t->stream));
-  t->n_submit++;
-  return PTAM_OK;
+  const int k = (int)(t->n_submit & 1);
+  TrackerDev d = t->dev;
+  d.src.l0 = d_images; d.src.stream_pitch = frame_pitch_bytes; d.src.pitch = stride;
+  t->dev.src = d.src;
+  if (ready_event) PTAM_CUDA_TRY(t, cudaStreamWaitEvent(t->stream, (cudaEvent_t)ready_event, 0));
+  return submit_common(t, d, (cudaEvent_t)ready_event, k);
 }
 
 int ptam_tracker_collect(ptam_tracker* t, ptam_track_result* results) {
@@ -625,10 +700,27 @@ int ptam_tracker_collect(ptam_tracker* t, ptam_track_result* results) {
   if (t->n_collect >= t->n_submit) { t->set_error("nothing in flight"); return PTAM_ERR_INVALID; }
   const int k = (int)(t->n_collect & 1);
   PTAM_CUDA_TRY(t, cudaEventSynchronize(t->ev_done[k]));
+  if (t->dbg_times && t->dbg_ev[k][3]) {
+    float h2d = 0, img = 0, chain = 0, gap = 0;
+    cudaEventElapsedTime(&h2d, t->dbg_ev[k][0], t->dbg_ev[k][1]);
+    cudaEventElapsedTime(&img, t->dbg_ev[k][1], t->dbg_ev[k][2]);
+    cudaEventElapsedTime(&chain, t->dbg_ev[k][1], t->dbg_ev[k][3]);
+    if (t->dbg_ev[k ^ 1][1] && t->n_collect > 0) cudaEventElapsedTime(&gap, t->dbg_ev[k ^ 1][1], t->dbg_ev[k][0]);
+    std::fprintf(stderr, "[ptam dbg] batch %lld: H2D %.3f ms, H2D end -> image work end %.3f, -> chain end %.3f, previous H2D end -> this H2D begin %.3f\n",
+                 t->n_collect, h2d, img, chain, gap);
+  }
   if (results) t->convert_results(t->h_ctl_slot[k], results);
   t->n_collect++;
   return PTAM_OK;
 }
+
+#ifdef PTAM_POSE_CLOCKS
+extern "C" int ptam_debug_pose_clocks(long long* out, int reset) {
+  if (out && cudaMemcpyFromSymbol(out, ptam::g_pose_clk, sizeof(long long) * 32) != cudaSuccess) return -1;
+  if (reset) { long long z[32] = {}; if (cudaMemcpyToSymbol(ptam::g_pose_clk, z, sizeof(z)) != cudaSuccess) return -1; }
+  return 0;
+}
+#endif
 
 int ptam_tracker_synchronize(ptam_tracker* t) {
   cudaSetDevice(t->device);
@@ -956,7 +1048,7 @@ int ptam_pose_update(ptam_tracker* t, double override_sigma_squared, int mark_ou
   d.refind_pose = t->refind_pose.p;
   d.unit_override_sigma = override_sigma_squared; d.unit_mark = mark_outliers ? 1 : 0;
   d.unit_mu = t->unit_mu.p; d.unit_nfound = t->unit_nfound.p;
-  k_pose<<<t->S, kPoseThreads, kPoseSmemBytes, t->stream>>>(d, 1);
+  k_pose<<<t->S, kPoseThreads, d.pose_ws_smem ? kPoseSmemBytes : 0, t->stream>>>(d, 1);
   t->launches++;
   PTAM_CUDA_TRY(t, cudaGetLastError());
   PTAM_CUDA_TRY(t, cudaStreamSynchronize(t->stream));

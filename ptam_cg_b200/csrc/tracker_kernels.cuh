@@ -27,7 +27,7 @@ struct LevelDesc {
   size_t img_off;       // byte offset inside a pyramid buffer
   size_t corner_off;    // offset (int2) inside the per-stream corner buffer
   size_t mask_off;      // offset (words) inside the per-stream mask buffer
-  int tiles_x, tiles_y, tile_base;  // k_fast tiling
+  int tiles_x, tiles_y, tile_base;  // k_fast tiling (tile_base counts from level 1: level 0 has its own launch)
 };
 
 struct Geom {
@@ -36,7 +36,7 @@ struct Geom {
   size_t corner_stride;  // int2 per stream
   int lut_stride;        // ints per stream
   size_t mask_stride;    // words per stream
-  int fast_tiles;        // tiles per frame over all levels
+  int fast_tiles;        // k_fast2 tiles per frame over levels 1..3
   int thresholds[kLevels];
 };
 
@@ -50,6 +50,7 @@ struct StreamCtl {
   int n_coarse, n_l3, n_fine;
   int try_coarse, coarse_range, did_coarse;
   int n_corners[kLevels];
+  int res_n_corners[kLevels];  // n_corners of THIS frame for the results (k_compact of the next batch may already run beside the fine pose)
   int needs_kf_distance;
   int n_cand;  // ZMSSD windows evaluated this frame (coarse + fine), for the roofline accounting
   // SmallBlurryImage rotation estimator (Tracker.cc:95-108,1012-1029)
@@ -116,6 +117,8 @@ struct TrackerDev {
   const int* pt_count;   // [S]
   PointArrays p;
   int S;
+  int s_off;                   // first stream of this launch (0 unless a batch is cut into groups)
+  int pose_ws_smem;            // k_pose keeps the per-point working set in (dynamic) shared memory
   int mode;                    // 0: TrackFrame; 1: MapMaker::ReFindInSingleKeyFrame (MapMaker.cc:943-1040);
                                // 2: PatchFinder unit entry (ptam_patch_search_batch / ptam_pose_update)
   const double* refind_pose;   // [S][12] keyframe poses for mode 1, the caller's poses for mode 2
@@ -132,6 +135,31 @@ struct TrackerDev {
   float taps25[12];            // Gaussian taps for sigma = 2.5 (SmallBlurryImage's default blur)
   int ks25;
 };
+
+constexpr int kF2W = 128, kF2H = 48;   // k_fast2 tile
+
+// Level geometry of a w x h frame (pyramid, masks, corner lists, k_fast2 tiling); host side.
+inline void make_geom(Geom& g, int w, int h) {
+  const int thr[4] = {10, 15, 15, 10};  // KeyFrame.cc:35-42
+  size_t img = 0, cor = 0, msk = 0;
+  int lut_o = 0, tiles = 0, lw = w, lh = h;
+  for (int l = 0; l < kLevels; l++) {
+    LevelDesc& L = g.lev[l];
+    L.w = lw; L.h = lh; L.pitch = (lw + 15) & ~15;
+    L.nwords = (lw + 31) / 32;
+    L.corner_cap = (lw > 6 ? lw - 6 : 0) * (lh > 6 ? lh - 6 : 0);
+    L.img_off = img; img += (size_t)L.pitch * lh; img = (img + 255) & ~(size_t)255;
+    L.corner_off = cor; cor += L.corner_cap;
+    L.lut_off = lut_o; lut_o += lh;
+    L.mask_off = msk; msk += (size_t)L.nwords * lh;
+    L.tiles_x = (lw + kF2W - 1) / kF2W; L.tiles_y = (lh + kF2H - 1) / kF2H;
+    L.tile_base = l == 0 ? 0 : tiles;
+    if (l > 0) tiles += L.tiles_x * L.tiles_y;
+    g.thresholds[l] = thr[l];
+    lw /= 2; lh /= 2;
+  }
+  g.pyr_bytes = img; g.corner_stride = cor; g.lut_stride = lut_o; g.mask_stride = msk; g.fast_tiles = tiles;
+}
 
 PTAM_DEV const uint8_t* level_image(const TrackerDev& d, int s, int l, int& pitch) {
   if (l == 0) { pitch = d.src.pitch; return d.src.l0 + (size_t)s * d.src.stream_pitch; }
@@ -201,23 +229,6 @@ __global__ void __launch_bounds__(256) k_pyramid(TrackerDev d) {
   }
 }
 
-// =============================================================================================
-// k_fast — FAST-10.  Tile = 128 px x 32 rows per CTA (256 threads), staged in shared memory with a
-// 3-row halo by 16-byte loads.  Three phases:
-//   1. compass pre-test on packed data: every thread tests 4 adjacent pixels of 4 rows.  Any arc of
-//      >= 10 ring pixels contains two ADJACENT compass points (ring 0/4/8/12 = below/right/above/
-//      left), so a corner needs (below|above) & (right|left) all brighter than p+t (or all darker
-//      than p-t).  The comparisons run two pixels per 32-bit register in 16-bit lanes:
-//      bit 15 of  x + (0x8000 - p - t - 1)  is set iff x > p + t,  bit 15 of  (0x8000 + p - t - 1) - x
-//      iff x < p - t;  no lane can carry or borrow into its neighbour.
-//   2. the surviving candidates (~9 % of level-0 pixels) are compacted into a CTA-wide list, so that
-//   3. every thread runs the full 16-pixel ring test (>= 10 contiguous, strict) on one candidate.
-// Output: one bit per pixel.  Raster order is restored by k_compact.
-// =============================================================================================
-constexpr int kFastTW = 128, kFastTH = 32;
-constexpr int kFastSW = kFastTW + 32;   // staged bytes per row: x0-16 .. x0+143 (ten 16-byte chunks)
-constexpr int kFastSR = kFastTH + 6;    // staged rows: y0-3 .. y0+34
-
 PTAM_DEV bool run10(unsigned m) {
   m |= m << 16;
   unsigned a = m & (m >> 1);
@@ -228,34 +239,80 @@ PTAM_DEV bool run10(unsigned m) {
   return (a & 0xFFFFu) != 0;
 }
 
-__global__ void __launch_bounds__(256) k_fast(TrackerDev d) {
-  __shared__ __align__(16) uint8_t tile[kFastSR * kFastSW];
-  __shared__ uint16_t cand_list[kFastTW * kFastTH];
-  __shared__ unsigned out_mask[kFastTH][4];
-  __shared__ int cand_count;
-  const int s = blockIdx.y;
-  int l = 0;
+// =============================================================================================
+// k_fast2 — pyramid + FAST-10, the per-frame form of KeyFrame::MakeKeyFrame_Lite's image work
+// (KeyFrame.cc:25-42).  Two launches: <true> runs on level 0 and ALSO writes levels 1..3 (every CTA
+// half-samples its own 128x48 tile three times: 8x8 level-0 blocks, one thread each, truncating mean
+// at every level exactly as CVD::halfSample), <false> runs FAST on levels 1..3.
+// Tile = 128 px x 48 rows per CTA (256 threads), staged in shared memory with a 3-row halo by 16-byte
+// loads.  Warp w owns rows 6w..6w+5, lane l the pixels 4l..4l+3 of each row.  Comparisons run two pixels
+// per 32-bit register in 16-bit lanes: bit 15 of  x + (0x8000 - p - t - 1)  is set iff x > p + t,  bit 15
+// of  (0x8000 + p - t - 1) - x  iff x < p - t;  no lane can carry or borrow into its neighbour.
+//   A. compass test on every pixel.  Any arc of >= 10 ring pixels contains two ADJACENT compass points
+//      (ring 0/4/8/12 = below/right/above/left): (below|above) & (right|left), all brighter than p+t or
+//      all darker than p-t.  The aligned word of a row is unpacked once and serves as the centre of row
+//      y, "above" of row y+3 and "below" of row y-3.  ~9 % of level-0 pixels pass (every edge does), in
+//      ~13 % of the 4-pixel words; those words go to a per-warp list (ballot + popc, no barrier).
+//   B. the same warp tests its listed words for an ANTIPODAL pair: an arc of >= 10 contains five
+//      consecutive even ring positions j .. j+8, hence both ends of one of the four diameters
+//      (0,8) (4,12) (2,10) (6,14).  A straight edge never has both ends of a diameter on its far side, so
+//      what is left (~2 % of level-0 pixels; 1.4 % are corners) goes to a CTA-wide list with the polarity.
+//   C. every thread runs the 16-pixel ring test (>= 10 contiguous, strict) of ONE candidate in ONE
+//      polarity: sign of  v * sg + c0  with (sg, c0) = (-1, p + t) for "brighter", (+1, t - p) for "darker".
+// Output: one bit per pixel.  Raster order is restored by k_compact.
+// =============================================================================================
+constexpr int kF2SW = kF2W + 32;   // staged bytes per row: x0-16 .. x0+143 (ten 16-byte chunks)
+constexpr int kF2SR = kF2H + 6;    // staged rows: y0-3 .. y0+50
+
+PTAM_DEV bool ring10(const uint8_t* c, int sg, int c0) {
+  unsigned m = 0;
+  const int dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+  const int dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
 #pragma unroll
-  for (int k = 1; k < kLevels; k++) if ((int)blockIdx.x >= d.g.lev[k].tile_base) l = k;
+  for (int j = 0; j < 16; j++) {
+    const int v = c[dy[j] * kF2SW + dx[j]];
+    m = __funnelshift_l((unsigned)(v * sg + c0), m, 1);  // shifts in the sign bit
+  }
+  return run10(m);
+}
+
+PTAM_DEV unsigned hsum2(unsigned a) { return (a & 0x00ff00ffu) + ((a >> 8) & 0x00ff00ffu); }  // [b0+b1, b2+b3] in 16-bit lanes
+PTAM_DEV unsigned lds32(const uint8_t* p) { return *reinterpret_cast<const unsigned*>(p); }
+
+template <bool kPyr, int kVarA = 1, int kEmit = 0, int kMinB = 6>
+__global__ void __launch_bounds__(256, kMinB) k_fast2(TrackerDev d) {
+  __shared__ __align__(16) uint8_t tile[kF2SR * kF2SW];
+  __shared__ unsigned word_list[8][6 * 32];       // per warp: words that passed A: row - 6w | lane << 8 | pass bits (7,15,23,31)
+  __shared__ uint16_t cand_list[kF2W * kF2H];     // pixels that passed B: row << 7 | x | polarity << 13
+  __shared__ unsigned out_mask[kF2H][4];
+  __shared__ int cand_count;
+  int l = 0, tx, ty, s;
+  if (kPyr) { tx = blockIdx.x; ty = blockIdx.y; s = blockIdx.z + d.s_off; }
+  else {
+    s = blockIdx.y + d.s_off;
+    l = 1;
+#pragma unroll
+    for (int k = 2; k < kLevels; k++) if ((int)blockIdx.x >= d.g.lev[k].tile_base) l = k;
+    const int t = blockIdx.x - d.g.lev[l].tile_base;
+    ty = t / d.g.lev[l].tiles_x; tx = t - ty * d.g.lev[l].tiles_x;
+  }
   const LevelDesc& L = d.g.lev[l];
-  const int t = blockIdx.x - L.tile_base;
-  const int tx = t % L.tiles_x, ty = t / L.tiles_x;
-  const int x0 = tx * kFastTW, y0 = ty * kFastTH;
+  const int x0 = tx * kF2W, y0 = ty * kF2H;
   int pitch;
   const uint8_t* im = level_image(d, s, l, pitch);
   const bool al16 = ((pitch & 15) == 0) && ((reinterpret_cast<uintptr_t>(im) & 15) == 0);
-  if (threadIdx.x < kFastTH * 4) (&out_mask[0][0])[threadIdx.x] = 0u;
+  if (threadIdx.x < kF2H * 4) (&out_mask[0][0])[threadIdx.x] = 0u;
   if (threadIdx.x == 0) cand_count = 0;
-  // ---- stage rows y0-3 .. y0+34, bytes x0-16 .. x0+143 (zero outside the image): thread -> one of the
-  // ten 16-byte column chunks and rows r0, r0 + 25, so the column tests are done once per thread
-  if (threadIdx.x < 25 * (kFastSW / 16)) {
-    const int r0 = threadIdx.x / (kFastSW / 16), c = threadIdx.x - r0 * (kFastSW / 16);
+  // ---- stage rows y0-3 .. y0+50, bytes x0-16 .. x0+143 (zero outside the image): thread -> one of the
+  // ten 16-byte column chunks and rows r0, r0 + 25, r0 + 50, so the column tests are done once per thread
+  if (threadIdx.x < 25 * (kF2SW / 16)) {
+    const int r0 = threadIdx.x / (kF2SW / 16), c = threadIdx.x - r0 * (kF2SW / 16);
     const int x = x0 - 16 + 16 * c;
     const int xmode = (x + 15 < 0 || x >= L.w) ? 0 : ((al16 && x >= 0 && x + 15 < L.w) ? 1 : 2);
 #pragma unroll
-    for (int rr = 0; rr < 2; rr++) {
+    for (int rr = 0; rr < 3; rr++) {
       const int r = r0 + 25 * rr;
-      if (r >= kFastSR) break;
+      if (r >= kF2SR) break;
       const int y = y0 - 3 + r;
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
       if (xmode && y >= 0 && y < L.h) {
@@ -269,89 +326,196 @@ __global__ void __launch_bounds__(256) k_fast(TrackerDev d) {
           v = make_uint4(w4[0], w4[1], w4[2], w4[3]);
         }
       }
-      *reinterpret_cast<uint4*>(&tile[r * kFastSW + 16 * c]) = v;
+      *reinterpret_cast<uint4*>(&tile[r * kF2SW + 16 * c]) = v;
     }
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int thr = d.g.thresholds[l];
-  // ---- phase 1: compass pre-test, 4 pixels x 4 rows per thread
+  // ---- levels 1..3 of this tile: thread -> one 8x8 level-0 block -> 4x4, 2x2, 1 pixel(s)
+  if (kPyr && threadIdx.x < (kF2W / 8) * (kF2H / 8)) {
+    const int bx = threadIdx.x & 15, by = threadIdx.x >> 4;
+    const LevelDesc &L1 = d.g.lev[1], &L2 = d.g.lev[2], &L3 = d.g.lev[3];
+    uint8_t* base = d.pyr + (size_t)s * d.g.pyr_bytes;
+    const int x1 = (x0 >> 1) + 4 * bx, y1 = (y0 >> 1) + 4 * by;
+    unsigned l1a[4], l1b[4];  // level-1 pixels (0,1) and (2,3) of row j in 16-bit lanes
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint2 a = *reinterpret_cast<const uint2*>(&tile[(3 + 8 * by + 2 * j) * kF2SW + 16 + 8 * bx]);
+      const uint2 b = *reinterpret_cast<const uint2*>(&tile[(4 + 8 * by + 2 * j) * kF2SW + 16 + 8 * bx]);
+      l1a[j] = ((hsum2(a.x) + hsum2(b.x)) >> 2) & 0x00ff00ffu;
+      l1b[j] = ((hsum2(a.y) + hsum2(b.y)) >> 2) & 0x00ff00ffu;
+      const unsigned w4 = __byte_perm(l1a[j], l1b[j], 0x6420);
+      if (y1 + j < L1.h) {
+        uint8_t* o = base + L1.img_off + (size_t)(y1 + j) * L1.pitch + x1;
+        if (x1 + 3 < L1.w) *reinterpret_cast<unsigned*>(o) = w4;
+        else
+          for (int k = 0; k < 3; k++) if (x1 + k < L1.w) o[k] = (uint8_t)(w4 >> (8 * k));
+      }
+    }
+    const int x2 = (x0 >> 2) + 2 * bx, y2 = (y0 >> 2) + 2 * by;
+    unsigned v2[2][2];
+#pragma unroll
+    for (int m = 0; m < 2; m++) {
+      const unsigned ua = l1a[2 * m] + l1a[2 * m + 1], ub = l1b[2 * m] + l1b[2 * m + 1];
+      v2[m][0] = ((ua + (ua >> 16)) & 0xffffu) >> 2;
+      v2[m][1] = ((ub + (ub >> 16)) & 0xffffu) >> 2;
+      if (y2 + m < L2.h) {
+        uint8_t* o = base + L2.img_off + (size_t)(y2 + m) * L2.pitch + x2;
+        if (x2 + 1 < L2.w) *reinterpret_cast<uint16_t*>(o) = (uint16_t)(v2[m][0] | (v2[m][1] << 8));
+        else if (x2 < L2.w) o[0] = (uint8_t)v2[m][0];
+      }
+    }
+    const int x3 = (x0 >> 3) + bx, y3 = (y0 >> 3) + by;
+    if (x3 < L3.w && y3 < L3.h)
+      base[L3.img_off + (size_t)y3 * L3.pitch + x3] = (uint8_t)((v2[0][0] + v2[0][1] + v2[1][0] + v2[1][1]) >> 2);
+  }
+  const int thr = min(max(d.g.thresholds[l], 0), 255);
   const unsigned K = 0x80008000u - (unsigned)(thr + 1) * 0x00010001u;
-  unsigned vmask = 0;
+  // ---- stage A: compass test, 4 pixels x 6 rows per thread
+  unsigned vm = 0;  // bit 8k+7: pixel k of this thread can be a corner (3-pixel border of the image)
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     const int xx = x0 + 4 * lane + k;
-    if (xx >= 3 && xx < L.w - 3) vmask |= 1u << k;
+    if (xx >= 3 && xx < L.w - 3) vm |= 0x80u << (8 * k);
   }
-  unsigned cand16 = 0;
+  const uint8_t* tcol = &tile[(6 * warp) * kF2SW + 16 + 4 * lane];
+  int n_words = 0;  // entries in this warp's list (warp-uniform)
+  const unsigned lt = (1u << lane) - 1u;
+  const unsigned ebase = (unsigned)lane << 8;
+  if (kVarA == 1) {
+    // byte lanes, four pixels per register, sign-agnostic: |x - p| > t for (below|above) & (right|left).
+    // |x - p| by VABSDIFF4; d > t per byte without carries between bytes: for t < 128 bit 7 of
+    // ((d & 0x7f) + (0x7f - t)) | d, for t >= 128 bit 7 of ((d & 0x7f) + (0x7f - (t & 0x7f))) & d.
+    unsigned cwr[12];
 #pragma unroll
-  for (int rr = 0; rr < 4; rr++) {
-    const int ry = 4 * warp + rr;  // row inside the tile; staged row ry+3 is the centre row
-    const int y = y0 + ry;
-    if (y >= 3 && y < L.h - 3) {  // warp-uniform
-      const unsigned* crow = reinterpret_cast<const unsigned*>(&tile[(ry + 3) * kFastSW + 12 + 4 * lane]);
-      const unsigned w0 = crow[0], cw = crow[1], w2 = crow[2];
-      const unsigned up = *reinterpret_cast<const unsigned*>(&tile[ry * kFastSW + 16 + 4 * lane]);
-      const unsigned dn = *reinterpret_cast<const unsigned*>(&tile[(ry + 6) * kFastSW + 16 + 4 * lane]);
-      const unsigned lft = __byte_perm(w0, cw, 0x4321);  // pixels x-3 .. x
-      const unsigned rgt = __byte_perm(cw, w2, 0x6543);  // pixels x+3 .. x+6
+    for (int r = 0; r < 12; r++) cwr[r] = lds32(tcol + r * kF2SW);
+    const unsigned m7 = 0x7f7f7f7fu, c = (unsigned)(0x7f - (thr & 0x7f)) * 0x01010101u;
+    const int i_lo = max(0, 3 - (y0 + 6 * warp)), i_hi = min(6, L.h - 3 - (y0 + 6 * warp));  // rows that can hold corners
+#define PTAM_STAGE_A(COMBINE)                                                                                   \
+    _Pragma("unroll") for (int i = 0; i < 6; i++) {                                                             \
+      const unsigned w0 = lds32(tcol + (i + 3) * kF2SW - 4), w2 = lds32(tcol + (i + 3) * kF2SW + 4);            \
+      const unsigned P = cwr[i + 3];                                                                            \
+      const unsigned dS = __vabsdiffu4(cwr[i + 6], P), dN = __vabsdiffu4(cwr[i], P);                            \
+      const unsigned dE = __vabsdiffu4(__byte_perm(P, w2, 0x6543), P), dW = __vabsdiffu4(__byte_perm(w0, P, 0x4321), P); \
+      const unsigned sS = (dS & m7) + c, sN = (dN & m7) + c, sE = (dE & m7) + c, sW = (dW & m7) + c;            \
+      unsigned z = (COMBINE) & vm;                                                                              \
+      if (i < i_lo || i >= i_hi) z = 0;                    /* warp-uniform */                                   \
+      const unsigned votes = __ballot_sync(kFull, z != 0);                                                      \
+      if (z) word_list[warp][n_words + __popc(votes & lt)] = z | ebase | i;                                     \
+      n_words += __popc(votes);                                                                                 \
+    }
+    if (thr < 128) { PTAM_STAGE_A((sS | dS | sN | dN) & (sE | dE | sW | dW)) }
+    else { PTAM_STAGE_A(((sS & dS) | (sN & dN)) & ((sE & dE) | (sW & dW))) }
+#undef PTAM_STAGE_A
+  } else {
+    unsigned lo[12], hi[12];  // aligned words of staged rows 6w .. 6w+11, pixels (0,1) and (2,3) in 16-bit lanes
+#pragma unroll
+    for (int r = 0; r < 12; r++) {
+      const unsigned cw = lds32(tcol + r * kF2SW);
+      lo[r] = __byte_perm(cw, 0u, 0x4140); hi[r] = __byte_perm(cw, 0u, 0x4342);
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      const int y = y0 + 6 * warp + i;
+      const unsigned w0 = lds32(tcol + (i + 3) * kF2SW - 4), w2 = lds32(tcol + (i + 3) * kF2SW + 4);
+      const unsigned Plo = lo[i + 3], Phi = hi[i + 3];
+      const unsigned lft_lo = __byte_perm(w0, 0u, 0x4241), lft_hi = __byte_perm(w0, Plo, 0x5453);   // pixels x-3 .. x
+      const unsigned rgt_lo = __byte_perm(Phi, w2, 0x1412), rgt_hi = __byte_perm(w2, 0u, 0x4241);   // pixels x+3 .. x+6
+      const unsigned Bl = K - Plo, Bh = K - Phi, Dl = Plo + K, Dh = Phi + K;
+      const unsigned r_lo = (((lo[i + 6] + Bl) | (lo[i] + Bl)) & ((rgt_lo + Bl) | (lft_lo + Bl))) |
+                            (((Dl - lo[i + 6]) | (Dl - lo[i])) & ((Dl - rgt_lo) | (Dl - lft_lo)));
+      const unsigned r_hi = (((hi[i + 6] + Bh) | (hi[i] + Bh)) & ((rgt_hi + Bh) | (lft_hi + Bh))) |
+                            (((Dh - hi[i + 6]) | (Dh - hi[i])) & ((Dh - rgt_hi) | (Dh - lft_hi)));
+      unsigned z = __byte_perm(r_lo, r_hi, 0x7531) & vm;   // bits 15 / 31 of the lanes -> bit 7 of bytes 0..3
+      if (y < 3 || y >= L.h - 3) z = 0;                    // warp-uniform
+      const unsigned votes = __ballot_sync(kFull, z != 0);
+      if (z) word_list[warp][n_words + __popc(votes & lt)] = z | ebase | i;
+      n_words += __popc(votes);
+    }
+  }
+  __syncwarp();
+  // ---- stage B: antipodal-pair test of the listed words (same warp), survivors to the CTA-wide pixel list
+  for (int wb = 0; wb < n_words; wb += 32) {
+    const int wi = wb + lane;
+    unsigned zb = 0, zd = 0, e0 = 0;
+    if (wi < n_words) {
+      const unsigned e = word_list[warp][wi];
+      const int ry = 6 * warp + (int)(e & 7u), wl = (e >> 8) & 31;
+      e0 = (unsigned)((ry << 7) + 4 * wl);
+      const uint8_t* tc = &tile[(ry + 3) * kF2SW + 16 + 4 * wl];
+      const unsigned cw = lds32(tc), w0 = lds32(tc - 4), w2 = lds32(tc + 4);
+      const unsigned cS = lds32(tc + 3 * kF2SW), cN = lds32(tc - 3 * kF2SW);
+      const unsigned a0 = lds32(tc + 2 * kF2SW - 4), a1 = lds32(tc + 2 * kF2SW), a2 = lds32(tc + 2 * kF2SW + 4);   // row y+2
+      const unsigned b0 = lds32(tc - 2 * kF2SW - 4), b1 = lds32(tc - 2 * kF2SW), b2 = lds32(tc - 2 * kF2SW + 4);   // row y-2
       const unsigned Plo = __byte_perm(cw, 0u, 0x4140), Phi = __byte_perm(cw, 0u, 0x4342);
-      const unsigned Blo = K - Plo, Bhi = K - Phi, Dlo = Plo + K, Dhi = Phi + K;
-      unsigned b_lo[4], b_hi[4], d_lo[4], d_hi[4];
-      const unsigned ring4[4] = {dn, rgt, up, lft};
+      const unsigned Bl = K - Plo, Bh = K - Phi, Dl = Plo + K, Dh = Phi + K;
+      // ring pixels of the four pixels, (0,1) and (2,3) in 16-bit lanes
+      const unsigned S_lo = __byte_perm(cS, 0u, 0x4140), S_hi = __byte_perm(cS, 0u, 0x4342);
+      const unsigned N_lo = __byte_perm(cN, 0u, 0x4140), N_hi = __byte_perm(cN, 0u, 0x4342);
+      const unsigned W_lo = __byte_perm(w0, 0u, 0x4241), W_hi = __byte_perm(w0, Plo, 0x5453);
+      const unsigned E_lo = __byte_perm(Phi, w2, 0x1412), E_hi = __byte_perm(w2, 0u, 0x4241);
+      const unsigned SW_lo = __byte_perm(a0, 0u, 0x4342), SW_hi = __byte_perm(a1, 0u, 0x4140);   // (x-2, y+2)
+      const unsigned SE_lo = __byte_perm(a1, 0u, 0x4342), SE_hi = __byte_perm(a2, 0u, 0x4140);   // (x+2, y+2)
+      const unsigned NW_lo = __byte_perm(b0, 0u, 0x4342), NW_hi = __byte_perm(b1, 0u, 0x4140);   // (x-2, y-2)
+      const unsigned NE_lo = __byte_perm(b1, 0u, 0x4342), NE_hi = __byte_perm(b2, 0u, 0x4140);   // (x+2, y-2)
+#define PTAM_AB(op, C, S_, N_, E_, W_, SE_, NW_, NE_, SW_)                                             \
+      ((((op(C, S_)) | (op(C, N_))) & ((op(C, E_)) | (op(C, W_)))) &                                  \
+       (((op(C, S_)) & (op(C, N_))) | ((op(C, E_)) & (op(C, W_))) | ((op(C, SE_)) & (op(C, NW_))) | ((op(C, NE_)) & (op(C, SW_)))))
+#define PTAM_BR(C, X) ((X) + (C))
+#define PTAM_DK(C, X) ((C) - (X))
+      const unsigned rb_lo = PTAM_AB(PTAM_BR, Bl, S_lo, N_lo, E_lo, W_lo, SE_lo, NW_lo, NE_lo, SW_lo);
+      const unsigned rb_hi = PTAM_AB(PTAM_BR, Bh, S_hi, N_hi, E_hi, W_hi, SE_hi, NW_hi, NE_hi, SW_hi);
+      const unsigned rd_lo = PTAM_AB(PTAM_DK, Dl, S_lo, N_lo, E_lo, W_lo, SE_lo, NW_lo, NE_lo, SW_lo);
+      const unsigned rd_hi = PTAM_AB(PTAM_DK, Dh, S_hi, N_hi, E_hi, W_hi, SE_hi, NW_hi, NE_hi, SW_hi);
+#undef PTAM_AB
+#undef PTAM_BR
+#undef PTAM_DK
+      zb = __byte_perm(rb_lo, rb_hi, 0x7531) & e & 0x80808080u;
+      zd = __byte_perm(rd_lo, rd_hi, 0x7531) & e & 0x80808080u;
+    }
+    const unsigned both = zb | zd;
+    if (kEmit == 1) {
+      // survivors of the warp's 32 words to the pixel list: one ballot per pixel slot, one atomic per round
+      const unsigned v0 = __ballot_sync(kFull, both & 0x80u), v1 = __ballot_sync(kFull, both & 0x8000u);
+      const unsigned v2 = __ballot_sync(kFull, both & 0x800000u), v3 = __ballot_sync(kFull, both & 0x80000000u);
+      const int n0 = __popc(v0), n1 = __popc(v1), n2 = __popc(v2), n3 = __popc(v3);
+      int o = 0;
+      if (lane == 0 && n0 + n1 + n2 + n3) o = atomicAdd(&cand_count, n0 + n1 + n2 + n3);
+      o = __shfl_sync(kFull, o, 0);
 #pragma unroll
-      for (int q = 0; q < 4; q++) {
-        const unsigned Xlo = __byte_perm(ring4[q], 0u, 0x4140), Xhi = __byte_perm(ring4[q], 0u, 0x4342);
-        b_lo[q] = Xlo + Blo; b_hi[q] = Xhi + Bhi;
-        d_lo[q] = Dlo - Xlo; d_hi[q] = Dhi - Xhi;
+      for (int k = 0; k < 4; k++) {
+        const unsigned vk = k == 0 ? v0 : k == 1 ? v1 : k == 2 ? v2 : v3;
+        const int b = 8 * k + 7;
+        if ((both >> b) & 1u)
+          cand_list[o + __popc(vk & lt)] = (uint16_t)((e0 + k) | (((zb >> b) & 1u) << 13) | (((zd >> b) & 1u) << 14));
+        o += k == 0 ? n0 : k == 1 ? n1 : k == 2 ? n2 : n3;
       }
-      const unsigned r_lo = ((b_lo[0] | b_lo[2]) & (b_lo[1] | b_lo[3])) | ((d_lo[0] | d_lo[2]) & (d_lo[1] | d_lo[3]));
-      const unsigned r_hi = ((b_hi[0] | b_hi[2]) & (b_hi[1] | b_hi[3])) | ((d_hi[0] | d_hi[2]) & (d_hi[1] | d_hi[3]));
-      const unsigned r = ((r_lo >> 15) & 1u) | ((r_lo >> 30) & 2u) | ((r_hi >> 13) & 4u) | ((r_hi >> 28) & 8u);
-      cand16 |= (r & vmask) << (4 * rr);
+    } else if (both) {
+      unsigned m = both;
+      int o = atomicAdd(&cand_count, __popc(m));
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        cand_list[o++] = (uint16_t)((e0 + (b >> 3)) | (((zb >> b) & 1u) << 13) | (((zd >> b) & 1u) << 14));
+      }
     }
-  }
-  // ---- phase 2: CTA-wide candidate list (order is irrelevant: the output is a bit mask)
-  {
-    const int nc = __popc(cand16);
-    int inc = nc;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int n = __shfl_up_sync(kFull, inc, o);
-      if (lane >= o) inc += n;
-    }
-    int base = 0;
-    if (lane == 31 && inc > 0) base = atomicAdd(&cand_count, inc);
-    base = __shfl_sync(kFull, base, 31);
-    int o = base + inc - nc;
-    // 16 predicated stores instead of a data-dependent loop: the loop ran for the busiest lane of the warp
-    const unsigned e0 = (unsigned)(((4 * warp) << 7) | (4 * lane));
-#pragma unroll
-    for (int b = 0; b < 16; b++)
-      if ((cand16 >> b) & 1u) cand_list[o++] = (uint16_t)(e0 + ((b >> 2) << 7) + (b & 3));
   }
   __syncthreads();
-  // ---- phase 3: full ring test, one candidate per thread
+  // ---- stage C: ring test, one candidate per thread
   const int n_cand = cand_count;
   for (int ci = threadIdx.x; ci < n_cand; ci += 256) {
-    const int e = cand_list[ci];
-    const int ry = e >> 7, px = e & 127;
-    const uint8_t* c = &tile[(ry + 3) * kFastSW + 16 + px];
+    const unsigned e = cand_list[ci];
+    const int pos = e & 0x1fff, pol = e >> 13;
+    const int ry = pos >> 7, px = pos & 127;
+    const uint8_t* c = &tile[(ry + 3) * kF2SW + 16 + px];
     const int p = *c;
-    const int hi = p + thr, lo = p - thr;
-    unsigned mb = 0, md = 0;
-    const int dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
-    const int dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
-#pragma unroll
-    for (int j = 0; j < 16; j++) {
-      const int v = c[dy[j] * kFastSW + dx[j]];
-      mb = __funnelshift_l((unsigned)(hi - v), mb, 1);  // shifts in the sign of (p+t) - v: v > p+t
-      md = __funnelshift_l((unsigned)(v - lo), md, 1);  // sign of v - (p-t): v < p-t
-    }
-    if (run10(mb) || run10(md)) atomicOr(&out_mask[ry][px >> 5], 1u << (px & 31));
+    const int sg = (pol & 1) ? -1 : 1, c0 = (pol & 1) ? p + thr : thr - p;
+    bool corner = ring10(c, sg, c0);
+    if (pol == 3 && !corner) corner = ring10(c, 1, thr - p);  // rare: both polarities passed B
+    if (corner) atomicOr(&out_mask[ry][px >> 5], 1u << (px & 31));
   }
   __syncthreads();
-  if (threadIdx.x < kFastTH * 4) {
+  if (threadIdx.x < kF2H * 4) {
     const int ry = threadIdx.x >> 2, wq = threadIdx.x & 3;
     const int y = y0 + ry, word = (x0 >> 5) + wq;
     if (y < L.h && word < L.nwords) d.mask[(size_t)s * d.g.mask_stride + L.mask_off + (size_t)y * L.nwords + word] = out_mask[ry][wq];
@@ -366,7 +530,7 @@ __global__ void __launch_bounds__(256) k_fast(TrackerDev d) {
 // =============================================================================================
 __global__ void __launch_bounds__(1024) k_compact(TrackerDev d) {
   __shared__ int wsum[32];
-  const int l = blockIdx.x, s = blockIdx.y;
+  const int l = blockIdx.x, s = blockIdx.y + d.s_off;
   const LevelDesc& L = d.g.lev[l];
   const uint32_t* mask = d.mask + (size_t)s * d.g.mask_stride + L.mask_off;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -638,7 +802,7 @@ __global__ void __launch_bounds__(256) k_sbi(TrackerDev d) {
   const SbiDev& sb = d.sbi;
   const int n = sb.n;
   const SbiScratch m = sbi_scratch(sbi_raw, n, red, fin, usum, &c2c_s, &mean_off_s);
-  const int s = blockIdx.x, tid = threadIdx.x;
+  const int s = blockIdx.x + d.s_off, tid = threadIdx.x;
   StreamCtl& ctl = d.ctl[s];
   int pitch;
   const uint8_t* l3 = level_image(d, s, 3, pitch);
@@ -699,7 +863,7 @@ __global__ void __launch_bounds__(256) k_reloc(TrackerDev d) {
   __shared__ int best_s;
   const SbiDev& sb = d.sbi;
   const int n = sb.n;
-  const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int s = blockIdx.x + d.s_off, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   StreamCtl& ctl = d.ctl[s];
   if (ctl.st.lost_frames < 3) {  // uniform: nothing below writes lost_frames
     if (tid == 0) { ctl.frame_mode = 0; ctl.reloc_kf = -1; ctl.reloc_score = 0.0; }
@@ -890,7 +1054,7 @@ __global__ void __launch_bounds__(1024) k_pvs_select(TrackerDev d) {
   __shared__ int running[kLevels];
   __shared__ int seg_src[6], seg_off[6], seg_n[6], seg_dst[6];
   __shared__ int nseg;
-  const int s = blockIdx.x;
+  const int s = blockIdx.x + d.s_off;
   StreamCtl& ctl = d.ctl[s];
   // a frame whose relocalisation failed is not tracked at all (frame_mode is written by k_reloc, before this kernel)
   const int fmode = (d.mode == 0 && d.reloc_on) ? ctl.frame_mode : 0;
@@ -1068,7 +1232,7 @@ PTAM_DEV double level_n_pos(double p, int l) { return (p + 0.5) / (double)(1 << 
 // point (re-projection with the current pose, Tracker.h:89-94; inverse warp matrix and the template
 // cache test, PatchFinder.cc:100-110), so that the warp-per-point k_search does not repeat it 32 times.
 __global__ void __launch_bounds__(128) k_search_prep(TrackerDev d, int stage) {
-  const int s = blockIdx.y;
+  const int s = blockIdx.y + d.s_off;
   StreamCtl& ctl = d.ctl[s];
   int begin, end;
   if (stage == 0) { begin = 0; end = ctl.n_coarse; }
@@ -1133,7 +1297,7 @@ __global__ void __launch_bounds__(128) k_search_prep(TrackerDev d, int stage) {
 __global__ void __launch_bounds__(128, 12) k_search(TrackerDev d, int stage) {
   __shared__ __align__(8) uint8_t stmpl[4][64];
   __shared__ int2 squeue[4][64];
-  const int s = blockIdx.y;
+  const int s = blockIdx.y + d.s_off;
   StreamCtl& ctl = d.ctl[s];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int item = blockIdx.x * 4 + warp;
@@ -1395,16 +1559,23 @@ __global__ void __launch_bounds__(128, 12) k_search(TrackerDev d, int stage) {
 // coarse points were found; stage 1: the ten fine iterations (Tracker.cc:614-643), measurement
 // export statistics, UpdateMotionModel, AssessTrackingQuality.
 // =============================================================================================
-constexpr int kPoseThreads = 256;  // two CTAs (streams) resident per SM
+#ifndef PTAM_POSE_THREADS
+#define PTAM_POSE_THREADS 256
+#endif
+constexpr int kPoseThreads = PTAM_POSE_THREADS;  // two CTAs (streams) resident per SM
 
 // exact k-th smallest (0-based) of n non-negative doubles: MSB-first radix select on the IEEE bit
 // patterns (order-isomorphic to the values), 8 bits per pass; the 256-bin histogram is scanned by
-// warp 0 (8 bins per lane + shuffle scan), so a pass costs three barriers and no serial loop.
+// warp 0 (8 bins per lane + shuffle scan), so a pass costs two barriers and no serial loop.
+// Squared errors of one frame share their top bits, so the histogram updates are aggregated per warp
+// (match.any on the digit: one shared-memory atomic per distinct digit and warp instead of one per
+// element on the same bin), and the passes stop as soon as the bin of the k-th element holds ONE element:
+// a last sweep fetches that element (usually after 3-4 of the 8 passes; ties run all 8).
 // keys are read through `at(i)`.  All threads of the block must call it.
 template <class At>
 PTAM_DEV double block_select_kth(At at, int n, int kth, int* hist /*2 x 256*/, unsigned long long* sh_prefix, int* sh_k) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) { *sh_prefix = 0ull; *sh_k = kth; }
+  if (threadIdx.x == 0) { *sh_prefix = 0ull; sh_k[0] = kth; sh_k[1] = 0; }
   for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
   __syncthreads();
   for (int pass = 0; pass < 8; pass++) {
@@ -1412,9 +1583,15 @@ PTAM_DEV double block_select_kth(At at, int n, int kth, int* hist /*2 x 256*/, u
     int* h = hist + 256 * (pass & 1);
     int* hnext = hist + 256 * ((pass + 1) & 1);
     const unsigned long long prefix = *sh_prefix;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const unsigned long long key = (unsigned long long)__double_as_longlong(at(i));
-      if (pass == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&h[(key >> shift) & 255], 1);
+    for (int base = 0; base < n; base += blockDim.x) {
+      const int i = base + threadIdx.x;
+      unsigned digit = 256u + lane;  // not a bin: lanes without an element match nobody
+      if (i < n) {
+        const unsigned long long key = (unsigned long long)__double_as_longlong(at(i));
+        if (pass == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8))) digit = (unsigned)(key >> shift) & 255u;
+      }
+      const unsigned peers = __match_any_sync(kFull, digit);
+      if (digit < 256u && lane == __ffs(peers) - 1) atomicAdd(&h[digit], __popc(peers));
     }
     __syncthreads();
     if (warp == 0) {
@@ -1427,19 +1604,31 @@ PTAM_DEV double block_select_kth(At at, int n, int kth, int* hist /*2 x 256*/, u
         const int v = __shfl_up_sync(kFull, inc, o);
         if (lane >= o) inc += v;
       }
-      const int kk = *sh_k;
-      __syncwarp();  // every lane has read *sh_k before the one owner rewrites it
+      const int kk = sh_k[0];
+      __syncwarp();  // every lane has read sh_k[0] before the one owner rewrites it
       const int excl = inc - tot;
       if (kk >= excl && kk < inc) {  // exactly one lane
         int r = kk - excl, q = 0;
         while (q < 7 && r >= c[q]) { r -= c[q]; q++; }
-        *sh_k = r;
+        sh_k[0] = r;
+        sh_k[1] = c[q] == 1 ? shift : 0;  // the k-th element is alone in its bin: bits below `shift` come from the element itself
         *sh_prefix = prefix | ((unsigned long long)(8 * lane + q) << shift);
       }
     } else {
       for (int i = threadIdx.x - 32; i < 256; i += blockDim.x - 32) hnext[i] = 0;  // for the next pass
     }
     __syncthreads();
+    const int uniq_shift = sh_k[1];
+    if (uniq_shift) {  // block-uniform
+      const unsigned long long pfx = *sh_prefix;
+      __syncthreads();  // everybody has read the prefix before its owner overwrites it
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned long long key = (unsigned long long)__double_as_longlong(at(i));
+        if ((key >> uniq_shift) == (pfx >> uniq_shift)) *sh_prefix = key;  // one element
+      }
+      __syncthreads();
+      break;
+    }
   }
   return __longlong_as_double((long long)*sh_prefix);
 }
@@ -1500,6 +1689,13 @@ PTAM_DEV void calc_jacobian(double X, double Y, double Z, double dv0, double dv1
   }
 }
 
+#ifdef PTAM_POSE_CLOCKS
+__device__ long long g_pose_clk[32];
+#define PCLK(k) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long t_ = clock64(); g_pose_clk[k] += t_ - pclk_last; pclk_last = t_; } } while (0)
+#else
+#define PCLK(k) do { } while (0)
+#endif
+
 struct PoseShared {
   double s_e2[kPoseSmemPts];
   double pose[12];
@@ -1507,7 +1703,7 @@ struct PoseShared {
   double mu_s[6];
   int hist[512];
   unsigned long long sh_prefix;
-  int sh_k;
+  int sh_k[2];
 };
 
 // The ten iterations of Tracker.cc:552-568 (stage 0) / 614-643 (stage 1) over the found set.
@@ -1520,6 +1716,9 @@ PTAM_DEV void pose_iterations(const TrackerDev& d, const Store& st, PoseShared& 
   double last_mu[6] = {0, 0, 0, 0, 0, 0};
   const bool e2_smem = nf <= kPoseSmemPts;
   const bool unit = d.mode == 2;  // ptam_pose_update: ONE CalcPoseUpdate at the projections of the patch search, not applied
+#ifdef PTAM_POSE_CLOCKS
+  long long pclk_last = clock64();
+#endif
   for (int it = 0; it < (unit ? 1 : 10); it++) {
     const bool nonlin = stage == 0 || it == 0 || it == 4 || it == 9;
     const double override_sigma = unit ? d.unit_override_sigma : (it > 5 ? (stage == 0 ? 1.0 : 16.0) : 0.0);
@@ -1559,16 +1758,18 @@ PTAM_DEV void pose_iterations(const TrackerDev& d, const Store& st, PoseShared& 
       if (e2_smem) sh.s_e2[i] = ee; else e2_global[fidx[i]] = ee;
     }
     __syncthreads();
+    PCLK(nonlin ? 0 : 1);
     double mu[6] = {0, 0, 0, 0, 0, 0};
     if (nf > 0) {
       double sigma2;
       if (override_sigma > 0) sigma2 = override_sigma;
       else {
         double med;
-        if (e2_smem) med = block_select_kth([&](int i) { return sh.s_e2[i]; }, nf, nf / 2, sh.hist, &sh.sh_prefix, &sh.sh_k);
-        else med = block_select_kth([&](int i) { return e2_global[fidx[i]]; }, nf, nf / 2, sh.hist, &sh.sh_prefix, &sh.sh_k);
+        if (e2_smem) med = block_select_kth([&](int i) { return sh.s_e2[i]; }, nf, nf / 2, sh.hist, &sh.sh_prefix, sh.sh_k);
+        else med = block_select_kth([&](int i) { return e2_global[fidx[i]]; }, nf, nf / 2, sh.hist, &sh.sh_prefix, sh.sh_k);
         sigma2 = mest_sigma_from_median(med, nf, est);
       }
+      PCLK(2);
       // weighted normal equations (TooN WLS<6>::add_mJ twice per point)
       double acc[32];
 #pragma unroll
@@ -1592,49 +1793,53 @@ PTAM_DEV void pose_iterations(const TrackerDev& d, const Store& st, PoseShared& 
 #pragma unroll
           for (int a = 0; a < 6; a++) {
 #pragma unroll
-            for (int b = 0; b <= a; b++) acc[c++] += Jw[a] * Jr[b];
+            for (int b = 0; b <= a; b++) { acc[c] = fma(Jw[a], Jr[b], acc[c]); c++; }
           }
 #pragma unroll
-          for (int a = 0; a < 6; a++) acc[21 + a] += er * Jw[a];
+          for (int a = 0; a < 6; a++) acc[21 + a] = fma(er, Jw[a], acc[21 + a]);
         }
       }
+      PCLK(3);
       warp_transpose_sum32(acc);
       if (lane < 27) sh.red[warp][lane] = acc[0];
       __syncthreads();
-      if (threadIdx.x < 27) {
-        double t = 0;
-        for (int wq = 0; wq < kPoseThreads / 32; wq++) t += sh.red[wq][threadIdx.x];
-        sh.red[0][threadIdx.x] = t;
+      PCLK(4);
+      if (warp == 0) {  // cross-warp sums, the 6x6 solve and the pose update without further block barriers
+        if (lane < 27) {
+          double t = 0;
+          for (int wq = 0; wq < kPoseThreads / 32; wq++) t += sh.red[wq][lane];
+          sh.red[0][lane] = t;
+        }
+        __syncwarp();
+        if (lane == 0) {
+          double tot[27];
+          for (int q = 0; q < 27; q++) tot[q] = sh.red[0][q];
+          double C[36], b[6], x[6];
+          int c = 0;
+          for (int a = 0; a < 6; a++)
+            for (int bb = 0; bb <= a; bb++) { C[6 * a + bb] = tot[c]; C[6 * bb + a] = tot[c]; c++; }
+          for (int a = 0; a < 6; a++) { C[7 * a] += 100.0; b[a] = tot[21 + a]; }  // add_prior(100)
+          ldlt_factor<6>(C);
+          ldlt_backsub<6>(C, b, x);
+          for (int a = 0; a < 6; a++) sh.mu_s[a] = x[a];
+          if (!unit) {  // mse3CamFromWorld = SE3<>::exp(v6Update) * mse3CamFromWorld
+            double ex[12], np[12];
+            se3_exp(x, ex);
+            se3_mul(ex, pose, np);
+            for (int i = 0; i < 12; i++) pose[i] = np[i];
+          }
+        }
       }
       __syncthreads();
-      if (threadIdx.x == 0) {
-        double tot[27];
-        for (int q = 0; q < 27; q++) tot[q] = sh.red[0][q];
-        double C[36], b[6], x[6];
-        int c = 0;
-        for (int a = 0; a < 6; a++)
-          for (int bb = 0; bb <= a; bb++) { C[6 * a + bb] = tot[c]; C[6 * bb + a] = tot[c]; c++; }
-        for (int a = 0; a < 6; a++) { C[7 * a] += 100.0; b[a] = tot[21 + a]; }  // add_prior(100)
-        ldlt_factor<6>(C);
-        ldlt_backsub<6>(C, b, x);
-        for (int a = 0; a < 6; a++) sh.mu_s[a] = x[a];
-      }
-      __syncthreads();
+      PCLK(5);
       for (int a = 0; a < 6; a++) mu[a] = sh.mu_s[a];
     }
     if (unit) {
       if (threadIdx.x < 6) d.unit_mu[6 * blockIdx.x + threadIdx.x] = mu[threadIdx.x];
       break;
     }
-    // mse3CamFromWorld = SE3<>::exp(v6Update) * mse3CamFromWorld
-    if (threadIdx.x == 0) {
-      double ex[12], np[12];
-      se3_exp(mu, ex);
-      se3_mul(ex, pose, np);
-      for (int i = 0; i < 12; i++) pose[i] = np[i];
-    }
     for (int a = 0; a < 6; a++) last_mu[a] = mu[a];
-    __syncthreads();
+    PCLK(6);
   }
 }
 
@@ -1645,7 +1850,7 @@ __global__ void __launch_bounds__(kPoseThreads, 2) k_pose(TrackerDev d, int stag
   __shared__ int sh_cnt[kPoseThreads / 32];
   __shared__ int nfound_s;
   double* pose = sh.pose;
-  const int s = blockIdx.x;
+  const int s = blockIdx.x + d.s_off;
   StreamCtl& ctl = d.ctl[s];
   const int cap = d.p.cap;
   const size_t gb = (size_t)s * cap;
@@ -1655,7 +1860,11 @@ __global__ void __launch_bounds__(kPoseThreads, 2) k_pose(TrackerDev d, int stag
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n_set = stage == 0 ? ctl.n_coarse : ctl.n_coarse + ctl.n_l3 + ctl.n_fine;
   const int fmode = (d.mode == 0 && d.reloc_on) ? ctl.frame_mode : 0;
+  if (stage == 0 && threadIdx.x < kLevels) ctl.res_n_corners[threadIdx.x] = ctl.n_corners[threadIdx.x];
   if (fmode == 2) return;  // relocalisation failed: the reference does nothing else this frame
+#ifdef PTAM_POSE_CLOCKS
+  long long pclk_last = clock64();
+#endif
 
   // compact the found entries (order preserved) once: the found set does not change during GN
   if (threadIdx.x == 0) nfound_s = 0;
@@ -1681,7 +1890,7 @@ __global__ void __launch_bounds__(kPoseThreads, 2) k_pose(TrackerDev d, int stag
     run = ctl.try_coarse && nf >= d.prm.coarse_min;
     if (threadIdx.x == 0) ctl.did_coarse = run ? 1 : 0;
   }
-  const bool in_smem = nf <= kPoseSmemPts;
+  const bool in_smem = d.pose_ws_smem && nf <= kPoseSmemPts;
   const PoseStoreSmem ss{reinterpret_cast<double*>(pose_dyn)};
   const PoseStoreGlobal sg{&d.p, gb, fidx};
   if (run) {
@@ -1693,7 +1902,9 @@ __global__ void __launch_bounds__(kPoseThreads, 2) k_pose(TrackerDev d, int stag
         for (int q = 0; q < 4; q++) ss.dv(i, q) = sg.dv(i, q);
       }
       __syncthreads();
+      PCLK(8);
       pose_iterations(d, ss, sh, stage, nf, gb, fidx, e2);
+      PCLK(9);
       for (int i = threadIdx.x; i < nf; i += blockDim.x) {  // what later stages and the getters read
         sg.image(i, 0) = ss.image(i, 0); sg.image(i, 1) = ss.image(i, 1);
         for (int q = 0; q < 3; q++) sg.v3(i, q) = ss.v3(i, q);
@@ -1764,6 +1975,7 @@ __global__ void __launch_bounds__(kPoseThreads, 2) k_pose(TrackerDev d, int stag
     if (st.tracking_quality == 0) st.lost_frames++; else st.lost_frames = 0;
     for (int i = 0; i < 12; i++) st.se3_cam_from_world[i] = pose[i];
   }
+  PCLK(10);
 }
 
 // =============================================================================================

@@ -263,6 +263,45 @@ def test_pipelined_submit_collect_matches_blocking(product, seq640, map640):
 
 
 @pytest.mark.gpu
+def test_pipelined_submit_device_matches_blocking(product, seq640, map640):
+    """ptam_tracker_submit_frames_device / _collect (device-resident frames, image work of batch i+1 beside the
+    fine pose iterations of batch i) gives bit-identical results to the blocking call, n_corners included."""
+    import torch
+    frames, poses = seq640
+    kfs, m = map640
+    S = 5
+    trackers = []
+    for _ in range(2):
+        t = Tracker(product, 640, 480, S)
+        for k in kfs:
+            t.add_keyframe(k)
+        for s in range(S):
+            t.set_map(s, m)
+            t.set_state(s, pose12=synth.perturb_pose(poses[2 + s], np.random.default_rng(s)), velocity=np.zeros(6), msd=0.0)
+        trackers.append(t)
+    a, b = trackers
+    n = 8
+    batches = [[np.ascontiguousarray(frames[2 + s + i]) for s in range(S)] for i in range(n)]
+    ref = [a.track_frames(bt) for bt in batches]
+    dev = [torch.from_numpy(np.stack(bt)).cuda() for bt in batches]
+    torch.cuda.synchronize()
+    out = []
+    b.submit_device(dev[0].data_ptr(), 640 * 480, 640)
+    for i in range(1, n):
+        b.submit_device(dev[i].data_ptr(), 640 * 480, 640)
+        out.append(b.collect())
+    out.append(b.collect())
+    # a blocking call after the pipelined ones sees their state
+    last = [np.ascontiguousarray(frames[2 + s + n]) for s in range(S)]
+    ra, rb = a.track_frames(last), b.track_frames(last)
+    for r_step, o_step in zip(ref + [ra], out + [rb]):
+        for r, o in zip(r_step, o_step):
+            assert list(r.se3_cam_from_world) == list(o.se3_cam_from_world)
+            assert list(r.meas_found) == list(o.meas_found) and list(r.n_corners) == list(o.n_corners)
+            assert list(r.meas_attempted) == list(o.meas_attempted)
+
+
+@pytest.mark.gpu
 def test_track_frames_1280x720(oracle, product):
     """BASELINE config C5 geometry: full TrackFrame parity at 1280x720 (map built at that size)."""
     from oracle.binding import detect_with
