@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <numeric>
 #include <type_traits>
 #include <vector>
@@ -101,9 +102,13 @@ struct ptam_bundle {
   BundleDev d{};
   Buf<double> cam_se3, cam_se3_new, U, epsA, pt_pos, pt_pos_new, V, epsB, Vinv, Ve, m_found, m_sin, m_v3cam, m_derivs,
       m_eps, m_e2, m_W, m_B, e2c, S, vE, upd, scal, Wp, err_cam, partials;
-  Buf<int> cam_fixed, cam_row, pt_off, pt_meas, pt_meas_ins, pt_cam, cam_off, cam_meas_ins, cam_meas_pt, blk_off, blk_cnt, pr_mj, pr_mk, nz_blocks, pair_info, free_cam,
+  Buf<int> cam_fixed, cam_row, pt_off, pt_meas, pt_meas_ins, pt_cam, cam_off, cam_meas_ins, cam_meas_pt, blk_off, blk_cnt, nz_blocks, pair_info, free_cam,
       m_cam, m_pt, m_state, counters, outliers;
   Buf<unsigned> tickets;
+  Buf<int> csr_cur;
+  Buf<long long> csr_pairs;
+  int* pair_buf = nullptr;      // pr_mj | pr_mk: sized by the device's own count of co-visible triples
+  size_t pair_cap = 0;
   double* h_scal = nullptr;  // pinned
   int* h_cnt = nullptr;      // pinned
   // multi-GPU shard: points [p_lo, p_hi) and their measurements live here; cameras are replicated
@@ -137,10 +142,28 @@ struct ptam_bundle {
 
   void set_error(const std::string& e) { err = e; }
 
+  // Device memory comes from the device's stream-ordered pool, kept warm (release threshold = everything): MapMaker
+  // builds a new Bundle per adjustment (Bundle.cc:35), and a cold cudaMalloc of the arena costs 0.6 - 16 ms.
+  cudaError_t dev_alloc(void** p, size_t bytes) {
+    static std::once_flag once[64];
+    std::call_once(once[device & 63], [&] {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      cudaGetLastError();
+    });
+    return cudaMallocAsync(p, bytes, stream);
+  }
+  void dev_free(void* p) { if (p) cudaFreeAsync(p, stream); }
+
   ~ptam_bundle() {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
-    if (arena) cudaFree(arena);
+    dev_free(arena);
+    dev_free(pair_buf);
+    if (stream) cudaStreamSynchronize(stream);
     for (auto e : prof_ev) if (e) cudaEventDestroy(e);
     if (comm && own_comm) nccl_api().CommDestroy(comm);
     if (h_scal) cudaFreeHost(h_scal);
@@ -185,6 +208,14 @@ struct ptam_bundle {
   // handle keeps only the measurements of the points it owns.
   int begin() {
     cudaSetDevice(device);
+    static const bool dbg_t = std::getenv("PTAM_B200_DEBUG_TIMES") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+      if (!dbg_t) return;
+      const auto now = std::chrono::steady_clock::now();
+      std::fprintf(stderr, "[ptam dbg] bundle begin: %-28s %.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+      t_last = now;
+    };
     if (world > 1 && !comm) { set_error("sharded handle without a communicator: call ptam_bundle_init_shard first"); return PTAM_ERR_NCCL; }
     const int C = n_cams(), P = n_pts(), MG = n_meas();
     const int n = 6 * n_free;
@@ -216,13 +247,26 @@ struct ptam_bundle {
     const std::vector<double>& v_sin = whole ? h_sin : l_sin;
     const int M = (int)l_gid.size();
     n_meas_local = M;
+    // The usual list (MapMaker.cc:871-882 walks the keyframes, and a keyframe's measurements by map point) is sorted
+    // by (camera, point): one sequential pass finds out, and counts the measurements per camera on the way.  Then
+    // list order = ascending camera id inside a point and ascending point id inside a camera, the camera CSR is the
+    // identity, and the point CSR is built on the device (k_ba_csr_*).  Any other list takes the host path below.
+    std::vector<int> coff(C + 1, 0);
+    bool fast = M > 0;
+    for (int m = 0; m < M; m++) {
+      coff[v_mcam[m] + 1]++;
+      if (m && !(v_mcam[m] > v_mcam[m - 1] || (v_mcam[m] == v_mcam[m - 1] && v_mpt[m] > v_mpt[m - 1]))) fast = false;
+    }
+    for (int j = 0; j < C; j++) coff[j + 1] += coff[j];
+    if (std::getenv("PTAM_B200_HOST_CSR")) fast = false;
+    std::vector<int> off, idx, idx_ins, ptcam, cidx, cidx_pt;
+    long long n_pairs_max = 0;
+    if (!fast) {
     // CSR by point.  The bucket pass is stable, so `idx` first holds every point's measurements in LIST order
-    // (the order V_i / epsB_i are summed in); the off-diagonal scripts want them by ascending camera id.  With
-    // the usual camera-major insertion (MapMaker.cc:871-882) the two orders agree and nothing is sorted.
-    std::vector<int> off(P + 1, 0), idx(M), idx_ins;
+    // (the order V_i / epsB_i are summed in); the off-diagonal scripts want them by ascending camera id.
+    off.assign(P + 1, 0); idx.resize(M);
     for (int m = 0; m < M; m++) off[v_mpt[m] + 1]++;
     for (int i = 0; i < P; i++) off[i + 1] += off[i];
-    long long n_pairs_max = 0;
     {
       std::vector<int> cur(off.begin(), off.end() - 1);
       for (int m = 0; m < M; m++) idx[cur[v_mpt[m]]++] = m;
@@ -239,13 +283,11 @@ struct ptam_bundle {
         n_pairs_max += k * (k - 1) / 2;
       }
     }
-    std::vector<int> ptcam(M);
+    ptcam.resize(M);
     for (int o = 0; o < M; o++) ptcam[o] = v_mcam[idx[o]];
     // CSR by camera: list order (U_j / epsA_j) and ascending point id (S_jj, the pair list); again one array
     // when the list is point-ordered inside every camera
-    std::vector<int> coff(C + 1, 0), cidx(M), cidx_pt;
-    for (int m = 0; m < M; m++) coff[v_mcam[m] + 1]++;
-    for (int j = 0; j < C; j++) coff[j + 1] += coff[j];
+    cidx.resize(M);
     {
       std::vector<int> cur(coff.begin(), coff.end() - 1);
       for (int m = 0; m < M; m++) cidx[cur[v_mcam[m]]++] = m;
@@ -258,6 +300,8 @@ struct ptam_bundle {
         }
       }
     }
+    }
+    lap("measurement lists (host)");
     std::vector<int> freecam;
     for (int j = 0; j < C; j++) if (!h_cam_fixed[j]) freecam.push_back(j);
     const long long n_blocks = (long long)n_free * (n_free - 1) / 2;
@@ -278,7 +322,7 @@ struct ptam_bundle {
       AL(pt_pos, 3 * (size_t)P); AL(pt_pos_new, 3 * (size_t)P); AL(V, 6 * (size_t)P); AL(epsB, 3 * (size_t)P);
       AL(Vinv, 9 * (size_t)P); AL(Ve, 3 * (size_t)P); AL(pt_off, P + 1); AL(pt_meas, M);
       AL(pt_meas_ins, idx_ins.empty() ? 0 : M); AL(pt_cam, M); AL(cam_off, C + 1); AL(cam_meas_ins, M);
-      AL(cam_meas_pt, cidx_pt.empty() ? 0 : M); AL(blk_off, n_blocks + 1); AL(blk_cnt, n_blocks); AL(nz_blocks, n_blocks); AL(pair_info, 4); AL(free_cam, n_free); AL(pr_mj, n_pairs_max); AL(pr_mk, n_pairs_max);
+      AL(cam_meas_pt, cidx_pt.empty() ? 0 : M); AL(blk_off, n_blocks + 1); AL(blk_cnt, n_blocks); AL(nz_blocks, n_blocks); AL(pair_info, 4); AL(free_cam, n_free); AL(csr_cur, P + 1); AL(csr_pairs, 1);
       AL(m_B, 6 * (size_t)M); AL(err_cam, C); AL(partials, grid_max); AL(tickets, 4);
       AL(m_cam, M); AL(m_pt, M); AL(m_found, 2 * (size_t)M); AL(m_sin, M); AL(m_state, M); AL(m_v3cam, 3 * (size_t)M);
       AL(m_derivs, 4 * (size_t)M); AL(m_eps, 2 * (size_t)M); AL(m_e2, M); AL(m_W, 18 * (size_t)M); AL(e2c, M);
@@ -290,22 +334,26 @@ struct ptam_bundle {
       if (!pass) {
         need = off;
         if (need > arena_cap) {
-          if (arena) { cudaStreamSynchronize(stream); cudaFree(arena); arena = nullptr; arena_cap = 0; }
-          PTAM_CUDA_TRY(this, cudaMalloc(&arena, need));
+          if (arena) { dev_free(arena); arena = nullptr; arena_cap = 0; }
+          PTAM_CUDA_TRY(this, dev_alloc(reinterpret_cast<void**>(&arena), need));
           arena_cap = need;
         }
       }
     }
+    lap("arena (cudaMalloc if grown)");
     PTAM_CUDA_TRY(this, cudaMemsetAsync(arena, 0, need, stream));
     PTAM_CUDA_TRY(this, cudaStreamSynchronize(stream));
+    lap("memset + sync");
 #define UP(buf, vec) if (!vec.empty()) PTAM_CUDA_TRY(this, cudaMemcpy(buf.p, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice))
     UP(cam_se3, h_cam_se3); UP(cam_fixed, h_cam_fixed); UP(cam_row, h_cam_row); UP(pt_pos, h_pts);
     UP(pt_off, off); UP(pt_meas, idx); UP(m_cam, v_mcam); UP(m_pt, v_mpt); UP(m_found, v_found); UP(m_sin, v_sin);
-    UP(m_gid, l_gid); UP(pt_meas_ins, idx_ins); UP(pt_cam, ptcam); UP(cam_off, coff); UP(cam_meas_ins, cidx); UP(cam_meas_pt, cidx_pt); UP(free_cam, freecam);
+    if (!whole) UP(m_gid, l_gid);
+    UP(pt_meas_ins, idx_ins); UP(pt_cam, ptcam); UP(cam_off, coff); UP(cam_meas_ins, cidx); UP(cam_meas_pt, cidx_pt); UP(free_cam, freecam);
 #undef UP
     // pageable H2D copies return once staged; the handle's streams are non-blocking (no implicit ordering with
     // the legacy stream the copies ran on), so finish them before the first kernel is queued
     PTAM_CUDA_TRY(this, cudaStreamSynchronize(cudaStreamLegacy));
+    lap("uploads");
     d.cam = cam; d.n_cams = C; d.n_pts = P; d.n_meas = M; d.n = n; d.est = prm.mestimator;
     d.p_lo = p_lo; d.p_hi = p_hi; d.add_cam_update = rank == 0 ? 1 : 0;
     d.cam_se3 = cam_se3.p; d.cam_se3_new = cam_se3_new.p; d.cam_fixed = cam_fixed.p; d.cam_row = cam_row.p;
@@ -317,17 +365,47 @@ struct ptam_bundle {
     d.hist16 = hist16.p; d.sel_state = sel_state.p; d.m_erase_step = m_erase_step.p;
     d.m_B = m_B.p; d.pt_meas_ins = idx_ins.empty() ? pt_meas.p : pt_meas_ins.p; d.pt_cam = pt_cam.p;
     d.cam_off = cam_off.p; d.cam_meas_ins = cam_meas_ins.p; d.cam_meas_pt = cidx_pt.empty() ? cam_meas_ins.p : cam_meas_pt.p;
-    d.n_blocks = n_blocks; d.blk_off = blk_off.p; d.pr_mj = pr_mj.p; d.pr_mk = pr_mk.p;
+    d.n_blocks = n_blocks; d.blk_off = blk_off.p;
     d.err_cam = err_cam.p; d.partials = partials.p; d.tickets = tickets.p;
     d.nz_blocks = nz_blocks.p; d.pair_info = pair_info.p; d.free_cam = free_cam.p;
+    if (M > 0) {
+      const int gm = (M + 255) / 256;
+      if (whole) { k_ba_iota<<<gm, 256, 0, stream>>>(m_gid.p, M); launches++; }
+      if (fast) {  // the point CSR on the device; the camera CSR is the identity
+        k_ba_csr_count<<<gm, 256, 0, stream>>>(m_pt.p, M, csr_cur.p);
+        k_ba_csr_scan<<<1, 1024, 0, stream>>>(csr_cur.p, pt_off.p, P, csr_pairs.p);
+        k_ba_csr_fill<<<gm, 256, 0, stream>>>(m_pt.p, M, pt_off.p, csr_cur.p, pt_meas.p);
+        k_ba_csr_sort<<<(P + 255) / 256, 256, 0, stream>>>(pt_off.p, P, pt_meas.p, m_cam.p, pt_cam.p);
+        k_ba_iota<<<gm, 256, 0, stream>>>(cam_meas_ins.p, M);
+        launches += 5;
+      }
+    }
     // the pair-major list of the off-diagonal blocks (GenerateOffDiagScripts, Bundle.cc:572-599), on the device
+    d.pr_mj = d.pr_mk = nullptr;
     if (n_blocks > 0 && p_hi > p_lo) {
       k_ba_pair_count<<<(p_hi - p_lo + 255) / 256, 256, 0, stream>>>(d, blk_cnt.p);
       k_ba_pair_scan<<<1, 1024, 0, stream>>>(blk_cnt.p, blk_off.p, nz_blocks.p, pair_info.p, n_blocks);
-      k_ba_pair_fill<<<148 * 8, 128, 0, stream>>>(d, pr_mj.p, pr_mk.p);
-      launches += 3;
+      launches += 2;
+      // the list itself is sized by the count just made (one scalar read-back)
+      long long bound = n_pairs_max;
+      int info[4] = {0, 0, 0, 0};
+      if (fast) PTAM_CUDA_TRY(this, cudaMemcpyAsync(&bound, csr_pairs.p, sizeof(long long), cudaMemcpyDeviceToHost, stream));
+      PTAM_CUDA_TRY(this, cudaMemcpyAsync(info, pair_info.p, sizeof(info), cudaMemcpyDeviceToHost, stream));
+      PTAM_CUDA_TRY(this, cudaStreamSynchronize(stream));
+      if (bound > 0x7fffffffLL) { set_error("graph too dense for the pair list (more than 2^31 co-visible triples)"); return PTAM_ERR_INVALID; }
+      const size_t triples = (size_t)std::max(info[2], 1);
+      if (2 * triples > pair_cap) {
+        dev_free(pair_buf);
+        pair_buf = nullptr; pair_cap = 0;
+        PTAM_CUDA_TRY(this, dev_alloc(reinterpret_cast<void**>(&pair_buf), 2 * triples * sizeof(int)));
+        pair_cap = 2 * triples;
+      }
+      d.pr_mj = pair_buf; d.pr_mk = pair_buf + triples;
+      k_ba_pair_fill<<<148 * 8, 128, 0, stream>>>(d, pair_buf, pair_buf + triples);
+      launches++;
       PTAM_CUDA_TRY(this, cudaGetLastError());
     }
+    lap("device lists");
     lambda = 0.0001; lambda_factor = 2.0;
     converged = false; hit_max = false; abort_seen = false;
     counter = 0; accepted = 0; lm_steps = 0; n_outliers = 0;

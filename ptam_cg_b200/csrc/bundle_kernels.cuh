@@ -643,6 +643,126 @@ __global__ void __launch_bounds__(256) k_ba_mirror(double* S, int n) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// CSR by point on the device (ptam_bundle_begin, the usual case: the measurement list is sorted by (camera,
+// point), MapMaker.cc:871-882).  Then list order, ascending camera id and ascending list index coincide inside
+// every point, so the slots of a point can be claimed in any order (integer atomics) and put in order afterwards:
+// the result does not depend on the schedule.
+//   k_ba_csr_count  thread per measurement: measurements per point
+//   k_ba_csr_scan   one CTA: pt_off = exclusive scan; the counters are zeroed again for the fill; also
+//                   sum k (k - 1) / 2, an upper bound of the co-visible triples (overflow check on the host)
+//   k_ba_csr_fill   thread per measurement: claims a slot of its point
+//   k_ba_csr_sort   thread per point: its slots by ascending list index (insertion sort, heap sort for long
+//                   lists), then the camera of every slot
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ba_csr_count(const int* m_pt, int M, int* cnt) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < M) atomicAdd(&cnt[m_pt[m]], 1);
+}
+
+__global__ void __launch_bounds__(1024) k_ba_csr_scan(int* cnt, int* off, int P, long long* pairs_bound) {
+  __shared__ int ws[32];
+  __shared__ long long wp[32];
+  __shared__ int carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kPer = 8;
+  if (threadIdx.x == 0) carry = 0;
+  long long pairs = 0;
+  __syncthreads();
+  for (int base = 0; base < P; base += blockDim.x * kPer) {
+    const int i0 = base + threadIdx.x * kPer;
+    int c[kPer], s0 = 0;
+#pragma unroll
+    for (int q = 0; q < kPer; q++) {
+      c[q] = i0 + q < P ? cnt[i0 + q] : 0;
+      if (i0 + q < P) cnt[i0 + q] = 0;
+      s0 += c[q];
+      pairs += (long long)c[q] * (c[q] - 1) / 2;
+    }
+    int inc = s0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(kFull, inc, o);
+      if (lane >= o) inc += u;
+    }
+    if (lane == 31) ws[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      int w = ws[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(kFull, w, o);
+        if (lane >= o) w += u;
+      }
+      ws[lane] = w;
+    }
+    __syncthreads();
+    int run = carry + (warp ? ws[warp - 1] : 0) + inc - s0;
+#pragma unroll
+    for (int q = 0; q < kPer; q++) {
+      if (i0 + q < P) off[i0 + q] = run;
+      run += c[q];
+    }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = run;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) off[P] = carry;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) pairs += __shfl_xor_sync(kFull, pairs, o);
+  if (lane == 0) wp[warp] = pairs;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long t = 0;
+    for (int w = 0; w < 32; w++) t += wp[w];
+    *pairs_bound = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_ba_csr_fill(const int* m_pt, int M, const int* off, int* cur, int* pt_meas) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const int i = m_pt[m];
+  pt_meas[off[i] + atomicAdd(&cur[i], 1)] = m;
+}
+
+__global__ void __launch_bounds__(256) k_ba_csr_sort(const int* off, int P, int* pt_meas, const int* m_cam, int* pt_cam) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  int* a = pt_meas + off[i];
+  const int k = off[i + 1] - off[i];
+  if (k <= 32) {
+    for (int q = 1; q < k; q++) {
+      const int v = a[q];
+      int r = q - 1;
+      while (r >= 0 && a[r] > v) { a[r + 1] = a[r]; r--; }
+      a[r + 1] = v;
+    }
+  } else {  // heap sort
+    auto sift = [&](int root, int end) {
+      for (;;) {
+        int child = 2 * root + 1;
+        if (child >= end) break;
+        if (child + 1 < end && a[child] < a[child + 1]) child++;
+        if (a[root] >= a[child]) break;
+        const int t = a[root]; a[root] = a[child]; a[child] = t;
+        root = child;
+      }
+    };
+    for (int st = k / 2 - 1; st >= 0; st--) sift(st, k);
+    for (int end = k - 1; end > 0; end--) {
+      const int t = a[0]; a[0] = a[end]; a[end] = t;
+      sift(0, end);
+    }
+  }
+  for (int q = 0; q < k; q++) pt_cam[off[i] + q] = m_cam[a[q]];
+}
+
+__global__ void __launch_bounds__(256) k_ba_iota(int* a, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = i;
+}
+
+// ---------------------------------------------------------------------------------------------
 // The pair-major list behind k_ba_schur_off (GenerateOffDiagScripts regrouped by camera pair,
 // Bundle.cc:572-599), built on the device once per Compute, without a sort:
 //   k_ba_pair_count  thread per point: +1 (integer atomics: exact) for every pair of free cameras observing it
