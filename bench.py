@@ -586,7 +586,7 @@ def main():
                                  f"({r['reduced_system_n']}^2 / 2 f64) + vE over NCCL")
                 res_sh = r.pop("_result")
                 if rank == 0:  # the same graph on this GPU alone: the sharded run must reproduce it
-                    one = bench_ba(prod, local, "C4", reps=1, graph=g4)
+                    one = bench_ba(prod, local, "C4", reps=2, graph=g4)
                     res_1 = one.pop("_result")
                     r["parity_vs_single_gpu"] = {
                         "trials_equal": one["lambda_trials"] == r["lambda_trials"], "accepted_equal": one["accepted"] == r["accepted"],

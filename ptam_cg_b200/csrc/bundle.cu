@@ -32,6 +32,10 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool load() {
     if (tried) return lib != nullptr;
@@ -45,26 +49,31 @@ struct NcclApi {
     CommInitRank = reinterpret_cast<decltype(CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
     CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
     AllReduce = reinterpret_cast<decltype(AllReduce)>(dlsym(lib, "ncclAllReduce"));
+    AllGather = reinterpret_cast<decltype(AllGather)>(dlsym(lib, "ncclAllGather"));
+    Broadcast = reinterpret_cast<decltype(Broadcast)>(dlsym(lib, "ncclBroadcast"));
+    GroupStart = reinterpret_cast<decltype(GroupStart)>(dlsym(lib, "ncclGroupStart"));
+    GroupEnd = reinterpret_cast<decltype(GroupEnd)>(dlsym(lib, "ncclGroupEnd"));
     GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
-    if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce || !GetErrorString) { err = "NCCL library lacks required symbols"; lib = nullptr; return false; }
+    if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce || !AllGather || !Broadcast || !GroupStart || !GroupEnd || !GetErrorString) { err = "NCCL library lacks required symbols"; lib = nullptr; return false; }
     return true;
   }
 };
 NcclApi& nccl_api() { static NcclApi a; return a; }
 
 // Contiguous point ranges balanced by measurement count: shard r owns points [begin[r], begin[r+1]).
-void shard_plan(int n_points, int n_meas, const int32_t* meas_point, int world, int32_t* begin) {
-  std::vector<long long> cnt(n_points + 1, 0);
+void shard_plan(int n_points, int n_meas, const int32_t* meas_point, int world, int32_t* begin, int* per_shard = nullptr) {
+  std::vector<int> cnt(n_points + 1, 0);
   for (int m = 0; m < n_meas; m++) cnt[meas_point[m] + 1]++;
   for (int i = 0; i < n_points; i++) cnt[i + 1] += cnt[i];
   begin[0] = 0;
   for (int r = 1; r < world; r++) {
-    const long long target = (long long)n_meas * r / world;
+    const int target = (int)((long long)n_meas * r / world);
     int b = (int)(std::lower_bound(cnt.begin(), cnt.end(), target) - cnt.begin());
     b = std::min(std::max(b, (int)begin[r - 1]), n_points);
     begin[r] = b;
   }
   begin[world] = n_points;
+  if (per_shard) for (int r = 0; r < world; r++) per_shard[r] = cnt[begin[r + 1]] - cnt[begin[r]];
 }
 }  // namespace
 
@@ -106,6 +115,9 @@ struct ptam_bundle {
       m_cam, m_pt, m_state, counters, outliers;
   Buf<unsigned> tickets;
   Buf<int> csr_cur;
+  Buf<double> s_pack, sel_gather;  // sharded handles: packed lower triangle of S + vE; every shard's squared errors
+  int sel_slot = 0;                // measurements per slot of sel_gather (the largest shard's count)
+  std::vector<int32_t> plan;       // points [plan[r], plan[r + 1]) belong to shard r
   Buf<long long> csr_pairs;
   int* pair_buf = nullptr;      // pr_mj | pr_mk: sized by the device's own count of co-visible triples
   size_t pair_cap = 0;
@@ -117,7 +129,7 @@ struct ptam_bundle {
   bool own_comm = false;
   int p_lo = 0, p_hi = 0;
   std::vector<int> l_gid;            // local measurement -> insertion index
-  Buf<int> m_gid, m_erase_step, g_steps, hist16, erase_cnt;
+  Buf<int> m_gid, m_erase_step, g_steps, g_pairs, g_cnt, hist16, erase_cnt;
   Buf<unsigned long long> sel_state;
   bool shards_dirty = false, abort_seen = false;
   std::vector<int> h_outliers;       // merged (point, camera) pairs in the reference's erase order
@@ -221,10 +233,15 @@ struct ptam_bundle {
     const int n = 6 * n_free;
     if (MG == 0) { set_error("no measurements (the reference asserts on this, Tools.h:155)"); return PTAM_ERR_INVALID; }
     p_lo = 0; p_hi = P;
+    plan.assign(world + 1, 0);
+    plan[world] = P;
+    sel_slot = 0;
     if (world > 1) {
-      std::vector<int32_t> plan(world + 1);
-      shard_plan(P, MG, h_mpt.data(), world, plan.data());
+      std::vector<int> per_rank(world, 0);  // measurements per shard
+      shard_plan(P, MG, h_mpt.data(), world, plan.data(), per_rank.data());
       p_lo = plan[rank]; p_hi = plan[rank + 1];
+      sel_slot = *std::max_element(per_rank.begin(), per_rank.end());
+      n_meas_local = per_rank[rank];
     }
     // a single-GPU handle uses the insertion-order arrays as they are; a shard copies out its own
     l_gid.clear();
@@ -235,10 +252,15 @@ struct ptam_bundle {
       l_gid.resize(MG);
       std::iota(l_gid.begin(), l_gid.end(), 0);
     } else {
+      const int ML = n_meas_local;
+      l_gid.resize(ML); l_mcam.resize(ML); l_mpt.resize(ML); l_found.resize(2 * (size_t)ML); l_sin.resize(ML);
+      int o = 0;
       for (int m = 0; m < MG; m++) {
-        if (h_mpt[m] < p_lo || h_mpt[m] >= p_hi) continue;
-        l_gid.push_back(m); l_mcam.push_back(h_mcam[m]); l_mpt.push_back(h_mpt[m]);
-        l_found.push_back(h_found[2 * m]); l_found.push_back(h_found[2 * m + 1]); l_sin.push_back(h_sin[m]);
+        const int pt = h_mpt[m];
+        if (pt < p_lo || pt >= p_hi) continue;
+        l_gid[o] = m; l_mcam[o] = h_mcam[m]; l_mpt[o] = pt;
+        l_found[2 * (size_t)o] = h_found[2 * (size_t)m]; l_found[2 * (size_t)o + 1] = h_found[2 * (size_t)m + 1]; l_sin[o] = h_sin[m];
+        o++;
       }
     }
     const std::vector<int>& v_mcam = whole ? h_mcam : l_mcam;
@@ -329,7 +351,8 @@ struct ptam_bundle {
       AL(S, (size_t)n * n); AL(vE, n); AL(upd, n); AL(scal, 8); AL(counters, 4); AL(outliers, 2 * (size_t)M);
       AL(Wp, ldlt_workspace_doubles(n));
       AL(m_gid, M); AL(m_erase_step, M); AL(hist16, kSelBins); AL(erase_cnt, (M + 1023) / 1024 + 1); AL(sel_state, 2);
-      AL(g_steps, world > 1 ? MG : 0);
+      AL(g_steps, world > 1 ? MG : 0); AL(g_pairs, world > 1 ? 2 * (size_t)MG : 0); AL(g_cnt, 1);
+      AL(s_pack, world > 1 ? (size_t)n * (n + 1) / 2 + n : 0); AL(sel_gather, world > 1 ? (size_t)world * sel_slot : 0);
 #undef AL
       if (!pass) {
         need = off;
@@ -363,6 +386,7 @@ struct ptam_bundle {
     d.m_eps = m_eps.p; d.m_e2 = m_e2.p; d.m_W = m_W.p; d.e2_compact = e2c.p; d.S = S.p; d.vE = vE.p; d.upd = upd.p;
     d.scal = scal.p; d.counters = counters.p; d.outliers = outliers.p;
     d.hist16 = hist16.p; d.sel_state = sel_state.p; d.m_erase_step = m_erase_step.p;
+    d.sel_keys = world > 1 ? sel_gather.p : nullptr; d.sel_n = world * sel_slot;
     d.m_B = m_B.p; d.pt_meas_ins = idx_ins.empty() ? pt_meas.p : pt_meas_ins.p; d.pt_cam = pt_cam.p;
     d.cam_off = cam_off.p; d.cam_meas_ins = cam_meas_ins.p; d.cam_meas_pt = cidx_pt.empty() ? cam_meas_ins.p : cam_meas_pt.p;
     d.n_blocks = n_blocks; d.blk_off = blk_off.p;
@@ -415,6 +439,19 @@ struct ptam_bundle {
     return PTAM_OK;
   }
 
+  // sharded handles: sum of the shards' partial S and vE on every shard.  Only the lower triangle is exchanged (the
+  // solver reads nothing else), packed row by row with vE behind it: one all-reduce of n (n + 1) / 2 + n doubles.
+  int exchange_reduced() {
+    const int n = d.n;
+    k_ba_pack_lower<<<148 * 4, 256, 0, stream>>>(d.S, d.vE, n, s_pack.p);
+    int rc = all_reduce(s_pack.p, (size_t)n * (n + 1) / 2 + n, ncclDouble, ncclSum, "all-reduce of the packed S and vE");
+    if (rc) return rc;
+    k_ba_unpack_lower<<<148 * 4, 256, 0, stream>>>(s_pack.p, n, d.S, d.vE);
+    launches += 2;
+    PTAM_CUDA_TRY(this, cudaGetLastError());
+    return PTAM_OK;
+  }
+
   int solve_reduced() {  // Cholesky<>(mS).backsub(vE), Bundle.cc:457-458
     const int64_t l0 = ldlt.launches;
     const cudaError_t e = ldlt.solve(d.S, d.vE, d.upd, Wp.p, d.n);
@@ -451,11 +488,19 @@ struct ptam_bundle {
       }
       return PTAM_OK;
     }
+    // sharded: ONE exchange, every shard's squared errors to every shard (8 B per measurement), then the same
+    // six local passes on the gathered keys: the median of the same multiset, bit for bit, on every shard
+    const int n_keys = world > 1 ? world * sel_slot : M;
+    if (world > 1 && sel_slot > 0) {
+      k_ba_sel_keys<<<(sel_slot + 255) / 256, 256, 0, stream>>>(d, sel_gather.p + (size_t)rank * sel_slot, sel_slot);
+      launches++;
+      int rc = nccl_try(nccl_api().AllGather(sel_gather.p + (size_t)rank * sel_slot, sel_gather.p, (size_t)sel_slot, ncclDouble, comm, stream),
+                        "all-gather of the squared errors");
+      if (rc) return rc;
+    }
     for (int pass = 0; pass < kSelPasses; pass++) {
       PTAM_CUDA_TRY(this, cudaMemsetAsync(hist16.p, 0, sizeof(int) * kSelBins, stream));
-      if (M > 0) { k_ba_hist<<<std::min((M + 255) / 256, 148 * 8), 256, 0, stream>>>(d, pass); launches++; }
-      int rc = all_reduce(hist16.p, kSelBins, ncclInt32, ncclSum, "all-reduce of the select histogram");
-      if (rc) return rc;
+      if (n_keys > 0) { k_ba_hist<<<std::min((n_keys + 255) / 256, 148 * 8), 256, 0, stream>>>(d, pass); launches++; }
       k_ba_pick<<<1, 1024, 0, stream>>>(d, pass, min_s2);
       launches++;
     }
@@ -512,9 +557,8 @@ struct ptam_bundle {
       pend(4);
       s_mirrored = false;
       pbegin(5);
-      if (n > 0) {  // the cross-camera J^T J reduction: partial S, vE of every shard -> total on every shard
-        if ((rc = all_reduce(d.S, (size_t)n * n, ncclDouble, ncclSum, "all-reduce of S"))) return rc;
-        if ((rc = all_reduce(d.vE, n, ncclDouble, ncclSum, "all-reduce of vE"))) return rc;
+      if (n > 0 && world > 1) {  // the cross-camera J^T J reduction: partial S, vE of every shard -> total on every shard
+        if ((rc = exchange_reduced())) return rc;
       }
       pend(5);
       pbegin(6); if ((rc = solve_reduced())) return rc; pend(6);
@@ -568,21 +612,34 @@ struct ptam_bundle {
     cudaSetDevice(device);
     const int P = d.n_pts, MG = n_meas(), M = d.n_meas;
     int rc;
-    if (d.p_lo > 0) PTAM_CUDA_TRY(this, cudaMemsetAsync(pt_pos.p, 0, sizeof(double) * 3 * (size_t)d.p_lo, stream));
-    if (d.p_hi < P) PTAM_CUDA_TRY(this, cudaMemsetAsync(pt_pos.p + 3 * (size_t)d.p_hi, 0, sizeof(double) * 3 * (size_t)(P - d.p_hi), stream));
-    if (P > 0 && (rc = all_reduce(pt_pos.p, 3 * (size_t)P, ncclDouble, ncclSum, "all-gather of the points"))) return rc;
+    if (P > 0) {  // every shard's own points to every shard: one broadcast per (unequal) range, in one group
+      if ((rc = nccl_try(nccl_api().GroupStart(), "ncclGroupStart"))) return rc;
+      for (int r = 0; r < world; r++) {
+        const size_t lo = (size_t)plan[r], cnt = (size_t)(plan[r + 1] - plan[r]);
+        if (cnt == 0) continue;
+        if ((rc = nccl_try(nccl_api().Broadcast(pt_pos.p + 3 * lo, pt_pos.p + 3 * lo, 3 * cnt, ncclDouble, r, comm, stream), "all-gather of the points"))) return rc;
+      }
+      if ((rc = nccl_try(nccl_api().GroupEnd(), "ncclGroupEnd"))) return rc;
+    }
     h_outliers.clear();
     if (MG > 0) {
       PTAM_CUDA_TRY(this, cudaMemsetAsync(g_steps.p, 0, sizeof(int) * (size_t)MG, stream));
       if (M > 0) { k_ba_scatter_steps<<<(M + 255) / 256, 256, 0, stream>>>(m_erase_step.p, m_gid.p, g_steps.p, M); launches++; }
       if ((rc = all_reduce(g_steps.p, MG, ncclInt32, ncclMax, "all-reduce of the outlier marks"))) return rc;
-      std::vector<int> steps(MG);
-      PTAM_CUDA_TRY(this, cudaMemcpyAsync(steps.data(), g_steps.p, sizeof(int) * (size_t)MG, cudaMemcpyDeviceToHost, stream));
+      // the marked ones as (index, step) pairs: a few per cent of the list, sorted here by (step, list order)
+      PTAM_CUDA_TRY(this, cudaMemsetAsync(g_cnt.p, 0, sizeof(int), stream));
+      k_ba_marks_compact<<<(MG + 255) / 256, 256, 0, stream>>>(g_steps.p, MG, g_pairs.p, g_cnt.p);
+      launches++;
+      int n_marked = 0;
+      PTAM_CUDA_TRY(this, cudaMemcpyAsync(&n_marked, g_cnt.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
       PTAM_CUDA_TRY(this, cudaStreamSynchronize(stream));
-      std::vector<int> ids;
-      for (int m = 0; m < MG; m++) if (steps[m] > 0) ids.push_back(m);
-      std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) { return steps[a] < steps[b]; });
-      for (int m : ids) { h_outliers.push_back(h_mpt[m]); h_outliers.push_back(h_mcam[m]); }
+      std::vector<int> pairs(2 * (size_t)n_marked);
+      if (n_marked) PTAM_CUDA_TRY(this, cudaMemcpy(pairs.data(), g_pairs.p, sizeof(int) * pairs.size(), cudaMemcpyDeviceToHost));
+      std::vector<int> ord(n_marked);
+      std::iota(ord.begin(), ord.end(), 0);
+      std::sort(ord.begin(), ord.end(), [&](int a, int b) {
+        return pairs[2 * a + 1] != pairs[2 * b + 1] ? pairs[2 * a + 1] < pairs[2 * b + 1] : pairs[2 * a] < pairs[2 * b]; });
+      for (int q : ord) { const int m = pairs[2 * q]; h_outliers.push_back(h_mpt[m]); h_outliers.push_back(h_mcam[m]); }
     } else {
       PTAM_CUDA_TRY(this, cudaStreamSynchronize(stream));
     }
@@ -843,8 +900,7 @@ int ptam_bundle_get_reduced_system(ptam_bundle* b, double* S, double* vE, int ca
   const int PO = b->d.p_hi - b->d.p_lo;
   if (PO > 0) k_ba_vinv<<<(PO + 255) / 256, 256, 0, b->stream>>>(b->d);
   { const int rc = b->build_reduced(); if (rc) return rc; }
-  { int rc = b->all_reduce(b->d.S, (size_t)n * n, ncclDouble, ncclSum, "all-reduce of S"); if (rc) return rc;
-    rc = b->all_reduce(b->d.vE, n, ncclDouble, ncclSum, "all-reduce of vE"); if (rc) return rc; }
+  if (b->world > 1) { const int rc = b->exchange_reduced(); if (rc) return rc; }
   k_ba_mirror<<<std::min<size_t>(((size_t)n * n + 255) / 256, 148 * 8), 256, 0, b->stream>>>(b->d.S, n);
   b->launches += 2;
   PTAM_CUDA_TRY(b, cudaGetLastError());

@@ -76,6 +76,8 @@ struct BundleDev {
   double* scal;
   int* hist16;                   // [2048] digit histogram of the distributed radix select
   unsigned long long* sel_state; // [0] key prefix found so far, [1] rank still to find inside it
+  const double* sel_keys;        // sharded handles: the squared errors of ALL shards (all-gathered, ~0 = not a key), else null
+  int sel_n;                     // entries of sel_keys
   int* counters;  // 0 n_valid, 1 n_outliers_total, 2 n_bad_this_step
   int* outliers;  // [M][2] (point, camera) in erase order
   int* m_erase_step;  // [M] LM step (1-based) at which the measurement was erased, 0 = still in the graph
@@ -203,14 +205,19 @@ __global__ void __launch_bounds__(256) k_ba_hist(BundleDev d, int pass) {
   const int shift = sel_shift(pass), width = sel_width(pass);
   const unsigned long long prefix = d.sel_state[0];
   const int lane = threadIdx.x & 31;
-  for (int m0 = blockIdx.x * blockDim.x; m0 < d.n_meas; m0 += gridDim.x * blockDim.x) {
+  const int n_keys = d.sel_keys ? d.sel_n : d.n_meas;
+  for (int m0 = blockIdx.x * blockDim.x; m0 < n_keys; m0 += gridDim.x * blockDim.x) {
     const int m = m0 + threadIdx.x;
     bool take = false;
     unsigned digit = 0;
-    if (m < d.n_meas && d.m_state[m] == M_ALIVE) {
-      const unsigned long long key = (unsigned long long)__double_as_longlong(d.m_e2[m]);
-      take = pass == 0 || (key >> (shift + width)) == (prefix >> (shift + width));
-      digit = (unsigned)(key >> shift) & ((1u << width) - 1u);
+    if (m < n_keys) {
+      unsigned long long key = ~0ull;
+      if (d.sel_keys) key = (unsigned long long)__double_as_longlong(d.sel_keys[m]);
+      else if (d.m_state[m] == M_ALIVE) key = (unsigned long long)__double_as_longlong(d.m_e2[m]);
+      if (key != ~0ull) {
+        take = pass == 0 || (key >> (shift + width)) == (prefix >> (shift + width));
+        digit = (unsigned)(key >> shift) & ((1u << width) - 1u);
+      }
     }
     const unsigned active = __ballot_sync(kFull, take);
     if (take) {
@@ -221,6 +228,41 @@ __global__ void __launch_bounds__(256) k_ba_hist(BundleDev d, int pass) {
   __syncthreads();
   for (int i = threadIdx.x; i < kSelBins; i += blockDim.x)
     if (h[i]) atomicAdd(&d.hist16[i], h[i]);
+}
+
+// Sharded handles: this shard's squared errors into its slot of the all-gather buffer (erased / outlier
+// measurements and the padding of the slot as ~0, which is no key: a NaN pattern no squared error has).
+__global__ void __launch_bounds__(256) k_ba_sel_keys(BundleDev d, double* slot, int slot_n) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= slot_n) return;
+  long long key = ~0ll;
+  if (m < d.n_meas && d.m_state[m] == M_ALIVE) key = __double_as_longlong(d.m_e2[m]);
+  slot[m] = __longlong_as_double(key);
+}
+
+// The lower triangle of S row by row (row r: r + 1 values at r (r + 1) / 2) with vE behind it: what the shards
+// exchange per lambda trial (n (n + 1) / 2 + n doubles instead of n^2 + n), and back.
+__global__ void __launch_bounds__(256) k_ba_pack_lower(const double* S, const double* vE, int n, double* out) {
+  for (int r = blockIdx.x; r < n; r += gridDim.x) {
+    const double* src = S + (size_t)r * n;
+    double* dst = out + (size_t)r * (r + 1) / 2;
+    for (int c = threadIdx.x; c <= r; c += blockDim.x) dst[c] = src[c];
+  }
+  if (blockIdx.x == 0) {
+    double* dst = out + (size_t)n * (n + 1) / 2;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) dst[c] = vE[c];
+  }
+}
+__global__ void __launch_bounds__(256) k_ba_unpack_lower(const double* in, int n, double* S, double* vE) {
+  for (int r = blockIdx.x; r < n; r += gridDim.x) {
+    double* dst = S + (size_t)r * n;
+    const double* src = in + (size_t)r * (r + 1) / 2;
+    for (int c = threadIdx.x; c <= r; c += blockDim.x) dst[c] = src[c];
+  }
+  if (blockIdx.x == 0) {
+    const double* src = in + (size_t)n * (n + 1) / 2;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) vE[c] = src[c];
+  }
 }
 
 __global__ void __launch_bounds__(1024) k_ba_pick(BundleDev d, int pass, double min_sigma_sq) {
@@ -1056,6 +1098,22 @@ __global__ void __launch_bounds__(1024) k_ba_erase_write(BundleDev d, const int*
 __global__ void __launch_bounds__(256) k_ba_scatter_steps(const int* step, const int* gid, int* out, int n) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m < n && step[m] > 0) out[gid[m]] = step[m];
+}
+
+// ... and the marked measurements as (global index, step) pairs, in any order (the host sorts the few of them)
+__global__ void __launch_bounds__(256) k_ba_marks_compact(const int* steps, int n, int* pairs, int* count) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int st = m < n ? steps[m] : 0;
+  const unsigned bal = __ballot_sync(kFull, st > 0);
+  if (!bal) return;
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == 0) base = atomicAdd(count, __popc(bal));
+  base = __shfl_sync(kFull, base, 0);
+  if (st > 0) {
+    const int o = base + __popc(bal & ((1u << lane) - 1u));
+    pairs[2 * o] = m; pairs[2 * o + 1] = st;
+  }
 }
 
 }  // namespace ptam

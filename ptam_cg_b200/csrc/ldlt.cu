@@ -3,10 +3,23 @@
 #include "ldlt_kernels.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace ptam {
 
 size_t ldlt_workspace_doubles(int n) { return 2 * (size_t)n * kNB; }
+
+// Kernel launch, optionally with programmatic stream serialisation (see griddep_wait in ldlt_kernels.cuh)
+template <class... P, class... A>
+static cudaError_t launch_k(void (*kern)(P...), int grid, int block, size_t smem, cudaStream_t st, bool pdl, A... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<P>(args)...);
+}
 
 #define LDLT_TRY(expr)                          \
   do {                                          \
@@ -16,6 +29,7 @@ size_t ldlt_workspace_doubles(int n) { return 2 * (size_t)n * kNB; }
 
 cudaError_t LdltSolver::init(cudaStream_t main_stream) {
   stream = main_stream;
+  use_pdl = !(std::getenv("PTAM_B200_NO_PDL"));
   LDLT_TRY(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
   LDLT_TRY(cudaFuncSetAttribute(k_ldlt_update, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpdateSmem));
   LDLT_TRY(cudaFuncSetAttribute(k_ldlt_step, cudaFuncAttributeMaxDynamicSharedMemorySize, kPanelSmem));
@@ -61,11 +75,13 @@ cudaError_t LdltSolver::solve(double* S, double* y, double* x, double* Wp, int n
     const int n_ctas = std::max(1, (rem + kPanelRows - 1) / kPanelRows);
     // panel k reads tiles the tail of panel k-2 updated, and overwrites the Wp buffer that tail read
     if (k >= 2 && tail_of[k - 2]) LDLT_TRY(cudaStreamWaitEvent(stream, ev_tail[k - 2], 0));
+    // programmatic dependent launch along the single-stream part of the chain (no event wait in front of this step)
+    const bool pdl = use_pdl && k > 0 && !(k >= 2 && tail_of[k - 2]) && !tail_of[k - 1];
     if (deferred) {
       const int nt = (n - k0 + kUTM - 1) / kUTM;  // tail of panel k-1: its trailing matrix starts at k0
-      k_ldlt_step<<<n_ctas + nt * nt, kPanelThreads, kPanelSmem, stream>>>(S, wp, wprev, y, n, k0, n_ctas);
+      LDLT_TRY(launch_k(k_ldlt_step, n_ctas + nt * nt, kPanelThreads, kPanelSmem, stream, pdl, S, wp, wprev, y, n, k0, n_ctas));
     } else {
-      k_ldlt_panel<<<n_ctas, kPanelThreads, kPanelSmem, stream>>>(S, wp, wprev, y, n, k0);
+      LDLT_TRY(launch_k(k_ldlt_panel, n_ctas, kPanelThreads, kPanelSmem, stream, pdl, S, wp, (const double*)wprev, y, n, k0));
     }
     launches++;
     tail_of[k] = false;

@@ -19,6 +19,7 @@ struct LdltSolver {
   std::vector<char> tail_of;
   std::string err;
   int64_t launches = 0;
+  bool use_pdl = true;  // programmatic dependent launch between the steps of the factorisation
 
   // `main_stream` is the stream the rest of the LM step runs on.  Returns cudaSuccess or the failing call's code.
   cudaError_t init(cudaStream_t main_stream);

@@ -55,21 +55,44 @@ __device__ long long g_dbg[8];
 #endif
 constexpr int kLda = kNB + 2;  // even row pitch: (row, even column) pairs are 16-byte aligned
 
+// Programmatic dependent launch: the steps of the factorisation are launched with programmatic stream
+// serialisation, so the CTAs of step k + 1 are already resident (shared memory carved, mbarrier initialised) when
+// step k retires; nothing step k wrote is read before griddep_wait().
+PTAM_DEV void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+PTAM_DEV void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// mma.m8n8k4 (f64): one 8x8 tile of  C -= L U^T  over the eight columns of a sub-panel.  C, L in `a`, U in `u`.
+PTAM_DEV void tile_rank8(double (*a)[kLda], const double (*u)[8], int r0, int c0, int k0, int lane) {
+  double2* cp = reinterpret_cast<double2*>(&a[r0 + (lane >> 2)][c0 + 2 * (lane & 3)]);
+  double2 c = *cp;
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const double fa = -a[r0 + (lane >> 2)][k0 + 4 * h + (lane & 3)];
+    const double fb = u[c0 + (lane >> 2)][4 * h + (lane & 3)];
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c.x), "+d"(c.y) : "d"(fa), "d"(fb));
+  }
+  *cp = c;
+}
+
+// Warp-specialised, with look-ahead: warps 0..1 (one thread per row) factor sub-panel s while warps 2..7 still apply
+// sub-panel s - 1 to the columns further right (8x8 tiles on the f64 tensor pipe, the matrix stays in shared
+// memory).  The update warps first bring the NEXT sub-panel's eight columns up to date and release the row warps
+// (named barrier 1), then do the rest; the row warps hand a finished sub-panel over through named barrier 2.
+// `us` is double-buffered by sub-panel parity ([2][64][8]).
 PTAM_DEV void block_ldlt64(double (*a)[kLda], double (*us)[8], double* dinv, double* ysh, int nb) {
-  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-  double ar[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; i++)
-#pragma unroll
-    for (int j = 0; j < 4; j++) ar[i][j] = a[ty + 16 * i][tx + 16 * j];
-  double yr = tid < kNB ? ysh[tid] : 0.0;  // threads 0..63 own one row of the current sub-panel each
-  if (tid < kNB) dinv[tid] = 1.0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool row_role = tid < kNB;
+  double yr = row_role ? ysh[tid] : 0.0;  // threads 0..63 own one row of every sub-panel
+  if (row_role) dinv[tid] = 1.0;
   __syncthreads();
+  const int nsub = (min(nb, kNB) + 7) >> 3;  // the identity padding of a short last block needs no work
+  if (row_role) {
+    const int r = tid;
 #pragma unroll 1
-  for (int c0 = 0; c0 < kNB; c0 += 8) {
-    if (c0 >= nb) break;  // the identity padding of a short last block needs no work
-    if (tid < kNB) {
-      const int r = tid;
+    for (int s = 0; s < nsub; s++) {
+      const int c0 = 8 * s;
+      double (*u)[8] = us + (s & 1) * kNB;
+      if (s > 0) asm volatile("bar.sync 1, 256;" ::: "memory");  // the columns of this sub-panel carry sub-panel s - 1
       // the 8x8 diagonal block of the sub-panel and its right-hand side, redundantly in every row thread
       // (broadcast loads): pivots, reciprocals and the L D values then need no exchange at all
       double dg[8][8], yv[8], pv[8], uv[8];
@@ -85,10 +108,10 @@ PTAM_DEV void block_ldlt64(double (*a)[kLda], double (*us)[8], double* dinv, dou
         for (int j = 0; j < 8; j += 2) { const double2 v = row[j >> 1]; pv[j] = v.x; pv[j + 1] = v.y; }
       }
       // the two row warps have read the diagonal block before its owners overwrite it below
-      asm volatile("bar.sync 1, 64;" ::: "memory");
+      asm volatile("bar.sync 3, 64;" ::: "memory");
 #pragma unroll
       for (int j = 0; j < 8; j++) {
-        const double rcp = 1.0 / dg[j][j];  // (a MUFU seed + two Newton steps was measured slower: 15.6 -> 16.6 us per block)
+        const double rcp = 1.0 / dg[j][j];
         if (r == c0 + j) dinv[c0 + j] = rcp;
         // own row (rows of the finished part and the pivot row itself stay as they are)
         const bool below = r > c0 + j;
@@ -112,60 +135,41 @@ PTAM_DEV void block_ldlt64(double (*a)[kLda], double (*us)[8], double* dinv, dou
         double2* row = reinterpret_cast<double2*>(&a[r][c0]);
 #pragma unroll
         for (int j = 0; j < 8; j += 2) row[j >> 1] = make_double2(pv[j], pv[j + 1]);
+      } else {  // rows of the finished sub-panels: their entries here are scratch, keep them finite for the tiles
+        double2* row = reinterpret_cast<double2*>(&a[r][c0]);
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) row[j >> 1] = make_double2(0.0, 0.0);
       }
-      double2* urow = reinterpret_cast<double2*>(&us[r][0]);
+      double2* urow = reinterpret_cast<double2*>(&u[r][0]);
 #pragma unroll
       for (int j = 0; j < 8; j += 2) urow[j >> 1] = make_double2(uv[j], uv[j + 1]);
       ysh[r] = yr;
+      asm volatile("bar.arrive 2, 256;" ::: "memory");  // sub-panel s is in shared memory
     }
-    __syncthreads();
-    const int t0 = c0 + 8;  // first row / column of the trailing matrix
-    if (t0 < kNB) {
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        if (16 * i + 15 < t0) continue;
-        double l[8];
-        {
-          const double2* row = reinterpret_cast<const double2*>(&a[ty + 16 * i][c0]);
-#pragma unroll
-          for (int q = 0; q < 8; q += 2) { const double2 v = row[q >> 1]; l[q] = v.x; l[q + 1] = v.y; }
-        }
-        if (ty + 16 * i < t0) {  // rows of the finished sub-panels: their entries here are scratch, keep them finite
-#pragma unroll
-          for (int q = 0; q < 8; q++) l[q] = 0.0;
-        }
-#pragma unroll
-        for (int j = 0; j <= i; j++) {
-          if (16 * j + 15 < t0) continue;
-          const double2* urow = reinterpret_cast<const double2*>(&us[tx + 16 * j][0]);
-          double acc = ar[i][j];
-#pragma unroll
-          for (int q = 0; q < 8; q += 2) { const double2 v = urow[q >> 1]; acc -= l[q] * v.x; acc -= l[q + 1] * v.y; }
-          ar[i][j] = acc;
-        }
+  } else {
+    const int uw = warp - 2;  // 0..5
+#pragma unroll 1
+    for (int s = 0; s < nsub; s++) {
+      const int c0 = 8 * s;
+      const double (*u)[8] = us + (s & 1) * kNB;
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (s + 1 < nsub) {  // the next sub-panel's columns first: they are the chain
+        for (int ti = s + 1 + uw; ti < nsub; ti += 6) tile_rank8(a, u, 8 * ti, c0 + 8, c0, lane);
+        asm volatile("bar.arrive 1, 256;" ::: "memory");
       }
-      // the owners of the next eight columns hand them to warp 0 (rows >= t0)
-      const int jn = t0 >> 4;
-      if ((tx >> 3) == ((t0 >> 3) & 1)) {
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const int r = ty + 16 * i;
-          if (r >= t0) {
-            // ar[i][jn] with a run-time jn: select without dynamic register indexing
-            const double v = jn == 0 ? ar[i][0] : jn == 1 ? ar[i][1] : jn == 2 ? ar[i][2] : ar[i][3];
-            a[r][tx + 16 * jn] = v;
-          }
-        }
-      }
+      int q = 0;
+      for (int tj = s + 2; tj < nsub; tj++)
+        for (int ti = tj; ti < nsub; ti++, q++)
+          if (q % 6 == uw) tile_rank8(a, u, 8 * ti, 8 * tj, c0, lane);
     }
-    __syncthreads();
   }
+  __syncthreads();
 }
 
 // Shared memory of k_ldlt_panel (dynamic): the diagonal block, the rank-8 operand, the right-hand side and
 // the reciprocals, plus three 64x64 operands of the PENDING update (see below); the third is reused for
 // the updated rows of this CTA.
-constexpr int kPanelSmem = (4 * kNB * kLda + kNB * 8 + 2 * kNB) * (int)sizeof(double) + 16;  // + the mbarrier of the bulk loads
+constexpr int kPanelSmem = (4 * kNB * kLda + 2 * kNB * 8 + 2 * kNB) * (int)sizeof(double) + 16;  // + the mbarrier of the bulk loads
 
 // Panel k, fused with the head of panel k-1's trailing update.  The columns of panel k still miss the
 // contribution of panel k-1 (the tail kernel of panel k-1 only covers the column blocks from k+1 on), so
@@ -179,7 +183,7 @@ PTAM_DEV void ldlt_panel_body(double* A, double* Wp, const double* Wprev, double
   double (*wd)[kLda] = lh + kNB;   // Wp_prev rows of the diagonal block
   double (*wo)[kLda] = wd + kNB;   // Wp_prev rows of this CTA, then the updated rows themselves
   double (*us)[8] = reinterpret_cast<double (*)[8]>(wo + kNB);
-  double* y1 = reinterpret_cast<double*>(us + kNB);
+  double* y1 = reinterpret_cast<double*>(us + 2 * kNB);  // `us` is double-buffered
   double* dinv = y1 + kNB;
   const int nb = min(kNB, n - k0);
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
@@ -200,6 +204,8 @@ PTAM_DEV void ldlt_panel_body(double* A, double* Wp, const double* Wprev, double
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    griddep_wait();
+    griddep_launch_dependents();
     const int rows_w = max(0, rows_own);
     if (tid == 0) {
       const unsigned bytes = (unsigned)(kNB + (pend ? 2 * kNB + rows_w : 0)) * kNB * (unsigned)sizeof(double);
@@ -224,6 +230,8 @@ PTAM_DEV void ldlt_panel_body(double* A, double* Wp, const double* Wprev, double
     }
     if (tid < kNB) y1[tid] = y[k0 + tid];
   } else {
+    griddep_wait();
+    griddep_launch_dependents();
     for (int i = tid; i < kNB * kNB; i += blockDim.x) {  // the short last panel (identity padding, no rows below it)
       const int r = i / kNB, c = i % kNB;
       a[r][c] = (r < nb && c <= r) ? A[(size_t)(k0 + r) * n + k0 + c] : (r == c ? 1.0 : 0.0);
@@ -378,7 +386,7 @@ PTAM_DEV void ldlt_update_body(double* A, const double* Wp, int n, int k0, int p
     bj = block - bi * (bi + 1);
   }
   const int i0 = r0 + bi * kUTM, j0 = r0 + bj * kUTN;
-  if (j0 >= n) return;  // the last row block may be short of its second diagonal column block
+  if (j0 >= n) { griddep_launch_dependents(); return; }  // the last row block may be short of its second diagonal column block
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned mbar_a = smem_u32(mbar);
   if (tid == 0) {
@@ -386,6 +394,8 @@ PTAM_DEV void ldlt_update_body(double* A, const double* Wp, int n, int k0, int p
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  griddep_wait();
+  griddep_launch_dependents();
   // ---- TMA-engine staging: one 512-byte bulk copy per tile row (192 rows, threads 0..191)
   {
     const int rows_i = min(kUTM, n - i0), rows_j = min(kUTN, n - j0);
