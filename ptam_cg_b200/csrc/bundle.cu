@@ -123,6 +123,7 @@ struct ptam_bundle {
   size_t pair_cap = 0;
   double* h_scal = nullptr;  // pinned
   int* h_cnt = nullptr;      // pinned
+  bool cnt_pending = false;  // h_cnt is on its way (lm_step queued the copy)
   // multi-GPU shard: points [p_lo, p_hi) and their measurements live here; cameras are replicated
   int rank = 0, world = 1;
   ncclComm_t comm = nullptr;
@@ -201,7 +202,7 @@ struct ptam_bundle {
     if (dev < 0 || dev >= ndev) { set_error("bad device index"); return PTAM_ERR_INVALID; }
     PTAM_CUDA_TRY(this, cudaSetDevice(dev));
     PTAM_CUDA_TRY(this, cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    PTAM_CUDA_TRY(this, cudaMallocHost(&h_scal, 8 * sizeof(double)));
+    PTAM_CUDA_TRY(this, cudaMallocHost(&h_scal, 16 * sizeof(double)));
     PTAM_CUDA_TRY(this, cudaMallocHost(&h_cnt, 4 * sizeof(int)));
     if (p) prm = *p; else ptam_bundle_default_params(&prm);
     cam = ptam_make_cam_model(cam_params, w, h);
@@ -352,7 +353,7 @@ struct ptam_bundle {
       AL(Wp, ldlt_workspace_doubles(n));
       AL(m_gid, M); AL(m_erase_step, M); AL(hist16, kSelBins); AL(erase_cnt, (M + 1023) / 1024 + 1); AL(sel_state, 2);
       AL(g_steps, world > 1 ? MG : 0); AL(g_pairs, world > 1 ? 2 * (size_t)MG : 0); AL(g_cnt, 1);
-      AL(s_pack, world > 1 ? (size_t)n * (n + 1) / 2 + n : 0); AL(sel_gather, world > 1 ? (size_t)world * sel_slot : 0);
+      AL(s_pack, world > 1 ? (size_t)n * (n + 1) / 2 + n + 8 : 0); AL(sel_gather, world > 1 ? (size_t)world * sel_slot : 0);
 #undef AL
       if (!pass) {
         need = off;
@@ -441,12 +442,12 @@ struct ptam_bundle {
 
   // sharded handles: sum of the shards' partial S and vE on every shard.  Only the lower triangle is exchanged (the
   // solver reads nothing else), packed row by row with vE behind it: one all-reduce of n (n + 1) / 2 + n doubles.
-  int exchange_reduced() {
+  int exchange_reduced(double* extra = nullptr, int n_extra = 0) {
     const int n = d.n;
-    k_ba_pack_lower<<<148 * 4, 256, 0, stream>>>(d.S, d.vE, n, s_pack.p);
-    int rc = all_reduce(s_pack.p, (size_t)n * (n + 1) / 2 + n, ncclDouble, ncclSum, "all-reduce of the packed S and vE");
+    k_ba_pack_lower<<<148 * 4, 256, 0, stream>>>(d.S, d.vE, n, s_pack.p, extra, n_extra);
+    int rc = all_reduce(s_pack.p, (size_t)n * (n + 1) / 2 + n + n_extra, ncclDouble, ncclSum, "all-reduce of the packed S and vE");
     if (rc) return rc;
-    k_ba_unpack_lower<<<148 * 4, 256, 0, stream>>>(s_pack.p, n, d.S, d.vE);
+    k_ba_unpack_lower<<<148 * 4, 256, 0, stream>>>(s_pack.p, n, d.S, d.vE, extra, n_extra);
     launches += 2;
     PTAM_CUDA_TRY(this, cudaGetLastError());
     return PTAM_OK;
@@ -531,24 +532,38 @@ struct ptam_bundle {
     if (PO > 0) { k_ba_acc_pt<<<(PO + 255) / 256, 256, 0, stream>>>(d); launches++; }
     pend(2);
     PTAM_CUDA_TRY(this, cudaGetLastError());
+    // sharded: the error sums and abort votes of this LM step (scal[2..5]) ride with the first lambda trial's
+    // exchange of S instead of a collective and a host synchronisation of their own
+    const bool merged = world > 1 && n > 0;
+    // a single-GPU handle needs no round trip of its own for them either: they are read back with the first trial's scalars
+    const bool defer = world == 1 || merged;
     if (world > 1) {
       h_scal[5] = local_abort() ? 1.0 : 0.0;
       PTAM_CUDA_TRY(this, cudaMemcpyAsync(scal.p + 5, h_scal + 5, sizeof(double), cudaMemcpyHostToDevice, stream));
-      if ((rc = all_reduce(scal.p + 2, 4, ncclDouble, ncclSum, "all-reduce of the error sums"))) return rc;
+      if (!merged && (rc = all_reduce(scal.p + 2, 4, ncclDouble, ncclSum, "all-reduce of the error sums"))) return rc;
     }
-    PTAM_CUDA_TRY(this, cudaMemcpyAsync(h_scal, scal.p, sizeof(double) * 8, cudaMemcpyDeviceToHost, stream));
-    PTAM_CUDA_TRY(this, cudaStreamSynchronize(stream));
-    pcollect();
-    sigma_sq = h_scal[1];
-    const double cur_err = h_scal[2];
-    if (world > 1) abort_seen = h_scal[5] > 0.0;
-    last_error = cur_err;
+    double cur_err = 0.0;
+    if (!defer) {
+      PTAM_CUDA_TRY(this, cudaMemcpyAsync(h_scal, scal.p, sizeof(double) * 8, cudaMemcpyDeviceToHost, stream));
+      PTAM_CUDA_TRY(this, cudaStreamSynchronize(stream));
+      pcollect();
+      sigma_sq = h_scal[1];
+      cur_err = h_scal[2];
+      if (world > 1) abort_seen = h_scal[5] > 0.0;
+      last_error = cur_err;
+    }
     double new_err = cur_err + 9999;
-    while (new_err > cur_err && !converged && !hit_max && !aborted()) {
+    bool first = true;
+    while ((new_err > cur_err || (defer && first)) && !converged && !hit_max && !aborted()) {
       // scal[3] new error, scal[4] squared update, scal[5] abort votes, scal[6] lambda
       trial_lambda = lambda;
-      h_scal[3] = 0.0; h_scal[4] = 0.0; h_scal[5] = (world > 1 && local_abort()) ? 1.0 : 0.0; h_scal[6] = lambda;
-      PTAM_CUDA_TRY(this, cudaMemcpyAsync(scal.p + 3, h_scal + 3, sizeof(double) * 4, cudaMemcpyHostToDevice, stream));
+      if (merged && first) {  // scal[3..5] are still on their way: only the lambda goes up now
+        h_scal[6] = lambda;
+        PTAM_CUDA_TRY(this, cudaMemcpyAsync(scal.p + 6, h_scal + 6, sizeof(double), cudaMemcpyHostToDevice, stream));
+      } else {
+        h_scal[3] = 0.0; h_scal[4] = 0.0; h_scal[5] = (world > 1 && local_abort()) ? 1.0 : 0.0; h_scal[6] = lambda;
+        PTAM_CUDA_TRY(this, cudaMemcpyAsync(scal.p + 3, h_scal + 3, sizeof(double) * 4, cudaMemcpyHostToDevice, stream));
+      }
       pbegin(3);
       if (PO > 0) { k_ba_vinv<<<(PO + 255) / 256, 256, 0, stream>>>(d); launches++; }
       pend(3);
@@ -558,7 +573,13 @@ struct ptam_bundle {
       s_mirrored = false;
       pbegin(5);
       if (n > 0 && world > 1) {  // the cross-camera J^T J reduction: partial S, vE of every shard -> total on every shard
-        if ((rc = exchange_reduced())) return rc;
+        if (merged && first) {
+          if ((rc = exchange_reduced(scal.p + 2, 4))) return rc;
+          // the reduced error sums and votes to the host (read at the trial's synchronisation below), then the
+          // trial's own accumulators start from zero
+          PTAM_CUDA_TRY(this, cudaMemcpyAsync(h_scal + 8, scal.p, sizeof(double) * 8, cudaMemcpyDeviceToHost, stream));
+          PTAM_CUDA_TRY(this, cudaMemsetAsync(scal.p + 3, 0, sizeof(double) * 3, stream));
+        } else if ((rc = exchange_reduced())) return rc;
       }
       pend(5);
       pbegin(6); if ((rc = solve_reduced())) return rc; pend(6);
@@ -569,16 +590,35 @@ struct ptam_bundle {
       pend(7);
       PTAM_CUDA_TRY(this, cudaGetLastError());
       if ((rc = all_reduce(scal.p + 3, 3, ncclDouble, ncclSum, "all-reduce of the trial scalars"))) return rc;
-      PTAM_CUDA_TRY(this, cudaMemcpyAsync(h_scal + 3, scal.p + 3, sizeof(double) * 3, cudaMemcpyDeviceToHost, stream));
+      if (world == 1) PTAM_CUDA_TRY(this, cudaMemcpyAsync(h_scal, scal.p, sizeof(double) * 8, cudaMemcpyDeviceToHost, stream));
+      else PTAM_CUDA_TRY(this, cudaMemcpyAsync(h_scal + 3, scal.p + 3, sizeof(double) * 3, cudaMemcpyDeviceToHost, stream));
       PTAM_CUDA_TRY(this, cudaStreamSynchronize(stream));
       pcollect();
+      bool step_vote = false;
+      if (defer && first) {  // sigma^2 and the error sum of the LM step: what the exchange brought along / this read-back
+        const double* hs = merged ? h_scal + 8 : h_scal;
+        sigma_sq = hs[1];
+        cur_err = hs[2];
+        last_error = cur_err;
+        step_vote = merged && hs[5] > 0.0;
+      }
+      first = false;
       new_err = h_scal[3];
       last_new_error = new_err;
-      if (world > 1) abort_seen = h_scal[5] > 0.0;
+      if (world > 1) abort_seen = step_vote || h_scal[5] > 0.0;
       if (h_scal[4] < prm.update_squared_convergence) converged = true;
       if (new_err > cur_err) { lambda = lambda * lambda_factor; lambda_factor = lambda_factor * 2; }  // ModifyLambda_BadStep
       counter++;
       if (counter >= prm.max_iterations) hit_max = true;
+    }
+    if (defer && first) {  // no trial ran (converged / iteration limit / abort on entry): fetch the sums on their own
+      if ((rc = all_reduce(scal.p + 2, 4, ncclDouble, ncclSum, "all-reduce of the error sums"))) return rc;
+      PTAM_CUDA_TRY(this, cudaMemcpyAsync(h_scal, scal.p, sizeof(double) * 8, cudaMemcpyDeviceToHost, stream));
+      PTAM_CUDA_TRY(this, cudaStreamSynchronize(stream));
+      pcollect();
+      sigma_sq = h_scal[1]; cur_err = h_scal[2]; last_error = cur_err;
+      if (world > 1) abort_seen = h_scal[5] > 0.0;
+      new_err = cur_err + 9999;
     }
     pbegin(9);
     if (new_err < cur_err) {  // ModifyLambda_GoodStep + commit
@@ -599,9 +639,16 @@ struct ptam_bundle {
     }
     pend(9);
     PTAM_CUDA_TRY(this, cudaMemcpyAsync(h_cnt, counters.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, stream));
+    cnt_pending = true;  // read at the next synchronisation that needs it (refresh_counts): no round trip of its own
+    if (profiling) { PTAM_CUDA_TRY(this, cudaStreamSynchronize(stream)); pcollect(); }
+    return PTAM_OK;
+  }
+
+  int refresh_counts() {
+    if (!cnt_pending) return PTAM_OK;
     PTAM_CUDA_TRY(this, cudaStreamSynchronize(stream));
-    pcollect();
     n_outliers = h_cnt[1];
+    cnt_pending = false;
     return PTAM_OK;
   }
 
@@ -760,7 +807,10 @@ int ptam_bundle_shard_plan(int n_points, int n_meas, const int32_t* meas_point, 
 }
 
 int ptam_bundle_begin(ptam_bundle* b) { return b->begin(); }
-int ptam_bundle_lm_step(ptam_bundle* b, const volatile unsigned char* abort_flag) { return b->lm_step(abort_flag); }
+int ptam_bundle_lm_step(ptam_bundle* b, const volatile unsigned char* abort_flag) {
+  const int rc = b->lm_step(abort_flag);
+  return rc ? rc : b->refresh_counts();  // the single-step entry returns with the handle's stream drained
+}
 
 int ptam_bundle_compute(ptam_bundle* b, const volatile unsigned char* abort_flag) {  // Bundle.cc:116-158
   const auto t0 = std::chrono::steady_clock::now();
@@ -775,6 +825,7 @@ int ptam_bundle_compute(ptam_bundle* b, const volatile unsigned char* abort_flag
     rc = b->lm_step(abort_flag);
     if (rc) return rc;
   }
+  if ((rc = b->refresh_counts())) return rc;
   rc = b->sync_shards();
   if (rc) return rc;
   if (b->profiling) b->prof_wall_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -801,6 +852,7 @@ int ptam_bundle_recompute(ptam_bundle* b, const volatile unsigned char* abort_fl
     rc = b->lm_step(abort_flag);
     if (rc) return rc;
   }
+  if ((rc = b->refresh_counts())) return rc;
   rc = b->sync_shards();
   if (rc) return rc;
   return b->accepted;

@@ -242,7 +242,8 @@ __global__ void __launch_bounds__(256) k_ba_sel_keys(BundleDev d, double* slot, 
 
 // The lower triangle of S row by row (row r: r + 1 values at r (r + 1) / 2) with vE behind it: what the shards
 // exchange per lambda trial (n (n + 1) / 2 + n doubles instead of n^2 + n), and back.
-__global__ void __launch_bounds__(256) k_ba_pack_lower(const double* S, const double* vE, int n, double* out) {
+// (`extra`: a few scalars that ride along, e.g. the error sums of the LM step with its first lambda trial.)
+__global__ void __launch_bounds__(256) k_ba_pack_lower(const double* S, const double* vE, int n, double* out, const double* extra, int n_extra) {
   for (int r = blockIdx.x; r < n; r += gridDim.x) {
     const double* src = S + (size_t)r * n;
     double* dst = out + (size_t)r * (r + 1) / 2;
@@ -251,9 +252,10 @@ __global__ void __launch_bounds__(256) k_ba_pack_lower(const double* S, const do
   if (blockIdx.x == 0) {
     double* dst = out + (size_t)n * (n + 1) / 2;
     for (int c = threadIdx.x; c < n; c += blockDim.x) dst[c] = vE[c];
+    if ((int)threadIdx.x < n_extra) dst[n + threadIdx.x] = extra[threadIdx.x];
   }
 }
-__global__ void __launch_bounds__(256) k_ba_unpack_lower(const double* in, int n, double* S, double* vE) {
+__global__ void __launch_bounds__(256) k_ba_unpack_lower(const double* in, int n, double* S, double* vE, double* extra, int n_extra) {
   for (int r = blockIdx.x; r < n; r += gridDim.x) {
     double* dst = S + (size_t)r * n;
     const double* src = in + (size_t)r * (r + 1) / 2;
@@ -262,6 +264,7 @@ __global__ void __launch_bounds__(256) k_ba_unpack_lower(const double* in, int n
   if (blockIdx.x == 0) {
     const double* src = in + (size_t)n * (n + 1) / 2;
     for (int c = threadIdx.x; c < n; c += blockDim.x) vE[c] = src[c];
+    if ((int)threadIdx.x < n_extra) extra[threadIdx.x] = src[n + threadIdx.x];
   }
 }
 
