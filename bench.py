@@ -201,6 +201,8 @@ def run_cpu_baseline(cpu, kfs, m, frames, poses, budget_s=10.0):
         from oracle.binding import oracle_lib
         p = run_cpu_baseline((oracle_lib(), "port"), kfs, m, frames, poses, budget_s=budget_s / 2)
         out["oracle_port"] = {"value": p["value"], "unit": "frames/s", "cores": 1, "sample": p["sample"]}
+        if "c1_cost_split_per_frame" in p:  # BASELINE config C1: pyramid / FAST / search / GN of one CPU frame
+            out["oracle_port"]["c1_cost_split_per_frame"] = p["c1_cost_split_per_frame"]
     return out
 
 
