@@ -496,7 +496,7 @@ def main():
     top = max(per_kernel, key=lambda k: per_kernel[k]["avg_ms"])
     traffic = None
     tj = ROOT / "profiles" / "traffic.json"
-    if tj.exists():  # DRAM bytes per launch from the committed ncu --set full capture, scaled to this batch size
+    if tj.exists() and (W, H) == (640, 480):  # DRAM bytes per launch from the committed ncu --set full capture, scaled to this batch size
         try:
             t = json.loads(tj.read_text())
             if top in t.get("kernels", {}):
