@@ -17,6 +17,11 @@ using namespace ptam;
 static thread_local std::string g_last_error;
 
 namespace {
+// k_pvs_select: 64 registers per thread, so 512 threads put two trackers on an SM (one wave for two streams per SM)
+inline int pvs_threads() {
+  static const int n = [] { const char* e = std::getenv("PTAM_B200_PVS_THREADS"); const int v = e ? std::atoi(e) : 512; return v >= 32 && v <= 1024 && v % 32 == 0 ? v : 512; }();
+  return n;
+}
 template <class T>
 struct DevBuf {
   T* p = nullptr;
@@ -408,7 +413,7 @@ struct ptam_tracker {
     if (prof) pbegin(3);
     k_sbi<<<S, 256, sbi_smem, stream>>>(d);
     if (d.reloc_on) { k_reloc<<<S, 256, sbi_smem, stream>>>(d); launches++; }
-    k_pvs_select<<<S, 1024, 0, stream>>>(d);
+    k_pvs_select<<<S, pvs_threads(), 0, stream>>>(d);
     if (prof) pend(3); else launches++;
     launches++;
     if (!prof) PTAM_CUDA_TRY(this, cudaStreamWaitEvent(stream, ev_img, 0));
@@ -818,7 +823,7 @@ int ptam_tracker_refind_in_keyframes(ptam_tracker* t, const uint8_t* const* imag
   d.refind_pose = t->refind_pose.p;
   int maxn = 0;
   for (int s = 0; s < t->S; s++) maxn = std::max(maxn, t->h_pt_count[s]);
-  k_pvs_select<<<t->S, 1024, 0, t->stream>>>(d);
+  k_pvs_select<<<t->S, pvs_threads(), 0, t->stream>>>(d);
   t->launches++;
   if (maxn > 0) {
     k_search_prep<<<dim3((maxn + 127) / 128, t->S), 128, 0, t->stream>>>(d, 1);
@@ -991,7 +996,7 @@ int ptam_patch_search_batch(ptam_tracker* t, const double* se3, unsigned range, 
   d.unit_range = range; d.unit_subpix_its = subpix_its;
   int maxn = 0;
   for (int s = 0; s < t->S; s++) maxn = std::max(maxn, t->h_pt_count[s]);
-  k_pvs_select<<<t->S, 1024, 0, t->stream>>>(d);
+  k_pvs_select<<<t->S, pvs_threads(), 0, t->stream>>>(d);
   t->launches++;
   if (maxn > 0) {
     k_search_prep<<<dim3((maxn + 127) / 128, t->S), 128, 0, t->stream>>>(d, 1);
