@@ -19,6 +19,7 @@
 #include <mutex>
 #include <numeric>
 #include <type_traits>
+#include <unordered_map>
 #include <vector>
 
 using namespace ptam;
@@ -60,6 +61,28 @@ struct NcclApi {
 };
 NcclApi& nccl_api() { static NcclApi a; return a; }
 
+// One peer window per communicator (kept for the communicator's life, grown when a larger system comes): the memory
+// the ranks of one node exchange S through (k_ba_peer_*).  Built collectively; any failure (no peer access, another
+// node, IPC refused) leaves `ok` false on EVERY rank, and the handles keep using NCCL.
+struct PeerWindow {
+  bool tried = false, ok = false;
+  int rank = 0, world = 0, device = 0;
+  size_t doubles = 0;          // capacity of the data part
+  double* local = nullptr;     // cudaMalloc: [doubles] + flag block
+  double* peer[kPeerMax] = {};
+  unsigned* flags[kPeerMax] = {};
+  int* err = nullptr;          // device int, local
+  unsigned epoch = 0;
+  void release() {
+    for (int p = 0; p < world; p++) if (p != rank && peer[p]) cudaIpcCloseMemHandle(peer[p]);
+    if (local) cudaFree(local);
+    if (err) cudaFree(err);
+    *this = PeerWindow();
+  }
+};
+std::mutex g_win_mutex;
+std::unordered_map<void*, PeerWindow>& peer_windows() { static std::unordered_map<void*, PeerWindow> m; return m; }
+
 // Contiguous point ranges balanced by measurement count: shard r owns points [begin[r], begin[r+1]).
 void shard_plan(int n_points, int n_meas, const int32_t* meas_point, int world, int32_t* begin, int* per_shard = nullptr) {
   std::vector<int> cnt(n_points + 1, 0);
@@ -89,6 +112,16 @@ struct Buf {
 };
 }  // namespace
 
+static void release_window(void* comm) {
+  std::lock_guard<std::mutex> lock(g_win_mutex);
+  auto it = peer_windows().find(comm);
+  if (it == peer_windows().end()) return;
+  cudaSetDevice(it->second.device);
+  cudaDeviceSynchronize();
+  it->second.release();
+  peer_windows().erase(it);
+}
+
 struct ptam_bundle {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -115,6 +148,8 @@ struct ptam_bundle {
       m_cam, m_pt, m_state, counters, outliers;
   Buf<unsigned> tickets;
   Buf<int> csr_cur;
+  PeerWindow* win = nullptr;       // sharded handles on one node: S / vE live in the communicator's peer window
+  int peer_row_lo = 0, peer_row_hi = 0;
   Buf<double> s_pack, sel_gather;  // sharded handles: packed lower triangle of S + vE; every shard's squared errors
   int sel_slot = 0;                // measurements per slot of sel_gather (the largest shard's count)
   std::vector<int32_t> plan;       // points [plan[r], plan[r + 1]) belong to shard r
@@ -178,7 +213,7 @@ struct ptam_bundle {
     dev_free(pair_buf);
     if (stream) cudaStreamSynchronize(stream);
     for (auto e : prof_ev) if (e) cudaEventDestroy(e);
-    if (comm && own_comm) nccl_api().CommDestroy(comm);
+    if (comm && own_comm) { release_window((void*)comm); nccl_api().CommDestroy(comm); }
     if (h_scal) cudaFreeHost(h_scal);
     if (h_cnt) cudaFreeHost(h_cnt);
     ldlt.destroy();
@@ -203,7 +238,7 @@ struct ptam_bundle {
     PTAM_CUDA_TRY(this, cudaSetDevice(dev));
     PTAM_CUDA_TRY(this, cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     PTAM_CUDA_TRY(this, cudaMallocHost(&h_scal, 16 * sizeof(double)));
-    PTAM_CUDA_TRY(this, cudaMallocHost(&h_cnt, 4 * sizeof(int)));
+    PTAM_CUDA_TRY(this, cudaMallocHost(&h_cnt, 8 * sizeof(int)));
     if (p) prm = *p; else ptam_bundle_default_params(&prm);
     cam = ptam_make_cam_model(cam_params, w, h);
     PTAM_CUDA_TRY(this, cudaFuncSetAttribute(k_ba_acc_cam, cudaFuncAttributeMaxDynamicSharedMemorySize, kAccCamSmem));
@@ -330,6 +365,11 @@ struct ptam_bundle {
     const long long n_blocks = (long long)n_free * (n_free - 1) / 2;
     if (n_pairs_max > 0x7fffffffLL || n_blocks > 0x7ffffff0LL) { set_error("graph too dense for the pair list (more than 2^31 camera pairs / co-visible triples)"); return PTAM_ERR_INVALID; }
     const int grid_max = std::max({(M + 255) / 256, (P + 255) / 256, 1});
+    win = n > 0 ? peer_window(n) : nullptr;  // collective on a sharded handle
+    if (win) {  // rows of the lower triangle per rank, equal element counts: row b_k = n sqrt(k / world)
+      auto bound = [&](int k) { return k >= world ? n : (int)std::lround(n * std::sqrt((double)k / world)); };
+      peer_row_lo = bound(rank); peer_row_hi = bound(rank + 1);
+    }
     // one arena for everything: two passes over the same layout (measure, then assign)
     size_t need = 0;
     for (int pass = 0; pass < 2; pass++) {
@@ -349,7 +389,7 @@ struct ptam_bundle {
       AL(m_B, 6 * (size_t)M); AL(err_cam, C); AL(partials, grid_max); AL(tickets, 4);
       AL(m_cam, M); AL(m_pt, M); AL(m_found, 2 * (size_t)M); AL(m_sin, M); AL(m_state, M); AL(m_v3cam, 3 * (size_t)M);
       AL(m_derivs, 4 * (size_t)M); AL(m_eps, 2 * (size_t)M); AL(m_e2, M); AL(m_W, 18 * (size_t)M); AL(e2c, M);
-      AL(S, (size_t)n * n); AL(vE, n); AL(upd, n); AL(scal, 8); AL(counters, 4); AL(outliers, 2 * (size_t)M);
+      AL(S, win ? 0 : (size_t)n * n); AL(vE, win ? 0 : n); AL(upd, n); AL(scal, 8); AL(counters, 4); AL(outliers, 2 * (size_t)M);
       AL(Wp, ldlt_workspace_doubles(n));
       AL(m_gid, M); AL(m_erase_step, M); AL(hist16, kSelBins); AL(erase_cnt, (M + 1023) / 1024 + 1); AL(sel_state, 2);
       AL(g_steps, world > 1 ? MG : 0); AL(g_pairs, world > 1 ? 2 * (size_t)MG : 0); AL(g_cnt, 1);
@@ -364,6 +404,7 @@ struct ptam_bundle {
         }
       }
     }
+    if (win) { S.p = win->local; vE.p = win->local + (size_t)n * n; }
     lap("arena (cudaMalloc if grown)");
     PTAM_CUDA_TRY(this, cudaMemsetAsync(arena, 0, need, stream));
     PTAM_CUDA_TRY(this, cudaStreamSynchronize(stream));
@@ -444,6 +485,15 @@ struct ptam_bundle {
   // solver reads nothing else), packed row by row with vE behind it: one all-reduce of n (n + 1) / 2 + n doubles.
   int exchange_reduced(double* extra = nullptr, int n_extra = 0) {
     const int n = d.n;
+    if (win) {  // one node: through NVLink peer memory (k_ba_peer_*), S and vE are reduced in place in every rank's window
+      const PeerWin v = peer_view();
+      const unsigned ea = ++win->epoch, eb = ++win->epoch;
+      k_ba_peer_reduce<<<148 * 2, 256, 0, stream>>>(v, ea, eb, peer_row_lo, peer_row_hi, extra, extra, n_extra);
+      k_ba_peer_wait<<<1, 32, 0, stream>>>(v, eb);
+      launches += 2;
+      PTAM_CUDA_TRY(this, cudaGetLastError());
+      return PTAM_OK;
+    }
     k_ba_pack_lower<<<148 * 4, 256, 0, stream>>>(d.S, d.vE, n, s_pack.p, extra, n_extra);
     int rc = all_reduce(s_pack.p, (size_t)n * (n + 1) / 2 + n + n_extra, ncclDouble, ncclSum, "all-reduce of the packed S and vE");
     if (rc) return rc;
@@ -451,6 +501,108 @@ struct ptam_bundle {
     launches += 2;
     PTAM_CUDA_TRY(this, cudaGetLastError());
     return PTAM_OK;
+  }
+
+  // Collective.  Returns the communicator's peer window with room for an n x n system, or nullptr (NCCL path).
+  PeerWindow* peer_window(int n) {
+    // measured (C4, 36 MB triangle): 2 ranks 0.10 ms against 0.15 ms for pack + ncclAllReduce + unpack; from 4 ranks on the
+    // owner-reduces scheme moves 2 (N - 1) / N of the triangle per rank and direction and NCCL (NVLS) is as fast or
+    // faster (0.20 against 0.19 ms at 4), so larger worlds stay on NCCL unless PTAM_B200_PEER_MAX_WORLD says otherwise
+    static const int max_world = [] { const char* e = std::getenv("PTAM_B200_PEER_MAX_WORLD"); return e ? std::atoi(e) : 2; }();
+    if (world < 2 || world > kPeerMax || world > max_world || std::getenv("PTAM_B200_NO_PEER")) return nullptr;
+    std::lock_guard<std::mutex> lock(g_win_mutex);
+    PeerWindow& w = peer_windows()[(void*)comm];
+    const size_t need = (size_t)n * n + n + (size_t)kPeerMax * kPeerExtra;
+    if (w.tried && (!w.ok || w.doubles >= need)) return w.ok ? &w : nullptr;
+    // (re)build: every rank takes this branch together, n is the same everywhere
+    const unsigned keep_epoch = w.epoch;
+    if (w.tried) { cudaStreamSynchronize(stream); w.release(); }
+    w.tried = true; w.rank = rank; w.world = world; w.device = device; w.epoch = keep_epoch;
+    const size_t flag_bytes = sizeof(unsigned) * 2 * kPeerMax;
+    int good = 1;
+    cudaIpcMemHandle_t mine{};
+    if (cudaMalloc(&w.local, need * sizeof(double) + flag_bytes) != cudaSuccess) { good = 0; w.local = nullptr; cudaGetLastError(); }
+    if (good && cudaMalloc(&w.err, 2 * sizeof(int)) != cudaSuccess) { good = 0; w.err = nullptr; cudaGetLastError(); }
+    if (good && cudaIpcGetMemHandle(&mine, w.local) != cudaSuccess) { good = 0; cudaGetLastError(); }
+    // the handles (and whether everybody got this far) travel through the communicator
+    struct Slot { cudaIpcMemHandle_t h; int good; int pad[15]; };
+    static_assert(sizeof(Slot) == 128, "slot size");
+    Slot* d_slots = nullptr;
+    std::vector<Slot> h_slots(world);
+    if (cudaMalloc(&d_slots, sizeof(Slot) * world) != cudaSuccess) { cudaGetLastError(); w.ok = false; return nullptr; }
+    Slot me{}; me.h = mine; me.good = good;
+    cudaMemcpyAsync(d_slots + rank, &me, sizeof(Slot), cudaMemcpyHostToDevice, stream);
+    if (w.local) cudaMemsetAsync(w.local, 0, need * sizeof(double) + flag_bytes, stream);
+    if (w.err) cudaMemsetAsync(w.err, 0, 2 * sizeof(int), stream);
+    nccl_api().AllGather(d_slots + rank, d_slots, sizeof(Slot), ncclChar, comm, stream);
+    cudaMemcpyAsync(h_slots.data(), d_slots, sizeof(Slot) * world, cudaMemcpyDeviceToHost, stream);
+    cudaStreamSynchronize(stream);
+    cudaFree(d_slots);
+    for (int p = 0; p < world; p++) good &= h_slots[p].good;
+    if (good) {
+      for (int p = 0; p < world && good; p++) {
+        if (p == rank) { w.peer[p] = w.local; continue; }
+        void* ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, h_slots[p].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { good = 0; cudaGetLastError(); }
+        w.peer[p] = (double*)ptr;
+      }
+    }
+    // second round: did everybody map everybody?  (also orders the zeroing above before anybody's first signal)
+    int* d_good = nullptr;
+    if (cudaMalloc(&d_good, sizeof(int)) == cudaSuccess) {
+      cudaMemcpyAsync(d_good, &good, sizeof(int), cudaMemcpyHostToDevice, stream);
+      nccl_api().AllReduce(d_good, d_good, 1, ncclInt32, ncclMin, comm, stream);
+      cudaMemcpyAsync(&good, d_good, sizeof(int), cudaMemcpyDeviceToHost, stream);
+      cudaStreamSynchronize(stream);
+      cudaFree(d_good);
+    } else { good = 0; cudaGetLastError(); }
+    if (!good) { const unsigned e = w.epoch; w.release(); w.tried = true; w.epoch = e; return nullptr; }
+    w.doubles = need;
+    for (int p = 0; p < world; p++) w.flags[p] = reinterpret_cast<unsigned*>(w.peer[p] + need);
+    w.ok = true;
+    if (std::getenv("PTAM_B200_PEER_TEST") && rank == 0) {  // debug probe: what a plain kernel gets out of the peer mapping
+      const size_t n2 = std::min<size_t>(need / 2, (size_t)2 << 20);  // 32 MB
+      cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+      for (int mode = 0; mode < 3; mode++) {
+        const double2* src = reinterpret_cast<const double2*>(mode == 0 ? w.peer[1] : w.local);
+        double2* dst = reinterpret_cast<double2*>(mode == 1 ? w.peer[1] : w.local) + (mode == 2 ? n2 : 0);
+        for (int rep = 0; rep < 3; rep++) {
+          cudaEventRecord(e0, stream);
+          k_ba_peer_copy<<<148 * 4, 256, 0, stream>>>(src, dst + (mode == 0 ? n2 : 0), n2);
+          cudaEventRecord(e1, stream);
+          cudaStreamSynchronize(stream);
+          float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+          if (rep == 2) std::fprintf(stderr, "[ptam dbg] peer window probe: %s 32 MB in %.1f us = %.0f GB/s\n",
+                                     mode == 0 ? "read from peer " : mode == 1 ? "write to peer  " : "local copy     ", 1e3 * ms, n2 * 16.0 / (ms * 1e-3) / 1e9);
+        }
+      }
+      cudaMemsetAsync(w.local, 0, need * sizeof(double), stream);
+      cudaStreamSynchronize(stream);
+    }
+    if (std::getenv("PTAM_B200_PEER_TEST")) {  // the exchange itself, back to back, on every rank
+      win = &w;
+      const int n_keep = d.n; d.n = n;
+      auto bound = [&](int k) { return k >= world ? n : (int)std::lround(n * std::sqrt((double)k / world)); };
+      peer_row_lo = bound(rank); peer_row_hi = bound(rank + 1);
+      cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+      for (int rep = 0; rep < 6; rep++) {
+        cudaEventRecord(e0, stream);
+        exchange_reduced();
+        cudaEventRecord(e1, stream);
+        cudaStreamSynchronize(stream);
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        std::fprintf(stderr, "[ptam dbg] rank %d: exchange %d of the %d x %d lower triangle: %.1f us\n", rank, rep, n, n, 1e3 * ms);
+      }
+      d.n = n_keep; win = nullptr;
+    }
+    return &w;
+  }
+
+  PeerWin peer_view() const {
+    PeerWin v{};
+    for (int p = 0; p < world; p++) { v.S[p] = win->peer[p]; v.flags[p] = win->flags[p]; }
+    v.rank = rank; v.world = world; v.n = d.n; v.err = win->err;
+    return v;
   }
 
   int solve_reduced() {  // Cholesky<>(mS).backsub(vE), Bundle.cc:457-458
@@ -516,7 +668,7 @@ struct ptam_bundle {
     // error scalars and only the reduced value is acted on
     auto local_abort = [&]() { return abort_flag && *abort_flag; };
     auto aborted = [&]() { return world > 1 ? abort_seen : local_abort(); };
-    const int C = d.n_cams, P = d.n_pts, M = d.n_meas, n = d.n;
+    const int C = d.n_cams, M = d.n_meas, n = d.n;
     const int PO = d.p_hi - d.p_lo;  // points owned by this shard
     int rc;
     lm_steps++;
@@ -592,8 +744,10 @@ struct ptam_bundle {
       if ((rc = all_reduce(scal.p + 3, 3, ncclDouble, ncclSum, "all-reduce of the trial scalars"))) return rc;
       if (world == 1) PTAM_CUDA_TRY(this, cudaMemcpyAsync(h_scal, scal.p, sizeof(double) * 8, cudaMemcpyDeviceToHost, stream));
       else PTAM_CUDA_TRY(this, cudaMemcpyAsync(h_scal + 3, scal.p + 3, sizeof(double) * 3, cudaMemcpyDeviceToHost, stream));
+      if (win) PTAM_CUDA_TRY(this, cudaMemcpyAsync(h_cnt + 4, win->err, sizeof(int), cudaMemcpyDeviceToHost, stream));
       PTAM_CUDA_TRY(this, cudaStreamSynchronize(stream));
       pcollect();
+      if (win && h_cnt[4]) { set_error("peer exchange of the reduced system timed out (a rank is gone)"); return PTAM_ERR_NCCL; }
       bool step_vote = false;
       if (defer && first) {  // sigma^2 and the error sum of the LM step: what the exchange brought along / this read-back
         const double* hs = merged ? h_scal + 8 : h_scal;
@@ -753,7 +907,8 @@ int ptam_bundle_set_shard(ptam_bundle* b, int rank, int world, void* comm) {
   if (world < 1 || rank < 0 || rank >= world) { b->set_error("bad shard description"); return PTAM_ERR_INVALID; }
   if (world > 1 && !comm) { b->set_error("world > 1 needs an ncclComm_t (or use ptam_bundle_init_shard)"); return PTAM_ERR_NCCL; }
   if (world > 1 && !nccl_api().load()) { b->set_error(nccl_api().err); return PTAM_ERR_NCCL; }
-  if (b->comm && b->own_comm) nccl_api().CommDestroy(b->comm);
+  if (b->comm && b->own_comm) { release_window((void*)b->comm); nccl_api().CommDestroy(b->comm); }
+  b->win = nullptr;
   b->rank = rank; b->world = world; b->comm = world > 1 ? (ncclComm_t)comm : nullptr; b->own_comm = false;
   b->begun = false;
   return PTAM_OK;
@@ -771,7 +926,8 @@ int ptam_nccl_unique_id(unsigned char id[PTAM_NCCL_UNIQUE_ID_BYTES]) {
 
 int ptam_bundle_init_shard(ptam_bundle* b, int rank, int world, const unsigned char id[PTAM_NCCL_UNIQUE_ID_BYTES]) {
   if (world < 1 || rank < 0 || rank >= world) { b->set_error("bad shard description"); return PTAM_ERR_INVALID; }
-  if (b->comm && b->own_comm) { nccl_api().CommDestroy(b->comm); b->comm = nullptr; }
+  if (b->comm && b->own_comm) { release_window((void*)b->comm); nccl_api().CommDestroy(b->comm); b->comm = nullptr; }
+  b->win = nullptr;
   b->rank = rank; b->world = world; b->own_comm = false; b->begun = false;
   if (world == 1) return PTAM_OK;
   if (!nccl_api().load()) { b->set_error(nccl_api().err); return PTAM_ERR_NCCL; }
@@ -796,7 +952,9 @@ void* ptam_nccl_comm_create(int device, int rank, int world, const unsigned char
   return comm;
 }
 void ptam_nccl_comm_destroy(void* comm) {
-  if (comm && nccl_api().load()) nccl_api().CommDestroy((ncclComm_t)comm);
+  if (!comm) return;
+  release_window(comm);
+  if (nccl_api().load()) nccl_api().CommDestroy((ncclComm_t)comm);
 }
 
 int ptam_bundle_shard_plan(int n_points, int n_meas, const int32_t* meas_point, int world, int32_t* point_begin) {

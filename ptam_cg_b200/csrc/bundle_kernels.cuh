@@ -1097,6 +1097,130 @@ __global__ void __launch_bounds__(1024) k_ba_erase_write(BundleDev d, const int*
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Sharded handles on one node: the cross-camera reduction of S, vE over NVLink peer memory, one kernel instead of
+// pack -> ncclAllReduce -> unpack.  Every rank's S / vE live in a window the other ranks map (CUDA IPC).  The lower
+// triangle is cut into row ranges of equal size, one per rank; the owner of an element reads every rank's copy
+// (P2P loads), adds them in rank order — so all ranks end up with the same bits — and stores the sum into every
+// rank's copy (P2P stores).  Two flag barriers in peer memory frame it: "S is built everywhere" before the first
+// load, "every owner has stored" before the solve.  A few scalars (the LM step's error sums and votes) ride along:
+// every rank writes its own into every rank's window before signalling, and each rank adds them up itself.
+// Spins are bounded: a rank that never arrives raises `err` instead of hanging the GPU.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPeerMax = 8;
+constexpr int kPeerExtra = 8;
+struct PeerWin {
+  double* S[kPeerMax];          // every rank's window: S [n][n], vE [n], extras [kPeerMax][kPeerExtra]
+  unsigned* flags[kPeerMax];    // every rank's flag block: [2][kPeerMax] (barrier A, barrier B), written by the peers
+  int rank, world, n;
+  int* err;                     // local: [0] time-out code, [1] CTAs of k_ba_peer_reduce that have finished (monotonic)
+};
+PTAM_DEV double* peer_vE(const PeerWin& w, int p) { return w.S[p] + (size_t)w.n * w.n; }
+PTAM_DEV double* peer_extra(const PeerWin& w, int p) { return w.S[p] + (size_t)w.n * w.n + w.n; }
+
+PTAM_DEV void peer_signal(const PeerWin& w, int which, unsigned epoch, int p) {  // thread p < world
+  __threadfence_system();
+  *reinterpret_cast<volatile unsigned*>(&w.flags[p][which * kPeerMax + w.rank]) = epoch;
+}
+
+PTAM_DEV bool peer_wait(const PeerWin& w, int which, unsigned epoch) {  // one thread
+  const volatile unsigned* f = w.flags[w.rank] + which * kPeerMax;
+  for (int p = 0; p < w.world; p++) {
+    long long spins = 0;
+    while ((int)(f[p] - epoch) < 0) {
+      if (++spins > 3000000ll) { w.err[0] = 1 + which; return false; }  // seconds: a peer is gone
+      __nanosleep(64);
+    }
+  }
+  __threadfence_system();
+  return true;
+}
+
+// barrier B, second half: every owner has stored (the solve may read S)
+__global__ void __launch_bounds__(32) k_ba_peer_wait(PeerWin w, unsigned epoch) {
+  if (threadIdx.x == 0) peer_wait(w, 1, epoch);
+}
+
+// rows [row_lo, row_hi) of the lower triangle belong to this rank; rank 0 also owns vE; every rank sums the extras.
+// CTA 0 first hands this rank's extras to the peers and signals barrier A ("my S is built": everything before this
+// kernel in the stream); every CTA waits for A of all ranks; the CTA that finishes last signals barrier B.
+__global__ void __launch_bounds__(256) k_ba_peer_reduce(PeerWin w, unsigned epoch_a, unsigned epoch_b, int row_lo, int row_hi,
+                                                        const double* extra_in, double* extra_out, int n_extra) {
+  __shared__ int ok;
+  if (blockIdx.x == 0 && (int)threadIdx.x < w.world) {
+    const int p = threadIdx.x;
+    for (int q = 0; q < n_extra; q++) peer_extra(w, p)[w.rank * kPeerExtra + q] = extra_in[q];
+    peer_signal(w, 0, epoch_a, p);
+  }
+  if (threadIdx.x == 0) ok = peer_wait(w, 0, epoch_a) ? 1 : 0;
+  __syncthreads();
+  const int n = w.n, W = w.world;
+  if (ok) {
+  // NVLink loads take microseconds: 16-byte accesses, four of them in flight per thread and peer (rows are 16-byte
+  // aligned when n is even, which 6 x cameras is)
+  const bool vec = (n & 1) == 0;
+  for (int r = row_lo + blockIdx.x; r < row_hi; r += gridDim.x) {
+    const size_t o = (size_t)r * n;
+    const int pairs = vec ? (r + 1) >> 1 : 0;
+    for (int i0 = threadIdx.x; i0 < pairs; i0 += 4 * blockDim.x) {
+      double2 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int i = i0 + u * blockDim.x;
+        v[u] = i < pairs ? *reinterpret_cast<const double2*>(w.S[0] + o + 2 * i) : make_double2(0.0, 0.0);
+      }
+      for (int p = 1; p < W; p++) {
+        double2 t[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int i = i0 + u * blockDim.x;
+          t[u] = i < pairs ? *reinterpret_cast<const double2*>(w.S[p] + o + 2 * i) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) { v[u].x += t[u].x; v[u].y += t[u].y; }
+      }
+      for (int p = 0; p < W; p++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int i = i0 + u * blockDim.x;
+          if (i < pairs) *reinterpret_cast<double2*>(w.S[p] + o + 2 * i) = v[u];
+        }
+      }
+    }
+    for (int c = 2 * pairs + threadIdx.x; c <= r; c += blockDim.x) {  // the odd element of the row (or the whole row)
+      double v = w.S[0][o + c];
+      for (int p = 1; p < W; p++) v += w.S[p][o + c];
+      for (int p = 0; p < W; p++) w.S[p][o + c] = v;
+    }
+  }
+  if (w.rank == 0 && blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < n; c += blockDim.x) {
+      double v = peer_vE(w, 0)[c];
+      for (int p = 1; p < W; p++) v += peer_vE(w, p)[c];
+      for (int p = 0; p < W; p++) peer_vE(w, p)[c] = v;
+    }
+  }
+  if (blockIdx.x == gridDim.x - 1 && (int)threadIdx.x < n_extra) {
+    const double* e = peer_extra(w, w.rank);
+    double v = e[threadIdx.x];
+    for (int p = 1; p < W; p++) v += e[p * kPeerExtra + threadIdx.x];
+    extra_out[threadIdx.x] = v;
+  }
+  }
+  // the last CTA to finish tells the peers that this rank's stores are on their way (fence, then flag)
+  __shared__ int last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(&w.err[1], 1) + 1) % (int)gridDim.x == 0;
+  __syncthreads();
+  if (last && (int)threadIdx.x < W) peer_signal(w, 1, epoch_b, threadIdx.x);
+}
+
+// (debug probe of the peer window: dst[i] = src[i] over 16-byte words, grid-stride)
+__global__ void __launch_bounds__(256) k_ba_peer_copy(const double2* src, double2* dst, size_t n2) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
 // sharded handles: local erase marks -> global measurement order (merged with an all-reduce max)
 __global__ void __launch_bounds__(256) k_ba_scatter_steps(const int* step, const int* gid, int* out, int n) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;

@@ -21,11 +21,14 @@ def main():
     r = bench_ba(prod, local, "C4", reps=3, shard=(rank, world, comm), graph=g4)
     prod.fn("nccl_comm_destroy")(comm)
     r.pop("_result")
+    allp = [None] * world
+    dist.all_gather_object(allp, r["phases_ms_per_call"])
     if rank == 0:
         one = bench_ba(prod, local, "C4", reps=2, graph=g4)
         one.pop("_result")
         print(json.dumps({"n_gpus": world, "sharded": {k: r[k] for k in ("value", "compute_ms", "lambda_trials", "phases_ms_per_call")},
-                          "single": {k: one[k] for k in ("value", "compute_ms", "lambda_trials", "phases_ms_per_call")}}), flush=True)
+                          "single": {k: one[k] for k in ("value", "compute_ms", "lambda_trials", "phases_ms_per_call")},
+                          "per_rank_phases_ms_per_call": allp}), flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
