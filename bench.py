@@ -147,6 +147,25 @@ def init_streams(trk, poses, offsets, n_frames, rng_seed=7):
                       velocity=np.zeros(6), msd=0.0, depth_mean=1.0)
 
 
+def pin_to_gpu_numa_node(gpu_index):
+    """One process per GPU: run on the cores NVML calls local to this GPU, so that the pinned frame buffers (first
+    touch) and the copy submissions sit on the GPU's own NUMA node / PCIe root.  Returns what was done, for the line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_cpu = os.cpu_count() or 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cores = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        allowed = sorted(set(cores) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return {"pinned": False, "why": "no NVML-local core is allowed to this process"}
+        os.sched_setaffinity(0, allowed)
+        return {"pinned": True, "cores": f"{allowed[0]}-{allowed[-1]} ({len(allowed)})"}
+    except Exception as e:  # NVML absent, cpuset restrictions ...
+        return {"pinned": False, "why": repr(e)[:120]}
+
+
 def cpu_reference_lib():
     """(library, kind) for the CPU legs: oracle/_ref/libref_ptam.so — the reference's own Tracker.cc /
     Bundle.cc ... compiled against header stand-ins (oracle/Makefile.ref; prebuilt, it travels with the
@@ -300,6 +319,7 @@ def main():
         reference_arm(args, rank, world)
         return
 
+    numa = pin_to_gpu_numa_node(local) if world > 1 else None
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -551,6 +571,7 @@ def main():
     if per_rank:
         per_rank["e2e_ms_per_step"] = e2e_per_rank
         out["per_rank"] = per_rank
+        out["config"]["cpu_affinity_rank0"] = numa
 
     # ================= BA (configs C3 / C4) =================
     # N = 1: Bundle::Compute on C3 and C4 on this GPU.  N > 1: C4 sharded over all ranks (points

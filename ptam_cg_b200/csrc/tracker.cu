@@ -79,6 +79,8 @@ struct ptam_tracker {
   DevBuf<int2> corners;
   DevBuf<int> lut;
   DevBuf<uint32_t> mask;
+  DevBuf<int> ncorn;           // [S][kLevels] corners per level of the current frames (k_fast2)
+  bool lists_stale = false;    // the corner lists / row LUTs lag behind the masks (TrackFrame does not need them)
   DevBuf<StreamCtl> ctl;
   DevBuf<int> pt_count;
   std::vector<int> h_pt_count;
@@ -209,6 +211,7 @@ struct ptam_tracker {
     PTAM_CUDA_TRY(this, corners.alloc(g.corner_stride * S));
     PTAM_CUDA_TRY(this, lut.alloc((size_t)g.lut_stride * S));
     PTAM_CUDA_TRY(this, mask.alloc(g.mask_stride * S));
+    PTAM_CUDA_TRY(this, ncorn.alloc((size_t)kLevels * S));
     PTAM_CUDA_TRY(this, ctl.alloc(S));
     PTAM_CUDA_TRY(this, pt_count.alloc(S));
     h_pt_count.assign(S, 0);
@@ -223,7 +226,7 @@ struct ptam_tracker {
     }
     PTAM_CUDA_TRY(this, cudaMemcpy(ctl.p, h_ctl, sizeof(StreamCtl) * S, cudaMemcpyHostToDevice));
     PTAM_CUDA_TRY(this, cudaStreamSynchronize(cudaStreamLegacy));
-    dev.pyr = pyr.p; dev.corners = corners.p; dev.lut = lut.p; dev.mask = mask.p; dev.ctl = ctl.p;
+    dev.pyr = pyr.p; dev.corners = corners.p; dev.lut = lut.p; dev.mask = mask.p; dev.ncorn = ncorn.p; dev.ctl = ctl.p;
     dev.pt_count = pt_count.p;
     dev.kf_ptrs = nullptr; dev.n_kf = 0;
     PTAM_CUDA_TRY(this, ensure_points(1024));
@@ -365,22 +368,40 @@ struct ptam_tracker {
     return PTAM_OK;
   }
 
-  void queue_keyframe(const TrackerDev& d, cudaStream_t st, bool prof, cudaEvent_t after_l0 = nullptr) {
+  // pyramid + FAST (+ corner lists and row LUTs when `lists`: TrackFrame itself reads the corner masks only, the
+  // lists are made on demand by ensure_lists())
+  void queue_keyframe(const TrackerDev& d, cudaStream_t st, bool prof, bool lists, cudaEvent_t after_l0 = nullptr) {
     const LevelDesc& L0 = d.g.lev[0];
+    cudaMemsetAsync(ncorn.p, 0, sizeof(int) * kLevels * S, st);
     if (prof) pbegin(0);
     k_fast2<true><<<dim3(L0.tiles_x, L0.tiles_y, S), 256, 0, st>>>(d);
     if (prof) pend(0); else launches++;
     if (after_l0) cudaEventRecord(after_l0, st);
     if (prof) pbegin(1);
     k_fast2<false><<<dim3(d.g.fast_tiles, S), 256, 0, st>>>(d);
-    if (prof) { pend(1); pbegin(2); } else launches++;
-    k_compact<<<dim3(kLevels, S), 1024, 0, st>>>(d);
-    if (prof) pend(2); else launches++;
+    if (prof) pend(1); else launches++;
+    if (lists) {
+      if (prof) pbegin(2);
+      k_compact<<<dim3(kLevels, S), 1024, 0, st>>>(d);
+      if (prof) pend(2); else launches++;
+    }
+    lists_stale = !lists;
+  }
+
+  // corner lists, row LUTs and StreamCtl::n_corners of the frames last processed (everything but TrackFrame's own
+  // search reads them: get_level, MakeKeyFrame_Rest, the epipolar search)
+  int ensure_lists() {
+    if (!lists_stale) return PTAM_OK;
+    k_compact<<<dim3(kLevels, S), 1024, 0, stream>>>(dev);
+    launches++;
+    PTAM_CUDA_TRY(this, cudaGetLastError());
+    lists_stale = false;
+    return PTAM_OK;
   }
 
   int launch_keyframe(const TrackerDev& d, bool collect = true) {
     rest_stream = -1;  // MakeKeyFrame_Rest results belong to the previous frame
-    queue_keyframe(d, stream, profiling);
+    queue_keyframe(d, stream, profiling, true);
     PTAM_CUDA_TRY(this, cudaGetLastError());
     return collect ? pcollect(7u) : PTAM_OK;
   }
@@ -393,9 +414,9 @@ struct ptam_tracker {
     static const bool no_istream = std::getenv("PTAM_B200_ISTREAM") && std::atoi(std::getenv("PTAM_B200_ISTREAM")) == 0;
     int maxn = 0;
     for (int s = 0; s < S; s++) maxn = std::max(maxn, h_pt_count[s]);
-    unsigned used = 7u | 8u | 32u | 128u;
-    if (prof) queue_keyframe(d, stream, true);
-    else if (no_istream) { queue_keyframe(d, stream, false); ensure_istream(); cudaEventRecord(ev_pyr, stream); cudaEventRecord(ev_img, stream); }
+    unsigned used = 3u | 8u | 32u | 128u;
+    if (prof) queue_keyframe(d, stream, true, false);
+    else if (no_istream) { queue_keyframe(d, stream, false, false); ensure_istream(); cudaEventRecord(ev_pyr, stream); cudaEventRecord(ev_img, stream); }
     else {
       int rc = ensure_istream();
       if (rc) return rc;
@@ -406,7 +427,7 @@ struct ptam_tracker {
         if (frames_ready) PTAM_CUDA_TRY(this, cudaStreamWaitEvent(istream, frames_ready, 0));
         if (imgfree_pending) PTAM_CUDA_TRY(this, cudaStreamWaitEvent(istream, ev_imgfree, 0));
       }
-      queue_keyframe(d, istream, false, ev_pyr);
+      queue_keyframe(d, istream, false, false, ev_pyr);
       PTAM_CUDA_TRY(this, cudaEventRecord(ev_img, istream));
       PTAM_CUDA_TRY(this, cudaStreamWaitEvent(stream, ev_pyr, 0));
     }
@@ -757,6 +778,7 @@ int ptam_tracker_level_size(const ptam_tracker* t, int level, int* w, int* h) {
 int ptam_tracker_get_level(ptam_tracker* t, int stream, int level, uint8_t* pixels, int32_t* corners_xy, int cap, int32_t* row_lut) {
   cudaSetDevice(t->device);
   if (stream < 0 || stream >= t->S || level < 0 || level >= kLevels) { t->set_error("bad stream / level"); return PTAM_ERR_INVALID; }
+  { const int rc = t->ensure_lists(); if (rc) return rc; }
   PTAM_CUDA_TRY(t, cudaStreamSynchronize(t->stream));
   const LevelDesc& L = t->dev.g.lev[level];
   if (pixels) {
@@ -839,6 +861,7 @@ int ptam_tracker_keyframe_rest(ptam_tracker* t, int stream, double min_shi_tomas
   cudaSetDevice(t->device);
   if (stream < 0 || stream >= t->S) { t->set_error("bad stream"); return PTAM_ERR_INVALID; }
   if (!t->dev.src.l0) { t->set_error("no frame processed yet"); return PTAM_ERR_INVALID; }
+  { const int rc = t->ensure_lists(); if (rc) return rc; }
   const Geom& g = t->dev.g;
   if (!t->rest_smap.p) {
     PTAM_CUDA_TRY(t, t->rest_smap.alloc(g.pyr_bytes));
@@ -871,6 +894,7 @@ int ptam_tracker_epipolar_search(ptam_tracker* t, int stream, int level, int src
   if (src_kf < 0 || src_kf >= (int)t->kf_bufs.size()) { t->set_error("unknown source keyframe"); return PTAM_ERR_INVALID; }
   if (!t->dev.src.l0) { t->set_error("no current frame: run ptam_tracker_make_keyframes / track_frames first"); return PTAM_ERR_INVALID; }
   if (n_cand <= 0) return PTAM_OK;
+  { const int rc = t->ensure_lists(); if (rc) return rc; }
   const Geom& g = t->dev.g;
   if (!t->epi_implane.p) PTAM_CUDA_TRY(t, t->epi_implane.alloc(g.corner_stride));
   if ((size_t)n_cand > t->epi_cand.n) {

@@ -111,6 +111,7 @@ struct TrackerDev {
   int2* corners;         // [S] corner lists
   int* lut;              // [S] row LUTs
   uint32_t* mask;        // [S] corner bitmasks
+  int* ncorn;            // [S][kLevels] corners per level, counted by k_fast2 (zeroed before it)
   const uint8_t* const* kf_ptrs;  // stored keyframe pyramids
   int n_kf;
   StreamCtl* ctl;        // [S]
@@ -515,10 +516,18 @@ __global__ void __launch_bounds__(256, kMinB) k_fast2(TrackerDev d) {
     if (corner) atomicOr(&out_mask[ry][px >> 5], 1u << (px & 31));
   }
   __syncthreads();
+  int n_here = 0;
   if (threadIdx.x < kF2H * 4) {
     const int ry = threadIdx.x >> 2, wq = threadIdx.x & 3;
     const int y = y0 + ry, word = (x0 >> 5) + wq;
-    if (y < L.h && word < L.nwords) d.mask[(size_t)s * d.g.mask_stride + L.mask_off + (size_t)y * L.nwords + word] = out_mask[ry][wq];
+    if (y < L.h && word < L.nwords) {
+      d.mask[(size_t)s * d.g.mask_stride + L.mask_off + (size_t)y * L.nwords + word] = out_mask[ry][wq];
+      n_here = __popc(out_mask[ry][wq]);
+    }
+  }
+  if (threadIdx.x < 192) {  // corners of this tile (warps 0..5 hold the mask words) -> the level's counter
+    n_here = __reduce_add_sync(kFull, n_here);
+    if ((threadIdx.x & 31) == 0 && n_here) atomicAdd(&d.ncorn[s * kLevels + l], n_here);
   }
 }
 
@@ -1273,24 +1282,13 @@ __global__ void __launch_bounds__(128) k_search_prep(TrackerDev d, int stage) {
   }
   d.p.flags[g] = fl;
   // ---- FindPatchCoarse, the scalar part (PatchFinder.cc:160-191): search centre and range in level
-  // coordinates (ir() truncation, C++ integer division), candidate index range from the row LUT
+  // coordinates (ir() truncation, C++ integer division), the candidates themselves come from the corner mask in k_search
   {
     const unsigned range = d.mode == 1 ? 4u : d.mode == 2 ? d.unit_range : (stage == 0 ? (unsigned)ctl.coarse_range : (ctl.did_coarse ? 5u : 10u));
     const int scale = 1 << sl;
     const int posx = (int)d.p.v2image[2 * g] / scale, posy = (int)d.p.v2image[2 * g + 1] / scale;
     const unsigned r = (range + scale - 1) / scale;
-    int top = posy - (int)r;
-    const int bot1 = posy + (int)r + 1;
-    const LevelDesc& L = d.g.lev[sl];
-    if (top < 0) top = 0;
-    int i0 = 0, i1 = 0;
-    if (!(top >= L.h) && !(bot1 <= 0)) {
-      const int* lut = d.lut + (size_t)s * d.g.lut_stride + L.lut_off;
-      i0 = lut[top];
-      i1 = bot1 >= L.h ? ctl.n_corners[sl] : lut[bot1];
-    }
     d.p.geo[2 * g] = make_int4(posx, posy, (int)r, 0);
-    d.p.geo[2 * g + 1] = make_int4(i0, i1, 0, 0);
   }
 }
 
@@ -1386,20 +1384,22 @@ __global__ void __launch_bounds__(128, 12) k_search(TrackerDev d, int stage) {
   bool found = false;
   double coarse[2] = {0, 0};
   {
-    const int4 g0 = d.p.geo[2 * g], g1 = d.p.geo[2 * g + 1];
+    const int4 g0 = d.p.geo[2 * g];
     const int posx = g0.x, posy = g0.y;
     const unsigned r = (unsigned)g0.z;
-    const int left = posx - (int)r, right = posx + (int)r;
     const LevelDesc& L = d.g.lev[sl];
     int pitch;
     const uint8_t* im = level_image(d, s, sl, pitch);
-    const int i0 = g1.x, i1 = g1.y;
-    if (i1 > i0) {
-      const int2* corners = d.corners + (size_t)s * d.g.corner_stride + L.corner_off;
-      // Candidates (disc test + 4-px border, PatchFinder.cc:193-196, ImageProcess.cc:134) are queued per
-      // warp; ZMSSD then runs four candidates at a time, eight lanes per candidate, one 8-pixel window
-      // row per lane: three aligned 32-bit loads + byte_perm, six dp4a, group reduction.  The winner is
-      // the minimum of (ssd, corner index), i.e. the first minimum in raster order (PatchFinder.cc:198).
+    // candidate corners: inside the disc of radius r around (posx, posy) and 4 px off the border (PatchFinder.cc:193-196,
+    // ImageProcess.cc:134).  They are read straight from the corner MASK of the level: lane -> one row of the
+    // window, the one to three mask words that cover [posx - r, posx + r]; no corner list, no row LUT on this path.
+    const int x_lo = max(posx - (int)r, 4), x_hi = min(posx + (int)r, L.w - 5);
+    const int y_lo = max(posy - (int)r, 4), y_hi = min(posy + (int)r, L.h - 5);
+    if (x_lo <= x_hi && y_lo <= y_hi) {
+      const uint32_t* mask = d.mask + (size_t)s * d.g.mask_stride + L.mask_off;
+      // Candidates are queued per warp; ZMSSD then runs four candidates at a time, eight lanes per candidate, one
+      // 8-pixel window row per lane: three aligned 32-bit loads + byte_perm, six dp4a, group reduction.  The winner
+      // is the minimum of (ssd, raster position), i.e. the first minimum in raster order (PatchFinder.cc:198).
       const int sub = lane & 7, grp = lane >> 3;
       const unsigned tw0 = *reinterpret_cast<const unsigned*>(&stmpl[warp][8 * sub]);
       const unsigned tw1 = *reinterpret_cast<const unsigned*>(&stmpl[warp][8 * sub + 4]);
@@ -1408,8 +1408,8 @@ __global__ void __launch_bounds__(128, 12) k_search(TrackerDev d, int stage) {
         for (int r0 = 0; r0 < n; r0 += 4) {
           const int kq = r0 + grp;
           const bool valid = kq < n;
-          const int2 e = squeue[warp][valid ? kq : 0];
-          const int cx = e.x & 0xffff, cy = e.x >> 16;
+          const int ek = squeue[warp][valid ? kq : 0].x;  // y << 16 | x: the raster position
+          const int cx = ek & 0xffff, cy = ek >> 16;
           const uint8_t* ip = im + (size_t)(cy - 4 + sub) * pitch + (cx - 4);
           const unsigned a = (unsigned)(reinterpret_cast<uintptr_t>(ip) & 3);
           const unsigned* wp = reinterpret_cast<const unsigned*>(ip - a);
@@ -1427,28 +1427,40 @@ __global__ void __launch_bounds__(128, 12) k_search(TrackerDev d, int stage) {
           }
           const int SA = tsum, SB = isum;
           const int ssd = ((2 * SA * SB - SA * SA - SB * SB) / 64 + isq + tsumsq - 2 * cross);  // C++ truncating division
-          if (valid && (ssd < best_ssd || (ssd == best_ssd && e.y < best_idx))) { best_ssd = ssd; best_idx = e.y; }
+          if (valid && (ssd < best_ssd || (ssd == best_ssd && ek < best_idx))) { best_ssd = ssd; best_idx = ek; }
         }
         __syncwarp();
       };
       int qn = 0, n_eval = 0;
       const unsigned lt = (1u << lane) - 1u;
-      for (int b0 = i0; b0 < i1; b0 += 32) {
-        const int i = b0 + lane;
-        int2 c = make_int2(0, 0);
-        bool pass = false;
-        if (i < i1) {
-          c = corners[i];
-          if (!(c.x < left || c.x > right)) {
-            const int ddx = posx - c.x, ddy = posy - c.y;
-            pass = !((unsigned)(ddx * ddx + ddy * ddy) > r * r) && c.x >= 4 && c.y >= 4 && c.x < L.w - 4 && c.y < L.h - 4;
+      const int w_lo = x_lo >> 5, w_hi = x_hi >> 5;
+      for (int yb = y_lo; yb <= y_hi; yb += 32) {
+        const int y = yb + lane;
+        const int ddy = posy - y;
+        for (int wi = w_lo; wi <= w_hi; wi++) {
+          unsigned m = 0;
+          if (y <= y_hi) {
+            m = __ldg(mask + (size_t)y * L.nwords + wi);
+            const int b_lo = max(x_lo - 32 * wi, 0), b_hi = min(x_hi - 32 * wi, 31);  // bits of this word inside [x_lo, x_hi]
+            m &= (0xffffffffu << b_lo) & (0xffffffffu >> (31 - b_hi));
+          }
+          while (__any_sync(kFull, m != 0)) {
+            bool pass = false;
+            int cx = 0;
+            if (m) {
+              const int b = __ffs(m) - 1;
+              m &= m - 1;
+              cx = 32 * wi + b;
+              const int ddx = posx - cx;
+              pass = !((unsigned)(ddx * ddx + ddy * ddy) > r * r);
+            }
+            const unsigned bal = __ballot_sync(kFull, pass);
+            if (pass) squeue[warp][qn + __popc(bal & lt)] = make_int2(cx | (y << 16), 0);
+            qn += __popc(bal);
+            n_eval += __popc(bal);
+            if (qn > 32) { __syncwarp(); process(qn); qn = 0; }
           }
         }
-        const unsigned m = __ballot_sync(kFull, pass);
-        if (pass) squeue[warp][qn + __popc(m & lt)] = make_int2(c.x | (c.y << 16), i);
-        qn += __popc(m);
-        n_eval += __popc(m);
-        if (qn > 32) { __syncwarp(); process(qn); qn = 0; }
       }
       __syncwarp();
       process(qn);
@@ -1459,7 +1471,7 @@ __global__ void __launch_bounds__(128, 12) k_search(TrackerDev d, int stage) {
         best_ssd = bs;
       }
       int bx = 0, by = 0;
-      if (best_ssd < kMaxSSD) { const int2 bc = corners[best_idx]; bx = bc.x; by = bc.y; }
+      if (best_ssd < kMaxSSD) { bx = best_idx & 0xffff; by = best_idx >> 16; }
       if (best_ssd < kMaxSSD) {
         coarse[0] = level_zero_pos((double)bx, sl);
         coarse[1] = level_zero_pos((double)by, sl);
@@ -1860,7 +1872,7 @@ __global__ void __launch_bounds__(kPoseThreads, 2) k_pose(TrackerDev d, int stag
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n_set = stage == 0 ? ctl.n_coarse : ctl.n_coarse + ctl.n_l3 + ctl.n_fine;
   const int fmode = (d.mode == 0 && d.reloc_on) ? ctl.frame_mode : 0;
-  if (stage == 0 && threadIdx.x < kLevels) ctl.res_n_corners[threadIdx.x] = ctl.n_corners[threadIdx.x];
+  if (stage == 0 && threadIdx.x < kLevels) ctl.res_n_corners[threadIdx.x] = d.ncorn[s * kLevels + threadIdx.x];
   if (fmode == 2) return;  // relocalisation failed: the reference does nothing else this frame
 #ifdef PTAM_POSE_CLOCKS
   long long pclk_last = clock64();
