@@ -1579,10 +1579,10 @@ constexpr int kPoseThreads = PTAM_POSE_THREADS;  // two CTAs (streams) resident 
 // exact k-th smallest (0-based) of n non-negative doubles: MSB-first radix select on the IEEE bit
 // patterns (order-isomorphic to the values), 8 bits per pass; the 256-bin histogram is scanned by
 // warp 0 (8 bins per lane + shuffle scan), so a pass costs two barriers and no serial loop.
-// Squared errors of one frame share their top bits, so the histogram updates are aggregated per warp
-// (match.any on the digit: one shared-memory atomic per distinct digit and warp instead of one per
-// element on the same bin), and the passes stop as soon as the bin of the k-th element holds ONE element:
-// a last sweep fetches that element (usually after 3-4 of the 8 passes; ties run all 8).
+// Squared errors of one frame share their top bits, so the histogram updates of the FIRST pass are aggregated per
+// warp (match.any on the digit: one shared-memory atomic per distinct digit and warp instead of one per element on
+// the same bin; the later digits are spread, where match.any costs more than it saves), and the passes stop as soon as
+// the bin of the k-th element holds ONE element: a last sweep fetches that element (usually after 3-4 of the 8 passes; ties run all 8).
 // keys are read through `at(i)`.  All threads of the block must call it.
 template <class At>
 PTAM_DEV double block_select_kth(At at, int n, int kth, int* hist /*2 x 256*/, unsigned long long* sh_prefix, int* sh_k) {
@@ -1602,8 +1602,12 @@ PTAM_DEV double block_select_kth(At at, int n, int kth, int* hist /*2 x 256*/, u
         const unsigned long long key = (unsigned long long)__double_as_longlong(at(i));
         if (pass == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8))) digit = (unsigned)(key >> shift) & 255u;
       }
-      const unsigned peers = __match_any_sync(kFull, digit);
-      if (digit < 256u && lane == __ffs(peers) - 1) atomicAdd(&h[digit], __popc(peers));
+      if (pass == 0) {  // sign + top exponent bits: one or two bins for the whole frame -> one atomic per warp and bin
+        const unsigned peers = __match_any_sync(kFull, digit);
+        if (digit < 256u && lane == __ffs(peers) - 1) atomicAdd(&h[digit], __popc(peers));
+      } else if (digit < 256u) {  // later digits are spread: match.any walks the distinct values, plain atomics are cheaper
+        atomicAdd(&h[digit], 1);
+      }
     }
     __syncthreads();
     if (warp == 0) {
@@ -1703,7 +1707,7 @@ PTAM_DEV void calc_jacobian(double X, double Y, double Z, double dv0, double dv1
 
 #ifdef PTAM_POSE_CLOCKS
 __device__ long long g_pose_clk[32];
-#define PCLK(k) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long t_ = clock64(); g_pose_clk[k] += t_ - pclk_last; pclk_last = t_; } } while (0)
+#define PCLK(k) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long t_ = clock64(); g_pose_clk[(k) + 16 * (stage == 0)] += t_ - pclk_last; pclk_last = t_; } } while (0)
 #else
 #define PCLK(k) do { } while (0)
 #endif

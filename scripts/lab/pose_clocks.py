@@ -40,12 +40,13 @@ def main():
     fn(out, 0)
     names = {0: "per-point (non-linear its)", 1: "per-point (linear its)", 2: "sigma select", 3: "WLS accumulate", 4: "transpose-sum + smem",
              5: "cross-warp sum + 6x6 solve", 6: "se3 exp + pose", 8: "compaction + gather", 9: "(iterations total marker)", 10: "write-back + motion model/quality"}
-    tot = sum(out[k] for k in range(11) if k != 9)
-    print("cycles of CTA 0 per frame (coarse + fine k_pose), S =", S)
-    for k in sorted(names):
-        if k == 9: continue
-        print("  %-34s %9.0f  %5.1f %%" % (names[k], out[k] / n, 100.0 * out[k] / max(tot, 1)))
-    print("  total %.0f cycles = %.1f us at 1.965 GHz" % (tot / n, tot / n / 1965.0))
+    for stage, off in (("fine", 0), ("coarse", 16)):
+        tot = sum(out[off + k] for k in range(11) if k != 9)
+        print("cycles of CTA 0 per frame, %s k_pose, S = %d" % (stage, S))
+        for k in sorted(names):
+            if k == 9: continue
+            print("  %-34s %9.0f  %5.1f %%" % (names[k], out[off + k] / n, 100.0 * out[off + k] / max(tot, 1)))
+        print("  total %.0f cycles = %.1f us at 1.965 GHz" % (tot / n, tot / n / 1965.0))
 
 if __name__ == "__main__":
     main()
