@@ -329,10 +329,13 @@ int ptam_bundle_add_measurements(ptam_bundle* b, int n, const int32_t* cam, cons
  * graph through the Add* calls, and the handle of rank r keeps the points of its contiguous range
  * (ptam_bundle_shard_plan, balanced by measurement count) with all their measurements; cameras are
  * replicated.  Inside ptam_bundle_compute / _lm_step the partial reduced camera system (S, vE) of
- * every rank is summed with ncclAllReduce (the cross-camera J^T J reduction) and solved identically
- * everywhere; the sigma-squared order statistic is found exactly by a radix select whose digit
- * histograms are all-reduced; error sums and abort votes ride in one small all-reduce per lambda
- * trial.  After compute every rank holds all points, cameras and the merged outlier list.
+ * every rank is summed (the cross-camera J^T J reduction: the packed lower triangle through ncclAllReduce,
+ * or, for two ranks of one node, in place through an NVLink peer window the ranks map with CUDA IPC) and
+ * solved identically everywhere; the sigma-squared order statistic is found exactly by a radix select on the
+ * all-gathered squared errors; the LM step's error sums and abort votes ride with the first exchange, the
+ * trial's in one small all-reduce.  After compute every rank holds all points, cameras and the merged
+ * outlier list.  The peer window belongs to the communicator: ONE sharded handle per communicator at a time
+ * (as MapMaker builds one Bundle at a time), and ptam_nccl_comm_destroy releases it.
  * In a sharded run compute / lm_step / get_point(s) / get_outliers / get_stats are COLLECTIVE.
  *   ptam_nccl_unique_id   rank 0 creates the id and ships it to the other ranks by any host channel;
  *   ptam_bundle_init_shard  creates the handle's own communicator from it (ncclCommInitRank);

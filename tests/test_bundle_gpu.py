@@ -58,6 +58,24 @@ def test_compute_matches_oracle(oracle, product, shape):
     assert np.abs(p.get_points() - g["true_points"]).mean() < 0.6 * np.abs(g["points"] - g["true_points"]).mean()
 
 
+def test_points_seen_by_more_than_32_cameras(oracle, product):
+    """Every point observed by 40 of 44 keyframes: the device-built point CSR takes its long-list path (heap sort of a
+    point's slots by list index), and the first reduced system must still be the oracle's bit for bit."""
+    g = synth.make_ba_graph(44, 60, 2400, seed=5)
+    assert np.bincount(np.asarray(g["meas_point"])).max() > 32
+    o, p = _pair(oracle, product, g)
+    o.begin(); p.begin()
+    o.lm_step(); p.lm_step()
+    n = 6 * int((g["cam_fixed"] == 0).sum())
+    So, eo = o.reduced_system(n)
+    Sp, ep = p.reduced_system(n)
+    assert np.array_equal(Sp, So) and np.array_equal(ep, eo)
+    _same_stats(o.stats(), p.stats(), rtol=1e-11)
+    o2, p2 = _pair(oracle, product, g)
+    assert o2.Compute() == p2.Compute()
+    assert np.array_equal(o2.GetOutlierMeasurements(), p2.GetOutlierMeasurements())
+
+
 def test_stepwise_and_reduced_system(oracle, product):
     g = synth.make_ba_graph(10, 500, 2500, seed=9)
     o, p = _pair(oracle, product, g)
