@@ -1128,7 +1128,7 @@ PTAM_DEV bool peer_wait(const PeerWin& w, int which, unsigned epoch) {  // one t
   for (int p = 0; p < w.world; p++) {
     long long spins = 0;
     while ((int)(f[p] - epoch) < 0) {
-      if (++spins > 3000000ll) { w.err[0] = 1 + which; return false; }  // seconds: a peer is gone
+      if (++spins > 15000000ll) { w.err[0] = 1 + which; return false; }  // ~10 s: a peer is gone
       __nanosleep(64);
     }
   }
