@@ -147,7 +147,7 @@ struct ptam_bundle {
   Buf<int> cam_fixed, cam_row, pt_off, pt_meas, pt_meas_ins, pt_cam, cam_off, cam_meas_ins, cam_meas_pt, blk_off, blk_cnt, nz_blocks, pair_info, free_cam,
       m_cam, m_pt, m_state, counters, outliers;
   Buf<unsigned> tickets;
-  Buf<int> csr_cur;
+  Buf<int> csr_cur, cam_order;
   PeerWindow* win = nullptr;       // sharded handles on one node: S / vE live in the communicator's peer window
   int peer_row_lo = 0, peer_row_hi = 0;
   Buf<double> s_pack, sel_gather;  // sharded handles: packed lower triangle of S + vE; every shard's squared errors
@@ -362,6 +362,9 @@ struct ptam_bundle {
     lap("measurement lists (host)");
     std::vector<int> freecam;
     for (int j = 0; j < C; j++) if (!h_cam_fixed[j]) freecam.push_back(j);
+    std::vector<int> camorder(C);  // per-camera kernels take the cameras with the most measurements first
+    std::iota(camorder.begin(), camorder.end(), 0);
+    std::stable_sort(camorder.begin(), camorder.end(), [&](int a, int b) { return coff[a + 1] - coff[a] > coff[b + 1] - coff[b]; });
     const long long n_blocks = (long long)n_free * (n_free - 1) / 2;
     if (n_pairs_max > 0x7fffffffLL || n_blocks > 0x7ffffff0LL) { set_error("graph too dense for the pair list (more than 2^31 camera pairs / co-visible triples)"); return PTAM_ERR_INVALID; }
     const int grid_max = std::max({(M + 255) / 256, (P + 255) / 256, 1});
@@ -385,7 +388,7 @@ struct ptam_bundle {
       AL(pt_pos, 3 * (size_t)P); AL(pt_pos_new, 3 * (size_t)P); AL(V, 6 * (size_t)P); AL(epsB, 3 * (size_t)P);
       AL(Vinv, 9 * (size_t)P); AL(Ve, 3 * (size_t)P); AL(pt_off, P + 1); AL(pt_meas, M);
       AL(pt_meas_ins, idx_ins.empty() ? 0 : M); AL(pt_cam, M); AL(cam_off, C + 1); AL(cam_meas_ins, M);
-      AL(cam_meas_pt, cidx_pt.empty() ? 0 : M); AL(blk_off, n_blocks + 1); AL(blk_cnt, n_blocks); AL(nz_blocks, n_blocks); AL(pair_info, 4); AL(free_cam, n_free); AL(csr_cur, P + 1); AL(csr_pairs, 1);
+      AL(cam_meas_pt, cidx_pt.empty() ? 0 : M); AL(blk_off, n_blocks + 1); AL(blk_cnt, n_blocks); AL(nz_blocks, n_blocks); AL(pair_info, 4); AL(free_cam, n_free); AL(cam_order, C); AL(csr_cur, P + 1); AL(csr_pairs, 1);
       AL(m_B, 6 * (size_t)M); AL(err_cam, C); AL(partials, grid_max); AL(tickets, 4);
       AL(m_cam, M); AL(m_pt, M); AL(m_found, 2 * (size_t)M); AL(m_sin, M); AL(m_state, M); AL(m_v3cam, 3 * (size_t)M);
       AL(m_derivs, 4 * (size_t)M); AL(m_eps, 2 * (size_t)M); AL(m_e2, M); AL(m_W, 18 * (size_t)M); AL(e2c, M);
@@ -413,7 +416,7 @@ struct ptam_bundle {
     UP(cam_se3, h_cam_se3); UP(cam_fixed, h_cam_fixed); UP(cam_row, h_cam_row); UP(pt_pos, h_pts);
     UP(pt_off, off); UP(pt_meas, idx); UP(m_cam, v_mcam); UP(m_pt, v_mpt); UP(m_found, v_found); UP(m_sin, v_sin);
     if (!whole) UP(m_gid, l_gid);
-    UP(pt_meas_ins, idx_ins); UP(pt_cam, ptcam); UP(cam_off, coff); UP(cam_meas_ins, cidx); UP(cam_meas_pt, cidx_pt); UP(free_cam, freecam);
+    UP(pt_meas_ins, idx_ins); UP(pt_cam, ptcam); UP(cam_off, coff); UP(cam_meas_ins, cidx); UP(cam_meas_pt, cidx_pt); UP(free_cam, freecam); UP(cam_order, camorder);
 #undef UP
     // pageable H2D copies return once staged; the handle's streams are non-blocking (no implicit ordering with
     // the legacy stream the copies ran on), so finish them before the first kernel is queued
@@ -433,7 +436,7 @@ struct ptam_bundle {
     d.cam_off = cam_off.p; d.cam_meas_ins = cam_meas_ins.p; d.cam_meas_pt = cidx_pt.empty() ? cam_meas_ins.p : cam_meas_pt.p;
     d.n_blocks = n_blocks; d.blk_off = blk_off.p;
     d.err_cam = err_cam.p; d.partials = partials.p; d.tickets = tickets.p;
-    d.nz_blocks = nz_blocks.p; d.pair_info = pair_info.p; d.free_cam = free_cam.p;
+    d.nz_blocks = nz_blocks.p; d.pair_info = pair_info.p; d.free_cam = free_cam.p; d.cam_order = cam_order.p;
     if (M > 0) {
       const int gm = (M + 255) / 256;
       if (whole) { k_ba_iota<<<gm, 256, 0, stream>>>(m_gid.p, M); launches++; }

@@ -50,6 +50,7 @@ struct BundleDev {
   // camera pairs (j > k, both free) in block order b = jf (jf - 1) / 2 + kf (jf, kf = start row / 6)
   long long n_blocks;
   const int* blk_off;   // [n_blocks + 1] triples of block b: [blk_off[b], blk_off[b + 1]), ascending point id
+  const int* cam_order; // cameras by descending measurement count (launch order of the per-camera kernels)
   const int* pr_mj;     // measurement of the point in camera j
   const int* pr_mk;     // ... and in camera k
   const int* nz_blocks; // the pairs with common points, long ones (>= kLongBlock triples) first
@@ -438,7 +439,7 @@ constexpr int kAccCamSmem = 28 * (kSegThreads + 1) * (int)sizeof(double);
 __global__ void __launch_bounds__(kSegThreads) k_ba_acc_cam(BundleDev d) {
   extern __shared__ __align__(16) double seg_sv[];
   __shared__ bool s_last;
-  const int c = blockIdx.x, t = threadIdx.x;
+  const int c = d.cam_order[blockIdx.x], t = threadIdx.x;  // longest camera first: the tail of the grid is short work
   const double sigma2 = d.scal[1];
   const bool cfree = !d.cam_fixed[c];
   const int o0 = d.cam_off[c], o1 = d.cam_off[c + 1];
@@ -560,9 +561,9 @@ __global__ void __launch_bounds__(256) k_ba_zero_lower(double* S, int n, unsigne
 // k_ba_schur_diag — CTA per camera j: S_jj = U*_j - sum_i W_ij V*_i^-1 W_ij^T,  vE_j = epsA_j - sum_i W_ij V*_i^-1 epsB_i
 // over camera j's points in POINT order (the reference scans i = 0 .. P-1, Bundle.cc:396-405).
 constexpr int kSchurDiagSmem = 27 * (kSegThreads + 1) * (int)sizeof(double);
-__global__ void __launch_bounds__(kSegThreads) k_ba_schur_diag(BundleDev d) {
+__global__ void __launch_bounds__(kSegThreads, 3) k_ba_schur_diag(BundleDev d) {
   extern __shared__ __align__(16) double seg_sv[];
-  const int c = blockIdx.x, t = threadIdx.x;
+  const int c = d.cam_order[blockIdx.x], t = threadIdx.x;  // longest camera first
   const int row = d.cam_row[c];
   if (row < 0) return;
   const double lambda = d.scal[6];
