@@ -748,9 +748,12 @@ struct ptam_bundle {
       if (world == 1) PTAM_CUDA_TRY(this, cudaMemcpyAsync(h_scal, scal.p, sizeof(double) * 8, cudaMemcpyDeviceToHost, stream));
       else PTAM_CUDA_TRY(this, cudaMemcpyAsync(h_scal + 3, scal.p + 3, sizeof(double) * 3, cudaMemcpyDeviceToHost, stream));
       if (win) PTAM_CUDA_TRY(this, cudaMemcpyAsync(h_cnt + 4, win->err, sizeof(int), cudaMemcpyDeviceToHost, stream));
+      const bool solve_flag = n > 0 && ldlt.dag_err != nullptr;
+      if (solve_flag) PTAM_CUDA_TRY(this, cudaMemcpyAsync(h_cnt + 5, ldlt.dag_err, sizeof(int), cudaMemcpyDeviceToHost, stream));
       PTAM_CUDA_TRY(this, cudaStreamSynchronize(stream));
       pcollect();
       if (win && h_cnt[4]) { set_error("peer exchange of the reduced system timed out (a rank is gone)"); return PTAM_ERR_NCCL; }
+      if (solve_flag && h_cnt[5]) { set_error("dense solve: a dependency of the persistent factorisation timed out"); return PTAM_ERR_CUDA; }
       bool step_vote = false;
       if (defer && first) {  // sigma^2 and the error sum of the LM step: what the exchange brought along / this read-back
         const double* hs = merged ? h_scal + 8 : h_scal;
