@@ -172,6 +172,12 @@ struct ptam_bundle {
   int n_meas_local = 0;
   unsigned char* arena = nullptr;
   size_t arena_cap = 0;
+  // One lambda trial of a single-GPU handle is a fixed sequence of launches and two small copies: it is captured
+  // once per handle into a CUDA graph and replayed (env PTAM_B200_NO_GRAPH=1: plain launches).
+  cudaGraphExec_t trial_exec = nullptr;
+  BundleDev trial_key{};
+  int64_t trial_launches = 0;
+  bool graph_off = false;
   // optional per-phase device timing (CUDA events on the handle's stream around each phase)
   bool profiling = false;
   cudaEvent_t prof_ev[2 * PTAM_BA_PHASES] = {};
@@ -212,6 +218,7 @@ struct ptam_bundle {
     dev_free(arena);
     dev_free(pair_buf);
     if (stream) cudaStreamSynchronize(stream);
+    if (trial_exec) cudaGraphExecDestroy(trial_exec);
     for (auto e : prof_ev) if (e) cudaEventDestroy(e);
     if (comm && own_comm) { release_window((void*)comm); nccl_api().CommDestroy(comm); }
     if (h_scal) cudaFreeHost(h_scal);
@@ -663,6 +670,65 @@ struct ptam_bundle {
     return PTAM_OK;
   }
 
+  // One lambda trial of a single-GPU handle, from the upload of its scalars (h_scal[3..6]) to the read-back of the
+  // results (h_scal[0..7], h_cnt[5]): Bundle.cc:341-506.  No host decision in between.
+  int enqueue_trial_single() {
+    int rc;
+    const int M = d.n_meas, PO = d.p_hi - d.p_lo;
+    PTAM_CUDA_TRY(this, cudaMemcpyAsync(scal.p + 3, h_scal + 3, sizeof(double) * 4, cudaMemcpyHostToDevice, stream));
+    pbegin(3);
+    if (PO > 0) { k_ba_vinv<<<(PO + 255) / 256, 256, 0, stream>>>(d); launches++; }
+    pend(3);
+    pbegin(4);
+    if ((rc = build_reduced())) return rc;
+    pend(4);
+    pbegin(6); if ((rc = solve_reduced())) return rc; pend(6);
+    pbegin(7);
+    k_ba_cam_update<<<1, 256, 0, stream>>>(d); launches++;  // first: it SETS the |delta|^2 slot, the points add to it
+    if (PO > 0) { k_ba_point_update<<<(PO + 255) / 256, 256, 0, stream>>>(d); launches++; }
+    if (M > 0) { k_ba_new_error<<<(M + 255) / 256, 256, 0, stream>>>(d); launches++; }
+    pend(7);
+    PTAM_CUDA_TRY(this, cudaGetLastError());
+    PTAM_CUDA_TRY(this, cudaMemcpyAsync(h_scal, scal.p, sizeof(double) * 8, cudaMemcpyDeviceToHost, stream));
+    if (d.n > 0 && ldlt.dag_err) PTAM_CUDA_TRY(this, cudaMemcpyAsync(h_cnt + 5, ldlt.dag_err, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    return PTAM_OK;
+  }
+
+  // The same through a CUDA graph: captured on first use (and again when the device graph of the handle changed),
+  // replayed afterwards.  Anything that cannot be captured switches the handle back to plain launches.
+  int run_trial_single() {
+    static const bool env_off = std::getenv("PTAM_B200_NO_GRAPH") != nullptr;
+    if (env_off || graph_off || profiling) return enqueue_trial_single();
+    if (!trial_exec || std::memcmp(&trial_key, &d, sizeof(BundleDev)) != 0) {
+      if (trial_exec) { cudaGraphExecDestroy(trial_exec); trial_exec = nullptr; }
+      if (d.n > 0 && ldlt.prepare(Wp.p, d.n) != cudaSuccess) { graph_off = true; cudaGetLastError(); return enqueue_trial_single(); }
+      const int64_t l0 = launches;
+      cudaGraph_t g = nullptr;
+      std::string keep = err;
+      bool ok = cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+      if (ok) {
+        const int rc = enqueue_trial_single();
+        const cudaError_t e = cudaStreamEndCapture(stream, &g);
+        ok = rc == PTAM_OK && e == cudaSuccess && g != nullptr;
+      }
+      if (ok) ok = cudaGraphInstantiate(&trial_exec, g, 0) == cudaSuccess;
+      if (g) cudaGraphDestroy(g);
+      trial_launches = launches - l0;
+      launches = l0;
+      if (!ok) {
+        cudaGetLastError();
+        err = keep;
+        if (trial_exec) { cudaGraphExecDestroy(trial_exec); trial_exec = nullptr; }
+        graph_off = true;
+        return enqueue_trial_single();
+      }
+      std::memcpy(&trial_key, &d, sizeof(BundleDev));
+    }
+    PTAM_CUDA_TRY(this, cudaGraphLaunch(trial_exec, stream));
+    launches += trial_launches;
+    return PTAM_OK;
+  }
+
   // Do_LM_Step (Bundle.cc:209-551)
   int lm_step(const volatile unsigned char* abort_flag) {
     cudaSetDevice(device);
@@ -712,6 +778,14 @@ struct ptam_bundle {
     while ((new_err > cur_err || (defer && first)) && !converged && !hit_max && !aborted()) {
       // scal[3] new error, scal[4] squared update, scal[5] abort votes, scal[6] lambda
       trial_lambda = lambda;
+      if (world == 1) {
+        h_scal[3] = 0.0; h_scal[4] = 0.0; h_scal[5] = 0.0; h_scal[6] = lambda;
+        if ((rc = run_trial_single())) return rc;
+        s_mirrored = false;
+        PTAM_CUDA_TRY(this, cudaStreamSynchronize(stream));
+        pcollect();
+        if (n > 0 && ldlt.dag_err && h_cnt[5]) { set_error("dense solve: a dependency of the persistent factorisation timed out"); return PTAM_ERR_CUDA; }
+      } else {
       if (merged && first) {  // scal[3..5] are still on their way: only the lambda goes up now
         h_scal[6] = lambda;
         PTAM_CUDA_TRY(this, cudaMemcpyAsync(scal.p + 6, h_scal + 6, sizeof(double), cudaMemcpyHostToDevice, stream));
@@ -754,6 +828,7 @@ struct ptam_bundle {
       pcollect();
       if (win && h_cnt[4]) { set_error("peer exchange of the reduced system timed out (a rank is gone)"); return PTAM_ERR_NCCL; }
       if (solve_flag && h_cnt[5]) { set_error("dense solve: a dependency of the persistent factorisation timed out"); return PTAM_ERR_CUDA; }
+      }
       bool step_vote = false;
       if (defer && first) {  // sigma^2 and the error sum of the LM step: what the exchange brought along / this read-back
         const double* hs = merged ? h_scal + 8 : h_scal;

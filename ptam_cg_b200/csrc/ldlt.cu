@@ -82,28 +82,31 @@ cudaError_t LdltSolver::solve(double* S, double* y, double* x, double* ws, int n
 // ldlt_dag.cuh; then z = D^-1 y and the backward substitution as before.  Large systems start with the per-panel
 // launch schedule: while the trailing update is what takes the time (hundreds of tiles per panel) its grids keep
 // two CTAs per SM busy; the persistent kernel takes over where the chain of panels is the limit.
-cudaError_t LdltSolver::solve_dag(double* S, double* y, double* x, double* ws, int n) {
-  if (n == 0) return cudaSuccess;
-  const int nblk = (n + kNB - 1) / kNB;
+static int dag_first_panel(int n, int nblk, int tail_tiles) {
   int k_start = 0;
   for (int k = 0; k < nblk; k++) {  // first panel whose tail is small enough
     const int rem = n - (k + 1) * kNB;
     const int nt = rem > 0 ? (rem + kUTM - 1) / kUTM : 0;
-    if (nt * nt <= dag_tail_tiles) { k_start = k; break; }
+    if (nt * nt <= tail_tiles) { k_start = k; break; }
   }
   if (k_start == 1) k_start = 2;  // the W rows of the two schedules must not overlap
   if (k_start >= nblk - 1) k_start = 0;
-  if (k_start > 0) {
-    const cudaError_t e = factor_steps(S, y, ws, n, k_start);
-    if (e != cudaSuccess) return e;
+  return k_start;
+}
+
+cudaError_t LdltSolver::prepare(double* ws, int n) {
+  if (n <= 0) return cudaSuccess;
+  const int nblk = (n + kNB - 1) / kNB;
+  if ((int)ev_panel.size() < nblk) {
+    const size_t old = ev_panel.size();
+    ev_panel.resize(nblk); ev_tail.resize(nblk); tail_of.resize(nblk, false);
+    for (size_t k = old; k < ev_panel.size(); k++) {
+      LDLT_TRY(cudaEventCreateWithFlags(&ev_panel[k], cudaEventDisableTiming));
+      LDLT_TRY(cudaEventCreateWithFlags(&ev_tail[k], cudaEventDisableTiming));
+    }
   }
-  LdltDagArgs a;
-  a.A = S; a.y = y; a.n = n; a.nblk = nblk; a.k_start = k_start;
-  a.W = ws;
-  a.gd = ws + (size_t)std::max(nblk, 2) * n * kNB;
-  a.flags = reinterpret_cast<int*>(a.gd + ((n + 1) & ~1));
-  int* task_off = a.flags + dag_flag_ints(nblk);
-  a.task_off = task_off;
+  if (!use_dag) return cudaSuccess;
+  const int k_start = dag_first_panel(n, nblk, dag_tail_tiles);
   if (dag_n != n || dag_ws != ws || dag_k_start != k_start) {
     // round k (k >= k_start): D(., k), tiles of column k+2, RU(., k+1), the other tiles of panel k; before them RU(., k_start)
     dag_off.assign(nblk + 1, 0);
@@ -113,10 +116,34 @@ cudaError_t LdltSolver::solve_dag(double* S, double* y, double* x, double* ws, i
       const int nt1 = std::max(0, (r0 < n ? (n - r0 + kUTM - 1) / kUTM : 0) - 1);
       dag_off[k + 1] = dag_off[k] + std::max(0, nblk - k - 2) + nt1 + std::max(0, nblk - k - 3) + nt1 * nt1;
     }
+    double* gd = ws + (size_t)std::max(nblk, 2) * n * kNB;
+    int* task_off = reinterpret_cast<int*>(gd + ((n + 1) & ~1)) + dag_flag_ints(nblk);
     LDLT_TRY(cudaMemcpyAsync(task_off, dag_off.data(), sizeof(int) * (nblk + 1), cudaMemcpyHostToDevice, stream));
-    dag_n = n; dag_ws = ws; dag_k_start = k_start;
+    LDLT_TRY(cudaStreamSynchronize(stream));  // the source is pageable
+    dag_n = n; dag_ws = ws; dag_k_start = k_start; dag_tasks = dag_off[nblk];
   }
-  a.n_tasks = dag_off[nblk];
+  return cudaSuccess;
+}
+
+cudaError_t LdltSolver::solve_dag(double* S, double* y, double* x, double* ws, int n) {
+  if (n == 0) return cudaSuccess;
+  const int nblk = (n + kNB - 1) / kNB;
+  const int k_start = dag_first_panel(n, nblk, dag_tail_tiles);
+  {
+    const cudaError_t e = prepare(ws, n);
+    if (e != cudaSuccess) return e;
+  }
+  if (k_start > 0) {
+    const cudaError_t e = factor_steps(S, y, ws, n, k_start);
+    if (e != cudaSuccess) return e;
+  }
+  LdltDagArgs a;
+  a.A = S; a.y = y; a.n = n; a.nblk = nblk; a.k_start = k_start;
+  a.W = ws;
+  a.gd = ws + (size_t)std::max(nblk, 2) * n * kNB;
+  a.flags = reinterpret_cast<int*>(a.gd + ((n + 1) & ~1));
+  a.task_off = a.flags + dag_flag_ints(nblk);
+  a.n_tasks = dag_tasks;
   dag_err = a.flags + kDagErr;
   const int n_flags = dag_flag_ints(nblk);
   k_ldlt_dag_init<<<(n_flags + 255) / 256, 256, 0, stream>>>(a.flags, n_flags, k_start);

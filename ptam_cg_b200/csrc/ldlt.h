@@ -24,7 +24,7 @@ struct LdltSolver {
   // the factorisation as one persistent launch (ldlt_dag.cuh); off: one launch per panel (PTAM_B200_LDLT_STEPS=1)
   bool use_dag = true;
   int dag_max_ctas = 0;             // CTAs of k_ldlt_dag that are resident at once (cooperative launch)
-  int dag_n = -1, dag_k_start = -1; // the system the task table in the workspace was written for
+  int dag_n = -1, dag_k_start = -1, dag_tasks = 0; // the system the task table in the workspace was written for
   int dag_tail_tiles = 120;         // panels whose tail has more 128x64 tiles than this keep the per-panel schedule
   const double* dag_ws = nullptr;
   std::vector<int> dag_off;
@@ -36,6 +36,9 @@ struct LdltSolver {
   // Solves S x = y for the symmetric S (n x n row-major, LOWER triangle read, overwritten by the L / D
   // factors) with y consumed in place.  A non-positive-definite S yields inf / NaN as in the reference.
   cudaError_t solve(double* S, double* y, double* x, double* workspace, int n);
+  // Everything solve() would do only once for this (workspace, n) -- the upload of the task table, the events of the
+  // per-panel schedule -- so that the solve itself is nothing but launches (it can then be captured into a CUDA graph).
+  cudaError_t prepare(double* workspace, int n);
   cudaError_t solve_steps(double* S, double* y, double* x, double* workspace, int n);
   cudaError_t solve_dag(double* S, double* y, double* x, double* workspace, int n);
   cudaError_t factor_steps(double* S, double* y, double* workspace, int n, int k_end);
