@@ -137,7 +137,7 @@ def bench_ba(prod, device=0, config="C3", reps=3, cpu_lib=None, shard=None, grap
     if sol[1]:
         ach = flops_per_trial(n) / (sol[0] / sol[1] * 1e-3) / 1e12
         out["solve_gflops"] = ach * 1e3
-        rl["solve"] = {"kernels": "k_ldlt_panel/_step/_update/_back (blocked LDL^T, DMMA m8n8k4 trailing update)", "bound": "tensor_f64",
+        rl["solve"] = {"kernels": "k_ldlt_dag (persistent blocked LDL^T: chain CTA + row-solve / diagonal / DMMA m8n8k4 tile tasks; k_ldlt_step/_update for the tile-bound head of large systems) + k_ldlt_scale/_back", "bound": "tensor_f64",
                        "flops_per_launch_group": flops_per_trial(n), "ms": sol[0] / sol[1], "achieved": ach, "peak": peak64,
                        "unit": "TFLOP/s", "frac": ach / peak64, "peak_source": src64}
     if jac[1]:  # b3 + b5: 320 B per measurement per LM step over the projection + Jacobian phases
