@@ -386,6 +386,12 @@ int ptam_bundle_get_reduced_system(ptam_bundle* b, double* S, double* vE, int ca
 int ptam_bundle_synchronize(ptam_bundle* b);
 void* ptam_bundle_cuda_stream(ptam_bundle* b);
 int64_t ptam_bundle_launch_count(const ptam_bundle* b);
+/* Task table of the persistent dense solve (reference: Cholesky<>(mS).backsub(vE), Bundle.cc:457-458) for an n x n
+ * reduced system: *k_start = first panel of the persistent kernel (the panels before it run one launch each),
+ * task_off[k], k = *k_start .. n_panels: first ticket of round k (see csrc/ldlt_dag.cuh).  Host arithmetic only, no
+ * device is touched; for tests of the task order.  Returns the number of 64-wide panels, or a negative PTAM_ERR_*
+ * when `cap` is smaller than panels + 1. */
+int ptam_bundle_solve_schedule(int n, int tail_tiles, int* k_start, int32_t* task_off, int cap);
 /* Per-phase device timing (CUDA events on the handle's stream).  Phase ids: 0 project (Bundle.cc:219-225),
  * 1 sigma-squared select (:230-237), 2 Jacobian/accumulate (:251-332), 3 V*^-1 + S/vE init (:341-392),
  * 4 Schur build (:396-446), 5 cross-shard all-reduce of S/vE, 6 dense LDL^T solve (:457-458),

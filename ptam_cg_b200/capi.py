@@ -90,7 +90,7 @@ BUNDLE_SYMBOLS = [
 PRODUCT_ONLY_SYMBOLS = [
     "global_last_error", "tracker_track_frames_device", "tracker_submit_frames", "tracker_submit_frames_device", "tracker_collect", "tracker_cuda_stream",
     "tracker_launch_count", "tracker_set_profiling", "tracker_get_kernel_times",
-    "bundle_cuda_stream", "bundle_launch_count",
+    "bundle_cuda_stream", "bundle_launch_count", "bundle_solve_schedule",
     "nccl_unique_id", "nccl_comm_create", "nccl_comm_destroy", "bundle_init_shard", "bundle_shard_plan",
     "bundle_set_profiling", "bundle_get_phase_times",
 ]

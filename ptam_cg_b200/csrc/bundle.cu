@@ -1229,4 +1229,14 @@ int ptam_debug_read(long long* out) { cudaDeviceSynchronize(); return (int)cudaM
 void* ptam_bundle_cuda_stream(ptam_bundle* b) { return (void*)b->stream; }
 int64_t ptam_bundle_launch_count(const ptam_bundle* b) { return b->launches; }
 
+int ptam_bundle_solve_schedule(int n, int tail_tiles, int* k_start, int32_t* task_off, int cap) {
+  if (n < 0 || !k_start || !task_off) return PTAM_ERR_INVALID;
+  std::vector<int> off;
+  const int ks = ldlt_dag_schedule(n, tail_tiles, off);
+  if ((int)off.size() > cap) return PTAM_ERR_INVALID;
+  *k_start = ks;
+  for (size_t i = 0; i < off.size(); i++) task_off[i] = off[i];
+  return (int)off.size() - 1;
+}
+
 }  // extern "C"

@@ -94,6 +94,20 @@ static int dag_first_panel(int n, int nblk, int tail_tiles) {
   return k_start;
 }
 
+int ldlt_dag_schedule(int n, int tail_tiles, std::vector<int>& off) {
+  const int nblk = (n + kNB - 1) / kNB;
+  const int k_start = dag_first_panel(n, nblk, tail_tiles);
+  // round k (k >= k_start): D(., k), tiles of column k+2, RU(., k+1), the other tiles of panel k; before them RU(., k_start)
+  off.assign(nblk + 1, 0);
+  off[k_start] = std::max(0, nblk - k_start - 2);
+  for (int k = k_start; k < nblk; k++) {
+    const int r0 = (k + 1) * kNB;
+    const int nt1 = std::max(0, (r0 < n ? (n - r0 + kUTM - 1) / kUTM : 0) - 1);
+    off[k + 1] = off[k] + std::max(0, nblk - k - 2) + nt1 + std::max(0, nblk - k - 3) + nt1 * nt1;
+  }
+  return k_start;
+}
+
 cudaError_t LdltSolver::prepare(double* ws, int n) {
   if (n <= 0) return cudaSuccess;
   const int nblk = (n + kNB - 1) / kNB;
@@ -108,14 +122,7 @@ cudaError_t LdltSolver::prepare(double* ws, int n) {
   if (!use_dag) return cudaSuccess;
   const int k_start = dag_first_panel(n, nblk, dag_tail_tiles);
   if (dag_n != n || dag_ws != ws || dag_k_start != k_start) {
-    // round k (k >= k_start): D(., k), tiles of column k+2, RU(., k+1), the other tiles of panel k; before them RU(., k_start)
-    dag_off.assign(nblk + 1, 0);
-    dag_off[k_start] = std::max(0, nblk - k_start - 2);
-    for (int k = k_start; k < nblk; k++) {
-      const int r0 = (k + 1) * kNB;
-      const int nt1 = std::max(0, (r0 < n ? (n - r0 + kUTM - 1) / kUTM : 0) - 1);
-      dag_off[k + 1] = dag_off[k] + std::max(0, nblk - k - 2) + nt1 + std::max(0, nblk - k - 3) + nt1 * nt1;
-    }
+    ldlt_dag_schedule(n, dag_tail_tiles, dag_off);
     double* gd = ws + (size_t)std::max(nblk, 2) * n * kNB;
     int* task_off = reinterpret_cast<int*>(gd + ((n + 1) & ~1)) + dag_flag_ints(nblk);
     LDLT_TRY(cudaMemcpyAsync(task_off, dag_off.data(), sizeof(int) * (nblk + 1), cudaMemcpyHostToDevice, stream));

@@ -14,6 +14,10 @@ namespace ptam {
 // reciprocals of D, the dependency flags and the task table of the persistent factorisation.
 size_t ldlt_workspace_doubles(int n);
 
+// Task table of the persistent factorisation (ldlt_dag.cuh): first panel of the persistent kernel and, from it on,
+// the first ticket of every round.  Pure host arithmetic.
+int ldlt_dag_schedule(int n, int tail_tiles, std::vector<int>& task_off);
+
 struct LdltSolver {
   cudaStream_t stream = nullptr, stream2 = nullptr;  // stream: the caller's; stream2: the solver's own
   std::vector<cudaEvent_t> ev_panel, ev_tail;
