@@ -396,7 +396,7 @@ struct ptam_bundle {
       AL(Vinv, 9 * (size_t)P); AL(Ve, 3 * (size_t)P); AL(pt_off, P + 1); AL(pt_meas, M);
       AL(pt_meas_ins, idx_ins.empty() ? 0 : M); AL(pt_cam, M); AL(cam_off, C + 1); AL(cam_meas_ins, M);
       AL(cam_meas_pt, cidx_pt.empty() ? 0 : M); AL(blk_off, n_blocks + 1); AL(blk_cnt, n_blocks); AL(nz_blocks, n_blocks); AL(pair_info, 4); AL(free_cam, n_free); AL(cam_order, C); AL(csr_cur, P + 1); AL(csr_pairs, 1);
-      AL(m_B, 6 * (size_t)M); AL(err_cam, C); AL(partials, grid_max); AL(tickets, 4);
+      AL(m_B, 6 * (size_t)M); AL(err_cam, C); AL(partials, grid_max); AL(tickets, 8);
       AL(m_cam, M); AL(m_pt, M); AL(m_found, 2 * (size_t)M); AL(m_sin, M); AL(m_state, M); AL(m_v3cam, 3 * (size_t)M);
       AL(m_derivs, 4 * (size_t)M); AL(m_eps, 2 * (size_t)M); AL(m_e2, M); AL(m_W, 18 * (size_t)M); AL(e2c, M);
       AL(S, win ? 0 : (size_t)n * n); AL(vE, win ? 0 : n); AL(upd, n); AL(scal, 8); AL(counters, 4); AL(outliers, 2 * (size_t)M);
@@ -661,10 +661,8 @@ struct ptam_bundle {
                         "all-gather of the squared errors");
       if (rc) return rc;
     }
-    for (int pass = 0; pass < kSelPasses; pass++) {
-      PTAM_CUDA_TRY(this, cudaMemsetAsync(hist16.p, 0, sizeof(int) * kSelBins, stream));
-      if (n_keys > 0) { k_ba_hist<<<std::min((n_keys + 255) / 256, 148 * 8), 256, 0, stream>>>(d, pass); launches++; }
-      k_ba_pick<<<1, 1024, 0, stream>>>(d, pass, min_s2);
+    for (int pass = 0; pass < kSelPasses; pass++) {  // the histogram starts zeroed (begin) and every pass leaves it so
+      k_ba_hist_pick<<<std::max(1, std::min((n_keys + 255) / 256, 148 * 8)), 256, 0, stream>>>(d, pass, min_s2);
       launches++;
     }
     return PTAM_OK;

@@ -85,7 +85,7 @@ struct BundleDev {
   // deterministic grid-wide sums
   double* err_cam;    // [C] each camera's share of the current robust error
   double* partials;   // [max grid] per-block partial sums of the kernel in flight
-  unsigned* tickets;  // [4] arrival counters (self-resetting)
+  unsigned* tickets;  // [8] arrival counters (self-resetting)
 };
 
 PTAM_DEV double block_sum(double v, double* sh /*32*/) {
@@ -188,19 +188,23 @@ __global__ void __launch_bounds__(1024) k_ba_select(BundleDev d, double min_sigm
 
 // ---------------------------------------------------------------------------------------------
 // Exact order statistic for large or sharded problems: MSB-first radix select over the IEEE bit
-// patterns, six passes with digit widths 11,11,11,11,11,9.  Every pass: k_ba_hist (all CTAs: digits
-// aggregated per warp with match.any, per-CTA histogram in shared memory, non-zero bins flushed with
-// global atomics) -> [all-reduce of the 2048 bins across shards] -> k_ba_pick (one CTA finds the bin
-// holding the wanted rank).  After the last pass the prefix IS the bit pattern of the floor(n/2)-th
-// smallest squared error (Tools.h:152-162 sorts and takes element n/2), identical on every shard.
+// patterns, six passes with digit widths 11,11,11,11,11,9.  Every pass is ONE launch, k_ba_hist_pick: all CTAs
+// add their digits (aggregated per warp with match.any, per-CTA histogram in shared memory, non-zero bins flushed
+// with global atomics); the last CTA to arrive finds the bin holding the wanted rank, extends the prefix and
+// leaves the histogram zeroed for the next pass (three launches per pass before: memset, histogram, pick).
+// Sharded handles run the same passes on the all-gathered keys of every shard.  After the last pass the prefix IS
+// the bit pattern of the floor(n/2)-th smallest squared error (Tools.h:152-162 sorts and takes element n/2),
+// identical on every shard.
 // ---------------------------------------------------------------------------------------------
 constexpr int kSelPasses = 6;
 constexpr int kSelBins = 2048;
 PTAM_HD int sel_shift(int pass) { return pass < 5 ? 53 - 11 * pass : 0; }
 PTAM_HD int sel_width(int pass) { return pass < 5 ? 11 : 9; }
 
-__global__ void __launch_bounds__(256) k_ba_hist(BundleDev d, int pass) {
+__global__ void __launch_bounds__(256) k_ba_hist_pick(BundleDev d, int pass, double min_sigma_sq) {
   __shared__ int h[kSelBins];
+  __shared__ int wsum[8];
+  __shared__ bool s_last;
   for (int i = threadIdx.x; i < kSelBins; i += blockDim.x) h[i] = 0;
   __syncthreads();
   const int shift = sel_shift(pass), width = sel_width(pass);
@@ -229,6 +233,59 @@ __global__ void __launch_bounds__(256) k_ba_hist(BundleDev d, int pass) {
   __syncthreads();
   for (int i = threadIdx.x; i < kSelBins; i += blockDim.x)
     if (h[i]) atomicAdd(&d.hist16[i], h[i]);
+  // ---- the last CTA to arrive picks the bin of the k-th key (the counter wraps to zero for the next pass)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicInc(d.tickets + 4, gridDim.x - 1) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int t = threadIdx.x, warp = t >> 5;
+  constexpr int kPer = kSelBins / 256;
+  int c[kPer], tot = 0;
+#pragma unroll
+  for (int q = 0; q < kPer; q++) { c[q] = __ldcg(&d.hist16[kPer * t + q]); tot += c[q]; }
+#pragma unroll
+  for (int q = 0; q < kPer; q++) d.hist16[kPer * t + q] = 0;  // the next pass (and the next LM step) start from zero
+  int inc = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(kFull, inc, o);
+    if (lane >= o) inc += v;
+  }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  int before = 0, n_all = 0;
+#pragma unroll
+  for (int w = 0; w < 8; w++) { if (w < warp) before += wsum[w]; n_all += wsum[w]; }
+  // pass 0: n_all = number of valid measurements over all shards
+  const long long kk = pass == 0 ? (long long)(n_all / 2) : (long long)d.sel_state[1];
+  const int excl = before + inc - tot;
+  if (n_all > 0 && kk >= excl && kk < excl + tot) {  // exactly one thread
+    int r = (int)(kk - excl), q = 0;
+    while (r >= c[q]) { r -= c[q]; q++; }
+    const unsigned long long prefix2 = (pass == 0 ? 0ull : prefix) | ((unsigned long long)(kPer * t + q) << shift);
+    d.sel_state[0] = prefix2;
+    d.sel_state[1] = (unsigned long long)r;
+    if (pass == kSelPasses - 1) {
+      const double med = __longlong_as_double((long long)prefix2);
+      const long long n = (long long)d.scal[0];
+      double s2 = mest_sigma_from_median(med, n, d.est);
+      if (s2 < min_sigma_sq) s2 = min_sigma_sq;
+      d.scal[7] = med;
+      d.scal[1] = s2;
+    }
+  }
+  if (pass == 0 && t == 0) {
+    d.scal[0] = (double)n_all;
+    d.counters[0] = n_all;
+    if (n_all == 0) {  // no valid measurement anywhere: same result as the single-CTA select on n = 0
+      double s2 = mest_sigma_from_median(0.0, 0, d.est);
+      if (s2 < min_sigma_sq) s2 = min_sigma_sq;
+      d.scal[7] = 0.0; d.scal[1] = s2;
+      d.sel_state[0] = 0ull; d.sel_state[1] = 0ull;
+    }
+  }
 }
 
 // Sharded handles: this shard's squared errors into its slot of the all-gather buffer (erased / outlier
@@ -269,61 +326,6 @@ __global__ void __launch_bounds__(256) k_ba_unpack_lower(const double* in, int n
   }
 }
 
-__global__ void __launch_bounds__(1024) k_ba_pick(BundleDev d, int pass, double min_sigma_sq) {
-  __shared__ int wsum[32];
-  __shared__ int total_s;
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int shift = sel_shift(pass);
-  const int c0 = d.hist16[2 * t], c1 = d.hist16[2 * t + 1];
-  const int tot = c0 + c1;
-  int inc = tot;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(kFull, inc, o);
-    if (lane >= o) inc += v;
-  }
-  if (lane == 31) wsum[warp] = inc;
-  __syncthreads();
-  if (warp == 0) {
-    int ws = wsum[lane];
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(kFull, ws, o);
-      if (lane >= o) ws += v;
-    }
-    wsum[lane] = ws;
-    if (lane == 31) total_s = ws;
-  }
-  __syncthreads();
-  const int n_all = total_s;  // pass 0: number of valid measurements over all shards
-  const long long kk = pass == 0 ? (long long)(n_all / 2) : (long long)d.sel_state[1];
-  const int excl = (warp ? wsum[warp - 1] : 0) + inc - tot;
-  if (n_all > 0 && kk >= excl && kk < excl + tot) {  // exactly one thread
-    int r = (int)(kk - excl), q = 0;
-    if (r >= c0) { r -= c0; q = 1; }
-    const unsigned long long prefix = (pass == 0 ? 0ull : d.sel_state[0]) | ((unsigned long long)(2 * t + q) << shift);
-    d.sel_state[0] = prefix;
-    d.sel_state[1] = (unsigned long long)r;
-    if (pass == kSelPasses - 1) {
-      const double med = __longlong_as_double((long long)prefix);
-      const long long n = (long long)d.scal[0];
-      double s2 = mest_sigma_from_median(med, n, d.est);
-      if (s2 < min_sigma_sq) s2 = min_sigma_sq;
-      d.scal[7] = med;
-      d.scal[1] = s2;
-    }
-  }
-  if (pass == 0 && t == 0) {
-    d.scal[0] = (double)n_all;
-    d.counters[0] = n_all;
-    if (n_all == 0) {  // no valid measurement anywhere: same result as the single-CTA select on n = 0
-      double s2 = mest_sigma_from_median(0.0, 0, d.est);
-      if (s2 < min_sigma_sq) s2 = min_sigma_sq;
-      d.scal[7] = 0.0; d.scal[1] = s2;
-      d.sel_state[0] = 0ull; d.sel_state[1] = 0ull;
-    }
-  }
-}
 
 // ---------------------------------------------------------------------------------------------
 // Deterministic accumulation.  Every sum of the reference that runs over measurements is taken IN THE

@@ -6,7 +6,7 @@
     sum of per-shard partial (S, vE) equals the oracle's full system;
   * the distributed order statistic: a multi-pass MSB radix select whose digit histograms are
     all-reduced finds the exact floor(n/2)-th smallest of the union of the shards' errors (the
-    protocol k_ba_hist / k_ba_pick run on the device).
+    protocol k_ba_hist_pick run on the device).
 The 2-GPU NCCL run of the same path is tests/test_bundle_sharded_gpu.py.
 """
 import os
@@ -40,7 +40,7 @@ def _radix_select_allreduce(local_vals, k_of_n):
     """exact k-th smallest of the union of all ranks' non-negative doubles; k_of_n(n) -> k."""
     keys = np.ascontiguousarray(local_vals, np.float64).view(np.uint64)
     prefix, k = np.uint64(0), None
-    for p in range(6):  # digit widths 11,11,11,11,11,9 as in k_ba_hist / k_ba_pick
+    for p in range(6):  # digit widths 11,11,11,11,11,9 as in k_ba_hist_pick
         shift = np.uint64(53 - 11 * p if p < 5 else 0)
         width = np.uint64(11 if p < 5 else 9)
         sel = keys if p == 0 else keys[(keys >> (shift + width)) == (prefix >> (shift + width))]
