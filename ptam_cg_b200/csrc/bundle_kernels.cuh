@@ -340,7 +340,11 @@ __global__ void __launch_bounds__(256) k_ba_unpack_lower(const double* in, int n
 // ways), then lane v adds value v of the 32 items one after the other.  Items that contribute nothing
 // (erased / outlier measurements, the tail of the last chunk) stage +0.0, which leaves a sum unchanged.
 // ---------------------------------------------------------------------------------------------
-constexpr int kSegThreads = 256;  // items per round of the per-camera segment kernels (CTA per camera)
+// Items per round of the per-camera segment kernels (CTA per camera).  The sums of a camera are taken in order by
+// ONE thread per value, so the longest camera (3 778 measurements at C4) is the critical path: with 512 items per
+// round its rounds halve while a round's staging, which is latency, takes as long as with 256 (k_ba_acc_cam
+// 70 -> 54 us, k_ba_schur_diag 115 -> 86 us at C4; one CTA per SM then, which is what the shared memory allows).
+constexpr int kSegThreads = 512;
 constexpr int kOffThreads = 128;  // ... of the per-camera-pair kernel
 constexpr int kLongBlock = 512;   // camera pairs with at least this many common points are scheduled first
 
@@ -568,7 +572,7 @@ __global__ void __launch_bounds__(256) k_ba_zero_lower(double* S, int n, unsigne
 // k_ba_schur_diag — CTA per camera j: S_jj = U*_j - sum_i W_ij V*_i^-1 W_ij^T,  vE_j = epsA_j - sum_i W_ij V*_i^-1 epsB_i
 // over camera j's points in POINT order (the reference scans i = 0 .. P-1, Bundle.cc:396-405).
 constexpr int kSchurDiagSmem = 27 * (kSegThreads + 1) * (int)sizeof(double);
-__global__ void __launch_bounds__(kSegThreads, 3) k_ba_schur_diag(BundleDev d) {
+__global__ void __launch_bounds__(kSegThreads, 1) k_ba_schur_diag(BundleDev d) {
   extern __shared__ __align__(16) double seg_sv[];
   const int c = d.cam_order[blockIdx.x], t = threadIdx.x;  // longest camera first
   const int row = d.cam_row[c];
