@@ -367,6 +367,21 @@ PTAM_DEV void grid_sum_finish(double t, double* partials, unsigned* ticket, doub
   }
 }
 
+// 16-byte accesses to the per-measurement records (W 144 B, B 48 B, derivatives 32 B, eps 16 B per measurement: all
+// multiples of 16 from 256-byte aligned arrays): half the memory instructions of the latency-bound passes.
+template <int N>
+PTAM_DEV void ld_pairs(const double* p, double (&v)[N]) {
+  static_assert(N % 2 == 0, "pairs");
+#pragma unroll
+  for (int q = 0; q < N; q += 2) { const double2 t = *reinterpret_cast<const double2*>(p + q); v[q] = t.x; v[q + 1] = t.y; }
+}
+template <int N>
+PTAM_DEV void st_pairs(double* p, const double (&v)[N]) {
+  static_assert(N % 2 == 0, "pairs");
+#pragma unroll
+  for (int q = 0; q < N; q += 2) *reinterpret_cast<double2*>(p + q) = make_double2(v[q], v[q + 1]);
+}
+
 // One round of a segment sum: thread t has staged the NV terms of item t at sv[q * (R + 1) + t] (value-major,
 // pitch R + 1: conflict-free both ways; zeros when the item contributes nothing); thread v < NV then adds (or
 // subtracts) value v of the round's `cnt` items one after the other.
@@ -406,13 +421,18 @@ __global__ void __launch_bounds__(128) k_ba_jacobian(BundleDev d) {
   const double sigma2 = d.scal[1];
   const double e2 = d.m_e2[m];
   const double w = mest_sqrt_weight(e2, sigma2, d.est);
-  const double eps0 = w * d.m_eps[2 * m], eps1 = w * d.m_eps[2 * m + 1];
-  d.m_eps[2 * m] = eps0; d.m_eps[2 * m + 1] = eps1;
+  double ep[2];
+  ld_pairs(d.m_eps + 2 * (size_t)m, ep);
+  const double eps0 = w * ep[0], eps1 = w * ep[1];
+  ep[0] = eps0; ep[1] = eps1;
+  st_pairs(d.m_eps + 2 * (size_t)m, ep);
   if (w == 0) { d.m_state[m] = M_BAD; return; }
   const int c = d.m_cam[m];
   const double s = d.m_sin[m];
-  const double d0 = s * (w * d.m_derivs[4 * m]), d1 = s * (w * d.m_derivs[4 * m + 1]);
-  const double d2 = s * (w * d.m_derivs[4 * m + 2]), d3 = s * (w * d.m_derivs[4 * m + 3]);
+  double dv[4];
+  ld_pairs(d.m_derivs + 4 * (size_t)m, dv);
+  const double d0 = s * (w * dv[0]), d1 = s * (w * dv[1]);
+  const double d2 = s * (w * dv[2]), d3 = s * (w * dv[3]);
   const double X = d.m_v3cam[3 * m], Y = d.m_v3cam[3 * m + 1], Z = d.m_v3cam[3 * m + 2];
   const double ooz = 1.0 / Z;
   double A[12];
@@ -428,14 +448,13 @@ __global__ void __launch_bounds__(128) k_ba_jacobian(BundleDev d) {
     B[q] = d0 * a0 + d1 * a1;
     B[3 + q] = d2 * a0 + d3 * a1;
   }
-  double* Bm = d.m_B + 6 * (size_t)m;
-#pragma unroll
-  for (int q = 0; q < 6; q++) Bm[q] = B[q];
-  double* Wm = d.m_W + 18 * (size_t)m;  // W = A^T B (6x3), zero for a fixed camera
+  st_pairs(d.m_B + 6 * (size_t)m, B);
+  double W[18];  // W = A^T B (6x3), zero for a fixed camera
 #pragma unroll
   for (int r = 0; r < 6; r++)
 #pragma unroll
-    for (int cc = 0; cc < 3; cc++) Wm[3 * r + cc] = A[r] * B[cc] + A[6 + r] * B[3 + cc];
+    for (int cc = 0; cc < 3; cc++) W[3 * r + cc] = A[r] * B[cc] + A[6 + r] * B[3 + cc];
+  st_pairs(d.m_W + 18 * (size_t)m, W);
 }
 
 // k_ba_acc_cam — CTA per camera, its measurements in list order: U_j (lower, packed 21), epsA_j (6) and the
@@ -472,12 +491,16 @@ __global__ void __launch_bounds__(kSegThreads) k_ba_acc_cam(BundleDev d) {
           filled = true;
           const double w = mest_sqrt_weight(e2, sigma2, d.est);
           const double s = d.m_sin[m];
-          const double d0 = s * (w * d.m_derivs[4 * m]), d1 = s * (w * d.m_derivs[4 * m + 1]);
-          const double d2 = s * (w * d.m_derivs[4 * m + 2]), d3 = s * (w * d.m_derivs[4 * m + 3]);
+          double dv[4];
+          ld_pairs(d.m_derivs + 4 * (size_t)m, dv);
+          const double d0 = s * (w * dv[0]), d1 = s * (w * dv[1]);
+          const double d2 = s * (w * dv[2]), d3 = s * (w * dv[3]);
           const double X = d.m_v3cam[3 * m], Y = d.m_v3cam[3 * m + 1], Z = d.m_v3cam[3 * m + 2];
           double A[12];
           ba_cam_jacobian(X, Y, Z, 1.0 / Z, d0, d1, d2, d3, A);
-          const double eps0 = d.m_eps[2 * m], eps1 = d.m_eps[2 * m + 1];  // already weighted
+          double ep[2];
+          ld_pairs(d.m_eps + 2 * (size_t)m, ep);
+          const double eps0 = ep[0], eps1 = ep[1];  // already weighted
           int q = 0;
 #pragma unroll
           for (int r = 0; r < 6; r++)
@@ -520,9 +543,11 @@ __global__ void __launch_bounds__(256) k_ba_acc_pt(BundleDev d) {
   for (int o = d.pt_off[i]; o < d.pt_off[i + 1]; o++) {
     const int m = d.pt_meas_ins[o];
     if (d.m_state[m] != M_ALIVE) continue;
-    const double* B = d.m_B + 6 * (size_t)m;
+    double B[6], ep[2];
+    ld_pairs(d.m_B + 6 * (size_t)m, B);
+    ld_pairs(d.m_eps + 2 * (size_t)m, ep);
     const double b0 = B[0], b1 = B[1], b2 = B[2], b3 = B[3], b4 = B[4], b5 = B[5];
-    const double eps0 = d.m_eps[2 * m], eps1 = d.m_eps[2 * m + 1];
+    const double eps0 = ep[0], eps1 = ep[1];
     V[0] += b0 * b0 + b3 * b3;
     V[1] += b1 * b0 + b4 * b3;
     V[2] += b1 * b1 + b4 * b4;
@@ -596,10 +621,8 @@ __global__ void __launch_bounds__(kSegThreads, 1) k_ba_schur_diag(BundleDev d) {
         const int i = d.m_pt[m];
         const double* Vi = d.Vinv + 9 * (size_t)i;
         const double* ve = d.Ve + 3 * (size_t)i;
-        const double* W = d.m_W + 18 * (size_t)m;
         double Wr[18], WV[18];
-#pragma unroll
-        for (int q = 0; q < 18; q++) Wr[q] = W[q];
+        ld_pairs(d.m_W + 18 * (size_t)m, Wr);
 #pragma unroll
         for (int r = 0; r < 6; r++)
 #pragma unroll
@@ -665,7 +688,8 @@ __global__ void __launch_bounds__(kOffThreads) k_ba_schur_off(BundleDev d) {
           // (W_ij V*_i^-1 kept from k_ba_schur_diag instead of recomputed here was tried: a second 18-double array
           // per measurement pushes the working set of the pairs out of the L2, 219 -> 367 us at C4)
           const double* Vi = d.Vinv + 9 * (size_t)d.m_pt[mj];
-          const double* Wj = d.m_W + 18 * (size_t)mj;
+          double Wj[18];
+          ld_pairs(d.m_W + 18 * (size_t)mj, Wj);
           const double* Wk = d.m_W + 18 * (size_t)mk;
           double WV[18];
 #pragma unroll
@@ -673,8 +697,7 @@ __global__ void __launch_bounds__(kOffThreads) k_ba_schur_off(BundleDev d) {
 #pragma unroll
             for (int cc = 0; cc < 3; cc++) WV[3 * r + cc] = Wj[3 * r] * Vi[cc] + Wj[3 * r + 1] * Vi[3 + cc] + Wj[3 * r + 2] * Vi[6 + cc];
           double wk[18];
-#pragma unroll
-          for (int q = 0; q < 18; q++) wk[q] = Wk[q];
+          ld_pairs(Wk, wk);
 #pragma unroll
           for (int r = 0; r < 6; r++)
 #pragma unroll
@@ -954,7 +977,8 @@ __global__ void __launch_bounds__(256) k_ba_point_update(BundleDev d) {
       if (d.m_state[m] != M_ALIVE) continue;
       const int row = d.cam_row[d.m_cam[m]];
       if (row < 0) continue;
-      const double* W = d.m_W + 18 * m;
+      double W[18];
+      ld_pairs(d.m_W + 18 * (size_t)m, W);
 #pragma unroll
       for (int r = 0; r < 3; r++) {
         double a = 0;
