@@ -142,7 +142,7 @@ struct ptam_bundle {
   bool s_mirrored = false;
   // device
   BundleDev d{};
-  Buf<double> cam_se3, cam_se3_new, U, epsA, pt_pos, pt_pos_new, V, epsB, Vinv, Ve, m_found, m_sin, m_v3cam, m_derivs,
+  Buf<double> cam_se3, cam_se3_new, U, epsA, pt_pos, pt_pos_new, V, epsB, Vinv, m_found, m_sin, m_v3cam, m_derivs,
       m_eps, m_e2, m_W, m_B, e2c, S, vE, upd, scal, Wp, err_cam, partials;
   Buf<int> cam_fixed, cam_row, pt_off, pt_meas, pt_meas_ins, pt_cam, cam_off, cam_meas_ins, cam_meas_pt, blk_off, blk_cnt, nz_blocks, pair_info, free_cam,
       m_cam, m_pt, m_state, counters, outliers;
@@ -393,11 +393,11 @@ struct ptam_bundle {
       AL(cam_se3, 12 * (size_t)C); AL(cam_se3_new, 12 * (size_t)C); AL(U, 21 * (size_t)C); AL(epsA, 6 * (size_t)C);
       AL(cam_fixed, C); AL(cam_row, C);
       AL(pt_pos, 3 * (size_t)P); AL(pt_pos_new, 3 * (size_t)P); AL(V, 6 * (size_t)P); AL(epsB, 3 * (size_t)P);
-      AL(Vinv, 9 * (size_t)P); AL(Ve, 3 * (size_t)P); AL(pt_off, P + 1); AL(pt_meas, M);
+      AL(Vinv, 12 * (size_t)P); AL(pt_off, P + 1); AL(pt_meas, M);
       AL(pt_meas_ins, idx_ins.empty() ? 0 : M); AL(pt_cam, M); AL(cam_off, C + 1); AL(cam_meas_ins, M);
       AL(cam_meas_pt, cidx_pt.empty() ? 0 : M); AL(blk_off, n_blocks + 1); AL(blk_cnt, n_blocks); AL(nz_blocks, n_blocks); AL(pair_info, 4); AL(free_cam, n_free); AL(cam_order, C); AL(csr_cur, P + 1); AL(csr_pairs, 1);
       AL(m_B, 6 * (size_t)M); AL(err_cam, C); AL(partials, grid_max); AL(tickets, 8);
-      AL(m_cam, M); AL(m_pt, M); AL(m_found, 2 * (size_t)M); AL(m_sin, M); AL(m_state, M); AL(m_v3cam, 3 * (size_t)M);
+      AL(m_cam, M); AL(m_pt, M); AL(m_found, 2 * (size_t)M); AL(m_sin, M); AL(m_state, M); AL(m_v3cam, 4 * (size_t)M);
       AL(m_derivs, 4 * (size_t)M); AL(m_eps, 2 * (size_t)M); AL(m_e2, M); AL(m_W, 18 * (size_t)M); AL(e2c, M);
       AL(S, win ? 0 : (size_t)n * n); AL(vE, win ? 0 : n); AL(upd, n); AL(scal, 8); AL(counters, 4); AL(outliers, 2 * (size_t)M);
       AL(Wp, ldlt_workspace_doubles(n));
@@ -433,7 +433,7 @@ struct ptam_bundle {
     d.p_lo = p_lo; d.p_hi = p_hi; d.add_cam_update = rank == 0 ? 1 : 0;
     d.cam_se3 = cam_se3.p; d.cam_se3_new = cam_se3_new.p; d.cam_fixed = cam_fixed.p; d.cam_row = cam_row.p;
     d.U = U.p; d.epsA = epsA.p; d.pt_pos = pt_pos.p; d.pt_pos_new = pt_pos_new.p; d.V = V.p; d.epsB = epsB.p;
-    d.Vinv = Vinv.p; d.Ve = Ve.p; d.pt_off = pt_off.p; d.pt_meas = pt_meas.p; d.m_cam = m_cam.p; d.m_pt = m_pt.p;
+    d.Vinv = Vinv.p; d.pt_off = pt_off.p; d.pt_meas = pt_meas.p; d.m_cam = m_cam.p; d.m_pt = m_pt.p;
     d.m_found = m_found.p; d.m_sin = m_sin.p; d.m_state = m_state.p; d.m_v3cam = m_v3cam.p; d.m_derivs = m_derivs.p;
     d.m_eps = m_eps.p; d.m_e2 = m_e2.p; d.m_W = m_W.p; d.e2_compact = e2c.p; d.S = S.p; d.vE = vE.p; d.upd = upd.p;
     d.scal = scal.p; d.counters = counters.p; d.outliers = outliers.p;

@@ -37,8 +37,7 @@ struct BundleDev {
   double* pt_pos_new;   // [P][3]
   double* V;            // [P][6] lower triangle packed (00,10,11,20,21,22)
   double* epsB;         // [P][3]
-  double* Vinv;         // [P][9]
-  double* Ve;           // [P][3]  V*^-1 epsB
+  double* Vinv;         // [P][12]: V*_i^-1 (9, row-major) and V*_i^-1 epsB_i (3): one 96-byte record, read as 16-byte pairs
   const int* pt_off;    // [P+1] CSR by point
   const int* pt_meas;   // [M] a point's measurements by ascending camera id (the reference's std::set<int> order)
   const int* pt_meas_ins;  // [M] the same in list (insertion) order; aliases pt_meas when the two agree
@@ -61,7 +60,7 @@ struct BundleDev {
   const double* m_found;  // [M][2]
   const double* m_sin;    // [M] dSqrtInvNoise
   int* m_state;           // [M]
-  double* m_v3cam;        // [M][3]
+  double* m_v3cam;        // [M][4] (x, y, z, pad: 32-byte records)
   double* m_derivs;       // [M][4]
   double* m_eps;          // [M][2]
   double* m_e2;           // [M]
@@ -102,6 +101,21 @@ PTAM_DEV double block_sum(double v, double* sh /*32*/) {
   return t;  // valid in warp 0
 }
 
+// 16-byte accesses to the per-measurement records (W 144 B, B 48 B, derivatives 32 B, eps 16 B per measurement: all
+// multiples of 16 from 256-byte aligned arrays): half the memory instructions of the latency-bound passes.
+template <int N>
+PTAM_DEV void ld_pairs(const double* p, double (&v)[N]) {
+  static_assert(N % 2 == 0, "pairs");
+#pragma unroll
+  for (int q = 0; q < N; q += 2) { const double2 t = *reinterpret_cast<const double2*>(p + q); v[q] = t.x; v[q + 1] = t.y; }
+}
+template <int N>
+PTAM_DEV void st_pairs(double* p, const double (&v)[N]) {
+  static_assert(N % 2 == 0, "pairs");
+#pragma unroll
+  for (int q = 0; q < N; q += 2) *reinterpret_cast<double2*>(p + q) = make_double2(v[q], v[q + 1]);
+}
+
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_ba_project(BundleDev d) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
@@ -110,16 +124,22 @@ __global__ void __launch_bounds__(256) k_ba_project(BundleDev d) {
   const int c = d.m_cam[m], p = d.m_pt[m];
   double v3[3];
   se3_apply(d.cam_se3 + 12 * c, d.pt_pos + 3 * p, v3);
-  d.m_v3cam[3 * m] = v3[0]; d.m_v3cam[3 * m + 1] = v3[1]; d.m_v3cam[3 * m + 2] = v3[2];
+  {
+    const double rec[4] = {v3[0], v3[1], v3[2], 0.0};
+    st_pairs(d.m_v3cam + 4 * (size_t)m, rec);
+  }
   if (v3[2] <= 0) { d.m_state[m] = M_BAD; return; }
   d.m_state[m] = M_ALIVE;
   const CamProj q = cam_project(d.cam, v3[0] / v3[2], v3[1] / v3[2]);
   double dv[4];
   cam_derivs(d.cam, q, dv);
-  for (int k = 0; k < 4; k++) d.m_derivs[4 * m + k] = dv[k];
+  st_pairs(d.m_derivs + 4 * (size_t)m, dv);
   const double s = d.m_sin[m];
-  const double e0 = s * (d.m_found[2 * m] - q.im[0]), e1 = s * (d.m_found[2 * m + 1] - q.im[1]);
-  d.m_eps[2 * m] = e0; d.m_eps[2 * m + 1] = e1;
+  double fd[2];
+  ld_pairs(d.m_found + 2 * (size_t)m, fd);
+  const double e0 = s * (fd[0] - q.im[0]), e1 = s * (fd[1] - q.im[1]);
+  const double ep[2] = {e0, e1};
+  st_pairs(d.m_eps + 2 * (size_t)m, ep);
   d.m_e2[m] = e0 * e0 + e1 * e1;
 }
 
@@ -367,21 +387,6 @@ PTAM_DEV void grid_sum_finish(double t, double* partials, unsigned* ticket, doub
   }
 }
 
-// 16-byte accesses to the per-measurement records (W 144 B, B 48 B, derivatives 32 B, eps 16 B per measurement: all
-// multiples of 16 from 256-byte aligned arrays): half the memory instructions of the latency-bound passes.
-template <int N>
-PTAM_DEV void ld_pairs(const double* p, double (&v)[N]) {
-  static_assert(N % 2 == 0, "pairs");
-#pragma unroll
-  for (int q = 0; q < N; q += 2) { const double2 t = *reinterpret_cast<const double2*>(p + q); v[q] = t.x; v[q + 1] = t.y; }
-}
-template <int N>
-PTAM_DEV void st_pairs(double* p, const double (&v)[N]) {
-  static_assert(N % 2 == 0, "pairs");
-#pragma unroll
-  for (int q = 0; q < N; q += 2) *reinterpret_cast<double2*>(p + q) = make_double2(v[q], v[q + 1]);
-}
-
 // One round of a segment sum: thread t has staged the NV terms of item t at sv[q * (R + 1) + t] (value-major,
 // pitch R + 1: conflict-free both ways; zeros when the item contributes nothing); thread v < NV then adds (or
 // subtracts) value v of the round's `cnt` items one after the other.
@@ -433,7 +438,9 @@ __global__ void __launch_bounds__(128) k_ba_jacobian(BundleDev d) {
   ld_pairs(d.m_derivs + 4 * (size_t)m, dv);
   const double d0 = s * (w * dv[0]), d1 = s * (w * dv[1]);
   const double d2 = s * (w * dv[2]), d3 = s * (w * dv[3]);
-  const double X = d.m_v3cam[3 * m], Y = d.m_v3cam[3 * m + 1], Z = d.m_v3cam[3 * m + 2];
+  double pc[4];
+  ld_pairs(d.m_v3cam + 4 * (size_t)m, pc);
+  const double X = pc[0], Y = pc[1], Z = pc[2];
   const double ooz = 1.0 / Z;
   double A[12];
   if (d.cam_fixed[c]) {
@@ -495,7 +502,9 @@ __global__ void __launch_bounds__(kSegThreads) k_ba_acc_cam(BundleDev d) {
           ld_pairs(d.m_derivs + 4 * (size_t)m, dv);
           const double d0 = s * (w * dv[0]), d1 = s * (w * dv[1]);
           const double d2 = s * (w * dv[2]), d3 = s * (w * dv[3]);
-          const double X = d.m_v3cam[3 * m], Y = d.m_v3cam[3 * m + 1], Z = d.m_v3cam[3 * m + 2];
+          double pc[4];
+          ld_pairs(d.m_v3cam + 4 * (size_t)m, pc);
+          const double X = pc[0], Y = pc[1], Z = pc[2];
           double A[12];
           ba_cam_jacobian(X, Y, Z, 1.0 / Z, d0, d1, d2, d3, A);
           double ep[2];
@@ -579,11 +588,13 @@ __global__ void __launch_bounds__(256) k_ba_vinv(BundleDev d) {
     Vs[0] *= (1.0 + lambda); Vs[4] *= (1.0 + lambda); Vs[8] *= (1.0 + lambda);
     ldlt_inverse<3>(Vs, inv);
   }
+  double rec[12];
 #pragma unroll
-  for (int k = 0; k < 9; k++) d.Vinv[9 * (size_t)i + k] = inv[k];
+  for (int k = 0; k < 9; k++) rec[k] = inv[k];
   const double* e = d.epsB + 3 * (size_t)i;
 #pragma unroll
-  for (int r = 0; r < 3; r++) d.Ve[3 * (size_t)i + r] = inv[3 * r] * e[0] + inv[3 * r + 1] * e[1] + inv[3 * r + 2] * e[2];
+  for (int r = 0; r < 3; r++) rec[9 + r] = inv[3 * r] * e[0] + inv[3 * r + 1] * e[1] + inv[3 * r + 2] * e[2];
+  st_pairs(d.Vinv + 12 * (size_t)i, rec);
 }
 
 // Schur complement (Bundle.cc:365-453): k_ba_zero_lower clears the lower triangle (the solve left its factors
@@ -619,8 +630,10 @@ __global__ void __launch_bounds__(kSegThreads, 1) k_ba_schur_diag(BundleDev d) {
       if (d.m_state[m] == M_ALIVE) {
         filled = true;
         const int i = d.m_pt[m];
-        const double* Vi = d.Vinv + 9 * (size_t)i;
-        const double* ve = d.Ve + 3 * (size_t)i;
+        double vv[12];
+        ld_pairs(d.Vinv + 12 * (size_t)i, vv);
+        const double* Vi = vv;
+        const double* ve = vv + 9;
         double Wr[18], WV[18];
         ld_pairs(d.m_W + 18 * (size_t)m, Wr);
 #pragma unroll
@@ -687,7 +700,8 @@ __global__ void __launch_bounds__(kOffThreads) k_ba_schur_off(BundleDev d) {
           filled = true;
           // (W_ij V*_i^-1 kept from k_ba_schur_diag instead of recomputed here was tried: a second 18-double array
           // per measurement pushes the working set of the pairs out of the L2, 219 -> 367 us at C4)
-          const double* Vi = d.Vinv + 9 * (size_t)d.m_pt[mj];
+          double Vi[10];
+          ld_pairs(d.Vinv + 12 * (size_t)d.m_pt[mj], Vi);
           double Wj[18];
           ld_pairs(d.m_W + 18 * (size_t)mj, Wj);
           const double* Wk = d.m_W + 18 * (size_t)mk;
@@ -988,7 +1002,8 @@ __global__ void __launch_bounds__(256) k_ba_point_update(BundleDev d) {
       }
     }
     const double v0 = d.epsB[3 * i] - sum[0], v1 = d.epsB[3 * i + 1] - sum[1], v2 = d.epsB[3 * i + 2] - sum[2];
-    const double* Vi = d.Vinv + 9 * i;
+    double Vi[10];
+    ld_pairs(d.Vinv + 12 * (size_t)i, Vi);
 #pragma unroll
     for (int r = 0; r < 3; r++) {
       const double u = Vi[3 * r] * v0 + Vi[3 * r + 1] * v1 + Vi[3 * r + 2] * v2;
@@ -1031,7 +1046,9 @@ __global__ void __launch_bounds__(256) k_ba_new_error(BundleDev d) {
     else {
       const CamProj q = cam_project(d.cam, v3[0] / v3[2], v3[1] / v3[2]);
       const double s = d.m_sin[m];
-      const double e0 = s * (d.m_found[2 * m] - q.im[0]), e1 = s * (d.m_found[2 * m + 1] - q.im[1]);
+      double fd[2];
+      ld_pairs(d.m_found + 2 * (size_t)m, fd);
+      const double e0 = s * (fd[0] - q.im[0]), e1 = s * (fd[1] - q.im[1]);
       e = mest_objective(e0 * e0 + e1 * e1, d.scal[1], d.est);
     }
   }
