@@ -54,11 +54,6 @@ __device__ long long g_dag_clk[32];
 PTAM_DEV int* dag_rflag(const LdltDagArgs& p, int i) { return p.flags + kDagRflag + i; }
 PTAM_DEV int* dag_uflag(const LdltDagArgs& p, int i, int j) { return p.flags + kDagRflag + p.nblk + i * p.nblk + j; }
 
-PTAM_DEV int dag_ld_acquire(const int* f) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-  return v;
-}
 PTAM_DEV int dag_ld_relaxed(const int* f) {
   int v;
   asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
