@@ -696,7 +696,8 @@ struct ptam_bundle {
   // replayed afterwards.  Anything that cannot be captured switches the handle back to plain launches.
   int run_trial_single() {
     static const bool env_off = std::getenv("PTAM_B200_NO_GRAPH") != nullptr;
-    if (env_off || graph_off || profiling) return enqueue_trial_single();
+    // (the all-per-panel schedule of the solve, PTAM_B200_LDLT_STEPS=1, is a diagnostic: it is not captured)
+    if (env_off || graph_off || profiling || !ldlt.use_dag) return enqueue_trial_single();
     if (!trial_exec || std::memcmp(&trial_key, &d, sizeof(BundleDev)) != 0) {
       if (trial_exec) { cudaGraphExecDestroy(trial_exec); trial_exec = nullptr; }
       if (d.n > 0 && ldlt.prepare(Wp.p, d.n) != cudaSuccess) { graph_off = true; cudaGetLastError(); return enqueue_trial_single(); }
