@@ -138,3 +138,12 @@ def test_hybrid_start_panel(product):
     assert ks == 26 and off[47] > off[26] > 0
     rem = 2994 - (ks + 1) * NB
     assert ((rem + TM - 1) // TM) ** 2 <= 120 < ((rem + NB + TM - 1) // TM) ** 2
+
+
+def test_schedule_entry_point_checks_its_arguments(product):
+    ks = C.c_int(0)
+    off = (C.c_int32 * 4)()
+    assert product.cdll.ptam_bundle_solve_schedule(2994, 120, C.byref(ks), off, 4) < 0      # 48 entries needed
+    assert product.cdll.ptam_bundle_solve_schedule(-2, 120, C.byref(ks), off, 4) < 0
+    assert product.cdll.ptam_bundle_solve_schedule(128, 120, None, off, 4) < 0
+    assert product.cdll.ptam_bundle_solve_schedule(128, 120, C.byref(ks), off, 4) == 2 and ks.value == 0
